@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py — cached-GET GB/s of the B200 cache-hit path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (restated)
+
+A "step" is one wave of BASELINE config C2: one 1 GiB object per GPU, 64
+concurrent GETs (50 % full, 50 % single range), cache-hit only.
+  value     payload GB/s with response buffers resident in HBM (kernel level)
+  e2e       the same wave served through the C ABI into pinned HOST windows, the
+            device->host copy inside the timed region (what the Go proxy would see)
+  roofline  achieved HBM traffic of the gather kernel (2 x payload: read + write)
+            / MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the nginx-restated CPU loop (oracle/) on this box's cores
+
+Multi-GPU: key-hash sharding — every rank owns one shard and serves
+its own object; there is no data-path collective, so scaling is weak.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WINDOW = 8 << 20          # e2e: per-connection pinned window (double buffered)
+FALLBACK_HBM_GBS = 6650.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons DURING the timed region."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_ev = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_ev.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_ev.wait(0.2)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# --------------------------------------------------------------------------- #
+# the CPU arm: the reference's cache-hit loop restated (oracle/), all host cores
+# --------------------------------------------------------------------------- #
+def cpu_serve(requests, length, seed, threads, budget_s, reps=1, shm_dir="/dev/shm"):
+    """pread(32 KiB)+copy of the C2 wave from a page-cache file; returns dict with GB/s.
+    The wave is cut into WINDOW-sized jobs; a bounded sample (prefix of the shuffled job
+    list) is timed so one call stays within ~budget_s."""
+    import ctypes as C
+
+    import numpy as np
+
+    from nezha_b200 import workloads as wl
+    from oracle import oracle as o
+
+    L = o.lib()
+    d = shm_dir if os.path.isdir(shm_dir) and os.access(shm_dir, os.W_OK) else "/tmp"
+    path = os.path.join(d, f"nezha_bench_obj_{os.getpid()}.bin")
+    data = wl.synth_bytes(length, seed)
+    with open(path, "wb") as f:
+        f.write(memoryview(data))
+    del data
+    fd = os.open(path, os.O_RDONLY)
+    try:
+        spans = []
+        for ci, rq in enumerate(requests):
+            s, l = (0, length) if rq is None else rq
+            for off in range(0, l, WINDOW):
+                spans.append((ci, s + off, min(WINDOW, l - off)))
+        rng = np.random.default_rng(1)
+        rng.shuffle(spans)
+        nconn = len(requests)
+        win = np.empty((nconn, WINDOW), dtype=np.uint8)      # one window per connection (response buffer)
+        win[:] = 0
+
+        def run(sample):
+            jobs = (o.Job * len(sample))()
+            for i, (ci, off, ln) in enumerate(sample):
+                jobs[i].fd, jobs[i].off, jobs[i].len = fd, off, ln
+                jobs[i].dst = win[ci].ctypes.data
+            t = L.nzo_serve_jobs(jobs, len(sample), threads)
+            if t < 0:
+                raise RuntimeError("cpu serve failed")
+            return t, sum(x[2] for x in sample)
+
+        # calibrate on ~1 GiB, then size the sample
+        probe = []
+        acc = 0
+        for sp in spans:
+            probe.append(sp)
+            acc += sp[2]
+            if acc >= (1 << 30):
+                break
+        t, b = run(probe)           # also warms the page cache mapping
+        t, b = run(probe)
+        rate = b / t
+        total = sum(x[2] for x in spans)
+        want = min(total, int(rate * budget_s))
+        sample, acc = [], 0
+        for sp in spans:
+            sample.append(sp)
+            acc += sp[2]
+            if acc >= want:
+                break
+        times = []
+        for _ in range(reps):
+            t, b = run(sample)
+            times.append(t)
+        return {"gbs": b / min(times) / 1e9, "times": times, "bytes": b, "total_bytes": total,
+                "sample": f"{len(sample)} of {len(spans)} 8 MiB windows of the C2 wave ({b / 2**30:.2f} of {total / 2**30:.2f} GiB), "
+                          f"pread 32 KiB + copy from a page-cache file, {threads} threads"}
+    finally:
+        os.close(fd)
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  nginx is not
+    installable here (no network, not in the image), so this is the oracle port of its
+    cache-hit loop (kind "port"), with all host threads."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    from nezha_b200 import workloads as wl
+
+    threads = os.cpu_count() or 1
+    reqs = wl.c2_requests(wl.C2_LENGTH, wl.C2_REQUESTS, seed=22)
+    nsteps = args.steps + args.warmup
+    budget = max(2.0, min(20.0, 150.0 / max(nsteps, 1)))
+    r = cpu_serve(reqs, wl.C2_LENGTH, 2, threads, budget, reps=nsteps)
+    times = r["times"][args.warmup:]
+    t_step = sum(times) / len(times)
+    gbs = r["bytes"] / t_step / 1e9     # the box has one set of host cores whatever N is: the CPU rate does not scale with GPUs
+    line = {
+        "impl": "reference", "metric": "cached-GET GB/s", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "C2: one 1 GiB object, 64 concurrent full+range GETs, cache-hit only (bounded sample)",
+                   "object_bytes": wl.C2_LENGTH, "requests": wl.C2_REQUESTS, "sharding": f"key-hash x{world}"},
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "nginx-restated CPU path (oracle port of nginx.conf's cache-hit loop: pread 32 KiB + copy), not nginx itself; "
+                "the reference's own configuration is worker_processes 1 (nginx.conf:2) — this arm uses every host thread instead",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------- #
+# the CUDA arm
+# --------------------------------------------------------------------------- #
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    import nezha_b200 as nz
+    from nezha_b200 import capi, workloads as wl
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L_obj = args.object_bytes
+    reqs = wl.c2_requests(L_obj, args.requests, seed=22 + rank)
+    spans = [((0, L_obj) if r is None else r) for r in reqs]
+    payload = sum(l for _, l in spans)
+
+    zone = nz.Zone(device=local, arena_bytes=L_obj + (64 << 20), max_objects=1024, shard_index=rank, shard_count=world)
+    # the shard's object: first bench key this shard owns (key-hash placement)
+    i = 0
+    while not zone.owns(wl.key128(wl.object_key_string("c2", i))):
+        i += 1
+    key = wl.key128(wl.object_key_string("c2", i))
+    data = wl.synth_bytes(L_obj, seed=2 + rank)
+    t0 = time.perf_counter()
+    crc = zone.put(key, data)
+    fill_s = time.perf_counter() - t0
+
+    # ---- kernel level: response buffers in HBM --------------------------------
+    offs, total = [], 0
+    for _, l in spans:
+        offs.append(total)
+        total += (l + 255) // 256 * 256
+    dbuf = zone.alloc_device(total)
+    gets = [nz.Get(key, dbuf, [] if r is None else [(r[0], r[1], 0)], 0, offs[j]) for j, r in enumerate(reqs)]
+    wave = zone.prepare(gets)
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        t = wave.submit(sptr)
+        res = t.wait()
+        t.free()
+    bad = [r.status for r in res if r.status != capi.NZ_OK]
+    if bad or sum(r.bytes for r in res) != payload:
+        raise SystemExit(f"bench.py: wave failed: {bad[:4]} bytes={sum(r.bytes for r in res)} want={payload}")
+    # spot parity of the wave inside bench (cheap): three slices against the source bytes
+    for j in (0, len(reqs) // 2, len(reqs) - 1):
+        s, l = spans[j]
+        n = min(l, 1 << 16)
+        got = dbuf.bytes(offs[j] + l - n, n)
+        if got != data[s + l - n:s + l].tobytes():
+            raise SystemExit("bench.py: served bytes differ from the source object")
+
+    sampler = ClockSampler(local)
+    launches0 = zone.stats().kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    ev0.record(stream)
+    tickets = [wave.submit(sptr) for _ in range(args.steps)]
+    ev1.record(stream)
+    ev1.synchronize()
+    barrier()
+    sampler.stop_ev.set()
+    ms = ev0.elapsed_time(ev1)
+    gather_ms = [t.gather_ms() for t in tickets]
+    for t in tickets:
+        t.wait()
+        t.free()
+    launches = zone.stats().kernel_launches - launches0
+    if world > 1:
+        tt = torch.tensor([ms], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+        pt = torch.tensor([float(payload)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(pt)
+        payload_all = float(pt.item())
+    else:
+        payload_all = float(payload)
+    ms_step = ms / args.steps
+    value = payload_all / (ms_step * 1e-3) / 1e9
+    hbm, which = peaks()
+    g_ms = sum(gather_ms) / len(gather_ms)
+    achieved = 2.0 * payload / (g_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                "traffic": None, "peak_source": which, "kernel": "k_gather",
+                "algorithmic_bytes_per_launch": 2 * payload, "kernel_ms": g_ms,
+                "kernel_share_of_step": g_ms / (ms / args.steps) if world == 1 else None}
+
+    # ---- e2e: through the C ABI into pinned host windows ----------------------
+    e2e = None
+    ttfb = None
+    if not args.no_e2e:
+        nreq = len(reqs)
+        hbuf = zone.alloc_host(nreq * 2 * WINDOW)
+        rounds = max((l + WINDOW - 1) // WINDOW for _, l in spans)
+        waves, h2d = [], 0
+        for r_i in range(rounds):
+            g = []
+            for j, (s, l) in enumerate(spans):
+                off = r_i * WINDOW
+                if off < l:
+                    g.append(nz.Get(key, hbuf, [(s + off, min(WINDOW, l - off), 0)], 0, (2 * j + (r_i & 1)) * WINDOW))
+            waves.append(zone.prepare(g))
+            h2d += len(g) * (64 + 32)
+        d2h = payload + nreq * 32 * 1
+
+        def e2e_step():
+            tk = [w.submit(sptr) for w in waves]
+            last = tk[-1].wait()
+            for t in tk:
+                t.free()
+            return last
+
+        for _ in range(1):
+            e2e_step()
+        # parity of the last window of connection 0 as landed in host memory
+        s0, l0 = spans[0]
+        last_r = (l0 - 1) // WINDOW
+        n0 = l0 - last_r * WINDOW
+        if hbuf.bytes((0 + (last_r & 1)) * WINDOW, min(n0, 4096)) != data[s0 + last_r * WINDOW:s0 + last_r * WINDOW + min(n0, 4096)].tobytes():
+            raise SystemExit("bench.py: e2e host window differs from the source object")
+        e_steps = max(1, min(args.steps, 3))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        e2e = {"value": payload_all * e_steps / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": e_steps, "window_bytes": WINDOW, "note": "kernel writes mapped pinned host windows directly (PCIe D2H in the timed region); "
+               "request descriptors are read by the plan kernel from pinned host memory"}
+        # ---- TTFB: first 256 KiB of each GET, unloaded, host clock around submit+wait ---
+        lat = []
+        for j, (s, l) in enumerate(spans):
+            w = zone.prepare([nz.Get(key, hbuf, [(s, min(l, 256 << 10), 0)], 0, 2 * j * WINDOW)])
+            for rep in range(3):
+                t0 = time.perf_counter()
+                t = w.submit(None)
+                t.wait()
+                dtt = time.perf_counter() - t0
+                t.free()
+            lat.append(dtt * 1e6)
+        lat.sort()
+        ttfb = {"p50_us": lat[len(lat) // 2], "p99_us": lat[min(len(lat) - 1, int(len(lat) * 0.99))], "first_bytes": 256 << 10,
+                "note": "host clock around nz_get_submit+nz_get_wait through Python ctypes, one GET in flight, first 256 KiB to pinned host"}
+        hbuf.free()
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) -----------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        r = cpu_serve(wl.c2_requests(L_obj, args.requests, seed=22), L_obj, 2, threads, args.cpu_budget)
+        r1 = cpu_serve(wl.c2_requests(L_obj, args.requests, seed=22), L_obj, 2, 1, min(args.cpu_budget, 6.0))
+        cpu = {"value": r["gbs"], "unit": "GB/s", "cores": threads, "kind": "port", "sample": r["sample"],
+               "one_worker_gbs": r1["gbs"], "one_worker_note": "worker_processes 1 (nginx.conf:2): the reference's actual configuration"}
+
+    if rank == 0:
+        line = {
+            "metric": "cached-GET GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "C2: one 1 GiB object per GPU, 64 concurrent GETs (32 full + 32 single-range, log-uniform 4 KiB-256 MiB), cache-hit only",
+                       "object_bytes": L_obj, "requests": len(reqs), "payload_bytes_per_gpu_step": payload,
+                       "response_buffers": "HBM", "l2": "inputs larger than L2 (1 GiB object, 33 GiB written per step); no flush needed",
+                       "sharding": f"key-hash x{world}, no data-path collective"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "ttfb": ttfb, "gpu_launches": int(launches),
+            "clocks": sampler.summary(), "fill_gbs": L_obj / fill_s / 1e9, "object_crc32c": f"{crc:08x}",
+        }
+        print(json.dumps(line), flush=True)
+    dbuf.free()
+    zone.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--object-bytes", type=int, default=1 << 30)
+    ap.add_argument("--requests", type=int, default=64)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,186 @@
+/*
+ * include/nezha_gpu.h — C ABI of libnezha_gpu.so, the B200 cache-hit data path.
+ *
+ * What this boundary replaces.  The reference (fast-ml/nezha) has NO plugin /
+ * FFI surface: it is built CGO_ENABLED=0 (/root/reference/Makefile:9,13) and its
+ * data plane is a separate stock nginx process configured by
+ * /root/reference/examples/demo/nginx.conf.  BASELINE.json:north_star therefore
+ * prescribes a NEW thin cgo shim; each entry point below cites the reference
+ * behaviour (nginx directive) whose work it takes over.  INTEGRATION.md shows the
+ * cgo stub a maintainer adds on the Go side.
+ *
+ * Rules of the ABI
+ *  - C linkage, plain pointers and sizes, no C++ or torch types, no exceptions.
+ *  - every function returns int32_t: 0 = NZ_OK, negative = NZ_E*; nz_strerror().
+ *  - every entry point may be called concurrently from any OS thread (cgo moves
+ *    goroutines between threads); the library sets the CUDA device itself.
+ *  - all I/O memory is C-owned (nz_buf); Go wraps it with unsafe.Slice and never
+ *    passes Go-heap pointers that must outlive a call.
+ *  - there is NO CPU fallback: without a CUDA device nz_init fails NZ_ECUDA.
+ */
+#ifndef NEZHA_GPU_H
+#define NEZHA_GPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NZ_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------ */
+#define NZ_OK          0
+#define NZ_EINVAL     (-1)   /* bad argument / range outside the object          */
+#define NZ_ENOMEM     (-2)   /* arena, descriptor table or host memory exhausted  */
+#define NZ_ECUDA      (-3)   /* CUDA runtime error (no device, launch failure)    */
+#define NZ_ENOTFOUND  (-4)   /* key not in the table (a MISS; per-request status) */
+#define NZ_ECORRUPT   (-5)   /* CRC-32C mismatch / malformed gzip member          */
+#define NZ_ETIMEOUT   (-6)   /* nz_get_wait timed out; ticket still valid         */
+#define NZ_EEXIST     (-7)   /* put of a key that is already live                 */
+#define NZ_EFULL      (-8)   /* hash table load limit reached                     */
+#define NZ_ENOSYS     (-9)   /* feature unavailable in this build / on this box   */
+#define NZ_ERANGE     (-10)  /* destination buffer too small                      */
+
+/* ---- object flags (stored) --------------------------------------------- */
+#define NZ_ENC_IDENTITY 0u
+#define NZ_ENC_GZIP     1u    /* stored bytes are one RFC 1952 member             */
+
+/* ---- get flags ---------------------------------------------------------- */
+#define NZ_GET_INFLATE  1u    /* serve the inflated representation (SPEC G)       */
+#define NZ_GET_VERIFY   2u    /* recompute CRC-32C of every 64 KiB chunk touched  */
+
+/* ---- buffer kinds -------------------------------------------------------- */
+#define NZ_BUF_PINNED_HOST 0  /* cudaHostAlloc, mapped: kernels write it directly */
+#define NZ_BUF_DEVICE      1  /* HBM response buffer                              */
+
+#define NZ_CRC_CHUNK 65536u   /* SPEC X2 */
+
+typedef struct nz_ctx    nz_ctx;
+typedef struct nz_buf    nz_buf;
+typedef struct nz_put    nz_put;
+typedef struct nz_ticket nz_ticket;
+
+typedef struct nz_config {
+    uint32_t struct_size;    /* sizeof(nz_config), for forward compatibility     */
+    int32_t  device;         /* CUDA ordinal                                      */
+    uint64_t arena_bytes;    /* HBM reserved for object extents                   */
+    uint64_t table_slots;    /* hash-table slots (rounded up to a power of two);  */
+                             /* replaces keys_zone=my_cache:10m (nginx.conf:38)   */
+    uint32_t max_objects;    /* extent descriptors                                */
+    uint32_t shard_index;    /* this GPU's shard (key-hash sharding)   */
+    uint32_t shard_count;    /* 0 or 1 = unsharded                                */
+    uint32_t flags;          /* reserved, 0                                       */
+} nz_config;
+
+typedef struct nz_extent {   /* result of nz_lookup for one key                   */
+    int32_t  status;         /* NZ_OK or NZ_ENOTFOUND                             */
+    uint32_t flags;          /* NZ_ENC_*                                          */
+    uint64_t stored_length;  /* bytes at rest                                     */
+    uint64_t raw_length;     /* inflated length (== stored_length for identity)   */
+    uint32_t crc32c;         /* CRC-32C of the stored bytes (x-goog-hash form)    */
+    uint32_t desc_index;     /* descriptor slot (diagnostic)                      */
+    uint64_t user_meta;      /* opaque host cookie given at put (headers blob id) */
+} nz_extent;
+
+typedef struct nz_seg {      /* one slice of the served representation            */
+    uint64_t src_off;        /* offset in the representation (stored or inflated) */
+    uint64_t len;
+    uint64_t dst_off;        /* offset in the destination buffer                  */
+} nz_seg;
+
+typedef struct nz_get_req {
+    uint8_t       key[16];   /* MD5 of "$host/$proxy_host$uri" (nginx.conf:56,38) */
+    uint32_t      flags;     /* NZ_GET_*                                          */
+    uint32_t      nseg;      /* 0 = whole object to dst_off 0                     */
+    const nz_seg* segs;      /* nseg entries (range filter output, SPEC R8/R9)    */
+    nz_buf*       dst;       /* response buffer; multipart part headers are       */
+                             /* written by the host into the gaps between segs    */
+    uint64_t      dst_base;  /* byte offset added to every dst_off                */
+} nz_get_req;
+
+typedef struct nz_get_res {
+    int32_t  status;         /* NZ_OK, NZ_ENOTFOUND, NZ_EINVAL, NZ_ECORRUPT, NZ_ERANGE */
+    uint32_t flags;          /* NZ_ENC_* of the stored object                     */
+    uint64_t bytes;          /* payload bytes written                             */
+    uint64_t length;         /* length of the representation served               */
+    uint32_t crc32c;         /* stored whole-object CRC-32C                       */
+    uint32_t reserved;
+} nz_get_res;
+
+typedef struct nz_stats {
+    uint64_t objects, arena_bytes, arena_used, table_slots, table_live;
+    uint64_t gets, get_bytes, hits, misses, puts, put_bytes, evictions, corrupt;
+    uint64_t kernel_launches;   /* kernels launched by this library since init     */
+} nz_stats;
+
+/* ---- lifecycle ----------------------------------------------------------- */
+int32_t     nz_abi_version(void);
+const char* nz_strerror(int32_t code);
+/* last CUDA error string seen by this thread's most recent failing call */
+const char* nz_last_error(void);
+int32_t nz_init(const nz_config* cfg, nz_ctx** out);
+int32_t nz_shutdown(nz_ctx* ctx);
+
+/* ---- C-owned I/O memory -------------------------------------------------- */
+int32_t  nz_buf_alloc(nz_ctx* ctx, uint64_t bytes, int32_t kind, nz_buf** out);
+/* wrap device memory owned by the caller (e.g. a framework tensor); not freed */
+int32_t  nz_buf_wrap_device(nz_ctx* ctx, void* devptr, uint64_t bytes, nz_buf** out);
+void*    nz_buf_ptr(nz_buf* b);       /* host address (NULL for device buffers)   */
+void*    nz_buf_devptr(nz_buf* b);    /* device address (mapped alias for pinned) */
+uint64_t nz_buf_size(nz_buf* b);
+int32_t  nz_buf_free(nz_buf* b);
+/* synchronous copies between a buffer and host memory (tools/tests; device buffers too) */
+int32_t  nz_buf_read(nz_buf* b, uint64_t off, void* host_dst, uint64_t n);
+int32_t  nz_buf_write(nz_buf* b, uint64_t off, const void* host_src, uint64_t n);
+
+/* ---- fill side: replaces nginx temp-file -> rename (SPEC H) - */
+int32_t nz_put_begin(nz_ctx* ctx, const uint8_t key[16], uint64_t stored_len,
+                     uint64_t raw_len, uint32_t enc_flags, uint64_t user_meta,
+                     nz_put** out);
+/* copy len bytes from host memory (pinned nz_buf memory goes async) */
+int32_t nz_put_write(nz_put* p, const void* src_host, uint64_t dst_off, uint64_t len);
+/* copy from device memory (synthetic fills, peer fills) */
+int32_t nz_put_write_device(nz_put* p, const void* src_dev, uint64_t dst_off, uint64_t len);
+/* read from a file: cuFile/GDS when available, else pread into pinned bounce buffers */
+int32_t nz_put_file(nz_put* p, int fd, uint64_t file_off, uint64_t dst_off, uint64_t len);
+/* computes the 64 KiB chunk CRC-32C table and the whole-object CRC on the device;
+ * if has_expected and it differs -> NZ_ECORRUPT and nothing is published; else the
+ * slot is published (visible to GETs).  The handle is consumed either way. */
+int32_t nz_put_commit(nz_put* p, uint32_t expected_crc32c, int32_t has_expected,
+                      uint32_t* out_crc32c);
+int32_t nz_put_abort(nz_put* p);
+int32_t nz_evict(nz_ctx* ctx, const uint8_t key[16]);
+
+/* ---- hit side ------------------------------------------------------------ */
+/* K1 probe: replaces the shm rbtree lookup of keys_zone (nginx.conf:38) */
+int32_t nz_lookup(nz_ctx* ctx, const uint8_t (*keys)[16], uint32_t n, nz_extent* out);
+
+/* One wave of GETs: probe + plan + range gather (+inflate, +verify) on the device.
+ * Replaces the cache-file read loop + range filter.  `cuda_stream`
+ * is a cudaStream_t to launch on, or NULL for the library's own stream pool.
+ * Returns immediately; results via the ticket. */
+int32_t nz_get_submit(nz_ctx* ctx, const nz_get_req* reqs, uint32_t n,
+                      void* cuda_stream, nz_ticket** out);
+/* timeout_us < 0 waits forever; res (n entries) may be NULL */
+int32_t nz_get_wait(nz_ticket* t, int64_t timeout_us, nz_get_res* res);
+int32_t nz_get_poll(nz_ticket* t);                 /* NZ_OK done, NZ_ETIMEOUT not yet */
+int32_t nz_ticket_elapsed_ms(nz_ticket* t, float* ms);  /* device time of the wave */
+int32_t nz_ticket_gather_ms(nz_ticket* t, float* ms);   /* device time of its gather kernel (K2) alone */
+int32_t nz_ticket_free(nz_ticket* t);
+
+int32_t nz_get_stats(nz_ctx* ctx, nz_stats* out);
+
+/* ---- standalone kernels exposed for parity tests and profiling ------------ */
+/* CRC-32C of n device bytes (K3); chunk table (may be NULL) gets ceil(n/64Ki) u32 */
+int32_t nz_crc32c_device(nz_ctx* ctx, const void* dev, uint64_t n, uint32_t* out_crc,
+                         uint32_t* out_chunks_host);
+/* fault injection for tests: XOR one stored byte of a live object in HBM */
+int32_t nz_debug_poke(nz_ctx* ctx, const uint8_t key[16], uint64_t off, uint8_t xor_mask);
+/* shard that owns a key: u64le(key[0:8]) mod shard_count */
+uint32_t nz_shard_of(const uint8_t key[16], uint32_t shard_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEZHA_GPU_H */

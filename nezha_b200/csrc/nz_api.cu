@@ -1,0 +1,803 @@
+// nezha_b200/csrc/nz_api.cu — the C ABI of include/nezha_gpu.h.
+//
+// Host side of the cache zone: arena allocator, descriptor slots, shadow index,
+// stream pool and GET waves.  All data-path work is CUDA (nz_kernels.cu,
+// nz_inflate.cu); there is deliberately no CPU fallback — if CUDA is missing every
+// entry point fails with NZ_ECUDA.
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <stdio.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <thread>
+
+#include "nz_internal.h"
+
+static thread_local char tl_err[512] = "";
+
+static int32_t cuda_fail(cudaError_t e, const char* what) {
+    snprintf(tl_err, sizeof tl_err, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return NZ_ECUDA;
+}
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t _e = (call);                              \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call);   \
+    } while (0)
+
+static inline uint64_t rd64(const uint8_t* p) {
+    uint64_t v;
+    memcpy(&v, p, 8);
+    return v;   // little-endian host
+}
+static inline uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+extern "C" {
+
+int32_t nz_abi_version(void) { return NZ_ABI_VERSION; }
+
+const char* nz_strerror(int32_t code) {
+    switch (code) {
+    case NZ_OK: return "ok";
+    case NZ_EINVAL: return "invalid argument or range outside the object";
+    case NZ_ENOMEM: return "out of arena / descriptor / host memory";
+    case NZ_ECUDA: return "CUDA error (no device or launch failure)";
+    case NZ_ENOTFOUND: return "key not found (miss)";
+    case NZ_ECORRUPT: return "CRC-32C mismatch or malformed gzip member";
+    case NZ_ETIMEOUT: return "timed out";
+    case NZ_EEXIST: return "key already present";
+    case NZ_EFULL: return "hash table full";
+    case NZ_ENOSYS: return "not available";
+    case NZ_ERANGE: return "destination buffer too small";
+    default: return "unknown error";
+    }
+}
+const char* nz_last_error(void) { return tl_err; }
+
+uint32_t nz_shard_of(const uint8_t key[16], uint32_t shard_count) {
+    if (shard_count <= 1) return 0;
+    return (uint32_t)(rd64(key) % shard_count);
+}
+
+// ---------------------------------------------------------------------------
+// lifecycle
+// ---------------------------------------------------------------------------
+int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
+    if (!cfg || !out || cfg->struct_size < sizeof(nz_config)) return NZ_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    if (ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+        snprintf(tl_err, sizeof tl_err, "no CUDA device %d (count %d)", cfg->device, ndev);
+        return NZ_ECUDA;
+    }
+    CK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    nz_ctx* c = new (std::nothrow) nz_ctx();
+    if (!c) return NZ_ENOMEM;
+    c->cfg = *cfg;
+    c->device = cfg->device;
+    c->sm_count = prop.multiProcessorCount;
+    if (c->cfg.shard_count == 0) c->cfg.shard_count = 1;
+    if (c->cfg.shard_index >= c->cfg.shard_count) { delete c; return NZ_EINVAL; }
+    if (c->cfg.max_objects == 0) c->cfg.max_objects = 1u << 16;
+    uint64_t slots = c->cfg.table_slots ? c->cfg.table_slots : 4ull * c->cfg.max_objects;
+    if (slots < 2ull * c->cfg.max_objects) slots = 2ull * c->cfg.max_objects;
+    uint64_t lines = 1;
+    while (lines * 4 < slots) lines <<= 1;
+    c->n_lines = lines;
+    c->arena_bytes = round_up(c->cfg.arena_bytes ? c->cfg.arena_bytes : (1ull << 30), 4096);
+
+#define CKI(call)                                                         \
+    do {                                                                  \
+        cudaError_t _e = (call);                                          \
+        if (_e != cudaSuccess) { int32_t rc = cuda_fail(_e, #call); nz_shutdown(c); return rc; } \
+    } while (0)
+    CKI(cudaMalloc(&c->arena, c->arena_bytes + 4096));
+    CKI(cudaMalloc(&c->table, lines * 4 * sizeof(NzSlot)));
+    CKI(cudaMemset(c->table, 0, lines * 4 * sizeof(NzSlot)));
+    CKI(cudaMalloc(&c->descs, (size_t)c->cfg.max_objects * sizeof(NzDesc)));
+    CKI(cudaMemset(c->descs, 0, (size_t)c->cfg.max_objects * sizeof(NzDesc)));
+    CKI(cudaMalloc(&c->crc_tables, 16 * 256 * sizeof(uint32_t)));
+    CKI(nz_upload_constants(c->crc_tables));
+    for (int i = 0; i < 8; ++i) {
+        cudaStream_t s;
+        CKI(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        c->streams.push_back(s);
+    }
+    CKI(cudaStreamCreateWithFlags(&c->put_stream, cudaStreamNonBlocking));
+#undef CKI
+    c->free_by_off[0] = c->arena_bytes;
+    c->free_desc.reserve(c->cfg.max_objects);
+    for (uint32_t i = c->cfg.max_objects; i-- > 0;) c->free_desc.push_back(i);
+    c->gather_grid = c->sm_count * nz_gather_blocks_per_sm();
+    c->inflate_grid = c->sm_count * nz_inflate_blocks_per_sm();
+    *out = c;
+    return NZ_OK;
+}
+
+static void ticket_destroy(nz_ticket* t) {
+    if (!t) return;
+    for (void* p : t->scratch) cudaFree(p);
+    if (t->pin) cudaFreeHost(t->pin);
+    if (t->dev) cudaFree(t->dev);
+    if (t->ev_start) cudaEventDestroy(t->ev_start);
+    if (t->ev_done) cudaEventDestroy(t->ev_done);
+    if (t->ev_g0) cudaEventDestroy(t->ev_g0);
+    if (t->ev_g1) cudaEventDestroy(t->ev_g1);
+    delete t;
+}
+
+int32_t nz_shutdown(nz_ctx* c) {
+    if (!c) return NZ_EINVAL;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (nz_ticket* t : c->ticket_pool) ticket_destroy(t);
+    for (cudaStream_t s : c->streams) cudaStreamDestroy(s);
+    if (c->put_stream) cudaStreamDestroy(c->put_stream);
+    for (int i = 0; i < 2; ++i) {
+        if (c->bounce[i]) cudaFreeHost(c->bounce[i]);
+        if (c->bounce_ev[i]) cudaEventDestroy(c->bounce_ev[i]);
+    }
+    if (c->arena) cudaFree(c->arena);
+    if (c->table) cudaFree(c->table);
+    if (c->descs) cudaFree(c->descs);
+    if (c->crc_tables) cudaFree(c->crc_tables);
+    delete c;
+    return NZ_OK;
+}
+
+// ---------------------------------------------------------------------------
+// buffers
+// ---------------------------------------------------------------------------
+int32_t nz_buf_alloc(nz_ctx* c, uint64_t bytes, int32_t kind, nz_buf** out) {
+    if (!c || !out || bytes == 0) return NZ_EINVAL;
+    CK(cudaSetDevice(c->device));
+    nz_buf* b = new (std::nothrow) nz_buf();
+    if (!b) return NZ_ENOMEM;
+    b->ctx = c; b->size = bytes; b->kind = kind; b->owned = true; b->host = nullptr; b->dev = nullptr;
+    cudaError_t e;
+    if (kind == NZ_BUF_PINNED_HOST) {
+        e = cudaHostAlloc(&b->host, bytes + 256, cudaHostAllocMapped | cudaHostAllocPortable);
+        if (e == cudaSuccess) e = cudaHostGetDevicePointer(&b->dev, b->host, 0);
+    } else if (kind == NZ_BUF_DEVICE) {
+        e = cudaMalloc(&b->dev, bytes + 256);
+    } else {
+        delete b;
+        return NZ_EINVAL;
+    }
+    if (e != cudaSuccess) {
+        if (b->host) cudaFreeHost(b->host);
+        delete b;
+        cudaGetLastError();
+        cuda_fail(e, "nz_buf_alloc");
+        return e == cudaErrorMemoryAllocation ? NZ_ENOMEM : NZ_ECUDA;
+    }
+    *out = b;
+    return NZ_OK;
+}
+int32_t nz_buf_wrap_device(nz_ctx* c, void* devptr, uint64_t bytes, nz_buf** out) {
+    if (!c || !out || !devptr || bytes == 0) return NZ_EINVAL;
+    nz_buf* b = new (std::nothrow) nz_buf();
+    if (!b) return NZ_ENOMEM;
+    b->ctx = c; b->size = bytes; b->kind = NZ_BUF_DEVICE; b->owned = false; b->host = nullptr; b->dev = devptr;
+    *out = b;
+    return NZ_OK;
+}
+void* nz_buf_ptr(nz_buf* b) { return b ? b->host : nullptr; }
+void* nz_buf_devptr(nz_buf* b) { return b ? b->dev : nullptr; }
+uint64_t nz_buf_size(nz_buf* b) { return b ? b->size : 0; }
+int32_t nz_buf_free(nz_buf* b) {
+    if (!b) return NZ_EINVAL;
+    if (b->owned) {
+        cudaSetDevice(b->ctx->device);
+        if (b->kind == NZ_BUF_PINNED_HOST) cudaFreeHost(b->host);
+        else cudaFree(b->dev);
+    }
+    delete b;
+    return NZ_OK;
+}
+
+int32_t nz_buf_read(nz_buf* b, uint64_t off, void* host_dst, uint64_t n) {
+    if (!b || (!host_dst && n) || off > b->size || n > b->size - off) return NZ_EINVAL;
+    if (!n) return NZ_OK;
+    CK(cudaSetDevice(b->ctx->device));
+    if (b->host) { memcpy(host_dst, (char*)b->host + off, n); return NZ_OK; }
+    CK(cudaMemcpy(host_dst, (char*)b->dev + off, n, cudaMemcpyDeviceToHost));
+    return NZ_OK;
+}
+int32_t nz_buf_write(nz_buf* b, uint64_t off, const void* host_src, uint64_t n) {
+    if (!b || (!host_src && n) || off > b->size || n > b->size - off) return NZ_EINVAL;
+    if (!n) return NZ_OK;
+    CK(cudaSetDevice(b->ctx->device));
+    if (b->host) { memcpy((char*)b->host + off, host_src, n); return NZ_OK; }
+    CK(cudaMemcpy((char*)b->dev + off, host_src, n, cudaMemcpyHostToDevice));
+    return NZ_OK;
+}
+
+// ---------------------------------------------------------------------------
+// arena (first fit, coalescing free list).  Extents are 4 KiB aligned so the
+// same offsets work for cuFile/GDS reads from the PV.
+// ---------------------------------------------------------------------------
+static bool arena_alloc(nz_ctx* c, uint64_t len, uint64_t* off) {
+    len = round_up(len ? len : 1, 4096);
+    for (auto it = c->free_by_off.begin(); it != c->free_by_off.end(); ++it) {
+        if (it->second >= len) {
+            *off = it->first;
+            uint64_t rest = it->second - len, o = it->first;
+            c->free_by_off.erase(it);
+            if (rest) c->free_by_off[o + len] = rest;
+            return true;
+        }
+    }
+    return false;
+}
+static void arena_free(nz_ctx* c, uint64_t off, uint64_t len) {
+    len = round_up(len ? len : 1, 4096);
+    auto it = c->free_by_off.emplace(off, len).first;
+    auto nx = std::next(it);
+    if (nx != c->free_by_off.end() && it->first + it->second == nx->first) {
+        it->second += nx->second;
+        c->free_by_off.erase(nx);
+    }
+    if (it != c->free_by_off.begin()) {
+        auto pv = std::prev(it);
+        if (pv->first + pv->second == it->first) {
+            pv->second += it->second;
+            c->free_by_off.erase(it);
+        }
+    }
+}
+
+// small pinned mailboxes for kernel -> host scalars (status words, CRCs)
+struct Mailbox { uint32_t crc; int32_t status; uint32_t pad[2]; };
+static Mailbox* mailbox_get() {
+    Mailbox* m = nullptr;
+    if (cudaHostAlloc((void**)&m, sizeof(Mailbox), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    m->crc = 0; m->status = NZ_ECUDA;
+    return m;
+}
+struct MailboxPool {
+    std::mutex mu;
+    std::vector<Mailbox*> free_;
+    Mailbox* get() {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            if (!free_.empty()) { Mailbox* m = free_.back(); free_.pop_back(); m->crc = 0; m->status = NZ_ECUDA; return m; }
+        }
+        return mailbox_get();
+    }
+    void put(Mailbox* m) { std::lock_guard<std::mutex> g(mu); free_.push_back(m); }
+};
+static MailboxPool g_mail;
+
+// ---------------------------------------------------------------------------
+// fill side
+// ---------------------------------------------------------------------------
+int32_t nz_put_begin(nz_ctx* c, const uint8_t key[16], uint64_t stored_len, uint64_t raw_len, uint32_t enc_flags,
+                     uint64_t user_meta, nz_put** out) {
+    if (!c || !key || !out) return NZ_EINVAL;
+    if (enc_flags & ~NZ_ENC_GZIP) return NZ_EINVAL;
+    if (!(enc_flags & NZ_ENC_GZIP)) raw_len = stored_len;
+    if (nz_shard_of(key, c->cfg.shard_count) != c->cfg.shard_index) return NZ_EINVAL;
+    const uint64_t k0 = rd64(key), k1 = rd64(key + 8);
+    const uint32_t n_chunks = (uint32_t)((stored_len + NZ_CRC_CHUNK - 1) / NZ_CRC_CHUNK);
+    const uint64_t data_len = round_up(stored_len ? stored_len : 1, 4096);
+    const uint64_t tab_len = round_up((uint64_t)(n_chunks ? n_chunks : 1) * 4, 256);
+    nz_put* p = new (std::nothrow) nz_put();
+    if (!p) return NZ_ENOMEM;
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        if (c->shadow.count({k0, k1})) { delete p; return NZ_EEXIST; }
+        if (c->shadow.size() * 2 >= c->n_lines * 4) { delete p; return NZ_EFULL; }
+        if (c->free_desc.empty()) { delete p; return NZ_ENOMEM; }
+        uint64_t off;
+        if (!arena_alloc(c, data_len + tab_len, &off)) { delete p; return NZ_ENOMEM; }
+        p->arena_off = off;
+        p->arena_len = data_len + tab_len;
+        // reserve the key so a concurrent put of the same key fails EEXIST
+        NzHostObj ho;
+        ho.desc = 0xFFFFFFFFu; ho.arena_off = off; ho.arena_len = p->arena_len;
+        ho.stored_len = stored_len; ho.raw_len = raw_len; ho.flags = enc_flags;
+        c->shadow[{k0, k1}] = ho;
+    }
+    p->ctx = c; p->k0 = k0; p->k1 = k1; p->stored_len = stored_len; p->raw_len = raw_len; p->user_meta = user_meta;
+    p->flags = enc_flags; p->crc_tab_off = p->arena_off + data_len; p->n_chunks = n_chunks;
+    p->stream = c->streams[c->rr.fetch_add(1) % c->streams.size()];
+    *out = p;
+    return NZ_OK;
+}
+
+int32_t nz_put_write(nz_put* p, const void* src_host, uint64_t dst_off, uint64_t len) {
+    if (!p || (!src_host && len) || dst_off > p->stored_len || len > p->stored_len - dst_off) return NZ_EINVAL;
+    if (!len) return NZ_OK;
+    CK(cudaSetDevice(p->ctx->device));
+    CK(cudaMemcpyAsync(p->ctx->arena + p->arena_off + dst_off, src_host, len, cudaMemcpyHostToDevice, p->stream));
+    return NZ_OK;
+}
+int32_t nz_put_write_device(nz_put* p, const void* src_dev, uint64_t dst_off, uint64_t len) {
+    if (!p || (!src_dev && len) || dst_off > p->stored_len || len > p->stored_len - dst_off) return NZ_EINVAL;
+    if (!len) return NZ_OK;
+    CK(cudaSetDevice(p->ctx->device));
+    CK(cudaMemcpyAsync(p->ctx->arena + p->arena_off + dst_off, src_dev, len, cudaMemcpyDeviceToDevice, p->stream));
+    return NZ_OK;
+}
+
+int32_t nz_put_file(nz_put* p, int fd, uint64_t file_off, uint64_t dst_off, uint64_t len) {
+    if (!p || fd < 0 || dst_off > p->stored_len || len > p->stored_len - dst_off) return NZ_EINVAL;
+    nz_ctx* c = p->ctx;
+    CK(cudaSetDevice(c->device));
+    std::lock_guard<std::mutex> g(c->put_mu);   // bounce buffers are shared
+    if (!c->bounce[0]) {
+        c->bounce_bytes = 16u << 20;
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaHostAlloc(&c->bounce[i], c->bounce_bytes, cudaHostAllocPortable));
+            CK(cudaEventCreateWithFlags(&c->bounce_ev[i], cudaEventDisableTiming));
+        }
+    }
+    uint64_t done = 0;
+    int which = 0;
+    while (done < len) {
+        const size_t want = (size_t)std::min<uint64_t>(c->bounce_bytes, len - done);
+        CK(cudaEventSynchronize(c->bounce_ev[which]));   // previous H2D out of this buffer finished
+        size_t got = 0;
+        while (got < want) {
+            ssize_t r = pread(fd, (char*)c->bounce[which] + got, want - got, (off_t)(file_off + done + got));
+            if (r < 0) { if (errno == EINTR) continue; snprintf(tl_err, sizeof tl_err, "pread: %s", strerror(errno)); return NZ_EINVAL; }
+            if (r == 0) { snprintf(tl_err, sizeof tl_err, "pread: short file"); return NZ_EINVAL; }
+            got += (size_t)r;
+        }
+        CK(cudaMemcpyAsync(c->arena + p->arena_off + dst_off + done, c->bounce[which], want, cudaMemcpyHostToDevice, p->stream));
+        CK(cudaEventRecord(c->bounce_ev[which], p->stream));
+        done += want;
+        which ^= 1;
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    return NZ_OK;
+}
+
+static void put_release(nz_put* p, bool drop_reservation) {
+    nz_ctx* c = p->ctx;
+    if (drop_reservation) {
+        std::lock_guard<std::mutex> g(c->mu);
+        c->shadow.erase({p->k0, p->k1});
+        arena_free(c, p->arena_off, p->arena_len);
+    }
+    delete p;
+}
+
+int32_t nz_put_abort(nz_put* p) {
+    if (!p) return NZ_EINVAL;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->stream);
+    put_release(p, true);
+    return NZ_OK;
+}
+
+int32_t nz_put_commit(nz_put* p, uint32_t expected, int32_t has_expected, uint32_t* out_crc) {
+    if (!p) return NZ_EINVAL;
+    nz_ctx* c = p->ctx;
+    int32_t rc = NZ_OK;
+    Mailbox* mb = nullptr;
+    uint32_t desc_idx = 0xFFFFFFFFu;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "cudaSetDevice"); goto fail; }
+    mb = g_mail.get();
+    if (!mb) { rc = NZ_ENOMEM; goto fail; }
+    {
+        void* mb_dev = nullptr;
+        e = cudaHostGetDevicePointer(&mb_dev, mb, 0);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaHostGetDevicePointer"); goto fail; }
+        uint32_t* tab = reinterpret_cast<uint32_t*>(c->arena + p->crc_tab_off);
+        e = nz_launch_crc_chunks(c->arena + p->arena_off, p->stored_len, tab, &((Mailbox*)mb_dev)->crc, c->crc_tables,
+                                 c->sm_count, p->stream);
+        c->launches += 2;
+        if (e != cudaSuccess) { rc = cuda_fail(e, "crc kernels"); goto fail; }
+        e = cudaStreamSynchronize(p->stream);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "crc sync"); goto fail; }
+        const uint32_t crc = mb->crc;
+        if (out_crc) *out_crc = crc;
+        if (has_expected && crc != expected) {
+            c->corrupt++;
+            rc = NZ_ECORRUPT;
+            goto fail;
+        }
+        {
+            std::lock_guard<std::mutex> g(c->mu);
+            if (c->free_desc.empty()) { rc = NZ_ENOMEM; goto fail; }
+            desc_idx = c->free_desc.back();
+            c->free_desc.pop_back();
+        }
+        NzDesc d;
+        memset(&d, 0, sizeof d);
+        d.arena_off = p->arena_off; d.stored_len = p->stored_len; d.raw_len = p->raw_len; d.user_meta = p->user_meta;
+        d.crc_tab_off = p->crc_tab_off; d.flags = p->flags; d.crc32c = crc; d.n_chunks = p->n_chunks;
+        uint64_t gen;
+        { std::lock_guard<std::mutex> g(c->mu); gen = c->gen++; }
+        d.gen = (uint32_t)gen;
+        e = cudaMemcpyAsync(c->descs + desc_idx, &d, sizeof d, cudaMemcpyHostToDevice, p->stream);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "desc upload"); goto fail; }
+        e = nz_launch_insert(c->table, c->n_lines - 1, p->k0, p->k1, desc_idx, gen, &((Mailbox*)mb_dev)->status, p->stream);
+        c->launches += 1;
+        if (e != cudaSuccess) { rc = cuda_fail(e, "insert"); goto fail; }
+        e = cudaStreamSynchronize(p->stream);
+        if (e != cudaSuccess) { rc = cuda_fail(e, "insert sync"); goto fail; }
+        rc = mb->status;
+        if (rc != NZ_OK) goto fail;
+        {
+            std::lock_guard<std::mutex> g(c->mu);
+            c->shadow[{p->k0, p->k1}].desc = desc_idx;
+        }
+        c->puts++;
+        c->put_bytes += p->stored_len;
+        g_mail.put(mb);
+        put_release(p, false);
+        return NZ_OK;
+    }
+fail:
+    if (desc_idx != 0xFFFFFFFFu) { std::lock_guard<std::mutex> g(c->mu); c->free_desc.push_back(desc_idx); }
+    if (mb) g_mail.put(mb);
+    cudaStreamSynchronize(p->stream);
+    put_release(p, true);
+    return rc;
+}
+
+int32_t nz_evict(nz_ctx* c, const uint8_t key[16]) {
+    if (!c || !key) return NZ_EINVAL;
+    CK(cudaSetDevice(c->device));
+    const uint64_t k0 = rd64(key), k1 = rd64(key + 8);
+    NzHostObj ho;
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        auto it = c->shadow.find({k0, k1});
+        if (it == c->shadow.end() || it->second.desc == 0xFFFFFFFFu) return NZ_ENOTFOUND;
+        ho = it->second;
+        c->shadow.erase(it);
+    }
+    Mailbox* mb = g_mail.get();
+    if (!mb) return NZ_ENOMEM;
+    void* mb_dev = nullptr;
+    CK(cudaHostGetDevicePointer(&mb_dev, mb, 0));
+    cudaError_t e = nz_launch_erase(c->table, c->n_lines - 1, k0, k1, &((Mailbox*)mb_dev)->status, c->put_stream);
+    c->launches += 1;
+    if (e != cudaSuccess) { g_mail.put(mb); return cuda_fail(e, "erase"); }
+    // in-flight GETs may still be reading the extent: drain the device before the bytes are reused
+    e = cudaDeviceSynchronize();
+    int32_t rc = mb->status;
+    g_mail.put(mb);
+    if (e != cudaSuccess) return cuda_fail(e, "erase sync");
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        arena_free(c, ho.arena_off, ho.arena_len);
+        c->free_desc.push_back(ho.desc);
+    }
+    c->evictions++;
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// K1 lookup
+// ---------------------------------------------------------------------------
+int32_t nz_lookup(nz_ctx* c, const uint8_t (*keys)[16], uint32_t n, nz_extent* out) {
+    if (!c || (n && (!keys || !out))) return NZ_EINVAL;
+    if (!n) return NZ_OK;
+    CK(cudaSetDevice(c->device));
+    const size_t kb = (size_t)n * 16, ob = (size_t)n * sizeof(nz_extent);
+    void* pin = nullptr;
+    void* pin_dev = nullptr;
+    CK(cudaHostAlloc(&pin, round_up(kb, 256) + ob, cudaHostAllocMapped | cudaHostAllocPortable));
+    cudaError_t e = cudaHostGetDevicePointer(&pin_dev, pin, 0);
+    if (e != cudaSuccess) { cudaFreeHost(pin); return cuda_fail(e, "cudaHostGetDevicePointer"); }
+    memcpy(pin, keys, kb);
+    cudaStream_t s = c->streams[c->rr.fetch_add(1) % c->streams.size()];
+    nz_extent* dout = reinterpret_cast<nz_extent*>((char*)pin_dev + round_up(kb, 256));
+    e = nz_launch_lookup(c->table, c->n_lines - 1, c->descs, (const uint64_t*)pin_dev, n, dout, s);
+    c->launches += 1;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { cudaFreeHost(pin); return cuda_fail(e, "lookup"); }
+    memcpy(out, (char*)pin + round_up(kb, 256), ob);
+    cudaFreeHost(pin);
+    return NZ_OK;
+}
+
+// ---------------------------------------------------------------------------
+// GET waves
+// ---------------------------------------------------------------------------
+static nz_ticket* ticket_acquire(nz_ctx* c, size_t pin_need, size_t dev_need) {
+    nz_ticket* t = nullptr;
+    {
+        std::lock_guard<std::mutex> g(c->tmu);
+        for (size_t i = 0; i < c->ticket_pool.size(); ++i) {
+            if (c->ticket_pool[i]->pin_cap >= pin_need && c->ticket_pool[i]->dev_cap >= dev_need) {
+                t = c->ticket_pool[i];
+                c->ticket_pool.erase(c->ticket_pool.begin() + i);
+                break;
+            }
+        }
+        if (!t && !c->ticket_pool.empty()) { t = c->ticket_pool.back(); c->ticket_pool.pop_back(); }
+    }
+    if (!t) {
+        t = new (std::nothrow) nz_ticket();
+        if (!t) return nullptr;
+        t->ctx = c;
+        if (cudaEventCreate(&t->ev_start) != cudaSuccess || cudaEventCreate(&t->ev_done) != cudaSuccess ||
+            cudaEventCreate(&t->ev_g0) != cudaSuccess || cudaEventCreate(&t->ev_g1) != cudaSuccess) { ticket_destroy(t); return nullptr; }
+    }
+    if (t->pin_cap < pin_need) {
+        if (t->pin) cudaFreeHost(t->pin);
+        t->pin = nullptr; t->pin_cap = 0;
+        size_t cap = std::max<size_t>(round_up(pin_need, 4096), 64 << 10);
+        if (cudaHostAlloc(&t->pin, cap, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+            cudaHostGetDevicePointer(&t->pin_dev, t->pin, 0) != cudaSuccess) { ticket_destroy(t); return nullptr; }
+        t->pin_cap = cap;
+    }
+    if (t->dev_cap < dev_need) {
+        if (t->dev) cudaFree(t->dev);
+        t->dev = nullptr; t->dev_cap = 0;
+        size_t cap = std::max<size_t>(round_up(dev_need, 4096), 64 << 10);
+        if (cudaMalloc(&t->dev, cap) != cudaSuccess) { ticket_destroy(t); return nullptr; }
+        t->dev_cap = cap;
+    }
+    return t;
+}
+
+int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_stream, nz_ticket** out) {
+    if (!c || !reqs || !n || !out) return NZ_EINVAL;
+    CK(cudaSetDevice(c->device));
+    // ---- host-side sizing ----
+    uint64_t nseg = 0;
+    bool any_inflate = false, any_verify = false;
+    for (uint32_t i = 0; i < n; ++i) {
+        const nz_get_req& r = reqs[i];
+        if (!r.dst || (r.nseg && !r.segs) || r.dst_base > r.dst->size) return NZ_EINVAL;
+        nseg += r.nseg ? r.nseg : 1;
+        any_inflate |= (r.flags & NZ_GET_INFLATE) != 0;
+        any_verify |= (r.flags & NZ_GET_VERIFY) != 0;
+    }
+    if (nseg > 0x7fffffffull) return NZ_EINVAL;
+    // verify work bound + inflate scratch sizing come from the host shadow (metadata only; the
+    // data path itself resolves keys on the device)
+    uint64_t ver_cap = 0;
+    std::vector<uint64_t> scratch_need(any_inflate ? n : 0, 0);
+    if (any_inflate || any_verify) {
+        std::lock_guard<std::mutex> g(c->mu);
+        for (uint32_t i = 0; i < n; ++i) {
+            const nz_get_req& r = reqs[i];
+            if (!(r.flags & (NZ_GET_INFLATE | NZ_GET_VERIFY))) continue;
+            auto it = c->shadow.find({rd64(r.key), rd64(r.key + 8)});
+            if (it == c->shadow.end() || it->second.desc == 0xFFFFFFFFu) continue;
+            const NzHostObj& ho = it->second;
+            const bool inflate = (r.flags & NZ_GET_INFLATE) && (ho.flags & NZ_ENC_GZIP);
+            if (r.flags & NZ_GET_VERIFY) {
+                const uint64_t all = (ho.stored_len + NZ_CRC_CHUNK - 1) / NZ_CRC_CHUNK;
+                if (inflate || r.nseg == 0) ver_cap += all;
+                else for (uint32_t k = 0; k < r.nseg; ++k) ver_cap += std::min<uint64_t>(all, r.segs[k].len / NZ_CRC_CHUNK + 2);
+            }
+            if (inflate && r.nseg != 0) scratch_need[i] = ho.raw_len;
+        }
+    }
+    if (ver_cap > 0xfffffff0ull) return NZ_EINVAL;
+
+    const size_t pin_reqs = round_up((size_t)n * sizeof(NzDevReq), 256);
+    const size_t pin_segs = round_up((size_t)nseg * sizeof(NzDevSeg), 256);
+    const size_t pin_res = round_up((size_t)n * sizeof(NzDevRes), 256);
+    const size_t dev_work = round_up((size_t)nseg * sizeof(NzSegWork), 256);
+    const size_t dev_tiles = round_up((size_t)(nseg + 1) * 8, 256);
+    const size_t dev_ver = round_up((size_t)ver_cap * sizeof(NzVerWork), 256);
+    const size_t dev_cnt = 256;
+    const size_t dev_infl = (size_t)n * sizeof(NzInflWork);      // followed directly by rq_src, rq_len
+    const size_t dev_rq = (size_t)n * 16;
+    nz_ticket* t = ticket_acquire(c, pin_reqs + pin_segs + pin_res, dev_work + dev_tiles + dev_ver + dev_cnt + round_up(dev_infl + dev_rq, 256));
+    if (!t) { cudaGetLastError(); snprintf(tl_err, sizeof tl_err, "ticket allocation failed"); return NZ_ENOMEM; }
+    t->n = n; t->nseg = (uint32_t)nseg;
+
+    NzDevReq* hreq = reinterpret_cast<NzDevReq*>(t->pin);
+    NzDevSeg* hseg = reinterpret_cast<NzDevSeg*>((char*)t->pin + pin_reqs);
+    NzDevRes* hres = reinterpret_cast<NzDevRes*>((char*)t->pin + pin_reqs + pin_segs);
+    uint32_t sb = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const nz_get_req& r = reqs[i];
+        NzDevReq& d = hreq[i];
+        d.k0 = rd64(r.key); d.k1 = rd64(r.key + 8);
+        d.dst = (uint64_t)(uintptr_t)r.dst->dev + r.dst_base;
+        d.dst_cap = r.dst->size - r.dst_base;
+        d.flags = r.flags;
+        d.seg_begin = sb;
+        d.whole = r.nseg == 0;
+        d.nseg = r.nseg ? r.nseg : 1;
+        d.scratch = 0; d.scratch_cap = 0;
+        if (any_inflate && scratch_need[i]) {
+            void* sp = nullptr;
+            if (cudaMalloc(&sp, scratch_need[i] + 512) == cudaSuccess) {
+                t->scratch.push_back(sp);
+                d.scratch = (uint64_t)(uintptr_t)sp;
+                d.scratch_cap = scratch_need[i];
+            } else {
+                cudaGetLastError();
+            }
+        }
+        if (r.nseg == 0) {
+            hseg[sb].src_off = 0; hseg[sb].len = 0; hseg[sb].dst_off = 0; hseg[sb].req = i; hseg[sb].pad = 0;
+            ++sb;
+        } else {
+            for (uint32_t k = 0; k < r.nseg; ++k, ++sb) {
+                hseg[sb].src_off = r.segs[k].src_off; hseg[sb].len = r.segs[k].len; hseg[sb].dst_off = r.segs[k].dst_off;
+                hseg[sb].req = i; hseg[sb].pad = 0;
+            }
+        }
+        hres[i].status = NZ_ECUDA; hres[i].flags = 0; hres[i].bytes = 0; hres[i].length = 0; hres[i].crc32c = 0; hres[i].reserved = 0;
+    }
+
+    char* dv = (char*)t->dev;
+    NzPlanArgs a;
+    a.table = c->table; a.line_mask = c->n_lines - 1; a.descs = c->descs; a.arena = c->arena;
+    a.reqs = reinterpret_cast<const NzDevReq*>(t->pin_dev); a.n = n;
+    a.segs = reinterpret_cast<const NzDevSeg*>((char*)t->pin_dev + pin_reqs); a.nseg = (uint32_t)nseg;
+    a.res = reinterpret_cast<NzDevRes*>((char*)t->pin_dev + pin_reqs + pin_segs);
+    a.work = reinterpret_cast<NzSegWork*>(dv);
+    a.tile_begin = reinterpret_cast<uint64_t*>(dv + dev_work);
+    a.ver = reinterpret_cast<NzVerWork*>(dv + dev_work + dev_tiles);
+    a.ver_cap = (uint32_t)ver_cap;
+    a.counters = reinterpret_cast<uint32_t*>(dv + dev_work + dev_tiles + dev_ver);
+    a.infl = reinterpret_cast<NzInflWork*>(dv + dev_work + dev_tiles + dev_ver + dev_cnt);
+
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : c->streams[c->rr.fetch_add(1) % c->streams.size()];
+    t->stream = s;
+    cudaError_t e;
+#define CKT(call) do { e = (call); if (e != cudaSuccess) { int32_t rc = cuda_fail(e, #call); nz_ticket_free(t); return rc; } } while (0)
+    CKT(cudaEventRecord(t->ev_start, s));
+    CKT(cudaMemsetAsync(a.counters, 0, 16, s));
+    CKT(nz_launch_plan(a, s));
+    c->launches += a.ver_cap ? 2 : 1;
+    if (any_inflate) {
+        CKT(nz_launch_inflate(a.infl, a.counters, a.res, c->crc_tables, c->inflate_grid, s));
+        c->launches += 1;
+    }
+    CKT(cudaEventRecord(t->ev_g0, s));
+    CKT(nz_launch_gather(a.work, a.tile_begin, a.nseg, c->gather_grid, s));
+    CKT(cudaEventRecord(t->ev_g1, s));
+    c->launches += 1;
+    if (any_verify && ver_cap) {
+        int grid = (int)std::min<uint64_t>(ver_cap, (uint64_t)c->sm_count * 8);
+        CKT(nz_launch_verify(a.ver, a.counters, a.res, c->crc_tables, grid, s));
+        c->launches += 1;
+    }
+    CKT(cudaEventRecord(t->ev_done, s));
+#undef CKT
+    *out = t;
+    return NZ_OK;
+}
+
+int32_t nz_get_poll(nz_ticket* t) {
+    if (!t) return NZ_EINVAL;
+    cudaError_t e = cudaEventQuery(t->ev_done);
+    if (e == cudaSuccess) return NZ_OK;
+    if (e == cudaErrorNotReady) return NZ_ETIMEOUT;
+    return cuda_fail(e, "cudaEventQuery");
+}
+
+int32_t nz_get_wait(nz_ticket* t, int64_t timeout_us, nz_get_res* res) {
+    if (!t) return NZ_EINVAL;
+    nz_ctx* c = t->ctx;
+    cudaSetDevice(c->device);
+    if (timeout_us < 0) {
+        CK(cudaEventSynchronize(t->ev_done));
+    } else {
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+            cudaError_t e = cudaEventQuery(t->ev_done);
+            if (e == cudaSuccess) break;
+            if (e != cudaErrorNotReady) return cuda_fail(e, "cudaEventQuery");
+            const auto us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+            if (us >= timeout_us) return NZ_ETIMEOUT;
+            if (us > 200) std::this_thread::sleep_for(std::chrono::microseconds(50));
+            else std::this_thread::yield();
+        }
+    }
+    const size_t pin_reqs = round_up((size_t)t->n * sizeof(NzDevReq), 256);
+    const size_t pin_segs = round_up((size_t)t->nseg * sizeof(NzDevSeg), 256);
+    const NzDevRes* hres = reinterpret_cast<const NzDevRes*>((char*)t->pin + pin_reqs + pin_segs);
+    uint64_t bytes = 0, hits = 0, misses = 0, corrupt = 0;
+    for (uint32_t i = 0; i < t->n; ++i) {
+        if (res) memcpy(&res[i], &hres[i], sizeof(nz_get_res));
+        if (hres[i].status == NZ_OK) { ++hits; bytes += hres[i].bytes; }
+        else if (hres[i].status == NZ_ENOTFOUND) ++misses;
+        else if (hres[i].status == NZ_ECORRUPT) ++corrupt;
+    }
+    if (!t->req_bytes_hint) {   // count a wave once even if waited twice
+        t->req_bytes_hint = 1;
+        c->gets += t->n; c->get_bytes += bytes; c->hits += hits; c->misses += misses; c->corrupt += corrupt;
+    }
+    return NZ_OK;
+}
+
+int32_t nz_ticket_elapsed_ms(nz_ticket* t, float* ms) {
+    if (!t || !ms) return NZ_EINVAL;
+    CK(cudaEventElapsedTime(ms, t->ev_start, t->ev_done));
+    return NZ_OK;
+}
+
+int32_t nz_ticket_gather_ms(nz_ticket* t, float* ms) {
+    if (!t || !ms) return NZ_EINVAL;
+    CK(cudaEventElapsedTime(ms, t->ev_g0, t->ev_g1));
+    return NZ_OK;
+}
+
+int32_t nz_ticket_free(nz_ticket* t) {
+    if (!t) return NZ_EINVAL;
+    nz_ctx* c = t->ctx;
+    cudaSetDevice(c->device);
+    cudaEventSynchronize(t->ev_done);   // never recycle buffers a kernel may still read
+    for (void* p : t->scratch) cudaFree(p);
+    t->scratch.clear();
+    t->req_bytes_hint = 0;
+    t->stream = nullptr;
+    std::lock_guard<std::mutex> g(c->tmu);
+    if (c->ticket_pool.size() < 64) c->ticket_pool.push_back(t);
+    else ticket_destroy(t);
+    return NZ_OK;
+}
+
+int32_t nz_get_stats(nz_ctx* c, nz_stats* out) {
+    if (!c || !out) return NZ_EINVAL;
+    memset(out, 0, sizeof *out);
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        out->objects = c->shadow.size();
+        uint64_t freeb = 0;
+        for (auto& kv : c->free_by_off) freeb += kv.second;
+        out->arena_used = c->arena_bytes - freeb;
+        out->table_live = c->shadow.size();
+    }
+    out->arena_bytes = c->arena_bytes;
+    out->table_slots = c->n_lines * 4;
+    out->gets = c->gets; out->get_bytes = c->get_bytes; out->hits = c->hits; out->misses = c->misses;
+    out->puts = c->puts; out->put_bytes = c->put_bytes; out->evictions = c->evictions; out->corrupt = c->corrupt;
+    out->kernel_launches = c->launches;
+    return NZ_OK;
+}
+
+int32_t nz_debug_poke(nz_ctx* c, const uint8_t key[16], uint64_t off, uint8_t xor_mask) {
+    if (!c || !key) return NZ_EINVAL;
+    CK(cudaSetDevice(c->device));
+    NzHostObj ho;
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        auto it = c->shadow.find({rd64(key), rd64(key + 8)});
+        if (it == c->shadow.end() || it->second.desc == 0xFFFFFFFFu) return NZ_ENOTFOUND;
+        ho = it->second;
+    }
+    if (off >= ho.stored_len) return NZ_EINVAL;
+    uint8_t b = 0;
+    CK(cudaMemcpy(&b, c->arena + ho.arena_off + off, 1, cudaMemcpyDeviceToHost));
+    b ^= xor_mask;
+    CK(cudaMemcpy(c->arena + ho.arena_off + off, &b, 1, cudaMemcpyHostToDevice));
+    return NZ_OK;
+}
+
+int32_t nz_crc32c_device(nz_ctx* c, const void* dev, uint64_t n, uint32_t* out_crc, uint32_t* out_chunks_host) {
+    if (!c || (!dev && n) || !out_crc) return NZ_EINVAL;
+    CK(cudaSetDevice(c->device));
+    const uint64_t nchunks = (n + NZ_CRC_CHUNK - 1) / NZ_CRC_CHUNK;
+    uint32_t* tab = nullptr;
+    CK(cudaMalloc(&tab, (nchunks + 1) * 4 + 256));
+    cudaStream_t s = c->streams[c->rr.fetch_add(1) % c->streams.size()];
+    uint32_t* whole = tab + nchunks;
+    cudaError_t e = nz_launch_crc_chunks((const uint8_t*)dev, n, tab, whole, c->crc_tables, c->sm_count, s);
+    c->launches += 2;
+    uint32_t h = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, whole, 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && out_chunks_host && nchunks) e = cudaMemcpyAsync(out_chunks_host, tab, nchunks * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(tab);
+    if (e != cudaSuccess) return cuda_fail(e, "crc32c_device");
+    *out_crc = h;
+    return NZ_OK;
+}
+
+}  // extern "C"

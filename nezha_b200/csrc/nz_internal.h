@@ -1,0 +1,215 @@
+// nezha_b200/csrc/nz_internal.h — device data layout and host context of
+// libnezha_gpu.so.  Names follow the reference's domain (cache zone, extents,
+// keys — /root/reference/examples/demo/nginx.conf:38,56), not ML vocabulary.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/nezha_gpu.h"
+
+// ---------------------------------------------------------------------------
+// HBM layout
+// ---------------------------------------------------------------------------
+// Hash table ("zone"): open addressing, linear probing by 128-byte lines.
+// One slot = 32 B, four slots per line, so one probe step is exactly one
+// coalesced 128 B transaction read by a 4-lane group (warp-ballot match).
+struct __align__(32) NzSlot {
+    uint64_t k0, k1;    // key128 (MD5 of "$host/$proxy_host$uri")
+    uint32_t state;     // NZ_SLOT_*
+    uint32_t desc;      // index into the descriptor array
+    uint64_t gen;       // insertion generation (diagnostic / ABA guard)
+};
+enum : uint32_t { NZ_SLOT_EMPTY = 0, NZ_SLOT_TOMB = 1, NZ_SLOT_LIVE = 2, NZ_SLOT_BUSY = 3 };
+
+// Extent descriptor: where an object's bytes live in the arena.
+struct __align__(64) NzDesc {
+    uint64_t arena_off;      // byte offset of the extent in the arena (4 KiB aligned)
+    uint64_t stored_len;     // bytes at rest
+    uint64_t raw_len;        // inflated length (== stored_len for identity)
+    uint64_t user_meta;      // host cookie
+    uint64_t crc_tab_off;    // arena offset of the u32 chunk-CRC table
+    uint32_t flags;          // NZ_ENC_*
+    uint32_t crc32c;         // whole-object CRC-32C of the stored bytes
+    uint32_t n_chunks;
+    uint32_t gen;
+    uint64_t pad;
+};
+static_assert(sizeof(NzSlot) == 32, "slot");
+static_assert(sizeof(NzDesc) == 64, "desc");
+
+// One GET as the device sees it (lives in mapped pinned memory, read once).
+struct __align__(16) NzDevReq {
+    uint64_t k0, k1;
+    uint64_t dst;          // device-visible address of the destination buffer + dst_base
+    uint64_t dst_cap;      // bytes available from dst
+    uint32_t flags;        // NZ_GET_*
+    uint32_t seg_begin;    // first entry in the segment array
+    uint32_t nseg;         // >= 1 (nseg==0 requests get one whole-object pseudo segment)
+    uint32_t whole;        // 1 = pseudo segment: serve [0, length)
+    uint64_t scratch;      // device address of the inflate scratch (0 = inflate straight to dst)
+    uint64_t scratch_cap;
+};
+struct __align__(8) NzDevSeg {
+    uint64_t src_off, len, dst_off;
+    uint32_t req;
+    uint32_t pad;
+};
+// Resolved copy work for the gather kernel.
+struct __align__(16) NzSegWork {
+    uint64_t src;          // device address of first byte
+    uint64_t dst;          // device-visible address of first byte
+    uint64_t len;
+    int64_t  vstart;       // = -(dst & 127): tile k covers [vstart + k*TILE, +TILE) ∩ [0,len)
+};
+// Per-request inflate work
+struct __align__(16) NzInflWork {
+    uint64_t src;          // gzip member
+    uint64_t src_len;
+    uint64_t dst;          // raw output
+    uint64_t dst_cap;
+    uint32_t req;
+    uint32_t pad;
+};
+struct __align__(8) NzDevRes {   // mirrors nz_get_res
+    int32_t  status;
+    uint32_t flags;
+    uint64_t bytes;
+    uint64_t length;
+    uint32_t crc32c;
+    uint32_t reserved;
+};
+static_assert(sizeof(NzDevRes) == sizeof(nz_get_res), "res layout");
+
+// Verify work: one 64 KiB chunk to re-checksum
+struct __align__(16) NzVerWork {
+    uint64_t ptr;
+    uint32_t len;
+    uint32_t expect;
+    uint32_t req;
+    uint32_t pad;
+};
+
+constexpr uint32_t NZ_TILE = 32768;          // gather tile (bytes of destination)
+constexpr int NZ_GATHER_THREADS = 256;
+constexpr int NZ_GATHER_UNROLL = 8;          // 16 B vectors in flight per thread
+
+// ---------------------------------------------------------------------------
+// host context
+// ---------------------------------------------------------------------------
+struct nz_buf {
+    nz_ctx* ctx;
+    void* host;        // pinned host address or nullptr
+    void* dev;         // device-visible address
+    uint64_t size;
+    int32_t kind;
+    bool owned;
+};
+
+struct NzHostObj {     // host shadow of a live object (arena bookkeeping, EEXIST, inflate sizing)
+    uint32_t desc;
+    uint64_t arena_off, arena_len;
+    uint64_t stored_len, raw_len;
+    uint32_t flags;
+};
+
+struct KeyHash {
+    size_t operator()(const std::pair<uint64_t, uint64_t>& k) const { return (size_t)(k.second ^ (k.first * 0x9E3779B97F4A7C15ull)); }
+};
+
+struct nz_ticket {
+    nz_ctx* ctx;
+    uint32_t n = 0, nseg = 0;
+    // pinned+mapped block: reqs | segs | res
+    void* pin = nullptr; void* pin_dev = nullptr; size_t pin_cap = 0;
+    // device block: segwork | tile prefix | verify work | inflate work | counters
+    void* dev = nullptr; size_t dev_cap = 0;
+    std::vector<void*> scratch;        // inflate scratch (arena-independent cudaMalloc'd, returned at free)
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_done = nullptr, ev_g0 = nullptr, ev_g1 = nullptr;
+    bool own_stream = false;
+    uint64_t req_bytes_hint = 0;
+};
+
+struct nz_put {
+    nz_ctx* ctx;
+    uint64_t k0, k1;
+    uint64_t stored_len, raw_len, user_meta;
+    uint32_t flags;
+    uint64_t arena_off, arena_len;     // extent + chunk-crc table
+    uint64_t crc_tab_off;
+    uint32_t n_chunks;
+    cudaStream_t stream;
+};
+
+struct nz_ctx {
+    nz_config cfg;
+    int device;
+    int sm_count;
+    int gather_grid;       // persistent grid size for k_gather
+    int inflate_grid;
+    uint8_t* arena = nullptr;
+    uint64_t arena_bytes = 0;
+    NzSlot* table = nullptr;
+    uint64_t n_lines = 0;           // table lines (4 slots each), power of two
+    NzDesc* descs = nullptr;
+    uint32_t* crc_tables = nullptr; // device: 8 x 256 u32 slice tables (Castagnoli), then 8 x 256 (IEEE)
+    std::mutex mu;                  // arena + shadow + desc free list
+    std::map<uint64_t, uint64_t> free_by_off;   // arena free list: off -> len
+    std::vector<uint32_t> free_desc;
+    std::unordered_map<std::pair<uint64_t, uint64_t>, NzHostObj, KeyHash> shadow;
+    uint64_t gen = 1;
+    // stream pool
+    std::vector<cudaStream_t> streams;
+    std::atomic<uint32_t> rr{0};
+    cudaStream_t put_stream = nullptr;
+    // ticket recycling
+    std::mutex tmu;
+    std::vector<nz_ticket*> ticket_pool;
+    // stats
+    std::atomic<uint64_t> gets{0}, get_bytes{0}, hits{0}, misses{0}, puts{0}, put_bytes{0}, evictions{0}, corrupt{0}, launches{0};
+    // bounce buffers for nz_put_file / pageable writes
+    void* bounce[2] = {nullptr, nullptr};
+    size_t bounce_bytes = 0;
+    cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
+    std::mutex put_mu;              // serialises fill-side device work
+};
+
+// ---------------------------------------------------------------------------
+// kernel launchers (nz_kernels.cu / nz_inflate.cu)
+// ---------------------------------------------------------------------------
+struct NzPlanArgs {
+    const NzSlot* table; uint64_t line_mask;
+    const NzDesc* descs;
+    const uint8_t* arena;
+    const NzDevReq* reqs; uint32_t n;
+    const NzDevSeg* segs; uint32_t nseg;
+    NzDevRes* res;
+    NzSegWork* work;            // nseg entries
+    uint64_t* tile_begin;       // nseg + 1
+    NzVerWork* ver;             // capacity ver_cap
+    uint32_t ver_cap;
+    NzInflWork* infl;           // capacity n
+    uint32_t* counters;         // [0]=n_ver [1]=n_infl
+};
+cudaError_t nz_launch_lookup(const NzSlot* table, uint64_t line_mask, const NzDesc* descs, const uint64_t* keys,
+                             uint32_t n, nz_extent* out, cudaStream_t s);
+cudaError_t nz_launch_insert(NzSlot* table, uint64_t line_mask, uint64_t k0, uint64_t k1, uint32_t desc, uint64_t gen,
+                             int32_t* status, cudaStream_t s);
+cudaError_t nz_launch_erase(NzSlot* table, uint64_t line_mask, uint64_t k0, uint64_t k1, int32_t* status, cudaStream_t s);
+cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s);
+cudaError_t nz_launch_gather(const NzSegWork* work, const uint64_t* tile_begin, uint32_t nseg, int grid, cudaStream_t s);
+cudaError_t nz_launch_verify(const NzVerWork* ver, const uint32_t* counters, NzDevRes* res, const uint32_t* crc_tables,
+                             int grid, cudaStream_t s);
+cudaError_t nz_launch_crc_chunks(const uint8_t* p, uint64_t n, uint32_t* chunk_out, uint32_t* whole_out,
+                                 const uint32_t* crc_tables, int sm_count, cudaStream_t s);
+cudaError_t nz_launch_inflate(const NzInflWork* infl, const uint32_t* counters, NzDevRes* res, const uint32_t* crc_tables,
+                              int grid, cudaStream_t s);
+cudaError_t nz_upload_constants(uint32_t* crc_tables_dev);
+int nz_gather_blocks_per_sm();
+int nz_inflate_blocks_per_sm();

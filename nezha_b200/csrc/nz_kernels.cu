@@ -1,0 +1,672 @@
+// nezha_b200/csrc/nz_kernels.cu — sm_100a kernels of the cache-hit path.
+//
+//   K1 k_lookup / probe_group4   key128 -> extent descriptor (warp-ballot over 128 B lines)
+//   K6 k_insert / k_erase        claim (CAS) + publish / tombstone
+//      k_plan                    one wave of GETs: probe, validate ranges, build copy work
+//   K2 k_gather                  persistent range-slice gather into the response buffers
+//   K3 k_crc_chunks / k_crc_fold CRC-32C chunk table + whole-object combine
+//      k_verify                  re-checksum the chunks a GET touched
+//
+// Byte/integer work bounded by HBM bandwidth: no tensor cores.  What these
+// replace in the reference: nginx's keys_zone rbtree lookup
+// (/root/reference/examples/demo/nginx.conf:38) and its cache-file read loop +
+// range filter.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nz_internal.h"
+
+#define POLY_C 0x82F63B78u
+
+// x^(8 * 2^k) mod P (reflected), k = 0..47; filled by nz_upload_constants.
+__constant__ uint32_t c_x8pow[48];
+
+// ---------------------------------------------------------------------------
+// small PTX helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {  // read-once data: do not pollute L1
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_cached(const void* p) {  // neighbours re-read this vector: keep in L1
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// K1: probe.  A 4-lane group owns one key; each lane reads one 32 B slot of the
+// current 128 B line (one coalesced transaction per group), the group matches
+// with a warp ballot.  Must be called by all 32 lanes of the warp.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t probe_group4(const NzSlot* __restrict__ table, uint64_t line_mask,
+                                                 uint64_t k0, uint64_t k1, bool active) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned gshift = lane & ~3u;
+    const unsigned q = lane & 3u;
+    uint64_t line = k1 & line_mask;
+    uint32_t found = 0xFFFFFFFFu;
+    bool done = !active;
+    for (uint64_t probe = 0; probe <= line_mask; ++probe) {
+        uint64_t s_k0 = 0, s_k1 = 0;
+        uint32_t s_state = NZ_SLOT_BUSY, s_desc = 0;
+        if (!done) {
+            const uint4* sp = reinterpret_cast<const uint4*>(table + (line * 4 + q));
+            uint4 a = __ldcg(sp), b = __ldcg(sp + 1);
+            s_k0 = (uint64_t)a.x | ((uint64_t)a.y << 32);
+            s_k1 = (uint64_t)a.z | ((uint64_t)a.w << 32);
+            s_state = b.x;
+            s_desc = b.y;
+        }
+        const bool match = !done && s_state == NZ_SLOT_LIVE && s_k0 == k0 && s_k1 == k1;
+        const bool empty = !done && s_state == NZ_SLOT_EMPTY;
+        const unsigned bm = __ballot_sync(0xffffffffu, match);
+        const unsigned be = __ballot_sync(0xffffffffu, empty);
+        const unsigned gm = (bm >> gshift) & 0xFu, ge = (be >> gshift) & 0xFu;
+        const uint32_t d = __shfl_sync(0xffffffffu, s_desc, gshift + (gm ? (__ffs(gm) - 1) : 0));
+        if (!done) {
+            if (gm) { found = d; done = true; }
+            else if (ge) { done = true; }
+        }
+        if (__all_sync(0xffffffffu, done)) break;
+        line = (line + 1) & line_mask;
+    }
+    return found;
+}
+
+__global__ void __launch_bounds__(256) k_lookup(const NzSlot* __restrict__ table, uint64_t line_mask,
+                                                const NzDesc* __restrict__ descs, const uint64_t* __restrict__ keys,
+                                                uint32_t n, nz_extent* __restrict__ out) {
+    const uint32_t groups_per_block = blockDim.x / 4;
+    const uint32_t g = threadIdx.x / 4;
+    const uint32_t stride = gridDim.x * groups_per_block;
+    const uint32_t rounds = (n + stride - 1) / stride;
+    for (uint32_t it = 0; it < rounds; ++it) {
+        const uint32_t r = it * stride + blockIdx.x * groups_per_block + g;
+        const bool active = r < n;
+        uint64_t k0 = 0, k1 = 0;
+        if (active) { k0 = keys[2 * r]; k1 = keys[2 * r + 1]; }
+        const uint32_t d = probe_group4(table, line_mask, k0, k1, active);
+        if (active && (threadIdx.x & 3u) == 0) {
+            nz_extent e;
+            if (d == 0xFFFFFFFFu) {
+                e.status = NZ_ENOTFOUND; e.flags = 0; e.stored_length = 0; e.raw_length = 0;
+                e.crc32c = 0; e.desc_index = 0xFFFFFFFFu; e.user_meta = 0;
+            } else {
+                const NzDesc ds = descs[d];
+                e.status = NZ_OK; e.flags = ds.flags; e.stored_length = ds.stored_len; e.raw_length = ds.raw_len;
+                e.crc32c = ds.crc32c; e.desc_index = d; e.user_meta = ds.user_meta;
+            }
+            out[r] = e;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K6: insert (claim with CAS, publish with a fence) / erase (tombstone)
+// ---------------------------------------------------------------------------
+__global__ void k_insert(NzSlot* table, uint64_t line_mask, uint64_t k0, uint64_t k1, uint32_t desc, uint64_t gen,
+                         int32_t* status) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint64_t line = k1 & line_mask;
+    for (uint64_t probe = 0; probe <= line_mask; ++probe) {
+        for (int q = 0; q < 4; ++q) {
+            NzSlot* s = table + line * 4 + q;
+            uint32_t st = *(volatile uint32_t*)&s->state;
+            if (st == NZ_SLOT_LIVE) {
+                if (s->k0 == k0 && s->k1 == k1) { *status = NZ_EEXIST; return; }
+                continue;
+            }
+            if (st == NZ_SLOT_EMPTY || st == NZ_SLOT_TOMB) {
+                if (atomicCAS(&s->state, st, (uint32_t)NZ_SLOT_BUSY) == st) {
+                    s->k0 = k0; s->k1 = k1; s->desc = desc; s->gen = gen;
+                    __threadfence();
+                    *(volatile uint32_t*)&s->state = NZ_SLOT_LIVE;
+                    *status = NZ_OK;
+                    return;
+                }
+            }
+        }
+        line = (line + 1) & line_mask;
+    }
+    *status = NZ_EFULL;
+}
+
+__global__ void k_erase(NzSlot* table, uint64_t line_mask, uint64_t k0, uint64_t k1, int32_t* status) {
+    const uint32_t d = probe_group4(table, line_mask, k0, k1, threadIdx.x < 4);
+    (void)d;
+    // re-walk to find the slot address (cheap; erase is rare)
+    if (threadIdx.x != 0) return;
+    uint64_t line = k1 & line_mask;
+    for (uint64_t probe = 0; probe <= line_mask; ++probe) {
+        bool saw_empty = false;
+        for (int q = 0; q < 4; ++q) {
+            NzSlot* s = table + line * 4 + q;
+            uint32_t st = *(volatile uint32_t*)&s->state;
+            if (st == NZ_SLOT_LIVE && s->k0 == k0 && s->k1 == k1) {
+                *(volatile uint32_t*)&s->state = NZ_SLOT_TOMB;
+                __threadfence();
+                *status = NZ_OK;
+                return;
+            }
+            if (st == NZ_SLOT_EMPTY) saw_empty = true;
+        }
+        if (saw_empty) break;
+        line = (line + 1) & line_mask;
+    }
+    *status = NZ_ENOTFOUND;
+}
+
+// ---------------------------------------------------------------------------
+// k_plan: one CTA turns a wave of GETs into copy / verify / inflate work.
+// ---------------------------------------------------------------------------
+struct PlanScratch {
+    uint64_t* rq_src;   // n: device address of byte 0 of the served representation
+    uint64_t* rq_len;   // n: its length
+};
+
+__global__ void __launch_bounds__(1024, 1)
+k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len) {
+    __shared__ uint64_t s_scan[1024];
+    __shared__ uint64_t s_carry;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t g = tid >> 2;
+
+    // ---- phase A: probe + per-request validation --------------------------
+    for (uint32_t base = 0; base < a.n; base += 256) {
+        const uint32_t r = base + g;
+        const bool active = r < a.n;
+        NzDevReq rq;
+        if (active) rq = a.reqs[r];
+        else { rq.k0 = rq.k1 = 0; }
+        const uint32_t d = probe_group4(a.table, a.line_mask, rq.k0, rq.k1, active);
+        if (!active || (tid & 3u) != 0) continue;
+        NzDevRes out;
+        out.status = NZ_OK; out.flags = 0; out.bytes = 0; out.length = 0; out.crc32c = 0; out.reserved = 0;
+        uint64_t src = 0, len = 0;
+        if (d == 0xFFFFFFFFu) {
+            out.status = NZ_ENOTFOUND;
+        } else {
+            const NzDesc ds = a.descs[d];
+            out.flags = ds.flags;
+            out.crc32c = ds.crc32c;
+            const bool inflate = (rq.flags & NZ_GET_INFLATE) && (ds.flags & NZ_ENC_GZIP);
+            len = inflate ? ds.raw_len : ds.stored_len;
+            out.length = len;
+            src = (uint64_t)(a.arena + ds.arena_off);
+            // validate slices against the representation and the destination
+            uint64_t bytes = 0;
+            if (rq.whole) {
+                bytes = len;
+                if (len > rq.dst_cap) out.status = NZ_ERANGE;
+            } else {
+                for (uint32_t i = 0; i < rq.nseg; ++i) {
+                    const NzDevSeg sg = a.segs[rq.seg_begin + i];
+                    if (sg.src_off > len || sg.len > len - sg.src_off) { out.status = NZ_EINVAL; break; }
+                    if (sg.dst_off > rq.dst_cap || sg.len > rq.dst_cap - sg.dst_off) { out.status = NZ_ERANGE; break; }
+                    bytes += sg.len;
+                }
+            }
+            if (out.status == NZ_OK) {
+                out.bytes = bytes;
+                if (inflate) {
+                    const bool direct = rq.whole && rq.scratch == 0;
+                    if (!direct && (rq.scratch == 0 || rq.scratch_cap < len)) {
+                        out.status = NZ_ENOMEM;
+                        out.bytes = 0;
+                    } else {
+                        const uint32_t slot = atomicAdd(&a.counters[1], 1u);
+                        NzInflWork w;
+                        w.src = src; w.src_len = ds.stored_len;
+                        w.dst = direct ? rq.dst : rq.scratch;
+                        w.dst_cap = direct ? rq.dst_cap : rq.scratch_cap;
+                        w.req = r; w.pad = direct ? 1u : 0u;
+                        a.infl[slot] = w;
+                        src = direct ? 0 : rq.scratch;   // direct: nothing left to gather
+                        if (direct) len = 0;
+                    }
+                }
+                // verify: inflate reads the whole member, so check every stored chunk
+                if (out.status == NZ_OK && (rq.flags & NZ_GET_VERIFY) && inflate) {
+                    const uint32_t* tab = reinterpret_cast<const uint32_t*>(a.arena + ds.crc_tab_off);
+                    const uint32_t first = atomicAdd(&a.counters[0], ds.n_chunks);
+                    for (uint32_t c = 0; c < ds.n_chunks && first + c < a.ver_cap; ++c) {
+                        NzVerWork v;
+                        const uint64_t off = (uint64_t)c * NZ_CRC_CHUNK;
+                        v.ptr = (uint64_t)(a.arena + ds.arena_off + off);
+                        v.len = (uint32_t)min((uint64_t)NZ_CRC_CHUNK, ds.stored_len - off);
+                        v.expect = tab[c]; v.req = r; v.pad = 0;
+                        a.ver[first + c] = v;
+                    }
+                }
+            }
+        }
+        if (out.status != NZ_OK) { len = 0; src = 0; }
+        rq_src[r] = src;
+        rq_len[r] = len;
+        a.res[r] = out;
+    }
+    __syncthreads();
+
+    // ---- phase B: per-segment copy work + exclusive scan of tile counts ----
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < a.nseg; base += 1024) {
+        const uint32_t s = base + tid;
+        uint64_t tiles = 0;
+        if (s < a.nseg) {
+            const NzDevSeg sg = a.segs[s];
+            const NzDevReq& rq = a.reqs[sg.req];
+            const int32_t st = a.res[sg.req].status;
+            NzSegWork w;
+            w.src = 0; w.dst = 0; w.len = 0; w.vstart = 0;
+            const uint64_t rlen = rq_len[sg.req];
+            if (st == NZ_OK && rlen > 0) {
+                const uint64_t off = rq.whole ? 0 : sg.src_off;
+                const uint64_t len = rq.whole ? rlen : sg.len;
+                const uint64_t doff = rq.whole ? 0 : sg.dst_off;
+                w.src = rq_src[sg.req] + off;
+                w.dst = rq.dst + doff;
+                w.len = len;
+                w.vstart = -(int64_t)(w.dst & 127u);
+                tiles = len ? (len + (w.dst & 127u) + NZ_TILE - 1) / NZ_TILE : 0;
+            }
+            a.work[s] = w;
+        }
+        // block exclusive scan (Hillis-Steele over 1024 entries)
+        s_scan[tid] = tiles;
+        __syncthreads();
+        for (uint32_t ofs = 1; ofs < 1024; ofs <<= 1) {
+            uint64_t v = (tid >= ofs) ? s_scan[tid - ofs] : 0;
+            __syncthreads();
+            s_scan[tid] += v;
+            __syncthreads();
+        }
+        const uint64_t incl = s_scan[tid];
+        const uint64_t carry = s_carry;
+        if (s < a.nseg) a.tile_begin[s] = carry + incl - tiles;
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + incl;
+        __syncthreads();
+    }
+    if (tid == 0) a.tile_begin[a.nseg] = s_carry;
+}
+
+// identity-object verify work is emitted by a second tiny kernel that has the
+// descriptor at hand (keeps k_plan's per-request state small).
+__global__ void __launch_bounds__(256)
+k_plan_verify(NzPlanArgs a) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t g = tid >> 2;
+    for (uint32_t base = 0; base < a.n; base += 64) {
+        const uint32_t r = base + g;
+        const bool want = r < a.n && (a.reqs[r].flags & NZ_GET_VERIFY) && a.res[r].status == NZ_OK;
+        uint64_t k0 = 0, k1 = 0;
+        if (want) { k0 = a.reqs[r].k0; k1 = a.reqs[r].k1; }
+        const uint32_t d = probe_group4(a.table, a.line_mask, k0, k1, want);
+        if (!want || (tid & 3u) != 0 || d == 0xFFFFFFFFu) continue;
+        const NzDesc ds = a.descs[d];
+        const NzDevReq rq = a.reqs[r];
+        if ((rq.flags & NZ_GET_INFLATE) && (ds.flags & NZ_ENC_GZIP)) continue;   // done in k_plan
+        const uint32_t* tab = reinterpret_cast<const uint32_t*>(a.arena + ds.crc_tab_off);
+        const uint32_t nsg = rq.whole ? 1u : rq.nseg;
+        for (uint32_t i = 0; i < nsg; ++i) {
+            uint64_t off = 0, len = ds.stored_len;
+            if (!rq.whole) { const NzDevSeg sg = a.segs[rq.seg_begin + i]; off = sg.src_off; len = sg.len; }
+            if (!len) continue;
+            const uint32_t c0 = (uint32_t)(off / NZ_CRC_CHUNK), c1 = (uint32_t)((off + len - 1) / NZ_CRC_CHUNK);
+            const uint32_t cnt = c1 - c0 + 1;
+            const uint32_t first = atomicAdd(&a.counters[0], cnt);
+            for (uint32_t c = 0; c < cnt && first + c < a.ver_cap; ++c) {
+                NzVerWork v;
+                const uint64_t coff = (uint64_t)(c0 + c) * NZ_CRC_CHUNK;
+                v.ptr = (uint64_t)(a.arena + ds.arena_off + coff);
+                v.len = (uint32_t)min((uint64_t)NZ_CRC_CHUNK, ds.stored_len - coff);
+                v.expect = tab[c0 + c]; v.req = r; v.pad = 0;
+                a.ver[first + c] = v;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2: range-slice gather.  Persistent grid; a tile is NZ_TILE bytes of one
+// segment, cut so that every interior tile boundary is 128 B aligned in the
+// DESTINATION (full-line writes).  The source may sit at any byte offset
+// (Range: bytes=a-b), so vectors are rebuilt from two aligned 16 B loads with a
+// funnel shift; every global access is a 16 B vector on a 16 B boundary.
+// ---------------------------------------------------------------------------
+template <int WS>   // WS = (source misalignment) / 4, 0..3 ; bs = 8 * (misalignment % 4)
+__device__ __forceinline__ uint4 realign(const uint4 a, const uint4 b, unsigned bs) {
+    uint4 o;
+    if constexpr (WS == 0) {
+        o.x = __funnelshift_r(a.x, a.y, bs); o.y = __funnelshift_r(a.y, a.z, bs);
+        o.z = __funnelshift_r(a.z, a.w, bs); o.w = __funnelshift_r(a.w, b.x, bs);
+    } else if constexpr (WS == 1) {
+        o.x = __funnelshift_r(a.y, a.z, bs); o.y = __funnelshift_r(a.z, a.w, bs);
+        o.z = __funnelshift_r(a.w, b.x, bs); o.w = __funnelshift_r(b.x, b.y, bs);
+    } else if constexpr (WS == 2) {
+        o.x = __funnelshift_r(a.z, a.w, bs); o.y = __funnelshift_r(a.w, b.x, bs);
+        o.z = __funnelshift_r(b.x, b.y, bs); o.w = __funnelshift_r(b.y, b.z, bs);
+    } else {
+        o.x = __funnelshift_r(a.w, b.x, bs); o.y = __funnelshift_r(b.x, b.y, bs);
+        o.z = __funnelshift_r(b.y, b.z, bs); o.w = __funnelshift_r(b.z, b.w, bs);
+    }
+    return o;
+}
+
+template <int WS>
+__device__ __forceinline__ void copy_vectors_shifted(const uint4* __restrict__ sa /*aligned base*/, uint4* __restrict__ d,
+                                                     uint32_t nvec, unsigned bs) {
+    constexpr int U = NZ_GATHER_UNROLL / 2;   // two loads per output vector
+    constexpr uint32_t STEP = NZ_GATHER_THREADS * U;
+    const uint32_t tid = threadIdx.x;
+    uint32_t base = 0;
+    for (; base + STEP <= nvec; base += STEP) {   // full steps: no predicates, all loads issued before any store
+        uint4 lo[U], hi[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t i = base + u * NZ_GATHER_THREADS + tid;
+            lo[u] = ldg_cached(sa + i);
+            hi[u] = ldg_cached(sa + i + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) stg_stream(d + base + u * NZ_GATHER_THREADS + tid, realign<WS>(lo[u], hi[u], bs));
+    }
+    for (uint32_t i = base + tid; i < nvec; i += NZ_GATHER_THREADS)
+        stg_stream(d + i, realign<WS>(ldg_cached(sa + i), ldg_cached(sa + i + 1), bs));
+}
+
+__device__ __forceinline__ void copy_vectors_aligned(const uint4* __restrict__ sv, uint4* __restrict__ dv, uint32_t nvec) {
+    constexpr int U = NZ_GATHER_UNROLL;
+    constexpr uint32_t STEP = NZ_GATHER_THREADS * U;
+    const uint32_t tid = threadIdx.x;
+    uint32_t base = 0;
+    for (; base + STEP <= nvec; base += STEP) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = ldg_stream(sv + base + u * NZ_GATHER_THREADS + tid);
+#pragma unroll
+        for (int u = 0; u < U; ++u) stg_stream(dv + base + u * NZ_GATHER_THREADS + tid, v[u]);
+    }
+    for (uint32_t i = base + tid; i < nvec; i += NZ_GATHER_THREADS) stg_stream(dv + i, ldg_stream(sv + i));
+}
+
+__device__ __forceinline__ void copy_tile(const uint8_t* __restrict__ s, uint8_t* __restrict__ d, uint32_t n) {
+    const uint32_t tid = threadIdx.x;
+    // head: bring the destination to a 16 B boundary (only the first tile of a segment can need it)
+    const uint32_t head = min(n, (uint32_t)((16u - ((uintptr_t)d & 15u)) & 15u));
+    if (tid < head) d[tid] = s[tid];
+    s += head; d += head; n -= head;
+    const uint32_t nvec = n >> 4;
+    const uint32_t tail = n & 15u;
+    if (tid < tail) d[(nvec << 4) + tid] = s[(nvec << 4) + tid];
+    if (nvec == 0) return;
+    const unsigned mis = (unsigned)((uintptr_t)s & 15u);
+    uint4* dv = reinterpret_cast<uint4*>(d);
+    if (mis == 0) {
+        copy_vectors_aligned(reinterpret_cast<const uint4*>(s), dv, nvec);
+    } else {
+        const uint4* sa = reinterpret_cast<const uint4*>(s - mis);
+        const unsigned bs = (mis & 3u) * 8u;
+        switch (mis >> 2) {
+        case 0: copy_vectors_shifted<0>(sa, dv, nvec, bs); break;
+        case 1: copy_vectors_shifted<1>(sa, dv, nvec, bs); break;
+        case 2: copy_vectors_shifted<2>(sa, dv, nvec, bs); break;
+        default: copy_vectors_shifted<3>(sa, dv, nvec, bs); break;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NZ_GATHER_THREADS, 2)
+k_gather(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_begin, uint32_t nseg) {
+    const uint64_t total = tile_begin[nseg];
+    uint64_t lo_t = 0, hi_t = 0;   // tile range of the cached segment (empty at start)
+    uint64_t w_src = 0, w_dst = 0, w_len = 0;
+    int64_t w_vstart = 0;
+    for (uint64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        if (tile < lo_t || tile >= hi_t) {
+            // binary search: last seg with tile_begin[seg] <= tile (uniform across the CTA)
+            uint32_t a = 0, b = nseg;
+            while (b - a > 1) {
+                const uint32_t m = (a + b) >> 1;
+                if (__ldg(tile_begin + m) <= tile) a = m; else b = m;
+            }
+            lo_t = __ldg(tile_begin + a);
+            hi_t = __ldg(tile_begin + a + 1);
+            const ulonglong2 p0 = __ldg(reinterpret_cast<const ulonglong2*>(work + a));
+            const ulonglong2 p1 = __ldg(reinterpret_cast<const ulonglong2*>(work + a) + 1);
+            w_src = p0.x; w_dst = p0.y; w_len = p1.x; w_vstart = (int64_t)p1.y;
+        }
+        const uint64_t k = tile - lo_t;
+        int64_t lo = w_vstart + (int64_t)(k * NZ_TILE);
+        int64_t hi = lo + NZ_TILE;
+        if (lo < 0) lo = 0;
+        if (hi > (int64_t)w_len) hi = (int64_t)w_len;
+        copy_tile(reinterpret_cast<const uint8_t*>(w_src) + lo, reinterpret_cast<uint8_t*>(w_dst) + lo, (uint32_t)(hi - lo));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K3: CRC-32C.  GF(2) helpers (zlib's multmodp restated for the Castagnoli
+// polynomial, reflected bit order: x^0 = 0x80000000).
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t gf_mul(uint32_t a, uint32_t b) {
+    uint32_t p = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        p ^= b & (0u - ((a >> (31 - i)) & 1u));
+        b = (b >> 1) ^ (POLY_C & (0u - (b & 1u)));
+    }
+    return p;
+}
+__device__ __forceinline__ uint32_t gf_xpow8(uint64_t nbytes) {   // x^(8*nbytes)
+    uint32_t p = 0x80000000u;
+    int k = 0;
+    while (nbytes) {
+        if (nbytes & 1) p = gf_mul(c_x8pow[k], p);
+        nbytes >>= 1;
+        ++k;
+    }
+    return p;
+}
+
+// CRC-32C of one chunk (<= 64 KiB) by a 256-thread CTA: thread t owns bytes
+// [256 t, 256 t + 256), slice-by-4 from shared tables, then the per-thread CRCs
+// are shifted to the chunk end (multiply by x^(8*bytes_after)) and XOR-reduced.
+// sT: 4 x 256 u32 tables in shared memory; sred: 8 u32.
+__device__ uint32_t block_crc32c_chunk(const uint8_t* __restrict__ p, uint32_t m, const uint32_t* sT, uint32_t* sred) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t beg = tid * 256u;
+    uint32_t contrib = 0;
+    if (beg < m) {
+        const uint32_t cnt = min(256u, m - beg);
+        const uint8_t* q = p + beg;
+        uint32_t crc = 0xFFFFFFFFu;
+        uint32_t i = 0;
+        if ((((uintptr_t)q) & 15u) == 0) {
+            for (; i + 16 <= cnt; i += 16) {
+                const uint4 v = ldg_cached(q + i);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    crc ^= w[j];
+                    crc = sT[3 * 256 + (crc & 0xff)] ^ sT[2 * 256 + ((crc >> 8) & 0xff)] ^
+                          sT[1 * 256 + ((crc >> 16) & 0xff)] ^ sT[crc >> 24];
+                }
+            }
+        }
+        for (; i < cnt; ++i) crc = (crc >> 8) ^ sT[(crc ^ q[i]) & 0xff];
+        crc = ~crc;
+        const uint32_t after = m - (beg + cnt);
+        contrib = after ? gf_mul(gf_xpow8(after), crc) : crc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) contrib ^= __shfl_xor_sync(0xffffffffu, contrib, o);
+    __syncthreads();                       // sred reuse across calls
+    if ((tid & 31u) == 0) sred[tid >> 5] = contrib;
+    __syncthreads();
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r ^= sred[i];
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+k_crc_chunks(const uint8_t* __restrict__ p, uint64_t n, uint32_t* __restrict__ chunk_out, const uint32_t* __restrict__ tables) {
+    __shared__ uint32_t sT[4 * 256];
+    __shared__ uint32_t sred[8];
+    for (uint32_t i = threadIdx.x; i < 1024; i += 256) sT[i] = tables[i];
+    __syncthreads();
+    const uint64_t nchunks = (n + NZ_CRC_CHUNK - 1) / NZ_CRC_CHUNK;
+    for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const uint64_t off = c * NZ_CRC_CHUNK;
+        const uint32_t m = (uint32_t)min((uint64_t)NZ_CRC_CHUNK, n - off);
+        const uint32_t crc = block_crc32c_chunk(p + off, m, sT, sred);
+        if (threadIdx.x == 0) chunk_out[c] = crc;
+    }
+}
+
+// whole-object CRC = sum_i chunk_i * x^(8 * bytes_after_i): each thread folds a
+// contiguous run of chunks Horner-style, then one shift to the object end.
+__global__ void __launch_bounds__(1024)
+k_crc_fold(const uint32_t* __restrict__ chunks, uint64_t n, uint32_t* __restrict__ whole_out) {
+    __shared__ uint32_t sred[32];
+    const uint64_t nchunks = (n + NZ_CRC_CHUNK - 1) / NZ_CRC_CHUNK;
+    const uint32_t tid = threadIdx.x;
+    const uint64_t per = (nchunks + 1023) / 1024;
+    const uint64_t c0 = (uint64_t)tid * per;
+    const uint64_t c1 = min(nchunks, c0 + per);
+    uint32_t acc = 0;
+    if (c0 < c1) {
+        const uint32_t x64k = c_x8pow[16];                       // x^(8*65536)
+        for (uint64_t c = c0; c < c1; ++c) {
+            const uint64_t len = min((uint64_t)NZ_CRC_CHUNK, n - c * NZ_CRC_CHUNK);
+            const uint32_t mul = (len == NZ_CRC_CHUNK) ? x64k : gf_xpow8(len);
+            acc = (c == c0) ? chunks[c] : (gf_mul(mul, acc) ^ chunks[c]);
+        }
+        const uint64_t end = min(n, c1 * (uint64_t)NZ_CRC_CHUNK);
+        const uint64_t after = n - end;
+        if (after) acc = gf_mul(gf_xpow8(after), acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((tid & 31u) == 0) sred[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t r = 0;
+        for (int i = 0; i < 32; ++i) r ^= sred[i];
+        *whole_out = r;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_verify(const NzVerWork* __restrict__ ver, const uint32_t* __restrict__ counters, NzDevRes* res, const uint32_t* __restrict__ tables) {
+    __shared__ uint32_t sT[4 * 256];
+    __shared__ uint32_t sred[8];
+    for (uint32_t i = threadIdx.x; i < 1024; i += 256) sT[i] = tables[i];
+    __syncthreads();
+    const uint32_t n = counters[0];
+    for (uint32_t c = blockIdx.x; c < n; c += gridDim.x) {
+        const NzVerWork v = ver[c];
+        const uint32_t crc = block_crc32c_chunk(reinterpret_cast<const uint8_t*>(v.ptr), v.len, sT, sred);
+        if (threadIdx.x == 0 && crc != v.expect) res[v.req].status = NZ_ECORRUPT;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+cudaError_t nz_launch_lookup(const NzSlot* table, uint64_t line_mask, const NzDesc* descs, const uint64_t* keys,
+                             uint32_t n, nz_extent* out, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const uint32_t per_block = 64;
+    uint32_t grid = (n + per_block - 1) / per_block;
+    if (grid > 1184) grid = 1184;
+    k_lookup<<<grid, 256, 0, s>>>(table, line_mask, descs, keys, n, out);
+    return cudaGetLastError();
+}
+cudaError_t nz_launch_insert(NzSlot* table, uint64_t line_mask, uint64_t k0, uint64_t k1, uint32_t desc, uint64_t gen,
+                             int32_t* status, cudaStream_t s) {
+    k_insert<<<1, 32, 0, s>>>(table, line_mask, k0, k1, desc, gen, status);
+    return cudaGetLastError();
+}
+cudaError_t nz_launch_erase(NzSlot* table, uint64_t line_mask, uint64_t k0, uint64_t k1, int32_t* status, cudaStream_t s) {
+    k_erase<<<1, 32, 0, s>>>(table, line_mask, k0, k1, status);
+    return cudaGetLastError();
+}
+cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s) {
+    // rq_src / rq_len live right after the inflate work array (see nz_api.cu: device block layout)
+    uint64_t* rq_src = reinterpret_cast<uint64_t*>(a.infl + a.n);
+    uint64_t* rq_len = rq_src + a.n;
+    k_plan<<<1, 1024, 0, s>>>(a, rq_src, rq_len);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (a.ver_cap) {
+        k_plan_verify<<<1, 256, 0, s>>>(a);
+        e = cudaGetLastError();
+    }
+    return e;
+}
+cudaError_t nz_launch_gather(const NzSegWork* work, const uint64_t* tile_begin, uint32_t nseg, int grid, cudaStream_t s) {
+    k_gather<<<grid, NZ_GATHER_THREADS, 0, s>>>(work, tile_begin, nseg);
+    return cudaGetLastError();
+}
+cudaError_t nz_launch_verify(const NzVerWork* ver, const uint32_t* counters, NzDevRes* res, const uint32_t* crc_tables,
+                             int grid, cudaStream_t s) {
+    k_verify<<<grid, 256, 0, s>>>(ver, counters, res, crc_tables);
+    return cudaGetLastError();
+}
+cudaError_t nz_launch_crc_chunks(const uint8_t* p, uint64_t n, uint32_t* chunk_out, uint32_t* whole_out,
+                                 const uint32_t* crc_tables, int sm_count, cudaStream_t s) {
+    const uint64_t nchunks = (n + NZ_CRC_CHUNK - 1) / NZ_CRC_CHUNK;
+    if (nchunks) {
+        uint64_t grid = nchunks;
+        const uint64_t cap = (uint64_t)sm_count * 8;
+        if (grid > cap) grid = cap;
+        k_crc_chunks<<<(unsigned)grid, 256, 0, s>>>(p, n, chunk_out, crc_tables);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    k_crc_fold<<<1, 1024, 0, s>>>(chunk_out, n, whole_out);
+    return cudaGetLastError();
+}
+
+int nz_gather_blocks_per_sm() {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather, NZ_GATHER_THREADS, 0) != cudaSuccess || nb < 1) nb = 4;
+    return nb;
+}
+
+// host-side GF(2) helpers to fill the constant tables (independent of oracle/)
+static uint32_t h_gf_mul(uint32_t a, uint32_t b) { return gf_mul(a, b); }
+
+cudaError_t nz_upload_constants(uint32_t* crc_tables_dev) {
+    // x^(8 * 2^k): start from x^8 and square
+    uint32_t x8pow[48];
+    uint32_t p = 0x80000000u >> 8;     // x^8 (reflected: bit 31 is x^0)
+    for (int k = 0; k < 48; ++k) { x8pow[k] = p; p = h_gf_mul(p, p); }
+    cudaError_t e = cudaMemcpyToSymbol(c_x8pow, x8pow, sizeof x8pow);
+    if (e != cudaSuccess) return e;
+    // slice tables: [0..7] Castagnoli, [8..15] IEEE (gzip trailer CRC-32)
+    static uint32_t t[16 * 256];
+    const uint32_t polys[2] = {POLY_C, 0xEDB88320u};
+    for (int pi = 0; pi < 2; ++pi) {
+        uint32_t* T = t + pi * 8 * 256;
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ polys[pi] : c >> 1;
+            T[i] = c;
+        }
+        for (int s = 1; s < 8; ++s)
+            for (uint32_t i = 0; i < 256; ++i) T[s * 256 + i] = (T[(s - 1) * 256 + i] >> 8) ^ T[T[(s - 1) * 256 + i] & 0xff];
+    }
+    return cudaMemcpy(crc_tables_dev, t, sizeof t, cudaMemcpyHostToDevice);
+}

@@ -1,0 +1,302 @@
+"""-m gpu: the CUDA path, called through the C ABI, against the oracle on the same
+seeded inputs — bit-exact (byte/integer work).  SPEC rule ids from oracle/SPEC.md.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import nezha_b200 as nz
+from nezha_b200 import capi, workloads as wl
+from oracle import oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def zone():
+    z = nz.Zone(device=0, arena_bytes=3 << 30, max_objects=1 << 12)
+    yield z
+    z.close()
+
+
+def K(i, cfg="t"):
+    return wl.key128(wl.object_key_string(cfg, i))
+
+
+SIZES = [0, 1, 15, 16, 17, 127, 128, 129, 4095, 4096, 32767, 32768, 32769, 65535, 65536, 65537, 100_000, 1_000_003, 5 * 65536 + 7]
+
+
+@pytest.fixture(scope="module")
+def objects(zone):
+    objs = {}
+    for i, n in enumerate(SIZES):
+        d = wl.synth_bytes(n, seed=100 + i)
+        crc = zone.put(K(i), d)
+        objs[i] = (d, crc)
+    return objs
+
+
+def test_put_crc_matches_oracle_X1_X2(zone, objects):
+    for i, (d, crc) in objects.items():
+        assert crc == o.crc32c(d), (i, len(d))
+    ext = zone.lookup([K(i) for i in objects])
+    for i, e in zip(objects, ext):
+        assert e.status == capi.NZ_OK and e.stored_length == len(objects[i][0]) == e.raw_length
+        assert e.crc32c == objects[i][1] and e.flags == capi.NZ_ENC_IDENTITY
+
+
+def test_lookup_miss_and_hit_K1(zone, objects):
+    keys = [K(0), K(10_000), K(3), os.urandom(16)]
+    ext = zone.lookup(keys)
+    assert [e.status for e in ext] == [capi.NZ_OK, capi.NZ_ENOTFOUND, capi.NZ_OK, capi.NZ_ENOTFOUND]
+    # many keys in one launch (several probe groups per warp)
+    many = [K(i % len(SIZES)) if i % 3 else os.urandom(16) for i in range(1000)]
+    ext = zone.lookup(many)
+    for i, e in enumerate(ext):
+        assert (e.status == capi.NZ_OK) == bool(i % 3)
+
+
+@pytest.mark.parametrize("device_dst", [False, True])
+def test_full_get_bit_exact_B1(zone, objects, device_dst):
+    for i, (d, crc) in objects.items():
+        res, body = zone.get(K(i), device_dst=device_dst)
+        assert res.status == capi.NZ_OK and res.bytes == len(d) == res.length and res.crc32c == crc
+        assert body == o.serve_slice_mem(d, 0, len(d))
+
+
+def test_single_ranges_all_alignments_R8(zone, objects):
+    """Range starts at every byte phase (source misalignment 0..15 vs the 16 B vector path)."""
+    d, _ = objects[SIZES.index(1_000_003)]
+    key = K(SIZES.index(1_000_003))
+    rng = np.random.default_rng(9)
+    cases = [(s, l) for s in range(0, 18) for l in (1, 15, 16, 17, 100, 4097)]
+    cases += [(int(rng.integers(0, len(d) - 70000)), int(rng.integers(1, 70000))) for _ in range(60)]
+    cases += [(len(d) - 1, 1), (0, len(d)), (1, len(d) - 1), (32768 - 5, 10), (65536 - 1, 2)]
+    for s, l in cases:
+        res, body = zone.get(key, segs=[(s, l)])
+        assert res.status == capi.NZ_OK and res.bytes == l
+        assert body == o.serve_slice_mem(d, s, l), (s, l)
+
+
+def test_ranges_to_misaligned_destination(zone, objects):
+    """dst_off at arbitrary byte phases (multipart bodies put slices after part headers)."""
+    d, _ = objects[SIZES.index(1_000_003)]
+    key = K(SIZES.index(1_000_003))
+    buf = zone.alloc_host(400_000)
+    try:
+        for dphase in range(0, 17):
+            for sphase in (0, 1, 7, 16, 21):
+                view = buf.numpy()
+                view[:] = 0xEE
+                segs = [(1000 + sphase, 70_001, dphase), (500_000, 33_000, 100_000 + dphase), (5, 3, 200_000 + dphase)]
+                t = zone.submit([nz.Get(key, buf, segs)])
+                r = t.wait()[0]
+                t.free()
+                assert r.status == capi.NZ_OK and r.bytes == sum(s[1] for s in segs)
+                for so, ln, do in segs:
+                    assert view[do:do + ln].tobytes() == d[so:so + ln].tobytes(), (dphase, sphase, so)
+                    assert view[do - 1] == 0xEE if do else True
+                    assert view[do + ln] == 0xEE        # no write past a slice
+    finally:
+        buf.free()
+
+
+def test_multipart_plan_served_R9(zone, objects):
+    """Whole oracle plan -> product: host writes the literals, the device gathers the slices."""
+    idx = SIZES.index(5 * 65536 + 7)
+    d, _ = objects[idx]
+    ob = o.Obj(len(d), "application/octet-stream", '"abc"', "Wed, 07 Nov 2018 15:20:01 GMT")
+    for spec in ["bytes=0-0,-1", "bytes=5-70000,65536-131071,300000-", "bytes=1-2,4-5,7-8,10-11,13-14"]:
+        plan = o.parse_plan(o.plan(o.Req(range=spec), ob, boundary=7))
+        assert plan.status == 206
+        want = plan.body_bytes(d.tobytes())
+        buf = zone.alloc_host(len(want))
+        try:
+            segs, off = [], 0
+            view = buf.numpy()
+            for kind, v in plan.body:
+                if kind == "lit":
+                    view[off:off + len(v)] = np.frombuffer(v, dtype=np.uint8)
+                    off += len(v)
+                else:
+                    segs.append((v[0], v[1], off))
+                    off += v[1]
+            t = zone.submit([nz.Get(K(idx), buf, segs)])
+            r = t.wait()[0]
+            t.free()
+            assert r.status == capi.NZ_OK
+            assert view[:off].tobytes() == want
+            assert int(dict(plan.headers)["Content-Length"]) == off
+        finally:
+            buf.free()
+
+
+def test_wave_of_mixed_requests(zone, objects):
+    """64 concurrent GETs in one wave: hits, misses, bad ranges, small buffers."""
+    rng = np.random.default_rng(3)
+    gets, expect, bufs = [], [], []
+    for j in range(64):
+        i = int(rng.integers(0, len(SIZES)))
+        d = objects[i][0]
+        kind = j % 8
+        if kind == 0:                       # miss
+            b = zone.alloc_device(64)
+            gets.append(nz.Get(os.urandom(16), b)); expect.append((capi.NZ_ENOTFOUND, b""))
+        elif kind == 1 and len(d) > 1:      # range outside the object
+            b = zone.alloc_device(64)
+            gets.append(nz.Get(K(i), b, [(len(d) - 1, 2, 0)])); expect.append((capi.NZ_EINVAL, b""))
+        elif kind == 2 and len(d) > 8:      # destination too small
+            b = zone.alloc_device(8)
+            gets.append(nz.Get(K(i), b)); expect.append((capi.NZ_ERANGE, b""))
+        elif kind in (3, 4) and len(d) > 2:
+            s = int(rng.integers(0, len(d) - 1)); l = int(rng.integers(1, len(d) - s))
+            b = zone.alloc_device(l)
+            gets.append(nz.Get(K(i), b, [(s, l, 0)])); expect.append((capi.NZ_OK, d[s:s + l].tobytes()))
+        else:
+            b = zone.alloc_device(max(len(d), 1))
+            gets.append(nz.Get(K(i), b)); expect.append((capi.NZ_OK, d.tobytes()))
+        bufs.append(b)
+    t = zone.submit(gets)
+    res = t.wait()
+    assert t.elapsed_ms() >= 0 and t.gather_ms() >= 0
+    t.free()
+    for r, (st, body), b in zip(res, expect, bufs):
+        assert r.status == st
+        if st == capi.NZ_OK:
+            assert r.bytes == len(body) and b.bytes(0, len(body)) == body
+        else:
+            assert r.bytes == 0
+    for b in bufs:
+        b.free()
+
+
+def test_verify_flag_and_corruption_X4(zone):
+    d = wl.synth_bytes(300_000, seed=77)
+    key = K(900)
+    crc = zone.put(key, d, expected_crc32c=o.crc32c(d))
+    assert crc == o.crc32c(d)
+    res, body = zone.get(key, flags=capi.NZ_GET_VERIFY)
+    assert res.status == capi.NZ_OK and body == d.tobytes()
+    res, body = zone.get(key, segs=[(70_000, 10)], flags=capi.NZ_GET_VERIFY)
+    assert res.status == capi.NZ_OK and body == d[70_000:70_010].tobytes()
+    assert zone.debug_poke(key, 200_000, 0x40) == capi.NZ_OK      # flip a bit in chunk 3
+    res, _ = zone.get(key, segs=[(0, 65536)], flags=capi.NZ_GET_VERIFY)
+    assert res.status == capi.NZ_OK                                # chunk 0 untouched
+    res, _ = zone.get(key, segs=[(199_000, 2000)], flags=capi.NZ_GET_VERIFY)
+    assert res.status == capi.NZ_ECORRUPT
+    res, _ = zone.get(key, flags=capi.NZ_GET_VERIFY)
+    assert res.status == capi.NZ_ECORRUPT
+    res, body = zone.get(key)                                      # without verify: bytes as stored (reference behaviour)
+    assert res.status == capi.NZ_OK and body != d.tobytes()
+    assert zone.evict(key) == capi.NZ_OK
+
+
+def test_commit_rejects_wrong_crc(zone):
+    d = wl.synth_bytes(10_000, seed=5)
+    with pytest.raises(nz.NezhaError) as ei:
+        zone.put(K(901), d, expected_crc32c=o.crc32c(d) ^ 1)
+    assert ei.value.code == capi.NZ_ECORRUPT
+    assert zone.lookup([K(901)])[0].status == capi.NZ_ENOTFOUND    # nothing published
+    zone.put(K(901), d, expected_crc32c=o.crc32c(d))               # and the key is free again
+    with pytest.raises(nz.NezhaError) as ei:
+        zone.put(K(901), d)
+    assert ei.value.code == capi.NZ_EEXIST
+    assert zone.evict(K(901)) == capi.NZ_OK
+    assert zone.evict(K(901)) == capi.NZ_ENOTFOUND
+    assert zone.lookup([K(901)])[0].status == capi.NZ_ENOTFOUND
+
+
+def test_crc32c_device_kernel_K3(zone):
+    import torch
+    rng = np.random.default_rng(11)
+    for n in [1, 255, 256, 257, 65535, 65536, 65537, 1_000_000, 16 * 65536]:
+        h = rng.integers(0, 256, n, dtype=np.uint8)
+        t = torch.from_numpy(h).cuda()
+        crc, chunks = zone.crc32c_device(t.data_ptr(), n, want_chunks=True)
+        ochunks, owhole = o.crc32c_chunks(h, 65536)
+        assert crc == owhole == o.crc32c(h)
+        assert np.array_equal(chunks, ochunks)
+        if n > 17:   # unaligned device pointer takes the byte path
+            crc2 = zone.crc32c_device(t.data_ptr() + 1, n - 1)
+            assert crc2 == o.crc32c(h[1:])
+
+
+def test_table_churn_insert_evict(zone):
+    """Tombstones + re-insert keep every live key reachable (K1/K6)."""
+    live = {}
+    rng = np.random.default_rng(21)
+    for rnd in range(3):
+        for i in range(200):
+            k = K(5000 + rnd * 1000 + i, "churn")
+            d = wl.synth_bytes(int(rng.integers(1, 3000)), seed=i + rnd)
+            zone.put(k, d)
+            live[k] = d
+        victims = list(live)[::3]
+        for k in victims:
+            assert zone.evict(k) == capi.NZ_OK
+            del live[k]
+        ext = zone.lookup(list(live) + victims)
+        assert all(e.status == capi.NZ_OK for e in ext[:len(live)])
+        assert all(e.status == capi.NZ_ENOTFOUND for e in ext[len(live):])
+    for k, d in list(live.items())[:50]:
+        res, body = zone.get(k)
+        assert res.status == capi.NZ_OK and body == d.tobytes()
+    for k in live:
+        zone.evict(k)
+
+
+def test_c1_reference_object_roundtrip(zone):
+    """BASELINE config C1: the 169,001,437-byte object under the reference's own key;
+    size-independent properties at full size: CRC-of-chunks == whole CRC, slices == source."""
+    d = wl.synth_bytes(wl.C1_LENGTH, seed=1)
+    key = wl.key128(wl.C1_KEY)
+    assert key.hex() == "9c30938a380ef9a0ce26538a0f68408e"
+    crc = zone.put(key, d)
+    assert crc == o.crc32c(d)
+    res, body = zone.get(key, device_dst=True)
+    assert res.status == capi.NZ_OK and res.bytes == wl.C1_LENGTH
+    assert o.crc32c(body) == crc and body[-100:] == d[-100:].tobytes()
+    for s, l in [(0, 1), (wl.C1_LENGTH - 1, 1), (123_456_789, 1 << 20), (7, 33_333_333)]:
+        res, body = zone.get(key, segs=[(s, l)])
+        assert body == d[s:s + l].tobytes()
+    assert zone.evict(key) == capi.NZ_OK
+
+
+def test_put_file_fill_path(zone, tmp_path):
+    d = wl.synth_bytes(40 << 20, seed=8)      # spans the 16 MiB bounce buffers
+    f = tmp_path / "obj.bin"
+    f.write_bytes(d.tobytes())
+    fd = os.open(f, os.O_RDONLY)
+    try:
+        crc = zone.put_file(K(902), fd, len(d))
+    finally:
+        os.close(fd)
+    assert crc == o.crc32c(d)
+    res, body = zone.get(K(902), segs=[(16 << 20, 1 << 20)])
+    assert body == d[16 << 20:17 << 20].tobytes()
+    zone.evict(K(902))
+
+
+def test_sharded_zone_rejects_foreign_keys():
+    z = nz.Zone(device=0, arena_bytes=64 << 20, max_objects=256, shard_index=1, shard_count=4)
+    try:
+        mine = [K(i, "sh") for i in range(64) if z.owns(K(i, "sh"))]
+        other = [K(i, "sh") for i in range(64) if not z.owns(K(i, "sh"))]
+        assert mine and other
+        z.put(mine[0], b"abc")
+        with pytest.raises(nz.NezhaError) as ei:
+            z.put(other[0], b"abc")
+        assert ei.value.code == capi.NZ_EINVAL
+        st = [e.status for e in z.lookup([mine[0], other[0]])]
+        assert st == [capi.NZ_OK, capi.NZ_ENOTFOUND]
+    finally:
+        z.close()
+
+
+def test_stats_and_launch_count(zone, objects):
+    s0 = zone.stats()
+    zone.get(K(1))
+    s1 = zone.stats()
+    assert s1.gets == s0.gets + 1 and s1.hits == s0.hits + 1
+    assert s1.kernel_launches > s0.kernel_launches
