@@ -231,14 +231,19 @@ def run_ours(args):
     dbuf = zone.alloc_device(total)
     gets = [nz.Get(key, dbuf, [] if r is None else [(r[0], r[1], 0)], 0, offs[j]) for j, r in enumerate(reqs)]
     wave = zone.prepare(gets)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: handle 0 would mean "use the zone's stream pool" to the C ABI
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
+    assert sptr != 0
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()          # samples from warm-up through the timed loop (both run the same wave back to back)
     for _ in range(max(args.warmup, 3)):
         t = wave.submit(sptr)
         res = t.wait()
@@ -254,11 +259,9 @@ def run_ours(args):
         if got != data[s + l - n:s + l].tobytes():
             raise SystemExit("bench.py: served bytes differ from the source object")
 
-    sampler = ClockSampler(local)
     launches0 = zone.stats().kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    sampler.start()
     ev0.record(stream)
     tickets = [wave.submit(sptr) for _ in range(args.steps)]
     ev1.record(stream)
@@ -385,7 +388,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--object-bytes", type=int, default=1 << 30)

@@ -123,7 +123,7 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
 
 static void ticket_destroy(nz_ticket* t) {
     if (!t) return;
-    for (void* p : t->scratch) cudaFree(p);
+    if (t->scratch) cudaFree(t->scratch);
     if (t->pin) cudaFreeHost(t->pin);
     if (t->dev) cudaFree(t->dev);
     if (t->ev_start) cudaEventDestroy(t->ev_start);
@@ -578,7 +578,9 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
                 if (inflate || r.nseg == 0) ver_cap += all;
                 else for (uint32_t k = 0; k < r.nseg; ++k) ver_cap += std::min<uint64_t>(all, r.segs[k].len / NZ_CRC_CHUNK + 2);
             }
-            if (inflate && r.nseg != 0) scratch_need[i] = ho.raw_len;
+            // the LZ77 window is the output itself: it must live in HBM, so ranges and host
+            // destinations inflate into device scratch first and are then gathered out
+            if (inflate && (r.nseg != 0 || r.dst->kind != NZ_BUF_DEVICE)) scratch_need[i] = ho.raw_len;
         }
     }
     if (ver_cap > 0xfffffff0ull) return NZ_EINVAL;
@@ -591,7 +593,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     const size_t dev_ver = round_up((size_t)ver_cap * sizeof(NzVerWork), 256);
     const size_t dev_cnt = 256;
     const size_t dev_infl = (size_t)n * sizeof(NzInflWork);      // followed directly by rq_src, rq_len
-    const size_t dev_rq = (size_t)n * 16;
+    const size_t dev_rq = (size_t)n * 24;                        // rq_src, rq_len, infl_meta
     nz_ticket* t = ticket_acquire(c, pin_reqs + pin_segs + pin_res, dev_work + dev_tiles + dev_ver + dev_cnt + round_up(dev_infl + dev_rq, 256));
     if (!t) { cudaGetLastError(); snprintf(tl_err, sizeof tl_err, "ticket allocation failed"); return NZ_ENOMEM; }
     t->n = n; t->nseg = (uint32_t)nseg;
@@ -599,6 +601,22 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     NzDevReq* hreq = reinterpret_cast<NzDevReq*>(t->pin);
     NzDevSeg* hseg = reinterpret_cast<NzDevSeg*>((char*)t->pin + pin_reqs);
     NzDevRes* hres = reinterpret_cast<NzDevRes*>((char*)t->pin + pin_reqs + pin_segs);
+    if (any_inflate) {
+        size_t need = 0;
+        for (uint32_t i = 0; i < n; ++i) if (scratch_need[i]) need += round_up(scratch_need[i] + 256, 256);
+        if (need > t->scratch_cap) {
+            if (t->scratch) cudaFree(t->scratch);
+            t->scratch = nullptr; t->scratch_cap = 0;
+            if (cudaMalloc(&t->scratch, need) != cudaSuccess) {
+                cudaGetLastError();
+                nz_ticket_free(t);
+                snprintf(tl_err, sizeof tl_err, "inflate scratch allocation of %zu bytes failed", need);
+                return NZ_ENOMEM;
+            }
+            t->scratch_cap = need;
+        }
+    }
+    size_t scratch_off = 0;
     uint32_t sb = 0;
     for (uint32_t i = 0; i < n; ++i) {
         const nz_get_req& r = reqs[i];
@@ -612,14 +630,9 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
         d.nseg = r.nseg ? r.nseg : 1;
         d.scratch = 0; d.scratch_cap = 0;
         if (any_inflate && scratch_need[i]) {
-            void* sp = nullptr;
-            if (cudaMalloc(&sp, scratch_need[i] + 512) == cudaSuccess) {
-                t->scratch.push_back(sp);
-                d.scratch = (uint64_t)(uintptr_t)sp;
-                d.scratch_cap = scratch_need[i];
-            } else {
-                cudaGetLastError();
-            }
+            d.scratch = (uint64_t)(uintptr_t)((char*)t->scratch + scratch_off);
+            d.scratch_cap = scratch_need[i];
+            scratch_off += round_up(scratch_need[i] + 256, 256);
         }
         if (r.nseg == 0) {
             hseg[sb].src_off = 0; hseg[sb].len = 0; hseg[sb].dst_off = 0; hseg[sb].req = i; hseg[sb].pad = 0;
@@ -645,6 +658,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     a.ver_cap = (uint32_t)ver_cap;
     a.counters = reinterpret_cast<uint32_t*>(dv + dev_work + dev_tiles + dev_ver);
     a.infl = reinterpret_cast<NzInflWork*>(dv + dev_work + dev_tiles + dev_ver + dev_cnt);
+    a.infl_meta = reinterpret_cast<uint64_t*>(a.infl + n) + 2 * (size_t)n;   // after rq_src, rq_len
 
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : c->streams[c->rr.fetch_add(1) % c->streams.size()];
     t->stream = s;
@@ -655,8 +669,8 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     CKT(nz_launch_plan(a, s));
     c->launches += a.ver_cap ? 2 : 1;
     if (any_inflate) {
-        CKT(nz_launch_inflate(a.infl, a.counters, a.res, c->crc_tables, c->inflate_grid, s));
-        c->launches += 1;
+        CKT(nz_launch_inflate(a.infl, a.infl_meta, a.counters, a.res, c->crc_tables, c->inflate_grid, c->sm_count, s));
+        c->launches += 2;
     }
     CKT(cudaEventRecord(t->ev_g0, s));
     CKT(nz_launch_gather(a.work, a.tile_begin, a.nseg, c->gather_grid, s));
@@ -733,8 +747,6 @@ int32_t nz_ticket_free(nz_ticket* t) {
     nz_ctx* c = t->ctx;
     cudaSetDevice(c->device);
     cudaEventSynchronize(t->ev_done);   // never recycle buffers a kernel may still read
-    for (void* p : t->scratch) cudaFree(p);
-    t->scratch.clear();
     t->req_bytes_hint = 0;
     t->stream = nullptr;
     std::lock_guard<std::mutex> g(c->tmu);

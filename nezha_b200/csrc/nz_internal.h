@@ -129,7 +129,7 @@ struct nz_ticket {
     void* pin = nullptr; void* pin_dev = nullptr; size_t pin_cap = 0;
     // device block: segwork | tile prefix | verify work | inflate work | counters
     void* dev = nullptr; size_t dev_cap = 0;
-    std::vector<void*> scratch;        // inflate scratch (arena-independent cudaMalloc'd, returned at free)
+    void* scratch = nullptr; size_t scratch_cap = 0;   // inflate scratch (grow-only, reused across waves)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_done = nullptr, ev_g0 = nullptr, ev_g1 = nullptr;
     bool own_stream = false;
@@ -195,7 +195,8 @@ struct NzPlanArgs {
     NzVerWork* ver;             // capacity ver_cap
     uint32_t ver_cap;
     NzInflWork* infl;           // capacity n
-    uint32_t* counters;         // [0]=n_ver [1]=n_infl
+    uint32_t* counters;         // [0]=n_ver [1]=n_infl [2]=inflate work-steal cursor
+    uint64_t* infl_meta;        // n: (produced length << 32) | trailer CRC-32, written by k_inflate
 };
 cudaError_t nz_launch_lookup(const NzSlot* table, uint64_t line_mask, const NzDesc* descs, const uint64_t* keys,
                              uint32_t n, nz_extent* out, cudaStream_t s);
@@ -208,8 +209,9 @@ cudaError_t nz_launch_verify(const NzVerWork* ver, const uint32_t* counters, NzD
                              int grid, cudaStream_t s);
 cudaError_t nz_launch_crc_chunks(const uint8_t* p, uint64_t n, uint32_t* chunk_out, uint32_t* whole_out,
                                  const uint32_t* crc_tables, int sm_count, cudaStream_t s);
-cudaError_t nz_launch_inflate(const NzInflWork* infl, const uint32_t* counters, NzDevRes* res, const uint32_t* crc_tables,
-                              int grid, cudaStream_t s);
+cudaError_t nz_launch_inflate(const NzInflWork* infl, uint64_t* meta, uint32_t* counters, NzDevRes* res,
+                              const uint32_t* crc_tables, int grid, int sm_count, cudaStream_t s);
 cudaError_t nz_upload_constants(uint32_t* crc_tables_dev);
+cudaError_t nz_inflate_upload_constants();
 int nz_gather_blocks_per_sm();
 int nz_inflate_blocks_per_sm();

@@ -15,11 +15,7 @@
 #include <stdint.h>
 
 #include "nz_internal.h"
-
-#define POLY_C 0x82F63B78u
-
-// x^(8 * 2^k) mod P (reflected), k = 0..47; filled by nz_upload_constants.
-__constant__ uint32_t c_x8pow[48];
+#include "nz_crc.cuh"
 
 // ---------------------------------------------------------------------------
 // small PTX helpers
@@ -455,70 +451,8 @@ k_gather(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_b
 }
 
 // ---------------------------------------------------------------------------
-// K3: CRC-32C.  GF(2) helpers (zlib's multmodp restated for the Castagnoli
-// polynomial, reflected bit order: x^0 = 0x80000000).
+// K3: CRC-32C chunk table + whole-object fold (device code in nz_crc.cuh)
 // ---------------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint32_t gf_mul(uint32_t a, uint32_t b) {
-    uint32_t p = 0;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        p ^= b & (0u - ((a >> (31 - i)) & 1u));
-        b = (b >> 1) ^ (POLY_C & (0u - (b & 1u)));
-    }
-    return p;
-}
-__device__ __forceinline__ uint32_t gf_xpow8(uint64_t nbytes) {   // x^(8*nbytes)
-    uint32_t p = 0x80000000u;
-    int k = 0;
-    while (nbytes) {
-        if (nbytes & 1) p = gf_mul(c_x8pow[k], p);
-        nbytes >>= 1;
-        ++k;
-    }
-    return p;
-}
-
-// CRC-32C of one chunk (<= 64 KiB) by a 256-thread CTA: thread t owns bytes
-// [256 t, 256 t + 256), slice-by-4 from shared tables, then the per-thread CRCs
-// are shifted to the chunk end (multiply by x^(8*bytes_after)) and XOR-reduced.
-// sT: 4 x 256 u32 tables in shared memory; sred: 8 u32.
-__device__ uint32_t block_crc32c_chunk(const uint8_t* __restrict__ p, uint32_t m, const uint32_t* sT, uint32_t* sred) {
-    const uint32_t tid = threadIdx.x;
-    const uint32_t beg = tid * 256u;
-    uint32_t contrib = 0;
-    if (beg < m) {
-        const uint32_t cnt = min(256u, m - beg);
-        const uint8_t* q = p + beg;
-        uint32_t crc = 0xFFFFFFFFu;
-        uint32_t i = 0;
-        if ((((uintptr_t)q) & 15u) == 0) {
-            for (; i + 16 <= cnt; i += 16) {
-                const uint4 v = ldg_cached(q + i);
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    crc ^= w[j];
-                    crc = sT[3 * 256 + (crc & 0xff)] ^ sT[2 * 256 + ((crc >> 8) & 0xff)] ^
-                          sT[1 * 256 + ((crc >> 16) & 0xff)] ^ sT[crc >> 24];
-                }
-            }
-        }
-        for (; i < cnt; ++i) crc = (crc >> 8) ^ sT[(crc ^ q[i]) & 0xff];
-        crc = ~crc;
-        const uint32_t after = m - (beg + cnt);
-        contrib = after ? gf_mul(gf_xpow8(after), crc) : crc;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) contrib ^= __shfl_xor_sync(0xffffffffu, contrib, o);
-    __syncthreads();                       // sred reuse across calls
-    if ((tid & 31u) == 0) sred[tid >> 5] = contrib;
-    __syncthreads();
-    uint32_t r = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) r ^= sred[i];
-    return r;
-}
-
 __global__ void __launch_bounds__(256)
 k_crc_chunks(const uint8_t* __restrict__ p, uint64_t n, uint32_t* __restrict__ chunk_out, const uint32_t* __restrict__ tables) {
     __shared__ uint32_t sT[4 * 256];
@@ -529,7 +463,7 @@ k_crc_chunks(const uint8_t* __restrict__ p, uint64_t n, uint32_t* __restrict__ c
     for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
         const uint64_t off = c * NZ_CRC_CHUNK;
         const uint32_t m = (uint32_t)min((uint64_t)NZ_CRC_CHUNK, n - off);
-        const uint32_t crc = block_crc32c_chunk(p + off, m, sT, sred);
+        const uint32_t crc = block_crc_chunk<0>(p + off, m, sT, sred);
         if (threadIdx.x == 0) chunk_out[c] = crc;
     }
 }
@@ -546,15 +480,15 @@ k_crc_fold(const uint32_t* __restrict__ chunks, uint64_t n, uint32_t* __restrict
     const uint64_t c1 = min(nchunks, c0 + per);
     uint32_t acc = 0;
     if (c0 < c1) {
-        const uint32_t x64k = c_x8pow[16];                       // x^(8*65536)
+        const uint32_t x64k = c_x8pow[0][16];                       // x^(8*65536)
         for (uint64_t c = c0; c < c1; ++c) {
             const uint64_t len = min((uint64_t)NZ_CRC_CHUNK, n - c * NZ_CRC_CHUNK);
-            const uint32_t mul = (len == NZ_CRC_CHUNK) ? x64k : gf_xpow8(len);
-            acc = (c == c0) ? chunks[c] : (gf_mul(mul, acc) ^ chunks[c]);
+            const uint32_t mul = (len == NZ_CRC_CHUNK) ? x64k : gf_xpow8<0>(len);
+            acc = (c == c0) ? chunks[c] : (gf_mul<0>(mul, acc) ^ chunks[c]);
         }
         const uint64_t end = min(n, c1 * (uint64_t)NZ_CRC_CHUNK);
         const uint64_t after = n - end;
-        if (after) acc = gf_mul(gf_xpow8(after), acc);
+        if (after) acc = gf_mul<0>(gf_xpow8<0>(after), acc);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, o);
@@ -576,7 +510,7 @@ k_verify(const NzVerWork* __restrict__ ver, const uint32_t* __restrict__ counter
     const uint32_t n = counters[0];
     for (uint32_t c = blockIdx.x; c < n; c += gridDim.x) {
         const NzVerWork v = ver[c];
-        const uint32_t crc = block_crc32c_chunk(reinterpret_cast<const uint8_t*>(v.ptr), v.len, sT, sred);
+        const uint32_t crc = block_crc_chunk<0>(reinterpret_cast<const uint8_t*>(v.ptr), v.len, sT, sred);
         if (threadIdx.x == 0 && crc != v.expect) res[v.req].status = NZ_ECORRUPT;
     }
 }
@@ -645,19 +579,14 @@ int nz_gather_blocks_per_sm() {
     return nb;
 }
 
-// host-side GF(2) helpers to fill the constant tables (independent of oracle/)
-static uint32_t h_gf_mul(uint32_t a, uint32_t b) { return gf_mul(a, b); }
-
 cudaError_t nz_upload_constants(uint32_t* crc_tables_dev) {
-    // x^(8 * 2^k): start from x^8 and square
-    uint32_t x8pow[48];
-    uint32_t p = 0x80000000u >> 8;     // x^8 (reflected: bit 31 is x^0)
-    for (int k = 0; k < 48; ++k) { x8pow[k] = p; p = h_gf_mul(p, p); }
-    cudaError_t e = cudaMemcpyToSymbol(c_x8pow, x8pow, sizeof x8pow);
+    cudaError_t e = nz_crc_upload_constants();
+    if (e != cudaSuccess) return e;
+    e = nz_inflate_upload_constants();
     if (e != cudaSuccess) return e;
     // slice tables: [0..7] Castagnoli, [8..15] IEEE (gzip trailer CRC-32)
     static uint32_t t[16 * 256];
-    const uint32_t polys[2] = {POLY_C, 0xEDB88320u};
+    const uint32_t polys[2] = {NZ_POLY_C, NZ_POLY_IEEE};
     for (int pi = 0; pi < 2; ++pi) {
         uint32_t* T = t + pi * 8 * 256;
         for (uint32_t i = 0; i < 256; ++i) {
