@@ -167,6 +167,7 @@ int32_t nz_get_wait(nz_ticket* t, int64_t timeout_us, nz_get_res* res);
 int32_t nz_get_poll(nz_ticket* t);                 /* NZ_OK done, NZ_ETIMEOUT not yet */
 int32_t nz_ticket_elapsed_ms(nz_ticket* t, float* ms);  /* device time of the wave */
 int32_t nz_ticket_gather_ms(nz_ticket* t, float* ms);   /* device time of its gather kernel (K2) alone */
+int32_t nz_ticket_inflate_ms(nz_ticket* t, float* ms);  /* device time of its inflate kernels (K4); 0 if none ran */
 int32_t nz_ticket_free(nz_ticket* t);
 
 int32_t nz_get_stats(nz_ctx* ctx, nz_stats* out);

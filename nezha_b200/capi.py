@@ -25,7 +25,7 @@ SYMBOLS = [
     "nz_buf_alloc", "nz_buf_wrap_device", "nz_buf_ptr", "nz_buf_devptr", "nz_buf_size", "nz_buf_free", "nz_buf_read", "nz_buf_write",
     "nz_put_begin", "nz_put_write", "nz_put_write_device", "nz_put_file", "nz_put_commit", "nz_put_abort",
     "nz_evict", "nz_lookup", "nz_get_submit", "nz_get_wait", "nz_get_poll", "nz_ticket_elapsed_ms",
-    "nz_ticket_gather_ms", "nz_ticket_free", "nz_get_stats", "nz_crc32c_device", "nz_debug_poke", "nz_shard_of",
+    "nz_ticket_gather_ms", "nz_ticket_inflate_ms", "nz_ticket_free", "nz_get_stats", "nz_crc32c_device", "nz_debug_poke", "nz_shard_of",
 ]
 
 
@@ -117,6 +117,7 @@ def load() -> C.CDLL:
     L.nz_get_poll.argtypes = [vp]
     L.nz_ticket_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.nz_ticket_gather_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.nz_ticket_inflate_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.nz_ticket_free.argtypes = [vp]
     L.nz_debug_poke.argtypes = [vp, u8p, C.c_uint64, C.c_uint8]
     L.nz_get_stats.argtypes = [vp, C.POINTER(Stats)]

@@ -130,6 +130,8 @@ static void ticket_destroy(nz_ticket* t) {
     if (t->ev_done) cudaEventDestroy(t->ev_done);
     if (t->ev_g0) cudaEventDestroy(t->ev_g0);
     if (t->ev_g1) cudaEventDestroy(t->ev_g1);
+    if (t->ev_i0) cudaEventDestroy(t->ev_i0);
+    if (t->ev_i1) cudaEventDestroy(t->ev_i1);
     delete t;
 }
 
@@ -526,7 +528,8 @@ static nz_ticket* ticket_acquire(nz_ctx* c, size_t pin_need, size_t dev_need) {
         if (!t) return nullptr;
         t->ctx = c;
         if (cudaEventCreate(&t->ev_start) != cudaSuccess || cudaEventCreate(&t->ev_done) != cudaSuccess ||
-            cudaEventCreate(&t->ev_g0) != cudaSuccess || cudaEventCreate(&t->ev_g1) != cudaSuccess) { ticket_destroy(t); return nullptr; }
+            cudaEventCreate(&t->ev_g0) != cudaSuccess || cudaEventCreate(&t->ev_g1) != cudaSuccess ||
+            cudaEventCreate(&t->ev_i0) != cudaSuccess || cudaEventCreate(&t->ev_i1) != cudaSuccess) { ticket_destroy(t); return nullptr; }
     }
     if (t->pin_cap < pin_need) {
         if (t->pin) cudaFreeHost(t->pin);
@@ -668,8 +671,11 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     CKT(cudaMemsetAsync(a.counters, 0, 16, s));
     CKT(nz_launch_plan(a, s));
     c->launches += a.ver_cap ? 2 : 1;
+    t->ran_inflate = any_inflate;
     if (any_inflate) {
+        CKT(cudaEventRecord(t->ev_i0, s));
         CKT(nz_launch_inflate(a.infl, a.infl_meta, a.counters, a.res, c->crc_tables, c->inflate_grid, c->sm_count, s));
+        CKT(cudaEventRecord(t->ev_i1, s));
         c->launches += 2;
     }
     CKT(cudaEventRecord(t->ev_g0, s));
@@ -739,6 +745,14 @@ int32_t nz_ticket_elapsed_ms(nz_ticket* t, float* ms) {
 int32_t nz_ticket_gather_ms(nz_ticket* t, float* ms) {
     if (!t || !ms) return NZ_EINVAL;
     CK(cudaEventElapsedTime(ms, t->ev_g0, t->ev_g1));
+    return NZ_OK;
+}
+
+int32_t nz_ticket_inflate_ms(nz_ticket* t, float* ms) {
+    if (!t || !ms) return NZ_EINVAL;
+    *ms = 0.f;
+    if (!t->ran_inflate) return NZ_OK;
+    CK(cudaEventElapsedTime(ms, t->ev_i0, t->ev_i1));
     return NZ_OK;
 }
 

@@ -131,7 +131,8 @@ struct nz_ticket {
     void* dev = nullptr; size_t dev_cap = 0;
     void* scratch = nullptr; size_t scratch_cap = 0;   // inflate scratch (grow-only, reused across waves)
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_done = nullptr, ev_g0 = nullptr, ev_g1 = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_done = nullptr, ev_g0 = nullptr, ev_g1 = nullptr, ev_i0 = nullptr, ev_i1 = nullptr;
+    bool ran_inflate = false;
     bool own_stream = false;
     uint64_t req_bytes_hint = 0;
 };

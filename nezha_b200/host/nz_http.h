@@ -1,0 +1,102 @@
+// nezha_b200/host/nz_http.h — host-side HTTP semantics of the cache-hit path.
+//
+// This is PRODUCT code (the compiled stand-in for the Go handler north_star asks
+// for; `go` is absent from the image): what nginx does around the body loop for
+// the vhosts of /root/reference/examples/demo/nginx.conf — pick the server block,
+// gate the method, build "$host/$proxy_host$uri", evaluate conditionals and Range,
+// and lay the response out as literals (written by the host) and slices (gathered
+// by the GPU through include/nezha_gpu.h).  Rule ids in comments (K1, R4, C6 ...)
+// are the numbered rules of the behaviour being matched; tests diff this layer
+// against the independent CPU restatement.
+#pragma once
+#include <cstdint>
+#include <optional>
+#include <string>
+#include <string_view>
+#include <utility>
+#include <vector>
+
+namespace nzh {
+
+struct VHost {
+    std::string server_name;   // nginx.conf:45 etc.
+    std::string proxy_host;    // host[:port] of proxy_pass, port only when not the scheme default
+    bool upstream_tls = false; // nginx.conf:113 (https://storage.googleapis.com)
+};
+
+struct Config {
+    std::vector<VHost> vhosts;           // first entry is the implicit default server
+    bool gunzip = false;                 // operator switch for inflate-on-hit (new behaviour)
+    static Config reference_default();   // the five live server blocks of examples/demo/nginx.conf
+    int select(std::string_view host_lower) const;
+};
+
+struct Request {
+    std::string method;
+    std::string target;                  // raw request-line target
+    int http_minor = 1;                  // -1 = HTTP/0.9
+    std::optional<std::string> host, range, if_range, if_none_match, if_match, if_modified_since,
+        if_unmodified_since, accept_encoding;
+};
+
+struct ObjectMeta {
+    uint64_t stored_length = 0;
+    int64_t raw_length = -1;             // inflated length when stored gzip and known
+    std::string content_type;
+    std::optional<std::string> etag, last_modified;
+    bool stored_gzip = false;
+};
+
+struct Part {
+    bool literal = false;
+    std::string bytes;                   // literal
+    uint64_t off = 0, len = 0;           // slice of the served representation
+};
+
+struct Plan {
+    int status = 0;
+    bool head = false, inflated = false, bypass = false;
+    std::vector<std::pair<std::string, std::string>> headers;
+    std::vector<Part> body;
+    uint64_t body_length() const;
+    std::string to_text() const;         // canonical text form used by the parity tests
+};
+
+// MD5 (RFC 1321): cache identity of the key string (nginx.conf:38)
+void md5(const void* data, size_t n, uint8_t out[16]);
+
+// "$host/$proxy_host$uri" (nginx.conf:56); nullopt = 400 Bad Request.  vhost_out gets the block index.
+std::optional<std::string> cache_key(const Config& cfg, const std::optional<std::string>& host_header,
+                                     std::string_view target, int* vhost_out);
+
+bool method_allowed(std::string_view method);   // nginx.conf:47-49 (unanchored GET|HEAD regex)
+
+struct ByteRange { int64_t start, end; };       // [start, end)
+enum class RangeVerdict { Ok, Ignore, Unsatisfiable };
+RangeVerdict parse_ranges(std::string_view spec_after_bytes_eq, int64_t length, std::vector<ByteRange>& out,
+                          size_t max_ranges = 64);
+
+int64_t parse_http_date(std::string_view s);    // seconds since the epoch, -1 if unparseable
+
+Plan plan_response(const Config& cfg, const Request& rq, const ObjectMeta& ob, uint64_t boundary);
+
+}  // namespace nzh
+
+// C view for the ctypes parity tests and for the proxy binary
+extern "C" {
+int nzh_cache_key(const char* host_hdr, const char* target, char* out, size_t cap);   // length or -400
+int nzh_method_allowed(const char* method);
+int nzh_parse_ranges(const char* spec, int64_t length, int64_t* out_pairs, int max_pairs, int* n_out);   // 0 ok,1 ignore,416
+int64_t nzh_parse_http_date(const char* s, size_t n);
+void nzh_md5(const void* data, size_t n, uint8_t out[16]);
+struct nzh_request {
+    const char* method; int http_minor;
+    const char *range, *if_range, *if_none_match, *if_match, *if_modified_since, *if_unmodified_since, *accept_encoding;
+};
+struct nzh_object {
+    int64_t stored_length, raw_length;
+    const char *content_type, *etag, *last_modified, *content_encoding;
+    int gunzip_enabled;
+};
+int nzh_plan_text(const nzh_request* rq, const nzh_object* ob, uint64_t boundary, char* out, size_t cap);
+}

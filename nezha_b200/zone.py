@@ -95,6 +95,11 @@ class Ticket:
         check(self.zone.L.nz_ticket_gather_ms(self.h, C.byref(ms)), "nz_ticket_gather_ms")
         return ms.value
 
+    def inflate_ms(self) -> float:
+        ms = C.c_float()
+        check(self.zone.L.nz_ticket_inflate_ms(self.h, C.byref(ms)), "nz_ticket_inflate_ms")
+        return ms.value
+
     def free(self):
         if self.h:
             self.zone.L.nz_ticket_free(self.h)

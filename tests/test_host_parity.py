@@ -1,0 +1,109 @@
+"""-m "not gpu": the product's host layer (nezha_b200/host/nz_http.cc) against the
+oracle restatement (oracle/nz_oracle.c) — two independent implementations of the
+same rules (oracle/SPEC.md K, V, C, R, G, E), diffed on KATs and on generated input."""
+import hashlib
+import string
+
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+from nezha_b200 import hostlib as h
+from oracle import oracle as o
+
+SET = settings(max_examples=400, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+
+
+def test_md5_matches():
+    for n in (0, 1, 55, 56, 63, 64, 65, 119, 120, 1000):
+        d = bytes((7 * i + 3) & 0xFF for i in range(n))
+        assert h.md5(d) == o.md5(d) == hashlib.md5(d).digest()
+
+
+def test_reference_key():
+    k = h.cache_key("www.cs.toronto.edu", "/~kriz/cifar-100-python.tar.gz")
+    assert k == b"www.cs.toronto.edu/www.cs.toronto.edu/~kriz/cifar-100-python.tar.gz"
+    assert h.md5(k).hex() == "9c30938a380ef9a0ce26538a0f68408e"
+
+
+HOSTS = ["www.cs.toronto.edu", "WWW.CS.TORONTO.EDU:80", "yann.lecun.com.", "storage.googleapis.com", "example.org",
+         "images.cocodataset.org:8080", "download.tensorflow.org", "[::1]:80", "bad host", "", None, "a/b", "x:y:z"]
+path_chars = st.sampled_from(list("ab/.%?#2F0e~-_ ") + ["%2e", "%2F", "%00", "%zz", "..", "//", "/./", "%41"])
+
+
+@SET
+@given(st.sampled_from(HOSTS), st.lists(path_chars, max_size=14).map("".join), st.booleans())
+def test_cache_key_differential(host, tail, absolute):
+    target = "/" + tail
+    if absolute:
+        target = "http://yann.lecun.com" + target
+    assert h.cache_key(host, target) == o.cache_key(host, target), (host, target)
+
+
+def test_cache_key_cases():
+    for host, target in [("x", "/a/.."), ("x", "/a/."), ("x", "/.."), ("x", "//"), ("x", "/a//b/"), ("x", "a"), ("x", ""),
+                         ("x", "/%2e%2e/a"), ("x", "/a/%2E%2E"), ("x", "/a%2Fb/../c"), ("x", "http://h"), ("x", "HTTPS://H:443/p?q"),
+                         ("x", "/a?b/../c"), ("x", "/a#b"), ("x", "/%"), ("x", "/%4")]:
+        assert h.cache_key(host, target) == o.cache_key(host, target), (host, target)
+
+
+@SET
+@given(st.text(alphabet="GETHADPOSTgeth X", max_size=8))
+def test_method_gate_differential(m):
+    assert h.method_allowed(m) == o.method_gate(m)
+
+
+range_tok = st.sampled_from(["0", "1", "5", "99", "100", "999", "1000", "1001", "65535", "9223372036854775807",
+                             "9223372036854775808", "99999999999999999999", "-", ",", " ", "  ", "a", "x", "-5", "0-", "-0"])
+
+
+@SET
+@given(st.lists(range_tok, max_size=9).map("".join), st.sampled_from([0, 1, 2, 100, 1000, 1 << 40]))
+def test_range_parse_differential(spec, length):
+    rc_o, rg_o = o.range_parse(spec, length)
+    rc_h, rg_h = h.parse_ranges(spec, length)
+    assert rc_h == rc_o, (spec, length)
+    if rc_o == 0:
+        assert rg_h == rg_o, (spec, length)
+
+
+DATES = ["Sun, 06 Nov 1994 08:49:37 GMT", "Sunday, 06-Nov-94 08:49:37 GMT", "Sun Nov  6 08:49:37 1994",
+         "Wed, 07 Nov 2018 15:20:01 GMT", "Wed, 07 Nov 2018 15:20:02 GMT", "Tue, 29 Feb 2000 12:00:00 GMT",
+         "Mon, 29 Feb 2001 12:00:00 GMT", "Thu, 31 Apr 2020 00:00:00 GMT", "Thu, 01 Jan 1970 00:00:00 GMT",
+         "Fri, 31 Dec 1999 23:59:60 GMT", "Sat, 01 Jan 2000 24:00:00 GMT", "Sun Nov 16 08:49:37 1994",
+         "Sunday, 06-Nov-69 08:49:37 GMT", "Sunday, 06-Nov-70 08:49:37 GMT", "garbage", "", "Sun, 06 Nov 1994",
+         "Sun, 6 Nov 1994 08:49:37 GMT", "Sun, 06 Nox 1994 08:49:37 GMT", "Sun, 06-Nov 1994 08:49:37 GMT"]
+
+
+def test_http_date_differential():
+    for d in DATES:
+        assert h.parse_http_date(d) == o.parse_http_time(d), d
+
+
+@SET
+@given(st.text(alphabet=string.ascii_letters + string.digits + " ,:-", max_size=34))
+def test_http_date_fuzz(d):
+    assert h.parse_http_date(d) == o.parse_http_time(d), d
+
+
+ETAGS = [None, '"abc"', 'W/"abc"', '"5be2f2c5-a12c15d"', ""]
+ETAG_LISTS = [None, "*", '"abc"', 'W/"abc"', '"x", "abc"', '"x","abc"', '"abc" , "y"', '"abcd"', 'W/"x", W/"abc"', "", " ", '"ab', 'abc',
+              '"5be2f2c5-a12c15d"', "W/", ",", '"abc"x']
+RANGES = [None, "bytes=0-0", "bytes=-1", "bytes=5-", "bytes=0-9,20-29", "bytes=10-5", "bytes=2000-", "BYTES=1-2", "bytes=", "bytes=0-",
+          "items=0-1", "bytes=0-999,0-999", "bytes= 1 - 2 ,-3", "bytes=0-0,0-0,0-0", "bytes=a", "bytes=-0", "bytes=99999999999999999999-"]
+IF_RANGES = [None, '"abc"', 'W/"abc"', "Wed, 07 Nov 2018 15:20:01 GMT", "Wed, 07 Nov 2018 15:20:02 GMT", "junk", '"']
+LMS = [None, "Wed, 07 Nov 2018 15:20:01 GMT", "not a date"]
+
+
+@SET
+@given(st.sampled_from(["GET", "HEAD", "POST", "XGET", "get"]), st.sampled_from([-1, 0, 1]), st.sampled_from(RANGES),
+       st.sampled_from(IF_RANGES), st.sampled_from(ETAG_LISTS), st.sampled_from(ETAG_LISTS), st.sampled_from([None] + DATES[:6]),
+       st.sampled_from([None] + DATES[:6]), st.sampled_from([None, "gzip", "gzip, deflate", "identity", "GZIP"]),
+       st.sampled_from([0, 1, 10, 1000]), st.sampled_from(ETAGS), st.sampled_from(LMS), st.sampled_from(["", "application/x-gzip", "text/plain"]),
+       st.sampled_from([None, "gzip", "GZIP", "br"]), st.sampled_from([-1, 0, 5000]), st.booleans(), st.integers(0, 2**63))
+def test_plan_differential(method, minor, rng, if_range, inm, im, ims, ius, ae, slen, etag, lm, ctype, cenc, rawlen, gunzip, bnd):
+    rq = o.Req(method, minor, rng, if_range, inm, im, ims, ius, ae)
+    ob = o.Obj(slen, ctype, etag, lm, cenc, rawlen, gunzip)
+    want = o.plan(rq, ob, bnd)
+    got = h.plan_text(method, minor, rng, if_range, inm, im, ims, ius, ae, stored_length=slen, raw_length=rawlen,
+                      content_type=ctype, etag=etag, last_modified=lm, content_encoding=cenc, gunzip_enabled=gunzip, boundary=bnd)
+    assert got == want, (rq, ob)
