@@ -45,6 +45,9 @@ extern "C" {
 /* ---- object flags (stored) --------------------------------------------- */
 #define NZ_ENC_IDENTITY 0u
 #define NZ_ENC_GZIP     1u    /* stored bytes are one RFC 1952 member             */
+#define NZ_ENC_STRIPE   4u    /* put: this object is one stripe of a larger object */
+                              /* (placed by the stripe plan, not by its own key hash) */
+#define NZ_ENC_STRIPED  8u    /* the object's bytes live in stripes on several GPUs */
 
 /* ---- get flags ---------------------------------------------------------- */
 #define NZ_GET_INFLATE  1u    /* serve the inflated representation (SPEC G)       */
@@ -171,6 +174,29 @@ int32_t nz_ticket_inflate_ms(nz_ticket* t, float* ms);  /* device time of its in
 int32_t nz_ticket_free(nz_ticket* t);
 
 int32_t nz_get_stats(nz_ctx* ctx, nz_stats* out);
+
+/* ---- cross-shard objects (the one exchange step) ---------------- */
+/* An object larger than one stripe is striped round-robin over the shards; the owner of
+ * its key holds the stripe map.  A GET on the owner gathers every stripe with direct peer
+ * loads over NVLink inside the same K2 kernel (no separate collective): the other GPUs'
+ * arenas are mapped through CUDA IPC. */
+#define NZ_IPC_HANDLE_BYTES 64
+typedef struct nz_stripe {
+    uint32_t shard;          /* GPU that holds this stripe                         */
+    uint32_t reserved;
+    uint64_t arena_off;      /* where it sits in that GPU's arena (nz_extent_location) */
+    uint64_t len;
+    uint64_t crc_tab_off;    /* its 64 KiB chunk-CRC table in that arena           */
+} nz_stripe;
+int32_t nz_arena_ipc_export(nz_ctx* ctx, uint8_t handle[NZ_IPC_HANDLE_BYTES], uint64_t* arena_bytes);
+int32_t nz_peer_attach(nz_ctx* ctx, uint32_t shard, const uint8_t handle[NZ_IPC_HANDLE_BYTES]);
+int32_t nz_extent_location(nz_ctx* ctx, const uint8_t key[16], uint64_t* arena_off,
+                           uint64_t* stored_len, uint64_t* crc_tab_off, uint32_t* crc32c);
+/* publish the stripe map on the owner; every stripe but the last must be stripe_bytes long */
+int32_t nz_put_striped(nz_ctx* ctx, const uint8_t key[16], uint64_t total_len, uint64_t stripe_bytes,
+                       uint32_t n_stripes, const nz_stripe* stripes, uint32_t crc32c, uint64_t user_meta);
+/* CRC-32C of A||B from crc(A), crc(B), len(B) (host arithmetic; whole-object CRC of a striped object) */
+uint32_t nz_crc32c_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);
 
 /* ---- standalone kernels exposed for parity tests and profiling ------------ */
 /* CRC-32C of n device bytes (K3); chunk table (may be NULL) gets ceil(n/64Ki) u32 */

@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "_build", "libnezha_gpu.so")
 
 NZ_OK, NZ_EINVAL, NZ_ENOMEM, NZ_ECUDA, NZ_ENOTFOUND = 0, -1, -2, -3, -4
 NZ_ECORRUPT, NZ_ETIMEOUT, NZ_EEXIST, NZ_EFULL, NZ_ENOSYS, NZ_ERANGE = -5, -6, -7, -8, -9, -10
-NZ_ENC_IDENTITY, NZ_ENC_GZIP = 0, 1
+NZ_ENC_IDENTITY, NZ_ENC_GZIP, NZ_ENC_STRIPE, NZ_ENC_STRIPED = 0, 1, 4, 8
+NZ_IPC_HANDLE_BYTES = 64
 NZ_GET_INFLATE, NZ_GET_VERIFY = 1, 2
 NZ_BUF_PINNED_HOST, NZ_BUF_DEVICE = 0, 1
 NZ_CRC_CHUNK = 65536
@@ -26,6 +27,7 @@ SYMBOLS = [
     "nz_put_begin", "nz_put_write", "nz_put_write_device", "nz_put_file", "nz_put_commit", "nz_put_abort",
     "nz_evict", "nz_lookup", "nz_get_submit", "nz_get_wait", "nz_get_poll", "nz_ticket_elapsed_ms",
     "nz_ticket_gather_ms", "nz_ticket_inflate_ms", "nz_ticket_free", "nz_get_stats", "nz_crc32c_device", "nz_debug_poke", "nz_shard_of",
+    "nz_arena_ipc_export", "nz_peer_attach", "nz_extent_location", "nz_put_striped", "nz_crc32c_combine",
 ]
 
 
@@ -66,6 +68,11 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "objects", "arena_bytes", "arena_used", "table_slots", "table_live", "gets", "get_bytes", "hits",
         "misses", "puts", "put_bytes", "evictions", "corrupt", "kernel_launches")]
+
+
+class Stripe(C.Structure):
+    _fields_ = [("shard", C.c_uint32), ("reserved", C.c_uint32), ("arena_off", C.c_uint64), ("len", C.c_uint64),
+                ("crc_tab_off", C.c_uint64)]
 
 
 class NezhaError(RuntimeError):
@@ -122,6 +129,12 @@ def load() -> C.CDLL:
     L.nz_debug_poke.argtypes = [vp, u8p, C.c_uint64, C.c_uint8]
     L.nz_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.nz_crc32c_device.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_uint32), vp]
+    L.nz_arena_ipc_export.argtypes = [vp, u8p, C.POINTER(C.c_uint64)]
+    L.nz_peer_attach.argtypes = [vp, C.c_uint32, u8p]
+    L.nz_extent_location.argtypes = [vp, u8p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+    L.nz_put_striped.argtypes = [vp, u8p, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(Stripe), C.c_uint32, C.c_uint64]
+    L.nz_crc32c_combine.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]
+    L.nz_crc32c_combine.restype = C.c_uint32
     L.nz_shard_of.argtypes = [u8p, C.c_uint32]
     L.nz_shard_of.restype = C.c_uint32
     for name in SYMBOLS:

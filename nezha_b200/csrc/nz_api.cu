@@ -34,6 +34,14 @@ static inline uint64_t rd64(const uint8_t* p) {
     return v;   // little-endian host
 }
 static inline uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+static uint32_t nz_gf_mul_c(uint32_t a, uint32_t b) {   // GF(2)[x] mod the reflected Castagnoli polynomial
+    uint32_t p = 0;
+    for (int i = 0; i < 32; ++i) {
+        p ^= b & (0u - ((a >> (31 - i)) & 1u));
+        b = (b >> 1) ^ (0x82F63B78u & (0u - (b & 1u)));
+    }
+    return p;
+}
 
 extern "C" {
 
@@ -111,6 +119,14 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
         c->streams.push_back(s);
     }
     CKI(cudaStreamCreateWithFlags(&c->put_stream, cudaStreamNonBlocking));
+    CKI(cudaMalloc(&c->peer_base_dev, sizeof(uint64_t) * c->cfg.shard_count));
+    CKI(cudaMemset(c->peer_base_dev, 0, sizeof(uint64_t) * c->cfg.shard_count));
+    c->peer_ptrs.assign(c->cfg.shard_count, nullptr);
+    c->peer_ptrs[c->cfg.shard_index] = c->arena;
+    {
+        const uint64_t self = (uint64_t)(uintptr_t)c->arena;
+        CKI(cudaMemcpy(c->peer_base_dev + c->cfg.shard_index, &self, 8, cudaMemcpyHostToDevice));
+    }
 #undef CKI
     c->free_by_off[0] = c->arena_bytes;
     c->free_desc.reserve(c->cfg.max_objects);
@@ -146,6 +162,9 @@ int32_t nz_shutdown(nz_ctx* c) {
         if (c->bounce[i]) cudaFreeHost(c->bounce[i]);
         if (c->bounce_ev[i]) cudaEventDestroy(c->bounce_ev[i]);
     }
+    for (size_t i = 0; i < c->peer_ptrs.size(); ++i)
+        if (c->peer_ptrs[i] && i != c->cfg.shard_index) cudaIpcCloseMemHandle(c->peer_ptrs[i]);
+    if (c->peer_base_dev) cudaFree(c->peer_base_dev);
     if (c->arena) cudaFree(c->arena);
     if (c->table) cudaFree(c->table);
     if (c->descs) cudaFree(c->descs);
@@ -284,9 +303,10 @@ static MailboxPool g_mail;
 int32_t nz_put_begin(nz_ctx* c, const uint8_t key[16], uint64_t stored_len, uint64_t raw_len, uint32_t enc_flags,
                      uint64_t user_meta, nz_put** out) {
     if (!c || !key || !out) return NZ_EINVAL;
-    if (enc_flags & ~NZ_ENC_GZIP) return NZ_EINVAL;
+    if (enc_flags & ~(NZ_ENC_GZIP | NZ_ENC_STRIPE)) return NZ_EINVAL;
     if (!(enc_flags & NZ_ENC_GZIP)) raw_len = stored_len;
-    if (nz_shard_of(key, c->cfg.shard_count) != c->cfg.shard_index) return NZ_EINVAL;
+    // a stripe is placed by its parent's stripe plan, every other object by its own key hash
+    if (!(enc_flags & NZ_ENC_STRIPE) && nz_shard_of(key, c->cfg.shard_count) != c->cfg.shard_index) return NZ_EINVAL;
     const uint64_t k0 = rd64(key), k1 = rd64(key + 8);
     const uint32_t n_chunks = (uint32_t)((stored_len + NZ_CRC_CHUNK - 1) / NZ_CRC_CHUNK);
     const uint64_t data_len = round_up(stored_len ? stored_len : 1, 4096);
@@ -433,7 +453,10 @@ int32_t nz_put_commit(nz_put* p, uint32_t expected, int32_t has_expected, uint32
         if (rc != NZ_OK) goto fail;
         {
             std::lock_guard<std::mutex> g(c->mu);
-            c->shadow[{p->k0, p->k1}].desc = desc_idx;
+            NzHostObj& ho = c->shadow[{p->k0, p->k1}];
+            ho.desc = desc_idx;
+            ho.crc_whole = crc;
+            ho.crc_tab_off = p->crc_tab_off;
         }
         c->puts++;
         c->put_bytes += p->stored_len;
@@ -460,6 +483,7 @@ int32_t nz_evict(nz_ctx* c, const uint8_t key[16]) {
         if (it == c->shadow.end() || it->second.desc == 0xFFFFFFFFu) return NZ_ENOTFOUND;
         ho = it->second;
         c->shadow.erase(it);
+        if (ho.stripe_bytes && c->n_striped) c->n_striped--;
     }
     Mailbox* mb = g_mail.get();
     if (!mb) return NZ_ENOMEM;
@@ -555,10 +579,37 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     // ---- host-side sizing ----
     uint64_t nseg = 0;
     bool any_inflate = false, any_verify = false;
+    // K5: a GET of a striped object is split at stripe boundaries here (the host knows the stripe
+    // size from its shadow), so on the device every slice lies inside exactly one stripe
+    std::vector<std::vector<nz_seg>> split;
+    if (c->n_striped.load() > 0) {
+        split.resize(n);
+        std::lock_guard<std::mutex> g(c->mu);
+        for (uint32_t i = 0; i < n; ++i) {
+            const nz_get_req& r = reqs[i];
+            auto it = c->shadow.find({rd64(r.key), rd64(r.key + 8)});
+            if (it == c->shadow.end() || !it->second.stripe_bytes || it->second.desc == 0xFFFFFFFFu) continue;
+            const uint64_t S = it->second.stripe_bytes, L = it->second.stored_len;
+            nz_seg whole{0, L, 0};
+            const nz_seg* src = r.nseg ? r.segs : &whole;
+            const uint32_t cnt = r.nseg ? r.nseg : 1;
+            for (uint32_t k = 0; k < cnt; ++k) {
+                uint64_t off = src[k].src_off, len = src[k].len, dst = src[k].dst_off;
+                if (off > L || len > L - off) { split[i].clear(); split[i].push_back(src[k]); break; }   // device reports EINVAL
+                while (len) {
+                    const uint64_t room = S - off % S, take = len < room ? len : room;
+                    split[i].push_back(nz_seg{off, take, dst});
+                    off += take; dst += take; len -= take;
+                }
+            }
+            if (split[i].empty()) split[i].push_back(nz_seg{0, 0, 0});   // empty object / zero-length request
+        }
+    }
     for (uint32_t i = 0; i < n; ++i) {
         const nz_get_req& r = reqs[i];
         if (!r.dst || (r.nseg && !r.segs) || r.dst_base > r.dst->size) return NZ_EINVAL;
-        nseg += r.nseg ? r.nseg : 1;
+        if (!split.empty() && !split[i].empty()) nseg += split[i].size();
+        else nseg += r.nseg ? r.nseg : 1;
         any_inflate |= (r.flags & NZ_GET_INFLATE) != 0;
         any_verify |= (r.flags & NZ_GET_VERIFY) != 0;
     }
@@ -596,7 +647,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     const size_t dev_ver = round_up((size_t)ver_cap * sizeof(NzVerWork), 256);
     const size_t dev_cnt = 256;
     const size_t dev_infl = (size_t)n * sizeof(NzInflWork);      // followed directly by rq_src, rq_len
-    const size_t dev_rq = (size_t)n * 24;                        // rq_src, rq_len, infl_meta
+    const size_t dev_rq = (size_t)n * 40;                        // rq_src, rq_len, infl_meta, rq_tab, rq_ssz
     nz_ticket* t = ticket_acquire(c, pin_reqs + pin_segs + pin_res, dev_work + dev_tiles + dev_ver + dev_cnt + round_up(dev_infl + dev_rq, 256));
     if (!t) { cudaGetLastError(); snprintf(tl_err, sizeof tl_err, "ticket allocation failed"); return NZ_ENOMEM; }
     t->n = n; t->nseg = (uint32_t)nseg;
@@ -629,15 +680,22 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
         d.dst_cap = r.dst->size - r.dst_base;
         d.flags = r.flags;
         d.seg_begin = sb;
-        d.whole = r.nseg == 0;
-        d.nseg = r.nseg ? r.nseg : 1;
+        const bool striped = !split.empty() && !split[i].empty();
+        d.whole = r.nseg == 0 && !striped;
+        d.nseg = striped ? (uint32_t)split[i].size() : (r.nseg ? r.nseg : 1);
         d.scratch = 0; d.scratch_cap = 0;
         if (any_inflate && scratch_need[i]) {
             d.scratch = (uint64_t)(uintptr_t)((char*)t->scratch + scratch_off);
             d.scratch_cap = scratch_need[i];
             scratch_off += round_up(scratch_need[i] + 256, 256);
         }
-        if (r.nseg == 0) {
+        if (striped) {
+            for (const nz_seg& sg : split[i]) {
+                hseg[sb].src_off = sg.src_off; hseg[sb].len = sg.len; hseg[sb].dst_off = sg.dst_off;
+                hseg[sb].req = i; hseg[sb].pad = 0;
+                ++sb;
+            }
+        } else if (r.nseg == 0) {
             hseg[sb].src_off = 0; hseg[sb].len = 0; hseg[sb].dst_off = 0; hseg[sb].req = i; hseg[sb].pad = 0;
             ++sb;
         } else {
@@ -662,6 +720,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     a.counters = reinterpret_cast<uint32_t*>(dv + dev_work + dev_tiles + dev_ver);
     a.infl = reinterpret_cast<NzInflWork*>(dv + dev_work + dev_tiles + dev_ver + dev_cnt);
     a.infl_meta = reinterpret_cast<uint64_t*>(a.infl + n) + 2 * (size_t)n;   // after rq_src, rq_len
+    a.peer_base = c->peer_base_dev;
 
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : c->streams[c->rr.fetch_add(1) % c->streams.size()];
     t->stream = s;
@@ -786,6 +845,128 @@ int32_t nz_get_stats(nz_ctx* c, nz_stats* out) {
     out->puts = c->puts; out->put_bytes = c->put_bytes; out->evictions = c->evictions; out->corrupt = c->corrupt;
     out->kernel_launches = c->launches;
     return NZ_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// cross-shard objects: IPC-mapped peer arenas + stripe maps
+// ---------------------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == NZ_IPC_HANDLE_BYTES, "IPC handle size");
+
+int32_t nz_arena_ipc_export(nz_ctx* c, uint8_t handle[NZ_IPC_HANDLE_BYTES], uint64_t* arena_bytes) {
+    if (!c || !handle) return NZ_EINVAL;
+    CK(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->arena));
+    memcpy(handle, &h, sizeof h);
+    if (arena_bytes) *arena_bytes = c->arena_bytes;
+    return NZ_OK;
+}
+
+int32_t nz_peer_attach(nz_ctx* c, uint32_t shard, const uint8_t handle[NZ_IPC_HANDLE_BYTES]) {
+    if (!c || !handle || shard >= c->cfg.shard_count || shard == c->cfg.shard_index) return NZ_EINVAL;
+    CK(cudaSetDevice(c->device));
+    if (c->peer_ptrs[shard]) return NZ_EEXIST;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_ptrs[shard] = p;
+    const uint64_t v = (uint64_t)(uintptr_t)p;
+    CK(cudaMemcpy(c->peer_base_dev + shard, &v, 8, cudaMemcpyHostToDevice));
+    return NZ_OK;
+}
+
+int32_t nz_extent_location(nz_ctx* c, const uint8_t key[16], uint64_t* arena_off, uint64_t* stored_len,
+                           uint64_t* crc_tab_off, uint32_t* crc32c) {
+    if (!c || !key) return NZ_EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    auto it = c->shadow.find({rd64(key), rd64(key + 8)});
+    if (it == c->shadow.end() || it->second.desc == 0xFFFFFFFFu || it->second.stripe_bytes) return NZ_ENOTFOUND;
+    if (arena_off) *arena_off = it->second.arena_off;
+    if (stored_len) *stored_len = it->second.stored_len;
+    if (crc_tab_off) *crc_tab_off = it->second.crc_tab_off;
+    if (crc32c) *crc32c = it->second.crc_whole;
+    return NZ_OK;
+}
+
+uint32_t nz_crc32c_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b) {
+    // x^(8*len_b) by square and multiply (no cycle shortcut: the Castagnoli polynomial is not irreducible)
+    uint32_t p = 0x80000000u, sq = 0x80000000u >> 8;
+    while (len_b) {
+        if (len_b & 1) p = nz_gf_mul_c(sq, p);
+        sq = nz_gf_mul_c(sq, sq);
+        len_b >>= 1;
+    }
+    return nz_gf_mul_c(p, crc_a) ^ crc_b;
+}
+
+int32_t nz_put_striped(nz_ctx* c, const uint8_t key[16], uint64_t total_len, uint64_t stripe_bytes, uint32_t n_stripes,
+                       const nz_stripe* stripes, uint32_t crc32c, uint64_t user_meta) {
+    if (!c || !key || !stripes || !n_stripes || !stripe_bytes) return NZ_EINVAL;
+    if (nz_shard_of(key, c->cfg.shard_count) != c->cfg.shard_index) return NZ_EINVAL;
+    uint64_t sum = 0;
+    for (uint32_t i = 0; i < n_stripes; ++i) {
+        if (stripes[i].shard >= c->cfg.shard_count) return NZ_EINVAL;
+        if (i + 1 < n_stripes && stripes[i].len != stripe_bytes) return NZ_EINVAL;
+        if (stripes[i].len == 0 || stripes[i].len > stripe_bytes) return NZ_EINVAL;
+        sum += stripes[i].len;
+    }
+    if (sum != total_len) return NZ_EINVAL;
+    CK(cudaSetDevice(c->device));
+    const uint64_t k0 = rd64(key), k1 = rd64(key + 8);
+    const uint64_t map_len = round_up((uint64_t)n_stripes * sizeof(NzDevStripe), 4096);
+    uint64_t off = 0;
+    uint32_t desc_idx;
+    uint64_t gen;
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        if (c->shadow.count({k0, k1})) return NZ_EEXIST;
+        if (c->shadow.size() * 2 >= c->n_lines * 4) return NZ_EFULL;
+        if (c->free_desc.empty()) return NZ_ENOMEM;
+        if (!arena_alloc(c, map_len, &off)) return NZ_ENOMEM;
+        desc_idx = c->free_desc.back();
+        c->free_desc.pop_back();
+        gen = c->gen++;
+        NzHostObj ho;
+        ho.desc = 0xFFFFFFFFu; ho.arena_off = off; ho.arena_len = map_len; ho.stored_len = total_len; ho.raw_len = total_len;
+        ho.flags = NZ_ENC_STRIPED; ho.stripe_bytes = stripe_bytes; ho.crc_whole = crc32c;
+        c->shadow[{k0, k1}] = ho;
+    }
+    int32_t rc = NZ_OK;
+    Mailbox* mb = g_mail.get();
+    cudaStream_t s = c->put_stream;
+    cudaError_t e = cudaSuccess;
+    void* mb_dev = nullptr;
+    NzDesc d;
+    memset(&d, 0, sizeof d);
+    d.arena_off = off; d.stored_len = total_len; d.raw_len = total_len; d.user_meta = user_meta; d.crc_tab_off = 0;
+    d.flags = NZ_ENC_STRIPED; d.crc32c = crc32c; d.n_chunks = n_stripes; d.gen = (uint32_t)gen; d.stripe_bytes = stripe_bytes;
+    if (!mb) { rc = NZ_ENOMEM; goto out; }
+    {
+        std::lock_guard<std::mutex> g(c->put_mu);
+        e = cudaHostGetDevicePointer(&mb_dev, mb, 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->arena + off, stripes, (size_t)n_stripes * sizeof(NzDevStripe), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->descs + desc_idx, &d, sizeof d, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = nz_launch_insert(c->table, c->n_lines - 1, k0, k1, desc_idx, gen, &((Mailbox*)mb_dev)->status, s);
+        c->launches += 1;
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    }
+    if (e != cudaSuccess) { rc = cuda_fail(e, "nz_put_striped"); goto out; }
+    rc = mb->status;
+out:
+    if (mb) g_mail.put(mb);
+    std::lock_guard<std::mutex> g(c->mu);
+    if (rc == NZ_OK) {
+        c->shadow[{k0, k1}].desc = desc_idx;
+        c->n_striped++;
+        c->puts++;
+    } else {
+        c->shadow.erase({k0, k1});
+        arena_free(c, off, map_len);
+        c->free_desc.push_back(desc_idx);
+    }
+    return rc;
 }
 
 int32_t nz_debug_poke(nz_ctx* c, const uint8_t key[16], uint64_t off, uint8_t xor_mask) {

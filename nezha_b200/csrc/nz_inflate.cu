@@ -8,10 +8,12 @@
 // from many streams in flight (config C3: thousands of 1 MiB objects per wave).
 //   * one WARP owns one stream; the Huffman/bit-reader state is warp-uniform (every
 //     lane holds the same registers, so no shuffles or divergence in the decode loop);
-//   * the 32 KiB LZ77 window is the OUTPUT ITSELF in HBM/L2 (ld.global.cg), which keeps
-//     shared memory down to ~2.5 KiB of decode tables per warp and lets 48 warps =
-//     48 streams run per SM; match copies are done by all 32 lanes at once
-//     (out[p+k] = out[p-dist + k mod dist], every source byte precedes p);
+//   * the 32 KiB LZ77 window is the OUTPUT ITSELF (L1/L2-resident recent bytes), which keeps
+//     shared memory down to ~6 KiB of decode tables per warp and lets 32 warps =
+//     32 streams run per SM; match copies are done by all 32 lanes at once;
+//   * table entries carry base + extra-bit counts, the bit reader keeps the next input
+//     word in a register one refill ahead: ~35 instructions per symbol instead of ~100
+//     in the first version (ncu: it was issue bound, 43 G warp instructions per 2 GiB);
 //   * the gzip trailer CRC-32 is checked by a second kernel (k_inflate_crc) that runs
 //     the same chunked CRC code as K3 with the IEEE tables.
 // This kernel is latency/ALU bound, not HBM bound: its roofline fraction is reported
@@ -23,12 +25,17 @@
 #include "nz_crc.cuh"
 
 constexpr int INF_WARPS = 4;          // streams per CTA
-constexpr int LL_BITS = 9;            // primary literal/length table: 512 entries
-constexpr int DS_BITS = 8;            // primary distance table: 256 entries
+constexpr int LL_BITS = 10;           // primary literal/length table: 1024 x u32
+constexpr int DS_BITS = 8;            // primary distance table: 256 x u32
 
+// Table entries carry everything the hot loop needs (no side tables):
+//   literal/length: [3:0] code length (0 = not in the primary table -> canonical slow path)
+//                   [5:4] kind 0 literal, 1 length, 2 end-of-block, 3 invalid symbol
+//                   [10:8] extra bits, [24:16] literal byte or length base
+//   distance:       [3:0] code length, [7:4] extra bits, [22:8] base, [31] invalid symbol
 struct __align__(16) WarpTabs {
-    uint16_t ll[1 << LL_BITS];        // (symbol << 4) | code length ; 0 = take the slow path
-    uint16_t ds[1 << DS_BITS];
+    uint32_t ll[1 << LL_BITS];
+    uint32_t ds[1 << DS_BITS];
     uint16_t ll_sym[288];             // symbols in canonical order (for codes longer than the table)
     uint16_t ds_sym[32];
     uint32_t ll_cnt[16];              // codes per length
@@ -42,52 +49,76 @@ __constant__ uint16_t c_dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65
 __constant__ uint8_t  c_dext[30]  = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 __constant__ uint8_t  c_clorder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
+__device__ __forceinline__ uint32_t ll_entry(int sym, int len) {
+    if (sym < 256) return ((uint32_t)sym << 16) | (uint32_t)len;
+    if (sym == 256) return (2u << 4) | (uint32_t)len;
+    if (sym >= 286) return (3u << 4) | (uint32_t)len;
+    return ((uint32_t)c_lbase[sym - 257] << 16) | ((uint32_t)c_lext[sym - 257] << 8) | (1u << 4) | (uint32_t)len;
+}
+__device__ __forceinline__ uint32_t ds_entry(int sym, int len) {
+    if (sym >= 30) return 0x80000000u | (uint32_t)len;
+    return ((uint32_t)c_dbase[sym] << 8) | ((uint32_t)c_dext[sym] << 4) | (uint32_t)len;
+}
+
 // ---------------------------------------------------------------------------
-// warp-uniform bit reader over global memory (LSB-first, RFC 1951 §3.1.1)
+// warp-uniform bit reader over global memory (LSB-first, RFC 1951 3.1.1).
+// 64-bit buffer refilled 32 aligned bits at a time; the next word is always
+// already in a register (loaded one refill ahead, so its latency is hidden).
+// Reads may run a few words past the member's end (inside the extent's slack);
+// the position checks at block boundaries and at the trailer catch that.
 // ---------------------------------------------------------------------------
 struct BitReader {
-    const uint8_t* p;      // next unread byte
-    const uint8_t* end;
+    const uint8_t* base;   // member start
+    const uint32_t* wp;    // next word to load
+    const uint32_t* wlim;  // loads beyond this mean a runaway stream
     uint64_t buf;
-    int cnt;               // valid bits in buf
+    uint32_t cnt;          // valid bits in buf
+    uint32_t nextw;        // word at wp[-1], not yet in buf
 };
-
-__device__ __forceinline__ void br_refill(BitReader& b) {
-    while (b.cnt <= 32) {
-        if ((((uintptr_t)b.p) & 3u) == 0 && b.p + 4 <= b.end) {
-            const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(b.p));
-            b.buf |= (uint64_t)w << b.cnt;
-            b.cnt += 32;
-            b.p += 4;
-        } else if (b.p < b.end) {
-            b.buf |= (uint64_t)__ldg(b.p) << b.cnt;
-            b.cnt += 8;
-            b.p += 1;
-        } else {
-            break;
-        }
+__device__ __forceinline__ void br_init(BitReader& b, const uint8_t* base, const uint8_t* at, const uint8_t* end) {
+    b.base = base;
+    b.buf = 0;
+    b.cnt = 0;
+    while ((((uintptr_t)at) & 3u) != 0) {          // up to 3 bytes to reach word alignment
+        b.buf |= (uint64_t)__ldg(at) << b.cnt;
+        b.cnt += 8;
+        ++at;
     }
+    b.wp = reinterpret_cast<const uint32_t*>(at);
+    b.wlim = reinterpret_cast<const uint32_t*>(end + 64);
+    b.nextw = __ldg(b.wp);
+    ++b.wp;
 }
-__device__ __forceinline__ bool br_take(BitReader& b, int n, uint32_t& v) {   // n <= 32
-    if (b.cnt < n) return false;
-    v = (uint32_t)(b.buf & ((1ull << n) - 1ull));
-    b.buf >>= n;
-    b.cnt -= n;
+__device__ __forceinline__ bool br_refill(BitReader& b) {   // afterwards cnt >= 33
+    if (b.cnt <= 32) {
+        b.buf |= (uint64_t)b.nextw << b.cnt;
+        b.cnt += 32;
+        if (b.wp > b.wlim) return false;
+        b.nextw = __ldg(b.wp);
+        ++b.wp;
+    }
     return true;
 }
+__device__ __forceinline__ uint32_t br_peek(const BitReader& b, uint32_t n) { return (uint32_t)b.buf & ((1u << n) - 1u); }
+__device__ __forceinline__ void br_drop(BitReader& b, uint32_t n) { b.buf >>= n; b.cnt -= n; }
+__device__ __forceinline__ uint32_t br_get(BitReader& b, uint32_t n) {   // n <= 16, caller refilled
+    const uint32_t v = br_peek(b, n);
+    br_drop(b, n);
+    return v;
+}
+// bits consumed since the member start
+__device__ __forceinline__ uint64_t br_bitpos(const BitReader& b) {
+    return 8ull * (uint64_t)(reinterpret_cast<const uint8_t*>(b.wp - 1) - b.base) - b.cnt;
+}
 
-// canonical decode one bit at a time (used for the code-length code and for codes
-// longer than the primary table).  cnt[len] = number of codes of that length,
-// sym = symbols in canonical order.
-__device__ __forceinline__ int slow_decode(BitReader& b, const uint32_t* cnt, const uint16_t* sym) {
+// canonical decode one bit at a time (code-length code, and codes longer than the primary table)
+__device__ __forceinline__ int slow_decode(BitReader& b, const uint32_t* cnt, const uint16_t* sym, int* len_out) {
     int code = 0, first = 0, index = 0;
     for (int len = 1; len <= 15; ++len) {
-        if (b.cnt < len) return -1;
         code |= (int)((b.buf >> (len - 1)) & 1u);
         const int count = (int)cnt[len];
         if (code - count < first) {
-            b.buf >>= len;
-            b.cnt -= len;
+            *len_out = len;
             return sym[index + (code - first)];
         }
         index += count;
@@ -101,8 +132,9 @@ __device__ __forceinline__ int slow_decode(BitReader& b, const uint32_t* cnt, co
 // Build canonical arrays (+ optional primary table) for `n` symbols whose lengths are
 // in lens[].  Warp-cooperative; returns 0 ok / -1 invalid set, following zlib's
 // inflate_table acceptance rule: over-subscribed sets are rejected, incomplete sets
-// only allowed when the longest code is 1 bit.
-__device__ int build_tables(const uint8_t* lens, int n, uint32_t* cnt, uint16_t* sym, uint16_t* tab, int tab_bits, bool is_codes) {
+// only allowed when the longest code is 1 bit (or the set is empty).
+// kind: 0 = code-length code (no table), 1 = literal/length, 2 = distance
+__device__ int build_tables(const uint8_t* lens, int n, uint32_t* cnt, uint16_t* sym, uint32_t* tab, int tab_bits, int kind) {
     const int lane = threadIdx.x & 31;
     __syncwarp();
     if (lane < 16) cnt[lane] = 0;
@@ -110,7 +142,6 @@ __device__ int build_tables(const uint8_t* lens, int n, uint32_t* cnt, uint16_t*
     __syncwarp();
     for (int s = lane; s < n; s += 32) atomicAdd(&cnt[lens[s]], 1u);
     __syncwarp();
-    // validity (uniform)
     int left = 1, maxlen = 0;
     for (int l = 1; l <= 15; ++l) {
         const int c = (int)cnt[l];
@@ -119,8 +150,8 @@ __device__ int build_tables(const uint8_t* lens, int n, uint32_t* cnt, uint16_t*
         left -= c;
         if (left < 0) return -1;                         // over-subscribed
     }
-    if (left > 0 && (is_codes || maxlen != 1)) {
-        if (!(maxlen == 0 && !is_codes)) return -1;      // incomplete (an empty set is accepted: no codes used)
+    if (left > 0 && (kind == 0 || maxlen != 1)) {
+        if (!(maxlen == 0 && kind != 0)) return -1;      // incomplete (an empty set is accepted: no codes used)
     }
     // lane l owns code length l: its first canonical index and first code
     int my_index = 0, my_code = 0;
@@ -140,7 +171,7 @@ __device__ int build_tables(const uint8_t* lens, int n, uint32_t* cnt, uint16_t*
             sym[my_index++] = (uint16_t)s;
             if (tab && l <= tab_bits) {
                 const uint32_t rev = __brev((uint32_t)my_code) >> (32 - l);
-                const uint16_t e = (uint16_t)((s << 4) | l);
+                const uint32_t e = kind == 1 ? ll_entry(s, l) : ds_entry(s, l);
                 for (uint32_t i = rev; i < (1u << tab_bits); i += (1u << l)) tab[i] = e;
             }
             ++my_code;
@@ -152,12 +183,14 @@ __device__ int build_tables(const uint8_t* lens, int n, uint32_t* cnt, uint16_t*
 
 // ---------------------------------------------------------------------------
 // one gzip member -> raw bytes.  Returns produced length, or -1.
-// crc_expect receives the trailer CRC-32.
+// crc_expect receives the trailer CRC-32.  Members inflating to >= 4 GiB are
+// declined (32-bit output cursor; ISIZE is mod 2^32 anyway).
 // ---------------------------------------------------------------------------
-__device__ int64_t inflate_member(const uint8_t* __restrict__ src, uint64_t n, uint8_t* __restrict__ out, uint64_t cap,
+__device__ int64_t inflate_member(const uint8_t* __restrict__ src, uint64_t n, uint8_t* __restrict__ out, uint64_t cap64,
                                   WarpTabs& T, uint32_t* crc_expect) {
     const int lane = threadIdx.x & 31;
-    if (n < 18) return -1;
+    if (n < 18 || cap64 >= 0xFFFFFF00ull) return -1;
+    const uint32_t cap = (uint32_t)cap64;
     // ---- RFC 1952 header (warp-uniform scalar reads) ----
     if (src[0] != 0x1f || src[1] != 0x8b || src[2] != 8) return -1;
     const uint32_t flg = src[3];
@@ -191,74 +224,66 @@ __device__ int64_t inflate_member(const uint8_t* __restrict__ src, uint64_t n, u
     if (pos + 8 > n) return -1;
 
     BitReader b;
-    b.p = src + pos;
-    b.end = src + n;
-    b.buf = 0;
-    b.cnt = 0;
-    uint64_t p = 0;                                      // bytes produced
-    uint32_t v;
+    br_init(b, src, src + pos, src + n);
+    const uint64_t bit_end = 8ull * (n - 8);             // deflate data may not reach into the trailer
+    uint32_t p = 0;                                      // bytes produced
     bool last = false;
     while (!last) {
-        br_refill(b);
-        if (!br_take(b, 3, v)) return -1;
-        last = v & 1u;
-        const uint32_t type = v >> 1;
+        if (!br_refill(b)) return -1;
+        if (br_bitpos(b) + 3 > bit_end) return -1;
+        const uint32_t hdr = br_get(b, 3);
+        last = hdr & 1u;
+        const uint32_t type = hdr >> 1;
         if (type == 0) {
-            // ---- stored block ----
-            b.buf >>= (b.cnt & 7);
-            b.cnt &= ~7;
-            br_refill(b);
-            uint32_t len, nlen;
-            if (!br_take(b, 16, len) || !br_take(b, 16, nlen)) return -1;
+            // ---- stored block: byte-granular, so leave the bit reader and re-enter after it ----
+            const uint64_t bp = (br_bitpos(b) + 7) >> 3;
+            if (bp + 4 > n - 8) return -1;
+            const uint8_t* q = src + bp;
+            const uint32_t len = q[0] | ((uint32_t)q[1] << 8), nlen = q[2] | ((uint32_t)q[3] << 8);
             if ((len ^ 0xFFFFu) != nlen) return -1;
-            // give whole buffered bytes back to the byte stream
-            b.p -= (b.cnt >> 3);
-            b.buf = 0;
-            b.cnt = 0;
-            if ((uint64_t)(b.end - b.p) < len) return -1;
-            if (p + len > cap) return -1;
+            if (bp + 4 + len > n - 8) return -1;
+            if (len > cap - p) return -1;
             __syncwarp();
-            for (uint32_t k = lane; k < len; k += 32) out[p + k] = __ldg(b.p + k);
+            for (uint32_t k = lane; k < len; k += 32) out[p + k] = __ldg(q + 4 + k);
             p += len;
-            b.p += len;
+            br_init(b, src, q + 4 + len, src + n);
             continue;
         }
         if (type == 3) return -1;
         if (type == 1) {
-            // ---- fixed codes (RFC 1951 §3.2.6) ----
+            // ---- fixed codes (RFC 1951 3.2.6) ----
             __syncwarp();
             for (int s = lane; s < 288; s += 32) T.lens[s] = (uint8_t)(s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8)));
-            if (lane < 32) T.lens[288 + lane] = 5;        // 30 used + 2 never-occurring, as zlib's fixed table
+            T.lens[288 + lane] = 5;                       // 30 used + 2 never-valid, as zlib's fixed table
             __syncwarp();
-            if (build_tables(T.lens, 288, T.ll_cnt, T.ll_sym, T.ll, LL_BITS, false) < 0) return -1;
-            if (build_tables(T.lens + 288, 32, T.ds_cnt, T.ds_sym, T.ds, DS_BITS, false) < 0) return -1;
+            if (build_tables(T.lens, 288, T.ll_cnt, T.ll_sym, T.ll, LL_BITS, 1) < 0) return -1;
+            if (build_tables(T.lens + 288, 32, T.ds_cnt, T.ds_sym, T.ds, DS_BITS, 2) < 0) return -1;
         } else {
-            // ---- dynamic codes (§3.2.7) ----
-            br_refill(b);
-            uint32_t hlit, hdist, hclen;
-            if (!br_take(b, 5, hlit) || !br_take(b, 5, hdist) || !br_take(b, 4, hclen)) return -1;
-            hlit += 257; hdist += 1; hclen += 4;
+            // ---- dynamic codes (3.2.7) ----
+            if (!br_refill(b)) return -1;
+            uint32_t hlit = br_get(b, 5) + 257, hdist = br_get(b, 5) + 1, hclen = br_get(b, 4) + 4;
             if (hlit > 286 || hdist > 30) return -1;
             __syncwarp();
             if (lane < 19) T.lens[lane] = 0;
             __syncwarp();
             for (uint32_t i = 0; i < hclen; ++i) {
-                br_refill(b);
-                if (!br_take(b, 3, v)) return -1;
+                if (!br_refill(b)) return -1;
+                const uint32_t v = br_get(b, 3);
                 if (lane == 0) T.lens[c_clorder[i]] = (uint8_t)v;
             }
             __syncwarp();
             // code-length code: canonical arrays only (reuse the distance slots)
-            if (build_tables(T.lens, 19, T.ds_cnt, T.ds_sym, nullptr, 0, true) < 0) return -1;
-            // the 19 lengths were read; now decode hlit + hdist code lengths into lens[]
+            if (build_tables(T.lens, 19, T.ds_cnt, T.ds_sym, nullptr, 0, 0) < 0) return -1;
             __syncwarp();
             uint32_t idx = 0;
             int prev = 0;
             const uint32_t total = hlit + hdist;
             while (idx < total) {
-                br_refill(b);
-                const int sym = slow_decode(b, T.ds_cnt, T.ds_sym);
+                if (!br_refill(b)) return -1;
+                int l;
+                const int sym = slow_decode(b, T.ds_cnt, T.ds_sym, &l);
                 if (sym < 0) return -1;
+                br_drop(b, (uint32_t)l);
                 if (sym < 16) {
                     if (lane == 0) T.lens[idx] = (uint8_t)sym;
                     prev = sym;
@@ -267,15 +292,12 @@ __device__ int64_t inflate_member(const uint8_t* __restrict__ src, uint64_t n, u
                     uint32_t rep, val = 0;
                     if (sym == 16) {
                         if (idx == 0) return -1;
-                        if (!br_take(b, 2, rep)) return -1;
-                        rep += 3;
+                        rep = br_get(b, 2) + 3;
                         val = (uint32_t)prev;
                     } else if (sym == 17) {
-                        if (!br_take(b, 3, rep)) return -1;
-                        rep += 3;
+                        rep = br_get(b, 3) + 3;
                     } else {
-                        if (!br_take(b, 7, rep)) return -1;
-                        rep += 11;
+                        rep = br_get(b, 7) + 11;
                     }
                     if (idx + rep > total) return -1;
                     if (lane == 0) for (uint32_t k = 0; k < rep; ++k) T.lens[idx + k] = (uint8_t)val;
@@ -283,6 +305,7 @@ __device__ int64_t inflate_member(const uint8_t* __restrict__ src, uint64_t n, u
                     if (sym != 16) prev = 0;
                 }
             }
+            if (br_bitpos(b) > bit_end) return -1;
             __syncwarp();
             // split into the two alphabets: distance lengths move to [288, 288+hdist)
             // (read all first, then write: the ranges can overlap)
@@ -294,79 +317,76 @@ __device__ int64_t inflate_member(const uint8_t* __restrict__ src, uint64_t n, u
             T.lens[288 + lane] = (lane < (int)hdist) ? dl : 0;
             __syncwarp();
             if (T.lens[256] == 0) return -1;              // zlib: "invalid code -- missing end-of-block"
-            if (build_tables(T.lens, 288, T.ll_cnt, T.ll_sym, T.ll, LL_BITS, false) < 0) return -1;
-            if (build_tables(T.lens + 288, 32, T.ds_cnt, T.ds_sym, T.ds, DS_BITS, false) < 0) return -1;
+            if (build_tables(T.lens, 288, T.ll_cnt, T.ll_sym, T.ll, LL_BITS, 1) < 0) return -1;
+            if (build_tables(T.lens + 288, 32, T.ds_cnt, T.ds_sym, T.ds, DS_BITS, 2) < 0) return -1;
         }
         // ---- symbol loop ----
         for (;;) {
-            br_refill(b);
-            uint32_t e = T.ll[b.buf & ((1u << LL_BITS) - 1u)];
-            int sym;
-            if (e) {
-                const int l = (int)(e & 15u);
-                if (b.cnt < l) return -1;
-                b.buf >>= l;
-                b.cnt -= l;
-                sym = (int)(e >> 4);
-            } else {
-                sym = slow_decode(b, T.ll_cnt, T.ll_sym);
+            if (!br_refill(b)) return -1;
+            uint32_t e = T.ll[br_peek(b, LL_BITS)];
+            if (e == 0) {
+                int l;
+                const int sym = slow_decode(b, T.ll_cnt, T.ll_sym, &l);
                 if (sym < 0) return -1;
+                e = ll_entry(sym, l);
             }
-            if (sym < 256) {
+            br_drop(b, e & 15u);
+            const uint32_t kind = (e >> 4) & 3u;
+            if (kind == 0) {                              // literal
                 if (p >= cap) return -1;
-                if (lane == 0) out[p] = (uint8_t)sym;
+                if (lane == 0) out[p] = (uint8_t)(e >> 16);
                 ++p;
                 continue;
             }
-            if (sym == 256) break;
-            sym -= 257;
-            if (sym >= 29) return -1;
-            uint32_t ext;
-            if (!br_take(b, c_lext[sym], ext)) return -1;
-            const uint32_t mlen = c_lbase[sym] + ext;
-            br_refill(b);
-            e = T.ds[b.buf & ((1u << DS_BITS) - 1u)];
-            int dsym;
-            if (e) {
-                const int l = (int)(e & 15u);
-                if (b.cnt < l) return -1;
-                b.buf >>= l;
-                b.cnt -= l;
-                dsym = (int)(e >> 4);
-            } else {
-                dsym = slow_decode(b, T.ds_cnt, T.ds_sym);
-                if (dsym < 0) return -1;
+            if (kind != 1) {
+                if (kind == 2) break;                     // end of block
+                return -1;                                // symbols 286/287
             }
-            if (dsym >= 30) return -1;
-            if (!br_take(b, c_dext[dsym], ext)) return -1;
-            const uint32_t dist = c_dbase[dsym] + ext;
+            const uint32_t mlen = (e >> 16) + br_get(b, (e >> 8) & 7u);
+            if (!br_refill(b)) return -1;
+            e = T.ds[br_peek(b, DS_BITS)];
+            if (e == 0) {
+                int l;
+                const int dsym = slow_decode(b, T.ds_cnt, T.ds_sym, &l);
+                if (dsym < 0) return -1;
+                e = ds_entry(dsym, l);
+            }
+            if (e & 0x80000000u) return -1;               // distance symbols 30/31
+            br_drop(b, e & 15u);
+            const uint32_t dist = ((e >> 8) & 0x7FFFu) + br_get(b, (e >> 4) & 15u);
             if (dist > p) return -1;                      // "invalid distance too far back"
-            if (p + mlen > cap) return -1;
-            // ---- LZ77 copy: all source bytes precede p, so the lanes are independent ----
+            if (mlen > cap - p) return -1;
+            // ---- LZ77 copy: the window is the output itself (L1/L2) ----
             __syncwarp();                                 // orders lane 0's literal stores / earlier copies
             const uint8_t* s0 = out + (p - dist);
             uint8_t* d0 = out + p;
-            if (dist >= mlen) {
-                for (uint32_t k = lane; k < mlen; k += 32) d0[k] = __ldcg(s0 + k);
-            } else {
-                for (uint32_t k = lane; k < mlen; k += 32) d0[k] = __ldcg(s0 + (k % dist));
+            if (dist >= mlen) {                           // no overlap: lanes independent
+                for (uint32_t k = lane; k < mlen; k += 32) d0[k] = s0[k];
+            } else if (dist >= 32) {                      // overlap, period >= warp: 32-byte steps in order
+                for (uint32_t k0 = 0; k0 < mlen; k0 += 32) {
+                    const uint32_t k = k0 + lane;
+                    if (k < mlen) d0[k] = s0[k];
+                    __syncwarp();
+                }
+            } else {                                      // short period: every source byte precedes p
+                for (uint32_t k = lane; k < mlen; k += 32) d0[k] = s0[k % dist];
             }
             p += mlen;
         }
+        if (br_bitpos(b) > bit_end) return -1;
     }
     // ---- RFC 1952 trailer ----
-    b.buf >>= (b.cnt & 7);
-    b.cnt &= ~7;
-    const uint8_t* tp = b.p - (b.cnt >> 3);
-    if ((uint64_t)(b.end - tp) != 8) return -1;           // SPEC G4: trailing bytes / second member -> declined
+    const uint64_t tpos = (br_bitpos(b) + 7) >> 3;
+    if (tpos != n - 8) return -1;                         // SPEC G4: trailing bytes / second member -> declined
+    const uint8_t* tp = src + tpos;
     const uint32_t crc = tp[0] | ((uint32_t)tp[1] << 8) | ((uint32_t)tp[2] << 16) | ((uint32_t)tp[3] << 24);
     const uint32_t isize = tp[4] | ((uint32_t)tp[5] << 8) | ((uint32_t)tp[6] << 16) | ((uint32_t)tp[7] << 24);
-    if (isize != (uint32_t)p) return -1;
+    if (isize != p) return -1;
     *crc_expect = crc;
     return (int64_t)p;
 }
 
-__global__ void __launch_bounds__(INF_WARPS * 32, 12)
+__global__ void __launch_bounds__(INF_WARPS * 32, 8)
 k_inflate(const NzInflWork* __restrict__ infl, uint64_t* __restrict__ meta, uint32_t* counters, NzDevRes* res) {
     __shared__ WarpTabs tabs[INF_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

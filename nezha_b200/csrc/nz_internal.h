@@ -38,7 +38,7 @@ struct __align__(64) NzDesc {
     uint32_t crc32c;         // whole-object CRC-32C of the stored bytes
     uint32_t n_chunks;
     uint32_t gen;
-    uint64_t pad;
+    uint64_t stripe_bytes;   // striped objects: stripe size; arena_off then points at the NzDevStripe map, n_chunks = stripes
 };
 static_assert(sizeof(NzSlot) == 32, "slot");
 static_assert(sizeof(NzDesc) == 64, "desc");
@@ -111,7 +111,16 @@ struct nz_buf {
     bool owned;
 };
 
+struct __align__(8) NzDevStripe {   // mirrors nz_stripe
+    uint32_t shard, reserved;
+    uint64_t arena_off, len, crc_tab_off;
+};
+static_assert(sizeof(NzDevStripe) == sizeof(nz_stripe), "stripe layout");
+
 struct NzHostObj {     // host shadow of a live object (arena bookkeeping, EEXIST, inflate sizing)
+    uint64_t stripe_bytes = 0;   // != 0: striped object, arena extent holds the stripe map
+    uint32_t crc_whole = 0;
+    uint64_t crc_tab_off = 0;
     uint32_t desc;
     uint64_t arena_off, arena_len;
     uint64_t stored_len, raw_len;
@@ -179,6 +188,9 @@ struct nz_ctx {
     size_t bounce_bytes = 0;
     cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
     std::mutex put_mu;              // serialises fill-side device work
+    uint64_t* peer_base_dev = nullptr;      // device array [shard_count]
+    std::vector<void*> peer_ptrs;           // host copy; nullptr = not attached
+    std::atomic<uint32_t> n_striped{0};     // live striped objects (GET submit consults the shadow only if > 0)
 };
 
 // ---------------------------------------------------------------------------
@@ -198,6 +210,7 @@ struct NzPlanArgs {
     NzInflWork* infl;           // capacity n
     uint32_t* counters;         // [0]=n_ver [1]=n_infl [2]=inflate work-steal cursor
     uint64_t* infl_meta;        // n: (produced length << 32) | trailer CRC-32, written by k_inflate
+    const uint64_t* peer_base;  // device array [shard_count]: base address of every shard's arena (own + IPC-mapped peers)
 };
 cudaError_t nz_launch_lookup(const NzSlot* table, uint64_t line_mask, const NzDesc* descs, const uint64_t* keys,
                              uint32_t n, nz_extent* out, cudaStream_t s);

@@ -169,7 +169,7 @@ struct PlanScratch {
 };
 
 __global__ void __launch_bounds__(1024, 1)
-k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len) {
+k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint64_t* rq_ssz) {
     __shared__ uint64_t s_scan[1024];
     __shared__ uint64_t s_carry;
     const uint32_t tid = threadIdx.x;
@@ -186,7 +186,7 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len) {
         if (!active || (tid & 3u) != 0) continue;
         NzDevRes out;
         out.status = NZ_OK; out.flags = 0; out.bytes = 0; out.length = 0; out.crc32c = 0; out.reserved = 0;
-        uint64_t src = 0, len = 0;
+        uint64_t src = 0, len = 0, tab = 0, ssz = 0;
         if (d == 0xFFFFFFFFu) {
             out.status = NZ_ENOTFOUND;
         } else {
@@ -197,6 +197,12 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len) {
             len = inflate ? ds.raw_len : ds.stored_len;
             out.length = len;
             src = (uint64_t)(a.arena + ds.arena_off);
+            if (ds.flags & NZ_ENC_STRIPED) {             // bytes live on several GPUs: arena_off is the stripe map
+                tab = src;
+                ssz = ds.stripe_bytes;
+                src = 0;
+                if (rq.whole || ssz == 0) out.status = NZ_EINVAL;   // the host always splits striped GETs per stripe
+            }
             // validate slices against the representation and the destination
             uint64_t bytes = 0;
             if (rq.whole) {
@@ -222,7 +228,7 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len) {
                         NzInflWork w;
                         w.src = src; w.src_len = ds.stored_len;
                         w.dst = direct ? rq.dst : rq.scratch;
-                        w.dst_cap = direct ? rq.dst_cap : rq.scratch_cap;
+                        w.dst_cap = len;             // exactly the inflated length (validated against dst/scratch above)
                         w.req = r; w.pad = direct ? 1u : 0u;
                         a.infl[slot] = w;
                         src = direct ? 0 : rq.scratch;   // direct: nothing left to gather
@@ -244,9 +250,11 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len) {
                 }
             }
         }
-        if (out.status != NZ_OK) { len = 0; src = 0; }
+        if (out.status != NZ_OK) { len = 0; src = 0; tab = 0; }
         rq_src[r] = src;
         rq_len[r] = len;
+        rq_tab[r] = tab;
+        rq_ssz[r] = ssz;
         a.res[r] = out;
     }
     __syncthreads();
@@ -269,10 +277,24 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len) {
                 const uint64_t len = rq.whole ? rlen : sg.len;
                 const uint64_t doff = rq.whole ? 0 : sg.dst_off;
                 w.src = rq_src[sg.req] + off;
+                const uint64_t tab = rq_tab[sg.req];
+                uint64_t ok_len = len;
+                if (tab) {                               // K5: the slice lies inside one stripe, maybe on a peer GPU
+                    const uint64_t ssz = rq_ssz[sg.req];
+                    const uint64_t k = off / ssz, within = off - k * ssz;
+                    const NzDevStripe st = reinterpret_cast<const NzDevStripe*>(tab)[k];
+                    const uint64_t base = a.peer_base ? a.peer_base[st.shard] : 0;
+                    if (within + len > st.len || base == 0) {
+                        ok_len = 0;
+                        a.res[sg.req].status = base == 0 ? NZ_ENOSYS : NZ_EINVAL;
+                        a.res[sg.req].bytes = 0;
+                    }
+                    w.src = base + st.arena_off + within;
+                }
                 w.dst = rq.dst + doff;
-                w.len = len;
+                w.len = ok_len;
                 w.vstart = -(int64_t)(w.dst & 127u);
-                tiles = len ? (len + (w.dst & 127u) + NZ_TILE - 1) / NZ_TILE : 0;
+                tiles = ok_len ? (ok_len + (w.dst & 127u) + NZ_TILE - 1) / NZ_TILE : 0;
             }
             a.work[s] = w;
         }
@@ -311,6 +333,7 @@ k_plan_verify(NzPlanArgs a) {
         const NzDesc ds = a.descs[d];
         const NzDevReq rq = a.reqs[r];
         if ((rq.flags & NZ_GET_INFLATE) && (ds.flags & NZ_ENC_GZIP)) continue;   // done in k_plan
+        if (ds.flags & NZ_ENC_STRIPED) continue;     // stripes carry their own chunk tables on their GPUs (verified at fill)
         const uint32_t* tab = reinterpret_cast<const uint32_t*>(a.arena + ds.crc_tab_off);
         const uint32_t nsg = rq.whole ? 1u : rq.nseg;
         for (uint32_t i = 0; i < nsg; ++i) {
@@ -540,7 +563,9 @@ cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s) {
     // rq_src / rq_len live right after the inflate work array (see nz_api.cu: device block layout)
     uint64_t* rq_src = reinterpret_cast<uint64_t*>(a.infl + a.n);
     uint64_t* rq_len = rq_src + a.n;
-    k_plan<<<1, 1024, 0, s>>>(a, rq_src, rq_len);
+    uint64_t* rq_tab = rq_src + 3 * (size_t)a.n;     // [rq_src | rq_len | infl_meta | rq_tab | rq_ssz]
+    uint64_t* rq_ssz = rq_src + 4 * (size_t)a.n;
+    k_plan<<<1, 1024, 0, s>>>(a, rq_src, rq_len, rq_tab, rq_ssz);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (a.ver_cap) {

@@ -271,6 +271,34 @@ class Zone:
         finally:
             buf.free()
 
+    # -- cross-shard objects (K5) ---------------------------------------------
+    def ipc_export(self) -> bytes:
+        h = (C.c_uint8 * capi.NZ_IPC_HANDLE_BYTES)()
+        n = C.c_uint64()
+        check(self.L.nz_arena_ipc_export(self.ctx, h, C.byref(n)), "nz_arena_ipc_export")
+        return bytes(h)
+
+    def peer_attach(self, shard: int, handle: bytes):
+        h = (C.c_uint8 * capi.NZ_IPC_HANDLE_BYTES).from_buffer_copy(handle)
+        check(self.L.nz_peer_attach(self.ctx, shard, h), "nz_peer_attach")
+
+    def extent_location(self, key: bytes):
+        k = (C.c_uint8 * 16).from_buffer_copy(key)
+        off, ln, tab, crc = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint32()
+        check(self.L.nz_extent_location(self.ctx, k, C.byref(off), C.byref(ln), C.byref(tab), C.byref(crc)),
+              "nz_extent_location")
+        return off.value, ln.value, tab.value, crc.value
+
+    def put_striped(self, key: bytes, total_len: int, stripe_bytes: int, stripes, crc32c: int, user_meta: int = 0):
+        """stripes: [(shard, arena_off, len, crc_tab_off)] in object order."""
+        k = (C.c_uint8 * 16).from_buffer_copy(key)
+        arr = (capi.Stripe * len(stripes))(*[capi.Stripe(s, 0, o, l, t) for s, o, l, t in stripes])
+        check(self.L.nz_put_striped(self.ctx, k, total_len, stripe_bytes, len(stripes), arr, crc32c, user_meta),
+              "nz_put_striped")
+
+    def crc32c_combine(self, crc_a: int, crc_b: int, len_b: int) -> int:
+        return self.L.nz_crc32c_combine(crc_a, crc_b, len_b)
+
     def debug_poke(self, key: bytes, off: int, xor_mask: int = 0x01) -> int:
         k = (C.c_uint8 * 16).from_buffer_copy(key)
         return self.L.nz_debug_poke(self.ctx, k, off, xor_mask)

@@ -64,3 +64,19 @@ def test_product_never_imports_oracle():
                 if re.search(r"nz_oracle|from oracle|import oracle|libnz_oracle|nzo_", t):
                     bad.append(os.path.join(d, f))
     assert not bad, bad
+
+
+def test_crc32c_combine_matches_oracle():
+    import numpy as np
+    from oracle import oracle as o
+    L = capi.load()
+    rng = np.random.default_rng(5)
+    for n1, n2 in [(1, 1), (100, 65536), (65536, 1), (12345, 678901)]:
+        a = rng.integers(0, 256, n1, dtype=np.uint8)
+        b = rng.integers(0, 256, n2, dtype=np.uint8)
+        assert L.nz_crc32c_combine(o.crc32c(a), o.crc32c(b), n2) == o.crc32c(np.concatenate([a, b]))
+    assert L.nz_crc32c_combine(0x12345678, 0, 0) == 0x12345678
+    assert L.nz_crc32c_combine(o.crc32c(b"x"), o.crc32c(bytes(1 << 20)), (1 << 33) + 5) == o.crc32c_combine(
+        o.crc32c(b"x"), o.crc32c(bytes(1 << 20)), (1 << 33) + 5)
+
+
