@@ -72,6 +72,27 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local: int):
+    """Run this rank on the CPU cores of the NUMA node its GPU hangs off, so the pinned
+    response windows are allocated next to the GPU's PCIe root (first touch)."""
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(local)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -203,6 +224,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (this path has no CPU fallback)")
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         import torch.distributed as dist
 
@@ -359,6 +382,7 @@ def run_ours(args):
     # ---- CPU baseline beside it (rank 0, N=1 only) -----------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        os.sched_setaffinity(0, all_cpus)      # the CPU arm gets every host core
         threads = os.cpu_count() or 1
         r = cpu_serve(wl.c2_requests(L_obj, args.requests, seed=22), L_obj, 2, threads, args.cpu_budget)
         r1 = cpu_serve(wl.c2_requests(L_obj, args.requests, seed=22), L_obj, 2, 1, min(args.cpu_budget, 6.0))
@@ -375,7 +399,7 @@ def run_ours(args):
                        "response_buffers": "HBM", "l2": "inputs larger than L2 (1 GiB object, 33 GiB written per step); no flush needed",
                        "sharding": f"key-hash x{world}, no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "ttfb": ttfb, "gpu_launches": int(launches),
-            "clocks": sampler.summary(), "fill_gbs": L_obj / fill_s / 1e9, "object_crc32c": f"{crc:08x}",
+            "clocks": sampler.summary(), "numa_node": numa, "fill_gbs": L_obj / fill_s / 1e9, "object_crc32c": f"{crc:08x}",
         }
         print(json.dumps(line), flush=True)
     dbuf.free()

@@ -143,6 +143,8 @@ int32_t nz_put_begin(nz_ctx* ctx, const uint8_t key[16], uint64_t stored_len,
                      nz_put** out);
 /* copy len bytes from host memory (pinned nz_buf memory goes async) */
 int32_t nz_put_write(nz_put* p, const void* src_host, uint64_t dst_off, uint64_t len);
+/* wait until every copy queued on this put has left its source buffer (to reuse a pinned window) */
+int32_t nz_put_sync(nz_put* p);
 /* copy from device memory (synthetic fills, peer fills) */
 int32_t nz_put_write_device(nz_put* p, const void* src_dev, uint64_t dst_off, uint64_t len);
 /* read from a file: cuFile/GDS when available, else pread into pinned bounce buffers */

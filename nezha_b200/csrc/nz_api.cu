@@ -342,6 +342,12 @@ int32_t nz_put_write(nz_put* p, const void* src_host, uint64_t dst_off, uint64_t
     CK(cudaMemcpyAsync(p->ctx->arena + p->arena_off + dst_off, src_host, len, cudaMemcpyHostToDevice, p->stream));
     return NZ_OK;
 }
+int32_t nz_put_sync(nz_put* p) {
+    if (!p) return NZ_EINVAL;
+    CK(cudaSetDevice(p->ctx->device));
+    CK(cudaStreamSynchronize(p->stream));
+    return NZ_OK;
+}
 int32_t nz_put_write_device(nz_put* p, const void* src_dev, uint64_t dst_off, uint64_t len) {
     if (!p || (!src_dev && len) || dst_off > p->stored_len || len > p->stored_len - dst_off) return NZ_EINVAL;
     if (!len) return NZ_OK;

@@ -410,6 +410,8 @@ const char* reason_phrase(int code) {
     case 405: return "Not Allowed";
     case 412: return "Precondition Failed";
     case 416: return "Requested Range Not Satisfiable";
+    case 502: return "Bad Gateway";
+    case 504: return "Gateway Time-out";
     default: return "";
     }
 }
@@ -444,6 +446,8 @@ Part literal(std::string b) {
     return s;
 }
 }  // namespace
+
+Plan error_page(int code, bool head) { return stock_page(code, head); }
 
 Plan plan_response(const Config& cfg, const Request& rq, const ObjectMeta& ob, uint64_t boundary) {
     if (!method_allowed(rq.method)) return stock_page(405, false);

@@ -79,6 +79,7 @@ RangeVerdict parse_ranges(std::string_view spec_after_bytes_eq, int64_t length, 
 int64_t parse_http_date(std::string_view s);    // seconds since the epoch, -1 if unparseable
 
 Plan plan_response(const Config& cfg, const Request& rq, const ObjectMeta& ob, uint64_t boundary);
+Plan error_page(int code, bool head);           // stock nginx page (server_tokens off, nginx.conf:20)
 
 }  // namespace nzh
 

@@ -1,0 +1,577 @@
+// nezha_b200/host/nzproxy.cc — the HTTP/1.1 front end of the GPU cache (port-80 wire contract).
+//
+// Compiled stand-in for the Go `app/proxy` that BASELINE.json:north_star asks for (no `go` in
+// this image).  It keeps the client contract of /root/reference/examples/demo/nginx.conf +
+// nginx.yaml — plain HTTP virtual-hosted by Host:, GET/HEAD only, `Server: nginx` — so training
+// pods are unchanged, and serves cache hits from HBM through the C ABI (include/nezha_gpu.h):
+//   request -> nz_http (key, method gate, conditionals, Range) -> plan of literals + slices
+//   slices  -> nz_get_submit into two pinned windows per connection (double buffered) -> write()
+// Misses are filled from the origin the vhost's proxy_pass names (HTTP/1.0, full object, the
+// three proxy_set_header lines of nginx.conf:52-54), admitted only on status 200
+// (proxy_cache_valid 200 1d, nginx.conf:57), then served like a hit.
+//
+// Threading: one thread per connection (cap --max-conns), blocking sockets; the GPU library is
+// thread safe.  Not here (out of scope this round): TLS upstream (GCS vhost), expiry/inactive
+// eviction timers, access log.
+#include <arpa/inet.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <netdb.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
+#include <signal.h>
+#include <sys/socket.h>
+#include <sys/time.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/nezha_gpu.h"
+#include "nz_http.h"
+
+namespace {
+
+struct Options {
+    std::string listen_ip = "0.0.0.0";
+    int port = 80;
+    int device = 0;
+    uint64_t arena_bytes = 8ull << 30;
+    uint32_t max_objects = 1u << 16;
+    uint64_t window_bytes = 4ull << 20;
+    uint64_t first_window = 256ull << 10;   // small first window keeps time-to-first-byte low
+    int max_conns = 512;
+    bool gunzip = false;
+    bool verify = false;
+    std::map<std::string, std::string> upstream;   // proxy_host -> ip:port override (tests; nginx resolves via DNS)
+};
+
+struct Entry {
+    nzh::ObjectMeta meta;
+    uint8_t key128[16];
+    time_t stored_at;
+};
+
+struct Key16 {
+    uint8_t b[16];
+    bool operator==(const Key16& o) const { return memcmp(b, o.b, 16) == 0; }
+};
+struct Key16Hash {
+    size_t operator()(const Key16& k) const { size_t v; memcpy(&v, k.b + 8, sizeof v); return v; }
+};
+
+struct Server {
+    Options opt;
+    nzh::Config cfg = nzh::Config::reference_default();
+    nz_ctx* ctx = nullptr;
+    std::mutex mu;
+    std::unordered_map<Key16, std::shared_ptr<Entry>, Key16Hash> index;   // headers blob per object (host side)
+    std::mutex fill_mu;                                                    // one fill at a time per process (coalesces stampedes)
+    std::mutex win_mu;
+    std::vector<nz_buf*> free_windows;
+    std::atomic<uint64_t> boundary{1};
+    std::atomic<int> conns{0};
+    std::atomic<uint64_t> hits{0}, misses{0}, bytes_out{0};
+};
+
+bool write_all(int fd, const void* p, size_t n) {
+    const char* c = static_cast<const char*>(p);
+    while (n) {
+        ssize_t w = ::send(fd, c, n, MSG_NOSIGNAL);
+        if (w < 0) {
+            if (errno == EINTR) continue;
+            return false;
+        }
+        c += w;
+        n -= (size_t)w;
+    }
+    return true;
+}
+
+std::string http_date(time_t t) {
+    char buf[64];
+    struct tm tmv;
+    gmtime_r(&t, &tmv);
+    strftime(buf, sizeof buf, "%a, %d %b %Y %H:%M:%S GMT", &tmv);
+    return buf;
+}
+
+const char* status_text(int code) {
+    switch (code) {
+    case 200: return "OK";
+    case 206: return "Partial Content";
+    case 304: return "Not Modified";
+    case 400: return "Bad Request";
+    case 405: return "Not Allowed";
+    case 412: return "Precondition Failed";
+    case 416: return "Requested Range Not Satisfiable";
+    case 502: return "Bad Gateway";
+    case 504: return "Gateway Time-out";
+    default: return "Error";
+    }
+}
+
+// ---- request parsing --------------------------------------------------------
+struct Parsed {
+    nzh::Request rq;
+    bool keep_alive = true;
+    bool ok = false;
+};
+
+std::string lower(std::string s) {
+    for (char& c : s) c = (char)tolower((unsigned char)c);
+    return s;
+}
+std::string trim(const std::string& s) {
+    size_t a = 0, b = s.size();
+    while (a < b && (s[a] == ' ' || s[a] == '\t')) ++a;
+    while (b > a && (s[b - 1] == ' ' || s[b - 1] == '\t' || s[b - 1] == '\r')) --b;
+    return s.substr(a, b - a);
+}
+
+Parsed parse_head(const std::string& head) {
+    Parsed p;
+    size_t eol = head.find("\r\n");
+    if (eol == std::string::npos) return p;
+    const std::string line = head.substr(0, eol);
+    const size_t s1 = line.find(' ');
+    if (s1 == std::string::npos) return p;
+    const size_t s2 = line.find(' ', s1 + 1);
+    p.rq.method = line.substr(0, s1);
+    if (s2 == std::string::npos) {           // HTTP/0.9
+        p.rq.target = line.substr(s1 + 1);
+        p.rq.http_minor = -1;
+        p.keep_alive = false;
+    } else {
+        p.rq.target = line.substr(s1 + 1, s2 - s1 - 1);
+        const std::string ver = line.substr(s2 + 1);
+        if (ver == "HTTP/1.1") p.rq.http_minor = 1;
+        else if (ver == "HTTP/1.0") { p.rq.http_minor = 0; p.keep_alive = false; }
+        else return p;
+    }
+    size_t pos = eol + 2;
+    while (pos < head.size()) {
+        const size_t e = head.find("\r\n", pos);
+        if (e == std::string::npos || e == pos) break;
+        const std::string h = head.substr(pos, e - pos);
+        pos = e + 2;
+        const size_t c = h.find(':');
+        if (c == std::string::npos) continue;
+        const std::string name = lower(h.substr(0, c));
+        const std::string val = trim(h.substr(c + 1));
+        if (name == "host") p.rq.host = val;
+        else if (name == "range") p.rq.range = val;
+        else if (name == "if-range") p.rq.if_range = val;
+        else if (name == "if-none-match") p.rq.if_none_match = val;
+        else if (name == "if-match") p.rq.if_match = val;
+        else if (name == "if-modified-since") p.rq.if_modified_since = val;
+        else if (name == "if-unmodified-since") p.rq.if_unmodified_since = val;
+        else if (name == "accept-encoding") p.rq.accept_encoding = val;
+        else if (name == "connection") {
+            const std::string v = lower(val);
+            if (v.find("close") != std::string::npos) p.keep_alive = false;
+            else if (v.find("keep-alive") != std::string::npos) p.keep_alive = true;
+        }
+    }
+    p.ok = true;
+    return p;
+}
+
+// ---- origin fetch (miss path) ------------------------------------------------
+int connect_to(const std::string& hostport, int default_port) {
+    std::string host = hostport;
+    int port = default_port;
+    const size_t c = hostport.rfind(':');
+    if (c != std::string::npos) { host = hostport.substr(0, c); port = atoi(hostport.c_str() + c + 1); }
+    struct addrinfo hints, *res = nullptr;
+    memset(&hints, 0, sizeof hints);
+    hints.ai_family = AF_INET;
+    hints.ai_socktype = SOCK_STREAM;
+    char ps[16];
+    snprintf(ps, sizeof ps, "%d", port);
+    if (getaddrinfo(host.c_str(), ps, &hints, &res) != 0 || !res) return -1;
+    int fd = socket(res->ai_family, res->ai_socktype, res->ai_protocol);
+    if (fd >= 0) {
+        struct timeval tv = {60, 0};     // proxy_connect/read timeouts default to 60 s
+        setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof tv);
+        setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &tv, sizeof tv);
+        if (connect(fd, res->ai_addr, res->ai_addrlen) != 0) { close(fd); fd = -1; }
+    }
+    freeaddrinfo(res);
+    return fd;
+}
+
+// returns HTTP status to relay (200 = admitted and indexed); fills `out` on 200
+int fill_from_origin(Server& S, int vhost, const std::string& host, const std::string& target, const std::string& client_ip,
+                     const uint8_t key128[16], std::shared_ptr<Entry>& out) {
+    const nzh::VHost& vh = S.cfg.vhosts[vhost];
+    auto it = S.opt.upstream.find(vh.proxy_host);
+    if (vh.upstream_tls && it == S.opt.upstream.end()) return 502;   // https upstream needs an override this round
+    const std::string addr = it != S.opt.upstream.end() ? it->second : vh.proxy_host;
+    int fd = connect_to(addr, 80);
+    if (fd < 0) return 502;
+    // nginx talks HTTP/1.0 to the upstream and strips Range/If-* when caching; nginx.conf:52-54 headers
+    std::string uri = target;
+    if (uri.rfind("http://", 0) == 0 || uri.rfind("https://", 0) == 0) {
+        const size_t s = uri.find('/', uri.find("://") + 3);
+        uri = s == std::string::npos ? "/" : uri.substr(s);
+    }
+    std::string req = "GET " + uri + " HTTP/1.0\r\nX-Real-IP: " + client_ip + "\r\nHost: " + host + "\r\nX-Forwarded-For: " + client_ip +
+                      "\r\nConnection: close\r\n\r\n";
+    if (!write_all(fd, req.data(), req.size())) { close(fd); return 502; }
+    std::string head;
+    std::vector<char> buf(1 << 16);
+    size_t body_at = std::string::npos;
+    while (body_at == std::string::npos) {
+        ssize_t r = recv(fd, buf.data(), buf.size(), 0);
+        if (r <= 0) { close(fd); return r == 0 ? 502 : 504; }
+        head.append(buf.data(), (size_t)r);
+        body_at = head.find("\r\n\r\n");
+        if (head.size() > (1 << 20)) { close(fd); return 502; }
+    }
+    std::string rest = head.substr(body_at + 4);
+    head.resize(body_at + 2);
+    int status = 0;
+    if (sscanf(head.c_str(), "HTTP/%*d.%*d %d", &status) != 1) { close(fd); return 502; }
+    nzh::ObjectMeta meta;
+    int64_t clen = -1;
+    bool cacheable = status == 200;
+    size_t pos = head.find("\r\n") + 2;
+    while (pos < head.size()) {
+        const size_t e = head.find("\r\n", pos);
+        if (e == std::string::npos) break;
+        const std::string h = head.substr(pos, e - pos);
+        pos = e + 2;
+        const size_t c = h.find(':');
+        if (c == std::string::npos) continue;
+        const std::string name = lower(h.substr(0, c)), val = trim(h.substr(c + 1));
+        if (name == "content-length") clen = atoll(val.c_str());
+        else if (name == "content-type") meta.content_type = val;
+        else if (name == "etag") meta.etag = val;
+        else if (name == "last-modified") meta.last_modified = val;
+        else if (name == "content-encoding") { if (lower(val) == "gzip") meta.stored_gzip = true; else cacheable = false; }
+        else if (name == "set-cookie") cacheable = false;                         // nginx: not cached
+        else if (name == "vary" && val == "*") cacheable = false;
+        else if (name == "cache-control") { const std::string v = lower(val); if (v.find("no-cache") != std::string::npos || v.find("no-store") != std::string::npos || v.find("private") != std::string::npos) cacheable = false; }
+    }
+    if (!cacheable || clen < 0) { close(fd); return status == 200 ? 502 : status; }   // uncached relays are not implemented: fail open to the client as 502
+    // stream the body into the arena through a pinned window
+    nz_put* put = nullptr;
+    if (nz_put_begin(S.ctx, key128, (uint64_t)clen, (uint64_t)clen, meta.stored_gzip ? NZ_ENC_GZIP : NZ_ENC_IDENTITY, 0, &put) != NZ_OK) {
+        close(fd);
+        return 502;
+    }
+    nz_buf* win = nullptr;
+    {
+        std::lock_guard<std::mutex> g(S.win_mu);
+        if (!S.free_windows.empty()) { win = S.free_windows.back(); S.free_windows.pop_back(); }
+    }
+    if (!win && nz_buf_alloc(S.ctx, S.opt.window_bytes, NZ_BUF_PINNED_HOST, &win) != NZ_OK) { nz_put_abort(put); close(fd); return 502; }
+    char* wp = static_cast<char*>(nz_buf_ptr(win));
+    uint64_t off = 0;
+    bool ok = true;
+    size_t have = std::min<size_t>(rest.size(), (size_t)clen);
+    if (have) memcpy(wp, rest.data(), have);
+    while (ok && off < (uint64_t)clen) {
+        while (have < S.opt.window_bytes && off + have < (uint64_t)clen) {
+            ssize_t r = recv(fd, wp + have, std::min<uint64_t>(S.opt.window_bytes - have, (uint64_t)clen - off - have), 0);
+            if (r <= 0) { ok = false; break; }
+            have += (size_t)r;
+        }
+        if (!ok) break;
+        if (nz_put_write(put, wp, off, have) != NZ_OK) { ok = false; break; }
+        if (nz_put_sync(put) != NZ_OK) { ok = false; break; }   // the window is reused: its H2D copy must have left it
+        off += have;
+        have = 0;
+    }
+    close(fd);
+    {
+        std::lock_guard<std::mutex> g(S.win_mu);
+        S.free_windows.push_back(win);
+    }
+    if (!ok) { nz_put_abort(put); return 502; }
+    uint32_t crc = 0;
+    if (nz_put_commit(put, 0, 0, &crc) != NZ_OK) return 502;
+    meta.stored_length = (uint64_t)clen;
+    meta.raw_length = -1;
+    if (meta.stored_gzip) {   // learn the inflated length from a lookup of the ISIZE trailer is host work: read last 4 bytes
+        // ISIZE is in the last 4 stored bytes; fetch them through a tiny GET
+        nz_buf* tb = nullptr;
+        if (clen >= 18 && nz_buf_alloc(S.ctx, 64, NZ_BUF_PINNED_HOST, &tb) == NZ_OK) {
+            nz_get_req rq;
+            memset(&rq, 0, sizeof rq);
+            memcpy(rq.key, key128, 16);
+            nz_seg sg = {(uint64_t)clen - 4, 4, 0};
+            rq.nseg = 1; rq.segs = &sg; rq.dst = tb;
+            nz_ticket* t = nullptr;
+            nz_get_res rs;
+            if (nz_get_submit(S.ctx, &rq, 1, nullptr, &t) == NZ_OK) {
+                if (nz_get_wait(t, -1, &rs) == NZ_OK && rs.status == NZ_OK) {
+                    uint32_t isz;
+                    memcpy(&isz, nz_buf_ptr(tb), 4);
+                    meta.raw_length = isz;
+                }
+                nz_ticket_free(t);
+            }
+            nz_buf_free(tb);
+        }
+    }
+    auto e = std::make_shared<Entry>();
+    e->meta = meta;
+    memcpy(e->key128, key128, 16);
+    e->stored_at = time(nullptr);
+    {
+        std::lock_guard<std::mutex> g(S.mu);
+        Key16 k;
+        memcpy(k.b, key128, 16);
+        S.index[k] = e;
+    }
+    out = e;
+    return 200;
+}
+
+// ---- serving -------------------------------------------------------------------
+bool send_plan(Server& S, int fd, const nzh::Plan& plan, const Entry* ent, bool keep_alive, nz_buf* win[2]) {
+    std::string h = std::string("HTTP/1.1 ") + std::to_string(plan.status) + " " + status_text(plan.status) + "\r\nServer: nginx\r\nDate: " +
+                    http_date(time(nullptr)) + "\r\n";
+    for (const auto& kv : plan.headers) h += kv.first + ": " + kv.second + "\r\n";
+    h += keep_alive ? "Connection: keep-alive\r\n" : "Connection: close\r\n";
+    h += "\r\n";
+    if (plan.head || plan.body.empty()) return write_all(fd, h.data(), h.size());
+    // literals are tiny; slices stream through the two pinned windows.  The header goes out with
+    // the first bytes of the body.
+    std::string pending = h;
+    const uint32_t flags = (plan.inflated ? NZ_GET_INFLATE : 0) | (S.opt.verify ? NZ_GET_VERIFY : 0);
+    for (const nzh::Part& part : plan.body) {
+        if (part.literal) { pending += part.bytes; continue; }
+        uint64_t off = part.off, left = part.len;
+        nz_ticket* tk[2] = {nullptr, nullptr};
+        uint64_t tk_len[2] = {0, 0};
+        int cur = 0;
+        bool first = true;
+        auto submit = [&](int slot) -> bool {
+            if (!left) { tk[slot] = nullptr; return true; }
+            const uint64_t n = std::min<uint64_t>(left, first ? S.opt.first_window : S.opt.window_bytes);
+            first = false;
+            nz_get_req rq;
+            memset(&rq, 0, sizeof rq);
+            memcpy(rq.key, ent->key128, 16);
+            rq.flags = flags;
+            nz_seg sg = {off, n, 0};
+            rq.nseg = 1; rq.segs = &sg; rq.dst = win[slot];
+            if (nz_get_submit(S.ctx, &rq, 1, nullptr, &tk[slot]) != NZ_OK) return false;
+            tk_len[slot] = n;
+            off += n;
+            left -= n;
+            return true;
+        };
+        if (!submit(0)) return false;
+        while (tk[cur]) {
+            if (!submit(cur ^ 1)) { nz_ticket_free(tk[cur]); return false; }        // next window in flight while this one is sent
+            nz_get_res rs;
+            const int32_t rc = nz_get_wait(tk[cur], -1, &rs);
+            nz_ticket_free(tk[cur]);
+            tk[cur] = nullptr;
+            if (rc != NZ_OK || rs.status != NZ_OK) {
+                if (tk[cur ^ 1]) { nz_get_wait(tk[cur ^ 1], -1, nullptr); nz_ticket_free(tk[cur ^ 1]); }
+                return false;                                                         // mid-body failure: drop the connection
+            }
+            if (!pending.empty()) {
+                if (!write_all(fd, pending.data(), pending.size())) { if (tk[cur ^ 1]) { nz_get_wait(tk[cur ^ 1], -1, nullptr); nz_ticket_free(tk[cur ^ 1]); } return false; }
+                pending.clear();
+            }
+            if (!write_all(fd, nz_buf_ptr(win[cur]), tk_len[cur])) { if (tk[cur ^ 1]) { nz_get_wait(tk[cur ^ 1], -1, nullptr); nz_ticket_free(tk[cur ^ 1]); } return false; }
+            S.bytes_out += tk_len[cur];
+            cur ^= 1;
+        }
+    }
+    if (!pending.empty() && !write_all(fd, pending.data(), pending.size())) return false;
+    return true;
+}
+
+void serve_connection(Server* Sp, int fd, std::string client_ip) {
+    Server& S = *Sp;
+    int one = 1;
+    setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
+    int sndbuf = 4 << 20;
+    setsockopt(fd, SOL_SOCKET, SO_SNDBUF, &sndbuf, sizeof sndbuf);
+    nz_buf* win[2] = {nullptr, nullptr};
+    {
+        std::lock_guard<std::mutex> g(S.win_mu);
+        for (int i = 0; i < 2 && !S.free_windows.empty(); ++i) { win[i] = S.free_windows.back(); S.free_windows.pop_back(); }
+    }
+    for (int i = 0; i < 2; ++i)
+        if (!win[i] && nz_buf_alloc(S.ctx, S.opt.window_bytes, NZ_BUF_PINNED_HOST, &win[i]) != NZ_OK) win[i] = nullptr;
+    std::string inbuf;
+    std::vector<char> tmp(16384);
+    bool alive = win[0] && win[1];
+    while (alive) {
+        size_t end;
+        while ((end = inbuf.find("\r\n\r\n")) == std::string::npos) {
+            if (inbuf.size() > 32768) { alive = false; break; }
+            ssize_t r = recv(fd, tmp.data(), tmp.size(), 0);
+            if (r <= 0) { alive = false; break; }
+            inbuf.append(tmp.data(), (size_t)r);
+        }
+        if (!alive) break;
+        const std::string head = inbuf.substr(0, end + 2);
+        inbuf.erase(0, end + 4);
+        Parsed pr = parse_head(head);
+        nzh::Plan plan;
+        std::shared_ptr<Entry> ent;
+        bool keep = pr.keep_alive;
+        auto stock = [&](int code) { plan = nzh::error_page(code, pr.ok && pr.rq.method == "HEAD"); };
+        if (!pr.ok) {
+            stock(400);
+            keep = false;
+        } else if (!nzh::method_allowed(pr.rq.method) || (pr.rq.method != "GET" && pr.rq.method != "HEAD")) {
+            stock(405);
+        } else {
+            int vhost = 0;
+            auto key = nzh::cache_key(S.cfg, pr.rq.host, pr.rq.target, &vhost);
+            if (!key) {
+                stock(400);
+                keep = false;
+            } else {
+                Key16 k;
+                nzh::md5(key->data(), key->size(), k.b);
+                {
+                    std::lock_guard<std::mutex> g(S.mu);
+                    auto it = S.index.find(k);
+                    if (it != S.index.end()) ent = it->second;
+                }
+                if (ent && time(nullptr) - ent->stored_at > 86400) ent.reset();   // proxy_cache_valid 200 1d: expired -> refetch
+                int st = 200;
+                if (!ent) {
+                    S.misses++;
+                    std::lock_guard<std::mutex> g(S.fill_mu);
+                    {
+                        std::lock_guard<std::mutex> g2(S.mu);
+                        auto it = S.index.find(k);
+                        if (it != S.index.end()) ent = it->second;      // filled by a concurrent request while we waited
+                    }
+                    if (!ent) {
+                        // $host for the upstream Host header = request host (proxy_set_header Host $host)
+                        std::string host = key->substr(0, key->find('/'));
+                        st = fill_from_origin(S, vhost, host, pr.rq.target, client_ip, k.b, ent);
+                    }
+                } else {
+                    S.hits++;
+                }
+                if (!ent) {
+                    stock(st == 200 ? 502 : st);
+                } else {
+                    nzh::Config cfg = S.cfg;
+                    cfg.gunzip = S.opt.gunzip;
+                    plan = nzh::plan_response(cfg, pr.rq, ent->meta, S.boundary.fetch_add(1));
+                }
+            }
+        }
+        if (pr.ok && pr.rq.http_minor < 1) keep = false;
+        if (!send_plan(S, fd, plan, ent.get(), keep, win)) break;
+        if (!keep) break;
+    }
+    {
+        std::lock_guard<std::mutex> g(S.win_mu);
+        for (int i = 0; i < 2; ++i) if (win[i]) S.free_windows.push_back(win[i]);
+    }
+    shutdown(fd, SHUT_RDWR);
+    close(fd);
+    S.conns--;
+}
+
+void usage() {
+    fprintf(stderr,
+            "nzproxy [--listen ip:port] [--device N] [--arena-gib G] [--max-objects N] [--window-mib M] [--first-window-kib K]\n"
+            "        [--max-conns N] [--gunzip] [--verify] [--upstream proxy_host=ip:port]...\n");
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    signal(SIGPIPE, SIG_IGN);
+    Server S;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto next = [&]() -> const char* { if (i + 1 >= argc) { usage(); exit(2); } return argv[++i]; };
+        if (a == "--listen") {
+            const std::string v = next();
+            const size_t c = v.rfind(':');
+            if (c == std::string::npos) S.opt.port = atoi(v.c_str());
+            else { S.opt.listen_ip = v.substr(0, c); S.opt.port = atoi(v.c_str() + c + 1); }
+        } else if (a == "--device") S.opt.device = atoi(next());
+        else if (a == "--arena-gib") S.opt.arena_bytes = (uint64_t)(atof(next()) * (1ull << 30));
+        else if (a == "--max-objects") S.opt.max_objects = (uint32_t)atoi(next());
+        else if (a == "--window-mib") S.opt.window_bytes = (uint64_t)(atof(next()) * (1ull << 20));
+        else if (a == "--first-window-kib") S.opt.first_window = (uint64_t)atoll(next()) << 10;
+        else if (a == "--max-conns") S.opt.max_conns = atoi(next());
+        else if (a == "--gunzip") S.opt.gunzip = true;
+        else if (a == "--verify") S.opt.verify = true;
+        else if (a == "--upstream") {
+            const std::string v = next();
+            const size_t e = v.find('=');
+            if (e == std::string::npos) { usage(); return 2; }
+            S.opt.upstream[v.substr(0, e)] = v.substr(e + 1);
+        } else { usage(); return 2; }
+    }
+    if (S.opt.first_window > S.opt.window_bytes) S.opt.first_window = S.opt.window_bytes;
+    nz_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.struct_size = sizeof cfg;
+    cfg.device = S.opt.device;
+    cfg.arena_bytes = S.opt.arena_bytes;
+    cfg.max_objects = S.opt.max_objects;
+    int32_t rc = nz_init(&cfg, &S.ctx);
+    if (rc != NZ_OK) {
+        fprintf(stderr, "nzproxy: nz_init failed: %s (%s) - there is no CPU fallback\n", nz_strerror(rc), nz_last_error());
+        return 1;
+    }
+    for (int i = 0; i < std::min(S.opt.max_conns, 160) * 2; ++i) {   // pinned windows up front: cudaHostAlloc is slow
+        nz_buf* b = nullptr;
+        if (nz_buf_alloc(S.ctx, S.opt.window_bytes, NZ_BUF_PINNED_HOST, &b) != NZ_OK) break;
+        S.free_windows.push_back(b);
+    }
+    int ls = socket(AF_INET, SOCK_STREAM, 0);
+    int one = 1;
+    setsockopt(ls, SOL_SOCKET, SO_REUSEADDR, &one, sizeof one);
+    struct sockaddr_in sa;
+    memset(&sa, 0, sizeof sa);
+    sa.sin_family = AF_INET;
+    sa.sin_port = htons((uint16_t)S.opt.port);
+    inet_pton(AF_INET, S.opt.listen_ip.c_str(), &sa.sin_addr);
+    if (bind(ls, (struct sockaddr*)&sa, sizeof sa) != 0 || listen(ls, 1024) != 0) {
+        perror("nzproxy: bind/listen");
+        return 1;
+    }
+    fprintf(stderr, "nzproxy: listening on %s:%d, device %d, arena %.1f GiB, %zu pinned windows of %.1f MiB\n", S.opt.listen_ip.c_str(),
+            S.opt.port, S.opt.device, S.opt.arena_bytes / 1073741824.0, S.free_windows.size(), S.opt.window_bytes / 1048576.0);
+    fflush(stderr);
+    for (;;) {
+        struct sockaddr_in ca;
+        socklen_t cl = sizeof ca;
+        int fd = accept(ls, (struct sockaddr*)&ca, &cl);
+        if (fd < 0) {
+            if (errno == EINTR) continue;
+            break;
+        }
+        if (S.conns.load() >= S.opt.max_conns) { close(fd); continue; }   // worker_connections analogue
+        S.conns++;
+        char ip[64];
+        inet_ntop(AF_INET, &ca.sin_addr, ip, sizeof ip);
+        std::thread(serve_connection, &S, fd, std::string(ip)).detach();
+    }
+    nz_shutdown(S.ctx);
+    return 0;
+}
