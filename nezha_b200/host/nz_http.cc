@@ -407,6 +407,7 @@ bool etag_in_list(std::string_view list, const std::optional<std::string>& etag,
 const char* reason_phrase(int code) {
     switch (code) {
     case 400: return "Bad Request";
+    case 404: return "Not Found";
     case 405: return "Not Allowed";
     case 412: return "Precondition Failed";
     case 416: return "Requested Range Not Satisfiable";

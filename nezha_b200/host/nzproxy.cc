@@ -114,6 +114,7 @@ const char* status_text(int code) {
     case 206: return "Partial Content";
     case 304: return "Not Modified";
     case 400: return "Bad Request";
+    case 404: return "Not Found";
     case 405: return "Not Allowed";
     case 412: return "Precondition Failed";
     case 416: return "Requested Range Not Satisfiable";

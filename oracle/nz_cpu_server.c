@@ -20,6 +20,7 @@
  */
 #define _GNU_SOURCE
 #include <arpa/inet.h>
+#include <ctype.h>
 #include <errno.h>
 #include <fcntl.h>
 #include <netinet/in.h>
@@ -30,6 +31,7 @@
 #include <string.h>
 #include <strings.h>
 #include <sys/epoll.h>
+#include <sys/prctl.h>
 #include <sys/socket.h>
 #include <sys/wait.h>
 #include <time.h>
@@ -239,6 +241,7 @@ done:
 
 /* push as much of the response as the socket takes; 1 = finished, 0 = would block, -1 = error */
 static int pump(conn* c) {
+    int budget = 16;   /* output buffers per event: round-robin fairness between connections of one worker */
     for (;;) {
         if (c->head_off < c->head_len) {
             ssize_t w = send(c->fd, c->head + c->head_off, (size_t)(c->head_len - c->head_off), MSG_NOSIGNAL);
@@ -255,6 +258,7 @@ static int pump(conn* c) {
         if (c->cur >= c->nseg) return 1;
         seg* s = &c->segs[c->cur];
         if (c->seg_done >= s->len) { c->cur++; c->seg_done = 0; continue; }
+        if (budget-- == 0) return 0;   /* yield; level-triggered EPOLLOUT brings us straight back */
         /* fill the other output buffer: the read loop of SPEC B1 */
         c->out_which ^= 1;
         int64_t want = s->len - c->seg_done;
@@ -353,7 +357,7 @@ int main(int argc, char** argv) {
         if (bind(ls, (struct sockaddr*)&sa, sizeof sa) || listen(ls, 1024)) { perror("bind/listen"); return 1; }
         if (workers == 1) { worker(ls); return 0; }
         pid_t p = fork();
-        if (p == 0) { worker(ls); _exit(0); }
+        if (p == 0) { prctl(PR_SET_PDEATHSIG, SIGTERM); worker(ls); _exit(0); }
         close(ls);
     }
     while (wait(NULL) > 0) {}

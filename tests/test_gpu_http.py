@@ -1,0 +1,205 @@
+"""-m gpu: HTTP-level differential replay (SURVEY.md §4 item 3, §8c parity definition).
+
+The same request log is sent to
+  * nzproxy          — the product: C++ front end over the C ABI, bodies from HBM, and
+  * nz_cpu_server    — the oracle's nginx-restated CPU server (pread 32 KiB + send),
+and status, the header subset {Content-Length, Content-Range, Content-Type, ETag,
+Last-Modified, Accept-Ranges, Content-Encoding} and the body SHA-256 must agree
+(multipart boundaries normalised; Date/Server/Connection ignored).  nzproxy starts
+cold, so the first GET of every object exercises the miss -> origin fetch -> fill path.
+"""
+import hashlib
+import http.client
+import http.server
+import os
+import re
+import signal
+import socket
+import subprocess
+import threading
+import time
+
+import pytest
+
+from nezha_b200 import workloads as wl
+from oracle import oracle as o
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LM = "Wed, 07 Nov 2018 15:20:01 GMT"
+SUBSET = ["content-length", "content-range", "content-type", "etag", "last-modified", "accept-ranges", "content-encoding"]
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def wait_port(port, timeout=60):
+    t0 = time.time()
+    while time.time() - t0 < timeout:
+        try:
+            socket.create_connection(("127.0.0.1", port), 0.2).close()
+            return
+        except OSError:
+            time.sleep(0.1)
+    raise RuntimeError(f"port {port} never opened")
+
+
+OBJECTS = {
+    # path -> (host, bytes, content-type, etag, encoding)
+    "/~kriz/cifar-100-python.tar.gz": ("www.cs.toronto.edu", wl.synth_bytes(3_000_017, 1).tobytes(), "application/x-gzip", '"5be2f2c5-a12c15d"', None),
+    "/exdb/mnist/train-images-idx3-ubyte.gz": ("yann.lecun.com", wl.synth_bytes(70_001, 2).tobytes(), "application/octet-stream", None, None),
+    "/bucket/big.bin": ("storage.googleapis.com", wl.synth_bytes(20 << 20, 3).tobytes(), "application/octet-stream", '"big"', None),
+    "/bucket/empty": ("storage.googleapis.com", b"", "application/octet-stream", '"e"', None),
+    "/zips/text.json.gz": ("images.cocodataset.org", wl.gzip_member(wl.text_like(500_000, 9)), "application/json", '"gz1"', "gzip"),
+}
+
+
+class Origin(http.server.BaseHTTPRequestHandler):
+    protocol_version = "HTTP/1.0"
+    hits = {}
+
+    def do_GET(self):
+        path = self.path.split("?")[0]
+        Origin.hits[path] = Origin.hits.get(path, 0) + 1
+        ent = OBJECTS.get(path)
+        if not ent:
+            self.send_response(404)
+            self.send_header("Content-Length", "0")
+            self.end_headers()
+            return
+        _, data, ctype, etag, enc = ent
+        self.send_response(200)
+        self.send_header("Content-Type", ctype)
+        self.send_header("Content-Length", str(len(data)))
+        if etag:
+            self.send_header("ETag", etag)
+        self.send_header("Last-Modified", LM)
+        if enc:
+            self.send_header("Content-Encoding", enc)
+        self.end_headers()
+        self.wfile.write(data)
+
+    def log_message(self, *a):
+        pass
+
+
+@pytest.fixture(scope="module")
+def servers(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cache")
+    lines = []
+    for path, (host, data, ctype, etag, enc) in OBJECTS.items():
+        key = o.cache_key(host, path)
+        hx = o.md5(key).hex()
+        (d / hx).write_bytes(data)
+        raw = len(o.gunzip(data)) if enc else -1
+        lines.append(f"{hx} {len(data)} {raw} {ctype} {etag or '-'} {enc or '-'} {LM}")
+    (d / "manifest").write_text("\n".join(lines) + "\n")
+    origin_port, gpu_port, cpu_port = free_port(), free_port(), free_port()
+    httpd = http.server.ThreadingHTTPServer(("127.0.0.1", origin_port), Origin)
+    threading.Thread(target=httpd.serve_forever, daemon=True).start()
+    ups = []
+    for h in {v[0] for v in OBJECTS.values()}:
+        ups += ["--upstream", f"{h}=127.0.0.1:{origin_port}"]
+    procs = [
+        subprocess.Popen([os.path.join(ROOT, "nezha_b200", "_build", "nzproxy"), "--listen", f"127.0.0.1:{gpu_port}", "--arena-gib", "1",
+                          "--max-conns", "32", "--window-mib", "1", "--first-window-kib", "64", "--verify"] + ups, start_new_session=True),
+        subprocess.Popen([os.path.join(ROOT, "oracle", "_build", "nz_cpu_server"), "--root", str(d), "--listen", f"127.0.0.1:{cpu_port}"],
+                         start_new_session=True),
+    ]
+    try:
+        wait_port(cpu_port)
+        wait_port(gpu_port, 120)
+        yield gpu_port, cpu_port
+    finally:
+        for p in procs:
+            try:
+                os.killpg(p.pid, signal.SIGTERM)
+            except ProcessLookupError:
+                pass
+        httpd.shutdown()
+
+
+def fetch(port, method, host, target, headers):
+    c = http.client.HTTPConnection("127.0.0.1", port, timeout=60)
+    c.putrequest(method, target, skip_host=True, skip_accept_encoding=True)
+    if host is not None:
+        c.putheader("Host", host)
+    for k, v in headers.items():
+        c.putheader(k, v)
+    c.endheaders()
+    r = c.getresponse()
+    body = r.read()
+    hd = {k.lower(): v for k, v in r.getheaders()}
+    c.close()
+    return r.status, hd, body
+
+
+def normalise(hd, body):
+    ct = hd.get("content-type", "")
+    m = re.match(r"multipart/byteranges; boundary=(\d{20})$", ct)
+    if m:
+        b = m.group(1).encode()
+        body = body.replace(b, b"B" * 20)
+        hd = dict(hd)
+        hd["content-type"] = "multipart/byteranges; boundary=" + "B" * 20
+    return {k: hd.get(k) for k in SUBSET}, hashlib.sha256(body).hexdigest(), len(body)
+
+
+LOG = []
+for _path, (_host, _data, *_r) in OBJECTS.items():
+    n = len(_data)
+    LOG += [("GET", _host, _path, {}), ("HEAD", _host, _path, {}), ("GET", _host, _path, {"Range": "bytes=0-0"}),
+            ("GET", _host, _path, {"Range": f"bytes={max(n - 5, 0)}-"}), ("GET", _host, _path, {"Range": "bytes=-7"}),
+            ("GET", _host, _path, {"Range": f"bytes={n}-"}), ("GET", _host, _path + "?alt=media", {"Range": "bytes=1-3,10-12,100-"}),
+            ("GET", _host, _path, {"If-Modified-Since": LM}), ("GET", _host, _path, {"If-None-Match": "*"}),
+            ("GET", _host, _path, {"If-Match": '"nope"'}), ("GET", _host.upper() + ":80", _path, {"Range": "bytes=5-4"}),
+            ("GET", _host, "//" + _path.lstrip("/").replace("/", "/./", 1), {"Range": "bytes=65530-65540"})]
+LOG += [
+    ("GET", "www.cs.toronto.edu", "/~kriz/cifar-100-python.tar.gz", {"Range": "bytes=7-2000000", "If-Range": '"5be2f2c5-a12c15d"'}),
+    ("GET", "www.cs.toronto.edu", "/~kriz/cifar-100-python.tar.gz", {"Range": "bytes=7-2000000", "If-Range": '"other"'}),
+    ("GET", "www.cs.toronto.edu", "/~kriz/cifar-100-python.tar.gz", {"Range": "bytes=1000000-1000099,5-70000, 2999999-"}),
+    ("GET", "storage.googleapis.com", "/bucket/big.bin", {"Range": "bytes=1048575-9437184"}),
+    ("GET", "storage.googleapis.com", "/bucket/big.bin", {"Range": "bytes=0-20971519"}),
+    ("POST", "www.cs.toronto.edu", "/~kriz/cifar-100-python.tar.gz", {}),
+    ("GET", "www.cs.toronto.edu", "/../etc/passwd", {}),
+    ("GET", "images.cocodataset.org", "/zips/text.json.gz", {"Accept-Encoding": "gzip"}),
+]
+
+
+def test_differential_replay(servers):
+    gpu, cpu = servers
+    for method, host, target, hdrs in LOG:
+        sg, hg, bg = fetch(gpu, method, host, target, hdrs)
+        sc, hc, bc = fetch(cpu, method, host, target, hdrs)
+        assert sg == sc, (method, host, target, hdrs, sg, sc)
+        assert normalise(hg, bg) == normalise(hc, bc), (method, host, target, hdrs)
+        assert hg.get("server") == "nginx"
+    # every object was fetched from the origin exactly once (miss -> fill -> hits)
+    for path in OBJECTS:
+        assert Origin.hits.get(path) == 1, (path, Origin.hits)
+
+
+def test_bodies_match_source_and_keepalive(servers):
+    gpu, _ = servers
+    c = http.client.HTTPConnection("127.0.0.1", gpu, timeout=60)
+    for path, (host, data, *_r) in OBJECTS.items():
+        for _ in range(2):                                   # same connection: keep-alive
+            c.request("GET", path, headers={"Host": host})
+            r = c.getresponse()
+            assert r.status == 200 and r.read() == data
+    c.request("GET", "/bucket/big.bin", headers={"Host": "storage.googleapis.com", "Range": "bytes=12345-7654321"})
+    r = c.getresponse()
+    assert r.status == 206 and r.read() == OBJECTS["/bucket/big.bin"][1][12345:7654322]
+    c.close()
+
+
+def test_origin_404_is_not_cached(servers):
+    gpu, _ = servers
+    s1, _, _ = fetch(gpu, "GET", "yann.lecun.com", "/nope", {})
+    s2, _, _ = fetch(gpu, "GET", "yann.lecun.com", "/nope", {})
+    assert s1 == 404 and s2 == 404 and Origin.hits.get("/nope") == 2      # proxy_cache_valid 200 only
