@@ -389,6 +389,13 @@ def run_ours(args):
         cpu = {"value": r["gbs"], "unit": "GB/s", "cores": threads, "kind": "port", "sample": r["sample"],
                "one_worker_gbs": r1["gbs"], "one_worker_note": "worker_processes 1 (nginx.conf:2): the reference's actual configuration"}
 
+    http = None
+    if rank == 0 and world == 1 and not args.no_http:
+        dbuf.free()
+        zone.close()
+        zone = None
+        os.sched_setaffinity(0, all_cpus)
+        http = http_bench(L_obj, reqs, local)
     if rank == 0:
         line = {
             "metric": "cached-GET GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
@@ -398,15 +405,133 @@ def run_ours(args):
                        "object_bytes": L_obj, "requests": len(reqs), "payload_bytes_per_gpu_step": payload,
                        "response_buffers": "HBM", "l2": "inputs larger than L2 (1 GiB object, 33 GiB written per step); no flush needed",
                        "sharding": f"key-hash x{world}, no data-path collective"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "ttfb": ttfb, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "ttfb": ttfb, "http": http, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "numa_node": numa, "fill_gbs": L_obj / fill_s / 1e9, "object_crc32c": f"{crc:08x}",
         }
         print(json.dumps(line), flush=True)
-    dbuf.free()
-    zone.close()
+    if zone is not None:
+        dbuf.free()
+        zone.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+# --------------------------------------------------------------------------- #
+# HTTP level: the metric at the wire (GB/s and p50 TTFB), GPU proxy vs restated CPU server
+# --------------------------------------------------------------------------- #
+def http_bench(L_obj, requests, device, seed=2):
+    """nzload (64 keep-alive connections, the C2 log) against nzproxy (bodies from HBM) and
+    against oracle/nz_cpu_server (pread 32 KiB + send) with 1 worker (nginx.conf:2) and with
+    one worker per core.  Loopback TCP on the same box, same run."""
+    import http.server
+    import shutil
+    import signal
+    import socket
+    import tempfile
+    import threading
+    import hashlib
+
+    from nezha_b200 import workloads as wl
+
+    def free_port():
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+    def wait_port(port, timeout=120):
+        t0 = time.time()
+        while time.time() - t0 < timeout:
+            try:
+                socket.create_connection(("127.0.0.1", port), 0.2).close(); return True
+            except OSError:
+                time.sleep(0.1)
+        return False
+
+    base = "/dev/shm" if os.access("/dev/shm", os.W_OK) else "/tmp"
+    d = tempfile.mkdtemp(prefix="nezha_http_", dir=base)
+    procs = []
+    out = {}
+    try:
+        path = "/nezha-bench/c2/obj-00000000.bin"
+        host = "storage.googleapis.com"
+        ks = wl.object_key_string("c2", 0)
+        hx = hashlib.md5(ks).hexdigest()
+        data = wl.synth_bytes(L_obj, seed)
+        with open(os.path.join(d, hx), "wb") as f:
+            f.write(memoryview(data))
+        del data
+        with open(os.path.join(d, "manifest"), "w") as f:
+            f.write(f'{hx} {L_obj} -1 application/octet-stream "c2-obj-0" - Wed, 07 Nov 2018 15:20:01 GMT\n')
+        with open(os.path.join(d, "log"), "w") as f:
+            for r in requests:
+                f.write(f"{host} {path} {'-' if r is None else f'bytes={r[0]}-{r[0] + r[1] - 1}'}\n")
+        nconn = len(requests)
+        nzload = os.path.join(ROOT, "nezha_b200", "_build", "nzload")
+
+        class Origin(http.server.BaseHTTPRequestHandler):
+            protocol_version = "HTTP/1.0"
+
+            def do_GET(self):
+                self.send_response(200)
+                self.send_header("Content-Type", "application/octet-stream")
+                self.send_header("Content-Length", str(L_obj))
+                self.send_header("ETag", '"c2-obj-0"')
+                self.send_header("Last-Modified", "Wed, 07 Nov 2018 15:20:01 GMT")
+                self.end_headers()
+                with open(os.path.join(d, hx), "rb") as fh:
+                    shutil.copyfileobj(fh, self.wfile, 4 << 20)
+
+            def log_message(self, *a):
+                pass
+
+        oport, gport = free_port(), free_port()
+        httpd = http.server.ThreadingHTTPServer(("127.0.0.1", oport), Origin)
+        threading.Thread(target=httpd.serve_forever, daemon=True).start()
+
+        def load(port, repeat, warmup):
+            r = subprocess.run([nzload, "--target", f"127.0.0.1:{port}", "--conns", str(nconn), "--log", os.path.join(d, "log"),
+                                "--repeat", str(repeat), "--warmup", str(warmup)], capture_output=True, text=True, timeout=600)
+            return json.loads(r.stdout.strip().splitlines()[-1])
+
+        # ---- GPU proxy ----
+        p = subprocess.Popen([os.path.join(ROOT, "nezha_b200", "_build", "nzproxy"), "--listen", f"127.0.0.1:{gport}", "--device", str(device),
+                              "--arena-gib", str(L_obj / 2**30 + 0.5), "--max-conns", str(2 * nconn), "--window-mib", "4", "--first-window-kib", "256",
+                              "--upstream", f"{host}=127.0.0.1:{oport}"], start_new_session=True, stderr=subprocess.DEVNULL)
+        procs.append(p)
+        if wait_port(gport):
+            import http.client
+            t0 = time.perf_counter()
+            c = http.client.HTTPConnection("127.0.0.1", gport, timeout=300)
+            c.request("GET", path, headers={"Host": host, "Range": "bytes=0-0"})      # miss -> fill from the origin
+            c.getresponse().read()
+            c.close()
+            fill_s = time.perf_counter() - t0
+            out["gpu"] = load(gport, 2, 1)
+            out["gpu"]["fill_from_origin_s"] = fill_s
+        os.killpg(p.pid, signal.SIGTERM)
+        httpd.shutdown()
+        # ---- CPU servers ----
+        for name, workers, repeat in (("cpu_1worker", 1, 1), ("cpu_allcores", os.cpu_count() or 1, 2)):
+            cport = free_port()
+            p = subprocess.Popen([os.path.join(ROOT, "oracle", "_build", "nz_cpu_server"), "--root", d, "--listen", f"127.0.0.1:{cport}",
+                                  "--workers", str(workers)], start_new_session=True, stderr=subprocess.DEVNULL)
+            procs.append(p)
+            if wait_port(cport, 30):
+                out[name] = load(cport, repeat, 1 if workers > 1 else 0)
+                out[name]["workers"] = workers
+            os.killpg(p.pid, signal.SIGTERM)
+        out["note"] = ("loopback TCP, nzload with %d keep-alive connections replaying the C2 log; TTFB = request sent -> first response byte; "
+                       "cpu_* is the nginx-restated server (oracle/nz_cpu_server.c), not nginx" % nconn)
+    except Exception as e:      # the HTTP section must never take the kernel-level numbers down with it
+        out["error"] = repr(e)
+    finally:
+        import signal as _s
+        for p in procs:
+            try:
+                os.killpg(p.pid, _s.SIGKILL)
+            except Exception:
+                pass
+        shutil.rmtree(d, ignore_errors=True)
+    return out
 
 
 # --------------------------------------------------------------------------- #
@@ -536,6 +661,7 @@ def main():
     ap.add_argument("--requests", type=int, default=64)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-http", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
     ap.add_argument("--c3-objects", type=int, default=10_000)
