@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <errno.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
 
@@ -131,7 +132,11 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
     c->free_by_off[0] = c->arena_bytes;
     c->free_desc.reserve(c->cfg.max_objects);
     for (uint32_t i = c->cfg.max_objects; i-- > 0;) c->free_desc.push_back(i);
-    c->gather_grid = c->sm_count * nz_gather_blocks_per_sm();
+    if (const char* ev = getenv("NZ_GATHER_VARIANT")) {
+        const int v = atoi(ev);
+        if (v >= 0 && v < nz_gather_num_variants()) c->gather_variant = v;
+    }
+    c->gather_grid = c->sm_count * nz_gather_blocks_per_sm(c->gather_variant);
     c->inflate_grid = c->sm_count * nz_inflate_blocks_per_sm();
     *out = c;
     return NZ_OK;
@@ -727,6 +732,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     a.infl = reinterpret_cast<NzInflWork*>(dv + dev_work + dev_tiles + dev_ver + dev_cnt);
     a.infl_meta = reinterpret_cast<uint64_t*>(a.infl + n) + 2 * (size_t)n;   // after rq_src, rq_len
     a.peer_base = c->peer_base_dev;
+    a.tile_bytes = nz_gather_tile_bytes(c->gather_variant);
 
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : c->streams[c->rr.fetch_add(1) % c->streams.size()];
     t->stream = s;
@@ -744,7 +750,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
         c->launches += 2;
     }
     CKT(cudaEventRecord(t->ev_g0, s));
-    CKT(nz_launch_gather(a.work, a.tile_begin, a.nseg, c->gather_grid, s));
+    CKT(nz_launch_gather(c->gather_variant, a.work, a.tile_begin, a.nseg, c->gather_grid, s));
     CKT(cudaEventRecord(t->ev_g1, s));
     c->launches += 1;
     if (any_verify && ver_cap) {

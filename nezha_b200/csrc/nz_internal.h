@@ -95,9 +95,6 @@ struct __align__(16) NzVerWork {
     uint32_t pad;
 };
 
-constexpr uint32_t NZ_TILE = 32768;          // gather tile (bytes of destination)
-constexpr int NZ_GATHER_THREADS = 256;
-constexpr int NZ_GATHER_UNROLL = 8;          // 16 B vectors in flight per thread
 
 // ---------------------------------------------------------------------------
 // host context
@@ -162,6 +159,7 @@ struct nz_ctx {
     int device;
     int sm_count;
     int gather_grid;       // persistent grid size for k_gather
+    int gather_variant = 0; // index into the k_gather variant table (env NZ_GATHER_VARIANT for sweeps)
     int inflate_grid;
     uint8_t* arena = nullptr;
     uint64_t arena_bytes = 0;
@@ -210,6 +208,7 @@ struct NzPlanArgs {
     NzInflWork* infl;           // capacity n
     uint32_t* counters;         // [0]=n_ver [1]=n_infl [2]=inflate work-steal cursor
     uint64_t* infl_meta;        // n: (produced length << 32) | trailer CRC-32, written by k_inflate
+    uint32_t tile_bytes;        // gather tile size of the selected k_gather variant
     const uint64_t* peer_base;  // device array [shard_count]: base address of every shard's arena (own + IPC-mapped peers)
 };
 cudaError_t nz_launch_lookup(const NzSlot* table, uint64_t line_mask, const NzDesc* descs, const uint64_t* keys,
@@ -218,7 +217,9 @@ cudaError_t nz_launch_insert(NzSlot* table, uint64_t line_mask, uint64_t k0, uin
                              int32_t* status, cudaStream_t s);
 cudaError_t nz_launch_erase(NzSlot* table, uint64_t line_mask, uint64_t k0, uint64_t k1, int32_t* status, cudaStream_t s);
 cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s);
-cudaError_t nz_launch_gather(const NzSegWork* work, const uint64_t* tile_begin, uint32_t nseg, int grid, cudaStream_t s);
+cudaError_t nz_launch_gather(int variant, const NzSegWork* work, const uint64_t* tile_begin, uint32_t nseg, int grid, cudaStream_t s);
+int nz_gather_num_variants();
+uint32_t nz_gather_tile_bytes(int variant);
 cudaError_t nz_launch_verify(const NzVerWork* ver, const uint32_t* counters, NzDevRes* res, const uint32_t* crc_tables,
                              int grid, cudaStream_t s);
 cudaError_t nz_launch_crc_chunks(const uint8_t* p, uint64_t n, uint32_t* chunk_out, uint32_t* whole_out,
@@ -227,5 +228,5 @@ cudaError_t nz_launch_inflate(const NzInflWork* infl, uint64_t* meta, uint32_t* 
                               const uint32_t* crc_tables, int grid, int sm_count, cudaStream_t s);
 cudaError_t nz_upload_constants(uint32_t* crc_tables_dev);
 cudaError_t nz_inflate_upload_constants();
-int nz_gather_blocks_per_sm();
+int nz_gather_blocks_per_sm(int variant);
 int nz_inflate_blocks_per_sm();

@@ -294,7 +294,7 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint6
                 w.dst = rq.dst + doff;
                 w.len = ok_len;
                 w.vstart = -(int64_t)(w.dst & 127u);
-                tiles = ok_len ? (ok_len + (w.dst & 127u) + NZ_TILE - 1) / NZ_TILE : 0;
+                tiles = ok_len ? (ok_len + (w.dst & 127u) + a.tile_bytes - 1) / a.tile_bytes : 0;
             }
             a.work[s] = w;
         }
@@ -381,43 +381,62 @@ __device__ __forceinline__ uint4 realign(const uint4 a, const uint4 b, unsigned 
     return o;
 }
 
-template <int WS>
+// cache-hint variants for the streaming loads/stores (HINT template parameter)
+template <int HINT>
+__device__ __forceinline__ uint4 ldg_s(const void* p) {
+    uint4 r;
+    if constexpr (HINT == 1)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+template <int HINT>
+__device__ __forceinline__ void stg_s(void* p, const uint4& v) {
+    if constexpr (HINT == 2)
+        asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else
+        asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int WS, int NT, int U2, int HINT>
 __device__ __forceinline__ void copy_vectors_shifted(const uint4* __restrict__ sa /*aligned base*/, uint4* __restrict__ d,
                                                      uint32_t nvec, unsigned bs) {
-    constexpr int U = NZ_GATHER_UNROLL / 2;   // two loads per output vector
-    constexpr uint32_t STEP = NZ_GATHER_THREADS * U;
+    constexpr int U = U2 > 1 ? U2 / 2 : 1;   // two loads per output vector
+    constexpr uint32_t STEP = NT * U;
     const uint32_t tid = threadIdx.x;
     uint32_t base = 0;
     for (; base + STEP <= nvec; base += STEP) {   // full steps: no predicates, all loads issued before any store
         uint4 lo[U], hi[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint32_t i = base + u * NZ_GATHER_THREADS + tid;
+            const uint32_t i = base + u * NT + tid;
             lo[u] = ldg_cached(sa + i);
             hi[u] = ldg_cached(sa + i + 1);
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) stg_stream(d + base + u * NZ_GATHER_THREADS + tid, realign<WS>(lo[u], hi[u], bs));
+        for (int u = 0; u < U; ++u) stg_s<HINT>(d + base + u * NT + tid, realign<WS>(lo[u], hi[u], bs));
     }
-    for (uint32_t i = base + tid; i < nvec; i += NZ_GATHER_THREADS)
-        stg_stream(d + i, realign<WS>(ldg_cached(sa + i), ldg_cached(sa + i + 1), bs));
+    for (uint32_t i = base + tid; i < nvec; i += NT)
+        stg_s<HINT>(d + i, realign<WS>(ldg_cached(sa + i), ldg_cached(sa + i + 1), bs));
 }
 
+template <int NT, int U, int HINT>
 __device__ __forceinline__ void copy_vectors_aligned(const uint4* __restrict__ sv, uint4* __restrict__ dv, uint32_t nvec) {
-    constexpr int U = NZ_GATHER_UNROLL;
-    constexpr uint32_t STEP = NZ_GATHER_THREADS * U;
+    constexpr uint32_t STEP = NT * U;
     const uint32_t tid = threadIdx.x;
     uint32_t base = 0;
     for (; base + STEP <= nvec; base += STEP) {
         uint4 v[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = ldg_stream(sv + base + u * NZ_GATHER_THREADS + tid);
+        for (int u = 0; u < U; ++u) v[u] = ldg_s<HINT>(sv + base + u * NT + tid);
 #pragma unroll
-        for (int u = 0; u < U; ++u) stg_stream(dv + base + u * NZ_GATHER_THREADS + tid, v[u]);
+        for (int u = 0; u < U; ++u) stg_s<HINT>(dv + base + u * NT + tid, v[u]);
     }
-    for (uint32_t i = base + tid; i < nvec; i += NZ_GATHER_THREADS) stg_stream(dv + i, ldg_stream(sv + i));
+    for (uint32_t i = base + tid; i < nvec; i += NT) stg_s<HINT>(dv + i, ldg_s<HINT>(sv + i));
 }
 
+template <int NT, int U, int HINT>
 __device__ __forceinline__ void copy_tile(const uint8_t* __restrict__ s, uint8_t* __restrict__ d, uint32_t n) {
     const uint32_t tid = threadIdx.x;
     // head: bring the destination to a 16 B boundary (only the first tile of a segment can need it)
@@ -431,45 +450,55 @@ __device__ __forceinline__ void copy_tile(const uint8_t* __restrict__ s, uint8_t
     const unsigned mis = (unsigned)((uintptr_t)s & 15u);
     uint4* dv = reinterpret_cast<uint4*>(d);
     if (mis == 0) {
-        copy_vectors_aligned(reinterpret_cast<const uint4*>(s), dv, nvec);
+        copy_vectors_aligned<NT, U, HINT>(reinterpret_cast<const uint4*>(s), dv, nvec);
     } else {
         const uint4* sa = reinterpret_cast<const uint4*>(s - mis);
         const unsigned bs = (mis & 3u) * 8u;
         switch (mis >> 2) {
-        case 0: copy_vectors_shifted<0>(sa, dv, nvec, bs); break;
-        case 1: copy_vectors_shifted<1>(sa, dv, nvec, bs); break;
-        case 2: copy_vectors_shifted<2>(sa, dv, nvec, bs); break;
-        default: copy_vectors_shifted<3>(sa, dv, nvec, bs); break;
+        case 0: copy_vectors_shifted<0, NT, U, HINT>(sa, dv, nvec, bs); break;
+        case 1: copy_vectors_shifted<1, NT, U, HINT>(sa, dv, nvec, bs); break;
+        case 2: copy_vectors_shifted<2, NT, U, HINT>(sa, dv, nvec, bs); break;
+        default: copy_vectors_shifted<3, NT, U, HINT>(sa, dv, nvec, bs); break;
         }
     }
 }
 
-__global__ void __launch_bounds__(NZ_GATHER_THREADS, 2)
-k_gather(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_begin, uint32_t nseg) {
-    const uint64_t total = tile_begin[nseg];
-    uint64_t lo_t = 0, hi_t = 0;   // tile range of the cached segment (empty at start)
-    uint64_t w_src = 0, w_dst = 0, w_len = 0;
-    int64_t w_vstart = 0;
-    for (uint64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        if (tile < lo_t || tile >= hi_t) {
-            // binary search: last seg with tile_begin[seg] <= tile (uniform across the CTA)
-            uint32_t a = 0, b = nseg;
-            while (b - a > 1) {
-                const uint32_t m = (a + b) >> 1;
-                if (__ldg(tile_begin + m) <= tile) a = m; else b = m;
-            }
-            lo_t = __ldg(tile_begin + a);
-            hi_t = __ldg(tile_begin + a + 1);
-            const ulonglong2 p0 = __ldg(reinterpret_cast<const ulonglong2*>(work + a));
-            const ulonglong2 p1 = __ldg(reinterpret_cast<const ulonglong2*>(work + a) + 1);
-            w_src = p0.x; w_dst = p0.y; w_len = p1.x; w_vstart = (int64_t)p1.y;
+// tile -> segment lookup shared by the gather variants (uniform across the CTA)
+struct TileCursor {
+    uint64_t lo_t = 0, hi_t = 0, src = 0, dst = 0, len = 0;
+    int64_t vstart = 0;
+    __device__ __forceinline__ void seek(uint64_t tile, const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_begin,
+                                         uint32_t nseg) {
+        if (tile >= lo_t && tile < hi_t) return;
+        uint32_t a = 0, b = nseg;
+        while (b - a > 1) {                    // last segment with tile_begin[seg] <= tile
+            const uint32_t m = (a + b) >> 1;
+            if (__ldg(tile_begin + m) <= tile) a = m; else b = m;
         }
-        const uint64_t k = tile - lo_t;
-        int64_t lo = w_vstart + (int64_t)(k * NZ_TILE);
-        int64_t hi = lo + NZ_TILE;
+        lo_t = __ldg(tile_begin + a);
+        hi_t = __ldg(tile_begin + a + 1);
+        const ulonglong2 p0 = __ldg(reinterpret_cast<const ulonglong2*>(work + a));
+        const ulonglong2 p1 = __ldg(reinterpret_cast<const ulonglong2*>(work + a) + 1);
+        src = p0.x; dst = p0.y; len = p1.x; vstart = (int64_t)p1.y;
+    }
+    __device__ __forceinline__ void span(uint64_t tile, uint32_t tile_bytes, int64_t& lo, int64_t& hi) const {
+        lo = vstart + (int64_t)((tile - lo_t) * tile_bytes);
+        hi = lo + tile_bytes;
         if (lo < 0) lo = 0;
-        if (hi > (int64_t)w_len) hi = (int64_t)w_len;
-        copy_tile(reinterpret_cast<const uint8_t*>(w_src) + lo, reinterpret_cast<uint8_t*>(w_dst) + lo, (uint32_t)(hi - lo));
+        if (hi > (int64_t)len) hi = (int64_t)len;
+    }
+};
+
+template <int NT, int U, int MINB, int HINT>
+__global__ void __launch_bounds__(NT, MINB)
+k_gather(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_begin, uint32_t nseg, uint32_t tile_bytes) {
+    const uint64_t total = tile_begin[nseg];
+    TileCursor c;
+    for (uint64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        c.seek(tile, work, tile_begin, nseg);
+        int64_t lo, hi;
+        c.span(tile, tile_bytes, lo, hi);
+        copy_tile<NT, U, HINT>(reinterpret_cast<const uint8_t*>(c.src) + lo, reinterpret_cast<uint8_t*>(c.dst) + lo, (uint32_t)(hi - lo));
     }
 }
 
@@ -574,9 +603,58 @@ cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s) {
     }
     return e;
 }
-cudaError_t nz_launch_gather(const NzSegWork* work, const uint64_t* tile_begin, uint32_t nseg, int grid, cudaStream_t s) {
-    k_gather<<<grid, NZ_GATHER_THREADS, 0, s>>>(work, tile_begin, nseg);
+// gather variants: {threads, vectors in flight per thread, CTAs per SM, cache hints}; tile = threads * U * 16 B
+struct GatherVariant { int nt, u, minb, hint; };
+static const GatherVariant kGatherVariants[] = {
+    {256, 8, 2, 0},   // 0: r01 baseline, 32 KiB tiles
+    {256, 4, 4, 0},   // 1
+    {512, 4, 2, 0},   // 2
+    {512, 8, 1, 0},   // 3
+    {1024, 4, 1, 0},  // 4
+    {128, 8, 4, 0},   // 5
+    {256, 8, 2, 1},   // 6: + L2::256B prefetch hint on loads
+    {256, 8, 2, 2},   // 7: + st.global.cs
+    {512, 4, 2, 1},   // 8
+    {256, 16, 1, 0},  // 9: 64 KiB tiles, deep unroll
+};
+constexpr int kNumGatherVariants = (int)(sizeof(kGatherVariants) / sizeof(kGatherVariants[0]));
+
+int nz_gather_num_variants() { return kNumGatherVariants; }
+uint32_t nz_gather_tile_bytes(int v) {
+    if (v < 0 || v >= kNumGatherVariants) v = 0;
+    return (uint32_t)(kGatherVariants[v].nt * kGatherVariants[v].u * 16);
+}
+
+template <int NT, int U, int MINB, int HINT>
+static cudaError_t launch_gather_t(const NzSegWork* work, const uint64_t* tile_begin, uint32_t nseg, int grid, cudaStream_t s) {
+    k_gather<NT, U, MINB, HINT><<<grid, NT, 0, s>>>(work, tile_begin, nseg, (uint32_t)(NT * U * 16));
     return cudaGetLastError();
+}
+template <int NT, int U, int MINB, int HINT>
+static int occ_gather_t() {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather<NT, U, MINB, HINT>, NT, 0) != cudaSuccess || nb < 1) nb = MINB;
+    return nb;
+}
+#define NZ_GV_SWITCH(v, F, ...)                                   \
+    switch (v) {                                                  \
+    case 1: return F<256, 4, 4, 0>(__VA_ARGS__);                  \
+    case 2: return F<512, 4, 2, 0>(__VA_ARGS__);                  \
+    case 3: return F<512, 8, 1, 0>(__VA_ARGS__);                  \
+    case 4: return F<1024, 4, 1, 0>(__VA_ARGS__);                 \
+    case 5: return F<128, 8, 4, 0>(__VA_ARGS__);                  \
+    case 6: return F<256, 8, 2, 1>(__VA_ARGS__);                  \
+    case 7: return F<256, 8, 2, 2>(__VA_ARGS__);                  \
+    case 8: return F<512, 4, 2, 1>(__VA_ARGS__);                  \
+    case 9: return F<256, 16, 1, 0>(__VA_ARGS__);                 \
+    default: return F<256, 8, 2, 0>(__VA_ARGS__);                 \
+    }
+
+cudaError_t nz_launch_gather(int variant, const NzSegWork* work, const uint64_t* tile_begin, uint32_t nseg, int grid, cudaStream_t s) {
+    NZ_GV_SWITCH(variant, launch_gather_t, work, tile_begin, nseg, grid, s)
+}
+int nz_gather_blocks_per_sm(int variant) {
+    NZ_GV_SWITCH(variant, occ_gather_t)
 }
 cudaError_t nz_launch_verify(const NzVerWork* ver, const uint32_t* counters, NzDevRes* res, const uint32_t* crc_tables,
                              int grid, cudaStream_t s) {
@@ -596,12 +674,6 @@ cudaError_t nz_launch_crc_chunks(const uint8_t* p, uint64_t n, uint32_t* chunk_o
     }
     k_crc_fold<<<1, 1024, 0, s>>>(chunk_out, n, whole_out);
     return cudaGetLastError();
-}
-
-int nz_gather_blocks_per_sm() {
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather, NZ_GATHER_THREADS, 0) != cudaSuccess || nb < 1) nb = 4;
-    return nb;
 }
 
 cudaError_t nz_upload_constants(uint32_t* crc_tables_dev) {
