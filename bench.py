@@ -310,10 +310,22 @@ def run_ours(args):
     value = payload_all / (ms_step * 1e-3) / 1e9
     hbm, which = peaks()
     g_ms = sum(gather_ms) / len(gather_ms)
-    achieved = 2.0 * payload / (g_ms * 1e-3) / 1e9
+    coalesce = os.environ.get("NZ_COALESCE", "1") != "0"
+    # algorithmic bytes of one launch: every payload byte is written once; the source is read once per
+    # DISTINCT slice when request coalescing is on (identical concurrent GETs are chained behind one
+    # leader and read once), once per request when it is off (2 x P)
+    distinct = {}
+    for j, (s_, l_) in enumerate(spans):
+        distinct[(s_, l_, offs[j] & 127)] = l_
+    read_bytes = sum(distinct.values()) if coalesce else payload
+    algo = read_bytes + payload
+    achieved = algo / (g_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                 "traffic": None, "peak_source": which, "kernel": "k_gather",
-                "algorithmic_bytes_per_launch": 2 * payload, "kernel_ms": g_ms,
+                "algorithmic_bytes_per_launch": algo, "kernel_ms": g_ms,
+                "accounting": ("source read once per distinct slice (request coalescing) + every payload byte written" if coalesce
+                               else "2 x payload (read + write per request)"),
+                "uncoalesced_equivalent_gbs": 2.0 * payload / (g_ms * 1e-3) / 1e9,
                 "kernel_share_of_step": g_ms / (ms / args.steps) if world == 1 else None}
 
     # ---- e2e: through the C ABI into pinned host windows ----------------------
@@ -404,6 +416,7 @@ def run_ours(args):
             "config": {"workload": "C2: one 1 GiB object per GPU, 64 concurrent GETs (32 full + 32 single-range, log-uniform 4 KiB-256 MiB), cache-hit only",
                        "object_bytes": L_obj, "requests": len(reqs), "payload_bytes_per_gpu_step": payload,
                        "response_buffers": "HBM", "l2": "inputs larger than L2 (1 GiB object, 33 GiB written per step); no flush needed",
+                       "request_coalescing": coalesce,
                        "sharding": f"key-hash x{world}, no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "ttfb": ttfb, "http": http, "gpu_launches": int(launches),
             "clocks": sampler.summary(), "numa_node": numa, "fill_gbs": L_obj / fill_s / 1e9, "object_crc32c": f"{crc:08x}",

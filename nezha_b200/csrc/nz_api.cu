@@ -136,6 +136,7 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
         const int v = atoi(ev);
         if (v >= 0 && v < nz_gather_num_variants()) c->gather_variant = v;
     }
+    if (const char* ev = getenv("NZ_COALESCE")) c->coalesce = atoi(ev) != 0;
     c->gather_grid = c->sm_count * nz_gather_blocks_per_sm(c->gather_variant);
     c->inflate_grid = c->sm_count * nz_inflate_blocks_per_sm();
     *out = c;
@@ -655,11 +656,12 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     const size_t pin_res = round_up((size_t)n * sizeof(NzDevRes), 256);
     const size_t dev_work = round_up((size_t)nseg * sizeof(NzSegWork), 256);
     const size_t dev_tiles = round_up((size_t)(nseg + 1) * 8, 256);
+    const size_t dev_chain = round_up((size_t)nseg * 8, 256);      // chain_head | chain_next (u32 each)
     const size_t dev_ver = round_up((size_t)ver_cap * sizeof(NzVerWork), 256);
     const size_t dev_cnt = 256;
     const size_t dev_infl = (size_t)n * sizeof(NzInflWork);      // followed directly by rq_src, rq_len
     const size_t dev_rq = (size_t)n * 40;                        // rq_src, rq_len, infl_meta, rq_tab, rq_ssz
-    nz_ticket* t = ticket_acquire(c, pin_reqs + pin_segs + pin_res, dev_work + dev_tiles + dev_ver + dev_cnt + round_up(dev_infl + dev_rq, 256));
+    nz_ticket* t = ticket_acquire(c, pin_reqs + pin_segs + pin_res, dev_work + dev_tiles + dev_chain + dev_ver + dev_cnt + round_up(dev_infl + dev_rq, 256));
     if (!t) { cudaGetLastError(); snprintf(tl_err, sizeof tl_err, "ticket allocation failed"); return NZ_ENOMEM; }
     t->n = n; t->nseg = (uint32_t)nseg;
 
@@ -726,10 +728,13 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     a.res = reinterpret_cast<NzDevRes*>((char*)t->pin_dev + pin_reqs + pin_segs);
     a.work = reinterpret_cast<NzSegWork*>(dv);
     a.tile_begin = reinterpret_cast<uint64_t*>(dv + dev_work);
-    a.ver = reinterpret_cast<NzVerWork*>(dv + dev_work + dev_tiles);
+    a.chain_head = reinterpret_cast<uint32_t*>(dv + dev_work + dev_tiles);
+    a.chain_next = a.chain_head + nseg;
+    a.coalesce = c->coalesce ? 1u : 0u;
+    a.ver = reinterpret_cast<NzVerWork*>(dv + dev_work + dev_tiles + dev_chain);
     a.ver_cap = (uint32_t)ver_cap;
-    a.counters = reinterpret_cast<uint32_t*>(dv + dev_work + dev_tiles + dev_ver);
-    a.infl = reinterpret_cast<NzInflWork*>(dv + dev_work + dev_tiles + dev_ver + dev_cnt);
+    a.counters = reinterpret_cast<uint32_t*>(dv + dev_work + dev_tiles + dev_chain + dev_ver);
+    a.infl = reinterpret_cast<NzInflWork*>(dv + dev_work + dev_tiles + dev_chain + dev_ver + dev_cnt);
     a.infl_meta = reinterpret_cast<uint64_t*>(a.infl + n) + 2 * (size_t)n;   // after rq_src, rq_len
     a.peer_base = c->peer_base_dev;
     a.tile_bytes = nz_gather_tile_bytes(c->gather_variant);
@@ -750,7 +755,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
         c->launches += 2;
     }
     CKT(cudaEventRecord(t->ev_g0, s));
-    CKT(nz_launch_gather(c->gather_variant, a.work, a.tile_begin, a.nseg, c->gather_grid, s));
+    CKT(nz_launch_gather(c->gather_variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, c->gather_grid, s));
     CKT(cudaEventRecord(t->ev_g1, s));
     c->launches += 1;
     if (any_verify && ver_cap) {

@@ -159,6 +159,7 @@ struct nz_ctx {
     int device;
     int sm_count;
     int gather_grid;       // persistent grid size for k_gather
+    bool coalesce = true;   // env NZ_COALESCE=0 turns request coalescing off (A/B measurements)
     int gather_variant = 0; // index into the k_gather variant table (env NZ_GATHER_VARIANT for sweeps)
     int inflate_grid;
     uint8_t* arena = nullptr;
@@ -209,6 +210,9 @@ struct NzPlanArgs {
     uint32_t* counters;         // [0]=n_ver [1]=n_infl [2]=inflate work-steal cursor
     uint64_t* infl_meta;        // n: (produced length << 32) | trailer CRC-32, written by k_inflate
     uint32_t tile_bytes;        // gather tile size of the selected k_gather variant
+    uint32_t coalesce;          // 1 = chain identical slices behind one leader (read once, write many)
+    uint32_t* chain_head;       // nseg: first follower of a leader slice, 0xFFFFFFFF = none
+    uint32_t* chain_next;       // nseg: next follower in the chain
     const uint64_t* peer_base;  // device array [shard_count]: base address of every shard's arena (own + IPC-mapped peers)
 };
 cudaError_t nz_launch_lookup(const NzSlot* table, uint64_t line_mask, const NzDesc* descs, const uint64_t* keys,
@@ -217,7 +221,8 @@ cudaError_t nz_launch_insert(NzSlot* table, uint64_t line_mask, uint64_t k0, uin
                              int32_t* status, cudaStream_t s);
 cudaError_t nz_launch_erase(NzSlot* table, uint64_t line_mask, uint64_t k0, uint64_t k1, int32_t* status, cudaStream_t s);
 cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s);
-cudaError_t nz_launch_gather(int variant, const NzSegWork* work, const uint64_t* tile_begin, uint32_t nseg, int grid, cudaStream_t s);
+cudaError_t nz_launch_gather(int variant, const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head,
+                             const uint32_t* chain_next, uint32_t nseg, int grid, cudaStream_t s);
 int nz_gather_num_variants();
 uint32_t nz_gather_tile_bytes(int variant);
 cudaError_t nz_launch_verify(const NzVerWork* ver, const uint32_t* counters, NzDevRes* res, const uint32_t* crc_tables,

@@ -259,49 +259,89 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint6
     }
     __syncthreads();
 
-    // ---- phase B: per-segment copy work + exclusive scan of tile counts ----
+    // ---- phase B1: per-segment copy work and tile counts ----------------------
+    uint64_t* tile_cnt = a.tile_begin;           // counts first, scanned in place in B3
+    for (uint32_t s = tid; s < a.nseg; s += 1024) {
+        uint64_t tiles = 0;
+        const NzDevSeg sg = a.segs[s];
+        const NzDevReq& rq = a.reqs[sg.req];
+        const int32_t st = a.res[sg.req].status;
+        NzSegWork w;
+        w.src = 0; w.dst = 0; w.len = 0; w.vstart = 0;
+        const uint64_t rlen = rq_len[sg.req];
+        if (st == NZ_OK && rlen > 0) {
+            const uint64_t off = rq.whole ? 0 : sg.src_off;
+            const uint64_t len = rq.whole ? rlen : sg.len;
+            const uint64_t doff = rq.whole ? 0 : sg.dst_off;
+            w.src = rq_src[sg.req] + off;
+            const uint64_t tab = rq_tab[sg.req];
+            uint64_t ok_len = len;
+            if (tab) {                               // K5: the slice lies inside one stripe, maybe on a peer GPU
+                const uint64_t ssz = rq_ssz[sg.req];
+                const uint64_t k = off / ssz, within = off - k * ssz;
+                const NzDevStripe stp = reinterpret_cast<const NzDevStripe*>(tab)[k];
+                const uint64_t pbase = a.peer_base ? a.peer_base[stp.shard] : 0;
+                if (within + len > stp.len || pbase == 0) {
+                    ok_len = 0;
+                    a.res[sg.req].status = pbase == 0 ? NZ_ENOSYS : NZ_EINVAL;
+                    a.res[sg.req].bytes = 0;
+                }
+                w.src = pbase + stp.arena_off + within;
+            }
+            w.dst = rq.dst + doff;
+            w.len = ok_len;
+            w.vstart = -(int64_t)(w.dst & 127u);
+            tiles = ok_len ? (ok_len + (w.dst & 127u) + a.tile_bytes - 1) / a.tile_bytes : 0;
+        }
+        a.work[s] = w;
+        tile_cnt[s] = tiles;
+        a.chain_head[s] = 0xFFFFFFFFu;
+        a.chain_next[s] = 0xFFFFFFFFu;
+    }
+    __threadfence_block();
+    __syncthreads();
+
+    // ---- phase B2: coalesce identical slices (read once, write many) -----------
+    // Concurrent GETs of the same bytes are the common case for a dataset cache (every
+    // worker pulls the same shard).  Slices with the same source, length and destination
+    // phase are chained behind one leader: the gather loads each tile once and stores it to
+    // every member, so HBM reads the source once instead of once per request.
+    if (a.coalesce && a.nseg > 1 && a.nseg <= 2048) {
+        __shared__ int s_tab[4096];
+        for (uint32_t i = tid; i < 4096; i += 1024) s_tab[i] = -1;
+        __syncthreads();
+        for (uint32_t s = tid; s < a.nseg; s += 1024) {
+            if (tile_cnt[s] == 0) continue;
+            const NzSegWork w = a.work[s];
+            uint64_t hsh = w.src * 0x9E3779B97F4A7C15ull ^ (w.len + (w.dst & 127u)) * 0xC2B2AE3D27D4EB4Full;
+            uint32_t h = (uint32_t)(hsh >> 40) & 4095u;
+            for (;;) {
+                int cur = s_tab[h];
+                if (cur == -1) {
+                    cur = atomicCAS(&s_tab[h], -1, (int)s);
+                    if (cur == -1) break;                       // this slice leads its group
+                }
+                const NzSegWork o = a.work[cur];
+                if (o.src == w.src && o.len == w.len && ((o.dst ^ w.dst) & 127u) == 0) {
+                    tile_cnt[s] = 0;                            // follower: its bytes are written by the leader's tiles
+                    a.chain_next[s] = atomicExch(&a.chain_head[cur], s);
+                    break;
+                }
+                h = (h + 1) & 4095u;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- phase B3: exclusive scan of tile counts -> tile_begin -------------------
     if (tid == 0) s_carry = 0;
     __syncthreads();
     for (uint32_t base = 0; base < a.nseg; base += 1024) {
         const uint32_t s = base + tid;
-        uint64_t tiles = 0;
-        if (s < a.nseg) {
-            const NzDevSeg sg = a.segs[s];
-            const NzDevReq& rq = a.reqs[sg.req];
-            const int32_t st = a.res[sg.req].status;
-            NzSegWork w;
-            w.src = 0; w.dst = 0; w.len = 0; w.vstart = 0;
-            const uint64_t rlen = rq_len[sg.req];
-            if (st == NZ_OK && rlen > 0) {
-                const uint64_t off = rq.whole ? 0 : sg.src_off;
-                const uint64_t len = rq.whole ? rlen : sg.len;
-                const uint64_t doff = rq.whole ? 0 : sg.dst_off;
-                w.src = rq_src[sg.req] + off;
-                const uint64_t tab = rq_tab[sg.req];
-                uint64_t ok_len = len;
-                if (tab) {                               // K5: the slice lies inside one stripe, maybe on a peer GPU
-                    const uint64_t ssz = rq_ssz[sg.req];
-                    const uint64_t k = off / ssz, within = off - k * ssz;
-                    const NzDevStripe st = reinterpret_cast<const NzDevStripe*>(tab)[k];
-                    const uint64_t base = a.peer_base ? a.peer_base[st.shard] : 0;
-                    if (within + len > st.len || base == 0) {
-                        ok_len = 0;
-                        a.res[sg.req].status = base == 0 ? NZ_ENOSYS : NZ_EINVAL;
-                        a.res[sg.req].bytes = 0;
-                    }
-                    w.src = base + st.arena_off + within;
-                }
-                w.dst = rq.dst + doff;
-                w.len = ok_len;
-                w.vstart = -(int64_t)(w.dst & 127u);
-                tiles = ok_len ? (ok_len + (w.dst & 127u) + a.tile_bytes - 1) / a.tile_bytes : 0;
-            }
-            a.work[s] = w;
-        }
-        // block exclusive scan (Hillis-Steele over 1024 entries)
+        const uint64_t tiles = s < a.nseg ? tile_cnt[s] : 0;
         s_scan[tid] = tiles;
         __syncthreads();
-        for (uint32_t ofs = 1; ofs < 1024; ofs <<= 1) {
+        for (uint32_t ofs = 1; ofs < 1024; ofs <<= 1) {         // Hillis-Steele
             uint64_t v = (tid >= ofs) ? s_scan[tid - ofs] : 0;
             __syncthreads();
             s_scan[tid] += v;
@@ -399,30 +439,48 @@ __device__ __forceinline__ void stg_s(void* p, const uint4& v) {
         asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// destinations of one tile: the leader's and, through the chain, every coalesced follower's
+struct DstChain {
+    uint8_t* d0;                                   // leader destination of this tile's first byte
+    int64_t lo;                                    // offset of the tile inside the slice
+    const NzSegWork* __restrict__ work;
+    const uint32_t* __restrict__ next;
+    uint32_t head;                                 // first follower or 0xFFFFFFFF
+};
+
 template <int WS, int NT, int U2, int HINT>
-__device__ __forceinline__ void copy_vectors_shifted(const uint4* __restrict__ sa /*aligned base*/, uint4* __restrict__ d,
+__device__ __forceinline__ void copy_vectors_shifted(const uint4* __restrict__ sa /*aligned base*/, const DstChain& c, uint32_t dskip,
                                                      uint32_t nvec, unsigned bs) {
     constexpr int U = U2 > 1 ? U2 / 2 : 1;   // two loads per output vector
     constexpr uint32_t STEP = NT * U;
     const uint32_t tid = threadIdx.x;
     uint32_t base = 0;
     for (; base + STEP <= nvec; base += STEP) {   // full steps: no predicates, all loads issued before any store
-        uint4 lo[U], hi[U];
+        uint4 v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint32_t i = base + u * NT + tid;
-            lo[u] = ldg_cached(sa + i);
-            hi[u] = ldg_cached(sa + i + 1);
+            v[u] = realign<WS>(ldg_cached(sa + i), ldg_cached(sa + i + 1), bs);
         }
+        uint4* d = reinterpret_cast<uint4*>(c.d0 + dskip);
 #pragma unroll
-        for (int u = 0; u < U; ++u) stg_s<HINT>(d + base + u * NT + tid, realign<WS>(lo[u], hi[u], bs));
+        for (int u = 0; u < U; ++u) stg_s<HINT>(d + base + u * NT + tid, v[u]);
+        for (uint32_t m = c.head; m != 0xFFFFFFFFu; m = __ldg(c.next + m)) {
+            uint4* dm = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(__ldg(&c.work[m].dst)) + c.lo + dskip);
+#pragma unroll
+            for (int u = 0; u < U; ++u) stg_s<HINT>(dm + base + u * NT + tid, v[u]);
+        }
     }
-    for (uint32_t i = base + tid; i < nvec; i += NT)
-        stg_s<HINT>(d + i, realign<WS>(ldg_cached(sa + i), ldg_cached(sa + i + 1), bs));
+    for (uint32_t i = base + tid; i < nvec; i += NT) {
+        const uint4 v = realign<WS>(ldg_cached(sa + i), ldg_cached(sa + i + 1), bs);
+        stg_s<HINT>(reinterpret_cast<uint4*>(c.d0 + dskip) + i, v);
+        for (uint32_t m = c.head; m != 0xFFFFFFFFu; m = __ldg(c.next + m))
+            stg_s<HINT>(reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(__ldg(&c.work[m].dst)) + c.lo + dskip) + i, v);
+    }
 }
 
 template <int NT, int U, int HINT>
-__device__ __forceinline__ void copy_vectors_aligned(const uint4* __restrict__ sv, uint4* __restrict__ dv, uint32_t nvec) {
+__device__ __forceinline__ void copy_vectors_aligned(const uint4* __restrict__ sv, const DstChain& c, uint32_t dskip, uint32_t nvec) {
     constexpr uint32_t STEP = NT * U;
     const uint32_t tid = threadIdx.x;
     uint32_t base = 0;
@@ -430,35 +488,55 @@ __device__ __forceinline__ void copy_vectors_aligned(const uint4* __restrict__ s
         uint4 v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) v[u] = ldg_s<HINT>(sv + base + u * NT + tid);
+        uint4* d = reinterpret_cast<uint4*>(c.d0 + dskip);
 #pragma unroll
-        for (int u = 0; u < U; ++u) stg_s<HINT>(dv + base + u * NT + tid, v[u]);
+        for (int u = 0; u < U; ++u) stg_s<HINT>(d + base + u * NT + tid, v[u]);
+        for (uint32_t m = c.head; m != 0xFFFFFFFFu; m = __ldg(c.next + m)) {
+            uint4* dm = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(__ldg(&c.work[m].dst)) + c.lo + dskip);
+#pragma unroll
+            for (int u = 0; u < U; ++u) stg_s<HINT>(dm + base + u * NT + tid, v[u]);
+        }
     }
-    for (uint32_t i = base + tid; i < nvec; i += NT) stg_s<HINT>(dv + i, ldg_s<HINT>(sv + i));
+    for (uint32_t i = base + tid; i < nvec; i += NT) {
+        const uint4 v = ldg_s<HINT>(sv + i);
+        stg_s<HINT>(reinterpret_cast<uint4*>(c.d0 + dskip) + i, v);
+        for (uint32_t m = c.head; m != 0xFFFFFFFFu; m = __ldg(c.next + m))
+            stg_s<HINT>(reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(__ldg(&c.work[m].dst)) + c.lo + dskip) + i, v);
+    }
 }
 
 template <int NT, int U, int HINT>
-__device__ __forceinline__ void copy_tile(const uint8_t* __restrict__ s, uint8_t* __restrict__ d, uint32_t n) {
+__device__ __forceinline__ void copy_tile(const uint8_t* __restrict__ s, const DstChain& c, uint32_t n) {
     const uint32_t tid = threadIdx.x;
-    // head: bring the destination to a 16 B boundary (only the first tile of a segment can need it)
-    const uint32_t head = min(n, (uint32_t)((16u - ((uintptr_t)d & 15u)) & 15u));
-    if (tid < head) d[tid] = s[tid];
-    s += head; d += head; n -= head;
-    const uint32_t nvec = n >> 4;
-    const uint32_t tail = n & 15u;
-    if (tid < tail) d[(nvec << 4) + tid] = s[(nvec << 4) + tid];
+    // head: bring the destination to a 16 B boundary (only the first tile of a slice can need it;
+    // coalesced members share the destination phase, so the same split applies to all of them)
+    const uint32_t head = min(n, (uint32_t)((16u - ((uintptr_t)c.d0 & 15u)) & 15u));
+    const uint32_t nvec = (n - head) >> 4;
+    const uint32_t tail = (n - head) & 15u;
+    if (tid < head || tid < tail) {
+        const uint32_t toff = head + (nvec << 4);
+        const uint8_t hb = tid < head ? s[tid] : 0, tb = tid < tail ? s[toff + tid] : 0;
+        if (tid < head) c.d0[tid] = hb;
+        if (tid < tail) c.d0[toff + tid] = tb;
+        for (uint32_t m = c.head; m != 0xFFFFFFFFu; m = __ldg(c.next + m)) {
+            uint8_t* dm = reinterpret_cast<uint8_t*>(__ldg(&c.work[m].dst)) + c.lo;
+            if (tid < head) dm[tid] = hb;
+            if (tid < tail) dm[toff + tid] = tb;
+        }
+    }
     if (nvec == 0) return;
+    s += head;
     const unsigned mis = (unsigned)((uintptr_t)s & 15u);
-    uint4* dv = reinterpret_cast<uint4*>(d);
     if (mis == 0) {
-        copy_vectors_aligned<NT, U, HINT>(reinterpret_cast<const uint4*>(s), dv, nvec);
+        copy_vectors_aligned<NT, U, HINT>(reinterpret_cast<const uint4*>(s), c, head, nvec);
     } else {
         const uint4* sa = reinterpret_cast<const uint4*>(s - mis);
         const unsigned bs = (mis & 3u) * 8u;
         switch (mis >> 2) {
-        case 0: copy_vectors_shifted<0, NT, U, HINT>(sa, dv, nvec, bs); break;
-        case 1: copy_vectors_shifted<1, NT, U, HINT>(sa, dv, nvec, bs); break;
-        case 2: copy_vectors_shifted<2, NT, U, HINT>(sa, dv, nvec, bs); break;
-        default: copy_vectors_shifted<3, NT, U, HINT>(sa, dv, nvec, bs); break;
+        case 0: copy_vectors_shifted<0, NT, U, HINT>(sa, c, head, nvec, bs); break;
+        case 1: copy_vectors_shifted<1, NT, U, HINT>(sa, c, head, nvec, bs); break;
+        case 2: copy_vectors_shifted<2, NT, U, HINT>(sa, c, head, nvec, bs); break;
+        default: copy_vectors_shifted<3, NT, U, HINT>(sa, c, head, nvec, bs); break;
         }
     }
 }
@@ -467,6 +545,7 @@ __device__ __forceinline__ void copy_tile(const uint8_t* __restrict__ s, uint8_t
 struct TileCursor {
     uint64_t lo_t = 0, hi_t = 0, src = 0, dst = 0, len = 0;
     int64_t vstart = 0;
+    uint32_t seg = 0;
     __device__ __forceinline__ void seek(uint64_t tile, const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_begin,
                                          uint32_t nseg) {
         if (tile >= lo_t && tile < hi_t) return;
@@ -475,6 +554,7 @@ struct TileCursor {
             const uint32_t m = (a + b) >> 1;
             if (__ldg(tile_begin + m) <= tile) a = m; else b = m;
         }
+        seg = a;
         lo_t = __ldg(tile_begin + a);
         hi_t = __ldg(tile_begin + a + 1);
         const ulonglong2 p0 = __ldg(reinterpret_cast<const ulonglong2*>(work + a));
@@ -491,14 +571,24 @@ struct TileCursor {
 
 template <int NT, int U, int MINB, int HINT>
 __global__ void __launch_bounds__(NT, MINB)
-k_gather(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_begin, uint32_t nseg, uint32_t tile_bytes) {
+k_gather(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_begin, const uint32_t* __restrict__ chain_head,
+         const uint32_t* __restrict__ chain_next, uint32_t nseg, uint32_t tile_bytes) {
     const uint64_t total = tile_begin[nseg];
     TileCursor c;
+    DstChain dc;
+    dc.work = work;
+    dc.next = chain_next;
+    dc.head = 0xFFFFFFFFu;
     for (uint64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const uint32_t before = c.seg;
+        const bool fresh = !(tile >= c.lo_t && tile < c.hi_t);
         c.seek(tile, work, tile_begin, nseg);
+        if (fresh || before != c.seg) dc.head = __ldg(chain_head + c.seg);
         int64_t lo, hi;
         c.span(tile, tile_bytes, lo, hi);
-        copy_tile<NT, U, HINT>(reinterpret_cast<const uint8_t*>(c.src) + lo, reinterpret_cast<uint8_t*>(c.dst) + lo, (uint32_t)(hi - lo));
+        dc.d0 = reinterpret_cast<uint8_t*>(c.dst) + lo;
+        dc.lo = lo;
+        copy_tile<NT, U, HINT>(reinterpret_cast<const uint8_t*>(c.src) + lo, dc, (uint32_t)(hi - lo));
     }
 }
 
@@ -626,8 +716,9 @@ uint32_t nz_gather_tile_bytes(int v) {
 }
 
 template <int NT, int U, int MINB, int HINT>
-static cudaError_t launch_gather_t(const NzSegWork* work, const uint64_t* tile_begin, uint32_t nseg, int grid, cudaStream_t s) {
-    k_gather<NT, U, MINB, HINT><<<grid, NT, 0, s>>>(work, tile_begin, nseg, (uint32_t)(NT * U * 16));
+static cudaError_t launch_gather_t(const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head,
+                                   const uint32_t* chain_next, uint32_t nseg, int grid, cudaStream_t s) {
+    k_gather<NT, U, MINB, HINT><<<grid, NT, 0, s>>>(work, tile_begin, chain_head, chain_next, nseg, (uint32_t)(NT * U * 16));
     return cudaGetLastError();
 }
 template <int NT, int U, int MINB, int HINT>
@@ -650,8 +741,9 @@ static int occ_gather_t() {
     default: return F<256, 8, 2, 0>(__VA_ARGS__);                 \
     }
 
-cudaError_t nz_launch_gather(int variant, const NzSegWork* work, const uint64_t* tile_begin, uint32_t nseg, int grid, cudaStream_t s) {
-    NZ_GV_SWITCH(variant, launch_gather_t, work, tile_begin, nseg, grid, s)
+cudaError_t nz_launch_gather(int variant, const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head,
+                             const uint32_t* chain_next, uint32_t nseg, int grid, cudaStream_t s) {
+    NZ_GV_SWITCH(variant, launch_gather_t, work, tile_begin, chain_head, chain_next, nseg, grid, s)
 }
 int nz_gather_blocks_per_sm(int variant) {
     NZ_GV_SWITCH(variant, occ_gather_t)

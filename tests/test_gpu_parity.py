@@ -300,3 +300,44 @@ def test_stats_and_launch_count(zone, objects):
     s1 = zone.stats()
     assert s1.gets == s0.gets + 1 and s1.hits == s0.hits + 1
     assert s1.kernel_launches > s0.kernel_launches
+
+
+def test_coalesced_identical_gets(zone, objects):
+    """Many concurrent GETs of the same bytes (the usual dataset-cache pattern) are chained behind
+    one leader slice: read once, written to every destination.  Every destination must still get
+    exactly the oracle's bytes, whatever its alignment class or memory kind."""
+    idx = SIZES.index(1_000_003)
+    d, _ = objects[idx]
+    key = K(idx)
+    n = len(d)
+    gets, checks, bufs = [], [], []
+    for j in range(40):                                   # identical full GETs: device and host destinations
+        b = zone.alloc_device(n) if j % 3 else zone.alloc_host(n)
+        bufs.append(b)
+        gets.append(nz.Get(key, b))
+        checks.append((b, 0, 0, n))
+    for j in range(24):                                   # identical misaligned range, two destination phases
+        b = zone.alloc_host(400_000)
+        bufs.append(b)
+        phase = 0 if j % 2 else 37
+        gets.append(nz.Get(key, b, [(12_345, 333_333, phase)]))
+        checks.append((b, phase, 12_345, 333_333))
+    for j in range(8):                                    # a multi-slice request repeated (multipart layout)
+        b = zone.alloc_device(300_000)
+        bufs.append(b)
+        gets.append(nz.Get(key, b, [(5, 70_000, 11), (500_000, 33_001, 100_000), (999_999, 4, 200_000)]))
+        checks += [(b, 11, 5, 70_000), (b, 100_000, 500_000, 33_001), (b, 200_000, 999_999, 4)]
+    b = zone.alloc_device(n)                              # and a different object in the same wave
+    bufs.append(b)
+    other = SIZES.index(100_000)
+    gets.append(nz.Get(K(other), b))
+    t = zone.submit(gets)
+    res = t.wait()
+    t.free()
+    assert all(r.status == capi.NZ_OK for r in res)
+    assert res[0].bytes == n and res[40].bytes == 333_333 and res[64].bytes == 70_000 + 33_001 + 4
+    for buf, doff, soff, ln in checks:
+        assert buf.bytes(doff, ln) == o.serve_slice_mem(d, soff, ln), (doff, soff, ln)
+    assert b.bytes(0, 100_000) == objects[other][0].tobytes()
+    for x in bufs:
+        x.free()
