@@ -664,6 +664,162 @@ def run_c3(args):
     return 0
 
 
+# --------------------------------------------------------------------------- #
+# C4: key-hash-sharded store, objects > 64 MiB striped over the shards, GETs that span shards
+# --------------------------------------------------------------------------- #
+def run_c4(args):
+    """BASELINE configs[3] scaled by --c4-gib-per-gpu (the named config is 125 GiB/GPU = 1 TB at 8 GPUs).
+    One process per GPU; each rank serves the GETs whose key it owns; a GET of a striped object pulls
+    the remote stripes with direct NVLink peer loads inside k_gather (K5).  Beside it: the same bytes
+    moved with an NCCL all-gather (the collective north_star names) for one large object."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import nezha_b200 as nz
+    from nezha_b200 import capi, shard, span, workloads as wl
+
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    bind_to_gpu_numa_node(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    per_gpu = int(args.c4_gib_per_gpu * (1 << 30))
+    total_target = per_gpu * world
+    # population: log-uniform 1 MiB .. 1 GiB until the target is reached (same list on every rank)
+    g = np.random.Generator(np.random.Philox(key=4))
+    sizes = []
+    acc = 0
+    while acc < total_target * 0.85:
+        sz = int(math.exp(g.uniform(math.log(1 << 20), math.log(1 << 30))))
+        sz = min(sz, total_target - acc)
+        sizes.append(sz)
+        acc += sz
+    keys = [wl.key128(wl.object_key_string("c4", i)) for i in range(len(sizes))]
+    zone = nz.Zone(device=local, arena_bytes=int(per_gpu * 1.25) + (256 << 20), max_objects=1 << 16, shard_index=rank, shard_count=world)
+    store = span.ShardedStore(zone, dist)
+    store.attach_peers()
+
+    def gen_for(i):
+        def gen(off, ln):
+            tg = torch.Generator(device="cuda")
+            tg.manual_seed(1_000_003 * i + off // (1 << 20))
+            return torch.randint(0, 256, (ln,), dtype=torch.uint8, device="cuda", generator=tg)
+        return gen
+
+    t0 = time.perf_counter()
+    crcs = {}
+    for i, (k, sz) in enumerate(zip(keys, sizes)):
+        c = store.put(k, sz, gen_for(i))
+        if c is not None:
+            crcs[i] = c
+    torch.cuda.synchronize()
+    dist.barrier()
+    fill_s = time.perf_counter() - t0
+    # request log: 256 in-flight GETs over the whole population (seed 44), routed to the owners
+    gq = np.random.Generator(np.random.Philox(key=44))
+    picks = gq.integers(0, len(sizes), args.c4_inflight)
+    mine = [int(i) for i in picks if shard.shard_of(keys[int(i)], world) == rank]
+    offs, total = [], 0
+    for i in mine:
+        offs.append(total)
+        total += (sizes[i] + 255) // 256 * 256
+    dbuf = zone.alloc_device(max(total, 256))
+    wave = zone.prepare([nz.Get(keys[i], dbuf, [], 0, offs[j]) for j, i in enumerate(mine)]) if mine else None
+    payload = float(sum(sizes[i] for i in mine))
+    remote = 0.0
+    for i in mine:
+        for sh, _, ln in shard.stripe_plan(keys[i], sizes[i], world):
+            if sh != rank:
+                remote += ln
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
+    sptr = stream.cuda_stream
+
+    def one():
+        if wave is None:
+            return None
+        t = wave.submit(sptr)
+        return t
+
+    for _ in range(max(args.warmup, 3)):
+        t = one()
+        if t:
+            res = t.wait()
+            t.free()
+            if any(r.status != capi.NZ_OK for r in res):
+                raise SystemExit(f"bench.py c4: rank {rank} wave failed {[r.status for r in res if r.status][:4]}")
+    # spot parity: the CRC-32C of one served striped object equals the CRC recorded at fill
+    big = [j for j, i in enumerate(mine) if sizes[i] > span.STRIPE_BYTES and i in crcs]
+    if big:
+        j = big[0]
+        i = mine[j]
+        if zone.crc32c_device(dbuf.dev + offs[j], sizes[i]) != crcs[i]:
+            raise SystemExit("bench.py c4: gathered striped object differs from what was stored (CRC-32C)")
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    tickets = [one() for _ in range(args.steps)]
+    ev1.record(stream)
+    ev1.synchronize()
+    dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    for t in tickets:
+        if t:
+            t.wait()
+            t.free()
+    ms_all, payload_all = shard.reduce_timing(dist, ms, payload, device="cuda")
+    _, remote_all = shard.reduce_timing(dist, ms, remote, device="cuda")
+    ms_step = ms_all / args.steps
+    value = payload_all / (ms_step * 1e-3) / 1e9
+    # worst rank's NVLink ingress rate
+    ingress = remote / (ms / args.steps * 1e-3) / 1e9 if ms > 0 else 0.0
+    it = torch.tensor([ingress], device="cuda", dtype=torch.float64)
+    dist.all_reduce(it, op=dist.ReduceOp.MAX)
+    # ---- NCCL all-gather baseline on one evenly striped object ----------------
+    nccl = None
+    try:
+        part = 64 << 20
+        src = torch.randint(0, 256, (part,), dtype=torch.uint8, device="cuda")
+        outb = torch.empty(part * world, dtype=torch.uint8, device="cuda")
+        for _ in range(3):
+            dist.all_gather_into_tensor(outb, src)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        e0.record()
+        reps = 10
+        for _ in range(reps):
+            dist.all_gather_into_tensor(outb, src)
+        e1.record()
+        e1.synchronize()
+        tms = e0.elapsed_time(e1) / reps
+        tt = torch.tensor([tms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        nccl = {"object_bytes": part * world, "ms": float(tt.item()), "gbs_per_gpu_assembled": part * world / (float(tt.item()) * 1e-3) / 1e9,
+                "note": "ncclAllGather of one object striped 64 MiB per rank: every rank ends with the whole object (then still needs a copy into the response)"}
+    except Exception as e:
+        nccl = {"error": repr(e)}
+    if rank == 0:
+        line = {
+            "metric": "cached-GET GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"C4: key-hash-sharded store, {len(sizes)} objects 1 MiB-1 GiB (log-uniform), {args.c4_gib_per_gpu} GiB/GPU "
+                                   f"(named config: 125 GiB/GPU), objects > 64 MiB striped round-robin, {args.c4_inflight} in-flight full GETs routed to owners",
+                       "objects": len(sizes), "bytes_total": int(acc), "inflight": args.c4_inflight, "response_buffers": "HBM",
+                       "exchange": "direct NVLink peer loads inside k_gather over CUDA-IPC-mapped arenas (no separate collective)"},
+            "span": {"remote_fraction": remote_all / payload_all if payload_all else 0.0, "nvlink_bytes_per_step": remote_all,
+                     "max_rank_ingress_gbs": float(it.item()), "nvlink_peak_gbs_per_dir": 770.0,
+                     "ingress_frac_of_peak": float(it.item()) / 770.0},
+            "nccl_allgather": nccl, "fill_s": fill_s, "gpu_launches": 2 * args.steps,
+        }
+        print(json.dumps(line), flush=True)
+    dbuf.free()
+    zone.close()
+    dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -676,7 +832,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-http", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
+    ap.add_argument("--c4-gib-per-gpu", type=float, default=16.0)
+    ap.add_argument("--c4-inflight", type=int, default=256)
     ap.add_argument("--c3-objects", type=int, default=10_000)
     ap.add_argument("--c3-wave", type=int, default=2048)
     args = ap.parse_args()
@@ -684,6 +842,8 @@ def main():
         return run_reference(args)
     if args.workload == "c3":
         return run_c3(args)
+    if args.workload == "c4":
+        return run_c4(args)
     return run_ours(args)
 
 
