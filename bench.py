@@ -236,6 +236,7 @@ def run_ours(args):
     payload = sum(l for _, l in spans)
 
     zone = nz.Zone(device=local, arena_bytes=L_obj + (64 << 20), max_objects=1024, shard_index=rank, shard_count=world)
+    zone.set_profiling(True)     # per-kernel CUDA events (roofline timing)
     # the shard's object: first bench key this shard owns (key-hash placement)
     i = 0
     while not zone.owns(wl.key128(wl.object_key_string("c2", i))):
@@ -387,7 +388,14 @@ def run_ours(args):
                 t.free()
             lat.append(dtt * 1e6)
         lat.sort()
-        ttfb = {"p50_us": lat[len(lat) // 2], "p99_us": lat[min(len(lat) - 1, int(len(lat) * 0.99))], "first_bytes": 256 << 10,
+        native = None
+        try:        # the same measurement without the interpreter in the loop
+            r = subprocess.run([os.path.join(ROOT, "nezha_b200", "_build", "nzlat"), "--device", str(local), "--iters", "2000"],
+                               capture_output=True, text=True, timeout=120)
+            native = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception as e:
+            native = {"error": repr(e)}
+        ttfb = {"native": native, "p50_us": lat[len(lat) // 2], "p99_us": lat[min(len(lat) - 1, int(len(lat) * 0.99))], "first_bytes": 256 << 10,
                 "note": "host clock around nz_get_submit+nz_get_wait through Python ctypes, one GET in flight, first 256 KiB to pinned host"}
         hbuf.free()
 
@@ -580,6 +588,7 @@ def run_c3(args):
     gen_s = time.perf_counter() - t0
     comp_total = sum(len(g) for g, _ in made)
     zone = nz.Zone(device=local, arena_bytes=comp_total + n_obj * 8192 + (64 << 20), max_objects=max(2 * n_obj, 1024))
+    zone.set_profiling(True)
     keys = [wl.key128(wl.object_key_string("c3", i)) for i in range(n_obj)]
     t0 = time.perf_counter()
     for k, (g, _) in zip(keys, made):
@@ -726,8 +735,8 @@ def run_c4(args):
     dbuf = zone.alloc_device(max(total, 256))
     wave = zone.prepare([nz.Get(keys[i], dbuf, [], 0, offs[j]) for j, i in enumerate(mine)]) if mine else None
     payload = float(sum(sizes[i] for i in mine))
-    remote = 0.0
-    for i in mine:
+    remote = 0.0          # NVLink bytes per wave: identical concurrent GETs are coalesced, so count distinct objects
+    for i in sorted(set(mine)):
         for sh, _, ln in shard.stripe_plan(keys[i], sizes[i], world):
             if sh != rank:
                 remote += ln
@@ -808,7 +817,7 @@ def run_c4(args):
                                    f"(named config: 125 GiB/GPU), objects > 64 MiB striped round-robin, {args.c4_inflight} in-flight full GETs routed to owners",
                        "objects": len(sizes), "bytes_total": int(acc), "inflight": args.c4_inflight, "response_buffers": "HBM",
                        "exchange": "direct NVLink peer loads inside k_gather over CUDA-IPC-mapped arenas (no separate collective)"},
-            "span": {"remote_fraction": remote_all / payload_all if payload_all else 0.0, "nvlink_bytes_per_step": remote_all,
+            "span": {"nvlink_bytes_over_payload": remote_all / payload_all if payload_all else 0.0, "nvlink_bytes_per_step": remote_all,
                      "max_rank_ingress_gbs": float(it.item()), "nvlink_peak_gbs_per_dir": 770.0,
                      "ingress_frac_of_peak": float(it.item()) / 770.0},
             "nccl_allgather": nccl, "fill_s": fill_s, "gpu_launches": 2 * args.steps,

@@ -176,6 +176,9 @@ int32_t nz_ticket_inflate_ms(nz_ticket* t, float* ms);  /* device time of its in
 int32_t nz_ticket_free(nz_ticket* t);
 
 int32_t nz_get_stats(nz_ctx* ctx, nz_stats* out);
+/* record per-kernel CUDA events in every wave so nz_ticket_*_ms work (off by default: each
+ * event record costs host time on the latency path) */
+int32_t nz_set_profiling(nz_ctx* ctx, int32_t on);
 
 /* ---- cross-shard objects (the one exchange step) ---------------- */
 /* An object larger than one stripe is striped round-robin over the shards; the owner of

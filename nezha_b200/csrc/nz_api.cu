@@ -137,6 +137,7 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
         if (v >= 0 && v < nz_gather_num_variants()) c->gather_variant = v;
     }
     if (const char* ev = getenv("NZ_COALESCE")) c->coalesce = atoi(ev) != 0;
+    if (const char* ev = getenv("NZ_PROFILE")) c->profile = atoi(ev) != 0;
     c->gather_grid = c->sm_count * nz_gather_blocks_per_sm(c->gather_variant);
     c->inflate_grid = c->sm_count * nz_inflate_blocks_per_sm();
     *out = c;
@@ -660,8 +661,9 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     const size_t dev_ver = round_up((size_t)ver_cap * sizeof(NzVerWork), 256);
     const size_t dev_cnt = 256;
     const size_t dev_infl = (size_t)n * sizeof(NzInflWork);      // followed directly by rq_src, rq_len
-    const size_t dev_rq = (size_t)n * 40;                        // rq_src, rq_len, infl_meta, rq_tab, rq_ssz
-    nz_ticket* t = ticket_acquire(c, pin_reqs + pin_segs + pin_res, dev_work + dev_tiles + dev_chain + dev_ver + dev_cnt + round_up(dev_infl + dev_rq, 256));
+    const size_t dev_rq = (size_t)n * 48;                        // rq_src, rq_len, infl_meta, rq_tab, rq_ssz, rq_stat(+pad)
+    const size_t dev_stage = round_up((size_t)n * sizeof(NzDevReq), 256) + round_up((size_t)nseg * sizeof(NzDevSeg), 256);
+    nz_ticket* t = ticket_acquire(c, pin_reqs + pin_segs + pin_res, dev_work + dev_tiles + dev_chain + dev_ver + dev_cnt + round_up(dev_infl + dev_rq, 256) + dev_stage);
     if (!t) { cudaGetLastError(); snprintf(tl_err, sizeof tl_err, "ticket allocation failed"); return NZ_ENOMEM; }
     t->n = n; t->nseg = (uint32_t)nseg;
 
@@ -720,11 +722,22 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
         hres[i].status = NZ_ECUDA; hres[i].flags = 0; hres[i].bytes = 0; hres[i].length = 0; hres[i].crc32c = 0; hres[i].reserved = 0;
     }
 
+    // upper bound on gather tiles when every slice length is known on the host (0 = unknown)
+    uint64_t tile_bound = 0;
+    {
+        const uint64_t tb = nz_gather_tile_bytes(c->gather_variant);
+        bool known = true;
+        for (uint32_t i = 0; i < (uint32_t)nseg && known; ++i) {
+            if (hseg[i].len == 0 && hreq[hseg[i].req].whole) known = false;
+            else tile_bound += hseg[i].len / tb + 2;
+        }
+        if (!known) tile_bound = 0;
+    }
     char* dv = (char*)t->dev;
     NzPlanArgs a;
     a.table = c->table; a.line_mask = c->n_lines - 1; a.descs = c->descs; a.arena = c->arena;
-    a.reqs = reinterpret_cast<const NzDevReq*>(t->pin_dev); a.n = n;
-    a.segs = reinterpret_cast<const NzDevSeg*>((char*)t->pin_dev + pin_reqs); a.nseg = (uint32_t)nseg;
+    a.reqs_host = reinterpret_cast<const NzDevReq*>(t->pin_dev); a.n = n;
+    a.segs_host = reinterpret_cast<const NzDevSeg*>((char*)t->pin_dev + pin_reqs); a.nseg = (uint32_t)nseg;
     a.res = reinterpret_cast<NzDevRes*>((char*)t->pin_dev + pin_reqs + pin_segs);
     a.work = reinterpret_cast<NzSegWork*>(dv);
     a.tile_begin = reinterpret_cast<uint64_t*>(dv + dev_work);
@@ -736,6 +749,12 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     a.counters = reinterpret_cast<uint32_t*>(dv + dev_work + dev_tiles + dev_chain + dev_ver);
     a.infl = reinterpret_cast<NzInflWork*>(dv + dev_work + dev_tiles + dev_chain + dev_ver + dev_cnt);
     a.infl_meta = reinterpret_cast<uint64_t*>(a.infl + n) + 2 * (size_t)n;   // after rq_src, rq_len
+    a.rq_stat = reinterpret_cast<int32_t*>(reinterpret_cast<uint64_t*>(a.infl + n) + 5 * (size_t)n);
+    {
+        char* stg = dv + dev_work + dev_tiles + dev_chain + dev_ver + dev_cnt + round_up(dev_infl + dev_rq, 256);
+        a.reqs_dev = reinterpret_cast<NzDevReq*>(stg);
+        a.segs_dev = reinterpret_cast<NzDevSeg*>(stg + round_up((size_t)n * sizeof(NzDevReq), 256));
+    }
     a.peer_base = c->peer_base_dev;
     a.tile_bytes = nz_gather_tile_bytes(c->gather_variant);
 
@@ -743,20 +762,22 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     t->stream = s;
     cudaError_t e;
 #define CKT(call) do { e = (call); if (e != cudaSuccess) { int32_t rc = cuda_fail(e, #call); nz_ticket_free(t); return rc; } } while (0)
-    CKT(cudaEventRecord(t->ev_start, s));
-    CKT(cudaMemsetAsync(a.counters, 0, 16, s));
+    t->profiled = c->profile;
+    if (t->profiled) CKT(cudaEventRecord(t->ev_start, s));
     CKT(nz_launch_plan(a, s));
     c->launches += a.ver_cap ? 2 : 1;
     t->ran_inflate = any_inflate;
     if (any_inflate) {
-        CKT(cudaEventRecord(t->ev_i0, s));
+        if (t->profiled) CKT(cudaEventRecord(t->ev_i0, s));
         CKT(nz_launch_inflate(a.infl, a.infl_meta, a.counters, a.res, c->crc_tables, c->inflate_grid, c->sm_count, s));
-        CKT(cudaEventRecord(t->ev_i1, s));
+        if (t->profiled) CKT(cudaEventRecord(t->ev_i1, s));
         c->launches += 2;
     }
-    CKT(cudaEventRecord(t->ev_g0, s));
-    CKT(nz_launch_gather(c->gather_variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, c->gather_grid, s));
-    CKT(cudaEventRecord(t->ev_g1, s));
+    if (t->profiled) CKT(cudaEventRecord(t->ev_g0, s));
+    int ggrid = c->gather_grid;
+    if (tile_bound && tile_bound < (uint64_t)ggrid) ggrid = (int)tile_bound;   // small waves: no more CTAs than tiles
+    CKT(nz_launch_gather(c->gather_variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s));
+    if (t->profiled) CKT(cudaEventRecord(t->ev_g1, s));
     c->launches += 1;
     if (any_verify && ver_cap) {
         int grid = (int)std::min<uint64_t>(ver_cap, (uint64_t)c->sm_count * 8);
@@ -782,7 +803,14 @@ int32_t nz_get_wait(nz_ticket* t, int64_t timeout_us, nz_get_res* res) {
     nz_ctx* c = t->ctx;
     cudaSetDevice(c->device);
     if (timeout_us < 0) {
-        CK(cudaEventSynchronize(t->ev_done));
+        // short waves finish in microseconds: poll first (a blocking sync costs an interrupt wake-up)
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+            cudaError_t e = cudaEventQuery(t->ev_done);
+            if (e == cudaSuccess) break;
+            if (e != cudaErrorNotReady) return cuda_fail(e, "cudaEventQuery");
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) { CK(cudaEventSynchronize(t->ev_done)); break; }
+        }
     } else {
         const auto t0 = std::chrono::steady_clock::now();
         for (;;) {
@@ -814,12 +842,14 @@ int32_t nz_get_wait(nz_ticket* t, int64_t timeout_us, nz_get_res* res) {
 
 int32_t nz_ticket_elapsed_ms(nz_ticket* t, float* ms) {
     if (!t || !ms) return NZ_EINVAL;
+    if (!t->profiled) return NZ_ENOSYS;      // nz_set_profiling(ctx, 1) first
     CK(cudaEventElapsedTime(ms, t->ev_start, t->ev_done));
     return NZ_OK;
 }
 
 int32_t nz_ticket_gather_ms(nz_ticket* t, float* ms) {
     if (!t || !ms) return NZ_EINVAL;
+    if (!t->profiled) return NZ_ENOSYS;
     CK(cudaEventElapsedTime(ms, t->ev_g0, t->ev_g1));
     return NZ_OK;
 }
@@ -828,6 +858,7 @@ int32_t nz_ticket_inflate_ms(nz_ticket* t, float* ms) {
     if (!t || !ms) return NZ_EINVAL;
     *ms = 0.f;
     if (!t->ran_inflate) return NZ_OK;
+    if (!t->profiled) return NZ_ENOSYS;
     CK(cudaEventElapsedTime(ms, t->ev_i0, t->ev_i1));
     return NZ_OK;
 }
@@ -842,6 +873,12 @@ int32_t nz_ticket_free(nz_ticket* t) {
     std::lock_guard<std::mutex> g(c->tmu);
     if (c->ticket_pool.size() < 64) c->ticket_pool.push_back(t);
     else ticket_destroy(t);
+    return NZ_OK;
+}
+
+int32_t nz_set_profiling(nz_ctx* c, int32_t on) {
+    if (!c) return NZ_EINVAL;
+    c->profile = on != 0;
     return NZ_OK;
 }
 

@@ -137,6 +137,7 @@ struct nz_ticket {
     void* dev = nullptr; size_t dev_cap = 0;
     void* scratch = nullptr; size_t scratch_cap = 0;   // inflate scratch (grow-only, reused across waves)
     cudaStream_t stream = nullptr;
+    bool profiled = false;             // kernel-level events recorded for this wave
     cudaEvent_t ev_start = nullptr, ev_done = nullptr, ev_g0 = nullptr, ev_g1 = nullptr, ev_i0 = nullptr, ev_i1 = nullptr;
     bool ran_inflate = false;
     bool own_stream = false;
@@ -159,6 +160,7 @@ struct nz_ctx {
     int device;
     int sm_count;
     int gather_grid;       // persistent grid size for k_gather
+    bool profile = false;   // record per-kernel CUDA events in every wave (nz_set_profiling / env NZ_PROFILE=1)
     bool coalesce = true;   // env NZ_COALESCE=0 turns request coalescing off (A/B measurements)
     int gather_variant = 0; // index into the k_gather variant table (env NZ_GATHER_VARIANT for sweeps)
     int inflate_grid;
@@ -199,8 +201,11 @@ struct NzPlanArgs {
     const NzSlot* table; uint64_t line_mask;
     const NzDesc* descs;
     const uint8_t* arena;
-    const NzDevReq* reqs; uint32_t n;
-    const NzDevSeg* segs; uint32_t nseg;
+    const NzDevReq* reqs_host; uint32_t n;      // mapped pinned (written by the host at submit)
+    const NzDevSeg* segs_host; uint32_t nseg;
+    NzDevReq* reqs_dev;                         // staged copies in HBM (filled by k_plan)
+    NzDevSeg* segs_dev;
+    int32_t* rq_stat;                           // n: per-request status as of phase A
     NzDevRes* res;
     NzSegWork* work;            // nseg entries
     uint64_t* tile_begin;       // nseg + 1

@@ -175,12 +175,28 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint6
     const uint32_t tid = threadIdx.x;
     const uint32_t g = tid >> 2;
 
+    // ---- stage the wave's descriptors from mapped pinned memory into HBM: one coalesced PCIe
+    // read instead of a round trip every time a later phase looks at a request or a slice -----
+    {
+        const uint4* s4 = reinterpret_cast<const uint4*>(a.reqs_host);
+        uint4* d4 = reinterpret_cast<uint4*>(a.reqs_dev);
+        for (uint32_t i = tid; i < a.n * (uint32_t)(sizeof(NzDevReq) / 16); i += 1024) d4[i] = s4[i];
+        s4 = reinterpret_cast<const uint4*>(a.segs_host);
+        d4 = reinterpret_cast<uint4*>(a.segs_dev);
+        for (uint32_t i = tid; i < a.nseg * (uint32_t)(sizeof(NzDevSeg) / 16); i += 1024) d4[i] = s4[i];
+        if (tid < 4) a.counters[tid] = 0;
+    }
+    __threadfence_block();
+    __syncthreads();
+    const NzDevReq* __restrict__ reqs = a.reqs_dev;
+    const NzDevSeg* __restrict__ segs = a.segs_dev;
+
     // ---- phase A: probe + per-request validation --------------------------
     for (uint32_t base = 0; base < a.n; base += 256) {
         const uint32_t r = base + g;
         const bool active = r < a.n;
         NzDevReq rq;
-        if (active) rq = a.reqs[r];
+        if (active) rq = reqs[r];
         else { rq.k0 = rq.k1 = 0; }
         const uint32_t d = probe_group4(a.table, a.line_mask, rq.k0, rq.k1, active);
         if (!active || (tid & 3u) != 0) continue;
@@ -210,7 +226,7 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint6
                 if (len > rq.dst_cap) out.status = NZ_ERANGE;
             } else {
                 for (uint32_t i = 0; i < rq.nseg; ++i) {
-                    const NzDevSeg sg = a.segs[rq.seg_begin + i];
+                    const NzDevSeg sg = segs[rq.seg_begin + i];
                     if (sg.src_off > len || sg.len > len - sg.src_off) { out.status = NZ_EINVAL; break; }
                     if (sg.dst_off > rq.dst_cap || sg.len > rq.dst_cap - sg.dst_off) { out.status = NZ_ERANGE; break; }
                     bytes += sg.len;
@@ -255,6 +271,7 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint6
         rq_len[r] = len;
         rq_tab[r] = tab;
         rq_ssz[r] = ssz;
+        a.rq_stat[r] = out.status;
         a.res[r] = out;
     }
     __syncthreads();
@@ -263,9 +280,9 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint6
     uint64_t* tile_cnt = a.tile_begin;           // counts first, scanned in place in B3
     for (uint32_t s = tid; s < a.nseg; s += 1024) {
         uint64_t tiles = 0;
-        const NzDevSeg sg = a.segs[s];
-        const NzDevReq& rq = a.reqs[sg.req];
-        const int32_t st = a.res[sg.req].status;
+        const NzDevSeg sg = segs[s];
+        const NzDevReq& rq = reqs[sg.req];
+        const int32_t st = a.rq_stat[sg.req];
         NzSegWork w;
         w.src = 0; w.dst = 0; w.len = 0; w.vstart = 0;
         const uint64_t rlen = rq_len[sg.req];
@@ -365,20 +382,20 @@ k_plan_verify(NzPlanArgs a) {
     const uint32_t g = tid >> 2;
     for (uint32_t base = 0; base < a.n; base += 64) {
         const uint32_t r = base + g;
-        const bool want = r < a.n && (a.reqs[r].flags & NZ_GET_VERIFY) && a.res[r].status == NZ_OK;
+        const bool want = r < a.n && (a.reqs_dev[r].flags & NZ_GET_VERIFY) && a.rq_stat[r] == NZ_OK;
         uint64_t k0 = 0, k1 = 0;
-        if (want) { k0 = a.reqs[r].k0; k1 = a.reqs[r].k1; }
+        if (want) { k0 = a.reqs_dev[r].k0; k1 = a.reqs_dev[r].k1; }
         const uint32_t d = probe_group4(a.table, a.line_mask, k0, k1, want);
         if (!want || (tid & 3u) != 0 || d == 0xFFFFFFFFu) continue;
         const NzDesc ds = a.descs[d];
-        const NzDevReq rq = a.reqs[r];
+        const NzDevReq rq = a.reqs_dev[r];
         if ((rq.flags & NZ_GET_INFLATE) && (ds.flags & NZ_ENC_GZIP)) continue;   // done in k_plan
         if (ds.flags & NZ_ENC_STRIPED) continue;     // stripes carry their own chunk tables on their GPUs (verified at fill)
         const uint32_t* tab = reinterpret_cast<const uint32_t*>(a.arena + ds.crc_tab_off);
         const uint32_t nsg = rq.whole ? 1u : rq.nseg;
         for (uint32_t i = 0; i < nsg; ++i) {
             uint64_t off = 0, len = ds.stored_len;
-            if (!rq.whole) { const NzDevSeg sg = a.segs[rq.seg_begin + i]; off = sg.src_off; len = sg.len; }
+            if (!rq.whole) { const NzDevSeg sg = a.segs_dev[rq.seg_begin + i]; off = sg.src_off; len = sg.len; }
             if (!len) continue;
             const uint32_t c0 = (uint32_t)(off / NZ_CRC_CHUNK), c1 = (uint32_t)((off + len - 1) / NZ_CRC_CHUNK);
             const uint32_t cnt = c1 - c0 + 1;

@@ -303,6 +303,9 @@ class Zone:
         k = (C.c_uint8 * 16).from_buffer_copy(key)
         return self.L.nz_debug_poke(self.ctx, k, off, xor_mask)
 
+    def set_profiling(self, on: bool = True):
+        check(self.L.nz_set_profiling(self.ctx, 1 if on else 0), "nz_set_profiling")
+
     def stats(self) -> capi.Stats:
         s = capi.Stats()
         check(self.L.nz_get_stats(self.ctx, C.byref(s)), "nz_get_stats")

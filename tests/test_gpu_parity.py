@@ -157,10 +157,12 @@ def test_wave_of_mixed_requests(zone, objects):
             b = zone.alloc_device(max(len(d), 1))
             gets.append(nz.Get(K(i), b)); expect.append((capi.NZ_OK, d.tobytes()))
         bufs.append(b)
+    zone.set_profiling(True)
     t = zone.submit(gets)
     res = t.wait()
     assert t.elapsed_ms() >= 0 and t.gather_ms() >= 0
     t.free()
+    zone.set_profiling(False)
     for r, (st, body), b in zip(res, expect, bufs):
         assert r.status == st
         if st == capi.NZ_OK:
