@@ -115,6 +115,8 @@ typedef struct nz_stats {
     uint64_t objects, arena_bytes, arena_used, table_slots, table_live;
     uint64_t gets, get_bytes, hits, misses, puts, put_bytes, evictions, corrupt;
     uint64_t kernel_launches;   /* kernels launched by this library since init     */
+    uint64_t file_cufile_bytes; /* nz_put_file bytes that arrived through cuFile/GDS */
+    uint64_t file_bounce_bytes; /* ... and through pread + pinned bounce buffers    */
 } nz_stats;
 
 /* ---- lifecycle ----------------------------------------------------------- */

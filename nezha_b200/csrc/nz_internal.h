@@ -183,7 +183,7 @@ struct nz_ctx {
     std::mutex tmu;
     std::vector<nz_ticket*> ticket_pool;
     // stats
-    std::atomic<uint64_t> gets{0}, get_bytes{0}, hits{0}, misses{0}, puts{0}, put_bytes{0}, evictions{0}, corrupt{0}, launches{0};
+    std::atomic<uint64_t> gets{0}, get_bytes{0}, hits{0}, misses{0}, puts{0}, put_bytes{0}, evictions{0}, corrupt{0}, launches{0}, file_cufile_bytes{0}, file_bounce_bytes{0};
     // bounce buffers for nz_put_file / pageable writes
     void* bounce[2] = {nullptr, nullptr};
     size_t bounce_bytes = 0;
@@ -236,6 +236,7 @@ cudaError_t nz_launch_crc_chunks(const uint8_t* p, uint64_t n, uint32_t* chunk_o
                                  const uint32_t* crc_tables, int sm_count, cudaStream_t s);
 cudaError_t nz_launch_inflate(const NzInflWork* infl, uint64_t* meta, uint32_t* counters, NzDevRes* res,
                               const uint32_t* crc_tables, int grid, int sm_count, cudaStream_t s);
+int64_t nz_cufile_read(int fd, uint64_t file_off, void* dev_base, uint64_t dev_off, uint64_t len);
 cudaError_t nz_upload_constants(uint32_t* crc_tables_dev);
 cudaError_t nz_inflate_upload_constants();
 int nz_gather_blocks_per_sm(int variant);

@@ -278,6 +278,27 @@ def test_put_file_fill_path(zone, tmp_path):
     res, body = zone.get(K(902), segs=[(16 << 20, 1 << 20)])
     assert body == d[16 << 20:17 << 20].tobytes()
     zone.evict(K(902))
+    st = zone.stats()
+    assert st.file_cufile_bytes + st.file_bounce_bytes >= len(d)      # one of the two paths carried the file
+    # unaligned file offset / length / destination offset through whichever path is active
+    fd = os.open(f, os.O_RDONLY)
+    try:
+        k = K(903)
+        import ctypes as C
+        kk = (C.c_uint8 * 16).from_buffer_copy(k)
+        p = C.c_void_p()
+        n = 1_000_003
+        capi.check(zone.L.nz_put_begin(zone.ctx, kk, n, n, 0, 0, C.byref(p)), "put_begin")
+        capi.check(zone.L.nz_put_file(p, fd, 12_345, 0, 500_001), "put_file a")
+        capi.check(zone.L.nz_put_file(p, fd, 12_345 + 500_001, 500_001, n - 500_001), "put_file b")
+        crc = C.c_uint32()
+        capi.check(zone.L.nz_put_commit(p, 0, 0, C.byref(crc)), "commit")
+    finally:
+        os.close(fd)
+    assert crc.value == o.crc32c(d[12_345:12_345 + n])
+    res, body = zone.get(K(903))
+    assert body == d[12_345:12_345 + n].tobytes()
+    zone.evict(K(903))
 
 
 def test_sharded_zone_rejects_foreign_keys():
