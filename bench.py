@@ -515,7 +515,7 @@ def http_bench(L_obj, requests, device, seed=2):
 
         # ---- GPU proxy ----
         p = subprocess.Popen([os.path.join(ROOT, "nezha_b200", "_build", "nzproxy"), "--listen", f"127.0.0.1:{gport}", "--device", str(device),
-                              "--arena-gib", str(L_obj / 2**30 + 0.5), "--max-conns", str(2 * nconn), "--window-mib", "4", "--first-window-kib", "256",
+                              "--arena-gib", str(L_obj / 2**30 + 0.5), "--max-conns", str(2 * nconn), "--window-mib", "4", "--first-window-kib", "64",
                               "--upstream", f"{host}=127.0.0.1:{oport}"], start_new_session=True, stderr=subprocess.DEVNULL)
         procs.append(p)
         if wait_port(gport):

@@ -52,6 +52,8 @@ extern "C" {
 /* ---- get flags ---------------------------------------------------------- */
 #define NZ_GET_INFLATE  1u    /* serve the inflated representation (SPEC G)       */
 #define NZ_GET_VERIFY   2u    /* recompute CRC-32C of every 64 KiB chunk touched  */
+#define NZ_GET_URGENT   4u    /* latency-critical (first window of a response): the wave runs on a
+                                 high-priority stream so it is not queued behind bulk waves      */
 
 /* ---- buffer kinds -------------------------------------------------------- */
 #define NZ_BUF_PINNED_HOST 0  /* cudaHostAlloc, mapped: kernels write it directly */

@@ -16,7 +16,7 @@ NZ_OK, NZ_EINVAL, NZ_ENOMEM, NZ_ECUDA, NZ_ENOTFOUND = 0, -1, -2, -3, -4
 NZ_ECORRUPT, NZ_ETIMEOUT, NZ_EEXIST, NZ_EFULL, NZ_ENOSYS, NZ_ERANGE = -5, -6, -7, -8, -9, -10
 NZ_ENC_IDENTITY, NZ_ENC_GZIP, NZ_ENC_STRIPE, NZ_ENC_STRIPED = 0, 1, 4, 8
 NZ_IPC_HANDLE_BYTES = 64
-NZ_GET_INFLATE, NZ_GET_VERIFY = 1, 2
+NZ_GET_INFLATE, NZ_GET_VERIFY, NZ_GET_URGENT = 1, 2, 4
 NZ_BUF_PINNED_HOST, NZ_BUF_DEVICE = 0, 1
 NZ_CRC_CHUNK = 65536
 

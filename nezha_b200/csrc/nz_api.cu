@@ -120,6 +120,16 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
         c->streams.push_back(s);
     }
     CKI(cudaStreamCreateWithFlags(&c->put_stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        CKI(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        for (int i = 0; i < 4; ++i) {
+            cudaStream_t s;
+            CKI(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi));
+            c->hi_streams.push_back(s);
+        }
+        if (const char* ev = getenv("NZ_HOST_GRID")) c->host_grid = atoi(ev) > 0 ? atoi(ev) : c->host_grid;
+    }
     CKI(cudaMalloc(&c->peer_base_dev, sizeof(uint64_t) * c->cfg.shard_count));
     CKI(cudaMemset(c->peer_base_dev, 0, sizeof(uint64_t) * c->cfg.shard_count));
     c->peer_ptrs.assign(c->cfg.shard_count, nullptr);
@@ -164,6 +174,7 @@ int32_t nz_shutdown(nz_ctx* c) {
     cudaDeviceSynchronize();
     for (nz_ticket* t : c->ticket_pool) ticket_destroy(t);
     for (cudaStream_t s : c->streams) cudaStreamDestroy(s);
+    for (cudaStream_t s : c->hi_streams) cudaStreamDestroy(s);
     if (c->put_stream) cudaStreamDestroy(c->put_stream);
     for (int i = 0; i < 2; ++i) {
         if (c->bounce[i]) cudaFreeHost(c->bounce[i]);
@@ -597,7 +608,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     CK(cudaSetDevice(c->device));
     // ---- host-side sizing ----
     uint64_t nseg = 0;
-    bool any_inflate = false, any_verify = false;
+    bool any_inflate = false, any_verify = false, any_urgent = false, all_host = true;
     // K5: a GET of a striped object is split at stripe boundaries here (the host knows the stripe
     // size from its shadow), so on the device every slice lies inside exactly one stripe
     std::vector<std::vector<nz_seg>> split;
@@ -631,6 +642,8 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
         else nseg += r.nseg ? r.nseg : 1;
         any_inflate |= (r.flags & NZ_GET_INFLATE) != 0;
         any_verify |= (r.flags & NZ_GET_VERIFY) != 0;
+        any_urgent |= (r.flags & NZ_GET_URGENT) != 0;
+        all_host &= r.dst->kind == NZ_BUF_PINNED_HOST;
     }
     if (nseg > 0x7fffffffull) return NZ_EINVAL;
     // verify work bound + inflate scratch sizing come from the host shadow (metadata only; the
@@ -764,7 +777,9 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     a.peer_base = c->peer_base_dev;
     a.tile_bytes = nz_gather_tile_bytes(c->gather_variant);
 
-    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : c->streams[c->rr.fetch_add(1) % c->streams.size()];
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream
+                     : any_urgent ? c->hi_streams[c->rr.fetch_add(1) % c->hi_streams.size()]
+                                  : c->streams[c->rr.fetch_add(1) % c->streams.size()];
     t->stream = s;
     cudaError_t e;
 #define CKT(call) do { e = (call); if (e != cudaSuccess) { int32_t rc = cuda_fail(e, #call); nz_ticket_free(t); return rc; } } while (0)
@@ -782,6 +797,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     if (t->profiled) CKT(cudaEventRecord(t->ev_g0, s));
     int ggrid = c->gather_grid;
     if (tile_bound && tile_bound < (uint64_t)ggrid) ggrid = (int)tile_bound;   // small waves: no more CTAs than tiles
+    if (all_host && !cuda_stream && ggrid > c->host_grid) ggrid = c->host_grid;  // PCIe-bound wave: a few SMs saturate the link
     CKT(nz_launch_gather(c->gather_variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s));
     if (t->profiled) CKT(cudaEventRecord(t->ev_g1, s));
     c->launches += 1;

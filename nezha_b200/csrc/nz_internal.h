@@ -179,6 +179,8 @@ struct nz_ctx {
     std::vector<cudaStream_t> streams;
     std::atomic<uint32_t> rr{0};
     cudaStream_t put_stream = nullptr;
+    std::vector<cudaStream_t> hi_streams;   // highest priority: NZ_GET_URGENT waves
+    int host_grid = 32;                     // CTAs for waves that only write pinned host memory (PCIe bound: leave the SMs free)
     // ticket recycling
     std::mutex tmu;
     std::vector<nz_ticket*> ticket_pool;

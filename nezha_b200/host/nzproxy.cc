@@ -27,6 +27,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -51,7 +53,7 @@ struct Options {
     uint64_t arena_bytes = 8ull << 30;
     uint32_t max_objects = 1u << 16;
     uint64_t window_bytes = 4ull << 20;
-    uint64_t first_window = 256ull << 10;   // small first window keeps time-to-first-byte low
+    uint64_t first_window = 64ull << 10;    // small first window keeps time-to-first-byte low (then x8 per window)
     int max_conns = 512;
     bool gunzip = false;
     bool verify = false;
@@ -343,6 +345,74 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
     return 200;
 }
 
+// ---- wave combiner ---------------------------------------------------------------
+// Every connection streams its response through windows; submitting each window as its own
+// wave would queue hundreds of tiny kernel pairs on the device.  Instead connection threads
+// enqueue their window requests and a dispatcher thread turns whatever is queued into ONE wave
+// (one plan + one gather kernel for all connections).  Two lanes: `urgent` carries the small
+// first window of every response on a high-priority stream (time to first byte), `bulk` the rest.
+struct WaveItem {
+    nz_get_req rq;
+    nz_seg sg;
+    nz_get_res rs;
+    int32_t rc = NZ_ECUDA;
+    std::atomic<int> done{0};
+};
+
+struct Combiner {
+    nz_ctx* ctx = nullptr;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<WaveItem*> q;
+    uint64_t cap_bytes = 64ull << 20;     // payload per wave: bounds how long a wave holds the PCIe link
+    int linger_us = 0;
+    bool stop = false;
+
+    void push(WaveItem* it) {
+        { std::lock_guard<std::mutex> g(mu); q.push_back(it); }
+        cv.notify_one();
+    }
+    static void wait(WaveItem* it) {
+        for (int spin = 0; spin < 2000 && !it->done.load(std::memory_order_acquire); ++spin) std::this_thread::yield();
+        while (!it->done.load(std::memory_order_acquire)) it->done.wait(0, std::memory_order_acquire);
+    }
+    void run() {
+        std::vector<WaveItem*> batch;
+        std::vector<nz_get_req> reqs;
+        std::vector<nz_get_res> res;
+        for (;;) {
+            batch.clear();
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || !q.empty(); });
+                if (stop) return;
+                if (linger_us > 0 && q.size() < 8) cv.wait_for(lk, std::chrono::microseconds(linger_us));
+                uint64_t bytes = 0;
+                while (!q.empty() && batch.size() < 512 && (batch.empty() || bytes + q.front()->sg.len <= cap_bytes)) {
+                    bytes += q.front()->sg.len;
+                    batch.push_back(q.front());
+                    q.pop_front();
+                }
+            }
+            reqs.resize(batch.size());
+            res.resize(batch.size());
+            for (size_t i = 0; i < batch.size(); ++i) { reqs[i] = batch[i]->rq; reqs[i].segs = &batch[i]->sg; }
+            nz_ticket* t = nullptr;
+            int32_t rc = nz_get_submit(ctx, reqs.data(), (uint32_t)reqs.size(), nullptr, &t);
+            if (rc == NZ_OK) rc = nz_get_wait(t, -1, res.data());
+            if (t) nz_ticket_free(t);
+            for (size_t i = 0; i < batch.size(); ++i) {
+                batch[i]->rc = rc;
+                if (rc == NZ_OK) batch[i]->rs = res[i];
+                batch[i]->done.store(1, std::memory_order_release);
+                batch[i]->done.notify_one();
+            }
+        }
+    }
+};
+
+static Combiner g_urgent, g_bulk;
+
 // ---- serving -------------------------------------------------------------------
 bool send_plan(Server& S, int fd, const nzh::Plan& plan, const Entry* ent, bool keep_alive, nz_buf* win[2]) {
     std::string h = std::string("HTTP/1.1 ") + std::to_string(plan.status) + " " + status_text(plan.status) + "\r\nServer: nginx\r\nDate: " +
@@ -355,46 +425,46 @@ bool send_plan(Server& S, int fd, const nzh::Plan& plan, const Entry* ent, bool 
     // the first bytes of the body.
     std::string pending = h;
     const uint32_t flags = (plan.inflated ? NZ_GET_INFLATE : 0) | (S.opt.verify ? NZ_GET_VERIFY : 0);
+    bool first = true;                                   // first window of the RESPONSE: small and urgent
     for (const nzh::Part& part : plan.body) {
         if (part.literal) { pending += part.bytes; continue; }
         uint64_t off = part.off, left = part.len;
-        nz_ticket* tk[2] = {nullptr, nullptr};
-        uint64_t tk_len[2] = {0, 0};
+        WaveItem item[2];
+        bool live[2] = {false, false};
         int cur = 0;
-        bool first = true;
-        auto submit = [&](int slot) -> bool {
-            if (!left) { tk[slot] = nullptr; return true; }
-            const uint64_t n = std::min<uint64_t>(left, first ? S.opt.first_window : S.opt.window_bytes);
+        uint64_t ramp = S.opt.first_window;
+        auto submit = [&](int slot) {
+            live[slot] = false;
+            if (!left) return;
+            const uint64_t n = std::min<uint64_t>(left, std::min<uint64_t>(ramp, S.opt.window_bytes));
+            ramp = std::min<uint64_t>(ramp * 8, S.opt.window_bytes);          // 1st window small, then grow quickly
+            WaveItem& it = item[slot];
+            memset(&it.rq, 0, sizeof it.rq);
+            memcpy(it.rq.key, ent->key128, 16);
+            it.rq.flags = flags | (first ? NZ_GET_URGENT : 0u);
+            it.sg = nz_seg{off, n, 0};
+            it.rq.nseg = 1; it.rq.segs = &it.sg; it.rq.dst = win[slot];
+            it.rc = NZ_ECUDA;
+            it.done.store(0, std::memory_order_relaxed);
+            (first ? g_urgent : g_bulk).push(&it);
             first = false;
-            nz_get_req rq;
-            memset(&rq, 0, sizeof rq);
-            memcpy(rq.key, ent->key128, 16);
-            rq.flags = flags;
-            nz_seg sg = {off, n, 0};
-            rq.nseg = 1; rq.segs = &sg; rq.dst = win[slot];
-            if (nz_get_submit(S.ctx, &rq, 1, nullptr, &tk[slot]) != NZ_OK) return false;
-            tk_len[slot] = n;
+            live[slot] = true;
             off += n;
             left -= n;
-            return true;
         };
-        if (!submit(0)) return false;
-        while (tk[cur]) {
-            if (!submit(cur ^ 1)) { nz_ticket_free(tk[cur]); return false; }        // next window in flight while this one is sent
-            nz_get_res rs;
-            const int32_t rc = nz_get_wait(tk[cur], -1, &rs);
-            nz_ticket_free(tk[cur]);
-            tk[cur] = nullptr;
-            if (rc != NZ_OK || rs.status != NZ_OK) {
-                if (tk[cur ^ 1]) { nz_get_wait(tk[cur ^ 1], -1, nullptr); nz_ticket_free(tk[cur ^ 1]); }
-                return false;                                                         // mid-body failure: drop the connection
+        submit(0);
+        while (live[cur]) {
+            submit(cur ^ 1);                                                  // next window in flight while this one is sent
+            Combiner::wait(&item[cur]);
+            live[cur] = false;
+            bool ok = item[cur].rc == NZ_OK && item[cur].rs.status == NZ_OK;
+            if (ok && !pending.empty()) { ok = write_all(fd, pending.data(), pending.size()); pending.clear(); }
+            if (ok) ok = write_all(fd, nz_buf_ptr(win[cur]), item[cur].sg.len);
+            if (!ok) {
+                if (live[cur ^ 1]) Combiner::wait(&item[cur ^ 1]);            // never leave a queued item pointing at this stack frame
+                return false;                                                 // mid-body failure: drop the connection
             }
-            if (!pending.empty()) {
-                if (!write_all(fd, pending.data(), pending.size())) { if (tk[cur ^ 1]) { nz_get_wait(tk[cur ^ 1], -1, nullptr); nz_ticket_free(tk[cur ^ 1]); } return false; }
-                pending.clear();
-            }
-            if (!write_all(fd, nz_buf_ptr(win[cur]), tk_len[cur])) { if (tk[cur ^ 1]) { nz_get_wait(tk[cur ^ 1], -1, nullptr); nz_ticket_free(tk[cur ^ 1]); } return false; }
-            S.bytes_out += tk_len[cur];
+            S.bytes_out += item[cur].sg.len;
             cur ^= 1;
         }
     }
@@ -544,6 +614,13 @@ int main(int argc, char** argv) {
         if (nz_buf_alloc(S.ctx, S.opt.window_bytes, NZ_BUF_PINNED_HOST, &b) != NZ_OK) break;
         S.free_windows.push_back(b);
     }
+    g_urgent.ctx = S.ctx; g_urgent.cap_bytes = 16ull << 20; g_urgent.linger_us = 0;
+    g_bulk.ctx = S.ctx; g_bulk.cap_bytes = 128ull << 20; g_bulk.linger_us = 20;
+    std::thread([] { g_urgent.run(); }).detach();
+    std::thread([] { g_urgent.run(); }).detach();
+    std::thread([] { g_bulk.run(); }).detach();
+    std::thread([] { g_bulk.run(); }).detach();
+    std::thread([] { g_bulk.run(); }).detach();
     int ls = socket(AF_INET, SOCK_STREAM, 0);
     int one = 1;
     setsockopt(ls, SOL_SOCKET, SO_REUSEADDR, &one, sizeof one);
