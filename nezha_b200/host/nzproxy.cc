@@ -368,12 +368,19 @@ struct Combiner {
     int linger_us = 0;
     bool stop = false;
 
+    std::atomic<int> pending{0};
+    int spin_us = 0;
     void push(WaveItem* it) {
-        { std::lock_guard<std::mutex> g(mu); q.push_back(it); }
+        { std::lock_guard<std::mutex> g(mu); q.push_back(it); pending.store(1, std::memory_order_release); }
         cv.notify_one();
     }
     static void wait(WaveItem* it) {
-        for (int spin = 0; spin < 2000 && !it->done.load(std::memory_order_acquire); ++spin) std::this_thread::yield();
+        // a window is ready in tens of microseconds: poll briefly before paying a futex sleep + wake-up
+        const auto t0 = std::chrono::steady_clock::now();
+        while (!it->done.load(std::memory_order_acquire)) {
+            __builtin_ia32_pause();
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(150)) break;
+        }
         while (!it->done.load(std::memory_order_acquire)) it->done.wait(0, std::memory_order_acquire);
     }
     void run() {
@@ -384,6 +391,16 @@ struct Combiner {
             batch.clear();
             {
                 std::unique_lock<std::mutex> lk(mu);
+                if (q.empty() && spin_us > 0) {          // hot dispatcher: poll the queue for a while before sleeping
+                    lk.unlock();
+                    const auto t0 = std::chrono::steady_clock::now();
+                    for (;;) {
+                        __builtin_ia32_pause();
+                        if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(spin_us)) break;
+                        if (pending.load(std::memory_order_acquire)) break;
+                    }
+                    lk.lock();
+                }
                 cv.wait(lk, [&] { return stop || !q.empty(); });
                 if (stop) return;
                 if (linger_us > 0 && q.size() < 8) cv.wait_for(lk, std::chrono::microseconds(linger_us));
@@ -393,6 +410,7 @@ struct Combiner {
                     batch.push_back(q.front());
                     q.pop_front();
                 }
+                if (q.empty()) pending.store(0, std::memory_order_release);
             }
             reqs.resize(batch.size());
             res.resize(batch.size());
@@ -614,7 +632,7 @@ int main(int argc, char** argv) {
         if (nz_buf_alloc(S.ctx, S.opt.window_bytes, NZ_BUF_PINNED_HOST, &b) != NZ_OK) break;
         S.free_windows.push_back(b);
     }
-    g_urgent.ctx = S.ctx; g_urgent.cap_bytes = 16ull << 20; g_urgent.linger_us = 0;
+    g_urgent.ctx = S.ctx; g_urgent.cap_bytes = 16ull << 20; g_urgent.linger_us = 0; g_urgent.spin_us = 2000;
     g_bulk.ctx = S.ctx; g_bulk.cap_bytes = 128ull << 20; g_bulk.linger_us = 20;
     std::thread([] { g_urgent.run(); }).detach();
     std::thread([] { g_urgent.run(); }).detach();
