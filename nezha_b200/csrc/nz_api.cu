@@ -112,7 +112,7 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
     CKI(cudaMemset(c->table, 0, lines * 4 * sizeof(NzSlot)));
     CKI(cudaMalloc(&c->descs, (size_t)c->cfg.max_objects * sizeof(NzDesc)));
     CKI(cudaMemset(c->descs, 0, (size_t)c->cfg.max_objects * sizeof(NzDesc)));
-    CKI(cudaMalloc(&c->crc_tables, 16 * 256 * sizeof(uint32_t)));
+    CKI(cudaMalloc(&c->crc_tables, (16 * 256 + 2 * 1280) * sizeof(uint32_t)));   // slice tables + fast-path tables (nz_crc.cuh)
     CKI(nz_upload_constants(c->crc_tables));
     for (int i = 0; i < 8; ++i) {
         cudaStream_t s;

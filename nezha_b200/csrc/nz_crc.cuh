@@ -89,6 +89,80 @@ __device__ uint32_t block_crc_chunk(const uint8_t* __restrict__ p, uint32_t m, c
     return r;
 }
 
+// ---------------------------------------------------------------------------
+// Fast path for a FULL 64 KiB chunk on a 16 B aligned pointer: coalesced 16 B loads.
+// Thread t reads vector t of each 4 KiB row (16 rows); each of its four 32-bit lanes keeps its own
+// running remainder with the row stride folded in:  acc = Z_4096(acc) ^ word   (Z_k = "append k zero
+// bytes", a linear map on 32 bits = 4 lookups in the stride table).  At the end the four lanes are
+// merged with the ordinary slice tables (Z_4), the thread's value is moved to the chunk end with one
+// GF(2) multiply by x^(8*(4096-16t-12)) and the CTA XOR-reduces.  The stride table is replicated
+// 8x in shared memory ([entry][copy], copy = lane & 7) so that random indices spread over the banks.
+//   fast tables in global memory (per polynomial): ZS[4*256] | K[256]
+// ---------------------------------------------------------------------------
+constexpr int NZ_CRC_FAST_WORDS = 4 * 256 + 256;
+
+template <int POLY>
+__device__ uint32_t block_crc_chunk64k(const uint8_t* __restrict__ p, const uint32_t* sZS8, const uint32_t* sT,
+                                       const uint32_t* __restrict__ gK, uint32_t* sred) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t cp = tid & 7u;
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    const uint4* v = reinterpret_cast<const uint4*>(p) + tid;
+#define NZ_ZS(a) (sZS8[((a) & 0xffu) * 8u + cp] ^ sZS8[(256u + (((a) >> 8) & 0xffu)) * 8u + cp] ^ \
+                  sZS8[(512u + (((a) >> 16) & 0xffu)) * 8u + cp] ^ sZS8[(768u + ((a) >> 24)) * 8u + cp])
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        uint4 w = crc_ldg16(v + i * 256);
+        if (i == 0 && tid == 0) w.x ^= 0xFFFFFFFFu;        // the CRC's initial value, folded into the first word
+        a0 = NZ_ZS(a0) ^ w.x;
+        a1 = NZ_ZS(a1) ^ w.y;
+        a2 = NZ_ZS(a2) ^ w.z;
+        a3 = NZ_ZS(a3) ^ w.w;
+    }
+#undef NZ_ZS
+#define NZ_Z4(a) (sT[3 * 256 + ((a) & 0xffu)] ^ sT[2 * 256 + (((a) >> 8) & 0xffu)] ^ sT[256 + (((a) >> 16) & 0xffu)] ^ sT[(a) >> 24])
+    uint32_t vv = NZ_Z4(a0) ^ a1;
+    vv = NZ_Z4(vv) ^ a2;
+    vv = NZ_Z4(vv) ^ a3;
+#undef NZ_Z4
+    uint32_t contrib = gf_mul<POLY>(__ldg(gK + tid), vv);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) contrib ^= __shfl_xor_sync(0xffffffffu, contrib, o);
+    __syncthreads();
+    if ((tid & 31u) == 0) sred[tid >> 5] = contrib;
+    __syncthreads();
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r ^= sred[i];
+    return ~r;
+}
+
+// loads the replicated stride table of one polynomial into shared memory (256 threads)
+__device__ __forceinline__ void crc_load_fast_tables(uint32_t* sZS8, const uint32_t* __restrict__ gfast) {
+    for (uint32_t i = threadIdx.x; i < 1024u * 8u; i += blockDim.x) sZS8[i] = gfast[i >> 3];
+}
+
+// host: fills ZS | K for both polynomials (2 * NZ_CRC_FAST_WORDS words)
+static inline void nz_crc_fill_fast_tables(uint32_t* out) {
+    for (int poly = 0; poly < 2; ++poly) {
+        uint32_t* T = out + poly * NZ_CRC_FAST_WORDS;
+        auto mul = [&](uint32_t a, uint32_t b) { return poly ? gf_mul<1>(a, b) : gf_mul<0>(a, b); };
+        auto xpow8 = [&](uint64_t nbytes) {
+            uint32_t p = 0x80000000u, sq = 0x80000000u >> 8;
+            while (nbytes) {
+                if (nbytes & 1) p = mul(sq, p);
+                sq = mul(sq, sq);
+                nbytes >>= 1;
+            }
+            return p;
+        };
+        const uint32_t xs = xpow8(4096);
+        for (int k = 0; k < 4; ++k)
+            for (uint32_t b = 0; b < 256; ++b) T[k * 256 + b] = mul(xs, b << (8 * k));
+        for (uint32_t t = 0; t < 256; ++t) T[1024 + t] = xpow8(4096 - 16 * t - 12);
+    }
+}
+
 // fills this translation unit's c_x8pow
 static inline cudaError_t nz_crc_upload_constants() {
     uint32_t h[2][48];

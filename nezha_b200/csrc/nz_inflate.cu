@@ -419,8 +419,11 @@ __global__ void __launch_bounds__(256)
 k_inflate_crc(const NzInflWork* __restrict__ infl, const uint64_t* __restrict__ meta, const uint32_t* __restrict__ counters,
               NzDevRes* res, const uint32_t* __restrict__ tables) {
     __shared__ uint32_t sT[4 * 256];
+    __shared__ uint32_t sZS8[1024 * 8];
     __shared__ uint32_t sred[8];
+    const uint32_t* fast = tables + 16 * 256 + NZ_CRC_FAST_WORDS;                         // IEEE: ZS | K
     for (uint32_t i = threadIdx.x; i < 1024; i += 256) sT[i] = tables[8 * 256 + i];   // IEEE slice tables
+    crc_load_fast_tables(sZS8, fast);
     __syncthreads();
     const uint32_t n = counters[1];
     for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
@@ -431,7 +434,8 @@ k_inflate_crc(const NzInflWork* __restrict__ infl, const uint64_t* __restrict__ 
         uint32_t acc = 0;
         for (uint64_t off = 0; off < len; off += NZ_CRC_CHUNK) {
             const uint32_t cl = (uint32_t)min((uint64_t)NZ_CRC_CHUNK, (uint64_t)len - off);
-            const uint32_t c = block_crc_chunk<1>(p + off, cl, sT, sred);
+            const uint32_t c = (cl == NZ_CRC_CHUNK && (((uintptr_t)p) & 15u) == 0) ? block_crc_chunk64k<1>(p + off, sZS8, sT, fast + 1024, sred)
+                                                                                    : block_crc_chunk<1>(p + off, cl, sT, sred);
             if (off == 0) acc = c;
             else acc = gf_mul<1>(cl == NZ_CRC_CHUNK ? c_x8pow[1][16] : gf_xpow8<1>(cl), acc) ^ c;
         }

@@ -615,14 +615,19 @@ k_gather(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_b
 __global__ void __launch_bounds__(256)
 k_crc_chunks(const uint8_t* __restrict__ p, uint64_t n, uint32_t* __restrict__ chunk_out, const uint32_t* __restrict__ tables) {
     __shared__ uint32_t sT[4 * 256];
+    __shared__ uint32_t sZS8[1024 * 8];
     __shared__ uint32_t sred[8];
+    const uint32_t* fast = tables + 16 * 256;                 // Castagnoli: ZS | K
     for (uint32_t i = threadIdx.x; i < 1024; i += 256) sT[i] = tables[i];
+    crc_load_fast_tables(sZS8, fast);
     __syncthreads();
     const uint64_t nchunks = (n + NZ_CRC_CHUNK - 1) / NZ_CRC_CHUNK;
+    const bool aligned = (((uintptr_t)p) & 15u) == 0;
     for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
         const uint64_t off = c * NZ_CRC_CHUNK;
         const uint32_t m = (uint32_t)min((uint64_t)NZ_CRC_CHUNK, n - off);
-        const uint32_t crc = block_crc_chunk<0>(p + off, m, sT, sred);
+        const uint32_t crc = (aligned && m == NZ_CRC_CHUNK) ? block_crc_chunk64k<0>(p + off, sZS8, sT, fast + 1024, sred)
+                                                            : block_crc_chunk<0>(p + off, m, sT, sred);
         if (threadIdx.x == 0) chunk_out[c] = crc;
     }
 }
@@ -663,13 +668,18 @@ k_crc_fold(const uint32_t* __restrict__ chunks, uint64_t n, uint32_t* __restrict
 __global__ void __launch_bounds__(256)
 k_verify(const NzVerWork* __restrict__ ver, const uint32_t* __restrict__ counters, NzDevRes* res, const uint32_t* __restrict__ tables) {
     __shared__ uint32_t sT[4 * 256];
+    __shared__ uint32_t sZS8[1024 * 8];
     __shared__ uint32_t sred[8];
+    const uint32_t* fast = tables + 16 * 256;
     for (uint32_t i = threadIdx.x; i < 1024; i += 256) sT[i] = tables[i];
+    crc_load_fast_tables(sZS8, fast);
     __syncthreads();
     const uint32_t n = counters[0];
     for (uint32_t c = blockIdx.x; c < n; c += gridDim.x) {
         const NzVerWork v = ver[c];
-        const uint32_t crc = block_crc_chunk<0>(reinterpret_cast<const uint8_t*>(v.ptr), v.len, sT, sred);
+        const uint8_t* vp = reinterpret_cast<const uint8_t*>(v.ptr);
+        const uint32_t crc = (v.len == NZ_CRC_CHUNK && (v.ptr & 15u) == 0) ? block_crc_chunk64k<0>(vp, sZS8, sT, fast + 1024, sred)
+                                                                           : block_crc_chunk<0>(vp, v.len, sT, sred);
         if (threadIdx.x == 0 && crc != v.expect) res[v.req].status = NZ_ECORRUPT;
     }
 }
@@ -791,7 +801,8 @@ cudaError_t nz_upload_constants(uint32_t* crc_tables_dev) {
     e = nz_inflate_upload_constants();
     if (e != cudaSuccess) return e;
     // slice tables: [0..7] Castagnoli, [8..15] IEEE (gzip trailer CRC-32)
-    static uint32_t t[16 * 256];
+    static uint32_t t[16 * 256 + 2 * NZ_CRC_FAST_WORDS];
+    nz_crc_fill_fast_tables(t + 16 * 256);
     const uint32_t polys[2] = {NZ_POLY_C, NZ_POLY_IEEE};
     for (int pi = 0; pi < 2; ++pi) {
         uint32_t* T = t + pi * 8 * 256;
