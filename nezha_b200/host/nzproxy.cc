@@ -35,6 +35,7 @@
 #include <ctime>
 #include <map>
 #include <memory>
+#include <optional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -58,12 +59,18 @@ struct Options {
     bool gunzip = false;
     bool verify = false;
     std::map<std::string, std::string> upstream;   // proxy_host -> ip:port override (tests; nginx resolves via DNS)
+    std::string pv_dir;                            // durable tier: write-through on fill, bulk reload at start (README.md:123)
+    int inactive_s = 3600;                         // proxy_cache_path ... inactive=60m (nginx.conf:38)
+    int valid_s = 86400;                           // proxy_cache_valid 200 1d (nginx.conf:57)
 };
 
 struct Entry {
     nzh::ObjectMeta meta;
     uint8_t key128[16];
     time_t stored_at;
+    uint32_t crc32c = 0;
+    std::atomic<time_t> last_access{0};    // inactive=60m bookkeeping (nginx.conf:38)
+    std::atomic<int> inflight{0};          // responses currently streaming this object
 };
 
 struct Key16 {
@@ -82,6 +89,7 @@ struct Server {
     std::unordered_map<Key16, std::shared_ptr<Entry>, Key16Hash> index;   // headers blob per object (host side)
     std::mutex fill_mu;                                                    // one fill at a time per process (coalesces stampedes)
     std::mutex win_mu;
+    std::mutex pv_mu;
     std::vector<nz_buf*> free_windows;
     std::atomic<uint64_t> boundary{1};
     std::atomic<int> conns{0};
@@ -216,6 +224,125 @@ int connect_to(const std::string& hostport, int default_port) {
     return fd;
 }
 
+bool write_fd_all(int fd, const void* p, size_t n) {
+    const char* c = static_cast<const char*>(p);
+    while (n) {
+        ssize_t w = ::write(fd, c, n);
+        if (w < 0) { if (errno == EINTR) continue; return false; }
+        c += w; n -= (size_t)w;
+    }
+    return true;
+}
+
+// ---- durable tier (PV): <dir>/<md5hex> extent files + <dir>/index.tsv ------------------------
+// index line: md5hex \t stored_len \t raw_len \t crc32c(hex) \t stored_at \t content-type \t etag \t gzip(0/1) \t last-modified
+std::string tsv(const std::optional<std::string>& s) { return s ? *s : std::string("\x01"); }   // \x01 = absent
+
+void pv_index_append(Server& S, const Entry& e) {
+    char hx[33];
+    for (int i = 0; i < 16; ++i) snprintf(hx + 2 * i, 3, "%02x", e.key128[i]);
+    char num[128];
+    snprintf(num, sizeof num, "\t%llu\t%lld\t%08x\t%lld\t", (unsigned long long)e.meta.stored_length, (long long)e.meta.raw_length, e.crc32c,
+             (long long)e.stored_at);
+    const std::string line = std::string(hx) + num + e.meta.content_type + "\t" + tsv(e.meta.etag) + "\t" + (e.meta.stored_gzip ? "1" : "0") + "\t" +
+                             tsv(e.meta.last_modified) + "\n";
+    std::lock_guard<std::mutex> g(S.pv_mu);
+    int fd = open((S.opt.pv_dir + "/index.tsv").c_str(), O_WRONLY | O_CREAT | O_APPEND, 0644);
+    if (fd >= 0) { write_fd_all(fd, line.data(), line.size()); close(fd); }
+}
+
+// cold start: bulk-load every still-valid object of the PV into HBM (cuFile/GDS when available)
+void pv_reload(Server& S) {
+    FILE* f = fopen((S.opt.pv_dir + "/index.tsv").c_str(), "r");
+    if (!f) return;
+    char line[4096];
+    uint64_t n_ok = 0, bytes = 0, n_bad = 0;
+    const time_t now = time(nullptr);
+    const auto t0 = std::chrono::steady_clock::now();
+    while (fgets(line, sizeof line, f)) {
+        std::vector<std::string> col;
+        char* save = nullptr;
+        std::string l(line);
+        if (!l.empty() && l.back() == '\n') l.pop_back();
+        size_t pos = 0;
+        for (;;) {
+            const size_t t = l.find('\t', pos);
+            col.push_back(l.substr(pos, t == std::string::npos ? std::string::npos : t - pos));
+            if (t == std::string::npos) break;
+            pos = t + 1;
+        }
+        (void)save;
+        if (col.size() != 9 || col[0].size() != 32) continue;
+        auto e = std::make_shared<Entry>();
+        for (int i = 0; i < 16; ++i) e->key128[i] = (uint8_t)strtoul(col[0].substr(2 * i, 2).c_str(), nullptr, 16);
+        e->meta.stored_length = strtoull(col[1].c_str(), nullptr, 10);
+        e->meta.raw_length = atoll(col[2].c_str());
+        e->crc32c = (uint32_t)strtoul(col[3].c_str(), nullptr, 16);
+        e->stored_at = (time_t)atoll(col[4].c_str());
+        e->meta.content_type = col[5];
+        if (col[6] != "\x01") e->meta.etag = col[6];
+        e->meta.stored_gzip = col[7] == "1";
+        if (col[8] != "\x01") e->meta.last_modified = col[8];
+        if (now - e->stored_at > S.opt.valid_s) continue;                       // expired: refetch on demand
+        Key16 k;
+        memcpy(k.b, e->key128, 16);
+        { std::lock_guard<std::mutex> g(S.mu); if (S.index.count(k)) continue; }   // a later line for the same key wins only if first is gone
+        const int fd = open((S.opt.pv_dir + "/" + col[0]).c_str(), O_RDONLY);
+        if (fd < 0) continue;
+        nz_put* put = nullptr;
+        bool ok = nz_put_begin(S.ctx, e->key128, e->meta.stored_length, e->meta.stored_length, e->meta.stored_gzip ? NZ_ENC_GZIP : NZ_ENC_IDENTITY, 0, &put) == NZ_OK;
+        if (ok) {
+            ok = nz_put_file(put, fd, 0, 0, e->meta.stored_length) == NZ_OK;
+            uint32_t crc = 0;
+            if (ok) ok = nz_put_commit(put, e->crc32c, 1, &crc) == NZ_OK;          // the PV copy must still match its CRC-32C
+            else nz_put_abort(put);
+        }
+        close(fd);
+        if (!ok) { ++n_bad; continue; }
+        e->last_access = now;
+        { std::lock_guard<std::mutex> g(S.mu); S.index[k] = e; }
+        ++n_ok; bytes += e->meta.stored_length;
+    }
+    fclose(f);
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    nz_stats st;
+    nz_get_stats(S.ctx, &st);
+    fprintf(stderr, "nzproxy: reloaded %llu objects (%.2f GiB) from %s in %.2f s (%.2f GB/s; cuFile %.2f GiB, bounce %.2f GiB), %llu rejected\n",
+            (unsigned long long)n_ok, bytes / 1073741824.0, S.opt.pv_dir.c_str(), dt, dt > 0 ? bytes / dt / 1e9 : 0.0,
+            st.file_cufile_bytes / 1073741824.0, st.file_bounce_bytes / 1073741824.0, (unsigned long long)n_bad);
+}
+
+// drop one object everywhere (device extent, host index, PV file)
+void drop_entry(Server& S, const std::shared_ptr<Entry>& e) {
+    Key16 k;
+    memcpy(k.b, e->key128, 16);
+    { std::lock_guard<std::mutex> g(S.mu); auto it = S.index.find(k); if (it != S.index.end() && it->second == e) S.index.erase(it); }
+    nz_evict(S.ctx, e->key128);
+    if (!S.opt.pv_dir.empty()) {
+        char hx[33];
+        for (int i = 0; i < 16; ++i) snprintf(hx + 2 * i, 3, "%02x", e->key128[i]);
+        unlink((S.opt.pv_dir + "/" + hx).c_str());
+    }
+}
+
+// cache manager: `inactive` purge every minute; also called with need_room when the arena is full (LRU)
+void cache_manager_pass(Server& S, bool need_room) {
+    std::vector<std::shared_ptr<Entry>> victims;
+    const time_t now = time(nullptr);
+    {
+        std::lock_guard<std::mutex> g(S.mu);
+        std::shared_ptr<Entry> oldest;
+        for (auto& kv : S.index) {
+            const std::shared_ptr<Entry>& e = kv.second;
+            if (e->inflight.load() > 0) continue;
+            if (now - e->last_access.load() > S.opt.inactive_s) victims.push_back(e);
+            else if (need_room && (!oldest || e->last_access.load() < oldest->last_access.load())) oldest = e;
+        }
+        if (need_room && victims.empty() && oldest) victims.push_back(oldest);
+    }
+    for (auto& e : victims) drop_entry(S, e);
+}
+
 // returns HTTP status to relay (200 = admitted and indexed); fills `out` on 200
 int fill_from_origin(Server& S, int vhost, const std::string& host, const std::string& target, const std::string& client_ip,
                      const uint8_t key128[16], std::shared_ptr<Entry>& out) {
@@ -251,6 +378,8 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
     nzh::ObjectMeta meta;
     int64_t clen = -1;
     bool cacheable = status == 200;
+    bool have_crc = false;
+    uint32_t want_crc = 0;
     size_t pos = head.find("\r\n") + 2;
     while (pos < head.size()) {
         const size_t e = head.find("\r\n", pos);
@@ -265,6 +394,21 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
         else if (name == "etag") meta.etag = val;
         else if (name == "last-modified") meta.last_modified = val;
         else if (name == "content-encoding") { if (lower(val) == "gzip") meta.stored_gzip = true; else cacheable = false; }
+        else if (name == "x-goog-hash") {                                         // GCS: crc32c=<base64 of the big-endian u32>
+            const size_t c32 = val.find("crc32c=");
+            if (c32 != std::string::npos && val.size() >= c32 + 7 + 8) {
+                static const std::string tb = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+                uint32_t acc = 0;
+                int nb = 0;
+                for (size_t i = c32 + 7; i < val.size() && nb < 6; ++i) {
+                    const size_t v = tb.find(val[i]);
+                    if (v == std::string::npos) break;
+                    acc = (acc << 6) | (uint32_t)v;
+                    ++nb;
+                }
+                if (nb == 6) { want_crc = acc >> 4; have_crc = true; }             // 36 bits read, 32 are data
+            }
+        }
         else if (name == "set-cookie") cacheable = false;                         // nginx: not cached
         else if (name == "vary" && val == "*") cacheable = false;
         else if (name == "cache-control") { const std::string v = lower(val); if (v.find("no-cache") != std::string::npos || v.find("no-store") != std::string::npos || v.find("private") != std::string::npos) cacheable = false; }
@@ -272,7 +416,12 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
     if (!cacheable || clen < 0) { close(fd); return status == 200 ? 502 : status; }   // uncached relays are not implemented: fail open to the client as 502
     // stream the body into the arena through a pinned window
     nz_put* put = nullptr;
-    if (nz_put_begin(S.ctx, key128, (uint64_t)clen, (uint64_t)clen, meta.stored_gzip ? NZ_ENC_GZIP : NZ_ENC_IDENTITY, 0, &put) != NZ_OK) {
+    int32_t prc = NZ_ENOMEM;
+    for (int attempt = 0; attempt < 64 && prc == NZ_ENOMEM; ++attempt) {     // arena full: evict least recently used, retry
+        prc = nz_put_begin(S.ctx, key128, (uint64_t)clen, (uint64_t)clen, meta.stored_gzip ? NZ_ENC_GZIP : NZ_ENC_IDENTITY, 0, &put);
+        if (prc == NZ_ENOMEM) cache_manager_pass(S, true);
+    }
+    if (prc != NZ_OK) {
         close(fd);
         return 502;
     }
@@ -285,6 +434,15 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
     char* wp = static_cast<char*>(nz_buf_ptr(win));
     uint64_t off = 0;
     bool ok = true;
+    int pv_fd = -1;
+    std::string pv_tmp, pv_final;
+    if (!S.opt.pv_dir.empty()) {                       // write-through to the durable tier (temp file -> rename, like nginx)
+        char hx[33];
+        for (int i = 0; i < 16; ++i) snprintf(hx + 2 * i, 3, "%02x", key128[i]);
+        pv_final = S.opt.pv_dir + "/" + hx;
+        pv_tmp = pv_final + ".part";
+        pv_fd = open(pv_tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    }
     size_t have = std::min<size_t>(rest.size(), (size_t)clen);
     if (have) memcpy(wp, rest.data(), have);
     while (ok && off < (uint64_t)clen) {
@@ -294,6 +452,7 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
             have += (size_t)r;
         }
         if (!ok) break;
+        if (pv_fd >= 0 && !write_fd_all(pv_fd, wp, have)) { close(pv_fd); unlink(pv_tmp.c_str()); pv_fd = -1; }
         if (nz_put_write(put, wp, off, have) != NZ_OK) { ok = false; break; }
         if (nz_put_sync(put) != NZ_OK) { ok = false; break; }   // the window is reused: its H2D copy must have left it
         off += have;
@@ -304,9 +463,12 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
         std::lock_guard<std::mutex> g(S.win_mu);
         S.free_windows.push_back(win);
     }
-    if (!ok) { nz_put_abort(put); return 502; }
+    if (!ok) { nz_put_abort(put); if (pv_fd >= 0) { close(pv_fd); unlink(pv_tmp.c_str()); } return 502; }
     uint32_t crc = 0;
-    if (nz_put_commit(put, 0, 0, &crc) != NZ_OK) return 502;
+    if (nz_put_commit(put, want_crc, have_crc ? 1 : 0, &crc) != NZ_OK) {          // NZ_ECORRUPT: origin's CRC-32C does not match
+        if (pv_fd >= 0) { close(pv_fd); unlink(pv_tmp.c_str()); }
+        return 502;
+    }
     meta.stored_length = (uint64_t)clen;
     meta.raw_length = -1;
     if (meta.stored_gzip) {   // learn the inflated length from a lookup of the ISIZE trailer is host work: read last 4 bytes
@@ -335,6 +497,12 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
     e->meta = meta;
     memcpy(e->key128, key128, 16);
     e->stored_at = time(nullptr);
+    e->last_access = e->stored_at;
+    e->crc32c = crc;
+    if (pv_fd >= 0) {
+        close(pv_fd);
+        if (rename(pv_tmp.c_str(), pv_final.c_str()) == 0) pv_index_append(S, *e);
+    }
     {
         std::lock_guard<std::mutex> g(S.mu);
         Key16 k;
@@ -541,7 +709,10 @@ void serve_connection(Server* Sp, int fd, std::string client_ip) {
                     auto it = S.index.find(k);
                     if (it != S.index.end()) ent = it->second;
                 }
-                if (ent && time(nullptr) - ent->stored_at > 86400) ent.reset();   // proxy_cache_valid 200 1d: expired -> refetch
+                if (ent && time(nullptr) - ent->stored_at > S.opt.valid_s) {       // proxy_cache_valid 200 1d: expired -> refetch
+                    if (ent->inflight.load() == 0) drop_entry(S, ent);
+                    ent.reset();
+                }
                 int st = 200;
                 if (!ent) {
                     S.misses++;
@@ -562,6 +733,8 @@ void serve_connection(Server* Sp, int fd, std::string client_ip) {
                 if (!ent) {
                     stock(st == 200 ? 502 : st);
                 } else {
+                    ent->last_access = time(nullptr);
+                    ent->inflight++;
                     nzh::Config cfg = S.cfg;
                     cfg.gunzip = S.opt.gunzip;
                     plan = nzh::plan_response(cfg, pr.rq, ent->meta, S.boundary.fetch_add(1));
@@ -569,7 +742,9 @@ void serve_connection(Server* Sp, int fd, std::string client_ip) {
             }
         }
         if (pr.ok && pr.rq.http_minor < 1) keep = false;
-        if (!send_plan(S, fd, plan, ent.get(), keep, win)) break;
+        const bool sent = send_plan(S, fd, plan, ent.get(), keep, win);
+        if (ent) ent->inflight--;
+        if (!sent) break;
         if (!keep) break;
     }
     {
@@ -584,7 +759,7 @@ void serve_connection(Server* Sp, int fd, std::string client_ip) {
 void usage() {
     fprintf(stderr,
             "nzproxy [--listen ip:port] [--device N] [--arena-gib G] [--max-objects N] [--window-mib M] [--first-window-kib K]\n"
-            "        [--max-conns N] [--gunzip] [--verify] [--upstream proxy_host=ip:port]...\n");
+            "        [--max-conns N] [--gunzip] [--verify] [--upstream proxy_host=ip:port]... [--pv DIR] [--inactive-s S] [--valid-s S]\n");
 }
 
 }  // namespace
@@ -607,6 +782,9 @@ int main(int argc, char** argv) {
         else if (a == "--first-window-kib") S.opt.first_window = (uint64_t)atoll(next()) << 10;
         else if (a == "--max-conns") S.opt.max_conns = atoi(next());
         else if (a == "--gunzip") S.opt.gunzip = true;
+        else if (a == "--pv") S.opt.pv_dir = next();
+        else if (a == "--inactive-s") S.opt.inactive_s = atoi(next());
+        else if (a == "--valid-s") S.opt.valid_s = atoi(next());
         else if (a == "--verify") S.opt.verify = true;
         else if (a == "--upstream") {
             const std::string v = next();
@@ -632,6 +810,8 @@ int main(int argc, char** argv) {
         if (nz_buf_alloc(S.ctx, S.opt.window_bytes, NZ_BUF_PINNED_HOST, &b) != NZ_OK) break;
         S.free_windows.push_back(b);
     }
+    if (!S.opt.pv_dir.empty()) pv_reload(S);
+    std::thread([&S] { for (;;) { std::this_thread::sleep_for(std::chrono::seconds(S.opt.inactive_s < 120 ? 1 : 60)); cache_manager_pass(S, false); } }).detach();
     g_urgent.ctx = S.ctx; g_urgent.cap_bytes = 16ull << 20; g_urgent.linger_us = 0; g_urgent.spin_us = 2000;
     g_bulk.ctx = S.ctx; g_bulk.cap_bytes = 128ull << 20; g_bulk.linger_us = 20;
     std::thread([] { g_urgent.run(); }).detach();

@@ -203,3 +203,137 @@ def test_origin_404_is_not_cached(servers):
     s1, _, _ = fetch(gpu, "GET", "yann.lecun.com", "/nope", {})
     s2, _, _ = fetch(gpu, "GET", "yann.lecun.com", "/nope", {})
     assert s1 == 404 and s2 == 404 and Origin.hits.get("/nope") == 2      # proxy_cache_valid 200 only
+
+
+# ---- fill-side policy: integrity header, durable tier, cache manager ----
+def _start_proxy(port, origin_port, extra):
+    ups = []
+    for h in ("www.cs.toronto.edu", "yann.lecun.com", "storage.googleapis.com", "images.cocodataset.org"):
+        ups += ["--upstream", f"{h}=127.0.0.1:{origin_port}"]
+    p = subprocess.Popen([os.path.join(ROOT, "nezha_b200", "_build", "nzproxy"), "--listen", f"127.0.0.1:{port}", "--max-conns", "16",
+                          "--window-mib", "1"] + ups + extra, start_new_session=True, stderr=subprocess.PIPE)
+    wait_port(port, 120)
+    return p
+
+
+def _stop(p):
+    try:
+        os.killpg(p.pid, signal.SIGTERM)
+    except ProcessLookupError:
+        pass
+    p.wait(timeout=20)
+
+
+class PolicyOrigin(http.server.BaseHTTPRequestHandler):
+    protocol_version = "HTTP/1.0"
+    hits = {}
+    objects = {}      # path -> (bytes, extra headers)
+
+    def do_GET(self):
+        path = self.path.split("?")[0]
+        PolicyOrigin.hits[path] = PolicyOrigin.hits.get(path, 0) + 1
+        ent = PolicyOrigin.objects.get(path)
+        if not ent:
+            self.send_response(404); self.send_header("Content-Length", "0"); self.end_headers(); return
+        data, extra = ent
+        self.send_response(200)
+        self.send_header("Content-Type", "application/octet-stream")
+        self.send_header("Content-Length", str(len(data)))
+        self.send_header("ETag", '"%s"' % hashlib.md5(data).hexdigest())
+        for k, v in extra.items():
+            self.send_header(k, v)
+        self.end_headers()
+        self.wfile.write(data)
+
+    def log_message(self, *a):
+        pass
+
+
+@pytest.fixture(scope="module")
+def policy_origin():
+    port = free_port()
+    httpd = http.server.ThreadingHTTPServer(("127.0.0.1", port), PolicyOrigin)
+    threading.Thread(target=httpd.serve_forever, daemon=True).start()
+    yield port
+    httpd.shutdown()
+
+
+def test_gcs_crc32c_header_is_verified_on_fill(policy_origin):
+    good = wl.synth_bytes(1_234_567, 70).tobytes()
+    bad = wl.synth_bytes(200_000, 71).tobytes()
+    PolicyOrigin.objects["/b/good"] = (good, {"x-goog-hash": "crc32c=" + o.crc32c_header(o.crc32c(good))})
+    PolicyOrigin.objects["/b/bad"] = (bad, {"x-goog-hash": "crc32c=" + o.crc32c_header(o.crc32c(bad) ^ 0x10) + ",md5=AAAA"})
+    port = free_port()
+    p = _start_proxy(port, policy_origin, ["--arena-gib", "0.5"])
+    try:
+        for _ in range(2):
+            s, _, b = fetch(port, "GET", "storage.googleapis.com", "/b/good", {})
+            assert s == 200 and b == good
+        assert PolicyOrigin.hits["/b/good"] == 1
+        s1, _, _ = fetch(port, "GET", "storage.googleapis.com", "/b/bad", {})
+        s2, _, _ = fetch(port, "GET", "storage.googleapis.com", "/b/bad", {})
+        assert s1 == 502 and s2 == 502 and PolicyOrigin.hits["/b/bad"] == 2      # never admitted (NZ_ECORRUPT at commit)
+    finally:
+        _stop(p)
+
+
+def test_pv_write_through_and_cold_start(policy_origin, tmp_path):
+    pv = tmp_path / "pv"
+    pv.mkdir()
+    objs = {f"/pv/obj{i}": wl.synth_bytes(2_000_000 + 333 * i, 80 + i).tobytes() for i in range(4)}
+    for k, v in objs.items():
+        PolicyOrigin.objects[k] = (v, {"Last-Modified": LM})
+    port = free_port()
+    p = _start_proxy(port, policy_origin, ["--arena-gib", "0.5", "--pv", str(pv)])
+    try:
+        for k, v in objs.items():
+            s, _, b = fetch(port, "GET", "yann.lecun.com", k, {})
+            assert s == 200 and b == v
+    finally:
+        _stop(p)
+    files = sorted(os.listdir(pv))
+    assert "index.tsv" in files and len([f for f in files if len(f) == 32]) == 4 and not [f for f in files if f.endswith(".part")]
+    before = dict(PolicyOrigin.hits)
+    port2 = free_port()
+    p2 = _start_proxy(port2, 1, ["--arena-gib", "0.5", "--pv", str(pv)])          # origin unreachable on purpose (port 1)
+    try:
+        for k, v in objs.items():
+            s, hd, b = fetch(port2, "GET", "yann.lecun.com", k, {"Range": "bytes=1000-1999999"})
+            assert s == 206 and b == v[1000:2000000] and hd.get("last-modified") == LM
+        assert PolicyOrigin.hits == before                                         # served from the reloaded PV copy
+        s, _, _ = fetch(port2, "GET", "yann.lecun.com", "/pv/never-seen", {})
+        assert s == 502
+    finally:
+        _stop(p2)
+    # a corrupted PV file is rejected at reload (CRC-32C recorded at fill)
+    victim = [f for f in files if len(f) == 32][0]
+    raw = bytearray((pv / victim).read_bytes()); raw[1000] ^= 1; (pv / victim).write_bytes(bytes(raw))
+    port3 = free_port()
+    p3 = _start_proxy(port3, 1, ["--arena-gib", "0.5", "--pv", str(pv)])
+    try:
+        codes = sorted(fetch(port3, "GET", "yann.lecun.com", k, {})[0] for k in objs)
+        assert codes == [200, 200, 200, 502]
+    finally:
+        _stop(p3)
+
+
+def test_inactive_purge_and_lru_under_pressure(policy_origin):
+    objs = {f"/lru/obj{i}": wl.synth_bytes(24 << 20, 90 + i).tobytes() for i in range(5)}     # 5 x 24 MiB into a 64 MiB arena
+    for k, v in objs.items():
+        PolicyOrigin.objects[k] = (v, {})
+    port = free_port()
+    p = _start_proxy(port, policy_origin, ["--arena-gib", "0.0625", "--inactive-s", "3"])
+    try:
+        for k, v in objs.items():
+            s, _, b = fetch(port, "GET", "www.cs.toronto.edu", k, {})
+            assert s == 200 and hashlib.sha256(b).digest() == hashlib.sha256(v).digest()    # the arena holds 2: older ones were evicted to make room
+        last = "/lru/obj4"
+        s, _, b = fetch(port, "GET", "www.cs.toronto.edu", last, {"Range": "bytes=0-9"})
+        assert s == 206 and b == objs[last][:10] and PolicyOrigin.hits[last] == 1          # most recent one is still cached
+        s, _, _ = fetch(port, "GET", "www.cs.toronto.edu", "/lru/obj0", {"Range": "bytes=0-9"})
+        assert PolicyOrigin.hits["/lru/obj0"] == 2                                          # the oldest was evicted and refetched
+        time.sleep(6)                                                                       # inactive=3 s: everything idles out
+        s, _, _ = fetch(port, "GET", "www.cs.toronto.edu", last, {"Range": "bytes=0-9"})
+        assert s == 206 and PolicyOrigin.hits[last] == 2
+    finally:
+        _stop(p)
