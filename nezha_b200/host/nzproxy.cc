@@ -398,15 +398,15 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
             const size_t c32 = val.find("crc32c=");
             if (c32 != std::string::npos && val.size() >= c32 + 7 + 8) {
                 static const std::string tb = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
-                uint32_t acc = 0;
+                uint64_t acc = 0;
                 int nb = 0;
                 for (size_t i = c32 + 7; i < val.size() && nb < 6; ++i) {
                     const size_t v = tb.find(val[i]);
                     if (v == std::string::npos) break;
-                    acc = (acc << 6) | (uint32_t)v;
+                    acc = (acc << 6) | (uint64_t)v;
                     ++nb;
                 }
-                if (nb == 6) { want_crc = acc >> 4; have_crc = true; }             // 36 bits read, 32 are data
+                if (nb == 6) { want_crc = (uint32_t)(acc >> 4); have_crc = true; }             // 36 bits read, 32 are data
             }
         }
         else if (name == "set-cookie") cacheable = false;                         // nginx: not cached
