@@ -69,7 +69,7 @@ struct Entry {
     uint8_t key128[16];
     time_t stored_at;
     uint32_t crc32c = 0;
-    std::atomic<time_t> last_access{0};    // inactive=60m bookkeeping (nginx.conf:38)
+    std::atomic<int64_t> last_access{0};   // monotonic ms; inactive=60m bookkeeping (nginx.conf:38)
     std::atomic<int> inflight{0};          // responses currently streaming this object
 };
 
@@ -224,6 +224,8 @@ int connect_to(const std::string& hostport, int default_port) {
     return fd;
 }
 
+int64_t now_ms() { return std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 bool write_fd_all(int fd, const void* p, size_t n) {
     const char* c = static_cast<const char*>(p);
     while (n) {
@@ -299,7 +301,7 @@ void pv_reload(Server& S) {
         }
         close(fd);
         if (!ok) { ++n_bad; continue; }
-        e->last_access = now;
+        e->last_access = now_ms();
         { std::lock_guard<std::mutex> g(S.mu); S.index[k] = e; }
         ++n_ok; bytes += e->meta.stored_length;
     }
@@ -328,14 +330,14 @@ void drop_entry(Server& S, const std::shared_ptr<Entry>& e) {
 // cache manager: `inactive` purge every minute; also called with need_room when the arena is full (LRU)
 void cache_manager_pass(Server& S, bool need_room) {
     std::vector<std::shared_ptr<Entry>> victims;
-    const time_t now = time(nullptr);
+    const int64_t now = now_ms();
     {
         std::lock_guard<std::mutex> g(S.mu);
         std::shared_ptr<Entry> oldest;
         for (auto& kv : S.index) {
             const std::shared_ptr<Entry>& e = kv.second;
             if (e->inflight.load() > 0) continue;
-            if (now - e->last_access.load() > S.opt.inactive_s) victims.push_back(e);
+            if (now - e->last_access.load() > (int64_t)S.opt.inactive_s * 1000) victims.push_back(e);
             else if (need_room && (!oldest || e->last_access.load() < oldest->last_access.load())) oldest = e;
         }
         if (need_room && victims.empty() && oldest) victims.push_back(oldest);
@@ -497,7 +499,7 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
     e->meta = meta;
     memcpy(e->key128, key128, 16);
     e->stored_at = time(nullptr);
-    e->last_access = e->stored_at;
+    e->last_access = now_ms();
     e->crc32c = crc;
     if (pv_fd >= 0) {
         close(pv_fd);
@@ -733,7 +735,7 @@ void serve_connection(Server* Sp, int fd, std::string client_ip) {
                 if (!ent) {
                     stock(st == 200 ? 502 : st);
                 } else {
-                    ent->last_access = time(nullptr);
+                    ent->last_access = now_ms();
                     ent->inflight++;
                     nzh::Config cfg = S.cfg;
                     cfg.gunzip = S.opt.gunzip;
