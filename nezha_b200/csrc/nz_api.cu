@@ -797,7 +797,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     if (t->profiled) CKT(cudaEventRecord(t->ev_g0, s));
     int ggrid = c->gather_grid;
     if (tile_bound && tile_bound < (uint64_t)ggrid) ggrid = (int)tile_bound;   // small waves: no more CTAs than tiles
-    if (all_host && !cuda_stream && ggrid > c->host_grid) ggrid = c->host_grid;  // PCIe-bound wave: a few SMs saturate the link
+    if (all_host && ggrid > c->host_grid) ggrid = c->host_grid;  // PCIe-bound wave: a few SMs saturate the link
     CKT(nz_launch_gather(c->gather_variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s));
     if (t->profiled) CKT(cudaEventRecord(t->ev_g1, s));
     c->launches += 1;
