@@ -310,6 +310,18 @@ def run_ours(args):
     ms_step = ms / args.steps
     value = payload_all / (ms_step * 1e-3) / 1e9
     hbm, which = peaks()
+    # context for write-dominated waves: what a pure fill reaches on this GPU right now
+    wbuf = torch.empty(1 << 31, dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        wbuf.zero_()
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record(stream)
+    for _ in range(5):
+        wbuf.zero_()
+    w1.record(stream)
+    w1.synchronize()
+    write_peak = 5 * (1 << 31) / (w0.elapsed_time(w1) * 1e-3) / 1e9
+    del wbuf
     g_ms = sum(gather_ms) / len(gather_ms)
     coalesce = os.environ.get("NZ_COALESCE", "1") != "0"
     # algorithmic bytes of one launch: every payload byte is written once; the source is read once per
@@ -327,7 +339,17 @@ def run_ours(args):
                 "accounting": ("source read once per distinct slice (request coalescing) + every payload byte written" if coalesce
                                else "2 x payload (read + write per request)"),
                 "uncoalesced_equivalent_gbs": 2.0 * payload / (g_ms * 1e-3) / 1e9,
+                "write_only_fill_gbs": write_peak, "read_bytes": read_bytes, "write_bytes": payload,
                 "kernel_share_of_step": g_ms / (ms / args.steps) if world == 1 else None}
+
+    try:
+        with open(os.path.join(ROOT, "profiles", "k_gather_traffic.json")) as f:
+            tr = json.load(f)
+        if tr.get("request_coalescing") == coalesce and tr.get("payload_bytes") == payload:
+            roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            roofline["traffic_source"] = tr.get("source")
+    except Exception:
+        pass
 
     # ---- e2e: through the C ABI into pinned host windows ----------------------
     e2e = None
