@@ -452,6 +452,10 @@ template <int HINT>
 __device__ __forceinline__ void stg_s(void* p, const uint4& v) {
     if constexpr (HINT == 2)
         asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else if constexpr (HINT == 3)
+        asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else if constexpr (HINT == 4)
+        asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
     else
         asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -733,6 +737,10 @@ static const GatherVariant kGatherVariants[] = {
     {256, 8, 2, 2},   // 7: + st.global.cs
     {512, 4, 2, 1},   // 8
     {256, 16, 1, 0},  // 9: 64 KiB tiles, deep unroll
+    {256, 8, 2, 3},   // 10: plain st.global
+    {256, 8, 2, 4},   // 11: st.global.cg
+    {256, 4, 6, 3},   // 12: plain stores, 6 CTAs/SM
+    {512, 8, 1, 3},   // 13: plain stores, 64 KiB tiles
 };
 constexpr int kNumGatherVariants = (int)(sizeof(kGatherVariants) / sizeof(kGatherVariants[0]));
 
@@ -765,6 +773,10 @@ static int occ_gather_t() {
     case 7: return F<256, 8, 2, 2>(__VA_ARGS__);                  \
     case 8: return F<512, 4, 2, 1>(__VA_ARGS__);                  \
     case 9: return F<256, 16, 1, 0>(__VA_ARGS__);                 \
+    case 10: return F<256, 8, 2, 3>(__VA_ARGS__);                 \
+    case 11: return F<256, 8, 2, 4>(__VA_ARGS__);                 \
+    case 12: return F<256, 4, 6, 3>(__VA_ARGS__);                 \
+    case 13: return F<512, 8, 1, 3>(__VA_ARGS__);                 \
     default: return F<256, 8, 2, 0>(__VA_ARGS__);                 \
     }
 
