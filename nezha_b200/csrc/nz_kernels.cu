@@ -724,6 +724,94 @@ cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s) {
     }
     return e;
 }
+// ---------------------------------------------------------------------------
+// K2 with TMA staging (variant 14).  A tile whose source, destinations and length are all
+// 16 B aligned is moved by the bulk-copy engine instead of through registers:
+//   cp.async.bulk  global -> shared   (one 32 KiB tile, completion on an mbarrier)
+//   cp.async.bulk  shared -> global   once per destination of the coalesced group
+// so a tile read once from HBM is written to every member with large contiguous bulk
+// stores and almost no instructions.  Two shared buffers per CTA alternate: the load of
+// tile i+1 is in flight while the stores of tile i drain.  Tiles that do not qualify (byte
+// ranges, tails) take the register path of copy_tile.  One elected thread drives the engine.
+// ---------------------------------------------------------------------------
+constexpr int NZ_TMA_THREADS = 128;
+constexpr uint32_t NZ_TMA_TILE = 32768;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(NZ_TMA_THREADS, 3)
+k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_begin, const uint32_t* __restrict__ chain_head,
+             const uint32_t* __restrict__ chain_next, uint32_t nseg) {
+    extern __shared__ __align__(128) uint8_t s_buf[];          // 2 x NZ_TMA_TILE
+    __shared__ __align__(8) uint64_t s_bar[2];
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s_bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s_bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    __syncthreads();
+    const uint64_t total = tile_begin[nseg];
+    TileCursor c;
+    DstChain dc;
+    dc.work = work;
+    dc.next = chain_next;
+    dc.head = 0xFFFFFFFFu;
+    uint32_t phase[2] = {0, 0};
+    uint32_t slot = 0;
+    for (uint64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const uint32_t before = c.seg;
+        const bool fresh = !(tile >= c.lo_t && tile < c.hi_t);
+        c.seek(tile, work, tile_begin, nseg);
+        if (fresh || before != c.seg) dc.head = __ldg(chain_head + c.seg);
+        int64_t lo, hi;
+        c.span(tile, NZ_TMA_TILE, lo, hi);
+        const uint8_t* s = reinterpret_cast<const uint8_t*>(c.src) + lo;
+        uint8_t* d = reinterpret_cast<uint8_t*>(c.dst) + lo;
+        const uint32_t n = (uint32_t)(hi - lo);
+        const uint32_t bulk = n & ~15u;                        // bytes the engine moves; the (<16 B) tail goes by hand
+        const bool engine = bulk >= 2048 && ((((uintptr_t)s) | ((uintptr_t)d)) & 15u) == 0;
+        if (!engine) {
+            dc.d0 = d;
+            dc.lo = lo;
+            copy_tile<NZ_TMA_THREADS, 8, 0>(s, dc, n);
+            continue;
+        }
+        if (tid == 0) {
+            const uint32_t buf = smem_u32(s_buf + slot * NZ_TMA_TILE), bar = smem_u32(&s_bar[slot]);
+            // the stores that last read this buffer (two tiles ago) must have finished reading it
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bulk) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(buf), "l"(s), "r"(bulk), "r"(bar) : "memory");
+            // wait for the tile to land
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(bar), "r"(phase[slot]) : "memory");
+            }
+            phase[slot] ^= 1u;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(d), "r"(buf), "r"(bulk) : "memory");
+            for (uint32_t m = dc.head; m != 0xFFFFFFFFu; m = __ldg(chain_next + m)) {
+                uint8_t* dm = reinterpret_cast<uint8_t*>(__ldg(&work[m].dst)) + lo;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dm), "r"(buf), "r"(bulk) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        slot ^= 1u;
+        // tail bytes of a slice's last tile (every member)
+        const uint32_t tail = n - bulk;
+        if (tid < tail) {
+            const uint8_t b = s[bulk + tid];
+            d[bulk + tid] = b;
+            for (uint32_t m = dc.head; m != 0xFFFFFFFFu; m = __ldg(chain_next + m))
+                (reinterpret_cast<uint8_t*>(__ldg(&work[m].dst)) + lo)[bulk + tid] = b;
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // gather variants: {threads, vectors in flight per thread, CTAs per SM, cache hints}; tile = threads * U * 16 B
 struct GatherVariant { int nt, u, minb, hint; };
 static const GatherVariant kGatherVariants[] = {
@@ -741,6 +829,7 @@ static const GatherVariant kGatherVariants[] = {
     {256, 8, 2, 4},   // 11: st.global.cg
     {256, 4, 6, 3},   // 12: plain stores, 6 CTAs/SM
     {512, 8, 1, 3},   // 13: plain stores, 64 KiB tiles
+    {128, 16, 3, 0},  // 14: TMA bulk-copy staging (k_gather_tma); nt*u*16 = 32 KiB tile
 };
 constexpr int kNumGatherVariants = (int)(sizeof(kGatherVariants) / sizeof(kGatherVariants[0]));
 
@@ -782,9 +871,24 @@ static int occ_gather_t() {
 
 cudaError_t nz_launch_gather(int variant, const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head,
                              const uint32_t* chain_next, uint32_t nseg, int grid, cudaStream_t s) {
+    if (variant == 14) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_gather_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * NZ_TMA_TILE);
+            attr_set = true;
+        }
+        k_gather_tma<<<grid, NZ_TMA_THREADS, 2 * NZ_TMA_TILE, s>>>(work, tile_begin, chain_head, chain_next, nseg);
+        return cudaGetLastError();
+    }
     NZ_GV_SWITCH(variant, launch_gather_t, work, tile_begin, chain_head, chain_next, nseg, grid, s)
 }
 int nz_gather_blocks_per_sm(int variant) {
+    if (variant == 14) {
+        int nb = 0;
+        cudaFuncSetAttribute(k_gather_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * NZ_TMA_TILE);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather_tma, NZ_TMA_THREADS, 2 * NZ_TMA_TILE) != cudaSuccess || nb < 1) nb = 3;
+        return nb;
+    }
     NZ_GV_SWITCH(variant, occ_gather_t)
 }
 cudaError_t nz_launch_verify(const NzVerWork* ver, const uint32_t* counters, NzDevRes* res, const uint32_t* crc_tables,

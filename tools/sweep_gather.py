@@ -9,7 +9,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 steps = sys.argv[1] if len(sys.argv) > 1 else "20"
 rows = []
-for v in range(14):
+for v in (int(x) for x in os.environ.get('NZ_SWEEP', ','.join(map(str, range(15)))).split(',')):
     env = dict(os.environ, NZ_GATHER_VARIANT=str(v))
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", steps, "--warmup", "3", "--no-e2e", "--no-cpu", "--no-http"],
                        env=env, capture_output=True, text=True)
