@@ -13,6 +13,7 @@
 // range filter.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "nz_internal.h"
 #include "nz_crc.cuh"
@@ -735,19 +736,24 @@ cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s) {
 // ranges, tails) take the register path of copy_tile.  One elected thread drives the engine.
 // ---------------------------------------------------------------------------
 constexpr int NZ_TMA_THREADS = 128;
-constexpr uint32_t NZ_TMA_TILE = 32768;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(NZ_TMA_THREADS, 3)
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+
+// STAGES shared buffers of tile_bytes each.  The load of tile i is issued before the stores of
+// tile i-1, so a tile's HBM read overlaps the previous tile's writes inside one CTA.
+template <int STAGES>
+__global__ void __launch_bounds__(NZ_TMA_THREADS)
 k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_begin, const uint32_t* __restrict__ chain_head,
-             const uint32_t* __restrict__ chain_next, uint32_t nseg) {
-    extern __shared__ __align__(128) uint8_t s_buf[];          // 2 x NZ_TMA_TILE
-    __shared__ __align__(8) uint64_t s_bar[2];
+             const uint32_t* __restrict__ chain_next, uint32_t nseg, uint32_t tile_bytes) {
+    extern __shared__ __align__(128) uint8_t s_buf[];          // STAGES x tile_bytes
+    __shared__ __align__(8) uint64_t s_bar[STAGES];
     const uint32_t tid = threadIdx.x;
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s_bar[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s_bar[1])));
+#pragma unroll
+        for (int i = 0; i < STAGES; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s_bar[i])));
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     __syncthreads();
@@ -757,15 +763,37 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
     dc.work = work;
     dc.next = chain_next;
     dc.head = 0xFFFFFFFFu;
-    uint32_t phase[2] = {0, 0};
+    uint32_t phase_bits = 0;                                   // bit s = parity to wait for on stage s
     uint32_t slot = 0;
+    // the engine tile whose load is in flight and whose stores are still to be issued (thread 0 only)
+    bool p_valid = false;
+    uint32_t p_slot = 0, p_bulk = 0, p_head = 0xFFFFFFFFu;
+    uint8_t* p_d = nullptr;
+    int64_t p_lo = 0;
+    auto flush = [&]() {                                       // thread 0: wait for the pending tile, fan it out
+        const uint32_t buf = smem_u32(s_buf + (size_t)p_slot * tile_bytes), bar = smem_u32(&s_bar[p_slot]);
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar), "r"((phase_bits >> p_slot) & 1u) : "memory");
+        }
+        phase_bits ^= 1u << p_slot;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(p_d), "r"(buf), "r"(p_bulk) : "memory");
+        for (uint32_t m = p_head; m != 0xFFFFFFFFu; m = __ldg(chain_next + m)) {
+            uint8_t* dm = reinterpret_cast<uint8_t*>(__ldg(&work[m].dst)) + p_lo;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dm), "r"(buf), "r"(p_bulk) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        p_valid = false;
+    };
     for (uint64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const uint32_t before = c.seg;
         const bool fresh = !(tile >= c.lo_t && tile < c.hi_t);
         c.seek(tile, work, tile_begin, nseg);
         if (fresh || before != c.seg) dc.head = __ldg(chain_head + c.seg);
         int64_t lo, hi;
-        c.span(tile, NZ_TMA_TILE, lo, hi);
+        c.span(tile, tile_bytes, lo, hi);
         const uint8_t* s = reinterpret_cast<const uint8_t*>(c.src) + lo;
         uint8_t* d = reinterpret_cast<uint8_t*>(c.dst) + lo;
         const uint32_t n = (uint32_t)(hi - lo);
@@ -778,38 +806,68 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
             continue;
         }
         if (tid == 0) {
-            const uint32_t buf = smem_u32(s_buf + slot * NZ_TMA_TILE), bar = smem_u32(&s_bar[slot]);
-            // the stores that last read this buffer (two tiles ago) must have finished reading it
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            const uint32_t buf = smem_u32(s_buf + (size_t)slot * tile_bytes), bar = smem_u32(&s_bar[slot]);
+            // stage `slot` was last read by the stores of the engine tile STAGES back; the store groups still
+            // allowed in flight are those of the tiles between (the immediately previous tile is not committed yet)
+            bulk_wait_read<(STAGES >= 2 ? STAGES - 2 : 0)>();
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bulk) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          :: "r"(buf), "l"(s), "r"(bulk), "r"(bar) : "memory");
-            // wait for the tile to land
-            uint32_t done = 0;
-            while (!done) {
-                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                             : "=r"(done) : "r"(bar), "r"(phase[slot]) : "memory");
-            }
-            phase[slot] ^= 1u;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(d), "r"(buf), "r"(bulk) : "memory");
-            for (uint32_t m = dc.head; m != 0xFFFFFFFFu; m = __ldg(chain_next + m)) {
-                uint8_t* dm = reinterpret_cast<uint8_t*>(__ldg(&work[m].dst)) + lo;
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dm), "r"(buf), "r"(bulk) : "memory");
-            }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (p_valid) flush();                              // previous tile: its load had a whole tile of time to land
+            p_valid = true; p_slot = slot; p_bulk = bulk; p_head = dc.head; p_d = d; p_lo = lo;
         }
-        slot ^= 1u;
+        slot = slot + 1 == STAGES ? 0 : slot + 1;
         // tail bytes of a slice's last tile (every member)
         const uint32_t tail = n - bulk;
         if (tid < tail) {
-            const uint8_t b = s[bulk + tid];
-            d[bulk + tid] = b;
+            const uint8_t b8 = s[bulk + tid];
+            d[bulk + tid] = b8;
             for (uint32_t m = dc.head; m != 0xFFFFFFFFu; m = __ldg(chain_next + m))
-                (reinterpret_cast<uint8_t*>(__ldg(&work[m].dst)) + lo)[bulk + tid] = b;
+                (reinterpret_cast<uint8_t*>(__ldg(&work[m].dst)) + lo)[bulk + tid] = b8;
         }
     }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (tid == 0) {
+        if (p_valid) flush();
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
+struct TmaCfg { int stages; uint32_t tile; };
+static TmaCfg tma_cfg() {
+    static TmaCfg c = [] {
+        TmaCfg t{3, 32768};
+        if (const char* e = getenv("NZ_TMA_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 4) t.stages = v; }
+        if (const char* e = getenv("NZ_TMA_TILE_KB")) { const int v = atoi(e); if (v == 16 || v == 32 || v == 64) t.tile = (uint32_t)v << 10; }
+        return t;
+    }();
+    return c;
+}
+template <int STAGES>
+static cudaError_t launch_tma(const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head, const uint32_t* chain_next,
+                              uint32_t nseg, int grid, cudaStream_t s, int* occ) {
+    const TmaCfg t = tma_cfg();
+    const size_t smem = (size_t)STAGES * t.tile;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_gather_tma<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    if (occ) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather_tma<STAGES>, NZ_TMA_THREADS, smem) != cudaSuccess || nb < 1) nb = 1;
+        *occ = nb;
+        return cudaSuccess;
+    }
+    k_gather_tma<STAGES><<<grid, NZ_TMA_THREADS, smem, s>>>(work, tile_begin, chain_head, chain_next, nseg, t.tile);
+    return cudaGetLastError();
+}
+static cudaError_t dispatch_tma(const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head, const uint32_t* chain_next,
+                                uint32_t nseg, int grid, cudaStream_t s, int* occ) {
+    switch (tma_cfg().stages) {
+    case 2: return launch_tma<2>(work, tile_begin, chain_head, chain_next, nseg, grid, s, occ);
+    case 4: return launch_tma<4>(work, tile_begin, chain_head, chain_next, nseg, grid, s, occ);
+    default: return launch_tma<3>(work, tile_begin, chain_head, chain_next, nseg, grid, s, occ);
+    }
 }
 
 // gather variants: {threads, vectors in flight per thread, CTAs per SM, cache hints}; tile = threads * U * 16 B
@@ -835,6 +893,7 @@ constexpr int kNumGatherVariants = (int)(sizeof(kGatherVariants) / sizeof(kGathe
 
 int nz_gather_num_variants() { return kNumGatherVariants; }
 uint32_t nz_gather_tile_bytes(int v) {
+    if (v == 14) return tma_cfg().tile;
     if (v < 0 || v >= kNumGatherVariants) v = 0;
     return (uint32_t)(kGatherVariants[v].nt * kGatherVariants[v].u * 16);
 }
@@ -871,22 +930,13 @@ static int occ_gather_t() {
 
 cudaError_t nz_launch_gather(int variant, const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head,
                              const uint32_t* chain_next, uint32_t nseg, int grid, cudaStream_t s) {
-    if (variant == 14) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(k_gather_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * NZ_TMA_TILE);
-            attr_set = true;
-        }
-        k_gather_tma<<<grid, NZ_TMA_THREADS, 2 * NZ_TMA_TILE, s>>>(work, tile_begin, chain_head, chain_next, nseg);
-        return cudaGetLastError();
-    }
+    if (variant == 14) return dispatch_tma(work, tile_begin, chain_head, chain_next, nseg, grid, s, nullptr);
     NZ_GV_SWITCH(variant, launch_gather_t, work, tile_begin, chain_head, chain_next, nseg, grid, s)
 }
 int nz_gather_blocks_per_sm(int variant) {
     if (variant == 14) {
-        int nb = 0;
-        cudaFuncSetAttribute(k_gather_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * NZ_TMA_TILE);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather_tma, NZ_TMA_THREADS, 2 * NZ_TMA_TILE) != cudaSuccess || nb < 1) nb = 3;
+        int nb = 1;
+        dispatch_tma(nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, &nb);
         return nb;
     }
     NZ_GV_SWITCH(variant, occ_gather_t)
