@@ -744,7 +744,7 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 
 // STAGES shared buffers of tile_bytes each.  The load of tile i is issued before the stores of
 // tile i-1, so a tile's HBM read overlaps the previous tile's writes inside one CTA.
-template <int STAGES>
+template <int STAGES, bool AHEAD>
 __global__ void __launch_bounds__(NZ_TMA_THREADS)
 k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_begin, const uint32_t* __restrict__ chain_head,
              const uint32_t* __restrict__ chain_next, uint32_t nseg, uint32_t tile_bytes) {
@@ -809,12 +809,18 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
             const uint32_t buf = smem_u32(s_buf + (size_t)slot * tile_bytes), bar = smem_u32(&s_bar[slot]);
             // stage `slot` was last read by the stores of the engine tile STAGES back; the store groups still
             // allowed in flight are those of the tiles between (the immediately previous tile is not committed yet)
-            bulk_wait_read<(STAGES >= 2 ? STAGES - 2 : 0)>();
+            if constexpr (AHEAD) bulk_wait_read<(STAGES >= 2 ? STAGES - 2 : 0)>();
+            else bulk_wait_read<STAGES - 1>();                 // every earlier tile's stores are committed here
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bulk) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          :: "r"(buf), "l"(s), "r"(bulk), "r"(bar) : "memory");
-            if (p_valid) flush();                              // previous tile: its load had a whole tile of time to land
-            p_valid = true; p_slot = slot; p_bulk = bulk; p_head = dc.head; p_d = d; p_lo = lo;
+            if constexpr (AHEAD) {
+                if (p_valid) flush();                          // previous tile: its load had a whole tile of time to land
+                p_valid = true; p_slot = slot; p_bulk = bulk; p_head = dc.head; p_d = d; p_lo = lo;
+            } else {                                           // other CTAs on the SM cover this tile's load latency
+                p_slot = slot; p_bulk = bulk; p_head = dc.head; p_d = d; p_lo = lo;
+                flush();
+            }
         }
         slot = slot + 1 == STAGES ? 0 : slot + 1;
         // tail bytes of a slice's last tile (every member)
@@ -832,41 +838,51 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
     }
 }
 
-struct TmaCfg { int stages; uint32_t tile; };
+struct TmaCfg { int stages; uint32_t tile; bool ahead; };
 static TmaCfg tma_cfg() {
     static TmaCfg c = [] {
-        TmaCfg t{3, 32768};
+        TmaCfg t{2, 32768, false};
+        if (const char* e = getenv("NZ_TMA_AHEAD")) t.ahead = atoi(e) != 0;
         if (const char* e = getenv("NZ_TMA_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 4) t.stages = v; }
         if (const char* e = getenv("NZ_TMA_TILE_KB")) { const int v = atoi(e); if (v == 16 || v == 32 || v == 64) t.tile = (uint32_t)v << 10; }
+        while ((size_t)t.stages * t.tile > (200u << 10)) --t.stages;     // stay inside one SM's shared memory
         return t;
     }();
     return c;
 }
-template <int STAGES>
+template <int STAGES, bool AHEAD>
 static cudaError_t launch_tma(const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head, const uint32_t* chain_next,
                               uint32_t nseg, int grid, cudaStream_t s, int* occ) {
     const TmaCfg t = tma_cfg();
     const size_t smem = (size_t)STAGES * t.tile;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_gather_tma<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_gather_tma<STAGES, AHEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
     if (occ) {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather_tma<STAGES>, NZ_TMA_THREADS, smem) != cudaSuccess || nb < 1) nb = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather_tma<STAGES, AHEAD>, NZ_TMA_THREADS, smem) != cudaSuccess || nb < 1) nb = 1;
         *occ = nb;
         return cudaSuccess;
     }
-    k_gather_tma<STAGES><<<grid, NZ_TMA_THREADS, smem, s>>>(work, tile_begin, chain_head, chain_next, nseg, t.tile);
+    k_gather_tma<STAGES, AHEAD><<<grid, NZ_TMA_THREADS, smem, s>>>(work, tile_begin, chain_head, chain_next, nseg, t.tile);
     return cudaGetLastError();
 }
 static cudaError_t dispatch_tma(const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head, const uint32_t* chain_next,
                                 uint32_t nseg, int grid, cudaStream_t s, int* occ) {
-    switch (tma_cfg().stages) {
-    case 2: return launch_tma<2>(work, tile_begin, chain_head, chain_next, nseg, grid, s, occ);
-    case 4: return launch_tma<4>(work, tile_begin, chain_head, chain_next, nseg, grid, s, occ);
-    default: return launch_tma<3>(work, tile_begin, chain_head, chain_next, nseg, grid, s, occ);
+    const TmaCfg t = tma_cfg();
+    if (t.ahead) {
+        switch (t.stages) {
+        case 2: return launch_tma<2, true>(work, tile_begin, chain_head, chain_next, nseg, grid, s, occ);
+        case 4: return launch_tma<4, true>(work, tile_begin, chain_head, chain_next, nseg, grid, s, occ);
+        default: return launch_tma<3, true>(work, tile_begin, chain_head, chain_next, nseg, grid, s, occ);
+        }
+    }
+    switch (t.stages) {
+    case 3: return launch_tma<3, false>(work, tile_begin, chain_head, chain_next, nseg, grid, s, occ);
+    case 4: return launch_tma<4, false>(work, tile_begin, chain_head, chain_next, nseg, grid, s, occ);
+    default: return launch_tma<2, false>(work, tile_begin, chain_head, chain_next, nseg, grid, s, occ);
     }
 }
 

@@ -3,9 +3,9 @@
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for coal in ("1", "0"):
-    for st in ("2", "3", "4"):
-        for tk in ("16", "32", "64"):
-            env = dict(os.environ, NZ_GATHER_VARIANT="14", NZ_TMA_STAGES=st, NZ_TMA_TILE_KB=tk, NZ_COALESCE=coal)
+    for st, tk, ah in [("2", "32", "0"), ("2", "16", "0"), ("2", "64", "0"), ("3", "16", "0"), ("3", "32", "0"), ("4", "16", "0"), ("1", "32", "0")]:
+        if True:
+            env = dict(os.environ, NZ_GATHER_VARIANT="14", NZ_TMA_STAGES=st, NZ_TMA_TILE_KB=tk, NZ_COALESCE=coal, NZ_TMA_AHEAD=ah)
             r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "10", "--warmup", "3", "--no-e2e", "--no-cpu", "--no-http"],
                                env=env, capture_output=True, text=True)
             line = [l for l in r.stdout.splitlines() if l.startswith("{")]
