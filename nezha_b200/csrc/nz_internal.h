@@ -162,7 +162,7 @@ struct nz_ctx {
     int gather_grid;       // persistent grid size for k_gather
     bool profile = false;   // record per-kernel CUDA events in every wave (nz_set_profiling / env NZ_PROFILE=1)
     bool coalesce = true;   // env NZ_COALESCE=0 turns request coalescing off (A/B measurements)
-    int gather_variant = 0; // index into the k_gather variant table (env NZ_GATHER_VARIANT for sweeps)
+    int gather_variant = 14; // k_gather variant: 14 = TMA bulk-copy staging (default, measured best); 0-13 register paths (env NZ_GATHER_VARIANT)
     int inflate_grid;
     uint8_t* arena = nullptr;
     uint64_t arena_bytes = 0;
