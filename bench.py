@@ -311,7 +311,7 @@ def run_ours(args):
     value = payload_all / (ms_step * 1e-3) / 1e9
     hbm, which = peaks()
     # context for write-dominated waves: what a pure fill reaches on this GPU right now
-    wbuf = torch.empty(1 << 31, dtype=torch.uint8, device="cuda")
+    wbuf = torch.empty(1 << 29, dtype=torch.int32, device="cuda")      # 2 GiB, filled as 32-bit words
     for _ in range(2):
         wbuf.zero_()
     w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
