@@ -29,10 +29,11 @@ constexpr int LL_BITS = 10;           // primary literal/length table: 1024 x u3
 constexpr int DS_BITS = 8;            // primary distance table: 256 x u32
 
 // Table entries carry everything the hot loop needs (no side tables):
-//   literal/length: [3:0] code length (0 = not in the primary table -> canonical slow path)
-//                   [5:4] kind 0 literal, 1 length, 2 end-of-block, 3 invalid symbol
-//                   [10:8] extra bits, [24:16] literal byte or length base
-//   distance:       [3:0] code length, [7:4] extra bits, [22:8] base, [31] invalid symbol
+//   both:           [7:0] bits to drop = code length + extra bits (0 = not in the primary table ->
+//                   canonical slow path), [11:8] code length (the extra bits sit right above it)
+//   literal/length: [13:12] kind 0 literal, 1 length, 2 end-of-block, 3 invalid symbol,
+//                   [24:16] literal byte or length base
+//   distance:       [30:16] base, [31] invalid symbol
 struct __align__(16) WarpTabs {
     uint32_t ll[1 << LL_BITS];
     uint32_t ds[1 << DS_BITS];
@@ -50,14 +51,21 @@ __constant__ uint8_t  c_dext[30]  = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6
 __constant__ uint8_t  c_clorder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 __device__ __forceinline__ uint32_t ll_entry(int sym, int len) {
-    if (sym < 256) return ((uint32_t)sym << 16) | (uint32_t)len;
-    if (sym == 256) return (2u << 4) | (uint32_t)len;
-    if (sym >= 286) return (3u << 4) | (uint32_t)len;
-    return ((uint32_t)c_lbase[sym - 257] << 16) | ((uint32_t)c_lext[sym - 257] << 8) | (1u << 4) | (uint32_t)len;
+    const uint32_t l = (uint32_t)len;
+    if (sym < 256) return ((uint32_t)sym << 16) | (l << 8) | l;
+    if (sym == 256) return (2u << 12) | (l << 8) | l;
+    if (sym >= 286) return (3u << 12) | (l << 8) | l;
+    return ((uint32_t)c_lbase[sym - 257] << 16) | (1u << 12) | (l << 8) | (l + c_lext[sym - 257]);
 }
 __device__ __forceinline__ uint32_t ds_entry(int sym, int len) {
-    if (sym >= 30) return 0x80000000u | (uint32_t)len;
-    return ((uint32_t)c_dbase[sym] << 8) | ((uint32_t)c_dext[sym] << 4) | (uint32_t)len;
+    const uint32_t l = (uint32_t)len;
+    if (sym >= 30) return 0x80000000u | (l << 8) | l;
+    return ((uint32_t)c_dbase[sym] << 16) | (l << 8) | (l + c_dext[sym]);
+}
+__device__ __forceinline__ uint32_t bfe32(uint32_t v, uint32_t pos, uint32_t len) {
+    uint32_t r;
+    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(v), "r"(pos), "r"(len));
+    return r;
 }
 
 // ---------------------------------------------------------------------------
@@ -323,15 +331,18 @@ __device__ int64_t inflate_member(const uint8_t* __restrict__ src, uint64_t n, u
         // ---- symbol loop ----
         for (;;) {
             if (!br_refill(b)) return -1;
-            uint32_t e = T.ll[br_peek(b, LL_BITS)];
+            uint32_t w = (uint32_t)b.buf;
+            uint32_t e = T.ll[w & ((1u << LL_BITS) - 1u)];
             if (e == 0) {
                 int l;
                 const int sym = slow_decode(b, T.ll_cnt, T.ll_sym, &l);
                 if (sym < 0) return -1;
                 e = ll_entry(sym, l);
             }
-            br_drop(b, e & 15u);
-            const uint32_t kind = (e >> 4) & 3u;
+            const uint32_t tot = e & 0xffu;
+            b.buf >>= tot;
+            b.cnt -= tot;
+            const uint32_t kind = (e >> 12) & 3u;
             if (kind == 0) {                              // literal
                 if (p >= cap) return -1;
                 if (lane == 0) out[p] = (uint8_t)(e >> 16);
@@ -342,34 +353,38 @@ __device__ int64_t inflate_member(const uint8_t* __restrict__ src, uint64_t n, u
                 if (kind == 2) break;                     // end of block
                 return -1;                                // symbols 286/287
             }
-            const uint32_t mlen = (e >> 16) + br_get(b, (e >> 8) & 7u);
+            const uint32_t cl = (e >> 8) & 15u;
+            const uint32_t mlen = (e >> 16) + bfe32(w, cl, tot - cl);
             if (!br_refill(b)) return -1;
-            e = T.ds[br_peek(b, DS_BITS)];
+            w = (uint32_t)b.buf;
+            e = T.ds[w & ((1u << DS_BITS) - 1u)];
             if (e == 0) {
                 int l;
                 const int dsym = slow_decode(b, T.ds_cnt, T.ds_sym, &l);
                 if (dsym < 0) return -1;
                 e = ds_entry(dsym, l);
             }
-            if (e & 0x80000000u) return -1;               // distance symbols 30/31
-            br_drop(b, e & 15u);
-            const uint32_t dist = ((e >> 8) & 0x7FFFu) + br_get(b, (e >> 4) & 15u);
-            if (dist > p) return -1;                      // "invalid distance too far back"
-            if (mlen > cap - p) return -1;
+            const uint32_t dtot = e & 0xffu, dcl = (e >> 8) & 15u;
+            const uint32_t dist = ((e >> 16) & 0x7FFFu) + bfe32(w, dcl, dtot - dcl);
+            b.buf >>= dtot;
+            b.cnt -= dtot;
+            // distance symbols 30/31, "invalid distance too far back", output overrun: one cold exit
+            if ((e >> 31) | (uint32_t)(dist > p) | (uint32_t)(mlen > cap - p)) return -1;
             // ---- LZ77 copy: the window is the output itself (L1/L2) ----
             __syncwarp();                                 // orders lane 0's literal stores / earlier copies
-            const uint8_t* s0 = out + (p - dist);
-            uint8_t* d0 = out + p;
-            if (dist >= mlen) {                           // no overlap: lanes independent
-                for (uint32_t k = lane; k < mlen; k += 32) d0[k] = s0[k];
+            uint8_t* dl = out + (p + (uint32_t)lane);
+            const uint8_t* sl = dl - dist;
+            if (dist >= mlen) {                           // no overlap: lanes independent; most matches fit one pass
+                if ((uint32_t)lane < mlen) *dl = *sl;
+                for (uint32_t k = (uint32_t)lane + 32; k < mlen; k += 32) dl[k - lane] = sl[k - lane];
             } else if (dist >= 32) {                      // overlap, period >= warp: 32-byte steps in order
                 for (uint32_t k0 = 0; k0 < mlen; k0 += 32) {
-                    const uint32_t k = k0 + lane;
-                    if (k < mlen) d0[k] = s0[k];
+                    if (k0 + (uint32_t)lane < mlen) dl[k0] = sl[k0];
                     __syncwarp();
                 }
             } else {                                      // short period: every source byte precedes p
-                for (uint32_t k = lane; k < mlen; k += 32) d0[k] = s0[k % dist];
+                const uint8_t* s0 = out + (p - dist);
+                for (uint32_t k = lane; k < mlen; k += 32) out[p + k] = s0[k % dist];
             }
             p += mlen;
         }
