@@ -867,7 +867,7 @@ def main():
     ap.add_argument("--c4-gib-per-gpu", type=float, default=16.0)
     ap.add_argument("--c4-inflight", type=int, default=256)
     ap.add_argument("--c3-objects", type=int, default=10_000)
-    ap.add_argument("--c3-wave", type=int, default=2048)
+    ap.add_argument("--c3-wave", type=int, default=8192)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

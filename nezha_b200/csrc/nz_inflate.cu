@@ -236,6 +236,10 @@ __device__ int64_t inflate_member(const uint8_t* __restrict__ src, uint64_t n, u
     const uint64_t bit_end = 8ull * (n - 8);             // deflate data may not reach into the trailer
     uint32_t p = 0;                                      // bytes produced
     bool last = false;
+    bool pend = false;                                   // a deferred short copy (see the symbol loop)
+    uint8_t pend_val = 0;
+    uint8_t* pend_dst = nullptr;
+    uint32_t pend_len = 0;
     while (!last) {
         if (!br_refill(b)) return -1;
         if (br_bitpos(b) + 3 > bit_end) return -1;
@@ -371,12 +375,21 @@ __device__ int64_t inflate_member(const uint8_t* __restrict__ src, uint64_t n, u
             // distance symbols 30/31, "invalid distance too far back", output overrun: one cold exit
             if ((e >> 31) | (uint32_t)(dist > p) | (uint32_t)(mlen > cap - p)) return -1;
             // ---- LZ77 copy: the window is the output itself (L1/L2) ----
+            // A window read costs an L2 round trip.  For the common short, non-overlapping match the load is
+            // issued now and its store is deferred until the next match (or the block end): the next symbols
+            // decode while the bytes are in flight.  Literals never need the pending bytes; a later copy might,
+            // so the pending store is retired before any new window read.
+            if (pend) { if ((uint32_t)lane < pend_len) *pend_dst = pend_val; pend = false; }
             __syncwarp();                                 // orders lane 0's literal stores / earlier copies
             uint8_t* dl = out + (p + (uint32_t)lane);
             const uint8_t* sl = dl - dist;
-            if (dist >= mlen) {                           // no overlap: lanes independent; most matches fit one pass
-                if ((uint32_t)lane < mlen) *dl = *sl;
-                for (uint32_t k = (uint32_t)lane + 32; k < mlen; k += 32) dl[k - lane] = sl[k - lane];
+            if (dist >= mlen && mlen <= 32) {
+                pend_val = (uint32_t)lane < mlen ? *sl : (uint8_t)0;
+                pend_dst = dl;
+                pend_len = mlen;
+                pend = true;
+            } else if (dist >= mlen) {                    // no overlap: lanes independent
+                for (uint32_t k = (uint32_t)lane; k < mlen; k += 32) dl[k - lane] = sl[k - lane];
             } else if (dist >= 32) {                      // overlap, period >= warp: 32-byte steps in order
                 for (uint32_t k0 = 0; k0 < mlen; k0 += 32) {
                     if (k0 + (uint32_t)lane < mlen) dl[k0] = sl[k0];
@@ -388,6 +401,8 @@ __device__ int64_t inflate_member(const uint8_t* __restrict__ src, uint64_t n, u
             }
             p += mlen;
         }
+        if (pend) { if ((uint32_t)lane < pend_len) *pend_dst = pend_val; pend = false; }
+        __syncwarp();
         if (br_bitpos(b) > bit_end) return -1;
     }
     // ---- RFC 1952 trailer ----
