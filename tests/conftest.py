@@ -10,6 +10,13 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real CUDA device (run under gpurun)")
+    # the suites drive built artefacts (libnezha_gpu.so, libnezha_host.so, nzproxy, the oracle):
+    # build them once if a fresh checkout has none (nvcc cross-compiles without a GPU)
+    need = [os.path.join(ROOT, "nezha_b200", "_build", n) for n in ("libnezha_gpu.so", "libnezha_host.so", "nzproxy", "nzwebhook", "nzload")]
+    need += [os.path.join(ROOT, "oracle", "_build", n) for n in ("libnz_oracle.so", "nz_cpu_server")]
+    if not all(os.path.exists(p) for p in need):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 def _has_gpu():
