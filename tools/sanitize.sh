@@ -9,4 +9,4 @@ timeout 1200 compute-sanitizer --tool memcheck --leak-check no --error-exitcode 
 echo "memcheck rc=$?" >> gpurun_out/sanitizer_memcheck_inflate.log
 timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "test_coalesced_identical_gets or test_crc32c_device_kernel_K3" > gpurun_out/sanitizer_racecheck.log 2>&1
 echo "racecheck rc=$?" >> gpurun_out/sanitizer_racecheck.log
-tail -4 gpurun_out/sanitizer_memcheck.log gpurun_out/sanitizer_memcheck_inflate.log gpurun_out/sanitizer_racecheck.log
+for f in gpurun_out/sanitizer_*.log; do tail -n 4 "$f"; done
