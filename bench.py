@@ -851,6 +851,119 @@ def run_c4(args):
     return 0
 
 
+# --------------------------------------------------------------------------- #
+# C5: cold fill from files on the PV (cuFile/GDS, else pinned bounce), then a hit sweep 1 MiB .. 1 GiB
+# --------------------------------------------------------------------------- #
+def run_c5(args):
+    import shutil
+    import tempfile
+
+    import numpy as np
+    import torch
+
+    import nezha_b200 as nz
+    from nezha_b200 import capi, workloads as wl
+
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    bind_to_gpu_numa_node(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    plan = [(1, 64), (4, 64), (16, 32), (64, 16), (256, 4), (1024, 2)]          # (MiB, objects) per size class
+    pv = tempfile.mkdtemp(prefix=f"nezha_pv_r{rank}_", dir=args.pv_dir)
+    zone = None
+    try:
+        files = []
+        t0 = time.perf_counter()
+        for mib, cnt in plan:
+            for j in range(cnt):
+                n = mib << 20
+                k = wl.key128(wl.object_key_string(f"c5-r{rank}-{mib}", j))
+                path = os.path.join(pv, k.hex())
+                with open(path, "wb") as f:
+                    f.write(memoryview(wl.synth_bytes(n, seed=5_000 + 100 * mib + j)))
+                files.append((mib, k, path, n))
+        write_s = time.perf_counter() - t0
+        total = sum(f[3] for f in files)
+        zone = nz.Zone(device=local, arena_bytes=total + (512 << 20), max_objects=4096, shard_index=0, shard_count=1)
+        zone.set_profiling(True)
+        # ---- cold fill: PV -> HBM ----
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for mib, k, path, n in files:
+            fd = os.open(path, os.O_RDONLY)
+            try:
+                zone.put_file(k, fd, n)
+            finally:
+                os.close(fd)
+        fill_s = time.perf_counter() - t0
+        st = zone.stats()
+        # ---- hit sweep ----
+        stream = torch.cuda.Stream(device=local)
+        torch.cuda.set_stream(stream)
+        sptr = stream.cuda_stream
+        rng = np.random.default_rng(55 + rank)
+        sweep = []
+        for mib, cnt in plan:
+            n = mib << 20
+            gets_n = 100 if mib <= 256 else 32
+            keys = [f[1] for f in files if f[0] == mib]
+            picks = rng.integers(0, len(keys), gets_n)
+            dbuf = zone.alloc_device(gets_n * n)
+            wave = zone.prepare([nz.Get(keys[int(p)], dbuf, [], 0, j * n) for j, p in enumerate(picks)])
+            for _ in range(3):
+                t = wave.submit(sptr); res = t.wait(); t.free()
+            if any(r.status != capi.NZ_OK for r in res):
+                raise SystemExit("bench.py c5: wave failed")
+            reps = max(3, min(args.steps, 20))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            tk = [wave.submit(sptr) for _ in range(reps)]
+            e1.record(stream)
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            for t in tk:
+                t.wait(); t.free()
+            distinct = len(set(int(p) for p in picks))
+            sweep.append({"object_mib": mib, "gets": gets_n, "distinct_objects": distinct, "ms_per_wave": ms,
+                          "payload_gbs": gets_n * n / (ms * 1e-3) / 1e9,
+                          "hbm_traffic_gbs": (distinct + gets_n) * n / (ms * 1e-3) / 1e9})
+            dbuf.free()
+        fill_gbs = total / fill_s / 1e9
+        if world > 1:
+            tt = torch.tensor([fill_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            fill_gbs = total * world / float(tt.item()) / 1e9
+            for row in sweep:
+                v = torch.tensor([row["payload_gbs"]], device="cuda", dtype=torch.float64)
+                dist.all_reduce(v)
+                row["payload_gbs_all_gpus"] = float(v.item())
+        if rank == 0:
+            big = sweep[-1]
+            line = {
+                "metric": "cached-GET GB/s", "value": big.get("payload_gbs_all_gpus", big["payload_gbs"]), "unit": "GB/s", "n_gpus": world,
+                "steps": args.steps, "warmup": 3, "ms_per_step": big["ms_per_wave"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": "C5: cold fill from files on the PV, then hit sweep 1 MiB..1 GiB (100 GETs per size, 32 for 1 GiB); value = the 1 GiB row",
+                           "pv_dir": args.pv_dir, "bytes_per_gpu": total, "response_buffers": "HBM"},
+                "fill": {"gbs": fill_gbs, "seconds": fill_s, "cufile_bytes": int(st.file_cufile_bytes), "bounce_bytes": int(st.file_bounce_bytes),
+                         "note": "cuFile/GDS is tried first; on a file system without GDS support the bytes go pread -> pinned bounce -> cudaMemcpyAsync",
+                         "file_write_s": write_s},
+                "sweep": sweep, "gpu_launches": 2 * sum(max(3, min(args.steps, 20)) for _ in plan),
+            }
+            print(json.dumps(line), flush=True)
+    finally:
+        if zone is not None:
+            zone.close()
+        shutil.rmtree(pv, ignore_errors=True)
+        if world > 1:
+            dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -863,7 +976,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-http", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--pv-dir", default="/tmp")
     ap.add_argument("--c4-gib-per-gpu", type=float, default=16.0)
     ap.add_argument("--c4-inflight", type=int, default=256)
     ap.add_argument("--c3-objects", type=int, default=10_000)
@@ -875,6 +989,8 @@ def main():
         return run_c3(args)
     if args.workload == "c4":
         return run_c4(args)
+    if args.workload == "c5":
+        return run_c5(args)
     return run_ours(args)
 
 
