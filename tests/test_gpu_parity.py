@@ -364,3 +364,41 @@ def test_coalesced_identical_gets(zone, objects):
     assert b.bytes(0, 100_000) == objects[other][0].tobytes()
     for x in bufs:
         x.free()
+
+
+def test_probe_chains_collisions_and_full_table():
+    """Every key lands on the same table line (crafted key[8:16]): linear probing walks several
+    128 B lines, tombstones are skipped on lookup and reused on insert, and the load limit answers NZ_EFULL."""
+    z = nz.Zone(device=0, arena_bytes=32 << 20, max_objects=32, table_slots=64)     # 16 lines of 4 slots
+    try:
+        def key(i):
+            return bytes([i, 0xAB, 0, 0, 0, 0, 0, 0]) + (0x5555_0000_0000_0003).to_bytes(8, "little")   # same line, distinct key128
+        data = {i: wl.synth_bytes(1000 + i, seed=700 + i) for i in range(32)}
+        for i in range(32):
+            z.put(key(i), data[i])
+        with pytest.raises(nz.NezhaError) as ei:                                     # 32 live in 64 slots: load limit 0.5
+            z.put(key(40), data[0])
+        assert ei.value.code in (capi.NZ_EFULL, capi.NZ_ENOMEM)
+        assert all(e.status == capi.NZ_OK and e.stored_length == 1000 + i for i, e in enumerate(z.lookup([key(i) for i in range(32)])))
+        for i in range(0, 32, 3):                                                    # tombstones inside the chain
+            assert z.evict(key(i)) == capi.NZ_OK
+        ext = z.lookup([key(i) for i in range(32)] + [key(99)])
+        for i in range(32):
+            assert (ext[i].status == capi.NZ_OK) == (i % 3 != 0), i
+        assert ext[32].status == capi.NZ_ENOTFOUND
+        for i in range(0, 32, 3):                                                    # re-insert: tombstones are reused
+            z.put(key(i), data[i])
+        for i in range(32):
+            res, body = z.get(key(i))
+            assert res.status == capi.NZ_OK and body == data[i].tobytes(), i
+        # a wave that mixes all of them with misses
+        bufs = [z.alloc_device(2000) for _ in range(40)]
+        gets = [nz.Get(key(i) if i < 32 else key(100 + i), bufs[i]) for i in range(40)]
+        t = z.submit(gets)
+        res = t.wait()
+        t.free()
+        assert [r.status for r in res] == [capi.NZ_OK] * 32 + [capi.NZ_ENOTFOUND] * 8
+        for b in bufs:
+            b.free()
+    finally:
+        z.close()
