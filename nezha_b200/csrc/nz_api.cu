@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <string>
 #include <thread>
 
 #include "nz_internal.h"
@@ -176,10 +177,7 @@ int32_t nz_shutdown(nz_ctx* c) {
     for (cudaStream_t s : c->streams) cudaStreamDestroy(s);
     for (cudaStream_t s : c->hi_streams) cudaStreamDestroy(s);
     if (c->put_stream) cudaStreamDestroy(c->put_stream);
-    for (int i = 0; i < 2; ++i) {
-        if (c->bounce[i]) cudaFreeHost(c->bounce[i]);
-        if (c->bounce_ev[i]) cudaEventDestroy(c->bounce_ev[i]);
-    }
+    if (c->bounce[0]) cudaFreeHost(c->bounce[0]);
     for (size_t i = 0; i < c->peer_ptrs.size(); ++i)
         if (c->peer_ptrs[i] && i != c->cfg.shard_index) cudaIpcCloseMemHandle(c->peer_ptrs[i]);
     if (c->peer_base_dev) cudaFree(c->peer_base_dev);
@@ -385,31 +383,67 @@ int32_t nz_put_file(nz_put* p, int fd, uint64_t file_off, uint64_t dst_off, uint
     }
     c->file_bounce_bytes += len;
     std::lock_guard<std::mutex> g(c->put_mu);   // bounce buffers are shared
+    // pread -> pinned bounce -> cudaMemcpyAsync.  One reader tops out at the page-cache copy rate
+    // (~10 GB/s), so large reads are split over NZ_BOUNCE_LANES reader threads, each with two pinned
+    // 8 MiB buffers and its own stream: reads and H2D copies of all lanes overlap.
+    constexpr int NZ_BOUNCE_LANES = 4;
+    constexpr size_t BUF = 8u << 20;
     if (!c->bounce[0]) {
-        c->bounce_bytes = 16u << 20;
-        for (int i = 0; i < 2; ++i) {
-            CK(cudaHostAlloc(&c->bounce[i], c->bounce_bytes, cudaHostAllocPortable));
-            CK(cudaEventCreateWithFlags(&c->bounce_ev[i], cudaEventDisableTiming));
-        }
+        c->bounce_bytes = BUF * 2 * NZ_BOUNCE_LANES;
+        CK(cudaHostAlloc(&c->bounce[0], c->bounce_bytes, cudaHostAllocPortable));
+        c->bounce[1] = c->bounce[0];
     }
-    uint64_t done = 0;
-    int which = 0;
-    while (done < len) {
-        const size_t want = (size_t)std::min<uint64_t>(c->bounce_bytes, len - done);
-        CK(cudaEventSynchronize(c->bounce_ev[which]));   // previous H2D out of this buffer finished
-        size_t got = 0;
-        while (got < want) {
-            ssize_t r = pread(fd, (char*)c->bounce[which] + got, want - got, (off_t)(file_off + done + got));
-            if (r < 0) { if (errno == EINTR) continue; snprintf(tl_err, sizeof tl_err, "pread: %s", strerror(errno)); return NZ_EINVAL; }
-            if (r == 0) { snprintf(tl_err, sizeof tl_err, "pread: short file"); return NZ_EINVAL; }
-            got += (size_t)r;
+    const int lanes = len >= (uint64_t)(4 * BUF) ? NZ_BOUNCE_LANES : 1;
+    const uint64_t per = round_up((len + lanes - 1) / lanes, 4096);
+    std::vector<int32_t> rcs(lanes, NZ_OK);
+    std::vector<std::string> errs(lanes);
+    auto lane_fn = [&](int li) {
+        cudaSetDevice(c->device);
+        const uint64_t beg = std::min<uint64_t>(len, per * li), end = std::min<uint64_t>(len, beg + per);
+        if (beg >= end) return;
+        cudaStream_t s = li == 0 ? p->stream : c->streams[(c->rr.fetch_add(1)) % c->streams.size()];
+        cudaEvent_t ev[2];
+        cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+        char* base = (char*)c->bounce[0] + (size_t)li * 2 * BUF;
+        uint64_t done = beg;
+        int which = 0;
+        bool used[2] = {false, false};
+        while (done < end && rcs[li] == NZ_OK) {
+            const size_t want = (size_t)std::min<uint64_t>(BUF, end - done);
+            if (used[which] && cudaEventSynchronize(ev[which]) != cudaSuccess) { rcs[li] = NZ_ECUDA; break; }
+            size_t got = 0;
+            while (got < want) {
+                ssize_t r = pread(fd, base + which * BUF + got, want - got, (off_t)(file_off + done + got));
+                if (r < 0) { if (errno == EINTR) continue; rcs[li] = NZ_EINVAL; errs[li] = std::string("pread: ") + strerror(errno); break; }
+                if (r == 0) { rcs[li] = NZ_EINVAL; errs[li] = "pread: short file"; break; }
+                got += (size_t)r;
+            }
+            if (rcs[li] != NZ_OK) break;
+            if (cudaMemcpyAsync(c->arena + p->arena_off + dst_off + done, base + which * BUF, want, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+                cudaEventRecord(ev[which], s) != cudaSuccess) { rcs[li] = NZ_ECUDA; break; }
+            used[which] = true;
+            done += want;
+            which ^= 1;
         }
-        CK(cudaMemcpyAsync(c->arena + p->arena_off + dst_off + done, c->bounce[which], want, cudaMemcpyHostToDevice, p->stream));
-        CK(cudaEventRecord(c->bounce_ev[which], p->stream));
-        done += want;
-        which ^= 1;
+        if (cudaStreamSynchronize(s) != cudaSuccess && rcs[li] == NZ_OK) rcs[li] = NZ_ECUDA;
+        cudaEventDestroy(ev[0]);
+        cudaEventDestroy(ev[1]);
+    };
+    if (lanes == 1) {
+        lane_fn(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int li = 1; li < lanes; ++li) th.emplace_back(lane_fn, li);
+        lane_fn(0);
+        for (auto& t : th) t.join();
     }
-    CK(cudaStreamSynchronize(p->stream));
+    for (int li = 0; li < lanes; ++li)
+        if (rcs[li] != NZ_OK) {
+            snprintf(tl_err, sizeof tl_err, "nz_put_file lane %d: %s", li, errs[li].empty() ? "CUDA error" : errs[li].c_str());
+            cudaGetLastError();
+            return rcs[li];
+        }
     return NZ_OK;
 }
 
