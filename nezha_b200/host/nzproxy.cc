@@ -51,6 +51,7 @@ struct Options {
     std::string listen_ip = "0.0.0.0";
     int port = 80;
     int device = 0;
+    std::vector<int> devices;                      // --devices 0,1,...: one zone per GPU, GETs routed by key hash
     uint64_t arena_bytes = 8ull << 30;
     uint32_t max_objects = 1u << 16;
     uint64_t window_bytes = 4ull << 20;
@@ -84,7 +85,9 @@ struct Key16Hash {
 struct Server {
     Options opt;
     nzh::Config cfg = nzh::Config::reference_default();
-    nz_ctx* ctx = nullptr;
+    nz_ctx* ctx = nullptr;                         // shard 0 (also owns the pinned windows)
+    std::vector<nz_ctx*> ctxs;                      // one per GPU; shard = u64le(key128[0:8]) mod nGPU
+    nz_ctx* zone_of(const uint8_t key128[16]) const { return ctxs[nz_shard_of(key128, (uint32_t)ctxs.size())]; }
     std::mutex mu;
     std::unordered_map<Key16, std::shared_ptr<Entry>, Key16Hash> index;   // headers blob per object (host side)
     std::mutex fill_mu;                                                    // one fill at a time per process (coalesces stampedes)
@@ -292,7 +295,7 @@ void pv_reload(Server& S) {
         const int fd = open((S.opt.pv_dir + "/" + col[0]).c_str(), O_RDONLY);
         if (fd < 0) continue;
         nz_put* put = nullptr;
-        bool ok = nz_put_begin(S.ctx, e->key128, e->meta.stored_length, e->meta.stored_length, e->meta.stored_gzip ? NZ_ENC_GZIP : NZ_ENC_IDENTITY, 0, &put) == NZ_OK;
+        bool ok = nz_put_begin(S.zone_of(e->key128), e->key128, e->meta.stored_length, e->meta.stored_length, e->meta.stored_gzip ? NZ_ENC_GZIP : NZ_ENC_IDENTITY, 0, &put) == NZ_OK;
         if (ok) {
             ok = nz_put_file(put, fd, 0, 0, e->meta.stored_length) == NZ_OK;
             uint32_t crc = 0;
@@ -319,7 +322,7 @@ void drop_entry(Server& S, const std::shared_ptr<Entry>& e) {
     Key16 k;
     memcpy(k.b, e->key128, 16);
     { std::lock_guard<std::mutex> g(S.mu); auto it = S.index.find(k); if (it != S.index.end() && it->second == e) S.index.erase(it); }
-    nz_evict(S.ctx, e->key128);
+    nz_evict(S.zone_of(e->key128), e->key128);
     if (!S.opt.pv_dir.empty()) {
         char hx[33];
         for (int i = 0; i < 16; ++i) snprintf(hx + 2 * i, 3, "%02x", e->key128[i]);
@@ -420,7 +423,7 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
     nz_put* put = nullptr;
     int32_t prc = NZ_ENOMEM;
     for (int attempt = 0; attempt < 64 && prc == NZ_ENOMEM; ++attempt) {     // arena full: evict least recently used, retry
-        prc = nz_put_begin(S.ctx, key128, (uint64_t)clen, (uint64_t)clen, meta.stored_gzip ? NZ_ENC_GZIP : NZ_ENC_IDENTITY, 0, &put);
+        prc = nz_put_begin(S.zone_of(key128), key128, (uint64_t)clen, (uint64_t)clen, meta.stored_gzip ? NZ_ENC_GZIP : NZ_ENC_IDENTITY, 0, &put);
         if (prc == NZ_ENOMEM) cache_manager_pass(S, true);
     }
     if (prc != NZ_OK) {
@@ -484,7 +487,7 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
             rq.nseg = 1; rq.segs = &sg; rq.dst = tb;
             nz_ticket* t = nullptr;
             nz_get_res rs;
-            if (nz_get_submit(S.ctx, &rq, 1, nullptr, &t) == NZ_OK) {
+            if (nz_get_submit(S.zone_of(key128), &rq, 1, nullptr, &t) == NZ_OK) {
                 if (nz_get_wait(t, -1, &rs) == NZ_OK && rs.status == NZ_OK) {
                     uint32_t isz;
                     memcpy(&isz, nz_buf_ptr(tb), 4);
@@ -530,7 +533,9 @@ struct WaveItem {
 };
 
 struct Combiner {
-    nz_ctx* ctx = nullptr;
+    nz_ctx* ctx = nullptr;                         // shard 0 (also owns the pinned windows)
+    std::vector<nz_ctx*> ctxs;                      // one per GPU; shard = u64le(key128[0:8]) mod nGPU
+    nz_ctx* zone_of(const uint8_t key128[16]) const { return ctxs[nz_shard_of(key128, (uint32_t)ctxs.size())]; }
     std::mutex mu;
     std::condition_variable cv;
     std::deque<WaveItem*> q;
@@ -599,7 +604,7 @@ struct Combiner {
     }
 };
 
-static Combiner g_urgent, g_bulk;
+static std::vector<std::unique_ptr<Combiner>> g_urgent, g_bulk;   // one pair of lanes per GPU
 
 // ---- serving -------------------------------------------------------------------
 bool send_plan(Server& S, int fd, const nzh::Plan& plan, const Entry* ent, bool keep_alive, nz_buf* win[2]) {
@@ -634,7 +639,10 @@ bool send_plan(Server& S, int fd, const nzh::Plan& plan, const Entry* ent, bool 
             it.rq.nseg = 1; it.rq.segs = &it.sg; it.rq.dst = win[slot];
             it.rc = NZ_ECUDA;
             it.done.store(0, std::memory_order_relaxed);
-            (first ? g_urgent : g_bulk).push(&it);
+            {
+                const uint32_t sh = nz_shard_of(ent->key128, (uint32_t)S.ctxs.size());
+                (first ? g_urgent[sh] : g_bulk[sh])->push(&it);
+            }
             first = false;
             live[slot] = true;
             off += n;
@@ -760,7 +768,7 @@ void serve_connection(Server* Sp, int fd, std::string client_ip) {
 
 void usage() {
     fprintf(stderr,
-            "nzproxy [--listen ip:port] [--device N] [--arena-gib G] [--max-objects N] [--window-mib M] [--first-window-kib K]\n"
+            "nzproxy [--listen ip:port] [--device N | --devices 0,1,..] [--arena-gib G] [--max-objects N] [--window-mib M] [--first-window-kib K]\n"
             "        [--max-conns N] [--gunzip] [--verify] [--upstream proxy_host=ip:port]... [--pv DIR] [--inactive-s S] [--valid-s S]\n");
 }
 
@@ -778,6 +786,16 @@ int main(int argc, char** argv) {
             if (c == std::string::npos) S.opt.port = atoi(v.c_str());
             else { S.opt.listen_ip = v.substr(0, c); S.opt.port = atoi(v.c_str() + c + 1); }
         } else if (a == "--device") S.opt.device = atoi(next());
+        else if (a == "--devices") {
+            std::string v = next();
+            size_t q = 0;
+            while (q <= v.size()) {
+                size_t c2 = v.find(',', q);
+                if (c2 == std::string::npos) c2 = v.size();
+                if (c2 > q) S.opt.devices.push_back(atoi(v.substr(q, c2 - q).c_str()));
+                q = c2 + 1;
+            }
+        }
         else if (a == "--arena-gib") S.opt.arena_bytes = (uint64_t)(atof(next()) * (1ull << 30));
         else if (a == "--max-objects") S.opt.max_objects = (uint32_t)atoi(next());
         else if (a == "--window-mib") S.opt.window_bytes = (uint64_t)(atof(next()) * (1ull << 20));
@@ -796,17 +814,25 @@ int main(int argc, char** argv) {
         } else { usage(); return 2; }
     }
     if (S.opt.first_window > S.opt.window_bytes) S.opt.first_window = S.opt.window_bytes;
-    nz_config cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.struct_size = sizeof cfg;
-    cfg.device = S.opt.device;
-    cfg.arena_bytes = S.opt.arena_bytes;
-    cfg.max_objects = S.opt.max_objects;
-    int32_t rc = nz_init(&cfg, &S.ctx);
-    if (rc != NZ_OK) {
-        fprintf(stderr, "nzproxy: nz_init failed: %s (%s) - there is no CPU fallback\n", nz_strerror(rc), nz_last_error());
-        return 1;
+    if (S.opt.devices.empty()) S.opt.devices.push_back(S.opt.device);
+    for (size_t i = 0; i < S.opt.devices.size(); ++i) {
+        nz_config cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.struct_size = sizeof cfg;
+        cfg.device = S.opt.devices[i];
+        cfg.arena_bytes = S.opt.arena_bytes;
+        cfg.max_objects = S.opt.max_objects;
+        cfg.shard_index = (uint32_t)i;
+        cfg.shard_count = (uint32_t)S.opt.devices.size();
+        nz_ctx* cx = nullptr;
+        int32_t rc = nz_init(&cfg, &cx);
+        if (rc != NZ_OK) {
+            fprintf(stderr, "nzproxy: nz_init(device %d) failed: %s (%s) - there is no CPU fallback\n", cfg.device, nz_strerror(rc), nz_last_error());
+            return 1;
+        }
+        S.ctxs.push_back(cx);
     }
+    S.ctx = S.ctxs[0];
     for (int i = 0; i < std::min(S.opt.max_conns, 160) * 2; ++i) {   // pinned windows up front: cudaHostAlloc is slow
         nz_buf* b = nullptr;
         if (nz_buf_alloc(S.ctx, S.opt.window_bytes, NZ_BUF_PINNED_HOST, &b) != NZ_OK) break;
@@ -814,13 +840,18 @@ int main(int argc, char** argv) {
     }
     if (!S.opt.pv_dir.empty()) pv_reload(S);
     std::thread([&S] { for (;;) { std::this_thread::sleep_for(std::chrono::seconds(S.opt.inactive_s < 120 ? 1 : 60)); cache_manager_pass(S, false); } }).detach();
-    g_urgent.ctx = S.ctx; g_urgent.cap_bytes = 16ull << 20; g_urgent.linger_us = 0; g_urgent.spin_us = 2000;
-    g_bulk.ctx = S.ctx; g_bulk.cap_bytes = 128ull << 20; g_bulk.linger_us = 20;
-    std::thread([] { g_urgent.run(); }).detach();
-    std::thread([] { g_urgent.run(); }).detach();
-    std::thread([] { g_bulk.run(); }).detach();
-    std::thread([] { g_bulk.run(); }).detach();
-    std::thread([] { g_bulk.run(); }).detach();
+    for (nz_ctx* cx : S.ctxs) {
+        auto u = std::make_unique<Combiner>();
+        u->ctx = cx; u->cap_bytes = 16ull << 20; u->linger_us = 0; u->spin_us = 2000;
+        auto k = std::make_unique<Combiner>();
+        k->ctx = cx; k->cap_bytes = 128ull << 20; k->linger_us = 20;
+        Combiner* up = u.get();
+        Combiner* kp = k.get();
+        g_urgent.push_back(std::move(u));
+        g_bulk.push_back(std::move(k));
+        for (int i = 0; i < 2; ++i) std::thread([up] { up->run(); }).detach();
+        for (int i = 0; i < 3; ++i) std::thread([kp] { kp->run(); }).detach();
+    }
     int ls = socket(AF_INET, SOCK_STREAM, 0);
     int one = 1;
     setsockopt(ls, SOL_SOCKET, SO_REUSEADDR, &one, sizeof one);
@@ -833,8 +864,8 @@ int main(int argc, char** argv) {
         perror("nzproxy: bind/listen");
         return 1;
     }
-    fprintf(stderr, "nzproxy: listening on %s:%d, device %d, arena %.1f GiB, %zu pinned windows of %.1f MiB\n", S.opt.listen_ip.c_str(),
-            S.opt.port, S.opt.device, S.opt.arena_bytes / 1073741824.0, S.free_windows.size(), S.opt.window_bytes / 1048576.0);
+    fprintf(stderr, "nzproxy: listening on %s:%d, %zu GPU shard(s), arena %.1f GiB each, %zu pinned windows of %.1f MiB\n", S.opt.listen_ip.c_str(),
+            S.opt.port, S.ctxs.size(), S.opt.arena_bytes / 1073741824.0, S.free_windows.size(), S.opt.window_bytes / 1048576.0);
     fflush(stderr);
     for (;;) {
         struct sockaddr_in ca;
@@ -850,6 +881,6 @@ int main(int argc, char** argv) {
         inet_ntop(AF_INET, &ca.sin_addr, ip, sizeof ip);
         std::thread(serve_connection, &S, fd, std::string(ip)).detach();
     }
-    nz_shutdown(S.ctx);
+    for (nz_ctx* cx : S.ctxs) nz_shutdown(cx);
     return 0;
 }

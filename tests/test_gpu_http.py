@@ -337,3 +337,27 @@ def test_inactive_purge_and_lru_under_pressure(policy_origin):
         assert s == 206 and PolicyOrigin.hits[last] == 2
     finally:
         _stop(p)
+
+
+def test_front_end_shards_across_two_gpus(policy_origin):
+    """nzproxy --devices 0,1: one zone per GPU, every GET routed to the shard its key hashes to."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    from nezha_b200 import shard
+    objs = {f"/two/obj{i}": wl.synth_bytes(3_000_000 + 17 * i, 120 + i).tobytes() for i in range(12)}
+    owners = set()
+    for k, v in objs.items():
+        PolicyOrigin.objects[k] = (v, {})
+        owners.add(shard.shard_of(o.md5(o.cache_key("images.cocodataset.org", k)), 2))
+    assert owners == {0, 1}                                  # the log really exercises both GPUs
+    port = free_port()
+    p = _start_proxy(port, policy_origin, ["--arena-gib", "0.5", "--devices", "0,1"])
+    try:
+        for rnd in range(2):
+            for k, v in objs.items():
+                s, _, b = fetch(port, "GET", "images.cocodataset.org", k, {"Range": "bytes=100-2999999"} if rnd else {})
+                assert s == (206 if rnd else 200) and b == (v[100:3000000] if rnd else v), k
+        assert all(PolicyOrigin.hits[k] == 1 for k in objs)
+    finally:
+        _stop(p)
