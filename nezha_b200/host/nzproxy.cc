@@ -654,6 +654,7 @@ bool send_plan(Server& S, int fd, const nzh::Plan& plan, const Entry* ent, bool 
             Combiner::wait(&item[cur]);
             live[cur] = false;
             bool ok = item[cur].rc == NZ_OK && item[cur].rs.status == NZ_OK;
+            if (!ok) fprintf(stderr, "nzproxy: window failed: submit/wait rc=%d (%s) status=%d [%s]\n", item[cur].rc, nz_strerror(item[cur].rc), item[cur].rs.status, nz_last_error());
             if (ok && !pending.empty()) { ok = write_all(fd, pending.data(), pending.size()); pending.clear(); }
             if (ok) ok = write_all(fd, nz_buf_ptr(win[cur]), item[cur].sg.len);
             if (!ok) {

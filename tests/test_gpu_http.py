@@ -210,8 +210,9 @@ def _start_proxy(port, origin_port, extra):
     ups = []
     for h in ("www.cs.toronto.edu", "yann.lecun.com", "storage.googleapis.com", "images.cocodataset.org"):
         ups += ["--upstream", f"{h}=127.0.0.1:{origin_port}"]
+    log = open(os.path.join(ROOT, "gpurun_out", f"nzproxy_{port}.log"), "wb") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else subprocess.DEVNULL
     p = subprocess.Popen([os.path.join(ROOT, "nezha_b200", "_build", "nzproxy"), "--listen", f"127.0.0.1:{port}", "--max-conns", "16",
-                          "--window-mib", "1"] + ups + extra, start_new_session=True, stderr=subprocess.PIPE)
+                          "--window-mib", "1"] + ups + extra, start_new_session=True, stderr=log)
     wait_port(port, 120)
     return p
 
