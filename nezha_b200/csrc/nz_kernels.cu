@@ -855,10 +855,12 @@ static cudaError_t launch_tma(const NzSegWork* work, const uint64_t* tile_begin,
                               uint32_t nseg, int grid, cudaStream_t s, int* occ) {
     const TmaCfg t = tma_cfg();
     const size_t smem = (size_t)STAGES * t.tile;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};          // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         cudaFuncSetAttribute(k_gather_tma<STAGES, AHEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     if (occ) {
         int nb = 0;
