@@ -119,6 +119,8 @@ typedef struct nz_stats {
     uint64_t kernel_launches;   /* kernels launched by this library since init     */
     uint64_t file_cufile_bytes; /* nz_put_file bytes that arrived through cuFile/GDS */
     uint64_t file_bounce_bytes; /* ... and through pread + pinned bounce buffers    */
+    uint64_t verify_chunks;       /* 64 KiB chunks checked for NZ_GET_VERIFY (stored-byte GETs) */
+    uint64_t verify_fused_chunks; /* ... of which the gather checksummed from its shared-memory copy (no second HBM read) */
 } nz_stats;
 
 /* ---- lifecycle ----------------------------------------------------------- */

@@ -67,7 +67,8 @@ class GetRes(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "objects", "arena_bytes", "arena_used", "table_slots", "table_live", "gets", "get_bytes", "hits",
-        "misses", "puts", "put_bytes", "evictions", "corrupt", "kernel_launches", "file_cufile_bytes", "file_bounce_bytes")]
+        "misses", "puts", "put_bytes", "evictions", "corrupt", "kernel_launches", "file_cufile_bytes", "file_bounce_bytes",
+        "verify_chunks", "verify_fused_chunks")]
 
 
 class Stripe(C.Structure):

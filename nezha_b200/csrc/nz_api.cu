@@ -113,7 +113,7 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
     CKI(cudaMemset(c->table, 0, lines * 4 * sizeof(NzSlot)));
     CKI(cudaMalloc(&c->descs, (size_t)c->cfg.max_objects * sizeof(NzDesc)));
     CKI(cudaMemset(c->descs, 0, (size_t)c->cfg.max_objects * sizeof(NzDesc)));
-    CKI(cudaMalloc(&c->crc_tables, (16 * 256 + 2 * 1280) * sizeof(uint32_t)));   // slice tables + fast-path tables (nz_crc.cuh)
+    CKI(cudaMalloc(&c->crc_tables, NZ_CRC_TABLE_WORDS * sizeof(uint32_t)));   // slice tables + fast-path tables + fused-verify tables (nz_crc.cuh)
     CKI(nz_upload_constants(c->crc_tables));
     for (int i = 0; i < 8; ++i) {
         cudaStream_t s;
@@ -707,7 +707,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
 
     const size_t pin_reqs = round_up((size_t)n * sizeof(NzDevReq), 256);
     const size_t pin_segs = round_up((size_t)nseg * sizeof(NzDevSeg), 256);
-    const size_t pin_res = round_up((size_t)n * sizeof(NzDevRes), 256);
+    const size_t pin_res = round_up((size_t)n * sizeof(NzDevRes) + 16, 256);     // + {verify chunks, of which fused}
     const size_t dev_work = round_up((size_t)nseg * sizeof(NzSegWork), 256);
     const size_t dev_tiles = round_up((size_t)(nseg + 1) * 8, 256);
     const size_t dev_chain = round_up((size_t)nseg * 8, 256);      // chain_head | chain_next (u32 each)
@@ -716,7 +716,8 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     const size_t dev_infl = (size_t)n * sizeof(NzInflWork);      // followed directly by rq_src, rq_len
     const size_t dev_rq = (size_t)n * 48;                        // rq_src, rq_len, infl_meta, rq_tab, rq_ssz, rq_stat(+pad)
     const size_t dev_stage = round_up((size_t)n * sizeof(NzDevReq), 256) + round_up((size_t)nseg * sizeof(NzDevSeg), 256);
-    nz_ticket* t = ticket_acquire(c, pin_reqs + pin_segs + pin_res, dev_work + dev_tiles + dev_chain + dev_ver + dev_cnt + round_up(dev_infl + dev_rq, 256) + dev_stage);
+    const size_t dev_segver = any_verify ? round_up((size_t)nseg * 4, 256) : 0;
+    nz_ticket* t = ticket_acquire(c, pin_reqs + pin_segs + pin_res, dev_work + dev_tiles + dev_chain + dev_ver + dev_cnt + round_up(dev_infl + dev_rq, 256) + dev_stage + dev_segver);
     if (!t) { cudaGetLastError(); snprintf(tl_err, sizeof tl_err, "ticket allocation failed"); return NZ_ENOMEM; }
     t->n = n; t->nseg = (uint32_t)nseg;
 
@@ -803,11 +804,17 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     a.infl = reinterpret_cast<NzInflWork*>(dv + dev_work + dev_tiles + dev_chain + dev_ver + dev_cnt);
     a.infl_meta = reinterpret_cast<uint64_t*>(a.infl + n) + 2 * (size_t)n;   // after rq_src, rq_len
     a.rq_stat = reinterpret_cast<int32_t*>(reinterpret_cast<uint64_t*>(a.infl + n) + 5 * (size_t)n);
+    a.rq_desc = reinterpret_cast<uint32_t*>(a.rq_stat + n);        // second half of the 8 B / request reserved for rq_stat
     {
         char* stg = dv + dev_work + dev_tiles + dev_chain + dev_ver + dev_cnt + round_up(dev_infl + dev_rq, 256);
         a.reqs_dev = reinterpret_cast<NzDevReq*>(stg);
         a.segs_dev = reinterpret_cast<NzDevSeg*>(stg + round_up((size_t)n * sizeof(NzDevReq), 256));
+        a.seg_ver = any_verify ? reinterpret_cast<uint32_t*>(stg + dev_stage) : nullptr;
     }
+    a.ver_stat = reinterpret_cast<uint32_t*>(a.res + n);
+    t->ver_stat = reinterpret_cast<uint32_t*>(hres + n);
+    t->ver_stat[0] = t->ver_stat[1] = 0;
+    a.fuse_verify = (any_verify && ver_cap && nz_gather_fuses_verify(c->gather_variant)) ? 1u : 0u;
     a.peer_base = c->peer_base_dev;
     a.tile_bytes = nz_gather_tile_bytes(c->gather_variant);
 
@@ -832,12 +839,13 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     int ggrid = c->gather_grid;
     if (tile_bound && tile_bound < (uint64_t)ggrid) ggrid = (int)tile_bound;   // small waves: no more CTAs than tiles
     if (all_host && ggrid > c->host_grid) ggrid = c->host_grid;  // PCIe-bound wave: a few SMs saturate the link
-    CKT(nz_launch_gather(c->gather_variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s));
+    if (a.fuse_verify) CKT(nz_launch_gather(c->gather_variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s, a.seg_ver, a.ver, c->crc_tables));
+    else CKT(nz_launch_gather(c->gather_variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s));
     if (t->profiled) CKT(cudaEventRecord(t->ev_g1, s));
     c->launches += 1;
     if (any_verify && ver_cap) {
         int grid = (int)std::min<uint64_t>(ver_cap, (uint64_t)c->sm_count * 8);
-        CKT(nz_launch_verify(a.ver, a.counters, a.res, c->crc_tables, grid, s));
+        CKT(nz_launch_verify(a, c->crc_tables, grid, s));
         c->launches += 1;
     }
     CKT(cudaEventRecord(t->ev_done, s));
@@ -892,6 +900,7 @@ int32_t nz_get_wait(nz_ticket* t, int64_t timeout_us, nz_get_res* res) {
     if (!t->req_bytes_hint) {   // count a wave once even if waited twice
         t->req_bytes_hint = 1;
         c->gets += t->n; c->get_bytes += bytes; c->hits += hits; c->misses += misses; c->corrupt += corrupt;
+        if (t->ver_stat) { c->verify_chunks += t->ver_stat[0]; c->verify_fused += t->ver_stat[1]; }
     }
     return NZ_OK;
 }
@@ -956,6 +965,8 @@ int32_t nz_get_stats(nz_ctx* c, nz_stats* out) {
     out->kernel_launches = c->launches;
     out->file_cufile_bytes = c->file_cufile_bytes;
     out->file_bounce_bytes = c->file_bounce_bytes;
+    out->verify_chunks = c->verify_chunks;
+    out->verify_fused_chunks = c->verify_fused;
     return NZ_OK;
 }
 

@@ -163,6 +163,87 @@ static inline void nz_crc_fill_fast_tables(uint32_t* out) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// Fused verify (K2 + K3): the gather kernel checksums a tile while it sits in shared memory.
+// A piece = the part of a tile inside one 64 KiB chunk; 16 B aligned, length a multiple of 16.
+// NT threads read it as rows of NT vectors (thread t takes vector t of every row; Z_{16 NT}
+// between rows), then the few vectors of the last partial row.  Each thread moves its value to
+// the end of the full-row region / of the piece with one GF(2) multiply by a table power; the CTA
+// XOR-reduces and ONE thread applies the factors every thread has in common.
+//   tables (Castagnoli, global memory at crc_tables + NZ_CRC_FUSE_OFF):
+//     ZS[4*256]  Z_2048 stride table (NT = 128)   | P16[k] = x^(8*16*k), k < 128 | P2K[m] = x^(8*2048*m), m < 32
+// Values are raw register states (initial all-ones folded into the first word of a chunk, no final
+// inversion), so pieces of one chunk combine by XOR after shifting each to the chunk end.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t crc_z4g(uint32_t a, const uint32_t* __restrict__ gT) {
+    return __ldg(gT + 3 * 256 + (a & 0xffu)) ^ __ldg(gT + 2 * 256 + ((a >> 8) & 0xffu)) ^ __ldg(gT + 256 + ((a >> 16) & 0xffu)) ^ __ldg(gT + (a >> 24));
+}
+// x^(8 n), n < 64 KiB
+__device__ __forceinline__ uint32_t crc_xpow8_small(uint32_t n, const uint32_t* __restrict__ gF) {
+    uint32_t r = __ldg(gF + 1024 + ((n >> 4) & 127u));
+    const uint32_t m = (n >> 11) & 31u;
+    if (m) r = gf_mul<0>(r, __ldg(gF + 1152 + m));
+    if (n & 15u) r = gf_mul<0>(r, gf_xpow8<0>(n & 15u));
+    return r;
+}
+template <int NT>
+__device__ __forceinline__ void crc_piece_partial(const uint8_t* p, uint32_t P, bool ones, const uint32_t* sZS8, const uint32_t* __restrict__ gT,
+                                                  const uint32_t* __restrict__ gF, uint32_t& main, uint32_t& part) {
+    static_assert(NT == 128, "stride table is Z_2048");
+    const uint32_t tid = threadIdx.x, cp = tid & 7u;
+    const uint32_t nvec = P >> 4, R = nvec / NT, rem = nvec % NT;
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    const uint4* v = reinterpret_cast<const uint4*>(p) + tid;
+#define NZ_ZS(a) (sZS8[((a) & 0xffu) * 8u + cp] ^ sZS8[(256u + (((a) >> 8) & 0xffu)) * 8u + cp] ^ \
+                  sZS8[(512u + (((a) >> 16) & 0xffu)) * 8u + cp] ^ sZS8[(768u + ((a) >> 24)) * 8u + cp])
+#pragma unroll 4
+    for (uint32_t r = 0; r < R; ++r) {
+        uint4 w = v[r * NT];
+        if (r == 0 && tid == 0 && ones) w.x ^= 0xFFFFFFFFu;
+        a0 = NZ_ZS(a0) ^ w.x;
+        a1 = NZ_ZS(a1) ^ w.y;
+        a2 = NZ_ZS(a2) ^ w.z;
+        a3 = NZ_ZS(a3) ^ w.w;
+    }
+#undef NZ_ZS
+    main = 0;
+    if (R) {
+        uint32_t vv = crc_z4g(a0, gT) ^ a1;
+        vv = crc_z4g(vv, gT) ^ a2;
+        vv = crc_z4g(vv, gT) ^ a3;
+        vv = crc_z4g(vv, gT);
+        main = gf_mul<0>(__ldg(gF + 1024 + (NT - 1 - tid)), vv);      // to the end of the full-row region
+    }
+    part = 0;
+    if (tid < rem) {
+        uint4 w = v[R * NT];
+        if (R == 0 && tid == 0 && ones) w.x ^= 0xFFFFFFFFu;
+        uint32_t vv = crc_z4g(w.x, gT) ^ w.y;
+        vv = crc_z4g(vv, gT) ^ w.z;
+        vv = crc_z4g(vv, gT) ^ w.w;
+        vv = crc_z4g(vv, gT);
+        part = gf_mul<0>(__ldg(gF + 1024 + (rem - 1 - tid)), vv);     // to the end of the piece
+    }
+}
+
+// host: ZS(2048) | P16 | P2K
+static inline void nz_crc_fill_fuse_tables(uint32_t* T) {
+    auto xpow8 = [](uint64_t nbytes) {
+        uint32_t p = 0x80000000u, sq = 0x80000000u >> 8;
+        while (nbytes) {
+            if (nbytes & 1) p = gf_mul<0>(sq, p);
+            sq = gf_mul<0>(sq, sq);
+            nbytes >>= 1;
+        }
+        return p;
+    };
+    const uint32_t xs = xpow8(2048);
+    for (int k = 0; k < 4; ++k)
+        for (uint32_t b = 0; b < 256; ++b) T[k * 256 + b] = gf_mul<0>(xs, b << (8 * k));
+    for (uint32_t k = 0; k < 128; ++k) T[1024 + k] = xpow8(16 * k);
+    for (uint32_t m = 0; m < 32; ++m) T[1152 + m] = xpow8(2048 * m);
+}
+
 // fills this translation unit's c_x8pow
 static inline cudaError_t nz_crc_upload_constants() {
     uint32_t h[2][48];

@@ -86,14 +86,27 @@ struct __align__(8) NzDevRes {   // mirrors nz_get_res
 };
 static_assert(sizeof(NzDevRes) == sizeof(nz_get_res), "res layout");
 
-// Verify work: one 64 KiB chunk to re-checksum
+// Verify work: one 64 KiB chunk of a stored extent whose CRC-32C must equal the table entry.
+// Two ways to get there.  Fused: the gather kernel checksums the tile while it sits in shared
+// memory and XORs the piece's contribution (shifted to the chunk end) into `acc`, counting bytes
+// in `got`; k_verify then only compares.  Separate: k_verify reads the chunk itself (chunks a
+// slice covers only partly, slices the bulk-copy engine cannot take).
+// device CRC table block (c->crc_tables): slice tables 16 x 256 | fast-path tables 2 x 1280 | fused-verify tables 1184
+constexpr int NZ_CRC_FUSE_OFF = 16 * 256 + 2 * 1280;
+constexpr int NZ_CRC_FUSE_WORDS = 1024 + 128 + 32;
+constexpr int NZ_CRC_TABLE_WORDS = NZ_CRC_FUSE_OFF + NZ_CRC_FUSE_WORDS;
+constexpr uint32_t NZ_VER_FUSED = 0x80000000u;   // in seg
+constexpr uint32_t NZ_VER_NOSEG = 0x7FFFFFFFu;   // seg & ~FUSED: no copy slice behind this entry (inflate input)
 struct __align__(16) NzVerWork {
     uint64_t ptr;
     uint32_t len;
     uint32_t expect;
     uint32_t req;
-    uint32_t pad;
+    uint32_t seg;          // leader slice (work index) | NZ_VER_FUSED
+    uint32_t acc;          // fused: XOR of piece remainders (raw register state, before the final inversion)
+    uint32_t got;          // fused: bytes accumulated
 };
+static_assert(sizeof(NzVerWork) == 32, "ver layout");
 
 
 // ---------------------------------------------------------------------------
@@ -142,6 +155,7 @@ struct nz_ticket {
     bool ran_inflate = false;
     bool own_stream = false;
     uint64_t req_bytes_hint = 0;
+    uint32_t* ver_stat = nullptr;      // pinned: {verify chunks emitted, of which checksummed inside the gather}
 };
 
 struct nz_put {
@@ -185,7 +199,7 @@ struct nz_ctx {
     std::mutex tmu;
     std::vector<nz_ticket*> ticket_pool;
     // stats
-    std::atomic<uint64_t> gets{0}, get_bytes{0}, hits{0}, misses{0}, puts{0}, put_bytes{0}, evictions{0}, corrupt{0}, launches{0}, file_cufile_bytes{0}, file_bounce_bytes{0};
+    std::atomic<uint64_t> gets{0}, get_bytes{0}, hits{0}, misses{0}, puts{0}, put_bytes{0}, evictions{0}, corrupt{0}, launches{0}, file_cufile_bytes{0}, file_bounce_bytes{0}, verify_chunks{0}, verify_fused{0};
     // bounce buffers for nz_put_file / pageable writes
     void* bounce[2] = {nullptr, nullptr};
     size_t bounce_bytes = 0;
@@ -221,6 +235,10 @@ struct NzPlanArgs {
     uint32_t* chain_head;       // nseg: first follower of a leader slice, 0xFFFFFFFF = none
     uint32_t* chain_next;       // nseg: next follower in the chain
     const uint64_t* peer_base;  // device array [shard_count]: base address of every shard's arena (own + IPC-mapped peers)
+    uint32_t* rq_desc;          // n: descriptor index of every request (0xFFFFFFFF = miss), written in phase A
+    uint32_t* seg_ver;          // nseg: first verify entry of a slice whose tiles are checksummed by the gather, else 0xFFFFFFFF
+    uint32_t fuse_verify;       // 1 = the gather variant in use checksums tiles in shared memory
+    uint32_t* ver_stat;         // mapped pinned: [0] = verify chunks of this wave, [1] = of which fused (written by k_plan_verify)
 };
 cudaError_t nz_launch_lookup(const NzSlot* table, uint64_t line_mask, const NzDesc* descs, const uint64_t* keys,
                              uint32_t n, nz_extent* out, cudaStream_t s);
@@ -229,11 +247,12 @@ cudaError_t nz_launch_insert(NzSlot* table, uint64_t line_mask, uint64_t k0, uin
 cudaError_t nz_launch_erase(NzSlot* table, uint64_t line_mask, uint64_t k0, uint64_t k1, int32_t* status, cudaStream_t s);
 cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s);
 cudaError_t nz_launch_gather(int variant, const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head,
-                             const uint32_t* chain_next, uint32_t nseg, int grid, cudaStream_t s);
+                             const uint32_t* chain_next, uint32_t nseg, int grid, cudaStream_t s,
+                             const uint32_t* seg_ver = nullptr, NzVerWork* ver = nullptr, const uint32_t* crc_tables = nullptr);
+bool nz_gather_fuses_verify(int variant);
 int nz_gather_num_variants();
 uint32_t nz_gather_tile_bytes(int variant);
-cudaError_t nz_launch_verify(const NzVerWork* ver, const uint32_t* counters, NzDevRes* res, const uint32_t* crc_tables,
-                             int grid, cudaStream_t s);
+cudaError_t nz_launch_verify(const NzPlanArgs& a, const uint32_t* crc_tables, int grid, cudaStream_t s);
 cudaError_t nz_launch_crc_chunks(const uint8_t* p, uint64_t n, uint32_t* chunk_out, uint32_t* whole_out,
                                  const uint32_t* crc_tables, int sm_count, cudaStream_t s);
 cudaError_t nz_launch_inflate(const NzInflWork* infl, uint64_t* meta, uint32_t* counters, NzDevRes* res,

@@ -261,7 +261,7 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint6
                         const uint64_t off = (uint64_t)c * NZ_CRC_CHUNK;
                         v.ptr = (uint64_t)(a.arena + ds.arena_off + off);
                         v.len = (uint32_t)min((uint64_t)NZ_CRC_CHUNK, ds.stored_len - off);
-                        v.expect = tab[c]; v.req = r; v.pad = 0;
+                        v.expect = tab[c]; v.req = r; v.seg = NZ_VER_NOSEG; v.acc = 0; v.got = 0;
                         a.ver[first + c] = v;
                     }
                 }
@@ -273,6 +273,7 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint6
         rq_tab[r] = tab;
         rq_ssz[r] = ssz;
         a.rq_stat[r] = out.status;
+        a.rq_desc[r] = d;
         a.res[r] = out;
     }
     __syncthreads();
@@ -375,42 +376,56 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint6
     if (tid == 0) a.tile_begin[a.nseg] = s_carry;
 }
 
-// identity-object verify work is emitted by a second tiny kernel that has the
-// descriptor at hand (keeps k_plan's per-request state small).
-__global__ void __launch_bounds__(256)
+// Verify work for stored (not inflated) bytes, emitted after coalescing is known: one warp per
+// slice.  Only the LEADER of a coalesced group gets entries (its followers deliver the same source
+// bytes; k_verify flags every member), and it gets them if any member asked for NZ_GET_VERIFY.
+// A chunk wholly inside a slice that the bulk-copy engine moves is marked NZ_VER_FUSED: the gather
+// checksums it from shared memory and k_verify only compares.
+__global__ void __launch_bounds__(1024)
 k_plan_verify(NzPlanArgs a) {
-    const uint32_t tid = threadIdx.x;
-    const uint32_t g = tid >> 2;
-    for (uint32_t base = 0; base < a.n; base += 64) {
-        const uint32_t r = base + g;
-        const bool want = r < a.n && (a.reqs_dev[r].flags & NZ_GET_VERIFY) && a.rq_stat[r] == NZ_OK;
-        uint64_t k0 = 0, k1 = 0;
-        if (want) { k0 = a.reqs_dev[r].k0; k1 = a.reqs_dev[r].k1; }
-        const uint32_t d = probe_group4(a.table, a.line_mask, k0, k1, want);
-        if (!want || (tid & 3u) != 0 || d == 0xFFFFFFFFu) continue;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t n_fused = 0;
+    for (uint32_t s = warp; s < a.nseg; s += 32) {
+        a.seg_ver[s] = 0xFFFFFFFFu;
+        const NzSegWork w = a.work[s];
+        if (w.len == 0 || a.tile_begin[s + 1] == a.tile_begin[s]) continue;          // failed / follower
+        const NzDevSeg sg = a.segs_dev[s];
+        bool want = (a.reqs_dev[sg.req].flags & NZ_GET_VERIFY) != 0;
+        for (uint32_t m = a.chain_head[s]; !want && m != 0xFFFFFFFFu; m = a.chain_next[m])
+            want = (a.reqs_dev[a.segs_dev[m].req].flags & NZ_GET_VERIFY) != 0;
+        if (!want) continue;
+        const NzDevReq rq = a.reqs_dev[sg.req];
+        const uint32_t d = a.rq_desc[sg.req];
+        if (d == 0xFFFFFFFFu) continue;
         const NzDesc ds = a.descs[d];
-        const NzDevReq rq = a.reqs_dev[r];
-        if ((rq.flags & NZ_GET_INFLATE) && (ds.flags & NZ_ENC_GZIP)) continue;   // done in k_plan
+        if ((rq.flags & NZ_GET_INFLATE) && (ds.flags & NZ_ENC_GZIP)) continue;       // done in k_plan (whole member)
         if (ds.flags & NZ_ENC_STRIPED) continue;     // stripes carry their own chunk tables on their GPUs (verified at fill)
         const uint32_t* tab = reinterpret_cast<const uint32_t*>(a.arena + ds.crc_tab_off);
-        const uint32_t nsg = rq.whole ? 1u : rq.nseg;
-        for (uint32_t i = 0; i < nsg; ++i) {
-            uint64_t off = 0, len = ds.stored_len;
-            if (!rq.whole) { const NzDevSeg sg = a.segs_dev[rq.seg_begin + i]; off = sg.src_off; len = sg.len; }
-            if (!len) continue;
-            const uint32_t c0 = (uint32_t)(off / NZ_CRC_CHUNK), c1 = (uint32_t)((off + len - 1) / NZ_CRC_CHUNK);
-            const uint32_t cnt = c1 - c0 + 1;
-            const uint32_t first = atomicAdd(&a.counters[0], cnt);
-            for (uint32_t c = 0; c < cnt && first + c < a.ver_cap; ++c) {
-                NzVerWork v;
-                const uint64_t coff = (uint64_t)(c0 + c) * NZ_CRC_CHUNK;
-                v.ptr = (uint64_t)(a.arena + ds.arena_off + coff);
-                v.len = (uint32_t)min((uint64_t)NZ_CRC_CHUNK, ds.stored_len - coff);
-                v.expect = tab[c0 + c]; v.req = r; v.pad = 0;
-                a.ver[first + c] = v;
-            }
+        const uint64_t off = rq.whole ? 0 : sg.src_off, len = w.len;
+        const uint32_t c0 = (uint32_t)(off / NZ_CRC_CHUNK), c1 = (uint32_t)((off + len - 1) / NZ_CRC_CHUNK);
+        const uint32_t cnt = c1 - c0 + 1;
+        uint32_t first = 0;
+        if (lane == 0) first = atomicAdd(&a.counters[0], cnt);
+        first = __shfl_sync(0xffffffffu, first, 0);
+        const bool fits = (uint64_t)first + cnt <= a.ver_cap;
+        const bool fusable = a.fuse_verify && fits && ((w.src | w.dst) & 15u) == 0;
+        for (uint32_t c = lane; c < cnt && first + c < a.ver_cap; c += 32) {
+            NzVerWork v;
+            const uint64_t coff = (uint64_t)(c0 + c) * NZ_CRC_CHUNK;
+            v.ptr = (uint64_t)(a.arena + ds.arena_off + coff);
+            v.len = (uint32_t)min((uint64_t)NZ_CRC_CHUNK, ds.stored_len - coff);
+            const bool inside = coff >= off && coff + v.len <= off + len;
+            v.expect = tab[c0 + c]; v.req = sg.req;
+            v.seg = s | ((fusable && inside) ? NZ_VER_FUSED : 0u);
+            v.acc = 0; v.got = 0;
+            a.ver[first + c] = v;
+            n_fused += (fusable && inside) ? 1u : 0u;
         }
+        if (fusable && lane == 0) a.seg_ver[s] = first;
     }
+    if (n_fused) atomicAdd(&a.counters[3], n_fused);
+    __syncthreads();
+    if (threadIdx.x == 0) { a.ver_stat[0] = min(a.counters[0], a.ver_cap); a.ver_stat[1] = a.counters[3]; }
 }
 
 // ---------------------------------------------------------------------------
@@ -671,7 +686,7 @@ k_crc_fold(const uint32_t* __restrict__ chunks, uint64_t n, uint32_t* __restrict
 }
 
 __global__ void __launch_bounds__(256)
-k_verify(const NzVerWork* __restrict__ ver, const uint32_t* __restrict__ counters, NzDevRes* res, const uint32_t* __restrict__ tables) {
+k_verify(NzPlanArgs a, const uint32_t* __restrict__ tables) {
     __shared__ uint32_t sT[4 * 256];
     __shared__ uint32_t sZS8[1024 * 8];
     __shared__ uint32_t sred[8];
@@ -679,13 +694,30 @@ k_verify(const NzVerWork* __restrict__ ver, const uint32_t* __restrict__ counter
     for (uint32_t i = threadIdx.x; i < 1024; i += 256) sT[i] = tables[i];
     crc_load_fast_tables(sZS8, fast);
     __syncthreads();
-    const uint32_t n = counters[0];
+    const uint32_t n = min(a.counters[0], a.ver_cap);
     for (uint32_t c = blockIdx.x; c < n; c += gridDim.x) {
-        const NzVerWork v = ver[c];
-        const uint8_t* vp = reinterpret_cast<const uint8_t*>(v.ptr);
-        const uint32_t crc = (v.len == NZ_CRC_CHUNK && (v.ptr & 15u) == 0) ? block_crc_chunk64k<0>(vp, sZS8, sT, fast + 1024, sred)
-                                                                           : block_crc_chunk<0>(vp, v.len, sT, sred);
-        if (threadIdx.x == 0 && crc != v.expect) res[v.req].status = NZ_ECORRUPT;
+        const NzVerWork v = a.ver[c];
+        bool bad;
+        if (v.seg & NZ_VER_FUSED) {                       // the gather already checksummed these bytes from shared memory
+            bad = v.got != v.len || ~v.acc != v.expect;
+        } else {
+            const uint8_t* vp = reinterpret_cast<const uint8_t*>(v.ptr);
+            const uint32_t crc = (v.len == NZ_CRC_CHUNK && (v.ptr & 15u) == 0) ? block_crc_chunk64k<0>(vp, sZS8, sT, fast + 1024, sred)
+                                                                               : block_crc_chunk<0>(vp, v.len, sT, sred);
+            bad = crc != v.expect;
+        }
+        if (threadIdx.x == 0 && bad) {
+            const uint32_t sg = v.seg & ~NZ_VER_FUSED;
+            if (sg == NZ_VER_NOSEG) {
+                a.res[v.req].status = NZ_ECORRUPT;
+            } else {                                      // the slice's request and every coalesced follower that asked
+                if (a.reqs_dev[v.req].flags & NZ_GET_VERIFY) a.res[v.req].status = NZ_ECORRUPT;
+                for (uint32_t m = a.chain_head[sg]; m != 0xFFFFFFFFu; m = a.chain_next[m]) {
+                    const uint32_t r = a.segs_dev[m].req;
+                    if (a.reqs_dev[r].flags & NZ_GET_VERIFY) a.res[r].status = NZ_ECORRUPT;
+                }
+            }
+        }
     }
 }
 
@@ -720,7 +752,7 @@ cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (a.ver_cap) {
-        k_plan_verify<<<1, 256, 0, s>>>(a);
+        k_plan_verify<<<1, 1024, 0, s>>>(a);
         e = cudaGetLastError();
     }
     return e;
@@ -744,13 +776,80 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 
 // STAGES shared buffers of tile_bytes each.  The load of tile i is issued before the stores of
 // tile i-1, so a tile's HBM read overlaps the previous tile's writes inside one CTA.
-template <int STAGES, bool AHEAD>
+// Fused verify (VERIFY = true): the CRC-32C of every tile piece is taken from the copy that sits in
+// shared memory (or, for the few short tiles of such a slice, from the source lines just read) and
+// XOR-accumulated per 64 KiB chunk in the wave's verify entries; k_verify compares afterwards.
+// HBM traffic stays read S + write P: the separate checksum pass over the source disappears.
+struct VerifyCtx {
+    const uint32_t* seg_ver;
+    NzVerWork* ver;
+    const uint32_t* gT;      // Castagnoli slice tables
+    const uint32_t* gF;      // fused-verify tables (ZS | P16 | P2K)
+    const uint32_t* sZS8;    // Z_2048 stride table, 8 copies, shared memory
+    uint32_t* sred;          // 8 words
+};
+
+// data: the tile's bytes (generic address: shared or global), gsrc: their address in the arena
+__device__ __forceinline__ void tile_verify(const VerifyCtx& vc, const uint8_t* data, const uint8_t* gsrc, uint32_t n, uint32_t vbase, uint64_t c0ptr) {
+    const uint32_t tid = threadIdx.x;
+    const uint64_t q0 = (uint64_t)(uintptr_t)gsrc - c0ptr;
+    const uint32_t j0 = (uint32_t)(q0 >> 16), j1 = (uint32_t)((q0 + n - 1) >> 16);
+    for (uint32_t j = j0; j <= j1; ++j) {
+        NzVerWork* e = vc.ver + vbase + j;
+        const uint32_t eseg = *reinterpret_cast<volatile uint32_t*>(&e->seg);
+        if (!(eseg & NZ_VER_FUSED)) continue;                  // chunk only partly inside the slice: k_verify reads it
+        const uint32_t elen = *reinterpret_cast<volatile uint32_t*>(&e->len);
+        const uint64_t cb = (uint64_t)j << 16;
+        const uint64_t pb = q0 > cb ? q0 : cb;
+        const uint64_t pe = (q0 + n) < (cb + NZ_CRC_CHUNK) ? (q0 + n) : (cb + NZ_CRC_CHUNK);
+        const uint32_t plen = (uint32_t)(pe - pb), off = (uint32_t)(pb - q0);
+        const uint32_t P = plen & ~15u, tail = plen & 15u;
+        const bool ones = pb == cb;
+        uint32_t m, pt;
+        crc_piece_partial<NZ_TMA_THREADS>(data + off, P, ones, vc.sZS8, vc.gT, vc.gF, m, pt);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m ^= __shfl_xor_sync(0xffffffffu, m, o);
+            pt ^= __shfl_xor_sync(0xffffffffu, pt, o);
+        }
+        __syncthreads();                                       // sred reuse
+        if ((tid & 31u) == 0) { vc.sred[tid >> 5] = m; vc.sred[4 + (tid >> 5)] = pt; }
+        __syncthreads();                                       // also: every thread is done reading the tile
+        if (tid == 32) {
+            const uint32_t M = vc.sred[0] ^ vc.sred[1] ^ vc.sred[2] ^ vc.sred[3];
+            uint32_t st = vc.sred[4] ^ vc.sred[5] ^ vc.sred[6] ^ vc.sred[7];
+            if (M) st ^= gf_mul<0>(__ldg(vc.gF + 1024 + ((P >> 4) % NZ_TMA_THREADS)), M);   // full rows -> end of the piece
+            if (tail) {
+                if (ones && P == 0) st = 0xFFFFFFFFu;
+                const uint8_t* tb = gsrc + off + P;
+                for (uint32_t i = 0; i < tail; ++i) st = (st >> 8) ^ __ldg(vc.gT + ((st ^ tb[i]) & 0xffu));
+            }
+            const uint32_t after = elen - (uint32_t)(pe - cb);
+            if (after) st = gf_mul<0>(crc_xpow8_small(after, vc.gF), st);
+            atomicXor(&e->acc, st);
+            atomicAdd(&e->got, plen);
+        }
+    }
+}
+
+template <int STAGES, bool AHEAD, bool VERIFY>
 __global__ void __launch_bounds__(NZ_TMA_THREADS)
 k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_begin, const uint32_t* __restrict__ chain_head,
-             const uint32_t* __restrict__ chain_next, uint32_t nseg, uint32_t tile_bytes) {
-    extern __shared__ __align__(128) uint8_t s_buf[];          // STAGES x tile_bytes
+             const uint32_t* __restrict__ chain_next, uint32_t nseg, uint32_t tile_bytes, const uint32_t* __restrict__ seg_ver,
+             NzVerWork* ver, const uint32_t* __restrict__ crc_tables) {
+    static_assert(!(AHEAD && VERIFY), "fused verify uses the simple pipeline");
+    extern __shared__ __align__(128) uint8_t s_buf[];          // STAGES x tile_bytes [ | 32 KiB stride table when VERIFY ]
     __shared__ __align__(8) uint64_t s_bar[STAGES];
+    __shared__ uint32_t s_red[8];
     const uint32_t tid = threadIdx.x;
+    VerifyCtx vc;
+    uint32_t vbase = 0xFFFFFFFFu;
+    uint64_t c0ptr = 0;
+    if constexpr (VERIFY) {
+        uint32_t* sz = reinterpret_cast<uint32_t*>(s_buf + (size_t)STAGES * tile_bytes);
+        crc_load_fast_tables(sz, crc_tables + NZ_CRC_FUSE_OFF);
+        vc.seg_ver = seg_ver; vc.ver = ver; vc.gT = crc_tables; vc.gF = crc_tables + NZ_CRC_FUSE_OFF; vc.sZS8 = sz; vc.sred = s_red;
+    }
     if (tid == 0) {
 #pragma unroll
         for (int i = 0; i < STAGES; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s_bar[i])));
@@ -791,7 +890,13 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
         const uint32_t before = c.seg;
         const bool fresh = !(tile >= c.lo_t && tile < c.hi_t);
         c.seek(tile, work, tile_begin, nseg);
-        if (fresh || before != c.seg) dc.head = __ldg(chain_head + c.seg);
+        if (fresh || before != c.seg) {
+            dc.head = __ldg(chain_head + c.seg);
+            if constexpr (VERIFY) {
+                vbase = __ldg(seg_ver + c.seg);
+                if (vbase != 0xFFFFFFFFu) c0ptr = *reinterpret_cast<volatile uint64_t*>(&ver[vbase].ptr);
+            }
+        }
         int64_t lo, hi;
         c.span(tile, tile_bytes, lo, hi);
         const uint8_t* s = reinterpret_cast<const uint8_t*>(c.src) + lo;
@@ -803,8 +908,40 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
             dc.d0 = d;
             dc.lo = lo;
             copy_tile<NZ_TMA_THREADS, 8, 0>(s, dc, n);
+            if constexpr (VERIFY) {
+                if (vbase != 0xFFFFFFFFu) tile_verify(vc, s, s, n, vbase, c0ptr);   // short tile of an engine slice: lines are L2-hot
+            }
             continue;
         }
+        if constexpr (VERIFY) {
+            // simple pipeline, every thread follows the barrier phases: load -> (all wait) -> stores -> checksum from shared memory
+            const uint32_t buf = smem_u32(s_buf + (size_t)slot * tile_bytes), bar = smem_u32(&s_bar[slot]);
+            if (tid == 0) {
+                bulk_wait_read<STAGES - 1>();
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bulk) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(buf), "l"(s), "r"(bulk), "r"(bar) : "memory");
+            }
+            const bool vt = vbase != 0xFFFFFFFFu;
+            if (vt || tid == 0) {
+                uint32_t done = 0;
+                while (!done) {
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                 : "=r"(done) : "r"(bar), "r"((phase_bits >> slot) & 1u) : "memory");
+                }
+            }
+            phase_bits ^= 1u << slot;
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(d), "r"(buf), "r"(bulk) : "memory");
+                for (uint32_t m = dc.head; m != 0xFFFFFFFFu; m = __ldg(chain_next + m)) {
+                    uint8_t* dm = reinterpret_cast<uint8_t*>(__ldg(&work[m].dst)) + lo;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dm), "r"(buf), "r"(bulk) : "memory");
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            if (vt) tile_verify(vc, s_buf + (size_t)slot * tile_bytes, s, n, vbase, c0ptr);
+        } else
         if (tid == 0) {
             const uint32_t buf = smem_u32(s_buf + (size_t)slot * tile_bytes), bar = smem_u32(&s_bar[slot]);
             // stage `slot` was last read by the stores of the engine tile STAGES back; the store groups still
@@ -850,41 +987,61 @@ static TmaCfg tma_cfg() {
     }();
     return c;
 }
-template <int STAGES, bool AHEAD>
-static cudaError_t launch_tma(const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head, const uint32_t* chain_next,
-                              uint32_t nseg, int grid, cudaStream_t s, int* occ) {
+struct TmaArgs {
+    const NzSegWork* work; const uint64_t* tile_begin; const uint32_t* chain_head; const uint32_t* chain_next;
+    uint32_t nseg; int grid; cudaStream_t s; int* occ;
+    const uint32_t* seg_ver; NzVerWork* ver; const uint32_t* crc_tables;
+};
+template <int STAGES, bool AHEAD, bool VERIFY>
+static cudaError_t launch_tma(const TmaArgs& a) {
     const TmaCfg t = tma_cfg();
-    const size_t smem = (size_t)STAGES * t.tile;
+    const size_t smem = (size_t)STAGES * t.tile + (VERIFY ? 32768 : 0);
     static bool attr_set[64] = {};          // function attributes are per device
+    static int max_grid[64] = {};           // VERIFY: resident CTAs (fewer fit per SM than the plain kernel's persistent grid)
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        cudaFuncSetAttribute(k_gather_tma<STAGES, AHEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        cudaFuncSetAttribute(k_gather_tma<STAGES, AHEAD, VERIFY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (dev >= 0 && dev < 64) {
+            attr_set[dev] = true;
+            int nb = 0, sms = 0;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather_tma<STAGES, AHEAD, VERIFY>, NZ_TMA_THREADS, smem) != cudaSuccess || nb < 1) nb = 1;
+            max_grid[dev] = nb * (sms > 0 ? sms : 1);
+        }
     }
-    if (occ) {
+    if (a.occ) {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather_tma<STAGES, AHEAD>, NZ_TMA_THREADS, smem) != cudaSuccess || nb < 1) nb = 1;
-        *occ = nb;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather_tma<STAGES, AHEAD, VERIFY>, NZ_TMA_THREADS, smem) != cudaSuccess || nb < 1) nb = 1;
+        *a.occ = nb;
         return cudaSuccess;
     }
-    k_gather_tma<STAGES, AHEAD><<<grid, NZ_TMA_THREADS, smem, s>>>(work, tile_begin, chain_head, chain_next, nseg, t.tile);
+    int grid = a.grid;
+    if (VERIFY && dev >= 0 && dev < 64 && max_grid[dev] > 0 && grid > max_grid[dev]) grid = max_grid[dev];
+    k_gather_tma<STAGES, AHEAD, VERIFY><<<grid, NZ_TMA_THREADS, smem, a.s>>>(a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, t.tile,
+                                                                              a.seg_ver, a.ver, a.crc_tables);
     return cudaGetLastError();
 }
-static cudaError_t dispatch_tma(const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head, const uint32_t* chain_next,
-                                uint32_t nseg, int grid, cudaStream_t s, int* occ) {
+static cudaError_t dispatch_tma(const TmaArgs& a) {
     const TmaCfg t = tma_cfg();
+    if (a.seg_ver) {                          // fused verify: simple pipeline only
+        switch (t.stages) {
+        case 3: return launch_tma<3, false, true>(a);
+        case 4: return launch_tma<4, false, true>(a);
+        default: return launch_tma<2, false, true>(a);
+        }
+    }
     if (t.ahead) {
         switch (t.stages) {
-        case 2: return launch_tma<2, true>(work, tile_begin, chain_head, chain_next, nseg, grid, s, occ);
-        case 4: return launch_tma<4, true>(work, tile_begin, chain_head, chain_next, nseg, grid, s, occ);
-        default: return launch_tma<3, true>(work, tile_begin, chain_head, chain_next, nseg, grid, s, occ);
+        case 2: return launch_tma<2, true, false>(a);
+        case 4: return launch_tma<4, true, false>(a);
+        default: return launch_tma<3, true, false>(a);
         }
     }
     switch (t.stages) {
-    case 3: return launch_tma<3, false>(work, tile_begin, chain_head, chain_next, nseg, grid, s, occ);
-    case 4: return launch_tma<4, false>(work, tile_begin, chain_head, chain_next, nseg, grid, s, occ);
-    default: return launch_tma<2, false>(work, tile_begin, chain_head, chain_next, nseg, grid, s, occ);
+    case 3: return launch_tma<3, false, false>(a);
+    case 4: return launch_tma<4, false, false>(a);
+    default: return launch_tma<2, false, false>(a);
     }
 }
 
@@ -946,22 +1103,23 @@ static int occ_gather_t() {
     default: return F<256, 8, 2, 0>(__VA_ARGS__);                 \
     }
 
+bool nz_gather_fuses_verify(int variant) { return variant == 14; }
 cudaError_t nz_launch_gather(int variant, const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head,
-                             const uint32_t* chain_next, uint32_t nseg, int grid, cudaStream_t s) {
-    if (variant == 14) return dispatch_tma(work, tile_begin, chain_head, chain_next, nseg, grid, s, nullptr);
+                             const uint32_t* chain_next, uint32_t nseg, int grid, cudaStream_t s,
+                             const uint32_t* seg_ver, NzVerWork* ver, const uint32_t* crc_tables) {
+    if (variant == 14) return dispatch_tma(TmaArgs{work, tile_begin, chain_head, chain_next, nseg, grid, s, nullptr, seg_ver, ver, crc_tables});
     NZ_GV_SWITCH(variant, launch_gather_t, work, tile_begin, chain_head, chain_next, nseg, grid, s)
 }
 int nz_gather_blocks_per_sm(int variant) {
     if (variant == 14) {
         int nb = 1;
-        dispatch_tma(nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, &nb);
+        dispatch_tma(TmaArgs{nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, &nb, nullptr, nullptr, nullptr});
         return nb;
     }
     NZ_GV_SWITCH(variant, occ_gather_t)
 }
-cudaError_t nz_launch_verify(const NzVerWork* ver, const uint32_t* counters, NzDevRes* res, const uint32_t* crc_tables,
-                             int grid, cudaStream_t s) {
-    k_verify<<<grid, 256, 0, s>>>(ver, counters, res, crc_tables);
+cudaError_t nz_launch_verify(const NzPlanArgs& a, const uint32_t* crc_tables, int grid, cudaStream_t s) {
+    k_verify<<<grid, 256, 0, s>>>(a, crc_tables);
     return cudaGetLastError();
 }
 cudaError_t nz_launch_crc_chunks(const uint8_t* p, uint64_t n, uint32_t* chunk_out, uint32_t* whole_out,
@@ -985,8 +1143,10 @@ cudaError_t nz_upload_constants(uint32_t* crc_tables_dev) {
     e = nz_inflate_upload_constants();
     if (e != cudaSuccess) return e;
     // slice tables: [0..7] Castagnoli, [8..15] IEEE (gzip trailer CRC-32)
-    static uint32_t t[16 * 256 + 2 * NZ_CRC_FAST_WORDS];
+    static uint32_t t[NZ_CRC_TABLE_WORDS];
+    static_assert(NZ_CRC_FUSE_OFF == 16 * 256 + 2 * NZ_CRC_FAST_WORDS, "table block layout");
     nz_crc_fill_fast_tables(t + 16 * 256);
+    nz_crc_fill_fuse_tables(t + NZ_CRC_FUSE_OFF);
     const uint32_t polys[2] = {NZ_POLY_C, NZ_POLY_IEEE};
     for (int pi = 0; pi < 2; ++pi) {
         uint32_t* T = t + pi * 8 * 256;
