@@ -149,6 +149,7 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
     }
     if (const char* ev = getenv("NZ_COALESCE")) c->coalesce = atoi(ev) != 0;
     if (const char* ev = getenv("NZ_PROFILE")) c->profile = atoi(ev) != 0;
+    if (const char* ev = getenv("NZ_FUSE_VERIFY")) c->fuse_verify = atoi(ev) != 0;
     c->gather_grid = c->sm_count * nz_gather_blocks_per_sm(c->gather_variant);
     c->inflate_grid = c->sm_count * nz_inflate_blocks_per_sm();
     *out = c;
@@ -814,7 +815,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     a.ver_stat = reinterpret_cast<uint32_t*>(a.res + n);
     t->ver_stat = reinterpret_cast<uint32_t*>(hres + n);
     t->ver_stat[0] = t->ver_stat[1] = 0;
-    a.fuse_verify = (any_verify && ver_cap && nz_gather_fuses_verify(c->gather_variant)) ? 1u : 0u;
+    a.fuse_verify = (any_verify && ver_cap && c->fuse_verify && nz_gather_fuses_verify(c->gather_variant)) ? 1u : 0u;
     a.peer_base = c->peer_base_dev;
     a.tile_bytes = nz_gather_tile_bytes(c->gather_variant);
 

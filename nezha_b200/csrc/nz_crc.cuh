@@ -170,8 +170,9 @@ static inline void nz_crc_fill_fast_tables(uint32_t* out) {
 // between rows), then the few vectors of the last partial row.  Each thread moves its value to
 // the end of the full-row region / of the piece with one GF(2) multiply by a table power; the CTA
 // XOR-reduces and ONE thread applies the factors every thread has in common.
-//   tables (Castagnoli, global memory at crc_tables + NZ_CRC_FUSE_OFF):
-//     ZS[4*256]  Z_2048 stride table (NT = 128)   | P16[k] = x^(8*16*k), k < 128 | P2K[m] = x^(8*2048*m), m < 32
+//   NT = 256: rows of 4 KiB, so the stride table is the fast path's Z_4096 (crc_tables + 16*256).
+//   powers (Castagnoli, global memory at crc_tables + NZ_CRC_FUSE_OFF):
+//     P16[k] = x^(8*16*k), k < 256 | P2K[m] = x^(8*2048*m), m < 32
 // Values are raw register states (initial all-ones folded into the first word of a chunk, no final
 // inversion), so pieces of one chunk combine by XOR after shifting each to the chunk end.
 // ---------------------------------------------------------------------------
@@ -180,16 +181,16 @@ __device__ __forceinline__ uint32_t crc_z4g(uint32_t a, const uint32_t* __restri
 }
 // x^(8 n), n < 64 KiB
 __device__ __forceinline__ uint32_t crc_xpow8_small(uint32_t n, const uint32_t* __restrict__ gF) {
-    uint32_t r = __ldg(gF + 1024 + ((n >> 4) & 127u));
+    uint32_t r = __ldg(gF + ((n >> 4) & 127u));
     const uint32_t m = (n >> 11) & 31u;
-    if (m) r = gf_mul<0>(r, __ldg(gF + 1152 + m));
+    if (m) r = gf_mul<0>(r, __ldg(gF + 256 + m));
     if (n & 15u) r = gf_mul<0>(r, gf_xpow8<0>(n & 15u));
     return r;
 }
 template <int NT>
 __device__ __forceinline__ void crc_piece_partial(const uint8_t* p, uint32_t P, bool ones, const uint32_t* sZS8, const uint32_t* __restrict__ gT,
                                                   const uint32_t* __restrict__ gF, uint32_t& main, uint32_t& part) {
-    static_assert(NT == 128, "stride table is Z_2048");
+    static_assert(NT == 256, "stride table is Z_4096");
     const uint32_t tid = threadIdx.x, cp = tid & 7u;
     const uint32_t nvec = P >> 4, R = nvec / NT, rem = nvec % NT;
     uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
@@ -212,7 +213,7 @@ __device__ __forceinline__ void crc_piece_partial(const uint8_t* p, uint32_t P, 
         vv = crc_z4g(vv, gT) ^ a2;
         vv = crc_z4g(vv, gT) ^ a3;
         vv = crc_z4g(vv, gT);
-        main = gf_mul<0>(__ldg(gF + 1024 + (NT - 1 - tid)), vv);      // to the end of the full-row region
+        main = gf_mul<0>(__ldg(gF + (NT - 1 - tid)), vv);      // to the end of the full-row region
     }
     part = 0;
     if (tid < rem) {
@@ -222,11 +223,11 @@ __device__ __forceinline__ void crc_piece_partial(const uint8_t* p, uint32_t P, 
         vv = crc_z4g(vv, gT) ^ w.z;
         vv = crc_z4g(vv, gT) ^ w.w;
         vv = crc_z4g(vv, gT);
-        part = gf_mul<0>(__ldg(gF + 1024 + (rem - 1 - tid)), vv);     // to the end of the piece
+        part = gf_mul<0>(__ldg(gF + (rem - 1 - tid)), vv);     // to the end of the piece
     }
 }
 
-// host: ZS(2048) | P16 | P2K
+// host: P16 | P2K
 static inline void nz_crc_fill_fuse_tables(uint32_t* T) {
     auto xpow8 = [](uint64_t nbytes) {
         uint32_t p = 0x80000000u, sq = 0x80000000u >> 8;
@@ -237,11 +238,8 @@ static inline void nz_crc_fill_fuse_tables(uint32_t* T) {
         }
         return p;
     };
-    const uint32_t xs = xpow8(2048);
-    for (int k = 0; k < 4; ++k)
-        for (uint32_t b = 0; b < 256; ++b) T[k * 256 + b] = gf_mul<0>(xs, b << (8 * k));
-    for (uint32_t k = 0; k < 128; ++k) T[1024 + k] = xpow8(16 * k);
-    for (uint32_t m = 0; m < 32; ++m) T[1152 + m] = xpow8(2048 * m);
+    for (uint32_t k = 0; k < 256; ++k) T[k] = xpow8(16 * k);
+    for (uint32_t m = 0; m < 32; ++m) T[256 + m] = xpow8(2048 * m);
 }
 
 // fills this translation unit's c_x8pow

@@ -91,9 +91,9 @@ static_assert(sizeof(NzDevRes) == sizeof(nz_get_res), "res layout");
 // memory and XORs the piece's contribution (shifted to the chunk end) into `acc`, counting bytes
 // in `got`; k_verify then only compares.  Separate: k_verify reads the chunk itself (chunks a
 // slice covers only partly, slices the bulk-copy engine cannot take).
-// device CRC table block (c->crc_tables): slice tables 16 x 256 | fast-path tables 2 x 1280 | fused-verify tables 1184
+// device CRC table block (c->crc_tables): slice tables 16 x 256 | fast-path tables 2 x 1280 | fused-verify powers 288
 constexpr int NZ_CRC_FUSE_OFF = 16 * 256 + 2 * 1280;
-constexpr int NZ_CRC_FUSE_WORDS = 1024 + 128 + 32;
+constexpr int NZ_CRC_FUSE_WORDS = 256 + 32;
 constexpr int NZ_CRC_TABLE_WORDS = NZ_CRC_FUSE_OFF + NZ_CRC_FUSE_WORDS;
 constexpr uint32_t NZ_VER_FUSED = 0x80000000u;   // in seg
 constexpr uint32_t NZ_VER_NOSEG = 0x7FFFFFFFu;   // seg & ~FUSED: no copy slice behind this entry (inflate input)
@@ -175,6 +175,7 @@ struct nz_ctx {
     int sm_count;
     int gather_grid;       // persistent grid size for k_gather
     bool profile = false;   // record per-kernel CUDA events in every wave (nz_set_profiling / env NZ_PROFILE=1)
+    bool fuse_verify = true; // env NZ_FUSE_VERIFY=0: NZ_GET_VERIFY re-reads every chunk in k_verify (A/B measurements)
     bool coalesce = true;   // env NZ_COALESCE=0 turns request coalescing off (A/B measurements)
     int gather_variant = 14; // k_gather variant: 14 = TMA bulk-copy staging (default, measured best); 0-13 register paths (env NZ_GATHER_VARIANT)
     int inflate_grid;

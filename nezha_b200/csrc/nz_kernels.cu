@@ -784,12 +784,14 @@ struct VerifyCtx {
     const uint32_t* seg_ver;
     NzVerWork* ver;
     const uint32_t* gT;      // Castagnoli slice tables
-    const uint32_t* gF;      // fused-verify tables (ZS | P16 | P2K)
-    const uint32_t* sZS8;    // Z_2048 stride table, 8 copies, shared memory
-    uint32_t* sred;          // 8 words
+    const uint32_t* gF;      // fused-verify powers (P16 | P2K)
+    const uint32_t* sZS8;    // Z_4096 stride table, 8 copies, shared memory
+    uint32_t* sred;          // 16 words
 };
 
 // data: the tile's bytes (generic address: shared or global), gsrc: their address in the arena
+constexpr int NZ_TMA_VTHREADS = 256;      // the VERIFY instantiation runs more warps: the checksum is latency bound
+
 __device__ __forceinline__ void tile_verify(const VerifyCtx& vc, const uint8_t* data, const uint8_t* gsrc, uint32_t n, uint32_t vbase, uint64_t c0ptr) {
     const uint32_t tid = threadIdx.x;
     const uint64_t q0 = (uint64_t)(uintptr_t)gsrc - c0ptr;
@@ -806,19 +808,20 @@ __device__ __forceinline__ void tile_verify(const VerifyCtx& vc, const uint8_t* 
         const uint32_t P = plen & ~15u, tail = plen & 15u;
         const bool ones = pb == cb;
         uint32_t m, pt;
-        crc_piece_partial<NZ_TMA_THREADS>(data + off, P, ones, vc.sZS8, vc.gT, vc.gF, m, pt);
+        crc_piece_partial<NZ_TMA_VTHREADS>(data + off, P, ones, vc.sZS8, vc.gT, vc.gF, m, pt);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             m ^= __shfl_xor_sync(0xffffffffu, m, o);
             pt ^= __shfl_xor_sync(0xffffffffu, pt, o);
         }
         __syncthreads();                                       // sred reuse
-        if ((tid & 31u) == 0) { vc.sred[tid >> 5] = m; vc.sred[4 + (tid >> 5)] = pt; }
+        if ((tid & 31u) == 0) { vc.sred[tid >> 5] = m; vc.sred[8 + (tid >> 5)] = pt; }
         __syncthreads();                                       // also: every thread is done reading the tile
         if (tid == 32) {
-            const uint32_t M = vc.sred[0] ^ vc.sred[1] ^ vc.sred[2] ^ vc.sred[3];
-            uint32_t st = vc.sred[4] ^ vc.sred[5] ^ vc.sred[6] ^ vc.sred[7];
-            if (M) st ^= gf_mul<0>(__ldg(vc.gF + 1024 + ((P >> 4) % NZ_TMA_THREADS)), M);   // full rows -> end of the piece
+            uint32_t M = 0, st = 0;
+#pragma unroll
+            for (int i = 0; i < NZ_TMA_VTHREADS / 32; ++i) { M ^= vc.sred[i]; st ^= vc.sred[8 + i]; }
+            if (M) st ^= gf_mul<0>(__ldg(vc.gF + ((P >> 4) % NZ_TMA_VTHREADS)), M);   // full rows -> end of the piece
             if (tail) {
                 if (ones && P == 0) st = 0xFFFFFFFFu;
                 const uint8_t* tb = gsrc + off + P;
@@ -833,21 +836,22 @@ __device__ __forceinline__ void tile_verify(const VerifyCtx& vc, const uint8_t* 
 }
 
 template <int STAGES, bool AHEAD, bool VERIFY>
-__global__ void __launch_bounds__(NZ_TMA_THREADS)
+__global__ void __launch_bounds__(VERIFY ? NZ_TMA_VTHREADS : NZ_TMA_THREADS)
 k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_begin, const uint32_t* __restrict__ chain_head,
              const uint32_t* __restrict__ chain_next, uint32_t nseg, uint32_t tile_bytes, const uint32_t* __restrict__ seg_ver,
              NzVerWork* ver, const uint32_t* __restrict__ crc_tables) {
     static_assert(!(AHEAD && VERIFY), "fused verify uses the simple pipeline");
     extern __shared__ __align__(128) uint8_t s_buf[];          // STAGES x tile_bytes [ | 32 KiB stride table when VERIFY ]
     __shared__ __align__(8) uint64_t s_bar[STAGES];
-    __shared__ uint32_t s_red[8];
+    __shared__ uint32_t s_red[16];
+    constexpr int NT = VERIFY ? NZ_TMA_VTHREADS : NZ_TMA_THREADS;
     const uint32_t tid = threadIdx.x;
     VerifyCtx vc;
     uint32_t vbase = 0xFFFFFFFFu;
     uint64_t c0ptr = 0;
     if constexpr (VERIFY) {
         uint32_t* sz = reinterpret_cast<uint32_t*>(s_buf + (size_t)STAGES * tile_bytes);
-        crc_load_fast_tables(sz, crc_tables + NZ_CRC_FUSE_OFF);
+        crc_load_fast_tables(sz, crc_tables + 16 * 256);       // Castagnoli Z_4096
         vc.seg_ver = seg_ver; vc.ver = ver; vc.gT = crc_tables; vc.gF = crc_tables + NZ_CRC_FUSE_OFF; vc.sZS8 = sz; vc.sred = s_red;
     }
     if (tid == 0) {
@@ -907,7 +911,7 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
         if (!engine) {
             dc.d0 = d;
             dc.lo = lo;
-            copy_tile<NZ_TMA_THREADS, 8, 0>(s, dc, n);
+            copy_tile<NT, 8, 0>(s, dc, n);
             if constexpr (VERIFY) {
                 if (vbase != 0xFFFFFFFFu) tile_verify(vc, s, s, n, vbase, c0ptr);   // short tile of an engine slice: lines are L2-hot
             }
@@ -996,6 +1000,7 @@ template <int STAGES, bool AHEAD, bool VERIFY>
 static cudaError_t launch_tma(const TmaArgs& a) {
     const TmaCfg t = tma_cfg();
     const size_t smem = (size_t)STAGES * t.tile + (VERIFY ? 32768 : 0);
+    constexpr int NTH = VERIFY ? NZ_TMA_VTHREADS : NZ_TMA_THREADS;
     static bool attr_set[64] = {};          // function attributes are per device
     static int max_grid[64] = {};           // VERIFY: resident CTAs (fewer fit per SM than the plain kernel's persistent grid)
     int dev = 0;
@@ -1006,19 +1011,19 @@ static cudaError_t launch_tma(const TmaArgs& a) {
             attr_set[dev] = true;
             int nb = 0, sms = 0;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather_tma<STAGES, AHEAD, VERIFY>, NZ_TMA_THREADS, smem) != cudaSuccess || nb < 1) nb = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather_tma<STAGES, AHEAD, VERIFY>, NTH, smem) != cudaSuccess || nb < 1) nb = 1;
             max_grid[dev] = nb * (sms > 0 ? sms : 1);
         }
     }
     if (a.occ) {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather_tma<STAGES, AHEAD, VERIFY>, NZ_TMA_THREADS, smem) != cudaSuccess || nb < 1) nb = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather_tma<STAGES, AHEAD, VERIFY>, NTH, smem) != cudaSuccess || nb < 1) nb = 1;
         *a.occ = nb;
         return cudaSuccess;
     }
     int grid = a.grid;
     if (VERIFY && dev >= 0 && dev < 64 && max_grid[dev] > 0 && grid > max_grid[dev]) grid = max_grid[dev];
-    k_gather_tma<STAGES, AHEAD, VERIFY><<<grid, NZ_TMA_THREADS, smem, a.s>>>(a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, t.tile,
+    k_gather_tma<STAGES, AHEAD, VERIFY><<<grid, NTH, smem, a.s>>>(a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, t.tile,
                                                                               a.seg_ver, a.ver, a.crc_tables);
     return cudaGetLastError();
 }
