@@ -538,7 +538,8 @@ def http_bench(L_obj, requests, device, seed=2):
         # ---- GPU proxy ----
         p = subprocess.Popen([os.path.join(ROOT, "nezha_b200", "_build", "nzproxy"), "--listen", f"127.0.0.1:{gport}", "--device", str(device),
                               "--arena-gib", str(L_obj / 2**30 + 0.5), "--max-conns", str(2 * nconn), "--window-mib", "4", "--first-window-kib", "64",
-                              "--upstream", f"{host}=127.0.0.1:{oport}"], start_new_session=True, stderr=subprocess.DEVNULL)
+                              "--upstream", f"{host}=127.0.0.1:{oport}"], start_new_session=True,
+                             stderr=open(os.environ["NZ_PROXY_LOG"], "w") if os.environ.get("NZ_PROXY_LOG") else subprocess.DEVNULL)
         procs.append(p)
         if wait_port(gport):
             import http.client
@@ -562,7 +563,7 @@ def http_bench(L_obj, requests, device, seed=2):
                 out[name] = load(cport, repeat, 1 if workers > 1 else 0)
                 out[name]["workers"] = workers
             os.killpg(p.pid, signal.SIGTERM)
-        out["note"] = ("loopback TCP, nzload with %d keep-alive connections replaying the C2 log; TTFB = request sent -> first response byte; "
+        out["note"] = ("loopback TCP, nzload with %d keep-alive connections replaying the C2 log; TTFB = request sent -> first response byte (ttfbody: first BODY byte; nzproxy sends the header before asking the GPU for the first window); "
                        "cpu_* is the nginx-restated server (oracle/nz_cpu_server.c), not nginx" % nconn)
     except Exception as e:      # the HTTP section must never take the kernel-level numbers down with it
         out["error"] = repr(e)

@@ -185,6 +185,13 @@ int32_t nz_get_stats(nz_ctx* ctx, nz_stats* out);
 /* record per-kernel CUDA events in every wave so nz_ticket_*_ms work (off by default: each
  * event record costs host time on the latency path) */
 int32_t nz_set_profiling(nz_ctx* ctx, int32_t on);
+/* Waves whose destinations are all pinned host memory (a front end streaming bodies to sockets):
+ * bound what they offer the PCIe link.  total_gbs > 0 paces the non-urgent ones so that together they
+ * stay near that rate (shared between the waves in flight); ctas > 0 sets how many CTAs such a wave
+ * runs on.  A saturated link keeps ~150-300 us of posted writes queued ahead of every later wave; kept
+ * just below saturation, a first window (NZ_GET_URGENT) still completes in ~40-60 us.
+ * 0 / 0 restores the defaults (unpaced, 32 CTAs): maximum throughput, the bench's e2e mode. */
+int32_t nz_set_host_rate(nz_ctx* ctx, double total_gbs, int32_t ctas);
 
 /* ---- cross-shard objects (the one exchange step) ---------------- */
 /* An object larger than one stripe is striped round-robin over the shards; the owner of

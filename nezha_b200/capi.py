@@ -26,7 +26,7 @@ SYMBOLS = [
     "nz_buf_alloc", "nz_buf_wrap_device", "nz_buf_ptr", "nz_buf_devptr", "nz_buf_size", "nz_buf_free", "nz_buf_read", "nz_buf_write",
     "nz_put_begin", "nz_put_write", "nz_put_sync", "nz_put_write_device", "nz_put_file", "nz_put_commit", "nz_put_abort",
     "nz_evict", "nz_lookup", "nz_get_submit", "nz_get_wait", "nz_get_poll", "nz_ticket_elapsed_ms",
-    "nz_ticket_gather_ms", "nz_ticket_inflate_ms", "nz_ticket_free", "nz_get_stats", "nz_set_profiling", "nz_crc32c_device", "nz_debug_poke", "nz_shard_of",
+    "nz_ticket_gather_ms", "nz_ticket_inflate_ms", "nz_ticket_free", "nz_get_stats", "nz_set_profiling", "nz_set_host_rate", "nz_crc32c_device", "nz_debug_poke", "nz_shard_of",
     "nz_arena_ipc_export", "nz_peer_attach", "nz_extent_location", "nz_put_striped", "nz_crc32c_combine",
 ]
 
@@ -131,6 +131,7 @@ def load() -> C.CDLL:
     L.nz_debug_poke.argtypes = [vp, u8p, C.c_uint64, C.c_uint8]
     L.nz_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.nz_set_profiling.argtypes = [vp, C.c_int32]
+    L.nz_set_host_rate.argtypes = [vp, C.c_double, C.c_int32]
     L.nz_crc32c_device.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_uint32), vp]
     L.nz_arena_ipc_export.argtypes = [vp, u8p, C.POINTER(C.c_uint64)]
     L.nz_peer_attach.argtypes = [vp, C.c_uint32, u8p]

@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -129,7 +130,9 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
             CKI(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi));
             c->hi_streams.push_back(s);
         }
-        if (const char* ev = getenv("NZ_HOST_GRID")) c->host_grid = atoi(ev) > 0 ? atoi(ev) : c->host_grid;
+        if (const char* ev = getenv("NZ_HOST_GRID")) c->host_grid = atoi(ev) > 0 ? atoi(ev) : c->host_grid.load();
+        if (const char* ev = getenv("NZ_HOST_RATE_GBS")) c->host_rate_gbs = atof(ev);
+        if (const char* ev = getenv("NZ_HOST_VARIANT")) { const int v = atoi(ev); if (v < nz_gather_num_variants()) c->host_variant = v; }
     }
     CKI(cudaMalloc(&c->peer_base_dev, sizeof(uint64_t) * c->cfg.shard_count));
     CKI(cudaMemset(c->peer_base_dev, 0, sizeof(uint64_t) * c->cfg.shard_count));
@@ -777,10 +780,12 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
         hres[i].status = NZ_ECUDA; hres[i].flags = 0; hres[i].bytes = 0; hres[i].length = 0; hres[i].crc32c = 0; hres[i].reserved = 0;
     }
 
+    // waves that only write pinned host memory may use their own gather variant (write-through stores)
+    const int variant = (all_host && c->host_variant >= 0) ? c->host_variant : c->gather_variant;
     // upper bound on gather tiles when every slice length is known on the host (0 = unknown)
     uint64_t tile_bound = 0;
     {
-        const uint64_t tb = nz_gather_tile_bytes(c->gather_variant);
+        const uint64_t tb = nz_gather_tile_bytes(variant);
         bool known = true;
         for (uint32_t i = 0; i < (uint32_t)nseg && known; ++i) {
             if (hseg[i].len == 0 && hreq[hseg[i].req].whole) known = false;
@@ -815,9 +820,9 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     a.ver_stat = reinterpret_cast<uint32_t*>(a.res + n);
     t->ver_stat = reinterpret_cast<uint32_t*>(hres + n);
     t->ver_stat[0] = t->ver_stat[1] = 0;
-    a.fuse_verify = (any_verify && ver_cap && c->fuse_verify && nz_gather_fuses_verify(c->gather_variant)) ? 1u : 0u;
+    a.fuse_verify = (any_verify && ver_cap && c->fuse_verify && nz_gather_fuses_verify(variant)) ? 1u : 0u;
     a.peer_base = c->peer_base_dev;
-    a.tile_bytes = nz_gather_tile_bytes(c->gather_variant);
+    a.tile_bytes = nz_gather_tile_bytes(variant);
 
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream
                      : any_urgent ? c->hi_streams[c->rr.fetch_add(1) % c->hi_streams.size()]
@@ -827,7 +832,15 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
 #define CKT(call) do { e = (call); if (e != cudaSuccess) { int32_t rc = cuda_fail(e, #call); nz_ticket_free(t); return rc; } } while (0)
     t->profiled = c->profile;
     if (t->profiled) CKT(cudaEventRecord(t->ev_start, s));
-    CKT(nz_launch_plan(a, s));
+    if (n <= NZ_SMALL_WAVE && nseg <= NZ_SMALL_WAVE) {
+        NzSmallWave sw;
+        memset(&sw, 0, sizeof sw);
+        memcpy(sw.reqs, hreq, n * sizeof(NzDevReq));
+        memcpy(sw.segs, hseg, (size_t)nseg * sizeof(NzDevSeg));
+        CKT(nz_launch_plan(a, s, &sw));
+    } else {
+        CKT(nz_launch_plan(a, s));
+    }
     c->launches += a.ver_cap ? 2 : 1;
     t->ran_inflate = any_inflate;
     if (any_inflate) {
@@ -840,8 +853,16 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     int ggrid = c->gather_grid;
     if (tile_bound && tile_bound < (uint64_t)ggrid) ggrid = (int)tile_bound;   // small waves: no more CTAs than tiles
     if (all_host && ggrid > c->host_grid) ggrid = c->host_grid;  // PCIe-bound wave: a few SMs saturate the link
-    if (a.fuse_verify) CKT(nz_launch_gather(c->gather_variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s, a.seg_ver, a.ver, c->crc_tables));
-    else CKT(nz_launch_gather(c->gather_variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s));
+    // paced host waves: each of the wave's CTAs issues one tile per pace_ns (urgent waves are never paced)
+    uint32_t pace_ns = 0;
+    const double total_rate = c->host_rate_gbs.load();
+    if (all_host && !any_urgent && total_rate > 0 && ggrid > 0) {
+        const int sharing = c->paced_inflight.fetch_add(1) + 1;          // this wave and the paced ones still in flight
+        t->paced = true;
+        pace_ns = (uint32_t)std::min(1e6, (double)a.tile_bytes * ggrid * sharing / total_rate);      // bytes / (GB/s) = ns
+    }
+    if (a.fuse_verify) CKT(nz_launch_gather(variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s, a.seg_ver, a.ver, c->crc_tables, pace_ns));
+    else CKT(nz_launch_gather(variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s, nullptr, nullptr, nullptr, pace_ns));
     if (t->profiled) CKT(cudaEventRecord(t->ev_g1, s));
     c->launches += 1;
     if (any_verify && ver_cap) {
@@ -874,7 +895,11 @@ int32_t nz_get_wait(nz_ticket* t, int64_t timeout_us, nz_get_res* res) {
             cudaError_t e = cudaEventQuery(t->ev_done);
             if (e == cudaSuccess) break;
             if (e != cudaErrorNotReady) return cuda_fail(e, "cudaEventQuery");
-            if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) { CK(cudaEventSynchronize(t->ev_done)); break; }
+            // long wave: sleep between polls (a blocking cudaEventSynchronize was measured to return ~300 us late)
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) {
+                struct timespec ts = {0, 20000};
+                nanosleep(&ts, nullptr);
+            }
         }
     } else {
         const auto t0 = std::chrono::steady_clock::now();
@@ -898,6 +923,7 @@ int32_t nz_get_wait(nz_ticket* t, int64_t timeout_us, nz_get_res* res) {
         else if (hres[i].status == NZ_ENOTFOUND) ++misses;
         else if (hres[i].status == NZ_ECORRUPT) ++corrupt;
     }
+    if (t->paced) { t->paced = false; c->paced_inflight--; }
     if (!t->req_bytes_hint) {   // count a wave once even if waited twice
         t->req_bytes_hint = 1;
         c->gets += t->n; c->get_bytes += bytes; c->hits += hits; c->misses += misses; c->corrupt += corrupt;
@@ -934,11 +960,19 @@ int32_t nz_ticket_free(nz_ticket* t) {
     nz_ctx* c = t->ctx;
     cudaSetDevice(c->device);
     cudaEventSynchronize(t->ev_done);   // never recycle buffers a kernel may still read
+    if (t->paced) { t->paced = false; c->paced_inflight--; }
     t->req_bytes_hint = 0;
     t->stream = nullptr;
     std::lock_guard<std::mutex> g(c->tmu);
     if (c->ticket_pool.size() < 64) c->ticket_pool.push_back(t);
     else ticket_destroy(t);
+    return NZ_OK;
+}
+
+int32_t nz_set_host_rate(nz_ctx* c, double total_gbs, int32_t ctas) {
+    if (!c || total_gbs < 0 || ctas < 0) return NZ_EINVAL;
+    c->host_rate_gbs = total_gbs;
+    c->host_grid = ctas > 0 ? ctas : 32;
     return NZ_OK;
 }
 

@@ -60,6 +60,13 @@ struct __align__(8) NzDevSeg {
     uint32_t req;
     uint32_t pad;
 };
+// Descriptors of a small wave travel as kernel parameters (host -> device direction), so the plan
+// kernel does not start with a PCIe read that queues behind bulk waves' posted writes.
+constexpr uint32_t NZ_SMALL_WAVE = 4;
+struct NzSmallWave {
+    NzDevReq reqs[NZ_SMALL_WAVE];
+    NzDevSeg segs[NZ_SMALL_WAVE];
+};
 // Resolved copy work for the gather kernel.
 struct __align__(16) NzSegWork {
     uint64_t src;          // device address of first byte
@@ -155,6 +162,7 @@ struct nz_ticket {
     bool ran_inflate = false;
     bool own_stream = false;
     uint64_t req_bytes_hint = 0;
+    bool paced = false;                // counted in ctx->paced_inflight
     uint32_t* ver_stat = nullptr;      // pinned: {verify chunks emitted, of which checksummed inside the gather}
 };
 
@@ -195,7 +203,10 @@ struct nz_ctx {
     std::atomic<uint32_t> rr{0};
     cudaStream_t put_stream = nullptr;
     std::vector<cudaStream_t> hi_streams;   // highest priority: NZ_GET_URGENT waves
-    int host_grid = 32;                     // CTAs for waves that only write pinned host memory (PCIe bound: leave the SMs free)
+    std::atomic<double> host_rate_gbs{0};   // > 0: pace such waves to this many GB/s in total (nz_set_host_rate / env NZ_HOST_RATE_GBS; 0 = unpaced)
+    std::atomic<int> paced_inflight{0};     // paced waves submitted and not yet seen complete
+    int host_variant = -1;                  // gather variant for such waves (-1 = gather_variant); env NZ_HOST_VARIANT
+    std::atomic<int> host_grid{32};                     // CTAs for waves that only write pinned host memory (PCIe bound: leave the SMs free)
     // ticket recycling
     std::mutex tmu;
     std::vector<nz_ticket*> ticket_pool;
@@ -246,10 +257,11 @@ cudaError_t nz_launch_lookup(const NzSlot* table, uint64_t line_mask, const NzDe
 cudaError_t nz_launch_insert(NzSlot* table, uint64_t line_mask, uint64_t k0, uint64_t k1, uint32_t desc, uint64_t gen,
                              int32_t* status, cudaStream_t s);
 cudaError_t nz_launch_erase(NzSlot* table, uint64_t line_mask, uint64_t k0, uint64_t k1, int32_t* status, cudaStream_t s);
-cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s);
+cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s, const NzSmallWave* small = nullptr);
 cudaError_t nz_launch_gather(int variant, const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head,
                              const uint32_t* chain_next, uint32_t nseg, int grid, cudaStream_t s,
-                             const uint32_t* seg_ver = nullptr, NzVerWork* ver = nullptr, const uint32_t* crc_tables = nullptr);
+                             const uint32_t* seg_ver = nullptr, NzVerWork* ver = nullptr, const uint32_t* crc_tables = nullptr,
+                             uint32_t pace_ns = 0);
 bool nz_gather_fuses_verify(int variant);
 int nz_gather_num_variants();
 uint32_t nz_gather_tile_bytes(int variant);

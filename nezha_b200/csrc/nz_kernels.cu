@@ -169,8 +169,9 @@ struct PlanScratch {
     uint64_t* rq_len;   // n: its length
 };
 
+template <bool SMALL>
 __global__ void __launch_bounds__(1024, 1)
-k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint64_t* rq_ssz) {
+k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint64_t* rq_ssz, const __grid_constant__ NzSmallWave small) {
     __shared__ uint64_t s_scan[1024];
     __shared__ uint64_t s_carry;
     const uint32_t tid = threadIdx.x;
@@ -179,10 +180,11 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint6
     // ---- stage the wave's descriptors from mapped pinned memory into HBM: one coalesced PCIe
     // read instead of a round trip every time a later phase looks at a request or a slice -----
     {
-        const uint4* s4 = reinterpret_cast<const uint4*>(a.reqs_host);
+        // (a small wave carries them as kernel parameters instead: no PCIe read at all)
+        const uint4* s4 = SMALL ? reinterpret_cast<const uint4*>(small.reqs) : reinterpret_cast<const uint4*>(a.reqs_host);
         uint4* d4 = reinterpret_cast<uint4*>(a.reqs_dev);
         for (uint32_t i = tid; i < a.n * (uint32_t)(sizeof(NzDevReq) / 16); i += 1024) d4[i] = s4[i];
-        s4 = reinterpret_cast<const uint4*>(a.segs_host);
+        s4 = SMALL ? reinterpret_cast<const uint4*>(small.segs) : reinterpret_cast<const uint4*>(a.segs_host);
         d4 = reinterpret_cast<uint4*>(a.segs_dev);
         for (uint32_t i = tid; i < a.nseg * (uint32_t)(sizeof(NzDevSeg) / 16); i += 1024) d4[i] = s4[i];
         if (tid < 4) a.counters[tid] = 0;
@@ -472,6 +474,8 @@ __device__ __forceinline__ void stg_s(void* p, const uint4& v) {
         asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
     else if constexpr (HINT == 4)
         asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else if constexpr (HINT == 5)   // write-through: a store to system memory leaves L2 at once instead of waiting there as a dirty line
+        asm volatile("st.global.wt.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
     else
         asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -742,13 +746,18 @@ cudaError_t nz_launch_erase(NzSlot* table, uint64_t line_mask, uint64_t k0, uint
     k_erase<<<1, 32, 0, s>>>(table, line_mask, k0, k1, status);
     return cudaGetLastError();
 }
-cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s) {
+cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s, const NzSmallWave* small) {
     // rq_src / rq_len live right after the inflate work array (see nz_api.cu: device block layout)
     uint64_t* rq_src = reinterpret_cast<uint64_t*>(a.infl + a.n);
     uint64_t* rq_len = rq_src + a.n;
     uint64_t* rq_tab = rq_src + 3 * (size_t)a.n;     // [rq_src | rq_len | infl_meta | rq_tab | rq_ssz]
     uint64_t* rq_ssz = rq_src + 4 * (size_t)a.n;
-    k_plan<<<1, 1024, 0, s>>>(a, rq_src, rq_len, rq_tab, rq_ssz);
+    if (small) {
+        k_plan<true><<<1, 1024, 0, s>>>(a, rq_src, rq_len, rq_tab, rq_ssz, *small);
+    } else {
+        static const NzSmallWave none = {};
+        k_plan<false><<<1, 1024, 0, s>>>(a, rq_src, rq_len, rq_tab, rq_ssz, none);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (a.ver_cap) {
@@ -839,7 +848,7 @@ template <int STAGES, bool AHEAD, bool VERIFY>
 __global__ void __launch_bounds__(VERIFY ? NZ_TMA_VTHREADS : NZ_TMA_THREADS)
 k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_begin, const uint32_t* __restrict__ chain_head,
              const uint32_t* __restrict__ chain_next, uint32_t nseg, uint32_t tile_bytes, const uint32_t* __restrict__ seg_ver,
-             NzVerWork* ver, const uint32_t* __restrict__ crc_tables) {
+             NzVerWork* ver, const uint32_t* __restrict__ crc_tables, uint32_t pace_ns) {
     static_assert(!(AHEAD && VERIFY), "fused verify uses the simple pipeline");
     extern __shared__ __align__(128) uint8_t s_buf[];          // STAGES x tile_bytes [ | 32 KiB stride table when VERIFY ]
     __shared__ __align__(8) uint64_t s_bar[STAGES];
@@ -868,6 +877,10 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
     dc.head = 0xFFFFFFFFu;
     uint32_t phase_bits = 0;                                   // bit s = parity to wait for on stage s
     uint32_t slot = 0;
+    // pacing (waves that write pinned host memory): this CTA issues at most one tile per pace_ns, so the wave
+    // offers the PCIe link a bounded rate and the posted-write queue ahead of latency-critical waves stays short
+    uint64_t pace_next = 0;
+    if (pace_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pace_next));
     // the engine tile whose load is in flight and whose stores are still to be issued (thread 0 only)
     bool p_valid = false;
     uint32_t p_slot = 0, p_bulk = 0, p_head = 0xFFFFFFFFu;
@@ -916,6 +929,15 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
                 if (vbase != 0xFFFFFFFFu) tile_verify(vc, s, s, n, vbase, c0ptr);   // short tile of an engine slice: lines are L2-hot
             }
             continue;
+        }
+        if (pace_ns && tid == 0) {
+            uint64_t now;
+            for (;;) {
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (now >= pace_next) break;
+                __nanosleep(100);
+            }
+            pace_next = (now - pace_next > 8ull * pace_ns ? now : pace_next) + pace_ns;     // no burst after a stall
         }
         if constexpr (VERIFY) {
             // simple pipeline, every thread follows the barrier phases: load -> (all wait) -> stores -> checksum from shared memory
@@ -995,6 +1017,7 @@ struct TmaArgs {
     const NzSegWork* work; const uint64_t* tile_begin; const uint32_t* chain_head; const uint32_t* chain_next;
     uint32_t nseg; int grid; cudaStream_t s; int* occ;
     const uint32_t* seg_ver; NzVerWork* ver; const uint32_t* crc_tables;
+    uint32_t pace_ns;
 };
 template <int STAGES, bool AHEAD, bool VERIFY>
 static cudaError_t launch_tma(const TmaArgs& a) {
@@ -1024,7 +1047,7 @@ static cudaError_t launch_tma(const TmaArgs& a) {
     int grid = a.grid;
     if (VERIFY && dev >= 0 && dev < 64 && max_grid[dev] > 0 && grid > max_grid[dev]) grid = max_grid[dev];
     k_gather_tma<STAGES, AHEAD, VERIFY><<<grid, NTH, smem, a.s>>>(a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, t.tile,
-                                                                              a.seg_ver, a.ver, a.crc_tables);
+                                                                              a.seg_ver, a.ver, a.crc_tables, a.pace_ns);
     return cudaGetLastError();
 }
 static cudaError_t dispatch_tma(const TmaArgs& a) {
@@ -1068,6 +1091,7 @@ static const GatherVariant kGatherVariants[] = {
     {256, 4, 6, 3},   // 12: plain stores, 6 CTAs/SM
     {512, 8, 1, 3},   // 13: plain stores, 64 KiB tiles
     {128, 16, 3, 0},  // 14: TMA bulk-copy staging (k_gather_tma); nt*u*16 = 32 KiB tile
+    {256, 8, 2, 5},   // 15: st.global.wt (write-through) - for waves whose destinations are all pinned host memory
 };
 constexpr int kNumGatherVariants = (int)(sizeof(kGatherVariants) / sizeof(kGatherVariants[0]));
 
@@ -1105,20 +1129,21 @@ static int occ_gather_t() {
     case 11: return F<256, 8, 2, 4>(__VA_ARGS__);                 \
     case 12: return F<256, 4, 6, 3>(__VA_ARGS__);                 \
     case 13: return F<512, 8, 1, 3>(__VA_ARGS__);                 \
+    case 15: return F<256, 8, 2, 5>(__VA_ARGS__);                 \
     default: return F<256, 8, 2, 0>(__VA_ARGS__);                 \
     }
 
 bool nz_gather_fuses_verify(int variant) { return variant == 14; }
 cudaError_t nz_launch_gather(int variant, const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head,
                              const uint32_t* chain_next, uint32_t nseg, int grid, cudaStream_t s,
-                             const uint32_t* seg_ver, NzVerWork* ver, const uint32_t* crc_tables) {
-    if (variant == 14) return dispatch_tma(TmaArgs{work, tile_begin, chain_head, chain_next, nseg, grid, s, nullptr, seg_ver, ver, crc_tables});
+                             const uint32_t* seg_ver, NzVerWork* ver, const uint32_t* crc_tables, uint32_t pace_ns) {
+    if (variant == 14) return dispatch_tma(TmaArgs{work, tile_begin, chain_head, chain_next, nseg, grid, s, nullptr, seg_ver, ver, crc_tables, pace_ns});
     NZ_GV_SWITCH(variant, launch_gather_t, work, tile_begin, chain_head, chain_next, nseg, grid, s)
 }
 int nz_gather_blocks_per_sm(int variant) {
     if (variant == 14) {
         int nb = 1;
-        dispatch_tma(TmaArgs{nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, &nb, nullptr, nullptr, nullptr});
+        dispatch_tma(TmaArgs{nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, &nb, nullptr, nullptr, nullptr, 0});
         return nb;
     }
     NZ_GV_SWITCH(variant, occ_gather_t)

@@ -1,7 +1,7 @@
 // nezha_b200/host/nzload.cc — HTTP load generator for the cached-GET metric.
 //
 // Measures what BASELINE.json's metric names at the wire: payload GB/s and time to first
-// byte of cached GETs, the same way against the GPU proxy (nzproxy) and the nginx-restated
+// byte (ttfb: first byte of the response; ttfbody: first byte of the BODY) of cached GETs, the same way against the GPU proxy (nzproxy) and the nginx-restated
 // CPU server.  One thread per connection (= one in-flight GET per connection, like the
 // reference's wget clients, /root/reference/examples/demo/kubeflow-test.yaml:20-22);
 // keep-alive; bodies are read and discarded.
@@ -35,7 +35,7 @@ static std::atomic<int> g_ready{0};
 static std::atomic<bool> g_go{false};
 static std::atomic<uint64_t> g_bytes{0}, g_reqs{0}, g_errors{0}, g_s2xx{0}, g_sother{0};
 static std::mutex g_mu;
-static std::vector<double> g_ttfb_us;
+static std::vector<double> g_ttfb_us, g_ttfbody_us;
 
 static int dial(const std::string& ip, int port) {
     int fd = socket(AF_INET, SOCK_STREAM, 0);
@@ -53,7 +53,7 @@ static int dial(const std::string& ip, int port) {
 }
 
 // one GET on an open connection; returns body bytes or -1; *ttfb_us gets the first-byte latency
-static int64_t one_get(int fd, const Req& r, std::vector<char>& buf, double* ttfb_us, int* status) {
+static int64_t one_get(int fd, const Req& r, std::vector<char>& buf, double* ttfb_us, int* status, double* ttfbody_us) {
     std::string q = "GET " + r.path + " HTTP/1.1\r\nHost: " + r.host + "\r\n";
     if (r.range != "-") q += "Range: " + r.range + "\r\n";
     q += "Connection: keep-alive\r\n\r\n";
@@ -84,9 +84,12 @@ static int64_t one_get(int fd, const Req& r, std::vector<char>& buf, double* ttf
         if (p != std::string::npos) clen = atoll(lower.c_str() + p + 17);
     }
     int64_t got = (int64_t)(head.size() - (he + 4));
+    *ttfbody_us = -1.0;
+    if (got > 0 || clen == 0) *ttfbody_us = std::chrono::duration<double, std::micro>(Clock::now() - t0).count();
     while (got < clen) {
         ssize_t n = recv(fd, buf.data(), (size_t)std::min<int64_t>((int64_t)buf.size(), clen - got), 0);
         if (n <= 0) return -1;
+        if (*ttfbody_us < 0) *ttfbody_us = std::chrono::duration<double, std::micro>(Clock::now() - t0).count();
         got += n;
     }
     return clen;
@@ -95,19 +98,19 @@ static int64_t one_get(int fd, const Req& r, std::vector<char>& buf, double* ttf
 static void client(std::string ip, int port, std::vector<Req> mine, int repeat, int warmup) {
     std::vector<char> buf(4 << 20);
     int fd = dial(ip, port);
-    std::vector<double> ttfb;
+    std::vector<double> ttfb, ttfbody;
     uint64_t bytes = 0, reqs = 0, errs = 0, ok2 = 0, oth = 0;
     auto run = [&](int rounds, bool count) {
         for (int k = 0; k < rounds; ++k)
             for (const Req& r : mine) {
                 if (fd < 0) fd = dial(ip, port);
                 if (fd < 0) { ++errs; continue; }
-                double t = 0;
+                double t = 0, tb = 0;
                 int st = 0;
-                const int64_t n = one_get(fd, r, buf, &t, &st);
+                const int64_t n = one_get(fd, r, buf, &t, &st, &tb);
                 if (n < 0) { close(fd); fd = -1; if (count) ++errs; continue; }
                 if (count) {
-                    bytes += (uint64_t)n; ++reqs; ttfb.push_back(t);
+                    bytes += (uint64_t)n; ++reqs; ttfb.push_back(t); ttfbody.push_back(tb);
                     if (st >= 200 && st < 300) ++ok2; else ++oth;
                 }
             }
@@ -120,6 +123,7 @@ static void client(std::string ip, int port, std::vector<Req> mine, int repeat, 
     g_bytes += bytes; g_reqs += reqs; g_errors += errs; g_s2xx += ok2; g_sother += oth;
     std::lock_guard<std::mutex> g(g_mu);
     g_ttfb_us.insert(g_ttfb_us.end(), ttfb.begin(), ttfb.end());
+    g_ttfbody_us.insert(g_ttfbody_us.end(), ttfbody.begin(), ttfbody.end());
 }
 
 int main(int argc, char** argv) {
@@ -157,11 +161,14 @@ int main(int argc, char** argv) {
     for (auto& t : th) t.join();
     const double secs = std::chrono::duration<double>(Clock::now() - t0).count();
     std::sort(g_ttfb_us.begin(), g_ttfb_us.end());
+    std::sort(g_ttfbody_us.begin(), g_ttfbody_us.end());
     auto pct = [&](double p) { return g_ttfb_us.empty() ? 0.0 : g_ttfb_us[std::min(g_ttfb_us.size() - 1, (size_t)(p * g_ttfb_us.size()))]; };
+    auto pctb = [&](double p) { return g_ttfbody_us.empty() ? 0.0 : g_ttfbody_us[std::min(g_ttfbody_us.size() - 1, (size_t)(p * g_ttfbody_us.size()))]; };
     printf("{\"bytes\": %llu, \"seconds\": %.6f, \"gbs\": %.4f, \"requests\": %llu, \"errors\": %llu, \"status_2xx\": %llu, \"status_other\": %llu, "
-           "\"conns\": %d, \"ttfb_us_p50\": %.1f, \"ttfb_us_p90\": %.1f, \"ttfb_us_p99\": %.1f, \"ttfb_us_min\": %.1f}\n",
+           "\"conns\": %d, \"ttfb_us_p50\": %.1f, \"ttfb_us_p90\": %.1f, \"ttfb_us_p99\": %.1f, \"ttfb_us_min\": %.1f, "
+           "\"ttfbody_us_p50\": %.1f, \"ttfbody_us_p90\": %.1f, \"ttfbody_us_p99\": %.1f}\n",
            (unsigned long long)g_bytes.load(), secs, g_bytes.load() / secs / 1e9, (unsigned long long)g_reqs.load(),
            (unsigned long long)g_errors.load(), (unsigned long long)g_s2xx.load(), (unsigned long long)g_sother.load(), conns, pct(0.5),
-           pct(0.9), pct(0.99), g_ttfb_us.empty() ? 0.0 : g_ttfb_us.front());
+           pct(0.9), pct(0.99), g_ttfb_us.empty() ? 0.0 : g_ttfb_us.front(), pctb(0.5), pctb(0.9), pctb(0.99));
     return 0;
 }

@@ -20,6 +20,7 @@
 #include <netinet/in.h>
 #include <netinet/tcp.h>
 #include <signal.h>
+#include <sys/prctl.h>
 #include <sys/socket.h>
 #include <sys/time.h>
 #include <unistd.h>
@@ -55,6 +56,9 @@ struct Options {
     uint64_t arena_bytes = 8ull << 30;
     uint32_t max_objects = 1u << 16;
     uint64_t window_bytes = 4ull << 20;
+    double host_rate_gbs = 38.0;            // all bulk windows together stay just under PCIe saturation (first windows then see a short queue)
+    bool early_header = true;               // --early-header 0: header goes out with the first body bytes (one segment)
+    int host_ctas = 2;                      // CTAs per wave of windows: two saturate the link already
     uint64_t first_window = 64ull << 10;    // small first window keeps time-to-first-byte low (then x8 per window)
     int max_conns = 512;
     bool gunzip = false;
@@ -530,7 +534,17 @@ struct WaveItem {
     nz_get_res rs;
     int32_t rc = NZ_ECUDA;
     std::atomic<int> done{0};
+    int64_t t_push = 0, t_done = 0;        // ns (steady clock), NZ_PROXY_TRACE only
 };
+
+// NZ_PROXY_TRACE=1: where a window's latency goes (queue -> submit -> device -> wake-up), printed once a second
+static bool g_trace = false;
+inline int64_t now_ns() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+struct LaneTrace {
+    std::atomic<uint64_t> items{0}, waves{0}, queue_ns{0}, submit_ns{0}, device_ns{0}, wake_ns{0}, bytes{0}, gpu_ns{0};
+};
+static LaneTrace g_tr[2];                  // 0 = urgent, 1 = bulk
+static std::atomic<uint64_t> g_first_ns{0}, g_first_n{0};   // request parsed -> first body window written to the socket
 
 struct Combiner {
     nz_ctx* ctx = nullptr;                         // shard 0 (also owns the pinned windows)
@@ -545,7 +559,9 @@ struct Combiner {
 
     std::atomic<int> pending{0};
     int spin_us = 0;
+    int lane = 1;                           // trace slot
     void push(WaveItem* it) {
+        if (g_trace) it->t_push = now_ns();
         { std::lock_guard<std::mutex> g(mu); q.push_back(it); pending.store(1, std::memory_order_release); }
         cv.notify_one();
     }
@@ -591,9 +607,21 @@ struct Combiner {
             res.resize(batch.size());
             for (size_t i = 0; i < batch.size(); ++i) { reqs[i] = batch[i]->rq; reqs[i].segs = &batch[i]->sg; }
             nz_ticket* t = nullptr;
+            const int64_t t_take = g_trace ? now_ns() : 0;
             int32_t rc = nz_get_submit(ctx, reqs.data(), (uint32_t)reqs.size(), nullptr, &t);
+            const int64_t t_sub = g_trace ? now_ns() : 0;
             if (rc == NZ_OK) rc = nz_get_wait(t, -1, res.data());
+            const int64_t t_dn = g_trace ? now_ns() : 0;
+            float gpu_ms = 0.f;
+            if (g_trace && t && nz_ticket_elapsed_ms(t, &gpu_ms) != NZ_OK) gpu_ms = 0.f;     // needs NZ_PROFILE=1
             if (t) nz_ticket_free(t);
+            if (g_trace) {
+                g_tr[lane].gpu_ns += (uint64_t)(gpu_ms * 1e6) * batch.size();
+                LaneTrace& T = g_tr[lane];
+                T.waves++; T.items += batch.size();
+                T.submit_ns += (uint64_t)(t_sub - t_take) * batch.size(); T.device_ns += (uint64_t)(t_dn - t_sub) * batch.size();
+                for (WaveItem* it : batch) { T.queue_ns += (uint64_t)(t_take - it->t_push); T.bytes += it->sg.len; it->t_done = t_dn; }
+            }
             for (size_t i = 0; i < batch.size(); ++i) {
                 batch[i]->rc = rc;
                 if (rc == NZ_OK) batch[i]->rs = res[i];
@@ -605,9 +633,12 @@ struct Combiner {
 };
 
 static std::vector<std::unique_ptr<Combiner>> g_urgent, g_bulk;   // one pair of lanes per GPU
+static std::atomic<int> g_direct{0};          // first windows being submitted straight from connection threads
+static int g_direct_max = 2;                  // env NZ_PROXY_DIRECT (0 = always through the urgent combiner)
+static std::atomic<uint64_t> g_direct_ns{0}, g_direct_n{0};
 
 // ---- serving -------------------------------------------------------------------
-bool send_plan(Server& S, int fd, const nzh::Plan& plan, const Entry* ent, bool keep_alive, nz_buf* win[2]) {
+bool send_plan(Server& S, int fd, const nzh::Plan& plan, const Entry* ent, bool keep_alive, nz_buf* win[2], int64_t t_req = 0) {
     std::string h = std::string("HTTP/1.1 ") + std::to_string(plan.status) + " " + status_text(plan.status) + "\r\nServer: nginx\r\nDate: " +
                     http_date(time(nullptr)) + "\r\n";
     for (const auto& kv : plan.headers) h += kv.first + ": " + kv.second + "\r\n";
@@ -626,6 +657,12 @@ bool send_plan(Server& S, int fd, const nzh::Plan& plan, const Entry* ent, bool 
         bool live[2] = {false, false};
         int cur = 0;
         uint64_t ramp = S.opt.first_window;
+        // status line + headers (+ a multipart preamble) are known from host-side metadata: they leave before the
+        // first window is even requested from the GPU, like a proxy forwarding upstream headers as they arrive
+        if (first && !pending.empty() && S.opt.early_header) {
+            if (!write_all(fd, pending.data(), pending.size())) return false;
+            pending.clear();
+        }
         auto submit = [&](int slot) {
             live[slot] = false;
             if (!left) return;
@@ -641,7 +678,21 @@ bool send_plan(Server& S, int fd, const nzh::Plan& plan, const Entry* ent, bool 
             it.done.store(0, std::memory_order_relaxed);
             {
                 const uint32_t sh = nz_shard_of(ent->key128, (uint32_t)S.ctxs.size());
-                (first ? g_urgent[sh] : g_bulk[sh])->push(&it);
+                // first window, urgent lane quiet: submit from this thread (no queue hop, no wake-up); a burst of
+                // simultaneous requests still goes through the combiner and becomes one wave
+                if (first && g_direct_max > 0 && g_direct.fetch_add(1) < g_direct_max) {
+                    const int64_t t0 = g_trace ? now_ns() : 0;
+                    nz_ticket* t = nullptr;
+                    it.rc = nz_get_submit(S.ctxs[sh], &it.rq, 1, nullptr, &t);
+                    if (it.rc == NZ_OK) it.rc = nz_get_wait(t, -1, &it.rs);
+                    if (t) nz_ticket_free(t);
+                    g_direct--;
+                    it.done.store(1, std::memory_order_release);
+                    if (g_trace) { it.t_done = now_ns(); g_direct_ns += (uint64_t)(it.t_done - t0); g_direct_n++; }
+                } else {
+                    if (first && g_direct_max > 0) g_direct--;
+                    (first ? g_urgent[sh] : g_bulk[sh])->push(&it);
+                }
             }
             first = false;
             live[slot] = true;
@@ -652,11 +703,13 @@ bool send_plan(Server& S, int fd, const nzh::Plan& plan, const Entry* ent, bool 
         while (live[cur]) {
             submit(cur ^ 1);                                                  // next window in flight while this one is sent
             Combiner::wait(&item[cur]);
+            if (g_trace) g_tr[(item[cur].rq.flags & NZ_GET_URGENT) ? 0 : 1].wake_ns += (uint64_t)(now_ns() - item[cur].t_done);
             live[cur] = false;
             bool ok = item[cur].rc == NZ_OK && item[cur].rs.status == NZ_OK;
             if (!ok) fprintf(stderr, "nzproxy: window failed: submit/wait rc=%d (%s) status=%d [%s]\n", item[cur].rc, nz_strerror(item[cur].rc), item[cur].rs.status, nz_last_error());
             if (ok && !pending.empty()) { ok = write_all(fd, pending.data(), pending.size()); pending.clear(); }
             if (ok) ok = write_all(fd, nz_buf_ptr(win[cur]), item[cur].sg.len);
+            if (g_trace && t_req && (item[cur].rq.flags & NZ_GET_URGENT)) { g_first_ns += (uint64_t)(now_ns() - t_req); g_first_n++; }
             if (!ok) {
                 if (live[cur ^ 1]) Combiner::wait(&item[cur ^ 1]);            // never leave a queued item pointing at this stack frame
                 return false;                                                 // mid-body failure: drop the connection
@@ -696,6 +749,7 @@ void serve_connection(Server* Sp, int fd, std::string client_ip) {
         if (!alive) break;
         const std::string head = inbuf.substr(0, end + 2);
         inbuf.erase(0, end + 4);
+        const int64_t t_req = g_trace ? now_ns() : 0;
         Parsed pr = parse_head(head);
         nzh::Plan plan;
         std::shared_ptr<Entry> ent;
@@ -753,7 +807,7 @@ void serve_connection(Server* Sp, int fd, std::string client_ip) {
             }
         }
         if (pr.ok && pr.rq.http_minor < 1) keep = false;
-        const bool sent = send_plan(S, fd, plan, ent.get(), keep, win);
+        const bool sent = send_plan(S, fd, plan, ent.get(), keep, win, t_req);
         if (ent) ent->inflight--;
         if (!sent) break;
         if (!keep) break;
@@ -769,7 +823,7 @@ void serve_connection(Server* Sp, int fd, std::string client_ip) {
 
 void usage() {
     fprintf(stderr,
-            "nzproxy [--listen ip:port] [--device N | --devices 0,1,..] [--arena-gib G] [--max-objects N] [--window-mib M] [--first-window-kib K]\n"
+            "nzproxy [--listen ip:port] [--device N | --devices 0,1,..] [--arena-gib G] [--max-objects N] [--window-mib M] [--first-window-kib K] [--host-rate-gbs R] [--host-ctas N]\n"
             "        [--max-conns N] [--gunzip] [--verify] [--upstream proxy_host=ip:port]... [--pv DIR] [--inactive-s S] [--valid-s S]\n");
 }
 
@@ -801,6 +855,9 @@ int main(int argc, char** argv) {
         else if (a == "--max-objects") S.opt.max_objects = (uint32_t)atoi(next());
         else if (a == "--window-mib") S.opt.window_bytes = (uint64_t)(atof(next()) * (1ull << 20));
         else if (a == "--first-window-kib") S.opt.first_window = (uint64_t)atoll(next()) << 10;
+        else if (a == "--host-rate-gbs") S.opt.host_rate_gbs = atof(next());
+        else if (a == "--host-ctas") S.opt.host_ctas = atoi(next());
+        else if (a == "--early-header") S.opt.early_header = atoi(next()) != 0;
         else if (a == "--max-conns") S.opt.max_conns = atoi(next());
         else if (a == "--gunzip") S.opt.gunzip = true;
         else if (a == "--pv") S.opt.pv_dir = next();
@@ -831,6 +888,7 @@ int main(int argc, char** argv) {
             fprintf(stderr, "nzproxy: nz_init(device %d) failed: %s (%s) - there is no CPU fallback\n", cfg.device, nz_strerror(rc), nz_last_error());
             return 1;
         }
+        if (!getenv("NZ_HOST_RATE_GBS") && !getenv("NZ_HOST_GRID")) nz_set_host_rate(cx, S.opt.host_rate_gbs, S.opt.host_ctas);
         S.ctxs.push_back(cx);
     }
     S.ctx = S.ctxs[0];
@@ -843,16 +901,45 @@ int main(int argc, char** argv) {
     std::thread([&S] { for (;;) { std::this_thread::sleep_for(std::chrono::seconds(S.opt.inactive_s < 120 ? 1 : 60)); cache_manager_pass(S, false); } }).detach();
     for (nz_ctx* cx : S.ctxs) {
         auto u = std::make_unique<Combiner>();
-        u->ctx = cx; u->cap_bytes = 16ull << 20; u->linger_us = 0; u->spin_us = 2000;
+        u->ctx = cx; u->cap_bytes = 16ull << 20; u->linger_us = 0; u->spin_us = 2000; u->lane = 0;
         auto k = std::make_unique<Combiner>();
-        k->ctx = cx; k->cap_bytes = 128ull << 20; k->linger_us = 20;
+        k->ctx = cx; k->cap_bytes = 16ull << 20; k->linger_us = 20;
+        if (const char* e = getenv("NZ_PROXY_BULK_CAP_MIB")) k->cap_bytes = (uint64_t)std::max(1, atoi(e)) << 20;
         Combiner* up = u.get();
         Combiner* kp = k.get();
         g_urgent.push_back(std::move(u));
         g_bulk.push_back(std::move(k));
-        for (int i = 0; i < 2; ++i) std::thread([up] { up->run(); }).detach();
-        for (int i = 0; i < 3; ++i) std::thread([kp] { kp->run(); }).detach();
+        int n_urgent = 2;
+        if (const char* e = getenv("NZ_PROXY_URGENT_THREADS")) n_urgent = std::max(1, atoi(e));
+        for (int i = 0; i < n_urgent; ++i) std::thread([up] { up->run(); }).detach();
+        int n_bulk = 2;
+        if (const char* e = getenv("NZ_PROXY_BULK_THREADS")) n_bulk = std::max(1, atoi(e));
+        for (int i = 0; i < n_bulk; ++i) std::thread([kp] { kp->run(); }).detach();
     }
+    if (const char* e = getenv("NZ_PROXY_TRACE")) g_trace = atoi(e) != 0;
+    if (const char* e = getenv("NZ_PROXY_DIRECT")) g_direct_max = atoi(e);
+    prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0);      // 1 us: the library's sleep-polling of long waves stays precise (inherited by threads)
+    if (g_trace)
+        std::thread([] {
+            uint64_t last = 0;
+            for (;;) {
+                std::this_thread::sleep_for(std::chrono::seconds(1));
+                const uint64_t tot = g_tr[0].items + g_tr[1].items;
+                if (tot == last) continue;
+                last = tot;
+                for (int l = 0; l < 2; ++l) {
+                    LaneTrace& T = g_tr[l];
+                    const double n = (double)std::max<uint64_t>(1, T.items.load());
+                    fprintf(stderr, "nzproxy trace %s: %llu windows in %llu waves (%.1f MiB/wave)  mean us: queue %.1f  submit %.1f  submit->done %.1f (on the GPU %.1f)  wake %.1f\n",
+                            l ? "bulk  " : "urgent", (unsigned long long)T.items.load(), (unsigned long long)T.waves.load(),
+                            T.bytes.load() / 1048576.0 / (double)std::max<uint64_t>(1, T.waves.load()), T.queue_ns / n / 1e3, T.submit_ns / n / 1e3,
+                            T.device_ns / n / 1e3, T.gpu_ns / n / 1e3, T.wake_ns / n / 1e3);
+                }
+                fprintf(stderr, "nzproxy trace: request parsed -> first window on the socket: mean %.1f us over %llu responses; %llu first windows submitted directly (mean %.1f us)\n",
+                        g_first_ns / (double)std::max<uint64_t>(1, g_first_n.load()) / 1e3, (unsigned long long)g_first_n.load(),
+                        (unsigned long long)g_direct_n.load(), g_direct_ns / (double)std::max<uint64_t>(1, g_direct_n.load()) / 1e3);
+            }
+        }).detach();
     int ls = socket(AF_INET, SOCK_STREAM, 0);
     int one = 1;
     setsockopt(ls, SOL_SOCKET, SO_REUSEADDR, &one, sizeof one);

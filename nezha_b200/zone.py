@@ -306,6 +306,9 @@ class Zone:
     def set_profiling(self, on: bool = True):
         check(self.L.nz_set_profiling(self.ctx, 1 if on else 0), "nz_set_profiling")
 
+    def set_host_rate(self, total_gbs: float, ctas: int = 0) -> None:
+        check(self.L.nz_set_host_rate(self.ctx, float(total_gbs), int(ctas)), "nz_set_host_rate")
+
     def stats(self) -> capi.Stats:
         s = capi.Stats()
         check(self.L.nz_get_stats(self.ctx, C.byref(s)), "nz_get_stats")
