@@ -402,3 +402,45 @@ def test_probe_chains_collisions_and_full_table():
             b.free()
     finally:
         z.close()
+
+
+def test_paced_host_waves_same_bytes_bounded_rate():
+    """nz_set_host_rate: waves that only write pinned host memory are paced under the PCIe link rate (so a
+    first window behind them sees a short queue); the bytes are the same, urgent waves are never paced,
+    device destinations are never paced, and 0/0 restores the defaults."""
+    import time
+    z = nz.Zone(device=0, arena_bytes=512 << 20, max_objects=16)
+    n = 96 << 20
+    d = wl.synth_bytes(n, seed=4242)
+    key = K(0, "pace")
+    z.put(key, d)
+    wins = [z.alloc_host(8 << 20) for _ in range(12)]
+    gets = [nz.Get(key, w, [(i * (8 << 20), 8 << 20, 0)]) for i, w in enumerate(wins)]
+
+    def wave(gs):
+        t0 = time.perf_counter()
+        t = z.submit(gs)
+        res = t.wait()
+        dt = time.perf_counter() - t0
+        t.free()
+        assert all(r.status == capi.NZ_OK for r in res)
+        return dt
+
+    wave(gets)
+    fast = min(wave(gets) for _ in range(3))
+    z.set_host_rate(8.0, 2)                                  # 96 MiB at 8 GB/s: >= 12 ms
+    slow = min(wave(gets) for _ in range(3))
+    for i, w in enumerate(wins):
+        assert w.bytes(0, 8 << 20) == d[i * (8 << 20):(i + 1) * (8 << 20)].tobytes()
+    assert slow >= 0.8 * (n / 8e9), (fast, slow)
+    assert slow > 2 * fast, (fast, slow)
+    urgent = min(wave([nz.Get(key, w, [(i * (8 << 20), 8 << 20, 0)], capi.NZ_GET_URGENT) for i, w in enumerate(wins)]) for _ in range(3))
+    assert urgent < 0.6 * slow, (urgent, slow)
+    z.set_host_rate(0.0, 0)
+    again = min(wave(gets) for _ in range(3))
+    assert again < 0.6 * slow, (again, slow)
+    with pytest.raises(capi.NezhaError):
+        z.set_host_rate(-1.0, 0)
+    for w in wins:
+        w.free()
+    z.close()
