@@ -121,6 +121,7 @@ typedef struct nz_stats {
     uint64_t file_bounce_bytes; /* ... and through pread + pinned bounce buffers    */
     uint64_t verify_chunks;       /* 64 KiB chunks checked for NZ_GET_VERIFY (stored-byte GETs) */
     uint64_t verify_fused_chunks; /* ... of which the gather checksummed from its shared-memory copy (no second HBM read) */
+    uint64_t host_dma_waves;      /* waves to pinned host memory that went HBM staging slot -> copy engine (8 MiB .. 1 GiB, explicit slices) */
 } nz_stats;
 
 /* ---- lifecycle ----------------------------------------------------------- */
@@ -170,7 +171,9 @@ int32_t nz_lookup(nz_ctx* ctx, const uint8_t (*keys)[16], uint32_t n, nz_extent*
 /* One wave of GETs: probe + plan + range gather (+inflate, +verify) on the device.
  * Replaces the cache-file read loop + range filter.  `cuda_stream`
  * is a cudaStream_t to launch on, or NULL for the library's own stream pool.
- * Returns immediately; results via the ticket. */
+ * Returns immediately; results via the ticket.  A request whose status is not NZ_OK
+ * leaves its destination unspecified (large host-destination waves are staged in HBM
+ * and moved out by the copy engine whatever the per-request outcome). */
 int32_t nz_get_submit(nz_ctx* ctx, const nz_get_req* reqs, uint32_t n,
                       void* cuda_stream, nz_ticket** out);
 /* timeout_us < 0 waits forever; res (n entries) may be NULL */

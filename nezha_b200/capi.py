@@ -68,7 +68,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "objects", "arena_bytes", "arena_used", "table_slots", "table_live", "gets", "get_bytes", "hits",
         "misses", "puts", "put_bytes", "evictions", "corrupt", "kernel_launches", "file_cufile_bytes", "file_bounce_bytes",
-        "verify_chunks", "verify_fused_chunks")]
+        "verify_chunks", "verify_fused_chunks", "host_dma_waves")]
 
 
 class Stripe(C.Structure):

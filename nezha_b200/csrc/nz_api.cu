@@ -132,6 +132,7 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
         }
         if (const char* ev = getenv("NZ_HOST_GRID")) c->host_grid = atoi(ev) > 0 ? atoi(ev) : c->host_grid.load();
         if (const char* ev = getenv("NZ_HOST_RATE_GBS")) c->host_rate_gbs = atof(ev);
+        if (const char* ev = getenv("NZ_HOST_DMA")) c->host_dma = atoi(ev) != 0;
         if (const char* ev = getenv("NZ_HOST_VARIANT")) { const int v = atoi(ev); if (v < nz_gather_num_variants()) c->host_variant = v; }
     }
     CKI(cudaMalloc(&c->peer_base_dev, sizeof(uint64_t) * c->cfg.shard_count));
@@ -154,6 +155,7 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
     if (const char* ev = getenv("NZ_PROFILE")) c->profile = atoi(ev) != 0;
     if (const char* ev = getenv("NZ_FUSE_VERIFY")) c->fuse_verify = atoi(ev) != 0;
     c->gather_grid = c->sm_count * nz_gather_blocks_per_sm(c->gather_variant);
+    if (const char* ev = getenv("NZ_GATHER_CTAS_PER_SM")) { const int v = atoi(ev); if (v >= 1 && v <= 16) c->gather_grid = c->sm_count * v; }
     c->inflate_grid = c->sm_count * nz_inflate_blocks_per_sm();
     *out = c;
     return NZ_OK;
@@ -189,6 +191,7 @@ int32_t nz_shutdown(nz_ctx* c) {
     if (c->table) cudaFree(c->table);
     if (c->descs) cudaFree(c->descs);
     if (c->crc_tables) cudaFree(c->crc_tables);
+    for (auto& sl : c->stage) { if (sl.buf) cudaFree(sl.buf); if (sl.free_ev) cudaEventDestroy(sl.free_ev); }
     delete c;
     return NZ_OK;
 }
@@ -388,16 +391,21 @@ int32_t nz_put_file(nz_put* p, int fd, uint64_t file_off, uint64_t dst_off, uint
     c->file_bounce_bytes += len;
     std::lock_guard<std::mutex> g(c->put_mu);   // bounce buffers are shared
     // pread -> pinned bounce -> cudaMemcpyAsync.  One reader tops out at the page-cache copy rate
-    // (~10 GB/s), so large reads are split over NZ_BOUNCE_LANES reader threads, each with two pinned
+    // (~5-10 GB/s), so large reads are split over up to NZ_BOUNCE_LANES (12; env) reader threads, each with two pinned
     // 8 MiB buffers and its own stream: reads and H2D copies of all lanes overlap.
-    constexpr int NZ_BOUNCE_LANES = 4;
+    constexpr int NZ_BOUNCE_LANES_MAX = 16;
+    static const int NZ_BOUNCE_LANES = [] {
+        int v = 12;
+        if (const char* e = getenv("NZ_BOUNCE_LANES")) v = atoi(e);
+        return v < 1 ? 1 : v > NZ_BOUNCE_LANES_MAX ? NZ_BOUNCE_LANES_MAX : v;
+    }();
     constexpr size_t BUF = 8u << 20;
     if (!c->bounce[0]) {
         c->bounce_bytes = BUF * 2 * NZ_BOUNCE_LANES;
         CK(cudaHostAlloc(&c->bounce[0], c->bounce_bytes, cudaHostAllocPortable));
         c->bounce[1] = c->bounce[0];
     }
-    const int lanes = len >= (uint64_t)(4 * BUF) ? NZ_BOUNCE_LANES : 1;
+    const int lanes = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)NZ_BOUNCE_LANES, len / (2 * BUF)));   // >= 16 MiB per lane
     const uint64_t per = round_up((len + lanes - 1) / lanes, 4096);
     std::vector<int32_t> rcs(lanes, NZ_OK);
     std::vector<std::string> errs(lanes);
@@ -684,6 +692,26 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
         all_host &= r.dst->kind == NZ_BUF_PINNED_HOST;
     }
     if (nseg > 0x7fffffffull) return NZ_EINVAL;
+    // ---- staged D2H (see nz_ctx::stage): explicit slices only, unpaced, not latency critical, 8 MiB .. 1 GiB ----
+    struct DmaCopy { void* host; uint64_t off, len; };
+    std::vector<DmaCopy> dma_copies;
+    uint64_t dma_bytes = 0;
+    bool dma = all_host && c->host_dma && !any_urgent && !any_inflate && split.empty() && c->host_rate_gbs.load() <= 0;
+    if (dma) {
+        dma_copies.reserve(nseg);
+        for (uint32_t i = 0; i < n && dma; ++i) {
+            const nz_get_req& r = reqs[i];
+            if (r.nseg == 0 || !r.dst->host) { dma = false; break; }
+            const uint64_t cap = r.dst->size - r.dst_base;
+            for (uint32_t k = 0; k < r.nseg; ++k) {
+                const nz_seg& sg = r.segs[k];
+                if (sg.dst_off > cap || sg.len > cap - sg.dst_off) { dma = false; break; }     // the device path reports NZ_ERANGE
+                dma_copies.push_back(DmaCopy{(char*)r.dst->host + r.dst_base + sg.dst_off, dma_bytes, sg.len});
+                dma_bytes += round_up(sg.len, 256);
+            }
+        }
+        if (dma_bytes < (8ull << 20) || dma_bytes > (1ull << 30)) dma = false;
+    }
     // verify work bound + inflate scratch sizing come from the host shadow (metadata only; the
     // data path itself resolves keys on the device)
     uint64_t ver_cap = 0;
@@ -751,6 +779,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
         d.k0 = rd64(r.key); d.k1 = rd64(r.key + 8);
         d.dst = (uint64_t)(uintptr_t)r.dst->dev + r.dst_base;
         d.dst_cap = r.dst->size - r.dst_base;
+        if (dma) { d.dst = 0; d.dst_cap = dma_bytes; }          // + staging base, patched once the slot is known
         d.flags = r.flags;
         d.seg_begin = sb;
         const bool striped = !split.empty() && !split[i].empty();
@@ -774,6 +803,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
         } else {
             for (uint32_t k = 0; k < r.nseg; ++k, ++sb) {
                 hseg[sb].src_off = r.segs[k].src_off; hseg[sb].len = r.segs[k].len; hseg[sb].dst_off = r.segs[k].dst_off;
+                if (dma) hseg[sb].dst_off = dma_copies[sb].off;  // slices land back to back in the staging slot
                 hseg[sb].req = i; hseg[sb].pad = 0;
             }
         }
@@ -781,7 +811,8 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     }
 
     // waves that only write pinned host memory may use their own gather variant (write-through stores)
-    const int variant = (all_host && c->host_variant >= 0) ? c->host_variant : c->gather_variant;
+    const bool host_kernel = all_host && !dma;      // the gather kernel itself stores across PCIe
+    const int variant = (host_kernel && c->host_variant >= 0) ? c->host_variant : c->gather_variant;
     // upper bound on gather tiles when every slice length is known on the host (0 = unknown)
     uint64_t tile_bound = 0;
     {
@@ -831,6 +862,28 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     cudaError_t e;
 #define CKT(call) do { e = (call); if (e != cudaSuccess) { int32_t rc = cuda_fail(e, #call); nz_ticket_free(t); return rc; } } while (0)
     t->profiled = c->profile;
+    std::unique_lock<std::mutex> stage_lk;
+    nz_ctx::StageSlot* slot = nullptr;
+    if (dma) {                                   // staging slot: next in the ring, reuse ordered behind its previous wave's copies
+        stage_lk = std::unique_lock<std::mutex>(c->stage_mu);
+        slot = &c->stage[c->stage_next++ % 4];
+        if (!slot->free_ev) CKT(cudaEventCreateWithFlags(&slot->free_ev, cudaEventDisableTiming));
+        if (slot->cap < dma_bytes) {
+            if (slot->used) CKT(cudaEventSynchronize(slot->free_ev));
+            if (slot->buf) cudaFree(slot->buf);
+            slot->buf = nullptr; slot->cap = 0; slot->used = false;
+            const size_t cap = round_up((size_t)dma_bytes, (size_t)64 << 20);
+            if (cudaMalloc(&slot->buf, cap) != cudaSuccess) {
+                cudaGetLastError();
+                nz_ticket_free(t);
+                snprintf(tl_err, sizeof tl_err, "staging allocation of %zu bytes failed", cap);
+                return NZ_ENOMEM;
+            }
+            slot->cap = cap;
+        }
+        if (slot->used) CKT(cudaStreamWaitEvent(s, slot->free_ev, 0));
+        for (uint32_t i = 0; i < n; ++i) hreq[i].dst = (uint64_t)(uintptr_t)slot->buf;
+    }
     if (t->profiled) CKT(cudaEventRecord(t->ev_start, s));
     if (n <= NZ_SMALL_WAVE && nseg <= NZ_SMALL_WAVE) {
         NzSmallWave sw;
@@ -852,11 +905,11 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     if (t->profiled) CKT(cudaEventRecord(t->ev_g0, s));
     int ggrid = c->gather_grid;
     if (tile_bound && tile_bound < (uint64_t)ggrid) ggrid = (int)tile_bound;   // small waves: no more CTAs than tiles
-    if (all_host && ggrid > c->host_grid) ggrid = c->host_grid;  // PCIe-bound wave: a few SMs saturate the link
+    if (host_kernel && ggrid > c->host_grid) ggrid = c->host_grid;  // PCIe-bound wave: a few SMs saturate the link
     // paced host waves: each of the wave's CTAs issues one tile per pace_ns (urgent waves are never paced)
     uint32_t pace_ns = 0;
     const double total_rate = c->host_rate_gbs.load();
-    if (all_host && !any_urgent && total_rate > 0 && ggrid > 0) {
+    if (host_kernel && !any_urgent && total_rate > 0 && ggrid > 0) {
         const int sharing = c->paced_inflight.fetch_add(1) + 1;          // this wave and the paced ones still in flight
         t->paced = true;
         pace_ns = (uint32_t)std::min(1e6, (double)a.tile_bytes * ggrid * sharing / total_rate);      // bytes / (GB/s) = ns
@@ -869,6 +922,13 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
         int grid = (int)std::min<uint64_t>(ver_cap, (uint64_t)c->sm_count * 8);
         CKT(nz_launch_verify(a, c->crc_tables, grid, s));
         c->launches += 1;
+    }
+    if (dma) {                                   // copy engine: every slice from the staging slot to its pinned destination
+        for (const DmaCopy& cp : dma_copies)
+            if (cp.len) CKT(cudaMemcpyAsync(cp.host, (char*)slot->buf + cp.off, cp.len, cudaMemcpyDeviceToHost, s));
+        CKT(cudaEventRecord(slot->free_ev, s));
+        slot->used = true;
+        c->dma_waves++;
     }
     CKT(cudaEventRecord(t->ev_done, s));
 #undef CKT
@@ -1002,6 +1062,7 @@ int32_t nz_get_stats(nz_ctx* c, nz_stats* out) {
     out->file_bounce_bytes = c->file_bounce_bytes;
     out->verify_chunks = c->verify_chunks;
     out->verify_fused_chunks = c->verify_fused;
+    out->host_dma_waves = c->dma_waves;
     return NZ_OK;
 }
 

@@ -204,6 +204,14 @@ struct nz_ctx {
     cudaStream_t put_stream = nullptr;
     std::vector<cudaStream_t> hi_streams;   // highest priority: NZ_GET_URGENT waves
     std::atomic<double> host_rate_gbs{0};   // > 0: pace such waves to this many GB/s in total (nz_set_host_rate / env NZ_HOST_RATE_GBS; 0 = unpaced)
+    // staged D2H: large waves to pinned host memory gather into an HBM staging slot at HBM speed, then the copy engine
+    // moves every slice out (256 B TLPs: ~57 GB/s where SM stores reach ~52).  Ring of slots, reuse ordered by events.
+    struct StageSlot { void* buf = nullptr; size_t cap = 0; cudaEvent_t free_ev = nullptr; bool used = false; };
+    StageSlot stage[4];
+    uint32_t stage_next = 0;
+    std::mutex stage_mu;
+    bool host_dma = true;                   // env NZ_HOST_DMA=0: always store from the gather kernel
+    std::atomic<uint64_t> dma_waves{0};
     std::atomic<int> paced_inflight{0};     // paced waves submitted and not yet seen complete
     int host_variant = -1;                  // gather variant for such waves (-1 = gather_variant); env NZ_HOST_VARIANT
     std::atomic<int> host_grid{32};                     // CTAs for waves that only write pinned host memory (PCIe bound: leave the SMs free)

@@ -40,7 +40,7 @@ def test_strerror_and_shard_of():
 def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(capi.Config) == 40 and C.sizeof(capi.Extent) == 40 and C.sizeof(capi.Seg) == 24
-    assert C.sizeof(capi.GetReq) == 48 and C.sizeof(capi.GetRes) == 32 and C.sizeof(capi.Stats) == 18 * 8
+    assert C.sizeof(capi.GetReq) == 48 and C.sizeof(capi.GetRes) == 32 and C.sizeof(capi.Stats) == 19 * 8
 
 
 def test_no_cpu_fallback():
