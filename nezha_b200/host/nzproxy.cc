@@ -11,8 +11,8 @@
 // (proxy_cache_valid 200 1d, nginx.conf:57), then served like a hit.
 //
 // Threading: one thread per connection (cap --max-conns), blocking sockets; the GPU library is
-// thread safe.  Not here (out of scope this round): TLS upstream (GCS vhost), expiry/inactive
-// eviction timers, access log.
+// thread safe.  TLS upstream for the GCS vhost (nginx.conf:113) with nginx's defaults (no verify, no SNI).  Not here:
+// the access log.
 #include <arpa/inet.h>
 #include <errno.h>
 #include <fcntl.h>
@@ -20,6 +20,8 @@
 #include <netinet/in.h>
 #include <netinet/tcp.h>
 #include <signal.h>
+#include <openssl/evp.h>
+#include <openssl/ssl.h>
 #include <sys/prctl.h>
 #include <sys/socket.h>
 #include <sys/time.h>
@@ -57,6 +59,7 @@ struct Options {
     uint32_t max_objects = 1u << 16;
     uint64_t window_bytes = 4ull << 20;
     double host_rate_gbs = 38.0;            // all bulk windows together stay just under PCIe saturation (first windows then see a short queue)
+    bool proxy_ssl_server_name = false;     // nginx default: no SNI towards an https upstream
     bool early_header = true;               // --early-header 0: header goes out with the first body bytes (one segment)
     int host_ctas = 2;                      // CTAs per wave of windows: two saturate the link already
     uint64_t first_window = 64ull << 10;    // small first window keeps time-to-first-byte low (then x8 per window)
@@ -352,15 +355,80 @@ void cache_manager_pass(Server& S, bool need_room) {
     for (auto& e : victims) drop_entry(S, e);
 }
 
+// ---- upstream connection: plain TCP, or TLS for `proxy_pass https://...` (nginx.conf:113) ------------------
+// nginx's defaults for an https upstream are mirrored: no certificate verification (proxy_ssl_verify off) and no
+// SNI (proxy_ssl_server_name off) unless --proxy-ssl-server-name is given.
+struct UpConn {
+    int fd = -1;
+    SSL* ssl = nullptr;
+    bool write_all_(const void* p, size_t n) {
+        if (!ssl) return write_all(fd, p, n);
+        const char* c = static_cast<const char*>(p);
+        while (n) {
+            const int w = SSL_write(ssl, c, (int)std::min<size_t>(n, 1 << 30));
+            if (w <= 0) return false;
+            c += w; n -= (size_t)w;
+        }
+        return true;
+    }
+    ssize_t read_(void* p, size_t n) {
+        if (!ssl) return recv(fd, p, n, 0);
+        const int r = SSL_read(ssl, p, (int)std::min<size_t>(n, 1 << 30));
+        return r > 0 ? r : (SSL_get_error(ssl, r) == SSL_ERROR_ZERO_RETURN ? 0 : -1);
+    }
+    void close_() {
+        if (ssl) { SSL_shutdown(ssl); SSL_free(ssl); ssl = nullptr; }
+        if (fd >= 0) { close(fd); fd = -1; }
+    }
+};
+SSL_CTX* upstream_tls_ctx() {
+    static SSL_CTX* ctx = [] {
+        SSL_CTX* c = SSL_CTX_new(TLS_client_method());
+        if (c) SSL_CTX_set_verify(c, SSL_VERIFY_NONE, nullptr);
+        return c;
+    }();
+    return ctx;
+}
+bool b64_decode(const std::string& in, std::vector<uint8_t>& out) {
+    static const std::string tb = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+    uint32_t acc = 0;
+    int bits = 0;
+    out.clear();
+    for (char ch : in) {
+        if (ch == '=') break;
+        const size_t v = tb.find(ch);
+        if (v == std::string::npos) return false;
+        acc = (acc << 6) | (uint32_t)v;
+        bits += 6;
+        if (bits >= 8) { bits -= 8; out.push_back((uint8_t)(acc >> bits)); }
+    }
+    return true;
+}
+
 // returns HTTP status to relay (200 = admitted and indexed); fills `out` on 200
 int fill_from_origin(Server& S, int vhost, const std::string& host, const std::string& target, const std::string& client_ip,
                      const uint8_t key128[16], std::shared_ptr<Entry>& out) {
     const nzh::VHost& vh = S.cfg.vhosts[vhost];
     auto it = S.opt.upstream.find(vh.proxy_host);
-    if (vh.upstream_tls && it == S.opt.upstream.end()) return 502;   // https upstream needs an override this round
-    const std::string addr = it != S.opt.upstream.end() ? it->second : vh.proxy_host;
-    int fd = connect_to(addr, 80);
-    if (fd < 0) return 502;
+    // --upstream host=ip:port keeps the vhost's scheme out of it (tests: plain origin); host=https://ip:port or no override
+    // on an https vhost means TLS
+    std::string addr = it != S.opt.upstream.end() ? it->second : vh.proxy_host;
+    bool tls = it == S.opt.upstream.end() ? vh.upstream_tls : false;
+    if (addr.rfind("https://", 0) == 0) { tls = true; addr = addr.substr(8); }
+    else if (addr.rfind("http://", 0) == 0) { tls = false; addr = addr.substr(7); }
+    UpConn up;
+    up.fd = connect_to(addr, tls ? 443 : 80);
+    if (up.fd < 0) return 502;
+    if (tls) {
+        SSL_CTX* cx = upstream_tls_ctx();
+        up.ssl = cx ? SSL_new(cx) : nullptr;
+        if (!up.ssl) { up.close_(); return 502; }
+        SSL_set_fd(up.ssl, up.fd);
+        if (S.opt.proxy_ssl_server_name) SSL_set_tlsext_host_name(up.ssl, vh.proxy_host.substr(0, vh.proxy_host.find(':')).c_str());
+        if (SSL_connect(up.ssl) != 1) { up.close_(); return 502; }
+    }
+    const int fd = up.fd;
+    (void)fd;
     // nginx talks HTTP/1.0 to the upstream and strips Range/If-* when caching; nginx.conf:52-54 headers
     std::string uri = target;
     if (uri.rfind("http://", 0) == 0 || uri.rfind("https://", 0) == 0) {
@@ -369,26 +437,27 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
     }
     std::string req = "GET " + uri + " HTTP/1.0\r\nX-Real-IP: " + client_ip + "\r\nHost: " + host + "\r\nX-Forwarded-For: " + client_ip +
                       "\r\nConnection: close\r\n\r\n";
-    if (!write_all(fd, req.data(), req.size())) { close(fd); return 502; }
+    if (!up.write_all_(req.data(), req.size())) { up.close_(); return 502; }
     std::string head;
     std::vector<char> buf(1 << 16);
     size_t body_at = std::string::npos;
     while (body_at == std::string::npos) {
-        ssize_t r = recv(fd, buf.data(), buf.size(), 0);
-        if (r <= 0) { close(fd); return r == 0 ? 502 : 504; }
+        ssize_t r = up.read_(buf.data(), buf.size());
+        if (r <= 0) { up.close_(); return r == 0 ? 502 : 504; }
         head.append(buf.data(), (size_t)r);
         body_at = head.find("\r\n\r\n");
-        if (head.size() > (1 << 20)) { close(fd); return 502; }
+        if (head.size() > (1 << 20)) { up.close_(); return 502; }
     }
     std::string rest = head.substr(body_at + 4);
     head.resize(body_at + 2);
     int status = 0;
-    if (sscanf(head.c_str(), "HTTP/%*d.%*d %d", &status) != 1) { close(fd); return 502; }
+    if (sscanf(head.c_str(), "HTTP/%*d.%*d %d", &status) != 1) { up.close_(); return 502; }
     nzh::ObjectMeta meta;
     int64_t clen = -1;
     bool cacheable = status == 200;
     bool have_crc = false;
     uint32_t want_crc = 0;
+    std::vector<uint8_t> want_md5;                 // Content-MD5 (RFC 1864; Azure) or x-goog-hash: md5= (GCS): base64 of the body's MD5
     size_t pos = head.find("\r\n") + 2;
     while (pos < head.size()) {
         const size_t e = head.find("\r\n", pos);
@@ -403,7 +472,14 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
         else if (name == "etag") meta.etag = val;
         else if (name == "last-modified") meta.last_modified = val;
         else if (name == "content-encoding") { if (lower(val) == "gzip") meta.stored_gzip = true; else cacheable = false; }
-        else if (name == "x-goog-hash") {                                         // GCS: crc32c=<base64 of the big-endian u32>
+        else if (name == "content-md5") { std::vector<uint8_t> m; if (b64_decode(val, m) && m.size() == 16) want_md5 = m; }
+        else if (name == "x-goog-hash") {                                         // GCS: crc32c=<base64 of the big-endian u32>[, md5=<base64>]
+            const size_t m5 = val.find("md5=");
+            if (m5 != std::string::npos) {
+                std::vector<uint8_t> m;
+                const size_t e5 = val.find(',', m5);
+                if (b64_decode(val.substr(m5 + 4, e5 == std::string::npos ? std::string::npos : e5 - m5 - 4), m) && m.size() == 16) want_md5 = m;
+            }
             const size_t c32 = val.find("crc32c=");
             if (c32 != std::string::npos && val.size() >= c32 + 7 + 8) {
                 static const std::string tb = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
@@ -422,7 +498,7 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
         else if (name == "vary" && val == "*") cacheable = false;
         else if (name == "cache-control") { const std::string v = lower(val); if (v.find("no-cache") != std::string::npos || v.find("no-store") != std::string::npos || v.find("private") != std::string::npos) cacheable = false; }
     }
-    if (!cacheable || clen < 0) { close(fd); return status == 200 ? 502 : status; }   // uncached relays are not implemented: fail open to the client as 502
+    if (!cacheable || clen < 0) { up.close_(); return status == 200 ? 502 : status; }   // uncached relays are not implemented: fail open to the client as 502
     // stream the body into the arena through a pinned window
     nz_put* put = nullptr;
     int32_t prc = NZ_ENOMEM;
@@ -431,7 +507,7 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
         if (prc == NZ_ENOMEM) cache_manager_pass(S, true);
     }
     if (prc != NZ_OK) {
-        close(fd);
+        up.close_();
         return 502;
     }
     nz_buf* win = nullptr;
@@ -439,7 +515,7 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
         std::lock_guard<std::mutex> g(S.win_mu);
         if (!S.free_windows.empty()) { win = S.free_windows.back(); S.free_windows.pop_back(); }
     }
-    if (!win && nz_buf_alloc(S.ctx, S.opt.window_bytes, NZ_BUF_PINNED_HOST, &win) != NZ_OK) { nz_put_abort(put); close(fd); return 502; }
+    if (!win && nz_buf_alloc(S.ctx, S.opt.window_bytes, NZ_BUF_PINNED_HOST, &win) != NZ_OK) { nz_put_abort(put); up.close_(); return 502; }
     char* wp = static_cast<char*>(nz_buf_ptr(win));
     uint64_t off = 0;
     bool ok = true;
@@ -454,23 +530,33 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
     }
     size_t have = std::min<size_t>(rest.size(), (size_t)clen);
     if (have) memcpy(wp, rest.data(), have);
+    EVP_MD_CTX* md = nullptr;
+    if (!want_md5.empty()) { md = EVP_MD_CTX_new(); if (md && EVP_DigestInit_ex(md, EVP_md5(), nullptr) != 1) { EVP_MD_CTX_free(md); md = nullptr; } }
     while (ok && off < (uint64_t)clen) {
         while (have < S.opt.window_bytes && off + have < (uint64_t)clen) {
-            ssize_t r = recv(fd, wp + have, std::min<uint64_t>(S.opt.window_bytes - have, (uint64_t)clen - off - have), 0);
+            ssize_t r = up.read_(wp + have, std::min<uint64_t>(S.opt.window_bytes - have, (uint64_t)clen - off - have));
             if (r <= 0) { ok = false; break; }
             have += (size_t)r;
         }
         if (!ok) break;
+        if (md) EVP_DigestUpdate(md, wp, have);
         if (pv_fd >= 0 && !write_fd_all(pv_fd, wp, have)) { close(pv_fd); unlink(pv_tmp.c_str()); pv_fd = -1; }
         if (nz_put_write(put, wp, off, have) != NZ_OK) { ok = false; break; }
         if (nz_put_sync(put) != NZ_OK) { ok = false; break; }   // the window is reused: its H2D copy must have left it
         off += have;
         have = 0;
     }
-    close(fd);
+    up.close_();
     {
         std::lock_guard<std::mutex> g(S.win_mu);
         S.free_windows.push_back(win);
+    }
+    if (md) {                                                   // the origin's MD5 of the body must match what arrived
+        uint8_t dg[EVP_MAX_MD_SIZE];
+        unsigned dl = 0;
+        EVP_DigestFinal_ex(md, dg, &dl);
+        EVP_MD_CTX_free(md);
+        if (ok && (dl != 16 || memcmp(dg, want_md5.data(), 16) != 0)) ok = false;
     }
     if (!ok) { nz_put_abort(put); if (pv_fd >= 0) { close(pv_fd); unlink(pv_tmp.c_str()); } return 502; }
     uint32_t crc = 0;
@@ -824,7 +910,7 @@ void serve_connection(Server* Sp, int fd, std::string client_ip) {
 void usage() {
     fprintf(stderr,
             "nzproxy [--listen ip:port] [--device N | --devices 0,1,..] [--arena-gib G] [--max-objects N] [--window-mib M] [--first-window-kib K] [--host-rate-gbs R] [--host-ctas N]\n"
-            "        [--max-conns N] [--gunzip] [--verify] [--upstream proxy_host=ip:port]... [--pv DIR] [--inactive-s S] [--valid-s S]\n");
+            "        [--max-conns N] [--gunzip] [--verify] [--upstream proxy_host=[https://]ip:port]... [--proxy-ssl-server-name] [--pv DIR] [--inactive-s S] [--valid-s S]\n");
 }
 
 }  // namespace
@@ -858,6 +944,7 @@ int main(int argc, char** argv) {
         else if (a == "--host-rate-gbs") S.opt.host_rate_gbs = atof(next());
         else if (a == "--host-ctas") S.opt.host_ctas = atoi(next());
         else if (a == "--early-header") S.opt.early_header = atoi(next()) != 0;
+        else if (a == "--proxy-ssl-server-name") S.opt.proxy_ssl_server_name = true;
         else if (a == "--max-conns") S.opt.max_conns = atoi(next());
         else if (a == "--gunzip") S.opt.gunzip = true;
         else if (a == "--pv") S.opt.pv_dir = next();

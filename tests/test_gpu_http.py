@@ -362,3 +362,56 @@ def test_front_end_shards_across_two_gpus(policy_origin):
         assert all(PolicyOrigin.hits[k] == 1 for k in objs)
     finally:
         _stop(p)
+
+
+# ---- https upstream of the GCS vhost (nginx.conf:113) and the origins' MD5 validators ----
+def test_tls_upstream_and_md5_validators(policy_origin, tmp_path):
+    """`proxy_pass https://storage.googleapis.com`: the fill goes over TLS with nginx's defaults (no verification,
+    no SNI); Content-MD5 (Azure Blob, RFC 1864) and x-goog-hash md5= are checked against the bytes that arrived."""
+    import base64
+    import ssl
+    crt, key = tmp_path / "o.crt", tmp_path / "o.key"
+    r = subprocess.run(["openssl", "req", "-x509", "-newkey", "rsa:2048", "-nodes", "-days", "2", "-subj", "/CN=localhost",
+                        "-keyout", str(key), "-out", str(crt)], capture_output=True)
+    if r.returncode != 0:
+        pytest.skip("openssl CLI not usable here")
+    tport = free_port()
+    httpd = http.server.ThreadingHTTPServer(("127.0.0.1", tport), PolicyOrigin)
+    cx = ssl.SSLContext(ssl.PROTOCOL_TLS_SERVER)
+    cx.load_cert_chain(str(crt), str(key))
+    httpd.socket = cx.wrap_socket(httpd.socket, server_side=True)
+    threading.Thread(target=httpd.serve_forever, daemon=True).start()
+    obj = wl.synth_bytes(3_333_333, 90).tobytes()
+    md5_b64 = base64.b64encode(hashlib.md5(obj).digest()).decode()
+    wrong = base64.b64encode(hashlib.md5(obj + b"x").digest()).decode()
+    PolicyOrigin.objects["/tls/obj"] = (obj, {"x-goog-hash": "crc32c=" + o.crc32c_header(o.crc32c(obj)) + ",md5=" + md5_b64})
+    PolicyOrigin.objects["/tls/azure-ok"] = (obj, {"Content-MD5": md5_b64})
+    PolicyOrigin.objects["/tls/azure-bad"] = (obj, {"Content-MD5": wrong})
+    PolicyOrigin.objects["/tls/goog-md5-bad"] = (obj, {"x-goog-hash": "md5=" + wrong})
+    port = free_port()
+    log = open(os.path.join(ROOT, "gpurun_out", f"nzproxy_{port}.log"), "wb") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else subprocess.DEVNULL
+    p = subprocess.Popen([os.path.join(ROOT, "nezha_b200", "_build", "nzproxy"), "--listen", f"127.0.0.1:{port}", "--max-conns", "16", "--window-mib", "1",
+                          "--arena-gib", "0.5", "--upstream", f"storage.googleapis.com=https://127.0.0.1:{tport}",
+                          "--upstream", f"www.cs.toronto.edu=127.0.0.1:{policy_origin}"], start_new_session=True, stderr=log)
+    wait_port(port, 120)
+    try:
+        before = PolicyOrigin.hits.get("/tls/obj", 0)
+        for _ in range(2):
+            s, hd, b = fetch(port, "GET", "storage.googleapis.com", "/tls/obj", {})
+            assert s == 200 and b == obj
+        assert PolicyOrigin.hits["/tls/obj"] == before + 1                       # second GET is a hit from HBM
+        s, _, b = fetch(port, "GET", "storage.googleapis.com", "/tls/obj", {"Range": "bytes=1000000-1000099"})
+        assert s == 206 and b == obj[1000000:1000100]
+        s, _, b = fetch(port, "GET", "storage.googleapis.com", "/tls/azure-ok", {})
+        assert s == 200 and b == obj
+        for path in ("/tls/azure-bad", "/tls/goog-md5-bad"):
+            s1, _, _ = fetch(port, "GET", "storage.googleapis.com", path, {})
+            s2, _, _ = fetch(port, "GET", "storage.googleapis.com", path, {})
+            assert s1 == 502 and s2 == 502 and PolicyOrigin.hits[path] == 2      # never admitted
+        # a plain-http vhost next to it still works, and a TLS port spoken to in plain text fails closed (502)
+        PolicyOrigin.objects["/plain"] = (b"hello" * 1000, {})
+        s, _, b = fetch(port, "GET", "www.cs.toronto.edu", "/plain", {})
+        assert s == 200 and b == b"hello" * 1000
+    finally:
+        _stop(p)
+        httpd.shutdown()
