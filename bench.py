@@ -548,7 +548,7 @@ def http_bench(L_obj, requests, device, seed=2):
 
         # ---- GPU proxy ----
         p = subprocess.Popen([os.path.join(ROOT, "nezha_b200", "_build", "nzproxy"), "--listen", f"127.0.0.1:{gport}", "--device", str(device),
-                              "--arena-gib", str(L_obj / 2**30 + 0.5), "--max-conns", str(2 * nconn), "--window-mib", "4", "--first-window-kib", "64",
+                              "--arena-gib", str(L_obj / 2**30 + 0.5), "--max-conns", str(2 * nconn), "--window-mib", "4", "--first-window-kib", os.environ.get("NZ_BENCH_FIRST_KIB", "16"),
                               "--upstream", f"{host}=127.0.0.1:{oport}"], start_new_session=True,
                              stderr=open(os.environ["NZ_PROXY_LOG"], "w") if os.environ.get("NZ_PROXY_LOG") else subprocess.DEVNULL)
         procs.append(p)

@@ -62,7 +62,7 @@ struct Options {
     bool proxy_ssl_server_name = false;     // nginx default: no SNI towards an https upstream
     bool early_header = true;               // --early-header 0: header goes out with the first body bytes (one segment)
     int host_ctas = 2;                      // CTAs per wave of windows: two saturate the link already
-    uint64_t first_window = 64ull << 10;    // small first window keeps time-to-first-byte low (then x8 per window)
+    uint64_t first_window = 16ull << 10;    // small first window keeps time-to-first-byte low (then x8 per window)
     int max_conns = 512;
     bool gunzip = false;
     bool verify = false;
@@ -720,7 +720,7 @@ struct Combiner {
 
 static std::vector<std::unique_ptr<Combiner>> g_urgent, g_bulk;   // one pair of lanes per GPU
 static std::atomic<int> g_direct{0};          // first windows being submitted straight from connection threads
-static int g_direct_max = 2;                  // env NZ_PROXY_DIRECT (0 = always through the urgent combiner)
+static int g_direct_max = 4;                  // env NZ_PROXY_DIRECT (0 = always through the urgent combiner)
 static std::atomic<uint64_t> g_direct_ns{0}, g_direct_n{0};
 
 // ---- serving -------------------------------------------------------------------
