@@ -154,6 +154,7 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
     if (const char* ev = getenv("NZ_COALESCE")) c->coalesce = atoi(ev) != 0;
     if (const char* ev = getenv("NZ_PROFILE")) c->profile = atoi(ev) != 0;
     if (const char* ev = getenv("NZ_FUSE_VERIFY")) c->fuse_verify = atoi(ev) != 0;
+    if (const char* ev = getenv("NZ_FUSE_SMALL")) c->fuse_small = atoi(ev) != 0;
     c->gather_grid = c->sm_count * nz_gather_blocks_per_sm(c->gather_variant);
     if (const char* ev = getenv("NZ_GATHER_CTAS_PER_SM")) { const int v = atoi(ev); if (v >= 1 && v <= 16) c->gather_grid = c->sm_count * v; }
     c->inflate_grid = c->sm_count * nz_inflate_blocks_per_sm();
@@ -885,12 +886,16 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
         for (uint32_t i = 0; i < n; ++i) hreq[i].dst = (uint64_t)(uintptr_t)slot->buf;
     }
     if (t->profiled) CKT(cudaEventRecord(t->ev_start, s));
+    // a few small slices (a first window): the planning CTA copies them itself, one launch instead of two
+    const bool fused_small = c->fuse_small && n <= NZ_SMALL_WAVE && nseg <= NZ_SMALL_WAVE && !any_inflate && !any_verify && !dma &&
+                             tile_bound > 0 && tile_bound <= 16 && a.tile_bytes == 32768;
     if (n <= NZ_SMALL_WAVE && nseg <= NZ_SMALL_WAVE) {
         NzSmallWave sw;
         memset(&sw, 0, sizeof sw);
         memcpy(sw.reqs, hreq, n * sizeof(NzDevReq));
         memcpy(sw.segs, hseg, (size_t)nseg * sizeof(NzDevSeg));
-        CKT(nz_launch_plan(a, s, &sw));
+        if (fused_small) a.coalesce = 0;
+        CKT(nz_launch_plan(a, s, &sw, fused_small));
     } else {
         CKT(nz_launch_plan(a, s));
     }
@@ -914,10 +919,11 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
         t->paced = true;
         pace_ns = (uint32_t)std::min(1e6, (double)a.tile_bytes * ggrid * sharing / total_rate);      // bytes / (GB/s) = ns
     }
-    if (a.fuse_verify) CKT(nz_launch_gather(variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s, a.seg_ver, a.ver, c->crc_tables, pace_ns));
+    if (fused_small) { /* copied by the plan kernel */ }
+    else if (a.fuse_verify) CKT(nz_launch_gather(variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s, a.seg_ver, a.ver, c->crc_tables, pace_ns));
     else CKT(nz_launch_gather(variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s, nullptr, nullptr, nullptr, pace_ns));
     if (t->profiled) CKT(cudaEventRecord(t->ev_g1, s));
-    c->launches += 1;
+    c->launches += fused_small ? 0 : 1;
     if (any_verify && ver_cap) {
         int grid = (int)std::min<uint64_t>(ver_cap, (uint64_t)c->sm_count * 8);
         CKT(nz_launch_verify(a, c->crc_tables, grid, s));

@@ -183,6 +183,7 @@ struct nz_ctx {
     int sm_count;
     int gather_grid;       // persistent grid size for k_gather
     bool profile = false;   // record per-kernel CUDA events in every wave (nz_set_profiling / env NZ_PROFILE=1)
+    bool fuse_small = true;  // env NZ_FUSE_SMALL=0: small waves launch plan and gather separately
     bool fuse_verify = true; // env NZ_FUSE_VERIFY=0: NZ_GET_VERIFY re-reads every chunk in k_verify (A/B measurements)
     bool coalesce = true;   // env NZ_COALESCE=0 turns request coalescing off (A/B measurements)
     int gather_variant = 14; // k_gather variant: 14 = TMA bulk-copy staging (default, measured best); 0-13 register paths (env NZ_GATHER_VARIANT)
@@ -265,7 +266,7 @@ cudaError_t nz_launch_lookup(const NzSlot* table, uint64_t line_mask, const NzDe
 cudaError_t nz_launch_insert(NzSlot* table, uint64_t line_mask, uint64_t k0, uint64_t k1, uint32_t desc, uint64_t gen,
                              int32_t* status, cudaStream_t s);
 cudaError_t nz_launch_erase(NzSlot* table, uint64_t line_mask, uint64_t k0, uint64_t k1, int32_t* status, cudaStream_t s);
-cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s, const NzSmallWave* small = nullptr);
+cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s, const NzSmallWave* small = nullptr, bool fused_copy = false);
 cudaError_t nz_launch_gather(int variant, const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head,
                              const uint32_t* chain_next, uint32_t nseg, int grid, cudaStream_t s,
                              const uint32_t* seg_ver = nullptr, NzVerWork* ver = nullptr, const uint32_t* crc_tables = nullptr,

@@ -169,7 +169,10 @@ struct PlanScratch {
     uint64_t* rq_len;   // n: its length
 };
 
-template <bool SMALL>
+// small waves: the planning CTA copies the few tiles itself (defined after copy_tile)
+__device__ void plan_fused_copy(const NzPlanArgs& a);
+
+template <bool SMALL, bool FUSED>
 __global__ void __launch_bounds__(1024, 1)
 k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint64_t* rq_ssz, const __grid_constant__ NzSmallWave small) {
     __shared__ uint64_t s_scan[1024];
@@ -376,6 +379,10 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint6
         __syncthreads();
     }
     if (tid == 0) a.tile_begin[a.nseg] = s_carry;
+    if constexpr (FUSED) {
+        __syncthreads();                         // work[] and tile_begin[] of this CTA are visible to all its threads
+        plan_fused_copy(a);
+    }
 }
 
 // Verify work for stored (not inflated) bytes, emitted after coalescing is known: one warp per
@@ -583,6 +590,28 @@ __device__ __forceinline__ void copy_tile(const uint8_t* __restrict__ s, const D
 }
 
 // tile -> segment lookup shared by the gather variants (uniform across the CTA)
+// A wave of a few small slices (a response's first window): one launch instead of two.  The planning CTA's
+// 1024 threads move the tiles (32 KiB = 1024 x 2 x 16 B) right after planning them; no coalescing chains (the
+// host turns coalescing off for such waves), plain loads of what this kernel wrote itself.
+__device__ void plan_fused_copy(const NzPlanArgs& a) {
+    DstChain dc;
+    dc.work = a.work;
+    dc.next = a.chain_next;
+    dc.head = 0xFFFFFFFFu;
+    for (uint32_t s = 0; s < a.nseg; ++s) {
+        const NzSegWork w = a.work[s];
+        const uint64_t t0 = a.tile_begin[s], t1 = a.tile_begin[s + 1];
+        for (uint64_t t = t0; t < t1; ++t) {
+            int64_t lo = w.vstart + (int64_t)((t - t0) * a.tile_bytes), hi = lo + a.tile_bytes;
+            if (lo < 0) lo = 0;
+            if (hi > (int64_t)w.len) hi = (int64_t)w.len;
+            dc.d0 = reinterpret_cast<uint8_t*>(w.dst) + lo;
+            dc.lo = lo;
+            copy_tile<1024, 2, 0>(reinterpret_cast<const uint8_t*>(w.src) + lo, dc, (uint32_t)(hi - lo));
+        }
+    }
+}
+
 struct TileCursor {
     uint64_t lo_t = 0, hi_t = 0, src = 0, dst = 0, len = 0;
     int64_t vstart = 0;
@@ -746,17 +775,19 @@ cudaError_t nz_launch_erase(NzSlot* table, uint64_t line_mask, uint64_t k0, uint
     k_erase<<<1, 32, 0, s>>>(table, line_mask, k0, k1, status);
     return cudaGetLastError();
 }
-cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s, const NzSmallWave* small) {
+cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s, const NzSmallWave* small, bool fused_copy) {
     // rq_src / rq_len live right after the inflate work array (see nz_api.cu: device block layout)
     uint64_t* rq_src = reinterpret_cast<uint64_t*>(a.infl + a.n);
     uint64_t* rq_len = rq_src + a.n;
     uint64_t* rq_tab = rq_src + 3 * (size_t)a.n;     // [rq_src | rq_len | infl_meta | rq_tab | rq_ssz]
     uint64_t* rq_ssz = rq_src + 4 * (size_t)a.n;
-    if (small) {
-        k_plan<true><<<1, 1024, 0, s>>>(a, rq_src, rq_len, rq_tab, rq_ssz, *small);
+    if (small && fused_copy) {
+        k_plan<true, true><<<1, 1024, 0, s>>>(a, rq_src, rq_len, rq_tab, rq_ssz, *small);
+    } else if (small) {
+        k_plan<true, false><<<1, 1024, 0, s>>>(a, rq_src, rq_len, rq_tab, rq_ssz, *small);
     } else {
         static const NzSmallWave none = {};
-        k_plan<false><<<1, 1024, 0, s>>>(a, rq_src, rq_len, rq_tab, rq_ssz, none);
+        k_plan<false, false><<<1, 1024, 0, s>>>(a, rq_src, rq_len, rq_tab, rq_ssz, none);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
