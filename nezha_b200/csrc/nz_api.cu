@@ -740,7 +740,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
 
     const size_t pin_reqs = round_up((size_t)n * sizeof(NzDevReq), 256);
     const size_t pin_segs = round_up((size_t)nseg * sizeof(NzDevSeg), 256);
-    const size_t pin_res = round_up((size_t)n * sizeof(NzDevRes) + 16, 256);     // + {verify chunks, of which fused}
+    const size_t pin_res = round_up((size_t)n * sizeof(NzDevRes) + 32, 256);     // + {verify chunks, of which fused, completion flag}
     const size_t dev_work = round_up((size_t)nseg * sizeof(NzSegWork), 256);
     const size_t dev_tiles = round_up((size_t)(nseg + 1) * 8, 256);
     const size_t dev_chain = round_up((size_t)nseg * 8, 256);      // chain_head | chain_next (u32 each)
@@ -851,7 +851,8 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     }
     a.ver_stat = reinterpret_cast<uint32_t*>(a.res + n);
     t->ver_stat = reinterpret_cast<uint32_t*>(hres + n);
-    t->ver_stat[0] = t->ver_stat[1] = 0;
+    t->ver_stat[0] = t->ver_stat[1] = t->ver_stat[2] = 0;
+    t->flag_wait = false;
     a.fuse_verify = (any_verify && ver_cap && c->fuse_verify && nz_gather_fuses_verify(variant)) ? 1u : 0u;
     a.peer_base = c->peer_base_dev;
     a.tile_bytes = nz_gather_tile_bytes(variant);
@@ -894,7 +895,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
         memset(&sw, 0, sizeof sw);
         memcpy(sw.reqs, hreq, n * sizeof(NzDevReq));
         memcpy(sw.segs, hseg, (size_t)nseg * sizeof(NzDevSeg));
-        if (fused_small) a.coalesce = 0;
+        if (fused_small) { a.coalesce = 0; t->flag_wait = true; }
         CKT(nz_launch_plan(a, s, &sw, fused_small));
     } else {
         CKT(nz_launch_plan(a, s));
@@ -944,6 +945,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
 
 int32_t nz_get_poll(nz_ticket* t) {
     if (!t) return NZ_EINVAL;
+    if (t->flag_wait && t->ver_stat && *(volatile uint32_t*)(t->ver_stat + 2)) return NZ_OK;
     cudaError_t e = cudaEventQuery(t->ev_done);
     if (e == cudaSuccess) return NZ_OK;
     if (e == cudaErrorNotReady) return NZ_ETIMEOUT;
@@ -954,7 +956,22 @@ int32_t nz_get_wait(nz_ticket* t, int64_t timeout_us, nz_get_res* res) {
     if (!t) return NZ_EINVAL;
     nz_ctx* c = t->ctx;
     cudaSetDevice(c->device);
-    if (timeout_us < 0) {
+    if (t->flag_wait && t->ver_stat) {            // fused small wave: the kernel's last store is a flag in pinned memory
+        volatile uint32_t* flag = t->ver_stat + 2;
+        const auto t0 = std::chrono::steady_clock::now();
+        uint32_t spins = 0;
+        while (!*flag) {
+            __builtin_ia32_pause();
+            if ((++spins & 1023u) == 0) {
+                const auto us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+                if (us > 300 || (timeout_us >= 0 && us >= timeout_us)) break;      // long queue ahead (or an error): the event path decides
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    }
+    if (t->flag_wait && t->ver_stat && t->ver_stat[2]) {
+        // complete: results are in pinned memory already
+    } else if (timeout_us < 0) {
         // short waves finish in microseconds: poll first (a blocking sync costs an interrupt wake-up)
         const auto t0 = std::chrono::steady_clock::now();
         for (;;) {
@@ -1001,6 +1018,7 @@ int32_t nz_get_wait(nz_ticket* t, int64_t timeout_us, nz_get_res* res) {
 int32_t nz_ticket_elapsed_ms(nz_ticket* t, float* ms) {
     if (!t || !ms) return NZ_EINVAL;
     if (!t->profiled) return NZ_ENOSYS;      // nz_set_profiling(ctx, 1) first
+    CK(cudaEventSynchronize(t->ev_done));    // a flag-completed small wave may return before its last event has been timestamped
     CK(cudaEventElapsedTime(ms, t->ev_start, t->ev_done));
     return NZ_OK;
 }
@@ -1008,6 +1026,7 @@ int32_t nz_ticket_elapsed_ms(nz_ticket* t, float* ms) {
 int32_t nz_ticket_gather_ms(nz_ticket* t, float* ms) {
     if (!t || !ms) return NZ_EINVAL;
     if (!t->profiled) return NZ_ENOSYS;
+    CK(cudaEventSynchronize(t->ev_done));
     CK(cudaEventElapsedTime(ms, t->ev_g0, t->ev_g1));
     return NZ_OK;
 }

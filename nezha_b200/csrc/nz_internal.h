@@ -162,6 +162,7 @@ struct nz_ticket {
     bool ran_inflate = false;
     bool own_stream = false;
     uint64_t req_bytes_hint = 0;
+    bool flag_wait = false;            // fused small wave: completion is the pinned flag ver_stat[2], no event query needed
     bool paced = false;                // counted in ctx->paced_inflight
     uint32_t* ver_stat = nullptr;      // pinned: {verify chunks emitted, of which checksummed inside the gather}
 };
@@ -259,7 +260,8 @@ struct NzPlanArgs {
     uint32_t* rq_desc;          // n: descriptor index of every request (0xFFFFFFFF = miss), written in phase A
     uint32_t* seg_ver;          // nseg: first verify entry of a slice whose tiles are checksummed by the gather, else 0xFFFFFFFF
     uint32_t fuse_verify;       // 1 = the gather variant in use checksums tiles in shared memory
-    uint32_t* ver_stat;         // mapped pinned: [0] = verify chunks of this wave, [1] = of which fused (written by k_plan_verify)
+    uint32_t* ver_stat;         // mapped pinned: [0] = verify chunks of this wave, [1] = of which fused (written by k_plan_verify),
+                                // [2] = completion flag of a fused small wave (written last by k_plan, polled by nz_get_wait)
 };
 cudaError_t nz_launch_lookup(const NzSlot* table, uint64_t line_mask, const NzDesc* descs, const uint64_t* keys,
                              uint32_t n, nz_extent* out, cudaStream_t s);

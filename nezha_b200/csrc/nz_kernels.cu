@@ -382,6 +382,11 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint6
     if constexpr (FUSED) {
         __syncthreads();                         // work[] and tile_begin[] of this CTA are visible to all its threads
         plan_fused_copy(a);
+        // completion flag in pinned host memory: results and payload first (system-scope fence by every writer), then
+        // the flag - the host polls a cache line instead of querying an event
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) *reinterpret_cast<volatile uint32_t*>(a.ver_stat + 2) = 1u;
     }
 }
 
