@@ -889,7 +889,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     if (t->profiled) CKT(cudaEventRecord(t->ev_start, s));
     // a few small slices (a first window): the planning CTA copies them itself, one launch instead of two
     const bool fused_small = c->fuse_small && n <= NZ_SMALL_WAVE && nseg <= NZ_SMALL_WAVE && !any_inflate && !any_verify && !dma &&
-                             tile_bound > 0 && tile_bound <= 16 && a.tile_bytes == 32768;
+                             tile_bound > 0 && tile_bound <= 64 && a.tile_bytes == 32768;
     if (n <= NZ_SMALL_WAVE && nseg <= NZ_SMALL_WAVE) {
         NzSmallWave sw;
         memset(&sw, 0, sizeof sw);

@@ -62,7 +62,7 @@ struct __align__(8) NzDevSeg {
 };
 // Descriptors of a small wave travel as kernel parameters (host -> device direction), so the plan
 // kernel does not start with a PCIe read that queues behind bulk waves' posted writes.
-constexpr uint32_t NZ_SMALL_WAVE = 4;
+constexpr uint32_t NZ_SMALL_WAVE = 4;       // 4 x (64 + 32) B of kernel parameters (32 entries measured +1.3 us on every single-GET wave)
 struct NzSmallWave {
     NzDevReq reqs[NZ_SMALL_WAVE];
     NzDevSeg segs[NZ_SMALL_WAVE];
