@@ -875,11 +875,12 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
             if (slot->buf) cudaFree(slot->buf);
             slot->buf = nullptr; slot->cap = 0; slot->used = false;
             const size_t cap = round_up((size_t)dma_bytes, (size_t)64 << 20);
-            if (cudaMalloc(&slot->buf, cap) != cudaSuccess) {
-                cudaGetLastError();
+            if (cudaMalloc(&slot->buf, cap) != cudaSuccess) {      // HBM is full (arena sized to the device): no staging from now on,
+                cudaGetLastError();                                // this wave is rebuilt for the direct path
+                stage_lk.unlock();
                 nz_ticket_free(t);
-                snprintf(tl_err, sizeof tl_err, "staging allocation of %zu bytes failed", cap);
-                return NZ_ENOMEM;
+                c->host_dma = false;
+                return nz_get_submit(c, reqs, n, cuda_stream, out);
             }
             slot->cap = cap;
         }
