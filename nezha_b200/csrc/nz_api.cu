@@ -650,38 +650,85 @@ static nz_ticket* ticket_acquire(nz_ctx* c, size_t pin_need, size_t dev_need) {
     return t;
 }
 
+// K5: a GET of a striped object is split at stripe boundaries on the host (the shadow knows the stripe
+// size), so on the device every slice lies inside exactly one stripe.  `split` stays empty when the zone
+// holds no striped object; split[i] stays empty for requests of ordinary objects.
+static void split_striped_gets(nz_ctx* c, const nz_get_req* reqs, uint32_t n, std::vector<std::vector<nz_seg>>& split) {
+    if (c->n_striped.load() == 0) return;
+    split.resize(n);
+    std::lock_guard<std::mutex> g(c->mu);
+    for (uint32_t i = 0; i < n; ++i) {
+        const nz_get_req& r = reqs[i];
+        auto it = c->shadow.find({rd64(r.key), rd64(r.key + 8)});
+        if (it == c->shadow.end() || !it->second.stripe_bytes || it->second.desc == 0xFFFFFFFFu) continue;
+        const uint64_t S = it->second.stripe_bytes, L = it->second.stored_len;
+        nz_seg whole{0, L, 0};
+        const nz_seg* src = r.nseg ? r.segs : &whole;
+        const uint32_t cnt = r.nseg ? r.nseg : 1;
+        for (uint32_t k = 0; k < cnt; ++k) {
+            uint64_t off = src[k].src_off, len = src[k].len, dst = src[k].dst_off;
+            if (off > L || len > L - off) { split[i].clear(); split[i].push_back(src[k]); break; }   // device reports EINVAL
+            while (len) {
+                const uint64_t room = S - off % S, take = len < room ? len : room;
+                split[i].push_back(nz_seg{off, take, dst});
+                off += take; dst += take; len -= take;
+            }
+        }
+        if (split[i].empty()) split[i].push_back(nz_seg{0, 0, 0});   // empty object / zero-length request
+    }
+}
+
+// Staged D2H: one copy-engine transfer per slice, from its place in the staging slot to its pinned destination.
+// Returns false (direct stores from the gather kernel instead) when a request has no explicit slices, a slice does
+// not fit its destination (the device path reports NZ_ERANGE), or the wave is outside 8 MiB .. 1 GiB.
+struct DmaCopy { void* host; uint64_t off, len; };
+static bool plan_staged_copies(const nz_get_req* reqs, uint32_t n, uint64_t nseg, std::vector<DmaCopy>& copies, uint64_t& bytes) {
+    copies.reserve(nseg);
+    bytes = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const nz_get_req& r = reqs[i];
+        if (r.nseg == 0 || !r.dst->host) return false;
+        const uint64_t cap = r.dst->size - r.dst_base;
+        for (uint32_t k = 0; k < r.nseg; ++k) {
+            const nz_seg& sg = r.segs[k];
+            if (sg.dst_off > cap || sg.len > cap - sg.dst_off) return false;
+            copies.push_back(DmaCopy{(char*)r.dst->host + r.dst_base + sg.dst_off, bytes, sg.len});
+            bytes += round_up(sg.len, 256);
+        }
+    }
+    return bytes >= (8ull << 20) && bytes <= (1ull << 30);
+}
+
+// Verify work bound + inflate scratch sizing come from the host shadow (metadata only; the data path itself
+// resolves keys on the device).  scratch_need is empty when no request asks for inflate.
+static void size_verify_and_scratch(nz_ctx* c, const nz_get_req* reqs, uint32_t n, uint64_t& ver_cap, std::vector<uint64_t>& scratch_need) {
+    std::lock_guard<std::mutex> g(c->mu);
+    for (uint32_t i = 0; i < n; ++i) {
+        const nz_get_req& r = reqs[i];
+        if (!(r.flags & (NZ_GET_INFLATE | NZ_GET_VERIFY))) continue;
+        auto it = c->shadow.find({rd64(r.key), rd64(r.key + 8)});
+        if (it == c->shadow.end() || it->second.desc == 0xFFFFFFFFu) continue;
+        const NzHostObj& ho = it->second;
+        const bool inflate = (r.flags & NZ_GET_INFLATE) && (ho.flags & NZ_ENC_GZIP);
+        if (r.flags & NZ_GET_VERIFY) {
+            const uint64_t all = (ho.stored_len + NZ_CRC_CHUNK - 1) / NZ_CRC_CHUNK;
+            if (inflate || r.nseg == 0) ver_cap += all;
+            else for (uint32_t k = 0; k < r.nseg; ++k) ver_cap += std::min<uint64_t>(all, r.segs[k].len / NZ_CRC_CHUNK + 2);
+        }
+        // the LZ77 window is the output itself: it must live in HBM, so ranges and host
+        // destinations inflate into device scratch first and are then gathered out
+        if (inflate && !scratch_need.empty() && (r.nseg != 0 || r.dst->kind != NZ_BUF_DEVICE)) scratch_need[i] = ho.raw_len;
+    }
+}
+
 int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_stream, nz_ticket** out) {
     if (!c || !reqs || !n || !out) return NZ_EINVAL;
     CK(cudaSetDevice(c->device));
     // ---- host-side sizing ----
     uint64_t nseg = 0;
     bool any_inflate = false, any_verify = false, any_urgent = false, all_host = true;
-    // K5: a GET of a striped object is split at stripe boundaries here (the host knows the stripe
-    // size from its shadow), so on the device every slice lies inside exactly one stripe
     std::vector<std::vector<nz_seg>> split;
-    if (c->n_striped.load() > 0) {
-        split.resize(n);
-        std::lock_guard<std::mutex> g(c->mu);
-        for (uint32_t i = 0; i < n; ++i) {
-            const nz_get_req& r = reqs[i];
-            auto it = c->shadow.find({rd64(r.key), rd64(r.key + 8)});
-            if (it == c->shadow.end() || !it->second.stripe_bytes || it->second.desc == 0xFFFFFFFFu) continue;
-            const uint64_t S = it->second.stripe_bytes, L = it->second.stored_len;
-            nz_seg whole{0, L, 0};
-            const nz_seg* src = r.nseg ? r.segs : &whole;
-            const uint32_t cnt = r.nseg ? r.nseg : 1;
-            for (uint32_t k = 0; k < cnt; ++k) {
-                uint64_t off = src[k].src_off, len = src[k].len, dst = src[k].dst_off;
-                if (off > L || len > L - off) { split[i].clear(); split[i].push_back(src[k]); break; }   // device reports EINVAL
-                while (len) {
-                    const uint64_t room = S - off % S, take = len < room ? len : room;
-                    split[i].push_back(nz_seg{off, take, dst});
-                    off += take; dst += take; len -= take;
-                }
-            }
-            if (split[i].empty()) split[i].push_back(nz_seg{0, 0, 0});   // empty object / zero-length request
-        }
-    }
+    split_striped_gets(c, reqs, n, split);
     for (uint32_t i = 0; i < n; ++i) {
         const nz_get_req& r = reqs[i];
         if (!r.dst || (r.nseg && !r.segs) || r.dst_base > r.dst->size) return NZ_EINVAL;
@@ -694,48 +741,13 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     }
     if (nseg > 0x7fffffffull) return NZ_EINVAL;
     // ---- staged D2H (see nz_ctx::stage): explicit slices only, unpaced, not latency critical, 8 MiB .. 1 GiB ----
-    struct DmaCopy { void* host; uint64_t off, len; };
     std::vector<DmaCopy> dma_copies;
     uint64_t dma_bytes = 0;
-    bool dma = all_host && c->host_dma && !any_urgent && !any_inflate && split.empty() && c->host_rate_gbs.load() <= 0;
-    if (dma) {
-        dma_copies.reserve(nseg);
-        for (uint32_t i = 0; i < n && dma; ++i) {
-            const nz_get_req& r = reqs[i];
-            if (r.nseg == 0 || !r.dst->host) { dma = false; break; }
-            const uint64_t cap = r.dst->size - r.dst_base;
-            for (uint32_t k = 0; k < r.nseg; ++k) {
-                const nz_seg& sg = r.segs[k];
-                if (sg.dst_off > cap || sg.len > cap - sg.dst_off) { dma = false; break; }     // the device path reports NZ_ERANGE
-                dma_copies.push_back(DmaCopy{(char*)r.dst->host + r.dst_base + sg.dst_off, dma_bytes, sg.len});
-                dma_bytes += round_up(sg.len, 256);
-            }
-        }
-        if (dma_bytes < (8ull << 20) || dma_bytes > (1ull << 30)) dma = false;
-    }
-    // verify work bound + inflate scratch sizing come from the host shadow (metadata only; the
-    // data path itself resolves keys on the device)
+    const bool dma = all_host && c->host_dma && !any_urgent && !any_inflate && split.empty() && c->host_rate_gbs.load() <= 0 &&
+                     plan_staged_copies(reqs, n, nseg, dma_copies, dma_bytes);
     uint64_t ver_cap = 0;
     std::vector<uint64_t> scratch_need(any_inflate ? n : 0, 0);
-    if (any_inflate || any_verify) {
-        std::lock_guard<std::mutex> g(c->mu);
-        for (uint32_t i = 0; i < n; ++i) {
-            const nz_get_req& r = reqs[i];
-            if (!(r.flags & (NZ_GET_INFLATE | NZ_GET_VERIFY))) continue;
-            auto it = c->shadow.find({rd64(r.key), rd64(r.key + 8)});
-            if (it == c->shadow.end() || it->second.desc == 0xFFFFFFFFu) continue;
-            const NzHostObj& ho = it->second;
-            const bool inflate = (r.flags & NZ_GET_INFLATE) && (ho.flags & NZ_ENC_GZIP);
-            if (r.flags & NZ_GET_VERIFY) {
-                const uint64_t all = (ho.stored_len + NZ_CRC_CHUNK - 1) / NZ_CRC_CHUNK;
-                if (inflate || r.nseg == 0) ver_cap += all;
-                else for (uint32_t k = 0; k < r.nseg; ++k) ver_cap += std::min<uint64_t>(all, r.segs[k].len / NZ_CRC_CHUNK + 2);
-            }
-            // the LZ77 window is the output itself: it must live in HBM, so ranges and host
-            // destinations inflate into device scratch first and are then gathered out
-            if (inflate && (r.nseg != 0 || r.dst->kind != NZ_BUF_DEVICE)) scratch_need[i] = ho.raw_len;
-        }
-    }
+    if (any_inflate || any_verify) size_verify_and_scratch(c, reqs, n, ver_cap, scratch_need);
     if (ver_cap > 0xfffffff0ull) return NZ_EINVAL;
 
     const size_t pin_reqs = round_up((size_t)n * sizeof(NzDevReq), 256);
