@@ -11,8 +11,7 @@
 // (proxy_cache_valid 200 1d, nginx.conf:57), then served like a hit.
 //
 // Threading: one thread per connection (cap --max-conns), blocking sockets; the GPU library is
-// thread safe.  TLS upstream for the GCS vhost (nginx.conf:113) with nginx's defaults (no verify, no SNI).  Not here:
-// the access log.
+// thread safe.  TLS upstream for the GCS vhost (nginx.conf:113) with nginx's defaults (no verify, no SNI).  --access-log writes nginx's `main` format (nginx.conf:16-19).
 #include <arpa/inet.h>
 #include <errno.h>
 #include <fcntl.h>
@@ -59,6 +58,7 @@ struct Options {
     uint32_t max_objects = 1u << 16;
     uint64_t window_bytes = 4ull << 20;
     double host_rate_gbs = 38.0;            // all bulk windows together stay just under PCIe saturation (first windows then see a short queue)
+    std::string access_log;                 // --access-log PATH: one line per request, nginx's `main` format (nginx.conf:16-19)
     bool proxy_ssl_server_name = false;     // nginx default: no SNI towards an https upstream
     bool early_header = true;               // --early-header 0: header goes out with the first body bytes (one segment)
     int host_ctas = 2;                      // CTAs per wave of windows: two saturate the link already
@@ -104,6 +104,8 @@ struct Server {
     std::atomic<uint64_t> boundary{1};
     std::atomic<int> conns{0};
     std::atomic<uint64_t> hits{0}, misses{0}, bytes_out{0};
+    int log_fd = -1;
+    std::mutex log_mu;
 };
 
 bool write_all(int fd, const void* p, size_t n) {
@@ -149,6 +151,7 @@ struct Parsed {
     nzh::Request rq;
     bool keep_alive = true;
     bool ok = false;
+    std::string request_line, referer, user_agent, x_forwarded_for;   // access log only (nginx.conf:16-18)
 };
 
 std::string lower(std::string s) {
@@ -167,6 +170,7 @@ Parsed parse_head(const std::string& head) {
     size_t eol = head.find("\r\n");
     if (eol == std::string::npos) return p;
     const std::string line = head.substr(0, eol);
+    p.request_line = line;
     const size_t s1 = line.find(' ');
     if (s1 == std::string::npos) return p;
     const size_t s2 = line.find(' ', s1 + 1);
@@ -200,6 +204,9 @@ Parsed parse_head(const std::string& head) {
         else if (name == "if-modified-since") p.rq.if_modified_since = val;
         else if (name == "if-unmodified-since") p.rq.if_unmodified_since = val;
         else if (name == "accept-encoding") p.rq.accept_encoding = val;
+        else if (name == "referer") p.referer = val;
+        else if (name == "user-agent") p.user_agent = val;
+        else if (name == "x-forwarded-for") p.x_forwarded_for = val;
         else if (name == "connection") {
             const std::string v = lower(val);
             if (v.find("close") != std::string::npos) p.keep_alive = false;
@@ -808,6 +815,22 @@ bool send_plan(Server& S, int fd, const nzh::Plan& plan, const Entry* ent, bool 
     return true;
 }
 
+// access_log ... main (nginx.conf:16-19):
+//   $remote_addr - $remote_user [$time_local] "$request" $status $body_bytes_sent "$http_referer" "$http_user_agent" "$http_x_forwarded_for"
+void access_log_line(Server& S, const std::string& client_ip, const Parsed& pr, int status, uint64_t body_bytes) {
+    if (S.log_fd < 0) return;
+    char ts[64];
+    time_t now = time(nullptr);
+    struct tm tmv;
+    localtime_r(&now, &tmv);
+    strftime(ts, sizeof ts, "%d/%b/%Y:%H:%M:%S %z", &tmv);
+    auto dash = [](const std::string& v) { return v.empty() ? std::string("-") : v; };
+    const std::string line = client_ip + " - - [" + ts + "] \"" + pr.request_line + "\" " + std::to_string(status) + " " + std::to_string(body_bytes) + " \"" +
+                             dash(pr.referer) + "\" \"" + dash(pr.user_agent) + "\" \"" + dash(pr.x_forwarded_for) + "\"\n";
+    std::lock_guard<std::mutex> g(S.log_mu);
+    write_fd_all(S.log_fd, line.data(), line.size());
+}
+
 void serve_connection(Server* Sp, int fd, std::string client_ip) {
     Server& S = *Sp;
     int one = 1;
@@ -894,6 +917,7 @@ void serve_connection(Server* Sp, int fd, std::string client_ip) {
         }
         if (pr.ok && pr.rq.http_minor < 1) keep = false;
         const bool sent = send_plan(S, fd, plan, ent.get(), keep, win, t_req);
+        access_log_line(S, client_ip, pr, plan.status, plan.head ? 0 : plan.body_length());
         if (ent) ent->inflight--;
         if (!sent) break;
         if (!keep) break;
@@ -910,7 +934,7 @@ void serve_connection(Server* Sp, int fd, std::string client_ip) {
 void usage() {
     fprintf(stderr,
             "nzproxy [--listen ip:port] [--device N | --devices 0,1,..] [--arena-gib G] [--max-objects N] [--window-mib M] [--first-window-kib K] [--host-rate-gbs R] [--host-ctas N]\n"
-            "        [--max-conns N] [--gunzip] [--verify] [--upstream proxy_host=[https://]ip:port]... [--proxy-ssl-server-name] [--pv DIR] [--inactive-s S] [--valid-s S]\n");
+            "        [--max-conns N] [--gunzip] [--verify] [--upstream proxy_host=[https://]ip:port]... [--proxy-ssl-server-name] [--access-log PATH] [--pv DIR] [--inactive-s S] [--valid-s S]\n");
 }
 
 }  // namespace
@@ -918,6 +942,19 @@ void usage() {
 int main(int argc, char** argv) {
     signal(SIGPIPE, SIG_IGN);
     Server S;
+    // both `--opt value` and `--opt=value` (the form deploy/nezha-b200.yaml uses)
+    std::vector<std::string> argx;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        const size_t eq = a.rfind("--", 0) == 0 ? a.find('=') : std::string::npos;
+        if (eq != std::string::npos && a != "--upstream") { argx.push_back(a.substr(0, eq)); argx.push_back(a.substr(eq + 1)); }
+        else argx.push_back(a);
+    }
+    std::vector<const char*> argp;
+    argp.push_back(argv[0]);
+    for (const std::string& a : argx) argp.push_back(a.c_str());
+    argc = (int)argp.size();
+    argv = const_cast<char**>(argp.data());
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto next = [&]() -> const char* { if (i + 1 >= argc) { usage(); exit(2); } return argv[++i]; };
@@ -945,6 +982,7 @@ int main(int argc, char** argv) {
         else if (a == "--host-ctas") S.opt.host_ctas = atoi(next());
         else if (a == "--early-header") S.opt.early_header = atoi(next()) != 0;
         else if (a == "--proxy-ssl-server-name") S.opt.proxy_ssl_server_name = true;
+        else if (a == "--access-log") S.opt.access_log = next();
         else if (a == "--max-conns") S.opt.max_conns = atoi(next());
         else if (a == "--gunzip") S.opt.gunzip = true;
         else if (a == "--pv") S.opt.pv_dir = next();
@@ -1002,6 +1040,10 @@ int main(int argc, char** argv) {
         int n_bulk = 2;
         if (const char* e = getenv("NZ_PROXY_BULK_THREADS")) n_bulk = std::max(1, atoi(e));
         for (int i = 0; i < n_bulk; ++i) std::thread([kp] { kp->run(); }).detach();
+    }
+    if (!S.opt.access_log.empty()) {
+        S.log_fd = open(S.opt.access_log.c_str(), O_WRONLY | O_CREAT | O_APPEND, 0644);
+        if (S.log_fd < 0) fprintf(stderr, "nzproxy: cannot open access log %s: %s\n", S.opt.access_log.c_str(), strerror(errno));
     }
     if (const char* e = getenv("NZ_PROXY_TRACE")) g_trace = atoi(e) != 0;
     if (const char* e = getenv("NZ_PROXY_DIRECT")) g_direct_max = atoi(e);

@@ -265,12 +265,26 @@ def test_gcs_crc32c_header_is_verified_on_fill(policy_origin):
     PolicyOrigin.objects["/b/good"] = (good, {"x-goog-hash": "crc32c=" + o.crc32c_header(o.crc32c(good))})
     PolicyOrigin.objects["/b/bad"] = (bad, {"x-goog-hash": "crc32c=" + o.crc32c_header(o.crc32c(bad) ^ 0x10) + ",md5=AAAA"})
     port = free_port()
-    p = _start_proxy(port, policy_origin, ["--arena-gib", "0.5"])
+    import tempfile
+    alog = tempfile.mktemp(prefix="nz_access_", suffix=".log")
+    p = _start_proxy(port, policy_origin, ["--arena-gib", "0.5", "--access-log", alog])
     try:
         for _ in range(2):
-            s, _, b = fetch(port, "GET", "storage.googleapis.com", "/b/good", {})
+            s, _, b = fetch(port, "GET", "storage.googleapis.com", "/b/good", {"User-Agent": "Wget/1.19", "Referer": "http://example/"})
             assert s == 200 and b == good
         assert PolicyOrigin.hits["/b/good"] == 1
+        s, _, b = fetch(port, "GET", "storage.googleapis.com", "/b/good", {"Range": "bytes=10-19"})
+        assert s == 206
+        s, _, _ = fetch(port, "HEAD", "storage.googleapis.com", "/b/good", {})
+        assert s == 200
+        # access_log ... main (nginx.conf:16-19)
+        import re
+        lines = open(alog).read().splitlines()
+        assert len(lines) == 4
+        pat = re.compile(r'^127\.0\.0\.1 - - \[\d{2}/[A-Z][a-z]{2}/\d{4}:\d{2}:\d{2}:\d{2} [+-]\d{4}\] "(GET|HEAD) /b/good HTTP/1\.1" (\d{3}) (\d+) "([^"]*)" "([^"]*)" "-"$')
+        got = [pat.match(l).groups() for l in lines]
+        assert [(g[0], g[1], int(g[2])) for g in got] == [("GET", "200", len(good)), ("GET", "200", len(good)), ("GET", "206", 10), ("HEAD", "200", 0)]
+        assert got[0][3] == "http://example/" and got[0][4] == "Wget/1.19" and got[2][3] == "-"
         s1, _, _ = fetch(port, "GET", "storage.googleapis.com", "/b/bad", {})
         s2, _, _ = fetch(port, "GET", "storage.googleapis.com", "/b/bad", {})
         assert s1 == 502 and s2 == 502 and PolicyOrigin.hits["/b/bad"] == 2      # never admitted (NZ_ECORRUPT at commit)
