@@ -390,10 +390,10 @@ int32_t nz_put_file(nz_put* p, int fd, uint64_t file_off, uint64_t dst_off, uint
         if (got == (int64_t)len) { c->file_cufile_bytes += len; return NZ_OK; }
     }
     c->file_bounce_bytes += len;
-    std::lock_guard<std::mutex> g(c->put_mu);   // bounce buffers are shared
     // pread -> pinned bounce -> cudaMemcpyAsync.  One reader tops out at the page-cache copy rate
     // (~5-10 GB/s), so large reads are split over up to NZ_BOUNCE_LANES (12; env) reader threads, each with two pinned
-    // 8 MiB buffers and its own stream: reads and H2D copies of all lanes overlap.
+    // 8 MiB buffers and its own stream: reads and H2D copies of all lanes overlap.  Lanes come from a pool shared by
+    // concurrent calls (a cold start loads many files at once).
     constexpr int NZ_BOUNCE_LANES_MAX = 16;
     static const int NZ_BOUNCE_LANES = [] {
         int v = 12;
@@ -401,12 +401,25 @@ int32_t nz_put_file(nz_put* p, int fd, uint64_t file_off, uint64_t dst_off, uint
         return v < 1 ? 1 : v > NZ_BOUNCE_LANES_MAX ? NZ_BOUNCE_LANES_MAX : v;
     }();
     constexpr size_t BUF = 8u << 20;
-    if (!c->bounce[0]) {
-        c->bounce_bytes = BUF * 2 * NZ_BOUNCE_LANES;
-        CK(cudaHostAlloc(&c->bounce[0], c->bounce_bytes, cudaHostAllocPortable));
-        c->bounce[1] = c->bounce[0];
+    const int want = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)NZ_BOUNCE_LANES, len / (2 * BUF)));   // >= 16 MiB per lane
+    std::vector<int> mine;
+    {
+        std::unique_lock<std::mutex> g(c->put_mu);
+        if (!c->bounce[0]) {
+            c->bounce_bytes = BUF * 2 * NZ_BOUNCE_LANES;
+            CK(cudaHostAlloc(&c->bounce[0], c->bounce_bytes, cudaHostAllocPortable));
+            c->bounce[1] = c->bounce[0];
+            c->lane_busy.assign(NZ_BOUNCE_LANES, 0);
+        }
+        c->lane_cv.wait(g, [&] { for (char b : c->lane_busy) if (!b) return true; return false; });
+        for (int li = 0; li < NZ_BOUNCE_LANES && (int)mine.size() < want; ++li)
+            if (!c->lane_busy[li]) { c->lane_busy[li] = 1; mine.push_back(li); }
     }
-    const int lanes = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)NZ_BOUNCE_LANES, len / (2 * BUF)));   // >= 16 MiB per lane
+    struct LaneRelease {
+        nz_ctx* c; const std::vector<int>& mine;
+        ~LaneRelease() { { std::lock_guard<std::mutex> g(c->put_mu); for (int li : mine) c->lane_busy[li] = 0; } c->lane_cv.notify_all(); }
+    } lane_release{c, mine};
+    const int lanes = (int)mine.size();
     const uint64_t per = round_up((len + lanes - 1) / lanes, 4096);
     std::vector<int32_t> rcs(lanes, NZ_OK);
     std::vector<std::string> errs(lanes);
@@ -418,7 +431,7 @@ int32_t nz_put_file(nz_put* p, int fd, uint64_t file_off, uint64_t dst_off, uint
         cudaEvent_t ev[2];
         cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
-        char* base = (char*)c->bounce[0] + (size_t)li * 2 * BUF;
+        char* base = (char*)c->bounce[0] + (size_t)mine[li] * 2 * BUF;
         uint64_t done = beg;
         int which = 0;
         bool used[2] = {false, false};

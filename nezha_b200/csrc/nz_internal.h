@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <map>
 #include <mutex>
 #include <unordered_map>
@@ -222,10 +223,13 @@ struct nz_ctx {
     std::vector<nz_ticket*> ticket_pool;
     // stats
     std::atomic<uint64_t> gets{0}, get_bytes{0}, hits{0}, misses{0}, puts{0}, put_bytes{0}, evictions{0}, corrupt{0}, launches{0}, file_cufile_bytes{0}, file_bounce_bytes{0}, verify_chunks{0}, verify_fused{0};
-    // bounce buffers for nz_put_file / pageable writes
+    // bounce lanes for nz_put_file: one pinned allocation cut into lanes of 2 x 8 MiB; a call takes as many free
+    // lanes as its length warrants (at least one, waiting if none is free), so files load concurrently
     void* bounce[2] = {nullptr, nullptr};
     size_t bounce_bytes = 0;
     cudaEvent_t bounce_ev[2] = {nullptr, nullptr};
+    std::vector<char> lane_busy;
+    std::condition_variable lane_cv;
     std::mutex put_mu;              // serialises fill-side device work
     uint64_t* peer_base_dev = nullptr;      // device array [shard_count]
     std::vector<void*> peer_ptrs;           // host copy; nullptr = not attached

@@ -270,17 +270,18 @@ void pv_index_append(Server& S, const Entry& e) {
     if (fd >= 0) { write_fd_all(fd, line.data(), line.size()); close(fd); }
 }
 
-// cold start: bulk-load every still-valid object of the PV into HBM (cuFile/GDS when available)
+// cold start: bulk-load every still-valid object of the PV into HBM (cuFile/GDS when available).  The index is
+// read first; the files then load on several threads at once (nz_put_file hands out its bounce lanes per call).
 void pv_reload(Server& S) {
     FILE* f = fopen((S.opt.pv_dir + "/index.tsv").c_str(), "r");
     if (!f) return;
     char line[4096];
-    uint64_t n_ok = 0, bytes = 0, n_bad = 0;
     const time_t now = time(nullptr);
     const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::pair<std::string, std::shared_ptr<Entry>>> todo;     // md5hex, entry (first line of a key wins)
+    std::unordered_map<Key16, bool, Key16Hash> seen;
     while (fgets(line, sizeof line, f)) {
         std::vector<std::string> col;
-        char* save = nullptr;
         std::string l(line);
         if (!l.empty() && l.back() == '\n') l.pop_back();
         size_t pos = 0;
@@ -290,7 +291,6 @@ void pv_reload(Server& S) {
             if (t == std::string::npos) break;
             pos = t + 1;
         }
-        (void)save;
         if (col.size() != 9 || col[0].size() != 32) continue;
         auto e = std::make_shared<Entry>();
         for (int i = 0; i < 16; ++i) e->key128[i] = (uint8_t)strtoul(col[0].substr(2 * i, 2).c_str(), nullptr, 16);
@@ -305,30 +305,48 @@ void pv_reload(Server& S) {
         if (now - e->stored_at > S.opt.valid_s) continue;                       // expired: refetch on demand
         Key16 k;
         memcpy(k.b, e->key128, 16);
-        { std::lock_guard<std::mutex> g(S.mu); if (S.index.count(k)) continue; }   // a later line for the same key wins only if first is gone
-        const int fd = open((S.opt.pv_dir + "/" + col[0]).c_str(), O_RDONLY);
-        if (fd < 0) continue;
-        nz_put* put = nullptr;
-        bool ok = nz_put_begin(S.zone_of(e->key128), e->key128, e->meta.stored_length, e->meta.stored_length, e->meta.stored_gzip ? NZ_ENC_GZIP : NZ_ENC_IDENTITY, 0, &put) == NZ_OK;
-        if (ok) {
-            ok = nz_put_file(put, fd, 0, 0, e->meta.stored_length) == NZ_OK;
-            uint32_t crc = 0;
-            if (ok) ok = nz_put_commit(put, e->crc32c, 1, &crc) == NZ_OK;          // the PV copy must still match its CRC-32C
-            else nz_put_abort(put);
-        }
-        close(fd);
-        if (!ok) { ++n_bad; continue; }
-        e->last_access = now_ms();
-        { std::lock_guard<std::mutex> g(S.mu); S.index[k] = e; }
-        ++n_ok; bytes += e->meta.stored_length;
+        if (seen.count(k)) continue;
+        seen[k] = true;
+        todo.emplace_back(col[0], e);
     }
     fclose(f);
+    std::atomic<size_t> next{0};
+    std::atomic<uint64_t> n_ok{0}, bytes{0}, n_bad{0};
+    auto worker = [&] {
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= todo.size()) return;
+            const std::shared_ptr<Entry>& e = todo[i].second;
+            const int fd = open((S.opt.pv_dir + "/" + todo[i].first).c_str(), O_RDONLY);
+            if (fd < 0) continue;
+            nz_put* put = nullptr;
+            bool ok = nz_put_begin(S.zone_of(e->key128), e->key128, e->meta.stored_length, e->meta.stored_length, e->meta.stored_gzip ? NZ_ENC_GZIP : NZ_ENC_IDENTITY, 0, &put) == NZ_OK;
+            if (ok) {
+                ok = nz_put_file(put, fd, 0, 0, e->meta.stored_length) == NZ_OK;
+                uint32_t crc = 0;
+                if (ok) ok = nz_put_commit(put, e->crc32c, 1, &crc) == NZ_OK;          // the PV copy must still match its CRC-32C
+                else nz_put_abort(put);
+            }
+            close(fd);
+            if (!ok) { ++n_bad; continue; }
+            e->last_access = now_ms();
+            Key16 k;
+            memcpy(k.b, e->key128, 16);
+            { std::lock_guard<std::mutex> g(S.mu); S.index[k] = e; }
+            ++n_ok; bytes += e->meta.stored_length;
+        }
+    };
+    std::vector<std::thread> th;
+    const size_t nth = std::min<size_t>(8, std::max<size_t>(1, todo.size()));
+    for (size_t i = 1; i < nth; ++i) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     nz_stats st;
     nz_get_stats(S.ctx, &st);
     fprintf(stderr, "nzproxy: reloaded %llu objects (%.2f GiB) from %s in %.2f s (%.2f GB/s; cuFile %.2f GiB, bounce %.2f GiB), %llu rejected\n",
-            (unsigned long long)n_ok, bytes / 1073741824.0, S.opt.pv_dir.c_str(), dt, dt > 0 ? bytes / dt / 1e9 : 0.0,
-            st.file_cufile_bytes / 1073741824.0, st.file_bounce_bytes / 1073741824.0, (unsigned long long)n_bad);
+            (unsigned long long)n_ok.load(), bytes.load() / 1073741824.0, S.opt.pv_dir.c_str(), dt, dt > 0 ? bytes.load() / dt / 1e9 : 0.0,
+            st.file_cufile_bytes / 1073741824.0, st.file_bounce_bytes / 1073741824.0, (unsigned long long)n_bad.load());
 }
 
 // drop one object everywhere (device extent, host index, PV file)

@@ -510,3 +510,35 @@ def test_staged_dma_host_waves_bit_exact():
     for w in wins + [b]:
         w.free()
     z.close()
+
+
+def test_concurrent_put_file_shares_bounce_lanes(tmp_path):
+    """A cold start loads many files at once: concurrent nz_put_file calls take bounce lanes from one pool
+    (large files several, small files one) and every object must arrive intact (CRC-32C vs the oracle)."""
+    from concurrent.futures import ThreadPoolExecutor
+    z = nz.Zone(device=0, arena_bytes=1 << 30, max_objects=64)
+    sizes = [70 << 20, 1, 4096, (33 << 20) + 5, 1 << 20, 123_457, 48 << 20, (16 << 20) - 1, 9 << 20, 65_536, 200 << 20, 3]
+    items = []
+    for i, n in enumerate(sizes):
+        d = wl.synth_bytes(n, seed=12_000 + i)
+        path = tmp_path / f"f{i}"
+        path.write_bytes(d.tobytes())
+        items.append((K(i, "cpf"), str(path), n, d))
+
+    def load(it):
+        k, path, n, d = it
+        fd = os.open(path, os.O_RDONLY)
+        try:
+            return z.put_file(k, fd, n)
+        finally:
+            os.close(fd)
+
+    with ThreadPoolExecutor(6) as ex:
+        crcs = list(ex.map(load, items))
+    for (k, path, n, d), crc in zip(items, crcs):
+        assert crc == o.crc32c(d.tobytes())
+    res, body = z.get(items[3][0], segs=[(1 << 20, 1 << 20)])
+    assert res.status == capi.NZ_OK and body == items[3][3][1 << 20:2 << 20].tobytes()
+    st = z.stats()
+    assert st.file_cufile_bytes + st.file_bounce_bytes == sum(sizes)
+    z.close()
