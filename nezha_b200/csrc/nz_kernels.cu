@@ -915,6 +915,8 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
     uint32_t slot = 0;
     // pacing (waves that write pinned host memory): this CTA issues at most one tile per pace_ns, so the wave
     // offers the PCIe link a bounded rate and the posted-write queue ahead of latency-critical waves stays short
+    bool pre_valid = false;                                    // VERIFY look-ahead: load of `pre_tile` already in flight
+    uint64_t pre_tile = 0;
     uint64_t pace_next = 0;
     if (pace_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pace_next));
     // the engine tile whose load is in flight and whose stores are still to be issued (thread 0 only)
@@ -978,12 +980,13 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
         if constexpr (VERIFY) {
             // simple pipeline, every thread follows the barrier phases: load -> (all wait) -> stores -> checksum from shared memory
             const uint32_t buf = smem_u32(s_buf + (size_t)slot * tile_bytes), bar = smem_u32(&s_bar[slot]);
-            if (tid == 0) {
+            if (tid == 0 && !(pre_valid && pre_tile == tile)) {   // not already in flight from the previous iteration's look-ahead
                 bulk_wait_read<STAGES - 1>();
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bulk) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              :: "r"(buf), "l"(s), "r"(bulk), "r"(bar) : "memory");
             }
+            pre_valid = false;
             const bool vt = vbase != 0xFFFFFFFFu;
             if (vt || tid == 0) {
                 uint32_t done = 0;
@@ -1001,6 +1004,29 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dm), "r"(buf), "r"(bulk) : "memory");
                 }
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            // look-ahead: the checksum below takes longer than a tile's load, so the next tile of this CTA is requested
+            // first (into the other stage; its previous stores are done once at most this tile's group is pending)
+            if (vt && tile + gridDim.x < total) {
+                TileCursor c2 = c;
+                c2.seek(tile + gridDim.x, work, tile_begin, nseg);
+                int64_t lo2, hi2;
+                c2.span(tile + gridDim.x, tile_bytes, lo2, hi2);
+                const uint8_t* s2 = reinterpret_cast<const uint8_t*>(c2.src) + lo2;
+                const uint8_t* d2 = reinterpret_cast<const uint8_t*>(c2.dst) + lo2;
+                const uint32_t bulk2 = (uint32_t)(hi2 - lo2) & ~15u;
+                if (bulk2 >= 2048 && ((((uintptr_t)s2) | ((uintptr_t)d2)) & 15u) == 0) {
+                    const uint32_t slot2 = slot + 1 == STAGES ? 0 : slot + 1;
+                    if (tid == 0) {
+                        const uint32_t buf2 = smem_u32(s_buf + (size_t)slot2 * tile_bytes), bar2 = smem_u32(&s_bar[slot2]);
+                        bulk_wait_read<STAGES - 1>();
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar2), "r"(bulk2) : "memory");
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     :: "r"(buf2), "l"(s2), "r"(bulk2), "r"(bar2) : "memory");
+                    }
+                    pre_valid = true;
+                    pre_tile = tile + gridDim.x;
+                }
             }
             if (vt) tile_verify(vc, s_buf + (size_t)slot * tile_bytes, s, n, vbase, c0ptr);
         } else
