@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <functional>
 #include <string>
 #include <thread>
 
@@ -359,10 +360,22 @@ int32_t nz_put_begin(nz_ctx* c, const uint8_t key[16], uint64_t stored_len, uint
     return NZ_OK;
 }
 
+static int32_t bounce_copy(nz_put* p, uint64_t dst_off, uint64_t len, const std::function<const char*(char*, uint64_t, size_t)>& reader);
+
 int32_t nz_put_write(nz_put* p, const void* src_host, uint64_t dst_off, uint64_t len) {
     if (!p || (!src_host && len) || dst_off > p->stored_len || len > p->stored_len - dst_off) return NZ_EINVAL;
     if (!len) return NZ_OK;
     CK(cudaSetDevice(p->ctx->device));
+    if (len >= (32ull << 20)) {          // big pageable source: the driver's own staging copy runs at ~10 GB/s; the bounce lanes at ~40
+        cudaPointerAttributes at;
+        const bool pageable = cudaPointerGetAttributes(&at, src_host) != cudaSuccess || at.type == cudaMemoryTypeUnregistered;
+        cudaGetLastError();
+        if (pageable)
+            return bounce_copy(p, dst_off, len, [&](char* dst, uint64_t off, size_t n) -> const char* {
+                memcpy(dst, static_cast<const char*>(src_host) + off, n);
+                return nullptr;
+            });
+    }
     CK(cudaMemcpyAsync(p->ctx->arena + p->arena_off + dst_off, src_host, len, cudaMemcpyHostToDevice, p->stream));
     return NZ_OK;
 }
@@ -380,16 +393,10 @@ int32_t nz_put_write_device(nz_put* p, const void* src_dev, uint64_t dst_off, ui
     return NZ_OK;
 }
 
-int32_t nz_put_file(nz_put* p, int fd, uint64_t file_off, uint64_t dst_off, uint64_t len) {
-    if (!p || fd < 0 || dst_off > p->stored_len || len > p->stored_len - dst_off) return NZ_EINVAL;
+// host bytes -> pinned bounce lanes -> cudaMemcpyAsync into the extent.  `reader(dst, off, n)` fills n bytes of the
+// source starting at byte `off` (a pread from a file, a memcpy from pageable memory) and returns nullptr or what failed.
+static int32_t bounce_copy(nz_put* p, uint64_t dst_off, uint64_t len, const std::function<const char*(char*, uint64_t, size_t)>& reader) {
     nz_ctx* c = p->ctx;
-    CK(cudaSetDevice(c->device));
-    if (len) {   // GPUDirect Storage first: the DMA lands straight in the extent
-        CK(cudaStreamSynchronize(p->stream));
-        const int64_t got = nz_cufile_read(fd, file_off, c->arena, p->arena_off + dst_off, len);
-        if (got == (int64_t)len) { c->file_cufile_bytes += len; return NZ_OK; }
-    }
-    c->file_bounce_bytes += len;
     // pread -> pinned bounce -> cudaMemcpyAsync.  One reader tops out at the page-cache copy rate
     // (~5-10 GB/s), so large reads are split over up to NZ_BOUNCE_LANES (12; env) reader threads, each with two pinned
     // 8 MiB buffers and its own stream: reads and H2D copies of all lanes overlap.  Lanes come from a pool shared by
@@ -438,14 +445,8 @@ int32_t nz_put_file(nz_put* p, int fd, uint64_t file_off, uint64_t dst_off, uint
         while (done < end && rcs[li] == NZ_OK) {
             const size_t want = (size_t)std::min<uint64_t>(BUF, end - done);
             if (used[which] && cudaEventSynchronize(ev[which]) != cudaSuccess) { rcs[li] = NZ_ECUDA; break; }
-            size_t got = 0;
-            while (got < want) {
-                ssize_t r = pread(fd, base + which * BUF + got, want - got, (off_t)(file_off + done + got));
-                if (r < 0) { if (errno == EINTR) continue; rcs[li] = NZ_EINVAL; errs[li] = std::string("pread: ") + strerror(errno); break; }
-                if (r == 0) { rcs[li] = NZ_EINVAL; errs[li] = "pread: short file"; break; }
-                got += (size_t)r;
-            }
-            if (rcs[li] != NZ_OK) break;
+            const char* why = reader(base + which * BUF, done, want);
+            if (why) { rcs[li] = NZ_EINVAL; errs[li] = why; break; }
             if (cudaMemcpyAsync(c->arena + p->arena_off + dst_off + done, base + which * BUF, want, cudaMemcpyHostToDevice, s) != cudaSuccess ||
                 cudaEventRecord(ev[which], s) != cudaSuccess) { rcs[li] = NZ_ECUDA; break; }
             used[which] = true;
@@ -466,11 +467,33 @@ int32_t nz_put_file(nz_put* p, int fd, uint64_t file_off, uint64_t dst_off, uint
     }
     for (int li = 0; li < lanes; ++li)
         if (rcs[li] != NZ_OK) {
-            snprintf(tl_err, sizeof tl_err, "nz_put_file lane %d: %s", li, errs[li].empty() ? "CUDA error" : errs[li].c_str());
+            snprintf(tl_err, sizeof tl_err, "bounce lane %d: %s", li, errs[li].empty() ? "CUDA error" : errs[li].c_str());
             cudaGetLastError();
             return rcs[li];
         }
     return NZ_OK;
+}
+
+int32_t nz_put_file(nz_put* p, int fd, uint64_t file_off, uint64_t dst_off, uint64_t len) {
+    if (!p || fd < 0 || dst_off > p->stored_len || len > p->stored_len - dst_off) return NZ_EINVAL;
+    nz_ctx* c = p->ctx;
+    CK(cudaSetDevice(c->device));
+    if (len) {   // GPUDirect Storage first: the DMA lands straight in the extent
+        CK(cudaStreamSynchronize(p->stream));
+        const int64_t got = nz_cufile_read(fd, file_off, c->arena, p->arena_off + dst_off, len);
+        if (got == (int64_t)len) { c->file_cufile_bytes += len; return NZ_OK; }
+    }
+    c->file_bounce_bytes += len;
+    return bounce_copy(p, dst_off, len, [&](char* dst, uint64_t off, size_t n) -> const char* {
+        size_t got = 0;
+        while (got < n) {
+            ssize_t r = pread(fd, dst + got, n - got, (off_t)(file_off + off + got));
+            if (r < 0) { if (errno == EINTR) continue; return "pread failed"; }
+            if (r == 0) return "pread: short file";
+            got += (size_t)r;
+        }
+        return nullptr;
+    });
 }
 
 static void put_release(nz_put* p, bool drop_reservation) {
