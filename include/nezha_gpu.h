@@ -176,7 +176,8 @@ int32_t nz_lookup(nz_ctx* ctx, const uint8_t (*keys)[16], uint32_t n, nz_extent*
  * and moved out by the copy engine whatever the per-request outcome). */
 int32_t nz_get_submit(nz_ctx* ctx, const nz_get_req* reqs, uint32_t n,
                       void* cuda_stream, nz_ticket** out);
-/* timeout_us < 0 waits forever; res (n entries) may be NULL */
+/* timeout_us < 0 waits forever; res (n entries) may be NULL.  Short waves are polled (a wave of a few small
+ * slices completes through a flag its kernel writes into pinned memory), long ones sleep between polls. */
 int32_t nz_get_wait(nz_ticket* t, int64_t timeout_us, nz_get_res* res);
 int32_t nz_get_poll(nz_ticket* t);                 /* NZ_OK done, NZ_ETIMEOUT not yet */
 int32_t nz_ticket_elapsed_ms(nz_ticket* t, float* ms);  /* device time of the wave */
@@ -193,7 +194,9 @@ int32_t nz_set_profiling(nz_ctx* ctx, int32_t on);
  * stay near that rate (shared between the waves in flight); ctas > 0 sets how many CTAs such a wave
  * runs on.  A saturated link keeps ~150-300 us of posted writes queued ahead of every later wave; kept
  * just below saturation, a first window (NZ_GET_URGENT) still completes in ~40-60 us.
- * 0 / 0 restores the defaults (unpaced, 32 CTAs): maximum throughput, the bench's e2e mode. */
+ * 0 / 0 restores the defaults (unpaced, 32 CTAs): maximum throughput, the bench's e2e mode.
+ * Nothing in the reference corresponds to it (examples/demo/nginx.conf sets no limit_rate /
+ * sendfile_max_chunk; its one worker never fills a link). */
 int32_t nz_set_host_rate(nz_ctx* ctx, double total_gbs, int32_t ctas);
 
 /* ---- cross-shard objects (the one exchange step) ---------------- */
