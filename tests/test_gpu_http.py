@@ -333,6 +333,8 @@ def test_pv_write_through_and_cold_start(policy_origin, tmp_path):
 
 
 def test_inactive_purge_and_lru_under_pressure(policy_origin):
+    """SPEC H1 (absent key -> MISS -> fill), H2 (`proxy_cache_valid 200 1d`: --valid-s, an expired entry is a MISS again),
+    H3 (`inactive=60m`: --inactive-s purge), plus LRU eviction when the arena is full (nginx has no max_size; HBM does)."""
     objs = {f"/lru/obj{i}": wl.synth_bytes(24 << 20, 90 + i).tobytes() for i in range(5)}     # 5 x 24 MiB into a 64 MiB arena
     for k, v in objs.items():
         PolicyOrigin.objects[k] = (v, {})

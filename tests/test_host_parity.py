@@ -107,3 +107,71 @@ def test_plan_differential(method, minor, rng, if_range, inm, im, ims, ius, ae, 
     got = h.plan_text(method, minor, rng, if_range, inm, im, ims, ius, ae, stored_length=slen, raw_length=rawlen,
                       content_type=ctype, etag=etag, last_modified=lm, content_encoding=cenc, gunzip_enabled=gunzip, boundary=bnd)
     assert got == want, (rq, ob)
+
+
+# ---- named rules of oracle/SPEC.md that the generated differentials cover only implicitly -------------------
+def _plan(**kw):
+    rq = dict(method="GET", http_minor=1, range=None, if_range=None, if_none_match=None, if_match=None, if_modified_since=None,
+              if_unmodified_since=None, accept_encoding=None)
+    ob = dict(stored_length=1000, raw_length=-1, content_type="application/x-gzip", etag='"abc"',
+              last_modified="Wed, 07 Nov 2018 15:20:01 GMT", content_encoding=None, gunzip_enabled=False, boundary=7)
+    rq.update({k: v for k, v in kw.items() if k in rq})
+    ob.update({k: v for k, v in kw.items() if k in ob})
+    got = h.plan_text(rq["method"], rq["http_minor"], rq["range"], rq["if_range"], rq["if_none_match"], rq["if_match"],
+                      rq["if_modified_since"], rq["if_unmodified_since"], rq["accept_encoding"], **ob)
+    want = o.plan(o.Req(rq["method"], rq["http_minor"], rq["range"], rq["if_range"], rq["if_none_match"], rq["if_match"],
+                        rq["if_modified_since"], rq["if_unmodified_since"], rq["accept_encoding"]),
+                  o.Obj(ob["stored_length"], ob["content_type"], ob["etag"], ob["last_modified"], ob["content_encoding"], ob["raw_length"],
+                        ob["gunzip_enabled"]), ob["boundary"])
+    assert got == want
+    lines = got.splitlines()
+    return int(lines[0].split()[1]), [l[4:] for l in lines if l.startswith("hdr ")], lines
+
+
+def test_entity_tag_lists_C6():
+    st_ = lambda **kw: _plan(**kw)[0]
+    assert st_(if_none_match="*", etag=None) == 304                      # `*` matches even without a stored ETag
+    assert st_(if_none_match='"abc"', etag=None) == 200                  # nothing else does
+    assert st_(if_none_match='"x", "abc"') == 304 and st_(if_none_match='"x","abc"') == 304 and st_(if_none_match=' , "abc" ,') == 304
+    assert st_(if_none_match='"abcd"') == 200 and st_(if_none_match='"abc"x') == 200      # must end at blanks, a comma or the end
+    assert st_(if_none_match='W/"abc"') == 304                           # If-None-Match compares weakly
+    assert st_(if_match='W/"abc"') == 412 and st_(if_match='"abc"') == 200 and st_(if_match="*") == 200   # If-Match strongly
+
+
+def test_412_is_a_stock_page_C8_E1():
+    status, hdrs, lines = _plan(if_match='"nope"')
+    assert status == 412 and not any(x.startswith(("ETag", "Last-Modified", "Accept-Ranges")) for x in hdrs)
+    body = bytes.fromhex([l for l in lines if l.startswith("lit ")][0][4:])
+    assert body.startswith(b"<html>\r\n<head><title>412 Precondition Failed</title>") and b"<center>nginx</center>" in body
+
+
+def test_range_grammar_R3():
+    """The functions take the part after `bytes=` (R2 strips the unit)."""
+    assert h.parse_ranges(" 1 - 2 , -3 ", 1000) == o.range_parse(" 1 - 2 , -3 ", 1000) == (0, [(1, 3), (997, 1000)])    # blanks around tokens
+    for spec in ["1-2,", "1-2, ,3-4", "9223372036854775807-", "9223372036854775808-", "99999999999999999999-", "1-2;3-4", "1--2", "1-2 3-4",
+                 "+1-2", "\t1-2", "", "-", "5-1"]:
+        assert h.parse_ranges(spec, 1000)[0] == o.range_parse(spec, 1000)[0] == 416, spec
+
+
+def test_206_keeps_validators_200_advertises_ranges_R10():
+    s200, h200, _ = _plan()
+    s206, h206, _ = _plan(range="bytes=10-19")
+    assert s200 == 200 and "Accept-Ranges: bytes" in h200
+    assert s206 == 206 and "Accept-Ranges: bytes" not in h206 and 'ETag: "abc"' in h206 and any(x.startswith("Last-Modified") for x in h206)
+    assert "Content-Range: bytes 10-19/1000" in h206
+
+
+def test_gunzip_applies_G1():
+    gz = dict(content_encoding="gzip", raw_length=5000)
+    assert _plan(gunzip_enabled=True, **gz)[2][2] == "repr inflated"                              # no Accept-Encoding: inflate
+    assert _plan(gunzip_enabled=True, accept_encoding="gzip, deflate", **gz)[2][2] == "repr identity"   # client takes gzip: as stored
+    assert _plan(gunzip_enabled=True, accept_encoding="identity", **gz)[2][2] == "repr inflated"
+    assert _plan(gunzip_enabled=False, **gz)[2][2] == "repr identity"                             # operator switch off = the reference (no `gunzip on`)
+    assert _plan(gunzip_enabled=True, content_encoding=None)[2][2] == "repr identity"
+    hdrs = _plan(gunzip_enabled=True, **gz)[1]
+    assert "Content-Length: 5000" in hdrs and not any(x.startswith("Content-Encoding") for x in hdrs)
+
+
+def test_crc32c_header_form_X3():
+    assert o.crc32c_header(0xE3069283) == "4waSgw=="          # GCS x-goog-hash: crc32c= base64(big-endian u32) of "123456789"
+    assert o.crc32c_header(0) == "AAAAAA==" and o.crc32c_header(0xFFFFFFFF) == "/////w=="
