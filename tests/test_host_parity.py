@@ -10,7 +10,7 @@ from hypothesis import HealthCheck, given, settings, strategies as st
 from nezha_b200 import hostlib as h
 from oracle import oracle as o
 
-SET = settings(max_examples=400, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+SET = settings(max_examples=int(__import__("os").environ.get("NZ_HYP_EXAMPLES", "400")), deadline=None, suppress_health_check=[HealthCheck.too_slow])
 
 
 def test_md5_matches():
