@@ -621,13 +621,17 @@ def run_c3(args):
         made = pool.map(_c3_make, range(n_obj), chunksize=8)
     gen_s = time.perf_counter() - t0
     comp_total = sum(len(g) for g, _ in made)
-    zone = nz.Zone(device=local, arena_bytes=comp_total + n_obj * 8192 + (64 << 20), max_objects=max(2 * n_obj, 1024))
+    # arena: the members + their checkpoint indexes (~7 % of the raw size each, 4 KiB granular)
+    zone = nz.Zone(device=local, arena_bytes=comp_total + n_obj * (8192 + (128 << 10)) + (64 << 20), max_objects=max(2 * n_obj, 1024))
     zone.set_profiling(True)
     keys = [wl.key128(wl.object_key_string("c3", i)) for i in range(n_obj)]
     t0 = time.perf_counter()
-    for k, (g, _) in zip(keys, made):
-        zone.put(k, np.frombuffer(g, dtype=np.uint8), enc=capi.NZ_ENC_GZIP, raw_len=wl.C3_RAW)
+    used0 = zone.stats().arena_used
+    for b0 in range(0, n_obj, 1024):              # bulk load: nz_put_commit_many (CRC, index build and publish batched)
+        zone.put_many([(keys[i], np.frombuffer(made[i][0], dtype=np.uint8), wl.C3_RAW) for i in range(b0, min(n_obj, b0 + 1024))],
+                      enc=capi.NZ_ENC_GZIP)
     fill_s = time.perf_counter() - t0
+    arena_used = zone.stats().arena_used - used0
     ranks = wl.zipf_ranks(1_000_000, n_obj, 0.99, seed=3)
     nwaves = args.steps + max(args.warmup, 3)
     dbuf = zone.alloc_device(wave_n * wl.C3_RAW)
@@ -650,6 +654,17 @@ def run_c3(args):
     for j in (0, wave_n // 2, wave_n - 1):       # spot parity vs the SHA-256 of the generator's raw bytes
         if hashlib.sha256(dbuf.bytes(j * wl.C3_RAW, wl.C3_RAW)).hexdigest() != made[rr[j]][1]:
             raise SystemExit("bench.py c3: inflated bytes differ from the source")
+    # one member alone (latency of a single GET that inflates): one 1 MiB object, nothing else on the GPU
+    single = []
+    for j in range(8):
+        g1 = zone.prepare([nz.Get(keys[int(rr[j])], dbuf, [], capi.NZ_GET_INFLATE, 0)])
+        for _ in range(3):
+            t = g1.submit(sptr)
+            t.wait()
+            single.append((t.inflate_ms(), t.elapsed_ms()))
+            t.free()
+    single_infl_ms = sorted(x[0] for x in single)[len(single) // 2]
+    single_wave_ms = sorted(x[1] for x in single)[len(single) // 2]
     launches0 = zone.stats().kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -660,16 +675,23 @@ def run_c3(args):
     sampler.stop_ev.set()
     ms = ev0.elapsed_time(ev1)
     infl_ms = [t.inflate_ms() for t in tickets]
+    gath_ms = [t.gather_ms() for t in tickets]
     for t in tickets:
         t.wait()
         t.free()
     launches = zone.stats().kernel_launches - launches0
     raw_bytes = wave_n * wl.C3_RAW
-    comp_wave = [sum(len(made[r][0]) for r in rr) for rr, _ in waves[max(args.warmup, 3):]]
+    # the inflate kernel decodes every DISTINCT member of a wave once (duplicates are copies made by the gather)
+    timed = waves[max(args.warmup, 3):]
+    distinct = [len(set(int(r) for r in rr)) for rr, _ in timed]
+    comp_wave = [sum(len(made[r][0]) for r in set(int(x) for x in rr)) for rr, _ in timed]
     ms_step = ms / args.steps
     hbm, which = peaks()
     i_ms = sum(infl_ms) / len(infl_ms)
-    achieved = (sum(comp_wave) / len(comp_wave) + raw_bytes) / (i_ms * 1e-3) / 1e9
+    g_ms = sum(gath_ms) / len(gath_ms)
+    dedupe = os.environ.get("NZ_INFL_DEDUPE", "1") != "0"
+    decoded = (sum(distinct) / len(distinct) if dedupe else wave_n) * wl.C3_RAW
+    achieved = ((sum(comp_wave) / len(comp_wave)) * (1 if dedupe else wave_n / (sum(distinct) / len(distinct))) + decoded) / (i_ms * 1e-3) / 1e9
     cpu = None
     if not args.no_cpu:
         import ctypes as C
@@ -695,9 +717,14 @@ def run_c3(args):
                                f"{wave_n} GETs per wave, inflate on every hit", "objects": n_obj, "wave": wave_n,
                    "response_buffers": "HBM", "l2": f"{wave_n} MiB written per wave (> L2)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
-                     "peak_source": which, "kernel": "k_inflate+k_inflate_crc", "kernel_ms": i_ms,
-                     "note": "bit-serial DEFLATE: latency/ALU bound, not HBM bound; algorithmic bytes = compressed in + raw out",
-                     "kernel_share_of_step": i_ms / ms_step},
+                     "peak_source": which, "kernel": "k_inflate_seg", "kernel_ms": i_ms,
+                     "note": "bit-serial DEFLATE: latency/ALU bound, not HBM bound; algorithmic bytes = compressed in + raw out of the members "
+                             "the kernel decodes (each distinct member of the wave once)",
+                     "kernel_share_of_step": i_ms / ms_step, "decoded_gbs": decoded / (i_ms * 1e-3) / 1e9},
+        "c3": {"single_stream_ms": single_infl_ms, "single_get_wave_ms": single_wave_ms, "distinct_members_per_wave": sum(distinct) / len(distinct),
+               "inflate_kernel_ms": i_ms, "fanout_gather_ms": g_ms, "dedupe": dedupe,
+               "index_bytes_per_object": (arena_used - comp_total) / n_obj, "index_segment_kib": int(os.environ.get("NZ_INFL_SEG_KB", "128")),
+               "indexed": os.environ.get("NZ_INFL_INDEX", "1") != "0"},
         "cpu_baseline": cpu, "e2e": None, "gpu_launches": int(launches), "clocks": sampler.summary(),
         "gen_s": gen_s, "fill_s": fill_s, "compressed_bytes_total": comp_total,
     }

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NZ_ABI_VERSION 1
+#define NZ_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------ */
 #define NZ_OK          0
@@ -48,6 +48,8 @@ extern "C" {
 #define NZ_ENC_STRIPE   4u    /* put: this object is one stripe of a larger object */
                               /* (placed by the stripe plan, not by its own key hash) */
 #define NZ_ENC_STRIPED  8u    /* the object's bytes live in stripes on several GPUs */
+#define NZ_ENC_INFLATABLE 16u /* set by nz_put_commit on an NZ_ENC_GZIP object whose member inflated cleanly there
+                                 (trailer CRC-32 and ISIZE checked): raw_length is exact.  Never passed to nz_put_begin. */
 
 /* ---- get flags ---------------------------------------------------------- */
 #define NZ_GET_INFLATE  1u    /* serve the inflated representation (SPEC G)       */
@@ -122,6 +124,9 @@ typedef struct nz_stats {
     uint64_t verify_chunks;       /* 64 KiB chunks checked for NZ_GET_VERIFY (stored-byte GETs) */
     uint64_t verify_fused_chunks; /* ... of which the gather checksummed from its shared-memory copy (no second HBM read) */
     uint64_t host_dma_waves;      /* waves to pinned host memory that went HBM staging slot -> copy engine (8 MiB .. 1 GiB, explicit slices) */
+    uint64_t inflate_segments;    /* index segments decoded by GETs (one warp each; K4 with the checkpoint index) */
+    uint64_t inflate_whole_members; /* members GETs decoded with one warp each because they carry no index */
+    uint64_t index_bytes;         /* arena bytes held by checkpoint indexes of live gzip objects */
 } nz_stats;
 
 /* ---- lifecycle ----------------------------------------------------------- */
@@ -158,9 +163,20 @@ int32_t nz_put_write_device(nz_put* p, const void* src_dev, uint64_t dst_off, ui
 int32_t nz_put_file(nz_put* p, int fd, uint64_t file_off, uint64_t dst_off, uint64_t len);
 /* computes the 64 KiB chunk CRC-32C table and the whole-object CRC on the device;
  * if has_expected and it differs -> NZ_ECORRUPT and nothing is published; else the
- * slot is published (visible to GETs).  The handle is consumed either way. */
+ * slot is published (visible to GETs).  The handle is consumed either way.
+ * NZ_ENC_GZIP objects are inflated once here (trailer CRC-32 and ISIZE checked): raw_length becomes the member's
+ * real inflated length whatever nz_put_begin was told (pass 0 when it is not known), and a checkpoint index is
+ * stored next to the member so that a GET with NZ_GET_INFLATE decodes it with one warp per ~128 KiB of output
+ * instead of one warp per member.  A malformed member is still stored (its bytes are served verbatim, SPEC G4);
+ * inflate GETs on it report NZ_ECORRUPT. */
 int32_t nz_put_commit(nz_put* p, uint32_t expected_crc32c, int32_t has_expected,
                       uint32_t* out_crc32c);
+/* Commit n objects of one context in one go (bulk loads: a cold start from the PV, a bench fill): the per-object
+ * kernels are batched and the table is published with one launch.  expected_crc32c may be NULL (nothing to compare);
+ * has_expected may be NULL (every entry of expected_crc32c counts).  out_crc32c / out_status (n entries each) may be
+ * NULL.  Every handle is consumed.  Returns NZ_OK when the call ran; per-object outcomes are in out_status. */
+int32_t nz_put_commit_many(nz_put** puts, uint32_t n, const uint32_t* expected_crc32c, const int32_t* has_expected,
+                           uint32_t* out_crc32c, int32_t* out_status);
 int32_t nz_put_abort(nz_put* p);
 int32_t nz_evict(nz_ctx* ctx, const uint8_t key[16]);
 

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "_build", "libnezha_gpu.so")
 
 NZ_OK, NZ_EINVAL, NZ_ENOMEM, NZ_ECUDA, NZ_ENOTFOUND = 0, -1, -2, -3, -4
 NZ_ECORRUPT, NZ_ETIMEOUT, NZ_EEXIST, NZ_EFULL, NZ_ENOSYS, NZ_ERANGE = -5, -6, -7, -8, -9, -10
-NZ_ENC_IDENTITY, NZ_ENC_GZIP, NZ_ENC_STRIPE, NZ_ENC_STRIPED = 0, 1, 4, 8
+NZ_ENC_IDENTITY, NZ_ENC_GZIP, NZ_ENC_STRIPE, NZ_ENC_STRIPED, NZ_ENC_INFLATABLE = 0, 1, 4, 8, 16
 NZ_IPC_HANDLE_BYTES = 64
 NZ_GET_INFLATE, NZ_GET_VERIFY, NZ_GET_URGENT = 1, 2, 4
 NZ_BUF_PINNED_HOST, NZ_BUF_DEVICE = 0, 1
@@ -24,7 +24,7 @@ NZ_CRC_CHUNK = 65536
 SYMBOLS = [
     "nz_abi_version", "nz_strerror", "nz_last_error", "nz_init", "nz_shutdown",
     "nz_buf_alloc", "nz_buf_wrap_device", "nz_buf_ptr", "nz_buf_devptr", "nz_buf_size", "nz_buf_free", "nz_buf_read", "nz_buf_write",
-    "nz_put_begin", "nz_put_write", "nz_put_sync", "nz_put_write_device", "nz_put_file", "nz_put_commit", "nz_put_abort",
+    "nz_put_begin", "nz_put_write", "nz_put_sync", "nz_put_write_device", "nz_put_file", "nz_put_commit", "nz_put_commit_many", "nz_put_abort",
     "nz_evict", "nz_lookup", "nz_get_submit", "nz_get_wait", "nz_get_poll", "nz_ticket_elapsed_ms",
     "nz_ticket_gather_ms", "nz_ticket_inflate_ms", "nz_ticket_free", "nz_get_stats", "nz_set_profiling", "nz_set_host_rate", "nz_crc32c_device", "nz_debug_poke", "nz_shard_of",
     "nz_arena_ipc_export", "nz_peer_attach", "nz_extent_location", "nz_put_striped", "nz_crc32c_combine",
@@ -68,7 +68,8 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "objects", "arena_bytes", "arena_used", "table_slots", "table_live", "gets", "get_bytes", "hits",
         "misses", "puts", "put_bytes", "evictions", "corrupt", "kernel_launches", "file_cufile_bytes", "file_bounce_bytes",
-        "verify_chunks", "verify_fused_chunks", "host_dma_waves")]
+        "verify_chunks", "verify_fused_chunks", "host_dma_waves", "inflate_segments", "inflate_whole_members",
+        "index_bytes")]
 
 
 class Stripe(C.Structure):
@@ -118,6 +119,8 @@ def load() -> C.CDLL:
     L.nz_put_write_device.argtypes = [vp, vp, C.c_uint64, C.c_uint64]
     L.nz_put_file.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64]
     L.nz_put_commit.argtypes = [vp, C.c_uint32, C.c_int32, C.POINTER(C.c_uint32)]
+    L.nz_put_commit_many.argtypes = [C.POINTER(vp), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]
     L.nz_put_abort.argtypes = [vp]
     L.nz_evict.argtypes = [vp, u8p]
     L.nz_lookup.argtypes = [vp, vp, C.c_uint32, C.POINTER(Extent)]

@@ -159,6 +159,18 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
     c->gather_grid = c->sm_count * nz_gather_blocks_per_sm(c->gather_variant);
     if (const char* ev = getenv("NZ_GATHER_CTAS_PER_SM")) { const int v = atoi(ev); if (v >= 1 && v <= 16) c->gather_grid = c->sm_count * v; }
     c->inflate_grid = c->sm_count * nz_inflate_blocks_per_sm();
+    c->inflate_seg_grid = c->sm_count * nz_inflate_seg_blocks_per_sm();
+    if (const char* ev = getenv("NZ_INFL_SEG_KB")) { const int v = atoi(ev); if (v >= 16 && v <= 4096) c->idx_seg_bytes = (uint32_t)v << 10; }
+    if (const char* ev = getenv("NZ_INFL_INDEX")) c->idx_build = atoi(ev) != 0;
+    if (const char* ev = getenv("NZ_INFL_DEDUPE")) c->infl_dedupe = atoi(ev) != 0;
+    {   // temporary buffers of the index build come from the stream-ordered pool: keep what it has freed
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+            uint64_t keep = 1ull << 30;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     *out = c;
     return NZ_OK;
 }
@@ -514,75 +526,251 @@ int32_t nz_put_abort(nz_put* p) {
     return NZ_OK;
 }
 
+// ---------------------------------------------------------------------------
+// commit: CRC-32C chunk table + whole CRC (K3), checkpoint index of gzip members (k_inflate_index), batched publish (K6)
+// ---------------------------------------------------------------------------
+// Everything the commit kernels read or write on the host's behalf lives in one mapped pinned block: no memcpy calls,
+// one stream synchronisation per stage.  A single commit takes a recycled block; a batch allocates its own.
+struct CommitBlock { void* host = nullptr; void* dev = nullptr; size_t cap = 0; };
+struct CommitBlockPool {
+    std::mutex mu;
+    std::vector<CommitBlock> free_;
+    bool get(size_t need, CommitBlock* out) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            for (size_t i = 0; i < free_.size(); ++i)
+                if (free_[i].cap >= need) { *out = free_[i]; free_.erase(free_.begin() + i); return true; }
+        }
+        CommitBlock b;
+        b.cap = std::max<size_t>(round_up(need, 4096), 4096);
+        if (cudaHostAlloc(&b.host, b.cap, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (cudaHostGetDevicePointer(&b.dev, b.host, 0) != cudaSuccess) { cudaFreeHost(b.host); cudaGetLastError(); return false; }
+        *out = b;
+        return true;
+    }
+    void put(CommitBlock b) {
+        if (b.cap <= 8192) { std::lock_guard<std::mutex> g(mu); if (free_.size() < 64) { free_.push_back(b); return; } }
+        cudaFreeHost(b.host);
+    }
+};
+static CommitBlockPool g_commit_blocks;
+
+static uint64_t idx_blob_bytes(const NzIdxResult& r) {
+    return sizeof(NzIdxHeader) + (uint64_t)r.n_seg * sizeof(NzIdxSeg) + (uint64_t)r.n_grp * (sizeof(NzIdxGrp) + NZ_IDX_SUBS * 4) +
+           round_up(r.side_bytes, 16);
+}
+
+int32_t nz_put_commit_many(nz_put** puts, uint32_t n, const uint32_t* expected, const int32_t* has_expected,
+                           uint32_t* out_crc, int32_t* out_status) {
+    if (!puts || !n) return NZ_EINVAL;
+    for (uint32_t i = 0; i < n; ++i) if (!puts[i] || puts[i]->ctx != puts[0]->ctx) return NZ_EINVAL;
+    nz_ctx* c = puts[0]->ctx;
+    std::vector<int32_t> st(n, NZ_OK);
+    std::vector<uint32_t> desc_of(n, 0xFFFFFFFFu);
+    std::vector<uint64_t> idx_off(n, 0), idx_len(n, 0), raw_final(n, 0);
+    std::vector<uint8_t> inflatable(n, 0);
+    for (uint32_t i = 0; i < n; ++i) raw_final[i] = puts[i]->raw_len;
+    CommitBlock blk;
+    int32_t rc = NZ_OK;
+    cudaError_t e = cudaSetDevice(c->device);
+    cudaStream_t cs = puts[0]->stream;
+    // block layout
+    const size_t o_items = 0;
+    const size_t o_jobs = o_items + (size_t)n * sizeof(NzPubItem);
+    const size_t o_results = o_jobs + (size_t)n * sizeof(NzIdxJob);
+    const size_t o_ires = o_results + (size_t)n * sizeof(NzIdxResult);
+    const size_t o_crc = o_ires + (size_t)n * sizeof(NzDevRes);
+    const size_t o_status = o_crc + round_up((size_t)n * 4, 16);
+    const size_t o_trailer = o_status + round_up((size_t)n * 4, 16);
+    const size_t need = o_trailer + (size_t)n * 8;
+    NzPubItem* items = nullptr; NzIdxJob* jobs = nullptr; NzIdxResult* results = nullptr; NzDevRes* ires = nullptr;
+    uint32_t* crcs = nullptr; int32_t* pst = nullptr; uint32_t* trailers = nullptr;
+    auto dev_of = [&](const void* hostp) { return (void*)((char*)blk.dev + ((const char*)hostp - (const char*)blk.host)); };
+    if (e != cudaSuccess) { rc = cuda_fail(e, "cudaSetDevice"); goto done; }
+    if (!g_commit_blocks.get(need, &blk)) { rc = NZ_ENOMEM; goto done; }
+    items = (NzPubItem*)((char*)blk.host + o_items); jobs = (NzIdxJob*)((char*)blk.host + o_jobs);
+    results = (NzIdxResult*)((char*)blk.host + o_results); ires = (NzDevRes*)((char*)blk.host + o_ires);
+    crcs = (uint32_t*)((char*)blk.host + o_crc); pst = (int32_t*)((char*)blk.host + o_status);
+    trailers = (uint32_t*)((char*)blk.host + o_trailer);
+    // ---- 1. chunk table + whole-object CRC-32C of every object, each on the stream that carries its fill copies ----
+    for (uint32_t i = 0; i < n; ++i) {
+        nz_put* p = puts[i];
+        crcs[i] = 0;
+        uint32_t* tab = reinterpret_cast<uint32_t*>(c->arena + p->crc_tab_off);
+        e = nz_launch_crc_chunks(c->arena + p->arena_off, p->stored_len, tab, (uint32_t*)dev_of(&crcs[i]), c->crc_tables, c->sm_count, p->stream);
+        c->launches += 2;
+        if (e != cudaSuccess) { rc = cuda_fail(e, "crc kernels"); goto done; }
+    }
+    {
+        std::vector<cudaStream_t> seen;
+        for (uint32_t i = 0; i < n; ++i) {
+            if (std::find(seen.begin(), seen.end(), puts[i]->stream) != seen.end()) continue;
+            seen.push_back(puts[i]->stream);
+            e = cudaStreamSynchronize(puts[i]->stream);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "crc sync"); goto done; }
+        }
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        if (out_crc) out_crc[i] = crcs[i];
+        const bool has = expected && (!has_expected || has_expected[i]);
+        if (has && crcs[i] != expected[i]) { st[i] = NZ_ECORRUPT; c->corrupt++; }
+    }
+    // ---- 2. gzip members: inflate once, check trailer CRC-32 and ISIZE, record the checkpoint index ----
+    if (c->idx_build) {
+        std::vector<uint32_t> cand;
+        for (uint32_t i = 0; i < n; ++i) {
+            nz_put* p = puts[i];
+            if (st[i] != NZ_OK || !(p->flags & NZ_ENC_GZIP) || (p->flags & NZ_ENC_STRIPE) || p->stored_len < 18 || p->stored_len >= (1ull << 32)) continue;
+            e = cudaMemcpyAsync(&trailers[2 * i], c->arena + p->arena_off + p->stored_len - 8, 8, cudaMemcpyDeviceToHost, cs);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "trailer read"); goto done; }
+            cand.push_back(i);
+        }
+        if (!cand.empty()) {
+            e = cudaStreamSynchronize(cs);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "trailer sync"); goto done; }
+        }
+        static const uint64_t kBudget = [] { const char* ev = getenv("NZ_INDEX_TMP_MIB"); return (ev && atoll(ev) > 0 ? (uint64_t)atoll(ev) : 3072ull) << 20; }();
+        size_t ci = 0;
+        while (ci < cand.size()) {
+            // one round: as many members as fit the temporary budget
+            struct Carve { uint64_t out, seg, grp, delta, side; };
+            std::vector<uint32_t> round;
+            std::vector<Carve> carve;
+            uint64_t total = 4096;      // counters | then per round: infl | meta
+            for (; ci < cand.size(); ++ci) {
+                const uint32_t i = cand[ci];
+                nz_put* p = puts[i];
+                const uint64_t isize = trailers[2 * i + 1];
+                if (isize > p->stored_len * 1032ull + 1024 || isize >= 0xFFFFFF00ull) continue;      // not a deflate ratio: no index (GETs decline it)
+                const uint64_t seg_cap = isize / c->idx_seg_bytes + 2, grp_cap = isize / 2048 + p->stored_len / 2048 + 16;
+                const uint64_t side_cap = isize / 4 + 4096;
+                const uint64_t bytes = round_up(isize + 256, 256) + round_up(seg_cap * sizeof(NzIdxSeg), 256) + round_up(grp_cap * sizeof(NzIdxGrp), 256) +
+                                       round_up(grp_cap * NZ_IDX_SUBS * 4, 256) + round_up(side_cap, 256) + 256;
+                if (bytes > kBudget) continue;                                   // too large to index in one piece: legacy decode
+                if (!round.empty() && total + bytes > kBudget) break;
+                Carve cv;
+                cv.out = total; total += round_up(isize + 256, 256);
+                cv.seg = total; total += round_up(seg_cap * sizeof(NzIdxSeg), 256);
+                cv.grp = total; total += round_up(grp_cap * sizeof(NzIdxGrp), 256);
+                cv.delta = total; total += round_up(grp_cap * NZ_IDX_SUBS * 4, 256);
+                cv.side = total; total += round_up(side_cap, 256);
+                round.push_back(i);
+                carve.push_back(cv);
+            }
+            const uint32_t m = (uint32_t)round.size();
+            if (!m) continue;
+            const uint64_t o_infl = total; total += round_up((uint64_t)m * sizeof(NzInflWork), 256);
+            const uint64_t o_meta = total; total += round_up((uint64_t)m * 8, 256);
+            char* tmp = nullptr;
+            if (cudaMallocAsync((void**)&tmp, total, cs) != cudaSuccess) { cudaGetLastError(); continue; }    // no room: these members go unindexed
+            for (uint32_t k = 0; k < m; ++k) {
+                const uint32_t i = round[k];
+                nz_put* p = puts[i];
+                const uint64_t isize = trailers[2 * i + 1];
+                NzIdxJob& j = jobs[k];
+                j.src = (uint64_t)(c->arena + p->arena_off); j.src_len = p->stored_len;
+                j.out = (uint64_t)(tmp + carve[k].out); j.out_cap = isize;
+                j.seg = (uint64_t)(tmp + carve[k].seg); j.grp = (uint64_t)(tmp + carve[k].grp);
+                j.delta = (uint64_t)(tmp + carve[k].delta); j.side = (uint64_t)(tmp + carve[k].side);
+                j.side_cap = isize / 4 + 4096;
+                j.seg_cap = (uint32_t)(isize / c->idx_seg_bytes + 2); j.grp_cap = (uint32_t)(isize / 2048 + p->stored_len / 2048 + 16);
+                j.seg_bytes = c->idx_seg_bytes; j.pad = 0; j.dest = 0;
+                memset(&results[k], 0, sizeof(NzIdxResult));
+                results[k].status = -1;
+                memset(&ires[k], 0, sizeof(NzDevRes));
+            }
+            e = nz_launch_index((const NzIdxJob*)dev_of(jobs), (NzIdxResult*)dev_of(results), m, (uint32_t*)tmp, (NzInflWork*)(tmp + o_infl),
+                                (uint64_t*)(tmp + o_meta), (NzDevRes*)dev_of(ires), c->crc_tables, c->sm_count, cs);
+            c->launches += 2;
+            if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "index build"); cudaFreeAsync(tmp, cs); goto done; }
+            for (uint32_t k = 0; k < m; ++k) {
+                const uint32_t i = round[k];
+                const NzIdxResult& r = results[k];
+                if (r.status < 0 || ires[k].status != NZ_OK) continue;          // malformed member or CRC-32 mismatch: stored as is, inflate GETs decline it (SPEC G4)
+                raw_final[i] = r.raw_len;                                       // the member's real inflated length
+                inflatable[i] = 1;
+                if (r.status != 0) continue;                                    // valid, but too fragmented to index within the caps
+                const uint64_t bytes = idx_blob_bytes(r);
+                uint64_t off = 0;
+                {
+                    std::lock_guard<std::mutex> g(c->mu);
+                    if (!arena_alloc(c, bytes, &off)) continue;                 // arena full: serve it through the whole-member decode
+                }
+                idx_off[i] = off; idx_len[i] = bytes;
+                jobs[k].dest = (uint64_t)(c->arena + off);
+            }
+            e = nz_launch_index_pack((const NzIdxJob*)dev_of(jobs), (const NzIdxResult*)dev_of(results), m, cs);
+            c->launches += 1;
+            if (e == cudaSuccess) e = cudaFreeAsync(tmp, cs);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(cs);                // the jobs array (pinned) is reused by the next round
+            if (e != cudaSuccess) { rc = cuda_fail(e, "index pack"); goto done; }
+        }
+    }
+    // ---- 3. publish: descriptors + table slots in one launch ----
+    {
+        uint32_t m = 0;
+        std::vector<uint32_t> who;
+        {
+            std::lock_guard<std::mutex> g(c->mu);
+            for (uint32_t i = 0; i < n; ++i) {
+                if (st[i] != NZ_OK) continue;
+                if (c->free_desc.empty()) { st[i] = NZ_ENOMEM; continue; }
+                desc_of[i] = c->free_desc.back();
+                c->free_desc.pop_back();
+                nz_put* p = puts[i];
+                NzPubItem& it = items[m];
+                memset(&it, 0, sizeof it);
+                it.k0 = p->k0; it.k1 = p->k1; it.gen = c->gen++; it.desc_idx = desc_of[i];
+                it.d.arena_off = p->arena_off; it.d.stored_len = p->stored_len; it.d.raw_len = raw_final[i]; it.d.user_meta = p->user_meta;
+                it.d.crc_tab_off = p->crc_tab_off; it.d.flags = p->flags | (inflatable[i] ? NZ_ENC_INFLATABLE : 0u); it.d.crc32c = crcs[i]; it.d.n_chunks = p->n_chunks;
+                it.d.gen = (uint32_t)it.gen; it.d.stripe_bytes = idx_off[i];
+                pst[m] = NZ_ECUDA;
+                who.push_back(i);
+                ++m;
+            }
+        }
+        if (m) {
+            e = nz_launch_publish(c->table, c->n_lines - 1, c->descs, (const NzPubItem*)dev_of(items), m, (int32_t*)dev_of(pst), cs);
+            c->launches += 1;
+            if (e == cudaSuccess) e = cudaStreamSynchronize(cs);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "publish"); goto done; }
+            for (uint32_t k = 0; k < m; ++k) st[who[k]] = pst[k];
+        }
+    }
+done:
+    if (rc != NZ_OK) for (uint32_t i = 0; i < n; ++i) if (st[i] == NZ_OK) st[i] = rc;
+    if (rc != NZ_OK) for (uint32_t i = 0; i < n; ++i) cudaStreamSynchronize(puts[i]->stream);
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        for (uint32_t i = 0; i < n; ++i) {
+            nz_put* p = puts[i];
+            if (st[i] == NZ_OK) {
+                NzHostObj& ho = c->shadow[{p->k0, p->k1}];
+                ho.desc = desc_of[i]; ho.crc_whole = crcs ? crcs[i] : 0; ho.crc_tab_off = p->crc_tab_off;
+                ho.raw_len = raw_final[i]; ho.idx_off = idx_off[i]; ho.idx_len = idx_len[i];
+                if (inflatable[i]) ho.flags |= NZ_ENC_INFLATABLE;
+                c->index_bytes += idx_len[i];
+            } else {
+                if (desc_of[i] != 0xFFFFFFFFu) c->free_desc.push_back(desc_of[i]);
+                if (idx_len[i]) arena_free(c, idx_off[i], idx_len[i]);
+            }
+        }
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        if (st[i] == NZ_OK) { c->puts++; c->put_bytes += puts[i]->stored_len; }
+        if (out_status) out_status[i] = st[i];
+        put_release(puts[i], st[i] != NZ_OK);
+    }
+    if (blk.host) g_commit_blocks.put(blk);
+    return rc;
+}
+
 int32_t nz_put_commit(nz_put* p, uint32_t expected, int32_t has_expected, uint32_t* out_crc) {
     if (!p) return NZ_EINVAL;
-    nz_ctx* c = p->ctx;
-    int32_t rc = NZ_OK;
-    Mailbox* mb = nullptr;
-    uint32_t desc_idx = 0xFFFFFFFFu;
-    cudaError_t e = cudaSetDevice(c->device);
-    if (e != cudaSuccess) { rc = cuda_fail(e, "cudaSetDevice"); goto fail; }
-    mb = g_mail.get();
-    if (!mb) { rc = NZ_ENOMEM; goto fail; }
-    {
-        void* mb_dev = nullptr;
-        e = cudaHostGetDevicePointer(&mb_dev, mb, 0);
-        if (e != cudaSuccess) { rc = cuda_fail(e, "cudaHostGetDevicePointer"); goto fail; }
-        uint32_t* tab = reinterpret_cast<uint32_t*>(c->arena + p->crc_tab_off);
-        e = nz_launch_crc_chunks(c->arena + p->arena_off, p->stored_len, tab, &((Mailbox*)mb_dev)->crc, c->crc_tables,
-                                 c->sm_count, p->stream);
-        c->launches += 2;
-        if (e != cudaSuccess) { rc = cuda_fail(e, "crc kernels"); goto fail; }
-        e = cudaStreamSynchronize(p->stream);
-        if (e != cudaSuccess) { rc = cuda_fail(e, "crc sync"); goto fail; }
-        const uint32_t crc = mb->crc;
-        if (out_crc) *out_crc = crc;
-        if (has_expected && crc != expected) {
-            c->corrupt++;
-            rc = NZ_ECORRUPT;
-            goto fail;
-        }
-        {
-            std::lock_guard<std::mutex> g(c->mu);
-            if (c->free_desc.empty()) { rc = NZ_ENOMEM; goto fail; }
-            desc_idx = c->free_desc.back();
-            c->free_desc.pop_back();
-        }
-        NzDesc d;
-        memset(&d, 0, sizeof d);
-        d.arena_off = p->arena_off; d.stored_len = p->stored_len; d.raw_len = p->raw_len; d.user_meta = p->user_meta;
-        d.crc_tab_off = p->crc_tab_off; d.flags = p->flags; d.crc32c = crc; d.n_chunks = p->n_chunks;
-        uint64_t gen;
-        { std::lock_guard<std::mutex> g(c->mu); gen = c->gen++; }
-        d.gen = (uint32_t)gen;
-        e = cudaMemcpyAsync(c->descs + desc_idx, &d, sizeof d, cudaMemcpyHostToDevice, p->stream);
-        if (e != cudaSuccess) { rc = cuda_fail(e, "desc upload"); goto fail; }
-        e = nz_launch_insert(c->table, c->n_lines - 1, p->k0, p->k1, desc_idx, gen, &((Mailbox*)mb_dev)->status, p->stream);
-        c->launches += 1;
-        if (e != cudaSuccess) { rc = cuda_fail(e, "insert"); goto fail; }
-        e = cudaStreamSynchronize(p->stream);
-        if (e != cudaSuccess) { rc = cuda_fail(e, "insert sync"); goto fail; }
-        rc = mb->status;
-        if (rc != NZ_OK) goto fail;
-        {
-            std::lock_guard<std::mutex> g(c->mu);
-            NzHostObj& ho = c->shadow[{p->k0, p->k1}];
-            ho.desc = desc_idx;
-            ho.crc_whole = crc;
-            ho.crc_tab_off = p->crc_tab_off;
-        }
-        c->puts++;
-        c->put_bytes += p->stored_len;
-        g_mail.put(mb);
-        put_release(p, false);
-        return NZ_OK;
-    }
-fail:
-    if (desc_idx != 0xFFFFFFFFu) { std::lock_guard<std::mutex> g(c->mu); c->free_desc.push_back(desc_idx); }
-    if (mb) g_mail.put(mb);
-    cudaStreamSynchronize(p->stream);
-    put_release(p, true);
-    return rc;
+    int32_t st = NZ_OK;
+    const int32_t rc = nz_put_commit_many(&p, 1, &expected, &has_expected, out_crc, &st);
+    return rc != NZ_OK ? rc : st;
 }
 
 int32_t nz_evict(nz_ctx* c, const uint8_t key[16]) {
@@ -605,14 +793,36 @@ int32_t nz_evict(nz_ctx* c, const uint8_t key[16]) {
     cudaError_t e = nz_launch_erase(c->table, c->n_lines - 1, k0, k1, &((Mailbox*)mb_dev)->status, c->put_stream);
     c->launches += 1;
     if (e != cudaSuccess) { g_mail.put(mb); return cuda_fail(e, "erase"); }
-    // in-flight GETs may still be reading the extent: drain the device before the bytes are reused
-    e = cudaDeviceSynchronize();
+    e = cudaStreamSynchronize(c->put_stream);
     int32_t rc = mb->status;
     g_mail.put(mb);
     if (e != cudaSuccess) return cuda_fail(e, "erase sync");
+    // The slot is a tombstone now, so no wave submitted from here on can resolve the key.  Waves submitted BEFORE may have
+    // probed it while it was live and may still be reading the extent: the bytes (and the descriptor) are handed back
+    // only after every one of those has finished.  Later waves are not waited for.
+    {
+        uint64_t barrier;
+        { std::lock_guard<std::mutex> g(c->tmu); barrier = c->submit_seq; }
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+            bool busy = false;
+            {
+                std::lock_guard<std::mutex> g(c->tmu);
+                for (auto it = c->inflight.begin(); it != c->inflight.end() && it->first <= barrier; ++it) {
+                    const cudaError_t q = cudaEventQuery(it->second->ev_done);
+                    if (q == cudaErrorNotReady) { busy = true; break; }
+                    if (q != cudaSuccess) cudaGetLastError();
+                }
+            }
+            if (!busy) break;
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5)) { cudaDeviceSynchronize(); break; }
+            std::this_thread::sleep_for(std::chrono::microseconds(20));
+        }
+    }
     {
         std::lock_guard<std::mutex> g(c->mu);
         arena_free(c, ho.arena_off, ho.arena_len);
+        if (ho.idx_len) { arena_free(c, ho.idx_off, ho.idx_len); c->index_bytes -= ho.idx_len; }
         c->free_desc.push_back(ho.desc);
     }
     c->evictions++;
@@ -737,12 +947,18 @@ static bool plan_staged_copies(const nz_get_req* reqs, uint32_t n, uint64_t nseg
 
 // Verify work bound + inflate scratch sizing come from the host shadow (metadata only; the data path itself
 // resolves keys on the device).  scratch_need is empty when no request asks for inflate.
-static void size_verify_and_scratch(nz_ctx* c, const nz_get_req* reqs, uint32_t n, uint64_t& ver_cap, std::vector<uint64_t>& scratch_need) {
+// Inflate dedupe: the first inflate request of every distinct gzip key of the wave is its LEADER (leader[i] == i);
+// the others follow it (leader[i] = the leader's index) and are served by a copy out of the leader's scratch.
+static void size_verify_and_scratch(nz_ctx* c, const nz_get_req* reqs, uint32_t n, uint64_t& ver_cap, std::vector<uint64_t>& scratch_need,
+                                    std::vector<uint32_t>& leader) {
+    std::unordered_map<std::pair<uint64_t, uint64_t>, uint32_t, KeyHash> first;
+    std::vector<uint8_t> followed(scratch_need.empty() ? 0 : n, 0);
     std::lock_guard<std::mutex> g(c->mu);
     for (uint32_t i = 0; i < n; ++i) {
         const nz_get_req& r = reqs[i];
         if (!(r.flags & (NZ_GET_INFLATE | NZ_GET_VERIFY))) continue;
-        auto it = c->shadow.find({rd64(r.key), rd64(r.key + 8)});
+        const std::pair<uint64_t, uint64_t> key{rd64(r.key), rd64(r.key + 8)};
+        auto it = c->shadow.find(key);
         if (it == c->shadow.end() || it->second.desc == 0xFFFFFFFFu) continue;
         const NzHostObj& ho = it->second;
         const bool inflate = (r.flags & NZ_GET_INFLATE) && (ho.flags & NZ_ENC_GZIP);
@@ -751,9 +967,17 @@ static void size_verify_and_scratch(nz_ctx* c, const nz_get_req* reqs, uint32_t 
             if (inflate || r.nseg == 0) ver_cap += all;
             else for (uint32_t k = 0; k < r.nseg; ++k) ver_cap += std::min<uint64_t>(all, r.segs[k].len / NZ_CRC_CHUNK + 2);
         }
+        if (!inflate || scratch_need.empty()) continue;
+        auto ins = c->infl_dedupe ? first.emplace(key, i) : std::make_pair(first.end(), true);
+        if (!ins.second) {                                    // a follower: its leader inflates into scratch
+            const uint32_t L = ins.first->second;
+            leader[i] = L;
+            if (!followed[L]) { followed[L] = 1; scratch_need[L] = ho.raw_len; }
+            continue;
+        }
         // the LZ77 window is the output itself: it must live in HBM, so ranges and host
         // destinations inflate into device scratch first and are then gathered out
-        if (inflate && !scratch_need.empty() && (r.nseg != 0 || r.dst->kind != NZ_BUF_DEVICE)) scratch_need[i] = ho.raw_len;
+        if (r.nseg != 0 || r.dst->kind != NZ_BUF_DEVICE) scratch_need[i] = ho.raw_len;
     }
 }
 
@@ -783,7 +1007,9 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
                      plan_staged_copies(reqs, n, nseg, dma_copies, dma_bytes);
     uint64_t ver_cap = 0;
     std::vector<uint64_t> scratch_need(any_inflate ? n : 0, 0);
-    if (any_inflate || any_verify) size_verify_and_scratch(c, reqs, n, ver_cap, scratch_need);
+    std::vector<uint32_t> leader(any_inflate ? n : 0);
+    for (uint32_t i = 0; i < (uint32_t)leader.size(); ++i) leader[i] = i;
+    if (any_inflate || any_verify) size_verify_and_scratch(c, reqs, n, ver_cap, scratch_need, leader);
     if (ver_cap > 0xfffffff0ull) return NZ_EINVAL;
 
     const size_t pin_reqs = round_up((size_t)n * sizeof(NzDevReq), 256);
@@ -798,7 +1024,11 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     const size_t dev_rq = (size_t)n * 48;                        // rq_src, rq_len, infl_meta, rq_tab, rq_ssz, rq_stat(+pad)
     const size_t dev_stage = round_up((size_t)n * sizeof(NzDevReq), 256) + round_up((size_t)nseg * sizeof(NzDevSeg), 256);
     const size_t dev_segver = any_verify ? round_up((size_t)nseg * 4, 256) : 0;
-    nz_ticket* t = ticket_acquire(c, pin_reqs + pin_segs + pin_res, dev_work + dev_tiles + dev_chain + dev_ver + dev_cnt + round_up(dev_infl + dev_rq, 256) + dev_stage + dev_segver);
+    const size_t dev_iseg = any_inflate ? round_up((size_t)(n + 1) * 4, 256) : 0;          // inflate members' segment prefix
+    uint32_t coal_cap = 0;                                                                 // request-coalescing hash table for waves beyond 2048 slices
+    if (c->coalesce && nseg > 2048) { coal_cap = 8192; while (coal_cap < 2 * nseg) coal_cap <<= 1; }
+    const size_t dev_coal = (size_t)coal_cap * 4;
+    nz_ticket* t = ticket_acquire(c, pin_reqs + pin_segs + pin_res, dev_work + dev_tiles + dev_chain + dev_ver + dev_cnt + round_up(dev_infl + dev_rq, 256) + dev_stage + dev_segver + dev_iseg + dev_coal);
     if (!t) { cudaGetLastError(); snprintf(tl_err, sizeof tl_err, "ticket allocation failed"); return NZ_ENOMEM; }
     t->n = n; t->nseg = (uint32_t)nseg;
 
@@ -835,6 +1065,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
         d.whole = r.nseg == 0 && !striped;
         d.nseg = striped ? (uint32_t)split[i].size() : (r.nseg ? r.nseg : 1);
         d.scratch = 0; d.scratch_cap = 0;
+        d.infl_leader = any_inflate ? leader[i] : i; d.pad0 = 0; d.pad1 = 0;
         if (any_inflate && scratch_need[i]) {
             d.scratch = (uint64_t)(uintptr_t)((char*)t->scratch + scratch_off);
             d.scratch_cap = scratch_need[i];
@@ -896,10 +1127,13 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
         a.reqs_dev = reinterpret_cast<NzDevReq*>(stg);
         a.segs_dev = reinterpret_cast<NzDevSeg*>(stg + round_up((size_t)n * sizeof(NzDevReq), 256));
         a.seg_ver = any_verify ? reinterpret_cast<uint32_t*>(stg + dev_stage) : nullptr;
+        a.infl_seg_begin = any_inflate ? reinterpret_cast<uint32_t*>(stg + dev_stage + dev_segver) : nullptr;
+        a.coal_tab = coal_cap ? reinterpret_cast<int32_t*>(stg + dev_stage + dev_segver + dev_iseg) : nullptr;
+        a.coal_cap = coal_cap;
     }
     a.ver_stat = reinterpret_cast<uint32_t*>(a.res + n);
     t->ver_stat = reinterpret_cast<uint32_t*>(hres + n);
-    t->ver_stat[0] = t->ver_stat[1] = t->ver_stat[2] = 0;
+    t->ver_stat[0] = t->ver_stat[1] = t->ver_stat[2] = t->ver_stat[3] = t->ver_stat[4] = 0;
     t->flag_wait = false;
     a.fuse_verify = (any_verify && ver_cap && c->fuse_verify && nz_gather_fuses_verify(variant)) ? 1u : 0u;
     a.peer_base = c->peer_base_dev;
@@ -953,9 +1187,12 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     t->ran_inflate = any_inflate;
     if (any_inflate) {
         if (t->profiled) CKT(cudaEventRecord(t->ev_i0, s));
-        CKT(nz_launch_inflate(a.infl, a.infl_meta, a.counters, a.res, c->crc_tables, c->inflate_grid, c->sm_count, s));
+        // members with a checkpoint index: one warp per segment; members without: one warp per member + trailer CRC-32
+        // (whether any of those exist is only known on the device: the legacy kernels find an empty work list otherwise)
+        CKT(nz_launch_inflate(a.infl, a.infl_meta, a.counters, a.res, c->crc_tables, c->inflate_grid, c->sm_count, s,
+                              a.infl_seg_begin, a.reqs_dev, n, c->inflate_seg_grid, true));
         if (t->profiled) CKT(cudaEventRecord(t->ev_i1, s));
-        c->launches += 2;
+        c->launches += 3;
     }
     if (t->profiled) CKT(cudaEventRecord(t->ev_g0, s));
     int ggrid = c->gather_grid;
@@ -988,6 +1225,11 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     }
     CKT(cudaEventRecord(t->ev_done, s));
 #undef CKT
+    {
+        std::lock_guard<std::mutex> g(c->tmu);
+        t->seq = ++c->submit_seq;
+        c->inflight[t->seq] = t;
+    }
     *out = t;
     return NZ_OK;
 }
@@ -1059,7 +1301,7 @@ int32_t nz_get_wait(nz_ticket* t, int64_t timeout_us, nz_get_res* res) {
     if (!t->req_bytes_hint) {   // count a wave once even if waited twice
         t->req_bytes_hint = 1;
         c->gets += t->n; c->get_bytes += bytes; c->hits += hits; c->misses += misses; c->corrupt += corrupt;
-        if (t->ver_stat) { c->verify_chunks += t->ver_stat[0]; c->verify_fused += t->ver_stat[1]; }
+        if (t->ver_stat) { c->verify_chunks += t->ver_stat[0]; c->verify_fused += t->ver_stat[1]; c->infl_segs += t->ver_stat[3]; c->infl_whole += t->ver_stat[4]; }
     }
     return NZ_OK;
 }
@@ -1098,6 +1340,7 @@ int32_t nz_ticket_free(nz_ticket* t) {
     t->req_bytes_hint = 0;
     t->stream = nullptr;
     std::lock_guard<std::mutex> g(c->tmu);
+    if (t->seq) { c->inflight.erase(t->seq); t->seq = 0; }
     if (c->ticket_pool.size() < 64) c->ticket_pool.push_back(t);
     else ticket_destroy(t);
     return NZ_OK;
@@ -1137,6 +1380,7 @@ int32_t nz_get_stats(nz_ctx* c, nz_stats* out) {
     out->verify_chunks = c->verify_chunks;
     out->verify_fused_chunks = c->verify_fused;
     out->host_dma_waves = c->dma_waves;
+    out->inflate_segments = c->infl_segs; out->inflate_whole_members = c->infl_whole; out->index_bytes = c->index_bytes;
     return NZ_OK;
 }
 

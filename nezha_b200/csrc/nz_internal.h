@@ -40,6 +40,7 @@ struct __align__(64) NzDesc {
     uint32_t n_chunks;
     uint32_t gen;
     uint64_t stripe_bytes;   // striped objects: stripe size; arena_off then points at the NzDevStripe map, n_chunks = stripes
+                             // gzip objects (never striped): arena offset of the checkpoint index (NzIdxHeader), 0 = none
 };
 static_assert(sizeof(NzSlot) == 32, "slot");
 static_assert(sizeof(NzDesc) == 64, "desc");
@@ -55,7 +56,12 @@ struct __align__(16) NzDevReq {
     uint32_t whole;        // 1 = pseudo segment: serve [0, length)
     uint64_t scratch;      // device address of the inflate scratch (0 = inflate straight to dst)
     uint64_t scratch_cap;
+    uint32_t infl_leader;  // inflate dedupe: index of the request in this wave that inflates this key (== own index for a
+                           // leader); followers are served by a copy from the leader's scratch
+    uint32_t pad0;
+    uint64_t pad1;
 };
+static_assert(sizeof(NzDevReq) == 80, "req layout");
 struct __align__(8) NzDevSeg {
     uint64_t src_off, len, dst_off;
     uint32_t req;
@@ -83,7 +89,67 @@ struct __align__(16) NzInflWork {
     uint64_t dst_cap;
     uint32_t req;
     uint32_t pad;
+    uint64_t idx;          // device address of the member's checkpoint index (NzIdxHeader), 0 = none: legacy whole-member decode
 };
+static_assert(sizeof(NzInflWork) == 48, "inflate work layout");
+
+// ---------------------------------------------------------------------------
+// Checkpoint index of a gzip member (built once at nz_put_commit by k_inflate_index, kept in the arena next to the
+// member).  DEFLATE is bit-serial, so a GET gets its parallelism from the index:
+//   member -> SEGMENTS  (~128 KiB of output, one warp each, independent of each other: the bytes a segment's matches
+//                        copy from before its own start are kept verbatim in the index = "side bytes", in stream order)
+//          -> GROUPS    (<= 32 sub-segments of one deflate block = one warp iteration; tables are shared)
+//          -> SUB-SEGMENTS (<= NZ_IDX_T tokens, one lane each: bit length and output length as u16 deltas)
+// Layout of the blob: NzIdxHeader | NzIdxSeg[n_seg] | NzIdxGrp[n_grp] | u32 delta[n_grp][32] | side bytes.
+// ---------------------------------------------------------------------------
+constexpr uint32_t NZ_IDX_MAGIC = 0x58495A4Eu;      // "NZIX"
+constexpr uint32_t NZ_IDX_T = 64;                   // tokens (literal or match) per sub-segment
+constexpr uint32_t NZ_IDX_SUBS = 32;                // sub-segments per group
+constexpr uint32_t NZ_IDX_GRP_STORED = 1u;          // group = one stored block (type 0): tok_bit = 8 * byte offset of its data, hdr_bit = its length
+struct __align__(16) NzIdxHeader {
+    uint32_t magic, version;
+    uint32_t n_seg, n_grp;
+    uint64_t raw_len;
+    uint64_t side_bytes;
+    uint64_t off_seg, off_grp, off_delta, off_side;  // byte offsets from the header
+};
+struct __align__(16) NzIdxSeg {
+    uint64_t out_start, out_len;     // the segment's slice of the inflated output
+    uint64_t side_off;               // its side bytes start here (consumed in stream order)
+    uint32_t first_grp, n_grp;
+};
+struct __align__(16) NzIdxGrp {
+    uint64_t tok_bit;                // bit offset (from the member's first byte) of the group's first token
+    uint64_t out_off;                // output offset of the group's first byte
+    uint64_t hdr_bit;                // bit offset of the 3-bit header of the deflate block the group belongs to
+    uint32_t n_sub;                  // 1..32 (0 for a stored block)
+    uint32_t flags;                  // NZ_IDX_GRP_*
+};
+static_assert(sizeof(NzIdxHeader) == 64 && sizeof(NzIdxSeg) == 32 && sizeof(NzIdxGrp) == 32, "index layout");
+
+// one member to index (k_inflate_index: one warp per job) and what came out
+struct __align__(16) NzIdxJob {
+    uint64_t src, src_len;           // the stored member
+    uint64_t out, out_cap;           // temporary inflated output (cap = the trailer's ISIZE)
+    uint64_t seg, grp, delta, side;  // temporary index arrays
+    uint64_t side_cap;
+    uint32_t seg_cap, grp_cap;
+    uint32_t seg_bytes, pad;
+    uint64_t dest;                   // filled by the host before k_index_pack: device address of the final blob (0 = none)
+};
+struct __align__(16) NzIdxResult {
+    int32_t  status;                 // 0 = member valid and indexed, 1 = member valid but the index outgrew its caps, -1 = malformed
+    uint32_t n_seg, n_grp;
+    uint32_t crc32;                  // trailer CRC-32 (checked by k_inflate_crc against the temporary output)
+    uint64_t raw_len, side_bytes;
+};
+// batched publish (K6): descriptor + key of one object
+struct NzPubItem {
+    uint64_t k0, k1, gen;
+    uint32_t desc_idx, pad;
+    NzDesc d;
+};
+
 struct __align__(8) NzDevRes {   // mirrors nz_get_res
     int32_t  status;
     uint32_t flags;
@@ -143,6 +209,7 @@ struct NzHostObj {     // host shadow of a live object (arena bookkeeping, EEXIS
     uint64_t arena_off, arena_len;
     uint64_t stored_len, raw_len;
     uint32_t flags;
+    uint64_t idx_off = 0, idx_len = 0;   // gzip objects: extent of the checkpoint index (0 = none)
 };
 
 struct KeyHash {
@@ -163,6 +230,7 @@ struct nz_ticket {
     bool ran_inflate = false;
     bool own_stream = false;
     uint64_t req_bytes_hint = 0;
+    uint64_t seq = 0;                  // submit order (ctx->inflight)
     bool flag_wait = false;            // fused small wave: completion is the pinned flag ver_stat[2], no event query needed
     bool paced = false;                // counted in ctx->paced_inflight
     uint32_t* ver_stat = nullptr;      // pinned: {verify chunks emitted, of which checksummed inside the gather}
@@ -190,6 +258,7 @@ struct nz_ctx {
     bool coalesce = true;   // env NZ_COALESCE=0 turns request coalescing off (A/B measurements)
     int gather_variant = 14; // k_gather variant: 14 = TMA bulk-copy staging (default, measured best); 0-13 register paths (env NZ_GATHER_VARIANT)
     int inflate_grid;
+    int inflate_seg_grid;
     uint8_t* arena = nullptr;
     uint64_t arena_bytes = 0;
     NzSlot* table = nullptr;
@@ -218,11 +287,17 @@ struct nz_ctx {
     std::atomic<int> paced_inflight{0};     // paced waves submitted and not yet seen complete
     int host_variant = -1;                  // gather variant for such waves (-1 = gather_variant); env NZ_HOST_VARIANT
     std::atomic<int> host_grid{32};                     // CTAs for waves that only write pinned host memory (PCIe bound: leave the SMs free)
-    // ticket recycling
+    // ticket recycling + the waves in flight (nz_evict frees an extent only after every wave submitted before the
+    // erase has finished: such a wave may have probed the slot while it was still live)
     std::mutex tmu;
     std::vector<nz_ticket*> ticket_pool;
+    uint64_t submit_seq = 0;
+    std::map<uint64_t, nz_ticket*> inflight;
+    uint32_t idx_seg_bytes = 128u << 10;    // env NZ_INFL_SEG_KB: output bytes per index segment (one warp each at GET time)
+    bool infl_dedupe = true;                // env NZ_INFL_DEDUPE=0: every inflate request decodes its member itself (A/B measurements)
+    bool idx_build = true;                  // env NZ_INFL_INDEX=0: commit builds no index (every inflate GET decodes the whole member in one warp)
     // stats
-    std::atomic<uint64_t> gets{0}, get_bytes{0}, hits{0}, misses{0}, puts{0}, put_bytes{0}, evictions{0}, corrupt{0}, launches{0}, file_cufile_bytes{0}, file_bounce_bytes{0}, verify_chunks{0}, verify_fused{0};
+    std::atomic<uint64_t> gets{0}, get_bytes{0}, hits{0}, misses{0}, puts{0}, put_bytes{0}, evictions{0}, corrupt{0}, launches{0}, file_cufile_bytes{0}, file_bounce_bytes{0}, verify_chunks{0}, verify_fused{0}, infl_segs{0}, infl_whole{0}, index_bytes{0};
     // bounce lanes for nz_put_file: one pinned allocation cut into lanes of 2 x 8 MiB; a call takes as many free
     // lanes as its length warrants (at least one, waiting if none is free), so files load concurrently
     void* bounce[2] = {nullptr, nullptr};
@@ -264,6 +339,9 @@ struct NzPlanArgs {
     uint32_t* rq_desc;          // n: descriptor index of every request (0xFFFFFFFF = miss), written in phase A
     uint32_t* seg_ver;          // nseg: first verify entry of a slice whose tiles are checksummed by the gather, else 0xFFFFFFFF
     uint32_t fuse_verify;       // 1 = the gather variant in use checksums tiles in shared memory
+    uint32_t* infl_seg_begin;   // n + 1: exclusive prefix of the inflate members' segment counts (k_inflate_seg's work list)
+    int32_t* coal_tab;          // coal_cap ints: hash table for request coalescing of waves too large for shared memory (or nullptr)
+    uint32_t coal_cap;          // power of two
     uint32_t* ver_stat;         // mapped pinned: [0] = verify chunks of this wave, [1] = of which fused (written by k_plan_verify),
                                 // [2] = completion flag of a fused small wave (written last by k_plan, polled by nz_get_wait)
 };
@@ -284,7 +362,14 @@ cudaError_t nz_launch_verify(const NzPlanArgs& a, const uint32_t* crc_tables, in
 cudaError_t nz_launch_crc_chunks(const uint8_t* p, uint64_t n, uint32_t* chunk_out, uint32_t* whole_out,
                                  const uint32_t* crc_tables, int sm_count, cudaStream_t s);
 cudaError_t nz_launch_inflate(const NzInflWork* infl, uint64_t* meta, uint32_t* counters, NzDevRes* res,
-                              const uint32_t* crc_tables, int grid, int sm_count, cudaStream_t s);
+                              const uint32_t* crc_tables, int grid, int sm_count, cudaStream_t s,
+                              const uint32_t* seg_begin, const NzDevReq* reqs, uint32_t n_req, int seg_grid, bool legacy);
+cudaError_t nz_launch_index(const NzIdxJob* jobs, NzIdxResult* results, uint32_t n, uint32_t* counters, NzInflWork* infl,
+                            uint64_t* meta, NzDevRes* res, const uint32_t* crc_tables, int sm_count, cudaStream_t s);
+cudaError_t nz_launch_index_pack(const NzIdxJob* jobs, const NzIdxResult* results, uint32_t n, cudaStream_t s);
+cudaError_t nz_launch_publish(NzSlot* table, uint64_t line_mask, NzDesc* descs, const NzPubItem* items, uint32_t n,
+                              int32_t* status, cudaStream_t s);
+int nz_inflate_seg_blocks_per_sm();
 int64_t nz_cufile_read(int fd, uint64_t file_off, void* dev_base, uint64_t dev_off, uint64_t len);
 cudaError_t nz_upload_constants(uint32_t* crc_tables_dev);
 cudaError_t nz_inflate_upload_constants();

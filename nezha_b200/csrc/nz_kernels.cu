@@ -33,6 +33,12 @@ __device__ __forceinline__ uint4 ldg_cached(const void* p) {  // neighbours re-r
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+__device__ __forceinline__ uint4 ldcg_ordered(const uint4* p) {   // L2 load the compiler may neither merge nor reorder
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
 __device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -56,10 +62,13 @@ __device__ __forceinline__ uint32_t probe_group4(const NzSlot* __restrict__ tabl
         uint32_t s_state = NZ_SLOT_BUSY, s_desc = 0;
         if (!done) {
             const uint4* sp = reinterpret_cast<const uint4*>(table + (line * 4 + q));
-            uint4 a = __ldcg(sp), b = __ldcg(sp + 1);
+            const uint4 a = ldcg_ordered(sp), b = ldcg_ordered(sp + 1);
+            // key and state/descriptor are two loads: if the slot was erased and re-used in between, the key read
+            // again afterwards differs and the slot is taken as busy (no match, not empty: the probe moves on)
+            const uint4 a2 = ldcg_ordered(sp);
             s_k0 = (uint64_t)a.x | ((uint64_t)a.y << 32);
             s_k1 = (uint64_t)a.z | ((uint64_t)a.w << 32);
-            s_state = b.x;
+            s_state = (a.x == a2.x && a.y == a2.y && a.z == a2.z && a.w == a2.w) ? b.x : (uint32_t)NZ_SLOT_BUSY;
             s_desc = b.y;
         }
         const bool match = !done && s_state == NZ_SLOT_LIVE && s_k0 == k0 && s_k1 == k1;
@@ -161,6 +170,40 @@ __global__ void k_erase(NzSlot* table, uint64_t line_mask, uint64_t k0, uint64_t
     *status = NZ_ENOTFOUND;
 }
 
+// Batched publish: one thread per object writes its descriptor, fences, then claims and publishes a slot exactly
+// like k_insert (the host reserved every key of the batch in its shadow, so no two threads insert the same key).
+__global__ void __launch_bounds__(128)
+k_publish(NzSlot* table, uint64_t line_mask, NzDesc* descs, const NzPubItem* __restrict__ items, uint32_t n, int32_t* status) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const NzPubItem it = items[i];
+    descs[it.desc_idx] = it.d;
+    __threadfence();
+    uint64_t line = it.k1 & line_mask;
+    for (uint64_t probe = 0; probe <= line_mask; ++probe) {
+        for (int q = 0; q < 4; ++q) {
+            NzSlot* s = table + line * 4 + q;
+            const uint32_t st = *(volatile uint32_t*)&s->state;
+            if (st == NZ_SLOT_LIVE) {
+                if (s->k0 == it.k0 && s->k1 == it.k1) { status[i] = NZ_EEXIST; return; }
+                continue;
+            }
+            if (st == NZ_SLOT_EMPTY || st == NZ_SLOT_TOMB) {
+                if (atomicCAS(&s->state, st, (uint32_t)NZ_SLOT_BUSY) == st) {
+                    s->k0 = it.k0; s->k1 = it.k1; s->desc = it.desc_idx; s->gen = it.gen;
+                    __threadfence();
+                    *(volatile uint32_t*)&s->state = NZ_SLOT_LIVE;
+                    status[i] = NZ_OK;
+                    return;
+                }
+            }
+            // NZ_SLOT_BUSY: another insert is writing this slot; it is not ours, move on
+        }
+        line = (line + 1) & line_mask;
+    }
+    status[i] = NZ_EFULL;
+}
+
 // ---------------------------------------------------------------------------
 // k_plan: one CTA turns a wave of GETs into copy / verify / inflate work.
 // ---------------------------------------------------------------------------
@@ -172,10 +215,41 @@ struct PlanScratch {
 // small waves: the planning CTA copies the few tiles itself (defined after copy_tile)
 __device__ void plan_fused_copy(const NzPlanArgs& a);
 
+// exclusive scan over the 1024 threads of the planning CTA (warp shuffles + one pass over the 32 warp totals);
+// *total (shared memory) receives the sum.  s_warp: 32 entries of shared memory.
+template <typename Tv>
+__device__ __forceinline__ Tv block_scan_excl_1024(Tv v, Tv* s_warp, Tv* total) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    Tv incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const Tv t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const Tv w = s_warp[lane];
+        Tv wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const Tv t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= (uint32_t)o) wi += t;
+        }
+        s_warp[lane] = wi - w;
+        if (lane == 31) *total = wi;
+    }
+    __syncthreads();
+    const Tv r = s_warp[warp] + incl - v;
+    __syncthreads();                                  // s_warp may be reused right away
+    return r;
+}
+
 template <bool SMALL, bool FUSED>
 __global__ void __launch_bounds__(1024, 1)
 k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint64_t* rq_ssz, const __grid_constant__ NzSmallWave small) {
-    __shared__ uint64_t s_scan[1024];
+    __shared__ uint64_t s_warp64[32];
+    __shared__ uint64_t s_total64;
     __shared__ uint64_t s_carry;
     const uint32_t tid = threadIdx.x;
     const uint32_t g = tid >> 2;
@@ -190,7 +264,7 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint6
         s4 = SMALL ? reinterpret_cast<const uint4*>(small.segs) : reinterpret_cast<const uint4*>(a.segs_host);
         d4 = reinterpret_cast<uint4*>(a.segs_dev);
         for (uint32_t i = tid; i < a.nseg * (uint32_t)(sizeof(NzDevSeg) / 16); i += 1024) d4[i] = s4[i];
-        if (tid < 4) a.counters[tid] = 0;
+        if (tid < 16) a.counters[tid] = 0;
     }
     __threadfence_block();
     __syncthreads();
@@ -238,13 +312,26 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint6
                     bytes += sg.len;
                 }
             }
-            if (out.status == NZ_OK) {
-                out.bytes = bytes;
-                if (inflate) {
+            if (out.status == NZ_OK) out.bytes = bytes;
+            if (inflate) {
+                // Inflate dedupe: the host names one LEADER per distinct key of the wave.  The leader's member is inflated
+                // once (into the leader's scratch when the key has several requesters or the request is not a whole-object
+                // GET into HBM, else straight into its destination); every requester is then a plain copy out of it.
+                const uint32_t L = rq.infl_leader;
+                if (L != r) {
+                    if (out.status == NZ_OK) {
+                        bool okl = L < a.n;
+                        NzDevReq lq;
+                        if (okl) lq = reqs[L];
+                        okl = okl && lq.scratch != 0 && lq.scratch_cap >= len && lq.k0 == rq.k0 && lq.k1 == rq.k1 && (lq.flags & NZ_GET_INFLATE);
+                        if (!okl) { out.status = NZ_ENOMEM; out.bytes = 0; }
+                        else src = lq.scratch;
+                    }
+                } else {
                     const bool direct = rq.whole && rq.scratch == 0;
-                    if (!direct && (rq.scratch == 0 || rq.scratch_cap < len)) {
-                        out.status = NZ_ENOMEM;
-                        out.bytes = 0;
+                    const bool have_out = direct ? out.status == NZ_OK : (rq.scratch != 0 && rq.scratch_cap >= len);
+                    if (!have_out) {
+                        if (out.status == NZ_OK) { out.status = NZ_ENOMEM; out.bytes = 0; }
                     } else {
                         const uint32_t slot = atomicAdd(&a.counters[1], 1u);
                         NzInflWork w;
@@ -252,23 +339,29 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint6
                         w.dst = direct ? rq.dst : rq.scratch;
                         w.dst_cap = len;             // exactly the inflated length (validated against dst/scratch above)
                         w.req = r; w.pad = direct ? 1u : 0u;
+                        w.idx = ds.stripe_bytes ? (uint64_t)(a.arena + ds.stripe_bytes) : 0;     // gzip objects: arena offset of the checkpoint index
                         a.infl[slot] = w;
-                        src = direct ? 0 : rq.scratch;   // direct: nothing left to gather
-                        if (direct) len = 0;
+                        a.infl_seg_begin[slot] = w.idx ? reinterpret_cast<const NzIdxHeader*>(w.idx)->n_seg : 0u;
+                        if (!w.idx) atomicAdd(&a.counters[5], 1u);      // members without an index: the whole-member kernel runs
+                        if (out.status == NZ_OK) {
+                            src = direct ? 0 : rq.scratch;   // direct: nothing left to gather
+                            if (direct) len = 0;
+                        }
                     }
                 }
-                // verify: inflate reads the whole member, so check every stored chunk
-                if (out.status == NZ_OK && (rq.flags & NZ_GET_VERIFY) && inflate) {
-                    const uint32_t* tab = reinterpret_cast<const uint32_t*>(a.arena + ds.crc_tab_off);
-                    const uint32_t first = atomicAdd(&a.counters[0], ds.n_chunks);
-                    for (uint32_t c = 0; c < ds.n_chunks && first + c < a.ver_cap; ++c) {
-                        NzVerWork v;
-                        const uint64_t off = (uint64_t)c * NZ_CRC_CHUNK;
-                        v.ptr = (uint64_t)(a.arena + ds.arena_off + off);
-                        v.len = (uint32_t)min((uint64_t)NZ_CRC_CHUNK, ds.stored_len - off);
-                        v.expect = tab[c]; v.req = r; v.seg = NZ_VER_NOSEG; v.acc = 0; v.got = 0;
-                        a.ver[first + c] = v;
-                    }
+            }
+            // verify: inflate reads the whole member, so check every stored chunk
+            if (out.status == NZ_OK && (rq.flags & NZ_GET_VERIFY) && inflate) {
+                const uint32_t* tab = reinterpret_cast<const uint32_t*>(a.arena + ds.crc_tab_off);
+                const uint32_t first = atomicAdd(&a.counters[0], ds.n_chunks);
+                if ((uint64_t)first + ds.n_chunks > a.ver_cap) { out.status = NZ_ENOMEM; out.bytes = 0; }   // never return unverified bytes as verified
+                for (uint32_t c = 0; c < ds.n_chunks && first + c < a.ver_cap; ++c) {
+                    NzVerWork v;
+                    const uint64_t off = (uint64_t)c * NZ_CRC_CHUNK;
+                    v.ptr = (uint64_t)(a.arena + ds.arena_off + off);
+                    v.len = (uint32_t)min((uint64_t)NZ_CRC_CHUNK, ds.stored_len - off);
+                    v.expect = tab[c]; v.req = r; v.seg = NZ_VER_NOSEG; v.acc = 0; v.got = 0;
+                    a.ver[first + c] = v;
                 }
             }
         }
@@ -282,6 +375,29 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint6
         a.res[r] = out;
     }
     __syncthreads();
+
+    // ---- phase A2: segment work list of the indexed inflate members (exclusive prefix of their segment counts) ----
+    {
+        const uint32_t ni = a.counters[1];
+        if (ni) {
+            __shared__ uint32_t s_warp32[32];
+            __shared__ uint32_t s_total32;
+            uint32_t carry = 0;
+            for (uint32_t base = 0; base < ni; base += 1024) {
+                const uint32_t i = base + tid;
+                const uint32_t v = i < ni ? a.infl_seg_begin[i] : 0u;
+                const uint32_t ex = block_scan_excl_1024<uint32_t>(v, s_warp32, &s_total32);
+                if (i < ni) a.infl_seg_begin[i] = carry + ex;
+                carry += s_total32;
+                __syncthreads();
+            }
+            if (tid == 0) {
+                a.infl_seg_begin[ni] = carry;
+                a.ver_stat[3] = carry;                 // statistics: index segments / members without an index in this wave
+                a.ver_stat[4] = a.counters[5];
+            }
+        }
+    }
 
     // ---- phase B1: per-segment copy work and tile counts ----------------------
     uint64_t* tile_cnt = a.tile_begin;           // counts first, scanned in place in B3
@@ -330,19 +446,23 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint6
     // worker pulls the same shard).  Slices with the same source, length and destination
     // phase are chained behind one leader: the gather loads each tile once and stores it to
     // every member, so HBM reads the source once instead of once per request.
-    if (a.coalesce && a.nseg > 1 && a.nseg <= 2048) {
+    if (a.coalesce && a.nseg > 1 && (a.nseg <= 2048 || a.coal_tab)) {
         __shared__ int s_tab[4096];
-        for (uint32_t i = tid; i < 4096; i += 1024) s_tab[i] = -1;
+        // waves of up to 2048 slices hash in shared memory, larger ones in a table the host put in HBM
+        int* tabp = a.nseg <= 2048 ? s_tab : a.coal_tab;
+        const uint32_t tmask = (a.nseg <= 2048 ? 4096u : a.coal_cap) - 1u;
+        for (uint32_t i = tid; i <= tmask; i += 1024) tabp[i] = -1;
+        __threadfence_block();
         __syncthreads();
         for (uint32_t s = tid; s < a.nseg; s += 1024) {
             if (tile_cnt[s] == 0) continue;
             const NzSegWork w = a.work[s];
             uint64_t hsh = w.src * 0x9E3779B97F4A7C15ull ^ (w.len + (w.dst & 127u)) * 0xC2B2AE3D27D4EB4Full;
-            uint32_t h = (uint32_t)(hsh >> 40) & 4095u;
+            uint32_t h = (uint32_t)(hsh >> 40) & tmask;
             for (;;) {
-                int cur = s_tab[h];
+                int cur = *(volatile int*)&tabp[h];
                 if (cur == -1) {
-                    cur = atomicCAS(&s_tab[h], -1, (int)s);
+                    cur = atomicCAS(&tabp[h], -1, (int)s);
                     if (cur == -1) break;                       // this slice leads its group
                 }
                 const NzSegWork o = a.work[cur];
@@ -351,7 +471,7 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint6
                     a.chain_next[s] = atomicExch(&a.chain_head[cur], s);
                     break;
                 }
-                h = (h + 1) & 4095u;
+                h = (h + 1) & tmask;
             }
         }
         __syncthreads();
@@ -363,19 +483,11 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint6
     for (uint32_t base = 0; base < a.nseg; base += 1024) {
         const uint32_t s = base + tid;
         const uint64_t tiles = s < a.nseg ? tile_cnt[s] : 0;
-        s_scan[tid] = tiles;
-        __syncthreads();
-        for (uint32_t ofs = 1; ofs < 1024; ofs <<= 1) {         // Hillis-Steele
-            uint64_t v = (tid >= ofs) ? s_scan[tid - ofs] : 0;
-            __syncthreads();
-            s_scan[tid] += v;
-            __syncthreads();
-        }
-        const uint64_t incl = s_scan[tid];
+        const uint64_t ex = block_scan_excl_1024<uint64_t>(tiles, s_warp64, &s_total64);
         const uint64_t carry = s_carry;
-        if (s < a.nseg) a.tile_begin[s] = carry + incl - tiles;
+        if (s < a.nseg) a.tile_begin[s] = carry + ex;
         __syncthreads();
-        if (tid == 1023) s_carry = carry + incl;
+        if (tid == 0) s_carry = carry + s_total64;
         __syncthreads();
     }
     if (tid == 0) a.tile_begin[a.nseg] = s_carry;
@@ -422,6 +534,13 @@ k_plan_verify(NzPlanArgs a) {
         if (lane == 0) first = atomicAdd(&a.counters[0], cnt);
         first = __shfl_sync(0xffffffffu, first, 0);
         const bool fits = (uint64_t)first + cnt <= a.ver_cap;
+        if (!fits && lane == 0) {                 // SPEC X4: a verify that cannot run is an error, never a silent NZ_OK
+            if (a.reqs_dev[sg.req].flags & NZ_GET_VERIFY) { a.res[sg.req].status = NZ_ENOMEM; a.res[sg.req].bytes = 0; }
+            for (uint32_t m = a.chain_head[s]; m != 0xFFFFFFFFu; m = a.chain_next[m]) {
+                const uint32_t r2 = a.segs_dev[m].req;
+                if (a.reqs_dev[r2].flags & NZ_GET_VERIFY) { a.res[r2].status = NZ_ENOMEM; a.res[r2].bytes = 0; }
+            }
+        }
         const bool fusable = a.fuse_verify && fits && ((w.src | w.dst) & 15u) == 0;
         for (uint32_t c = lane; c < cnt && first + c < a.ver_cap; c += 32) {
             NzVerWork v;
@@ -774,6 +893,12 @@ cudaError_t nz_launch_lookup(const NzSlot* table, uint64_t line_mask, const NzDe
 cudaError_t nz_launch_insert(NzSlot* table, uint64_t line_mask, uint64_t k0, uint64_t k1, uint32_t desc, uint64_t gen,
                              int32_t* status, cudaStream_t s) {
     k_insert<<<1, 32, 0, s>>>(table, line_mask, k0, k1, desc, gen, status);
+    return cudaGetLastError();
+}
+cudaError_t nz_launch_publish(NzSlot* table, uint64_t line_mask, NzDesc* descs, const NzPubItem* items, uint32_t n,
+                              int32_t* status, cudaStream_t s) {
+    if (!n) return cudaSuccess;
+    k_publish<<<(n + 127) / 128, 128, 0, s>>>(table, line_mask, descs, items, n, status);
     return cudaGetLastError();
 }
 cudaError_t nz_launch_erase(NzSlot* table, uint64_t line_mask, uint64_t k0, uint64_t k1, int32_t* status, cudaStream_t s) {

@@ -450,6 +450,82 @@ Part literal(std::string b) {
 
 Plan error_page(int code, bool head) { return stock_page(code, head); }
 
+// ---- admission / validity (SPEC H2) -------------------------------------------------------------
+namespace {
+bool ieq(std::string_view a, std::string_view b) {
+    if (a.size() != b.size()) return false;
+    for (size_t i = 0; i < a.size(); ++i)
+        if (tolower((unsigned char)a[i]) != tolower((unsigned char)b[i])) return false;
+    return true;
+}
+size_t ifind(std::string_view hay, std::string_view needle) {      // case-insensitive substring (ngx_strlcasestrn)
+    if (needle.empty() || hay.size() < needle.size()) return std::string_view::npos;
+    for (size_t i = 0; i + needle.size() <= hay.size(); ++i)
+        if (ieq(hay.substr(i, needle.size()), needle)) return i;
+    return std::string_view::npos;
+}
+int64_t atoi_strict(std::string_view s) {                          // ngx_atoi: digits only; -1 on anything else or overflow
+    if (s.empty()) return -1;
+    int64_t v = 0;
+    for (char c : s) {
+        if (c < '0' || c > '9') return -1;
+        if (v > (INT64_MAX - (c - '0')) / 10) return -1;
+        v = v * 10 + (c - '0');
+    }
+    return v;
+}
+}  // namespace
+
+Admission admission(int status, const std::vector<std::pair<std::string, std::string>>& headers, int64_t now, int64_t default_valid_s) {
+    Admission a;
+    if (status != 200) return a;                                   // H2a: proxy_cache_valid names 200 only
+    bool cacheable = true, xae_seen = false;
+    int64_t valid = 0;
+    for (const auto& h : headers) {
+        const std::string_view name = h.first, val = h.second;
+        if (ieq(name, "set-cookie")) cacheable = false;            // H2b
+        else if (ieq(name, "vary")) { if (val == "*") cacheable = false; }
+        else if (ieq(name, "x-accel-expires")) {                   // H2c
+            xae_seen = true;
+            if (!val.empty() && val[0] == '@') {
+                const int64_t n = atoi_strict(val.substr(1));
+                if (n >= 0) valid = n;
+            } else {
+                const int64_t n = atoi_strict(val);
+                if (n == 0) cacheable = false;
+                else if (n > 0) valid = now + n;
+            }
+        } else if (ieq(name, "cache-control")) {                   // H2d
+            if (valid != 0 && xae_seen) continue;
+            if (ifind(val, "no-cache") != std::string_view::npos || ifind(val, "no-store") != std::string_view::npos ||
+                ifind(val, "private") != std::string_view::npos) { cacheable = false; continue; }
+            size_t p = ifind(val, "s-maxage="), skip = 9;
+            if (p == std::string_view::npos) { p = ifind(val, "max-age="); skip = 8; }
+            if (p == std::string_view::npos) continue;
+            int64_t n = 0;
+            bool bad = false;
+            for (size_t i = p + skip; i < val.size(); ++i) {
+                const char c = val[i];
+                if (c == ',' || c == ';' || c == ' ') break;
+                if (c >= '0' && c <= '9') { n = n * 10 + (c - '0'); if (n > (int64_t)1 << 40) n = (int64_t)1 << 40; continue; }
+                bad = true;
+                break;
+            }
+            if (bad || n == 0) { cacheable = false; continue; }
+            valid = now + n;
+        } else if (ieq(name, "expires")) {                         // H2e
+            if (valid != 0) continue;
+            const int64_t t = parse_http_date(val);
+            if (t < 0 || t < now) { cacheable = false; continue; }
+            valid = t;
+        }
+    }
+    if (cacheable && valid == 0) valid = now + default_valid_s;    // H2f: proxy_cache_valid 200 1d
+    a.cacheable = cacheable;
+    a.valid_until = cacheable ? valid : 0;
+    return a;
+}
+
 Plan plan_response(const Config& cfg, const Request& rq, const ObjectMeta& ob, uint64_t boundary) {
     if (!method_allowed(rq.method)) return stock_page(405, false);
     const bool head = rq.method == "HEAD";
@@ -632,5 +708,24 @@ int nzh_plan_text(const nzh_request* rq, const nzh_object* ob, uint64_t boundary
     if (t.size() + 1 > cap) return -1;
     std::memcpy(out, t.c_str(), t.size() + 1);
     return (int)t.size();
+}
+int nzh_admission(int status, const char* headers, int64_t now, int64_t default_valid_s, int64_t* valid_until) {
+    std::vector<std::pair<std::string, std::string>> hv;
+    std::string_view all(headers ? headers : "");
+    while (!all.empty()) {
+        const size_t e = all.find('\n');
+        const std::string_view line = all.substr(0, e);
+        all = e == std::string_view::npos ? std::string_view() : all.substr(e + 1);
+        const size_t c = line.find(':');
+        if (c == std::string_view::npos) continue;
+        size_t v = c + 1;
+        while (v < line.size() && (line[v] == ' ' || line[v] == '\t')) ++v;
+        size_t ve = line.size();
+        while (ve > v && (line[ve - 1] == ' ' || line[ve - 1] == '\t' || line[ve - 1] == '\r')) --ve;
+        hv.emplace_back(std::string(line.substr(0, c)), std::string(line.substr(v, ve - v)));
+    }
+    const nzh::Admission a = nzh::admission(status, hv, now, default_valid_s);
+    if (valid_until) *valid_until = a.valid_until;
+    return a.cacheable ? 1 : 0;
 }
 }

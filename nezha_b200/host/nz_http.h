@@ -78,6 +78,13 @@ RangeVerdict parse_ranges(std::string_view spec_after_bytes_eq, int64_t length, 
 
 int64_t parse_http_date(std::string_view s);    // seconds since the epoch, -1 if unparseable
 
+// Cache admission and validity of an upstream response (SPEC H2a-H2e: nginx's proxy_cache_valid 200 1d, nginx.conf:57,
+// overridden by X-Accel-Expires / Cache-Control / Expires exactly as nginx's upstream header handlers do, in
+// arrival order).  headers: (name, value) as received.  valid_until: absolute seconds.
+struct Admission { bool cacheable = false; int64_t valid_until = 0; };
+Admission admission(int status, const std::vector<std::pair<std::string, std::string>>& headers, int64_t now,
+                    int64_t default_valid_s = 86400);
+
 Plan plan_response(const Config& cfg, const Request& rq, const ObjectMeta& ob, uint64_t boundary);
 Plan error_page(int code, bool head);           // stock nginx page (server_tokens off, nginx.conf:20)
 
@@ -100,4 +107,6 @@ struct nzh_object {
     int gunzip_enabled;
 };
 int nzh_plan_text(const nzh_request* rq, const nzh_object* ob, uint64_t boundary, char* out, size_t cap);
+// headers: "Name: value\n" lines in arrival order.  Returns 1 cacheable / 0 not; *valid_until = absolute seconds.
+int nzh_admission(int status, const char* headers, int64_t now, int64_t default_valid_s, int64_t* valid_until);
 }

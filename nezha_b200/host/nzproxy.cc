@@ -76,6 +76,7 @@ struct Entry {
     nzh::ObjectMeta meta;
     uint8_t key128[16];
     time_t stored_at;
+    int64_t valid_until = 0;               // SPEC H2: absolute seconds (upstream X-Accel-Expires / Cache-Control / Expires, else stored_at + 1 d)
     uint32_t crc32c = 0;
     std::atomic<int64_t> last_access{0};   // monotonic ms; inactive=60m bookkeeping (nginx.conf:38)
     std::atomic<int> inflight{0};          // responses currently streaming this object
@@ -97,7 +98,11 @@ struct Server {
     nz_ctx* zone_of(const uint8_t key128[16]) const { return ctxs[nz_shard_of(key128, (uint32_t)ctxs.size())]; }
     std::mutex mu;
     std::unordered_map<Key16, std::shared_ptr<Entry>, Key16Hash> index;   // headers blob per object (host side)
-    std::mutex fill_mu;                                                    // one fill at a time per process (coalesces stampedes)
+    // one fill per KEY at a time (concurrent misses of one object coalesce into one origin fetch - nginx would need
+    // proxy_cache_lock for that); misses of different keys fill concurrently
+    std::mutex fill_mu;
+    std::condition_variable fill_cv;
+    std::unordered_map<Key16, int, Key16Hash> filling;
     std::mutex win_mu;
     std::mutex pv_mu;
     std::vector<nz_buf*> free_windows;
@@ -151,6 +156,7 @@ struct Parsed {
     nzh::Request rq;
     bool keep_alive = true;
     bool ok = false;
+    bool has_body = false;               // Content-Length > 0 or Transfer-Encoding present
     std::string request_line, referer, user_agent, x_forwarded_for;   // access log only (nginx.conf:16-18)
 };
 
@@ -204,6 +210,8 @@ Parsed parse_head(const std::string& head) {
         else if (name == "if-modified-since") p.rq.if_modified_since = val;
         else if (name == "if-unmodified-since") p.rq.if_unmodified_since = val;
         else if (name == "accept-encoding") p.rq.accept_encoding = val;
+        else if (name == "content-length") { if (atoll(val.c_str()) > 0) p.has_body = true; }
+        else if (name == "transfer-encoding") p.has_body = true;
         else if (name == "referer") p.referer = val;
         else if (name == "user-agent") p.user_agent = val;
         else if (name == "x-forwarded-for") p.x_forwarded_for = val;
@@ -254,7 +262,7 @@ bool write_fd_all(int fd, const void* p, size_t n) {
 }
 
 // ---- durable tier (PV): <dir>/<md5hex> extent files + <dir>/index.tsv ------------------------
-// index line: md5hex \t stored_len \t raw_len \t crc32c(hex) \t stored_at \t content-type \t etag \t gzip(0/1) \t last-modified
+// index line: md5hex \t stored_len \t raw_len \t crc32c(hex) \t stored_at \t content-type \t etag \t gzip(0/1) \t last-modified [\t valid_until]
 std::string tsv(const std::optional<std::string>& s) { return s ? *s : std::string("\x01"); }   // \x01 = absent
 
 void pv_index_append(Server& S, const Entry& e) {
@@ -264,10 +272,23 @@ void pv_index_append(Server& S, const Entry& e) {
     snprintf(num, sizeof num, "\t%llu\t%lld\t%08x\t%lld\t", (unsigned long long)e.meta.stored_length, (long long)e.meta.raw_length, e.crc32c,
              (long long)e.stored_at);
     const std::string line = std::string(hx) + num + e.meta.content_type + "\t" + tsv(e.meta.etag) + "\t" + (e.meta.stored_gzip ? "1" : "0") + "\t" +
-                             tsv(e.meta.last_modified) + "\n";
+                             tsv(e.meta.last_modified) + "\t" + std::to_string((long long)e.valid_until) + "\n";
     std::lock_guard<std::mutex> g(S.pv_mu);
     int fd = open((S.opt.pv_dir + "/index.tsv").c_str(), O_WRONLY | O_CREAT | O_APPEND, 0644);
     if (fd >= 0) { write_fd_all(fd, line.data(), line.size()); close(fd); }
+}
+
+// The commit inflated a gzip member once (include/nezha_gpu.h): its real inflated length is in the descriptor, and
+// NZ_ENC_INFLATABLE says the member checked out.  Anything else is served verbatim (SPEC G4: fail open).
+void learn_raw_length(Server& S, Entry& e) {
+    e.meta.raw_length = -1;
+    if (!e.meta.stored_gzip) return;
+    nz_extent ext;
+    memset(&ext, 0, sizeof ext);
+    uint8_t k[1][16];
+    memcpy(k[0], e.key128, 16);
+    if (nz_lookup(S.zone_of(e.key128), k, 1, &ext) == NZ_OK && ext.status == NZ_OK && (ext.flags & NZ_ENC_INFLATABLE))
+        e.meta.raw_length = (int64_t)ext.raw_length;
 }
 
 // cold start: bulk-load every still-valid object of the PV into HBM (cuFile/GDS when available).  The index is
@@ -291,7 +312,7 @@ void pv_reload(Server& S) {
             if (t == std::string::npos) break;
             pos = t + 1;
         }
-        if (col.size() != 9 || col[0].size() != 32) continue;
+        if ((col.size() != 9 && col.size() != 10) || col[0].size() != 32) continue;
         auto e = std::make_shared<Entry>();
         for (int i = 0; i < 16; ++i) e->key128[i] = (uint8_t)strtoul(col[0].substr(2 * i, 2).c_str(), nullptr, 16);
         e->meta.stored_length = strtoull(col[1].c_str(), nullptr, 10);
@@ -302,7 +323,8 @@ void pv_reload(Server& S) {
         if (col[6] != "\x01") e->meta.etag = col[6];
         e->meta.stored_gzip = col[7] == "1";
         if (col[8] != "\x01") e->meta.last_modified = col[8];
-        if (now - e->stored_at > S.opt.valid_s) continue;                       // expired: refetch on demand
+        e->valid_until = col.size() == 10 ? atoll(col[9].c_str()) : (int64_t)e->stored_at + S.opt.valid_s;
+        if ((int64_t)now > e->valid_until) continue;                            // expired: refetch on demand
         Key16 k;
         memcpy(k.b, e->key128, 16);
         if (seen.count(k)) continue;
@@ -320,7 +342,7 @@ void pv_reload(Server& S) {
             const int fd = open((S.opt.pv_dir + "/" + todo[i].first).c_str(), O_RDONLY);
             if (fd < 0) continue;
             nz_put* put = nullptr;
-            bool ok = nz_put_begin(S.zone_of(e->key128), e->key128, e->meta.stored_length, e->meta.stored_length, e->meta.stored_gzip ? NZ_ENC_GZIP : NZ_ENC_IDENTITY, 0, &put) == NZ_OK;
+            bool ok = nz_put_begin(S.zone_of(e->key128), e->key128, e->meta.stored_length, 0, e->meta.stored_gzip ? NZ_ENC_GZIP : NZ_ENC_IDENTITY, 0, &put) == NZ_OK;
             if (ok) {
                 ok = nz_put_file(put, fd, 0, 0, e->meta.stored_length) == NZ_OK;
                 uint32_t crc = 0;
@@ -329,6 +351,7 @@ void pv_reload(Server& S) {
             }
             close(fd);
             if (!ok) { ++n_bad; continue; }
+            learn_raw_length(S, *e);
             e->last_access = now_ms();
             Key16 k;
             memcpy(k.b, e->key128, 16);
@@ -349,35 +372,53 @@ void pv_reload(Server& S) {
             st.file_cufile_bytes / 1073741824.0, st.file_bounce_bytes / 1073741824.0, (unsigned long long)n_bad.load());
 }
 
-// drop one object everywhere (device extent, host index, PV file)
-void drop_entry(Server& S, const std::shared_ptr<Entry>& e) {
+// drop one object everywhere (device extent, host index, PV file).  Responses take their reference on an entry under
+// S.mu together with the index lookup, so an entry seen here with no response in flight cannot gain one afterwards.
+bool drop_entry(Server& S, const std::shared_ptr<Entry>& e) {
     Key16 k;
     memcpy(k.b, e->key128, 16);
-    { std::lock_guard<std::mutex> g(S.mu); auto it = S.index.find(k); if (it != S.index.end() && it->second == e) S.index.erase(it); }
+    {
+        std::lock_guard<std::mutex> g(S.mu);
+        if (e->inflight.load() > 0) return false;                   // still streaming: the next pass takes it
+        auto it = S.index.find(k);
+        if (it == S.index.end() || it->second != e) return false;   // already dropped (or replaced) by someone else
+        S.index.erase(it);
+    }
     nz_evict(S.zone_of(e->key128), e->key128);
     if (!S.opt.pv_dir.empty()) {
         char hx[33];
         for (int i = 0; i < 16; ++i) snprintf(hx + 2 * i, 3, "%02x", e->key128[i]);
         unlink((S.opt.pv_dir + "/" + hx).c_str());
     }
+    return true;
 }
 
 // cache manager: `inactive` purge every minute; also called with need_room when the arena is full (LRU)
-void cache_manager_pass(Server& S, bool need_room) {
+// need_bytes > 0: the arena of shard `shard` is full - evict least recently used objects OF THAT SHARD until at
+// least need_bytes of extents were handed back.  Returns the bytes freed.
+uint64_t cache_manager_pass(Server& S, uint64_t need_bytes = 0, uint32_t shard = 0) {
     std::vector<std::shared_ptr<Entry>> victims;
     const int64_t now = now_ms();
     {
         std::lock_guard<std::mutex> g(S.mu);
-        std::shared_ptr<Entry> oldest;
+        std::vector<std::shared_ptr<Entry>> lru;
         for (auto& kv : S.index) {
             const std::shared_ptr<Entry>& e = kv.second;
             if (e->inflight.load() > 0) continue;
             if (now - e->last_access.load() > (int64_t)S.opt.inactive_s * 1000) victims.push_back(e);
-            else if (need_room && (!oldest || e->last_access.load() < oldest->last_access.load())) oldest = e;
+            else if (need_bytes && nz_shard_of(e->key128, (uint32_t)S.ctxs.size()) == shard) lru.push_back(e);
         }
-        if (need_room && victims.empty() && oldest) victims.push_back(oldest);
+        if (need_bytes) {
+            std::sort(lru.begin(), lru.end(), [](const auto& a, const auto& b) { return a->last_access.load() < b->last_access.load(); });
+            uint64_t got = 0;
+            for (auto& e : victims) if (nz_shard_of(e->key128, (uint32_t)S.ctxs.size()) == shard) got += e->meta.stored_length;
+            for (auto& e : lru) { if (got >= need_bytes) break; victims.push_back(e); got += e->meta.stored_length; }
+        }
     }
-    for (auto& e : victims) drop_entry(S, e);
+    uint64_t freed = 0;
+    for (auto& e : victims)
+        if (drop_entry(S, e) && nz_shard_of(e->key128, (uint32_t)S.ctxs.size()) == shard) freed += e->meta.stored_length;
+    return freed;
 }
 
 // ---- upstream connection: plain TCP, or TLS for `proxy_pass https://...` (nginx.conf:113) ------------------
@@ -430,9 +471,11 @@ bool b64_decode(const std::string& in, std::vector<uint8_t>& out) {
     return true;
 }
 
-// returns HTTP status to relay (200 = admitted and indexed); fills `out` on 200
+// returns 200 = admitted and indexed (fills `out`); -1 = the upstream response was not cacheable (SPEC H2) and has been
+// relayed to the client as it came, uncached, the way nginx proxies such a response (the connection then closes);
+// anything else = the status of the stock error page to send
 int fill_from_origin(Server& S, int vhost, const std::string& host, const std::string& target, const std::string& client_ip,
-                     const uint8_t key128[16], std::shared_ptr<Entry>& out) {
+                     const uint8_t key128[16], std::shared_ptr<Entry>& out, int client_fd, bool head_only) {
     const nzh::VHost& vh = S.cfg.vhosts[vhost];
     auto it = S.opt.upstream.find(vh.proxy_host);
     // --upstream host=ip:port keeps the vhost's scheme out of it (tests: plain origin); host=https://ip:port or no override
@@ -479,7 +522,8 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
     if (sscanf(head.c_str(), "HTTP/%*d.%*d %d", &status) != 1) { up.close_(); return 502; }
     nzh::ObjectMeta meta;
     int64_t clen = -1;
-    bool cacheable = status == 200;
+    bool storable = true;                          // representable in the store (identity or gzip, known length)
+    std::vector<std::pair<std::string, std::string>> hv;    // upstream headers in arrival order (admission, relay)
     bool have_crc = false;
     uint32_t want_crc = 0;
     std::vector<uint8_t> want_md5;                 // Content-MD5 (RFC 1864; Azure) or x-goog-hash: md5= (GCS): base64 of the body's MD5
@@ -492,11 +536,12 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
         const size_t c = h.find(':');
         if (c == std::string::npos) continue;
         const std::string name = lower(h.substr(0, c)), val = trim(h.substr(c + 1));
+        hv.emplace_back(h.substr(0, c), val);
         if (name == "content-length") clen = atoll(val.c_str());
         else if (name == "content-type") meta.content_type = val;
         else if (name == "etag") meta.etag = val;
         else if (name == "last-modified") meta.last_modified = val;
-        else if (name == "content-encoding") { if (lower(val) == "gzip") meta.stored_gzip = true; else cacheable = false; }
+        else if (name == "content-encoding") { if (lower(val) == "gzip") meta.stored_gzip = true; else storable = false; }
         else if (name == "content-md5") { std::vector<uint8_t> m; if (b64_decode(val, m) && m.size() == 16) want_md5 = m; }
         else if (name == "x-goog-hash") {                                         // GCS: crc32c=<base64 of the big-endian u32>[, md5=<base64>]
             const size_t m5 = val.find("md5=");
@@ -519,17 +564,47 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
                 if (nb == 6) { want_crc = (uint32_t)(acc >> 4); have_crc = true; }             // 36 bits read, 32 are data
             }
         }
-        else if (name == "set-cookie") cacheable = false;                         // nginx: not cached
-        else if (name == "vary" && val == "*") cacheable = false;
-        else if (name == "cache-control") { const std::string v = lower(val); if (v.find("no-cache") != std::string::npos || v.find("no-store") != std::string::npos || v.find("private") != std::string::npos) cacheable = false; }
     }
-    if (!cacheable || clen < 0) { up.close_(); return status == 200 ? 502 : status; }   // uncached relays are not implemented: fail open to the client as 502
+    // SPEC H2: status 200 only; Set-Cookie / Vary: * never; X-Accel-Expires > Cache-Control > Expires > proxy_cache_valid 200 1d
+    const nzh::Admission adm = nzh::admission(status, hv, (int64_t)time(nullptr), S.opt.valid_s);
+    // An object that can never fit the shard's arena is not worth flushing the cache for (and an origin may claim any length)
+    const bool fits = clen >= 0 && (uint64_t)clen + (1u << 20) <= S.opt.arena_bytes;
+    if (!adm.cacheable || !storable || !fits) {
+        // relay uncached: upstream status line and headers as they came (hop-by-hop ones replaced), body until its end
+        const size_t sl_end = head.find("\r\n");
+        std::string sline = head.substr(0, sl_end);
+        const size_t sp = sline.find(' ');
+        std::string rh = "HTTP/1.1" + (sp == std::string::npos ? std::string(" 502 Bad Gateway") : sline.substr(sp)) + "\r\nServer: nginx\r\nDate: " + http_date(time(nullptr)) + "\r\n";
+        for (const auto& kv : hv) {
+            const std::string n = lower(kv.first);
+            if (n == "server" || n == "date" || n == "connection" || n == "keep-alive" || n == "proxy-connection" || n == "transfer-encoding") continue;
+            rh += kv.first + ": " + kv.second + "\r\n";
+        }
+        rh += "Connection: close\r\n\r\n";
+        bool ok = write_all(client_fd, rh.data(), rh.size());
+        uint64_t sent = 0;
+        if (ok && !head_only) {
+            if (!rest.empty()) { ok = write_all(client_fd, rest.data(), rest.size()); sent += rest.size(); }
+            while (ok && (clen < 0 || sent < (uint64_t)clen)) {
+                const ssize_t r = up.read_(buf.data(), buf.size());
+                if (r <= 0) break;
+                ok = write_all(client_fd, buf.data(), (size_t)r);
+                sent += (size_t)r;
+            }
+        }
+        up.close_();
+        S.bytes_out += sent;
+        return -1;
+    }
     // stream the body into the arena through a pinned window
     nz_put* put = nullptr;
     int32_t prc = NZ_ENOMEM;
-    for (int attempt = 0; attempt < 64 && prc == NZ_ENOMEM; ++attempt) {     // arena full: evict least recently used, retry
-        prc = nz_put_begin(S.zone_of(key128), key128, (uint64_t)clen, (uint64_t)clen, meta.stored_gzip ? NZ_ENC_GZIP : NZ_ENC_IDENTITY, 0, &put);
-        if (prc == NZ_ENOMEM) cache_manager_pass(S, true);
+    const uint32_t shard = nz_shard_of(key128, (uint32_t)S.ctxs.size());
+    for (int attempt = 0; attempt < 8 && prc == NZ_ENOMEM; ++attempt) {
+        // raw_len 0: nz_put_commit inflates a gzip member once and records its real inflated length
+        prc = nz_put_begin(S.ctxs[shard], key128, (uint64_t)clen, 0, meta.stored_gzip ? NZ_ENC_GZIP : NZ_ENC_IDENTITY, 0, &put);
+        // arena of THIS shard full: hand back at least the bytes needed, least recently used first; give up when nothing was freed
+        if (prc == NZ_ENOMEM && cache_manager_pass(S, (uint64_t)clen + (64u << 10), shard) == 0) break;
     }
     if (prc != NZ_OK) {
         up.close_();
@@ -591,34 +666,14 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
     }
     meta.stored_length = (uint64_t)clen;
     meta.raw_length = -1;
-    if (meta.stored_gzip) {   // learn the inflated length from a lookup of the ISIZE trailer is host work: read last 4 bytes
-        // ISIZE is in the last 4 stored bytes; fetch them through a tiny GET
-        nz_buf* tb = nullptr;
-        if (clen >= 18 && nz_buf_alloc(S.ctx, 64, NZ_BUF_PINNED_HOST, &tb) == NZ_OK) {
-            nz_get_req rq;
-            memset(&rq, 0, sizeof rq);
-            memcpy(rq.key, key128, 16);
-            nz_seg sg = {(uint64_t)clen - 4, 4, 0};
-            rq.nseg = 1; rq.segs = &sg; rq.dst = tb;
-            nz_ticket* t = nullptr;
-            nz_get_res rs;
-            if (nz_get_submit(S.zone_of(key128), &rq, 1, nullptr, &t) == NZ_OK) {
-                if (nz_get_wait(t, -1, &rs) == NZ_OK && rs.status == NZ_OK) {
-                    uint32_t isz;
-                    memcpy(&isz, nz_buf_ptr(tb), 4);
-                    meta.raw_length = isz;
-                }
-                nz_ticket_free(t);
-            }
-            nz_buf_free(tb);
-        }
-    }
     auto e = std::make_shared<Entry>();
     e->meta = meta;
     memcpy(e->key128, key128, 16);
     e->stored_at = time(nullptr);
+    e->valid_until = adm.valid_until;
     e->last_access = now_ms();
     e->crc32c = crc;
+    learn_raw_length(S, *e);               // gzip: the inflated length the commit found (stays -1 if the member does not inflate: served verbatim, SPEC G4)
     if (pv_fd >= 0) {
         close(pv_fd);
         if (rename(pv_tmp.c_str(), pv_final.c_str()) == 0) pv_index_append(S, *e);
@@ -855,6 +910,11 @@ void serve_connection(Server* Sp, int fd, std::string client_ip) {
     setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
     int sndbuf = 4 << 20;
     setsockopt(fd, SOL_SOCKET, SO_SNDBUF, &sndbuf, sizeof sndbuf);
+    {   // nginx defaults: client_header_timeout 60s / keepalive_timeout 65s (one receive timeout covers both here), send_timeout 60s
+        struct timeval rtv = {65, 0}, stv = {60, 0};
+        setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &rtv, sizeof rtv);
+        setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &stv, sizeof stv);
+    }
     nz_buf* win[2] = {nullptr, nullptr};
     {
         std::lock_guard<std::mutex> g(S.win_mu);
@@ -896,43 +956,65 @@ void serve_connection(Server* Sp, int fd, std::string client_ip) {
             } else {
                 Key16 k;
                 nzh::md5(key->data(), key->size(), k.b);
-                {
+                // lookup and reference in one critical section: the cache manager only drops entries it sees unreferenced
+                // under the same lock, so a response never streams an object that is being evicted (or its successor)
+                auto lookup_ref = [&]() {
                     std::lock_guard<std::mutex> g(S.mu);
                     auto it = S.index.find(k);
-                    if (it != S.index.end()) ent = it->second;
-                }
-                if (ent && time(nullptr) - ent->stored_at > S.opt.valid_s) {       // proxy_cache_valid 200 1d: expired -> refetch
-                    if (ent->inflight.load() == 0) drop_entry(S, ent);
-                    ent.reset();
-                }
+                    if (it == S.index.end()) return;
+                    if ((int64_t)time(nullptr) > it->second->valid_until) return;      // SPEC H2: expired -> MISS (refetched below)
+                    ent = it->second;
+                    ent->inflight++;
+                };
+                lookup_ref();
                 int st = 200;
                 if (!ent) {
                     S.misses++;
-                    std::lock_guard<std::mutex> g(S.fill_mu);
-                    {
-                        std::lock_guard<std::mutex> g2(S.mu);
-                        auto it = S.index.find(k);
-                        if (it != S.index.end()) ent = it->second;      // filled by a concurrent request while we waited
+                    {   // one fill per key: later misses of the same key wait for the first and then find the entry
+                        std::unique_lock<std::mutex> g(S.fill_mu);
+                        S.fill_cv.wait(g, [&] { return S.filling.count(k) == 0; });
+                        S.filling[k] = 1;
                     }
+                    lookup_ref();                                                       // filled by a concurrent request while we waited
                     if (!ent) {
-                        // $host for the upstream Host header = request host (proxy_set_header Host $host)
-                        std::string host = key->substr(0, key->find('/'));
-                        st = fill_from_origin(S, vhost, host, pr.rq.target, client_ip, k.b, ent);
+                        {   // an expired (or otherwise stale) entry of this key goes first; if a response still streams it, serve as uncached miss
+                            std::shared_ptr<Entry> old;
+                            { std::lock_guard<std::mutex> g(S.mu); auto it = S.index.find(k); if (it != S.index.end()) old = it->second; }
+                            if (old && !drop_entry(S, old)) st = 504;
+                        }
+                        if (st == 200) {
+                            // $host for the upstream Host header = request host (proxy_set_header Host $host)
+                            std::string host = key->substr(0, key->find('/'));
+                            std::shared_ptr<Entry> fresh;
+                            st = fill_from_origin(S, vhost, host, pr.rq.target, client_ip, k.b, fresh, fd, pr.rq.method == "HEAD");
+                            if (st == 200) lookup_ref();
+                        }
                     }
+                    {
+                        std::lock_guard<std::mutex> g(S.fill_mu);
+                        S.filling.erase(k);
+                    }
+                    S.fill_cv.notify_all();
                 } else {
                     S.hits++;
+                }
+                if (st == -1) {                       // relayed uncached: the response is on the wire already
+                    access_log_line(S, client_ip, pr, 200, 0);
+                    break;
                 }
                 if (!ent) {
                     stock(st == 200 ? 502 : st);
                 } else {
                     ent->last_access = now_ms();
-                    ent->inflight++;
                     nzh::Config cfg = S.cfg;
                     cfg.gunzip = S.opt.gunzip;
                     plan = nzh::plan_response(cfg, pr.rq, ent->meta, S.boundary.fetch_add(1));
                 }
             }
         }
+        // a request that carries a body is answered and the connection closed: the body is never read (nginx would
+        // discard it; parsing it as the next request must not happen)
+        if (pr.ok && pr.has_body) keep = false;
         if (pr.ok && pr.rq.http_minor < 1) keep = false;
         const bool sent = send_plan(S, fd, plan, ent.get(), keep, win, t_req);
         access_log_line(S, client_ip, pr, plan.status, plan.head ? 0 : plan.body_length());
@@ -1041,7 +1123,7 @@ int main(int argc, char** argv) {
         S.free_windows.push_back(b);
     }
     if (!S.opt.pv_dir.empty()) pv_reload(S);
-    std::thread([&S] { for (;;) { std::this_thread::sleep_for(std::chrono::seconds(S.opt.inactive_s < 120 ? 1 : 60)); cache_manager_pass(S, false); } }).detach();
+    std::thread([&S] { for (;;) { std::this_thread::sleep_for(std::chrono::seconds(S.opt.inactive_s < 120 ? 1 : 60)); cache_manager_pass(S); } }).detach();
     for (nz_ctx* cx : S.ctxs) {
         auto u = std::make_unique<Combiner>();
         u->ctx = cx; u->cap_bytes = 16ull << 20; u->linger_us = 0; u->spin_us = 2000; u->lane = 0;

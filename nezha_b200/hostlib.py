@@ -38,6 +38,7 @@ def load():
         L.nzh_parse_http_date.restype = C.c_int64
         L.nzh_md5.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p]
         L.nzh_plan_text.argtypes = [C.POINTER(Request), C.POINTER(Object), C.c_uint64, C.c_char_p, C.c_size_t]
+        L.nzh_admission.argtypes = [C.c_int, C.c_char_p, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]
         _lib = L
     return _lib
 
@@ -87,3 +88,11 @@ def plan_text(method="GET", http_minor=1, range=None, if_range=None, if_none_mat
     if n < 0:
         raise RuntimeError("plan overflow")
     return out.raw[:n].decode("latin-1")
+
+
+def admission(status: int, headers, now: int, default_valid_s: int = 86400):
+    """SPEC H2 (nginx.conf:57): (cacheable, valid_until) of an upstream response; headers in arrival order."""
+    blob = "".join(f"{k}: {v}\n" for k, v in headers).encode("latin-1")
+    vu = C.c_int64()
+    c = load().nzh_admission(status, blob, now, default_valid_s, C.byref(vu))
+    return bool(c), vu.value

@@ -209,6 +209,45 @@ class Zone:
               "nz_put_commit")
         return crc.value
 
+    def put_many(self, objects, enc: int = capi.NZ_ENC_IDENTITY) -> List[int]:
+        """Bulk load: `objects` = [(key, data[, raw_len])], data bytes / numpy uint8.  One nz_put_commit_many for the
+        lot (batched CRC / index / publish kernels).  Returns the CRC-32C of every object; raises on any failure."""
+        import numpy as np
+
+        n = len(objects)
+        if n == 0:
+            return []
+        handles = (C.c_void_p * n)()
+        keep = []
+        made = 0
+        try:
+            for i, obj in enumerate(objects):
+                key, data = obj[0], obj[1]
+                raw_len = obj[2] if len(obj) > 2 else None
+                if isinstance(data, (bytes, bytearray)):
+                    arr = np.frombuffer(data, dtype=np.uint8)
+                else:
+                    arr = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+                m = arr.size
+                k = (C.c_uint8 * 16).from_buffer_copy(key)
+                p = C.c_void_p()
+                check(self.L.nz_put_begin(self.ctx, k, m, raw_len if raw_len is not None else (0 if enc & capi.NZ_ENC_GZIP else m),
+                                          enc, 0, C.byref(p)), "nz_put_begin")
+                handles[i] = p
+                made = i + 1
+                keep.append(arr)
+                check(self.L.nz_put_write(p, arr.ctypes.data if m else None, 0, m), "nz_put_write")
+        except Exception:
+            for i in range(made):
+                self.L.nz_put_abort(handles[i])
+            raise
+        crcs = (C.c_uint32 * n)()
+        sts = (C.c_int32 * n)()
+        check(self.L.nz_put_commit_many(handles, n, None, None, crcs, sts), "nz_put_commit_many")
+        for i in range(n):
+            check(sts[i], f"nz_put_commit_many[{i}]")
+        return list(crcs)
+
     def put_file(self, key: bytes, fd: int, length: int, file_off: int = 0, enc: int = capi.NZ_ENC_IDENTITY,
                  raw_len: Optional[int] = None, expected_crc32c: Optional[int] = None) -> int:
         k = (C.c_uint8 * 16).from_buffer_copy(key)

@@ -15,6 +15,9 @@
  *   body           sendfile off, output_buffers 2 32k (nginx defaults, nothing set in the conf):
  *                  pread 32 KiB into an output buffer, send it, repeat (SPEC B1)
  * A miss answers 504 (the fill path is not part of the hit-path baseline).
+ * --gunzip: the operator switch of SPEC G (new behaviour): stored `Content-Encoding: gzip` objects are inflated with
+ * zlib when they are loaded; requests without `Accept-Encoding: gzip` are served the inflated representation (a member
+ * zlib declines stays as stored, SPEC G4).
  *
  * manifest line:  <md5hex> <stored_len> <raw_len|-1> <content-type|-> <etag|-> <encoding|-> <last-modified...|->
  */
@@ -48,10 +51,12 @@ typedef struct obj {
     int64_t stored_len, raw_len;
     char ctype[128], etag[128], lm[64], enc[16];
     int has_etag, has_lm, has_enc;
+    uint8_t* raw;                    /* --gunzip: inflated representation (NULL = none) */
 } obj;
 
 static obj* g_objs;
 static int g_nobj;
+static int g_gunzip;
 static uint64_t g_boundary = 1;
 
 typedef struct seg { int lit; char* bytes; int64_t off, len; } seg;
@@ -68,6 +73,7 @@ typedef struct conn {
     uint8_t out[2][OUTBUF];          /* output_buffers 2 32k */
     int out_len, out_off, out_which;
     int keep, active;
+    int inflated;                    /* slices address the inflated representation */
 } conn;
 
 static int hexv(int c) { return c <= '9' ? c - '0' : (c | 32) - 'a' + 10; }
@@ -103,6 +109,22 @@ static int load_manifest(const char* dir) {
         snprintf(path, sizeof path, "%s/%s", dir, hex);
         o->fd = open(path, O_RDONLY);
         if (o->fd < 0) continue;
+        o->raw = NULL;
+        if (o->has_enc && !strcasecmp(o->enc, "gzip")) {
+            o->raw_len = -1;                                   /* known only if the member inflates (SPEC G3/G4) */
+            if (g_gunzip && sl >= 18) {
+                uint8_t* st = malloc((size_t)sl);
+                if (st && pread(o->fd, st, (size_t)sl, 0) == (ssize_t)sl) {
+                    int64_t isz = nzo_gzip_isize(st, (size_t)sl);
+                    uint8_t* rw = isz >= 0 ? malloc((size_t)isz + 1) : NULL;
+                    if (rw) {
+                        int64_t got = nzo_gunzip(st, (size_t)sl, rw, (size_t)isz + 1);
+                        if (got == isz) { o->raw = rw; o->raw_len = got; } else free(rw);
+                    }
+                }
+                free(st);
+            }
+        }
         g_nobj++;
     }
     fclose(f);
@@ -199,7 +221,7 @@ static void build_response(conn* c, char* head) {
         memset(&ob, 0, sizeof ob);
         ob.stored_length = o->stored_len; ob.raw_length = o->raw_len; ob.content_type = o->ctype;
         ob.etag = o->has_etag ? o->etag : NULL; ob.last_modified = o->has_lm ? o->lm : NULL;
-        ob.content_encoding = o->has_enc ? o->enc : NULL; ob.gunzip_enabled = 0;
+        ob.content_encoding = o->has_enc ? o->enc : NULL; ob.gunzip_enabled = g_gunzip;
         plan = malloc(1 << 16);
         if (nzo_plan(&rq, &ob, g_boundary++, plan, 1 << 16) < 0) { simple_page(c, 400, 0); goto done; }
         int status = 0, headonly = 0;
@@ -210,6 +232,7 @@ static void build_response(conn* c, char* head) {
         char hdrs[4096]; int hdl = 0;
         for (char* ln = strtok_r(plan, "\n", &save); ln; ln = strtok_r(NULL, "\n", &save)) {
             if (!strncmp(ln, "status ", 7)) status = atoi(ln + 7);
+            else if (!strncmp(ln, "repr ", 5)) c->inflated = !strcmp(ln + 5, "inflated");
             else if (!strncmp(ln, "head ", 5)) headonly = atoi(ln + 5);
             else if (!strncmp(ln, "hdr ", 4)) hdl += snprintf(hdrs + hdl, sizeof hdrs - (size_t)hdl, "%s\r\n", ln + 4);
             else if (!strncmp(ln, "lit ", 4) && c->nseg < MAXSEG) {
@@ -266,9 +289,14 @@ static int pump(conn* c) {
         if (s->lit) {
             memcpy(c->out[c->out_which], s->bytes + c->seg_done, (size_t)want);
         } else {
-            ssize_t r = pread(c->o->fd, c->out[c->out_which], (size_t)want, s->off + c->seg_done);
-            if (r <= 0) return -1;
-            want = r;
+            if (c->inflated) {
+                if (!c->o->raw || s->off + c->seg_done + want > c->o->raw_len) return -1;
+                memcpy(c->out[c->out_which], c->o->raw + s->off + c->seg_done, (size_t)want);
+            } else {
+                ssize_t r = pread(c->o->fd, c->out[c->out_which], (size_t)want, s->off + c->seg_done);
+                if (r <= 0) return -1;
+                want = r;
+            }
         }
         c->out_len = (int)want; c->out_off = 0;
         c->seg_done += want;
@@ -340,6 +368,7 @@ int main(int argc, char** argv) {
         if (!strcmp(argv[i], "--root") && i + 1 < argc) dir = argv[++i];
         else if (!strcmp(argv[i], "--listen") && i + 1 < argc) { char* v = argv[++i]; char* c = strrchr(v, ':'); if (c) { *c = 0; ip = v; port = atoi(c + 1); } else port = atoi(v); }
         else if (!strcmp(argv[i], "--workers") && i + 1 < argc) workers = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--gunzip")) g_gunzip = 1;
         else { fprintf(stderr, "nz_cpu_server --root DIR [--listen ip:port] [--workers N]\n"); return 2; }
     }
     signal(SIGPIPE, SIG_IGN);

@@ -19,6 +19,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <strings.h>
 #include <time.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -847,4 +848,96 @@ double nzo_serve_jobs(const nzo_job* jobs, int n, int threads) {
 double nzo_gunzip_jobs(nzo_zjob* jobs, int n, int threads) {
     work w = {NULL, jobs, n, 0, 0, PTHREAD_MUTEX_INITIALIZER};
     return run_workers(&w, threads);
+}
+
+
+/* ------------------------------------------------------------------------- */
+/* SPEC H2: admission / validity of an upstream response (nginx.conf:57)      */
+/* ------------------------------------------------------------------------- */
+static int h2_name_is(const char* line, size_t nlen, const char* want) {
+    return strlen(want) == nlen && strncasecmp(line, want, nlen) == 0;
+}
+static const char* h2_casestr(const char* s, size_t n, const char* needle) {
+    size_t m = strlen(needle);
+    for (size_t i = 0; m && i + m <= n; i++)
+        if (strncasecmp(s + i, needle, m) == 0) return s + i;
+    return NULL;
+}
+static int64_t h2_digits(const char* s, size_t n) {      /* all digits -> value, else -1 */
+    if (n == 0) return -1;
+    int64_t v = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (!isdigit((unsigned char)s[i])) return -1;
+        if (v > (INT64_MAX - 9) / 10) return -1;
+        v = v * 10 + (s[i] - '0');
+    }
+    return v;
+}
+int nzo_admission(int status, const char* headers, int64_t now, int64_t default_valid_s, int64_t* valid_until) {
+    int cacheable = 1, seen_xae = 0;
+    int64_t valid = 0;
+    if (valid_until) *valid_until = 0;
+    if (status != 200) return 0;                                           /* H2a */
+    const char* p = headers ? headers : "";
+    while (*p) {
+        const char* eol = strchr(p, '\n');
+        size_t ll = eol ? (size_t)(eol - p) : strlen(p);
+        const char* colon = memchr(p, ':', ll);
+        if (colon) {
+            size_t nlen = (size_t)(colon - p);
+            const char* v = colon + 1;
+            const char* ve = p + ll;
+            while (v < ve && (*v == ' ' || *v == '\t')) v++;
+            while (ve > v && (ve[-1] == ' ' || ve[-1] == '\t' || ve[-1] == '\r')) ve--;
+            size_t vl = (size_t)(ve - v);
+            if (h2_name_is(p, nlen, "Set-Cookie")) {                        /* H2b */
+                cacheable = 0;
+            } else if (h2_name_is(p, nlen, "Vary")) {
+                if (vl == 1 && v[0] == '*') cacheable = 0;
+            } else if (h2_name_is(p, nlen, "X-Accel-Expires")) {            /* H2c */
+                seen_xae = 1;
+                if (vl && v[0] == '@') {
+                    int64_t n = h2_digits(v + 1, vl - 1);
+                    if (n >= 0) valid = n;
+                } else {
+                    int64_t n = h2_digits(v, vl);
+                    if (n == 0) cacheable = 0;
+                    if (n > 0) valid = now + n;
+                }
+            } else if (h2_name_is(p, nlen, "Cache-Control")) {              /* H2d */
+                if (!(valid != 0 && seen_xae)) {
+                    if (h2_casestr(v, vl, "no-cache") || h2_casestr(v, vl, "no-store") || h2_casestr(v, vl, "private")) {
+                        cacheable = 0;
+                    } else {
+                        const char* q = h2_casestr(v, vl, "s-maxage=");
+                        size_t skip = 9;
+                        if (!q) { q = h2_casestr(v, vl, "max-age="); skip = 8; }
+                        if (q) {
+                            int64_t n = 0;
+                            int broke = 0;
+                            for (q += skip; q < ve; q++) {
+                                if (*q == ',' || *q == ';' || *q == ' ') break;
+                                if (*q < '0' || *q > '9') { broke = 1; break; }
+                                n = n * 10 + (*q - '0');
+                                if (n > ((int64_t)1 << 40)) n = (int64_t)1 << 40;
+                            }
+                            if (broke || n == 0) cacheable = 0;
+                            else valid = now + n;
+                        }
+                    }
+                }
+            } else if (h2_name_is(p, nlen, "Expires")) {                    /* H2e */
+                if (valid == 0) {
+                    int64_t t = nzo_parse_http_time(v, vl);
+                    if (t < 0 || t < now) cacheable = 0;
+                    else valid = t;
+                }
+            }
+        }
+        if (!eol) break;
+        p = eol + 1;
+    }
+    if (cacheable && valid == 0) valid = now + default_valid_s;            /* H2f */
+    if (valid_until) *valid_until = cacheable ? valid : 0;
+    return cacheable;
 }

@@ -54,6 +54,8 @@ int nzo_range_parse(const char* spec, int64_t content_length,
 
 /* ---- HTTP dates (SPEC C7): seconds since epoch or -1 ------------------- */
 int64_t nzo_parse_http_time(const char* s, size_t n);
+/* SPEC H2: headers = "Name: value\n" lines in arrival order; returns 1 cacheable / 0; *valid_until absolute seconds */
+int nzo_admission(int status, const char* headers, int64_t now, int64_t default_valid_s, int64_t* valid_until);
 
 /* ---- whole request plan (SPEC V,C,R,G,E) ------------------------------- */
 typedef struct nzo_request {

@@ -94,6 +94,7 @@ def lib():
         L.nzo_range_parse.argtypes = [C.c_char_p, C.c_int64, C.POINTER(_Range), C.c_int, C.POINTER(C.c_int)]
         L.nzo_parse_http_time.argtypes = [C.c_char_p, C.c_size_t]
         L.nzo_parse_http_time.restype = C.c_int64
+        L.nzo_admission.argtypes = [C.c_int, C.c_char_p, C.c_int64, C.c_int64, C.POINTER(C.c_int64)]
         L.nzo_plan.argtypes = [C.POINTER(_Request), C.POINTER(_Object), C.c_uint64, C.c_char_p, C.c_size_t]
         L.nzo_gunzip.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.nzo_gunzip.restype = C.c_int64
@@ -323,3 +324,11 @@ def serve_slice_fd(fd: int, off: int, length: int) -> bytes:
     if r != length:
         raise IOError("short read")
     return out.raw[:length]
+
+
+def admission(status: int, headers, now: int, default_valid_s: int = 86400):
+    """SPEC H2: (cacheable, valid_until) for an upstream response; headers = [(name, value)] in arrival order."""
+    blob = "".join(f"{k}: {v}\n" for k, v in headers).encode("latin-1")
+    vu = C.c_int64()
+    c = lib().nzo_admission(status, blob, now, default_valid_s, C.byref(vu))
+    return bool(c), vu.value

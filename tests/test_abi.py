@@ -24,7 +24,7 @@ def test_header_symbols_exported():
     missing = [s for s in declared if not hasattr(L, s)]
     assert not missing, missing
     assert sorted(capi.SYMBOLS) == declared, (set(declared) ^ set(capi.SYMBOLS))
-    assert L.nz_abi_version() == 1
+    assert L.nz_abi_version() == 2
 
 
 def test_strerror_and_shard_of():
@@ -40,7 +40,7 @@ def test_strerror_and_shard_of():
 def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(capi.Config) == 40 and C.sizeof(capi.Extent) == 40 and C.sizeof(capi.Seg) == 24
-    assert C.sizeof(capi.GetReq) == 48 and C.sizeof(capi.GetRes) == 32 and C.sizeof(capi.Stats) == 19 * 8
+    assert C.sizeof(capi.GetReq) == 48 and C.sizeof(capi.GetRes) == 32 and C.sizeof(capi.Stats) == 22 * 8
 
 
 def test_no_cpu_fallback():

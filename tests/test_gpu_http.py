@@ -431,3 +431,98 @@ def test_tls_upstream_and_md5_validators(policy_origin, tmp_path):
     finally:
         _stop(p)
         httpd.shutdown()
+
+
+# ---- validity from upstream headers (SPEC H2) at the wire -------------------------------------
+def test_upstream_validity_headers_H2(policy_origin):
+    body = {k: wl.synth_bytes(150_000 + 7 * i, 300 + i).tobytes() for i, k in enumerate(
+        ["maxage1", "nostore", "xae0", "xae_over_cc", "cc_then_xae", "cookie", "expired", "smaxage", "plain"])}
+    hdr = {
+        "maxage1": {"Cache-Control": "public, max-age=1"},
+        "nostore": {"Cache-Control": "no-store"},
+        "xae0": {"X-Accel-Expires": "0"},
+        "xae_over_cc": {"X-Accel-Expires": "3600", "Cache-Control": "no-cache"},      # arrival order: XAE first -> CC ignored (H2d)
+        "cc_then_xae": {"Cache-Control": "private", "X-Accel-Expires": "3600"},       # CC first -> sticky uncacheable
+        "cookie": {"Set-Cookie": "sid=1"},
+        "expired": {"Expires": "Wed, 07 Nov 2018 00:00:00 GMT"},
+        "smaxage": {"Cache-Control": "max-age=0, s-maxage=3600"},                     # s-maxage is read first
+        "plain": {},
+    }
+    for k in body:
+        PolicyOrigin.objects["/v/" + k] = (body[k], hdr[k])
+    port = free_port()
+    p = _start_proxy(port, policy_origin, ["--arena-gib", "0.5"])
+    try:
+        def get(k):
+            s, hd, b = fetch(port, "GET", "storage.googleapis.com", "/v/" + k, {})
+            assert s == 200 and b == body[k], (k, s, len(b))
+            return hd
+        for k in body:
+            PolicyOrigin.hits.pop("/v/" + k, None)
+            get(k); get(k)
+        cached = {k: PolicyOrigin.hits["/v/" + k] == 1 for k in body}
+        assert cached == {"maxage1": True, "nostore": False, "xae0": False, "xae_over_cc": True, "cc_then_xae": False, "cookie": False,
+                          "expired": False, "smaxage": True, "plain": True}, cached
+        # the oracle's restatement of the same rule agrees, header for header
+        now = int(time.time())
+        for k in body:
+            assert o.admission(200, list(hdr[k].items()), now)[0] == cached[k], k
+        # an uncacheable response is relayed with the origin's own headers
+        assert get("cookie").get("set-cookie") == "sid=1" and get("nostore").get("cache-control") == "no-store"
+        time.sleep(2.3)                                        # max-age=1 has run out: refetched once, then cached again
+        get("maxage1"); get("maxage1")
+        assert PolicyOrigin.hits["/v/maxage1"] == 2
+        get("plain")
+        assert PolicyOrigin.hits["/v/plain"] == 1              # proxy_cache_valid 200 1d still covers it
+    finally:
+        _stop(p)
+
+
+# ---- SPEC G1-G4 at the wire: nzproxy --gunzip vs the restated CPU server --gunzip -------------------------
+def test_gunzip_switch_differential(policy_origin, tmp_path):
+    raw = wl.text_like(700_001, 41).tobytes()
+    gz = wl.gzip_member(raw)
+    objs = {
+        "/g/text.json.gz": (gz, "application/json", '"gz-ok"'),
+        "/g/broken.gz": (gz[: len(gz) // 2], "application/json", '"gz-bad"'),          # truncated member: served as stored (G4)
+        "/g/plain.bin": (wl.synth_bytes(90_001, 42).tobytes(), "application/octet-stream", '"id"'),
+    }
+    d = tmp_path / "cache"
+    d.mkdir()
+    lines = []
+    for path, (data, ctype, etag) in objs.items():
+        enc = "gzip" if path.endswith(".gz") else None
+        PolicyOrigin.objects[path] = (data, {"Content-Encoding": "gzip"} if enc else {})
+        hx = o.md5(o.cache_key("storage.googleapis.com", path)).hex()
+        (d / hx).write_bytes(data)
+        lines.append(f"{hx} {len(data)} -1 application/octet-stream \"{hashlib.md5(data).hexdigest()}\" {enc or '-'} -")
+    (d / "manifest").write_text("\n".join(lines) + "\n")
+    gpu_port, cpu_port = free_port(), free_port()
+    p = _start_proxy(gpu_port, policy_origin, ["--arena-gib", "0.5", "--gunzip"])
+    cpu = subprocess.Popen([os.path.join(ROOT, "oracle", "_build", "nz_cpu_server"), "--root", str(d), "--listen", f"127.0.0.1:{cpu_port}", "--gunzip"],
+                           start_new_session=True)
+    try:
+        wait_port(cpu_port)
+        log = []
+        for path in objs:
+            log += [("GET", path, {}), ("HEAD", path, {}), ("GET", path, {"Accept-Encoding": "gzip"}), ("GET", path, {"Accept-Encoding": "br, GZIP;q=0.5"}),
+                    ("GET", path, {"Range": "bytes=100-199"}), ("GET", path, {"Range": "bytes=-9"}), ("GET", path, {"Range": "bytes=699990-"}),
+                    ("GET", path, {"Range": "bytes=5-9,300000-300100"}), ("GET", path, {"Range": "bytes=100-199", "Accept-Encoding": "gzip"}),
+                    ("GET", path, {"If-None-Match": '"%s"' % hashlib.md5(objs[path][0]).hexdigest()})]
+        for method, path, hdrs in log:
+            sg, hg, bg = fetch(gpu_port, method, "storage.googleapis.com", path, hdrs)
+            sc, hc, bc = fetch(cpu_port, method, "storage.googleapis.com", path, hdrs)
+            assert sg == sc, (method, path, hdrs, sg, sc)
+            assert normalise(hg, bg) == normalise(hc, bc), (method, path, hdrs, normalise(hg, bg)[0], normalise(hc, bc)[0])
+        s, hd, b = fetch(gpu_port, "GET", "storage.googleapis.com", "/g/text.json.gz", {})
+        assert s == 200 and b == raw and "content-encoding" not in hd and hd["content-length"] == str(len(raw)) and hd["etag"].startswith('W/')
+        s, hd, b = fetch(gpu_port, "GET", "storage.googleapis.com", "/g/broken.gz", {})
+        assert s == 200 and b == objs["/g/broken.gz"][0] and hd.get("content-encoding") == "gzip"
+        for path in objs:
+            assert PolicyOrigin.hits[path] == 1, (path, PolicyOrigin.hits[path])
+    finally:
+        _stop(p)
+        try:
+            os.killpg(cpu.pid, signal.SIGTERM)
+        except ProcessLookupError:
+            pass

@@ -97,7 +97,7 @@ def test_inflate_to_host_and_ranges_G3(zone, corpus):
     assert res.status == capi.NZ_EINVAL
     # without the flag the stored member is served verbatim (reference behaviour, SPEC B3)
     res, body = zone.get(key)
-    assert res.status == capi.NZ_OK and body == member(raw) and res.flags == capi.NZ_ENC_GZIP
+    assert res.status == capi.NZ_OK and body == member(raw) and res.flags == capi.NZ_ENC_GZIP | capi.NZ_ENC_INFLATABLE
     # verify + inflate: every stored chunk is re-checksummed
     res, body = zone.get(key, flags=capi.NZ_GET_INFLATE | capi.NZ_GET_VERIFY)
     assert res.status == capi.NZ_OK and body == raw
@@ -213,3 +213,145 @@ def test_wave_of_many_streams(zone):
         buf.free()
         for k in keys:
             zone.evict(k)
+
+
+# ---------------------------------------------------------------------------
+# checkpoint index (built at commit) + inflate dedupe
+# ---------------------------------------------------------------------------
+def test_commit_learns_the_inflated_length(zone, corpus):
+    """nz_put_commit inflates the member once: raw_length is the member's, whatever nz_put_begin was told."""
+    raw = corpus["text_odd"]
+    for told in (0, len(raw), 12345):
+        key = put_gz(zone, member(raw), told)
+        ext = zone.lookup([key])[0]
+        assert ext.status == capi.NZ_OK and ext.raw_length == len(raw) and ext.flags == capi.NZ_ENC_GZIP | capi.NZ_ENC_INFLATABLE, told
+        res, body = zone.get(key, flags=capi.NZ_GET_INFLATE, device_dst=True)
+        assert res.status == capi.NZ_OK and body == raw
+        zone.evict(key)
+
+
+@pytest.mark.parametrize("level", [1, 6, 9])
+def test_multi_segment_members(zone, level):
+    """Members of several index segments: every segment decodes on its own warp; matches that reach back across a
+    segment boundary take their bytes from the index."""
+    rng = np.random.default_rng(77)
+    block = rng.integers(0, 256, 30_000, dtype=np.uint8).tobytes()
+    cases = {
+        "text_5MiB": wl.text_like(5 << 20, seed=91).tobytes(),
+        "far_repeat": block * 40,                                          # distance ~30000 matches across every boundary
+        "mixed": wl.text_like(700_000, seed=92).tobytes() + bytes(300_000) + rng.integers(0, 256, 200_000, dtype=np.uint8).tobytes()
+                 + wl.text_like(900_000, seed=93).tobytes(),                # huffman blocks, long runs, stored blocks
+    }
+    for name, raw in cases.items():
+        gz = member(raw, level)
+        key = put_gz(zone, gz, 0)
+        st0 = zone.stats()
+        res, body = zone.get(key, flags=capi.NZ_GET_INFLATE, device_dst=True)
+        assert res.status == capi.NZ_OK and res.length == len(raw), (name, level, res.status)
+        assert body == raw == o.gunzip(gz), (name, level)
+        st1 = zone.stats()
+        # the member went through the index: about one segment per 128 KiB of output, none decoded whole
+        assert st1.inflate_segments - st0.inflate_segments >= len(raw) // (160 << 10) and st1.inflate_whole_members == st0.inflate_whole_members
+        assert st1.index_bytes > 0
+        for s, l in [(131_071, 3), (len(raw) - 5, 5), (262_144 - 100, 300_000)]:
+            res, body = zone.get(key, segs=[(s, l)], flags=capi.NZ_GET_INFLATE)
+            assert res.status == capi.NZ_OK and body == raw[s:s + l], (name, s, l)
+        zone.evict(key)
+
+
+def test_fragmented_member_without_index(zone, corpus):
+    """A member cut into thousands of tiny deflate blocks outgrows the index caps: it is served by the whole-member
+    decode instead, bit-exact all the same."""
+    raw = corpus["text_odd"][:120_000]
+    c = zlib.compressobj(6, zlib.DEFLATED, 31)
+    parts = []
+    for i in range(0, len(raw), 40):
+        parts.append(c.compress(raw[i:i + 40]))
+        parts.append(c.flush(zlib.Z_FULL_FLUSH))
+    gz = b"".join(parts) + c.flush()
+    assert o.gunzip(gz) == raw
+    key = put_gz(zone, gz, 0)
+    assert zone.lookup([key])[0].raw_length == len(raw)
+    st0 = zone.stats()
+    res, body = zone.get(key, flags=capi.NZ_GET_INFLATE, device_dst=True)
+    assert res.status == capi.NZ_OK and body == raw
+    st1 = zone.stats()
+    assert st1.inflate_whole_members == st0.inflate_whole_members + 1 and st1.inflate_segments == st0.inflate_segments
+    zone.evict(key)
+
+
+def test_dedupe_one_decode_many_requesters(zone, corpus):
+    """A wave asking for the same member many times inflates it once; every requester gets its own bytes, and a
+    requester with a bad slice fails alone."""
+    raw = corpus["text_1MiB"]
+    other = corpus["text_odd"]
+    k1 = put_gz(zone, member(raw), len(raw))
+    k2 = put_gz(zone, member(other), len(other))
+    dev = zone.alloc_device(8 << 20)
+    host = zone.alloc_host(4 << 20)
+    try:
+        gets = [
+            nz.Get(k1, dev, [(len(raw), 1, 0)], capi.NZ_GET_INFLATE, 0),                      # 0: leader, slice outside -> EINVAL
+            nz.Get(k1, dev, [], capi.NZ_GET_INFLATE, 1 << 20),                                 # 1: whole -> HBM
+            nz.Get(k1, host, [], capi.NZ_GET_INFLATE, 0),                                      # 2: whole -> pinned host
+            nz.Get(k1, dev, [(5, 70_000, 0), (900_000, 100_000, 70_000)], capi.NZ_GET_INFLATE, 3 << 20),   # 3: two slices
+            nz.Get(k2, dev, [], capi.NZ_GET_INFLATE, 4 << 20),                                 # 4: sole requester of k2: direct
+            nz.Get(k1, dev, [], capi.NZ_GET_INFLATE | capi.NZ_GET_VERIFY, 5 << 20),            # 5: whole, verified
+            nz.Get(k1, dev, [], 0, 7 << 20),                                                   # 6: the stored member, no inflate
+        ]
+        st0 = zone.stats()
+        t = zone.submit(gets)
+        res = t.wait()
+        t.free()
+        st1 = zone.stats()
+        # k1 (1 MiB = 8 segments) decoded once for its five inflate requesters, k2 (333 333 B = 3 segments) once
+        assert 8 + 2 <= st1.inflate_segments - st0.inflate_segments <= 9 + 3
+        assert res[0].status == capi.NZ_EINVAL
+        assert [r.status for r in res[1:]] == [capi.NZ_OK] * 6
+        assert dev.bytes(1 << 20, len(raw)) == raw
+        assert host.bytes(0, len(raw)) == raw
+        assert dev.bytes(3 << 20, 170_000) == raw[5:70_005] + raw[900_000:1_000_000]
+        assert dev.bytes(4 << 20, len(other)) == other
+        assert dev.bytes(5 << 20, len(raw)) == raw
+        assert dev.bytes(7 << 20, res[6].bytes) == member(raw)
+    finally:
+        dev.free()
+        host.free()
+        zone.evict(k1)
+        zone.evict(k2)
+
+
+def test_put_many_bulk_commit(zone):
+    """nz_put_commit_many: one batched commit of gzip and identity objects."""
+    raws = [wl.text_like(50_000 + 4001 * i, seed=700 + i).tobytes() for i in range(40)]
+    keys = [wl.key128(b"inflate-test/many/%d" % i) for i in range(40)]
+    crcs = zone.put_many([(k, member(r), 0) for k, r in zip(keys, raws)], enc=capi.NZ_ENC_GZIP)
+    assert crcs == [o.crc32c(member(r)) for r in raws]
+    ext = zone.lookup(keys)
+    assert [e.raw_length for e in ext] == [len(r) for r in raws]
+    buf = zone.alloc_device(40 * (256 << 10))
+    try:
+        t = zone.submit([nz.Get(k, buf, [], capi.NZ_GET_INFLATE, i * (256 << 10)) for i, k in enumerate(keys)])
+        res = t.wait()
+        t.free()
+        assert all(r.status == capi.NZ_OK for r in res)
+        for i in range(40):
+            assert buf.bytes(i * (256 << 10), len(raws[i])) == raws[i], i
+    finally:
+        buf.free()
+        for k in keys:
+            zone.evict(k)
+
+
+def test_stored_byte_corrupted_after_commit(zone, corpus):
+    """A member whose bytes rot in HBM after its index was built: verify catches it; without verify the decode either
+    notices (recorded lengths no longer reproduce) or returns bytes, but never crashes the wave."""
+    raw = corpus["text_1MiB"]
+    gz = member(raw)
+    key = put_gz(zone, gz, len(raw))
+    zone.debug_poke(key, len(gz) // 2, 0x10)
+    res, _ = zone.get(key, flags=capi.NZ_GET_INFLATE | capi.NZ_GET_VERIFY, device_dst=True)
+    assert res.status == capi.NZ_ECORRUPT
+    res, _ = zone.get(key, flags=capi.NZ_GET_INFLATE, device_dst=True)
+    assert res.status in (capi.NZ_OK, capi.NZ_ECORRUPT)
+    zone.evict(key)

@@ -175,3 +175,57 @@ def test_gunzip_applies_G1():
 def test_crc32c_header_form_X3():
     assert o.crc32c_header(0xE3069283) == "4waSgw=="          # GCS x-goog-hash: crc32c= base64(big-endian u32) of "123456789"
     assert o.crc32c_header(0) == "AAAAAA==" and o.crc32c_header(0xFFFFFFFF) == "/////w=="
+
+
+# ---------------------------------------------------------------------------
+# SPEC H2: admission / validity from upstream headers (nginx.conf:57)
+# ---------------------------------------------------------------------------
+NOW = 1_541_604_001          # 2018-11-07, the README's wget log
+DATE_OK = "Thu, 08 Nov 2018 15:20:01 GMT"      # NOW + 86400
+DATE_PAST = "Wed, 07 Nov 2018 00:00:00 GMT"
+
+
+def _adm(status, headers):
+    a, b = h.admission(status, headers, NOW), o.admission(status, headers, NOW)
+    assert a == b, (status, headers, a, b)
+    return a
+
+
+def test_admission_named_rules_H2():
+    assert _adm(200, []) == (True, NOW + 86400)                                              # H2f: proxy_cache_valid 200 1d
+    assert _adm(404, []) == (False, 0) and _adm(206, [("Cache-Control", "max-age=60")]) == (False, 0)     # H2a
+    assert _adm(200, [("Set-Cookie", "a=b")]) == (False, 0)                                  # H2b
+    assert _adm(200, [("Vary", "*")]) == (False, 0) and _adm(200, [("Vary", "Accept-Encoding")])[0]
+    assert _adm(200, [("Cache-Control", "public, max-age=60")]) == (True, NOW + 60)          # H2d
+    assert _adm(200, [("cache-control", "MAX-AGE=60, s-maxage=7")]) == (True, NOW + 7)       # s-maxage wins, case-insensitive
+    assert _adm(200, [("Cache-Control", "max-age=0")]) == (False, 0)
+    assert _adm(200, [("Cache-Control", "max-age=6x")]) == (False, 0)
+    assert _adm(200, [("Cache-Control", "max-age=60;foo")]) == (True, NOW + 60)
+    for v in ("no-cache", "No-Store", "private, max-age=60", "xprivatex"):
+        assert _adm(200, [("Cache-Control", v)]) == (False, 0), v
+    assert _adm(200, [("Expires", DATE_OK)]) == (True, NOW + 86400 - 0) or True              # H2e (value checked below)
+    assert _adm(200, [("Expires", DATE_OK)])[1] == h.parse_http_date(DATE_OK)
+    assert _adm(200, [("Expires", DATE_PAST)]) == (False, 0) and _adm(200, [("Expires", "0")]) == (False, 0)
+    assert _adm(200, [("X-Accel-Expires", "30")]) == (True, NOW + 30)                        # H2c
+    assert _adm(200, [("X-Accel-Expires", "0")]) == (False, 0)
+    assert _adm(200, [("X-Accel-Expires", "@1541700000")]) == (True, 1541700000)
+    assert _adm(200, [("X-Accel-Expires", "soon")]) == (True, NOW + 86400)                   # unparseable: ignored
+    # precedence follows arrival order exactly as nginx's handlers do
+    assert _adm(200, [("X-Accel-Expires", "30"), ("Cache-Control", "no-store")]) == (True, NOW + 30)      # CC skipped once XAE set a time
+    assert _adm(200, [("Cache-Control", "no-store"), ("X-Accel-Expires", "30")]) == (False, 0)            # CC ran first: sticky
+    assert _adm(200, [("Expires", DATE_OK), ("Cache-Control", "max-age=5")]) == (True, NOW + 5)           # CC overrides an earlier Expires
+    assert _adm(200, [("Cache-Control", "max-age=5"), ("Expires", DATE_PAST)]) == (True, NOW + 5)         # Expires skipped: valid already set
+    assert _adm(200, [("X-Accel-Expires", "soon"), ("Cache-Control", "max-age=5")]) == (True, NOW + 5)    # XAE seen but set nothing
+
+
+hdr_names = st.sampled_from(["Cache-Control", "cache-control", "Expires", "X-Accel-Expires", "x-accel-expires", "Set-Cookie", "Vary",
+                             "Content-Type", "ETag"])
+hdr_vals = st.sampled_from(["max-age=60", "s-maxage=10, max-age=99", "max-age=0", "max-age=", "max-age=1 2", "no-cache", "private",
+                            "public", "NO-STORE", "max-age=12;x", "30", "0", "@1541700000", "@", "@x", "-1", "", "*", "a=b",
+                            DATE_OK, DATE_PAST, "Thu, 08 Nov 2018 15:20:01", "garbage", " 5", "5 ", "99999999999999999999"])
+
+
+@SET
+@given(st.sampled_from([200, 200, 200, 206, 301, 404, 500]), st.lists(st.tuples(hdr_names, hdr_vals), max_size=6))
+def test_admission_differential_H2(status, headers):
+    _adm(status, headers)
