@@ -617,8 +617,20 @@ def run_c3(args):
     torch.cuda.set_device(local)
     n_obj, wave_n = args.c3_objects, args.c3_wave
     t0 = time.perf_counter()
-    with mp.get_context("fork").Pool(min(64, os.cpu_count() or 1)) as pool:
-        made = pool.map(_c3_make, range(n_obj), chunksize=8)
+    cache = os.environ.get("NZ_C3_CACHE")          # tools: keep the generated members between runs of one session
+    cpath = os.path.join(cache, f"c3_{n_obj}.pkl") if cache else None
+    if cpath and os.path.exists(cpath):
+        import pickle
+        with open(cpath, "rb") as f:
+            made = pickle.load(f)
+    else:
+        with mp.get_context("fork").Pool(min(64, os.cpu_count() or 1)) as pool:
+            made = pool.map(_c3_make, range(n_obj), chunksize=8)
+        if cpath:
+            import pickle
+            os.makedirs(cache, exist_ok=True)
+            with open(cpath, "wb") as f:
+                pickle.dump(made, f, protocol=4)
     gen_s = time.perf_counter() - t0
     comp_total = sum(len(g) for g, _ in made)
     # arena: the members + their checkpoint indexes (~7 % of the raw size each, 4 KiB granular)

@@ -642,7 +642,7 @@ int32_t nz_put_commit_many(nz_put** puts, uint32_t n, const uint32_t* expected, 
                 nz_put* p = puts[i];
                 const uint64_t isize = trailers[2 * i + 1];
                 if (isize > p->stored_len * 1032ull + 1024 || isize >= 0xFFFFFF00ull) continue;      // not a deflate ratio: no index (GETs decline it)
-                const uint64_t seg_cap = isize / c->idx_seg_bytes + 2, grp_cap = isize / 2048 + p->stored_len / 2048 + 16;
+                const uint64_t seg_cap = isize / c->idx_seg_bytes + 2, grp_cap = isize / 1024 + p->stored_len / 1024 + 16;
                 const uint64_t side_cap = isize / 4 + 4096;
                 const uint64_t bytes = round_up(isize + 256, 256) + round_up(seg_cap * sizeof(NzIdxSeg), 256) + round_up(grp_cap * sizeof(NzIdxGrp), 256) +
                                        round_up(grp_cap * NZ_IDX_SUBS * 4, 256) + round_up(side_cap, 256) + 256;
@@ -673,7 +673,7 @@ int32_t nz_put_commit_many(nz_put** puts, uint32_t n, const uint32_t* expected, 
                 j.seg = (uint64_t)(tmp + carve[k].seg); j.grp = (uint64_t)(tmp + carve[k].grp);
                 j.delta = (uint64_t)(tmp + carve[k].delta); j.side = (uint64_t)(tmp + carve[k].side);
                 j.side_cap = isize / 4 + 4096;
-                j.seg_cap = (uint32_t)(isize / c->idx_seg_bytes + 2); j.grp_cap = (uint32_t)(isize / 2048 + p->stored_len / 2048 + 16);
+                j.seg_cap = (uint32_t)(isize / c->idx_seg_bytes + 2); j.grp_cap = (uint32_t)(isize / 1024 + p->stored_len / 1024 + 16);
                 j.seg_bytes = c->idx_seg_bytes; j.pad = 0; j.dest = 0;
                 memset(&results[k], 0, sizeof(NzIdxResult));
                 results[k].status = -1;

@@ -32,6 +32,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "nz_internal.h"
@@ -604,11 +606,13 @@ struct SegShared {
     uint32_t list[NZ_IDX_SUBS * LIST_STRIDE];
 };
 
-// lane-private bit reader (phase 1: every lane walks its own sub-segment)
+// lane-private bit reader (phase 1: every lane walks its own sub-segment).  Two words are always in flight ahead of
+// the buffer, so a refill never waits for memory (a sub-segment's compressed bytes are touched once: they mostly miss L1)
 struct LaneBits {
-    const uint32_t* wp;
+    const uint32_t* wp;     // next word to request
     uint64_t buf;
     uint32_t cnt;
+    uint32_t w1, w2;        // the next two words, already requested
 };
 __device__ __forceinline__ void lb_init(LaneBits& b, const uint8_t* base, uint64_t bit) {
     const uint8_t* at = base + (bit >> 3);
@@ -617,12 +621,16 @@ __device__ __forceinline__ void lb_init(LaneBits& b, const uint8_t* base, uint64
     const uint32_t skip = mis * 8u + (uint32_t)(bit & 7u);          // 0..31
     b.buf = ((uint64_t)__ldg(wa) | ((uint64_t)__ldg(wa + 1) << 32)) >> skip;
     b.cnt = 64u - skip;
-    b.wp = wa + 2;
+    b.w1 = __ldg(wa + 2);
+    b.w2 = __ldg(wa + 3);
+    b.wp = wa + 4;
 }
 __device__ __forceinline__ void lb_refill(LaneBits& b) {             // afterwards cnt >= 33
     if (b.cnt <= 32) {
-        b.buf |= (uint64_t)__ldg(b.wp) << b.cnt;
+        b.buf |= (uint64_t)b.w1 << b.cnt;
         b.cnt += 32;
+        b.w1 = b.w2;
+        b.w2 = __ldg(b.wp);
         ++b.wp;
     }
 }
@@ -648,12 +656,12 @@ __device__ __forceinline__ int lane_slow_decode(uint64_t buf, const uint32_t* cn
 __device__ bool inflate_segment(const NzInflWork& w, uint32_t si, SegShared& S) {
     const int lane = threadIdx.x & 31;
     const uint8_t* __restrict__ src = reinterpret_cast<const uint8_t*>(w.src);
-    uint8_t* __restrict__ out = reinterpret_cast<uint8_t*>(w.dst);
+    uint8_t* out = reinterpret_cast<uint8_t*>(w.dst);
     const uint8_t* idx = reinterpret_cast<const uint8_t*>(w.idx);
     const NzIdxHeader* H = reinterpret_cast<const NzIdxHeader*>(idx);
     if (H->magic != NZ_IDX_MAGIC || si >= H->n_seg || H->raw_len != w.dst_cap) return false;
     const NzIdxSeg sg = reinterpret_cast<const NzIdxSeg*>(idx + H->off_seg)[si];
-    const NzIdxGrp* grps = reinterpret_cast<const NzIdxGrp*>(idx + H->off_grp);
+    const uint4* grps = reinterpret_cast<const uint4*>(idx + H->off_grp);
     const uint32_t* deltas = reinterpret_cast<const uint32_t*>(idx + H->off_delta);
     const uint8_t* __restrict__ side = idx + H->off_side + sg.side_off;
     const uint32_t seg_start = (uint32_t)sg.out_start;
@@ -661,9 +669,18 @@ __device__ bool inflate_segment(const NzInflWork& w, uint32_t si, SegShared& S) 
     uint32_t side_cur = 0;
     uint64_t tables_of = ~0ull;                            // header bit of the block whose tables are in shared memory
     bool bad = false;
-    const int grp8 = lane >> 2, sub4 = lane & 3;
-    for (uint32_t g = sg.first_grp; g < sg.first_grp + sg.n_grp; ++g) {
-        const NzIdxGrp G = grps[g];
+    const uint32_t lm_le = 0xFFFFFFFFu >> (31 - lane);      // bits 0..lane
+    const uint32_t g_end = sg.first_grp + sg.n_grp;
+    // the next group's record and deltas are requested one group ahead
+    uint4 nga = make_uint4(0, 0, 0, 0), ngb = nga;
+    uint32_t nd = 0;
+    if (sg.n_grp) { nga = __ldg(grps + 2 * (size_t)sg.first_grp); ngb = __ldg(grps + 2 * (size_t)sg.first_grp + 1); nd = __ldg(deltas + (size_t)sg.first_grp * NZ_IDX_SUBS + lane); }
+    for (uint32_t g = sg.first_grp; g < g_end; ++g) {
+        NzIdxGrp G;
+        G.tok_bit = (uint64_t)nga.x | ((uint64_t)nga.y << 32); G.out_off = (uint64_t)nga.z | ((uint64_t)nga.w << 32);
+        G.hdr_bit = (uint64_t)ngb.x | ((uint64_t)ngb.y << 32); G.n_sub = ngb.z; G.flags = ngb.w;
+        const uint32_t d = nd;
+        if (g + 1 < g_end) { nga = __ldg(grps + 2 * (size_t)(g + 1)); ngb = __ldg(grps + 2 * (size_t)(g + 1) + 1); nd = __ldg(deltas + (size_t)(g + 1) * NZ_IDX_SUBS + lane); }
         if (G.flags & NZ_IDX_GRP_STORED) {
             const uint8_t* q = src + (G.tok_bit >> 3);
             const uint32_t len = (uint32_t)G.hdr_bit;
@@ -683,8 +700,7 @@ __device__ bool inflate_segment(const NzInflWork& w, uint32_t si, SegShared& S) 
             tables_of = G.hdr_bit;
         }
         // ---- this lane's sub-segment ----
-        const uint32_t d = (uint32_t)lane < G.n_sub ? __ldg(deltas + (size_t)g * NZ_IDX_SUBS + lane) : 0u;
-        const uint32_t my_bits = d & 0xffffu, my_out = d >> 16;
+        const uint32_t my_bits = (uint32_t)lane < G.n_sub ? d & 0xffffu : 0u, my_out = (uint32_t)lane < G.n_sub ? d >> 16 : 0u;
         uint32_t bit_incl = my_bits, out_incl = my_out;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -738,7 +754,7 @@ __device__ bool inflate_segment(const NzInflWork& w, uint32_t si, SegShared& S) 
                 }
                 const uint32_t dtot = e & 0xffu, dcl = (e >> 8) & 15u;
                 const uint32_t dist = ((e >> 16) & 0x7FFFu) + bfe32(wv, dcl, dtot - dcl);
-                if (dtot > rem || (e >> 31) || nm >= NZ_IDX_T || nlit > 63u) { bad = true; break; }
+                if (dtot > rem || (e >> 31) || nm >= NZ_IDX_T || nlit >= NZ_IDX_T) { bad = true; break; }
                 b.buf >>= dtot; b.cnt -= dtot; rem -= dtot;
                 myq[nm++] = nlit | ((mlen - 3u) << 6) | ((dist - 1u) << 14);
                 o += mlen;
@@ -748,64 +764,125 @@ __device__ bool inflate_segment(const NzInflWork& w, uint32_t si, SegShared& S) 
         }
         if (__any_sync(0xffffffffu, bad)) return false;
         __syncwarp();
-        // ---- phase 2: LZ77 copies in stream order, 8 matches per step (4 lanes each) ----
+        // ---- phase 2: LZ77 copies, OUTPUT-centric.  One sub-segment's queue (<= 32 matches, one per lane) at a time; its
+        // output range is walked 128 bytes per iteration, lane b taking bytes p+b, p+32+b, p+64+b, p+96+b: each finds the
+        // match that covers its byte (start bits of the window + population count, then three shuffles), every byte whose
+        // source lies below p - or on a byte of this iteration that is already final - is loaded, then all are stored
+        // (coalesced), and the few that depend on a byte of the same iteration take another round.
         for (uint32_t s = 0; s < G.n_sub; ++s) {
             const uint32_t c = __shfl_sync(0xffffffffu, nm, s);
-            uint32_t base = __shfl_sync(0xffffffffu, out0, s);
-            const uint32_t* q = S.list + s * LIST_STRIDE;
-            for (uint32_t k0 = 0; k0 < c; k0 += 8) {
-                const uint32_t k = k0 + grp8;
-                const bool valid = k < c;
-                const uint32_t ent = valid ? q[k] : 0u;
-                const uint32_t mlen = valid ? ((ent >> 6) & 255u) + 3u : 0u;
-                const uint32_t dist = (ent >> 14) + 1u;
-                uint32_t incl = (ent & 63u) + mlen;        // literals before the match + the match
+            if (c == 0) continue;
+            const uint32_t base = __shfl_sync(0xffffffffu, out0, s);
+            const bool have = (uint32_t)lane < c;
+            const uint32_t ent = have ? S.list[s * LIST_STRIDE + lane] : 0u;
+            const uint32_t ml = have ? ((ent >> 6) & 255u) + 3u : 0u;
+            const uint32_t ds = (ent >> 14) + 1u;
+            uint32_t incl = (ent & 63u) + ml;              // literals before the match + the match
 #pragma unroll
-                for (int o = 4; o < 32; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                const uint32_t pos = base + incl - mlen;
-                base += __shfl_sync(0xffffffffu, incl, 31);
-                if (__any_sync(0xffffffffu, valid && dist > pos)) return false;     // would reach before the member's first byte
-                // bytes from before the segment come from the index's side bytes, consumed in stream order
-                const int64_t srcp = (int64_t)pos - (int64_t)dist;
-                uint32_t nside = 0;
-                if (valid && srcp < (int64_t)seg_start) nside = min(mlen, (uint32_t)((int64_t)seg_start - srcp));
-                uint32_t sbase = 0;
-                if (__any_sync(0xffffffffu, nside != 0)) {
-                    if (seg_start == 0) return false;
-                    uint32_t sincl = nside;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const uint32_t mpos = have ? base + incl - ml : 0xFFFFFFFFu;      // absent lanes never start inside a window
+            const uint32_t mend = have ? mpos + ml : 0xFFFFFFFFu;
+            if (__any_sync(0xffffffffu, have && ds > mpos)) return false;    // would reach before the member's first byte
+            // bytes from before the segment come from the index's side bytes, consumed in stream order
+            uint32_t ns = 0, sb = 0;
+            bool list_side = false;
+            if (seg_start != 0) {
+                ns = (have && mpos - ds < seg_start) ? min(ml, seg_start - (mpos - ds)) : 0u;
+                list_side = __any_sync(0xffffffffu, ns != 0);
+                if (list_side) {
+                    uint32_t sincl = ns;
 #pragma unroll
-                    for (int o = 4; o < 32; o <<= 1) {
+                    for (int o = 1; o < 32; o <<= 1) {
                         const uint32_t t = __shfl_up_sync(0xffffffffu, sincl, o);
                         if (lane >= o) sincl += t;
                     }
-                    sbase = side_cur + sincl - nside;
+                    sb = side_cur + sincl - ns;
                     side_cur += __shfl_sync(0xffffffffu, sincl, 31);
                 }
-                // a match whose source range lies below the first unfinished match of the step is ready
-                const uint32_t src_hi = pos - dist + min(mlen, dist);          // one past its last source byte (periodic when dist < mlen)
-                bool done = !valid;
-                for (;;) {
-                    const uint32_t pending = __ballot_sync(0xffffffffu, !done);
-                    if (pending == 0) break;
-                    const int first = __ffs(pending) - 1;
-                    const uint32_t hwm = __shfl_sync(0xffffffffu, pos, first);
-                    const bool ready = !done && (src_hi <= hwm || grp8 == (first >> 2));
-                    if (ready) {
-                        uint8_t* dp = out + pos;
-                        if (dist >= mlen) {
-                            for (uint32_t i = sub4; i < mlen; i += 4) dp[i] = i < nside ? __ldg(side + sbase + i) : dp[(int64_t)i - (int64_t)dist];
-                        } else {
-                            for (uint32_t i = sub4; i < mlen; i += 4) {
-                                const uint32_t j = i % dist;
-                                dp[i] = j < nside ? __ldg(side + sbase + j) : dp[(int64_t)j - (int64_t)dist];
-                            }
-                        }
-                        done = true;
+            }
+            const uint32_t p_first = __shfl_sync(0xffffffffu, mpos, 0), p_last = __shfl_sync(0xffffffffu, mend, (int)c - 1);
+            uint32_t nbefore = 0;                           // matches that start below p
+            for (uint32_t p = p_first; p < p_last; p += 128u) {
+                const uint32_t rel = mpos - p;              // < 128: this match starts in the iteration's range
+                const uint32_t bit = 1u << (rel & 31u);
+                uint32_t sm[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) sm[u] = __reduce_or_sync(0xffffffffu, (rel >> 5) == (uint32_t)u ? bit : 0u);
+                uint32_t sp[4], so[4], vv[4], mpv[4], mdv[4], mnsv[4], msbv[4];
+                bool act[4], fs[4];
+                uint32_t nb = nbefore;
+                bool periodic = false;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t cnt = nb + __popc(sm[u] & lm_le);          // matches that start at or below this lane's byte
+                    nb += __popc(sm[u]);
+                    const int mi = (int)(cnt - 1u) & 31;
+                    const uint32_t mp = __shfl_sync(0xffffffffu, mpos, mi), me = __shfl_sync(0xffffffffu, mend, mi);
+                    const uint32_t md = __shfl_sync(0xffffffffu, ds, mi);
+                    const uint32_t x = p + 32u * u + (uint32_t)lane;
+                    act[u] = cnt != 0 && x < me;                              // covered by that match (else a literal, already in place)
+                    sp[u] = x - md;                                           // source position (first period)
+                    mpv[u] = mp; mdv[u] = md;
+                    periodic |= act[u] && x - mp >= md;                       // a match longer than its distance repeats its first `dist` bytes
+                    fs[u] = false;
+                    so[u] = 0; mnsv[u] = 0; msbv[u] = 0;
+                    if (list_side) {
+                        mnsv[u] = __shfl_sync(0xffffffffu, ns, mi);
+                        msbv[u] = __shfl_sync(0xffffffffu, sb, mi);
+                        fs[u] = act[u] && x - mp < mnsv[u];
+                        so[u] = msbv[u] + (x - mp);
                     }
+                }
+                if (__any_sync(0xffffffffu, periodic)) {                      // rare on text: take the byte from the first period, which lies below the match
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t i = p + 32u * u + (uint32_t)lane - mpv[u];
+                        if (act[u] && i >= mdv[u]) {
+                            const uint32_t j = i % mdv[u];
+                            sp[u] = mpv[u] - mdv[u] + j;
+                            fs[u] = j < mnsv[u];
+                            so[u] = msbv[u] + j;
+                        }
+                    }
+                }
+                nbefore = nb;
+                // round 1: every byte whose source lies below p (or in the side bytes) - on text nearly all of them
+                {
+                    bool rdy[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        rdy[u] = act[u] && (fs[u] || (int32_t)(sp[u] - p) < 0);
+                        if (rdy[u]) vv[u] = fs[u] ? (uint32_t)__ldg(side + so[u]) : (uint32_t)out[sp[u]];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (rdy[u]) { out[p + 32u * u + (uint32_t)lane] = (uint8_t)vv[u]; act[u] = false; }
+                }
+                __syncwarp();                                                 // the stores above are visible to every lane's later loads
+                if (!__any_sync(0xffffffffu, act[0] | act[1] | act[2] | act[3])) continue;
+                // further rounds: a byte is ready once its source byte (inside this iteration's range) is no longer pending
+                uint32_t pend[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pend[u] = __ballot_sync(0xffffffffu, act[u]);
+                while (pend[0] | pend[1] | pend[2] | pend[3]) {
+                    bool rdy[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t dd = sp[u] - p;
+                        const uint32_t wsel = (dd >> 5) & 3u;
+                        const uint32_t pw = wsel == 0 ? pend[0] : wsel == 1 ? pend[1] : wsel == 2 ? pend[2] : pend[3];
+                        rdy[u] = act[u] && !((pw >> (dd & 31u)) & 1u);
+                        if (rdy[u]) vv[u] = (uint32_t)out[sp[u]];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (rdy[u]) { out[p + 32u * u + (uint32_t)lane] = (uint8_t)vv[u]; act[u] = false; }
                     __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) pend[u] = __ballot_sync(0xffffffffu, act[u]);
                 }
             }
         }
@@ -815,7 +892,8 @@ __device__ bool inflate_segment(const NzInflWork& w, uint32_t si, SegShared& S) 
 }
 
 // seg_begin[0..n_infl]: exclusive prefix of the members' segment counts (0 for members without an index), by k_plan
-__global__ void __launch_bounds__(SEG_WARPS * 32, 7)
+template <int MINB>
+__global__ void __launch_bounds__(SEG_WARPS * 32, MINB)
 k_inflate_seg(const NzInflWork* __restrict__ infl, const uint32_t* __restrict__ seg_begin, uint32_t* counters, NzDevRes* res,
               const NzDevReq* __restrict__ reqs, uint32_t n_req) {
     __shared__ SegShared sh[SEG_WARPS];
@@ -940,12 +1018,19 @@ k_inflate_crc(const NzInflWork* __restrict__ infl, const uint64_t* __restrict__ 
     }
 }
 
+// k_inflate_seg is built for 10 CTAs/SM (96 registers, a few spilled words; default: measured +13 % on the C3 wave) and for 8
+// (115 registers, no spills); env NZ_INFL_OCC=8 picks the latter
+static int seg_variant() {
+    static const int v = [] { const char* e = getenv("NZ_INFL_OCC"); return e && atoi(e) == 8 ? 8 : 10; }();
+    return v;
+}
 cudaError_t nz_launch_inflate(const NzInflWork* infl, uint64_t* meta, uint32_t* counters, NzDevRes* res,
                               const uint32_t* crc_tables, int grid, int sm_count, cudaStream_t s,
                               const uint32_t* seg_begin, const NzDevReq* reqs, uint32_t n_req, int seg_grid, bool legacy) {
     cudaError_t e;
     if (seg_grid > 0) {
-        k_inflate_seg<<<seg_grid, SEG_WARPS * 32, 0, s>>>(infl, seg_begin, counters, res, reqs, n_req);
+        if (seg_variant() == 10) k_inflate_seg<10><<<seg_grid, SEG_WARPS * 32, 0, s>>>(infl, seg_begin, counters, res, reqs, n_req);
+        else k_inflate_seg<8><<<seg_grid, SEG_WARPS * 32, 0, s>>>(infl, seg_begin, counters, res, reqs, n_req);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
@@ -984,7 +1069,9 @@ int nz_inflate_blocks_per_sm() {
 }
 int nz_inflate_seg_blocks_per_sm() {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_inflate_seg, SEG_WARPS * 32, 0) != cudaSuccess || nb < 1) nb = 4;
+    const cudaError_t e = seg_variant() == 10 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_inflate_seg<10>, SEG_WARPS * 32, 0)
+                                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_inflate_seg<8>, SEG_WARPS * 32, 0);
+    if (e != cudaSuccess || nb < 1) nb = 4;
     return nb;
 }
 

@@ -99,11 +99,11 @@ static_assert(sizeof(NzInflWork) == 48, "inflate work layout");
 //   member -> SEGMENTS  (~128 KiB of output, one warp each, independent of each other: the bytes a segment's matches
 //                        copy from before its own start are kept verbatim in the index = "side bytes", in stream order)
 //          -> GROUPS    (<= 32 sub-segments of one deflate block = one warp iteration; tables are shared)
-//          -> SUB-SEGMENTS (<= NZ_IDX_T tokens, one lane each: bit length and output length as u16 deltas)
+//          -> SUB-SEGMENTS (<= NZ_IDX_T = 32 tokens, one lane each: bit length and output length as u16 deltas)
 // Layout of the blob: NzIdxHeader | NzIdxSeg[n_seg] | NzIdxGrp[n_grp] | u32 delta[n_grp][32] | side bytes.
 // ---------------------------------------------------------------------------
 constexpr uint32_t NZ_IDX_MAGIC = 0x58495A4Eu;      // "NZIX"
-constexpr uint32_t NZ_IDX_T = 64;                   // tokens (literal or match) per sub-segment
+constexpr uint32_t NZ_IDX_T = 32;                   // tokens (literal or match) per sub-segment
 constexpr uint32_t NZ_IDX_SUBS = 32;                // sub-segments per group
 constexpr uint32_t NZ_IDX_GRP_STORED = 1u;          // group = one stored block (type 0): tok_bit = 8 * byte offset of its data, hdr_bit = its length
 struct __align__(16) NzIdxHeader {
