@@ -161,6 +161,8 @@ int32_t nz_put_sync(nz_put* p);
 int32_t nz_put_write_device(nz_put* p, const void* src_dev, uint64_t dst_off, uint64_t len);
 /* read from a file: cuFile/GDS when available, else pread into pinned bounce buffers */
 int32_t nz_put_file(nz_put* p, int fd, uint64_t file_off, uint64_t dst_off, uint64_t len);
+/* which stage of the cuFile/GDS path last decided ("ok", or the call that refused and its error codes) */
+const char* nz_cufile_status(void);
 /* computes the 64 KiB chunk CRC-32C table and the whole-object CRC on the device;
  * if has_expected and it differs -> NZ_ECORRUPT and nothing is published; else the
  * slot is published (visible to GETs).  The handle is consumed either way.

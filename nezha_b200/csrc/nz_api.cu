@@ -134,7 +134,6 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
         if (const char* ev = getenv("NZ_HOST_GRID")) c->host_grid = atoi(ev) > 0 ? atoi(ev) : c->host_grid.load();
         if (const char* ev = getenv("NZ_HOST_RATE_GBS")) c->host_rate_gbs = atof(ev);
         if (const char* ev = getenv("NZ_HOST_DMA")) c->host_dma = atoi(ev) != 0;
-        if (const char* ev = getenv("NZ_HOST_VARIANT")) { const int v = atoi(ev); if (v < nz_gather_num_variants()) c->host_variant = v; }
     }
     CKI(cudaMalloc(&c->peer_base_dev, sizeof(uint64_t) * c->cfg.shard_count));
     CKI(cudaMemset(c->peer_base_dev, 0, sizeof(uint64_t) * c->cfg.shard_count));
@@ -148,11 +147,10 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
     c->free_by_off[0] = c->arena_bytes;
     c->free_desc.reserve(c->cfg.max_objects);
     for (uint32_t i = c->cfg.max_objects; i-- > 0;) c->free_desc.push_back(i);
-    if (const char* ev = getenv("NZ_GATHER_VARIANT")) {
-        const int v = atoi(ev);
-        if (v >= 0 && v < nz_gather_num_variants()) c->gather_variant = v;
-    }
+    if (const char* ev = getenv("NZ_GATHER_VARIANT"))      // "0" / "reg": register path only; anything else: the default bulk-copy kernel
+        c->gather_variant = (!strcmp(ev, "0") || !strcmp(ev, "reg")) ? NZ_GATHER_REG : NZ_GATHER_TMA;
     if (const char* ev = getenv("NZ_COALESCE")) c->coalesce = atoi(ev) != 0;
+    if (const char* ev = getenv("NZ_SPAN_SPREAD")) { const int v = atoi(ev); if (v >= 0 && v <= 4096) c->span_spread = (uint32_t)v; }
     if (const char* ev = getenv("NZ_PROFILE")) c->profile = atoi(ev) != 0;
     if (const char* ev = getenv("NZ_FUSE_VERIFY")) c->fuse_verify = atoi(ev) != 0;
     if (const char* ev = getenv("NZ_FUSE_SMALL")) c->fuse_small = atoi(ev) != 0;
@@ -506,6 +504,12 @@ int32_t nz_put_file(nz_put* p, int fd, uint64_t file_off, uint64_t dst_off, uint
         }
         return nullptr;
     });
+}
+
+const char* nz_cufile_status(void) {
+    static thread_local char buf[256];
+    nz_cufile_why(buf, sizeof buf);
+    return buf;
 }
 
 static void put_release(nz_put* p, bool drop_reservation) {
@@ -964,7 +968,14 @@ static void size_verify_and_scratch(nz_ctx* c, const nz_get_req* reqs, uint32_t 
         const bool inflate = (r.flags & NZ_GET_INFLATE) && (ho.flags & NZ_ENC_GZIP);
         if (r.flags & NZ_GET_VERIFY) {
             const uint64_t all = (ho.stored_len + NZ_CRC_CHUNK - 1) / NZ_CRC_CHUNK;
-            if (inflate || r.nseg == 0) ver_cap += all;
+            if (ho.stripe_bytes) {
+                // striped: the GET is split at stripe boundaries and every piece is checked against its stripe's own chunk
+                // table (on the GPU that holds the stripe): up to two partial chunks per piece
+                auto bound = [&](uint64_t len) { return len / NZ_CRC_CHUNK + 2 + 2 * (len / ho.stripe_bytes + 2); };
+                if (r.nseg == 0) ver_cap += bound(ho.stored_len);
+                else for (uint32_t k = 0; k < r.nseg; ++k) ver_cap += bound(r.segs[k].len);
+            }
+            else if (inflate || r.nseg == 0) ver_cap += all;
             else for (uint32_t k = 0; k < r.nseg; ++k) ver_cap += std::min<uint64_t>(all, r.segs[k].len / NZ_CRC_CHUNK + 2);
         }
         if (!inflate || scratch_need.empty()) continue;
@@ -1092,7 +1103,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
 
     // waves that only write pinned host memory may use their own gather variant (write-through stores)
     const bool host_kernel = all_host && !dma;      // the gather kernel itself stores across PCIe
-    const int variant = (host_kernel && c->host_variant >= 0) ? c->host_variant : c->gather_variant;
+    const int variant = c->gather_variant;
     // upper bound on gather tiles when every slice length is known on the host (0 = unknown)
     uint64_t tile_bound = 0;
     {
@@ -1206,9 +1217,14 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
         t->paced = true;
         pace_ns = (uint32_t)std::min(1e6, (double)a.tile_bytes * ggrid * sharing / total_rate);      // bytes / (GB/s) = ns
     }
+    // K5: a wave with striped sources walks its tiles spread over the whole wave, so the CTAs running at any moment
+    // pull from stripes on different peers (see TileOrder in nz_kernels.cu)
+    uint32_t spread = 0;
+    if (c->span_spread)
+        for (const auto& sp : split) if (!sp.empty()) { spread = c->span_spread; break; }
     if (fused_small) { /* copied by the plan kernel */ }
-    else if (a.fuse_verify) CKT(nz_launch_gather(variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s, a.seg_ver, a.ver, c->crc_tables, pace_ns));
-    else CKT(nz_launch_gather(variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s, nullptr, nullptr, nullptr, pace_ns));
+    else if (a.fuse_verify) CKT(nz_launch_gather(variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s, a.seg_ver, a.ver, c->crc_tables, pace_ns, spread));
+    else CKT(nz_launch_gather(variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s, nullptr, nullptr, nullptr, pace_ns, spread));
     if (t->profiled) CKT(cudaEventRecord(t->ev_g1, s));
     c->launches += fused_small ? 0 : 1;
     if (any_verify && ver_cap) {

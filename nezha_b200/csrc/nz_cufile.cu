@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <cufile.h>
 #include <dlfcn.h>
+#include <errno.h>
+#include <string.h>
 #include <fcntl.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -28,6 +30,13 @@ struct Api {
 };
 Api g_api;
 std::once_flag g_once;
+// why the last attempt (or the driver open) did not carry the bytes: read back through nz_cufile_status
+std::mutex g_why_mu;
+char g_why[256] = "not tried";
+void why(const char* stage, int err, int cu_err) {
+    std::lock_guard<std::mutex> g(g_why_mu);
+    snprintf(g_why, sizeof g_why, "%s: cufile err %d, cuda err %d, errno %d", stage, err, cu_err, errno);
+}
 
 void init_api() {
     if (const char* ev = getenv("NZ_CUFILE"))
@@ -37,14 +46,16 @@ void init_api() {
         g_api.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
         if (g_api.lib) break;
     }
-    if (!g_api.lib) return;
+    if (!g_api.lib) { why("dlopen libcufile", 0, 0); return; }
     g_api.DriverOpen = (CUfileError_t(*)())dlsym(g_api.lib, "cuFileDriverOpen");
     g_api.HandleRegister = (CUfileError_t(*)(CUfileHandle_t*, CUfileDescr_t*))dlsym(g_api.lib, "cuFileHandleRegister");
     g_api.HandleDeregister = (void (*)(CUfileHandle_t))dlsym(g_api.lib, "cuFileHandleDeregister");
     g_api.Read = (ssize_t(*)(CUfileHandle_t, void*, size_t, off_t, off_t))dlsym(g_api.lib, "cuFileRead");
-    if (!g_api.DriverOpen || !g_api.HandleRegister || !g_api.HandleDeregister || !g_api.Read) return;
+    if (!g_api.DriverOpen || !g_api.HandleRegister || !g_api.HandleDeregister || !g_api.Read) { why("dlsym", 0, 0); return; }
     const CUfileError_t st = g_api.DriverOpen();
     g_api.ok = st.err == CU_FILE_SUCCESS;
+    if (!g_api.ok) why("cuFileDriverOpen", (int)st.err, (int)st.cu_err);
+    else why("driver open", 0, 0);
 }
 }  // namespace
 
@@ -64,7 +75,15 @@ int64_t nz_cufile_read(int fd, uint64_t file_off, void* dev_base, uint64_t dev_o
     d.handle.fd = use;
     CUfileHandle_t h;
     CUfileError_t st = g_api.HandleRegister(&h, &d);
+    if (st.err != CU_FILE_SUCCESS && dfd >= 0) {          // the O_DIRECT descriptor was refused: the plain one (compat mode)
+        why("cuFileHandleRegister(O_DIRECT)", (int)st.err, (int)st.cu_err);
+        close(dfd);
+        dfd = -1;
+        d.handle.fd = fd;
+        st = g_api.HandleRegister(&h, &d);
+    }
     if (st.err != CU_FILE_SUCCESS) {
+        why("cuFileHandleRegister", (int)st.err, (int)st.cu_err);
         if (dfd >= 0) close(dfd);
         return -1;
     }
@@ -73,10 +92,16 @@ int64_t nz_cufile_read(int fd, uint64_t file_off, void* dev_base, uint64_t dev_o
     while (done < len) {
         const size_t want = (size_t)((len - done) > (64ull << 20) ? (64ull << 20) : (len - done));
         const ssize_t r = g_api.Read(h, dev_base, want, (off_t)(file_off + done), (off_t)(dev_off + done));
-        if (r <= 0) { rc = -1; break; }
+        if (r <= 0) { why("cuFileRead", (int)r, 0); rc = -1; break; }
         done += (uint64_t)r;
     }
     g_api.HandleDeregister(h);
     if (dfd >= 0) close(dfd);
+    if (rc >= 0) why("ok", 0, 0);
     return rc < 0 ? -1 : (int64_t)done;
+}
+
+void nz_cufile_why(char* out, size_t cap) {
+    std::lock_guard<std::mutex> g(g_why_mu);
+    snprintf(out, cap, "%s", g_why);
 }

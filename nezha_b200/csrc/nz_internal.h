@@ -247,6 +247,8 @@ struct nz_put {
     cudaStream_t stream;
 };
 
+constexpr int NZ_GATHER_REG = 0, NZ_GATHER_TMA = 1;     // the two K2 kernels (nz_kernels.cu)
+
 struct nz_ctx {
     nz_config cfg;
     int device;
@@ -256,7 +258,8 @@ struct nz_ctx {
     bool fuse_small = true;  // env NZ_FUSE_SMALL=0: small waves launch plan and gather separately
     bool fuse_verify = true; // env NZ_FUSE_VERIFY=0: NZ_GET_VERIFY re-reads every chunk in k_verify (A/B measurements)
     bool coalesce = true;   // env NZ_COALESCE=0 turns request coalescing off (A/B measurements)
-    int gather_variant = 14; // k_gather variant: 14 = TMA bulk-copy staging (default, measured best); 0-13 register paths (env NZ_GATHER_VARIANT)
+    uint32_t span_spread = 64; // K5: rows of the spread tile order of waves with striped sources (env NZ_SPAN_SPREAD, 0 = plain order)
+    int gather_variant = NZ_GATHER_TMA; // K2 kernel: bulk-copy engine staging (default) or the register path (env NZ_GATHER_VARIANT=0|reg)
     int inflate_grid;
     int inflate_seg_grid;
     uint8_t* arena = nullptr;
@@ -285,7 +288,6 @@ struct nz_ctx {
     bool host_dma = true;                   // env NZ_HOST_DMA=0: always store from the gather kernel
     std::atomic<uint64_t> dma_waves{0};
     std::atomic<int> paced_inflight{0};     // paced waves submitted and not yet seen complete
-    int host_variant = -1;                  // gather variant for such waves (-1 = gather_variant); env NZ_HOST_VARIANT
     std::atomic<int> host_grid{32};                     // CTAs for waves that only write pinned host memory (PCIe bound: leave the SMs free)
     // ticket recycling + the waves in flight (nz_evict frees an extent only after every wave submitted before the
     // erase has finished: such a wave may have probed the slot while it was still live)
@@ -354,9 +356,8 @@ cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s, const NzSmallWav
 cudaError_t nz_launch_gather(int variant, const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head,
                              const uint32_t* chain_next, uint32_t nseg, int grid, cudaStream_t s,
                              const uint32_t* seg_ver = nullptr, NzVerWork* ver = nullptr, const uint32_t* crc_tables = nullptr,
-                             uint32_t pace_ns = 0);
+                             uint32_t pace_ns = 0, uint32_t spread = 0);
 bool nz_gather_fuses_verify(int variant);
-int nz_gather_num_variants();
 uint32_t nz_gather_tile_bytes(int variant);
 cudaError_t nz_launch_verify(const NzPlanArgs& a, const uint32_t* crc_tables, int grid, cudaStream_t s);
 cudaError_t nz_launch_crc_chunks(const uint8_t* p, uint64_t n, uint32_t* chunk_out, uint32_t* whole_out,
@@ -371,6 +372,7 @@ cudaError_t nz_launch_publish(NzSlot* table, uint64_t line_mask, NzDesc* descs, 
                               int32_t* status, cudaStream_t s);
 int nz_inflate_seg_blocks_per_sm();
 int64_t nz_cufile_read(int fd, uint64_t file_off, void* dev_base, uint64_t dev_off, uint64_t len);
+void nz_cufile_why(char* out, size_t cap);
 cudaError_t nz_upload_constants(uint32_t* crc_tables_dev);
 cudaError_t nz_inflate_upload_constants();
 int nz_gather_blocks_per_sm(int variant);

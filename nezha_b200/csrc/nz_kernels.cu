@@ -525,9 +525,24 @@ k_plan_verify(NzPlanArgs a) {
         if (d == 0xFFFFFFFFu) continue;
         const NzDesc ds = a.descs[d];
         if ((rq.flags & NZ_GET_INFLATE) && (ds.flags & NZ_ENC_GZIP)) continue;       // done in k_plan (whole member)
-        if (ds.flags & NZ_ENC_STRIPED) continue;     // stripes carry their own chunk tables on their GPUs (verified at fill)
+        // where the checked bytes and their chunk table live: the object's extent, or - for a striped object, whose GET the
+        // host split at stripe boundaries - the one stripe this slice lies in, on whichever GPU holds it (its chunk
+        // table sits next to it in that GPU's arena and is read over NVLink like the bytes)
+        const uint8_t* vbase_ptr = a.arena + ds.arena_off;
         const uint32_t* tab = reinterpret_cast<const uint32_t*>(a.arena + ds.crc_tab_off);
-        const uint64_t off = rq.whole ? 0 : sg.src_off, len = w.len;
+        uint64_t vlen = ds.stored_len;
+        uint64_t off = rq.whole ? 0 : sg.src_off;
+        const uint64_t len = w.len;
+        if (ds.flags & NZ_ENC_STRIPED) {
+            const uint64_t k = off / ds.stripe_bytes;
+            const NzDevStripe stp = reinterpret_cast<const NzDevStripe*>(a.arena + ds.arena_off)[k];
+            const uint64_t pbase = a.peer_base ? a.peer_base[stp.shard] : 0;
+            if (pbase == 0) continue;                    // k_plan already failed this request (NZ_ENOSYS)
+            off -= k * ds.stripe_bytes;
+            vbase_ptr = reinterpret_cast<const uint8_t*>(pbase + stp.arena_off);
+            tab = reinterpret_cast<const uint32_t*>(pbase + stp.crc_tab_off);
+            vlen = stp.len;
+        }
         const uint32_t c0 = (uint32_t)(off / NZ_CRC_CHUNK), c1 = (uint32_t)((off + len - 1) / NZ_CRC_CHUNK);
         const uint32_t cnt = c1 - c0 + 1;
         uint32_t first = 0;
@@ -545,8 +560,8 @@ k_plan_verify(NzPlanArgs a) {
         for (uint32_t c = lane; c < cnt && first + c < a.ver_cap; c += 32) {
             NzVerWork v;
             const uint64_t coff = (uint64_t)(c0 + c) * NZ_CRC_CHUNK;
-            v.ptr = (uint64_t)(a.arena + ds.arena_off + coff);
-            v.len = (uint32_t)min((uint64_t)NZ_CRC_CHUNK, ds.stored_len - coff);
+            v.ptr = (uint64_t)(vbase_ptr + coff);
+            v.len = (uint32_t)min((uint64_t)NZ_CRC_CHUNK, vlen - coff);
             const bool inside = coff >= off && coff + v.len <= off + len;
             v.expect = tab[c0 + c]; v.req = sg.req;
             v.seg = s | ((fusable && inside) ? NZ_VER_FUSED : 0u);
@@ -587,30 +602,6 @@ __device__ __forceinline__ uint4 realign(const uint4 a, const uint4 b, unsigned 
     return o;
 }
 
-// cache-hint variants for the streaming loads/stores (HINT template parameter)
-template <int HINT>
-__device__ __forceinline__ uint4 ldg_s(const void* p) {
-    uint4 r;
-    if constexpr (HINT == 1)
-        asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    else
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-template <int HINT>
-__device__ __forceinline__ void stg_s(void* p, const uint4& v) {
-    if constexpr (HINT == 2)
-        asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    else if constexpr (HINT == 3)
-        asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    else if constexpr (HINT == 4)
-        asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    else if constexpr (HINT == 5)   // write-through: a store to system memory leaves L2 at once instead of waiting there as a dirty line
-        asm volatile("st.global.wt.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    else
-        asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
 // destinations of one tile: the leader's and, through the chain, every coalesced follower's
 struct DstChain {
     uint8_t* d0;                                   // leader destination of this tile's first byte
@@ -620,7 +611,7 @@ struct DstChain {
     uint32_t head;                                 // first follower or 0xFFFFFFFF
 };
 
-template <int WS, int NT, int U2, int HINT>
+template <int WS, int NT, int U2>
 __device__ __forceinline__ void copy_vectors_shifted(const uint4* __restrict__ sa /*aligned base*/, const DstChain& c, uint32_t dskip,
                                                      uint32_t nvec, unsigned bs) {
     constexpr int U = U2 > 1 ? U2 / 2 : 1;   // two loads per output vector
@@ -636,22 +627,22 @@ __device__ __forceinline__ void copy_vectors_shifted(const uint4* __restrict__ s
         }
         uint4* d = reinterpret_cast<uint4*>(c.d0 + dskip);
 #pragma unroll
-        for (int u = 0; u < U; ++u) stg_s<HINT>(d + base + u * NT + tid, v[u]);
+        for (int u = 0; u < U; ++u) stg_stream(d + base + u * NT + tid, v[u]);
         for (uint32_t m = c.head; m != 0xFFFFFFFFu; m = __ldg(c.next + m)) {
             uint4* dm = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(__ldg(&c.work[m].dst)) + c.lo + dskip);
 #pragma unroll
-            for (int u = 0; u < U; ++u) stg_s<HINT>(dm + base + u * NT + tid, v[u]);
+            for (int u = 0; u < U; ++u) stg_stream(dm + base + u * NT + tid, v[u]);
         }
     }
     for (uint32_t i = base + tid; i < nvec; i += NT) {
         const uint4 v = realign<WS>(ldg_cached(sa + i), ldg_cached(sa + i + 1), bs);
-        stg_s<HINT>(reinterpret_cast<uint4*>(c.d0 + dskip) + i, v);
+        stg_stream(reinterpret_cast<uint4*>(c.d0 + dskip) + i, v);
         for (uint32_t m = c.head; m != 0xFFFFFFFFu; m = __ldg(c.next + m))
-            stg_s<HINT>(reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(__ldg(&c.work[m].dst)) + c.lo + dskip) + i, v);
+            stg_stream(reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(__ldg(&c.work[m].dst)) + c.lo + dskip) + i, v);
     }
 }
 
-template <int NT, int U, int HINT>
+template <int NT, int U>
 __device__ __forceinline__ void copy_vectors_aligned(const uint4* __restrict__ sv, const DstChain& c, uint32_t dskip, uint32_t nvec) {
     constexpr uint32_t STEP = NT * U;
     const uint32_t tid = threadIdx.x;
@@ -659,25 +650,25 @@ __device__ __forceinline__ void copy_vectors_aligned(const uint4* __restrict__ s
     for (; base + STEP <= nvec; base += STEP) {
         uint4 v[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = ldg_s<HINT>(sv + base + u * NT + tid);
+        for (int u = 0; u < U; ++u) v[u] = ldg_stream(sv + base + u * NT + tid);
         uint4* d = reinterpret_cast<uint4*>(c.d0 + dskip);
 #pragma unroll
-        for (int u = 0; u < U; ++u) stg_s<HINT>(d + base + u * NT + tid, v[u]);
+        for (int u = 0; u < U; ++u) stg_stream(d + base + u * NT + tid, v[u]);
         for (uint32_t m = c.head; m != 0xFFFFFFFFu; m = __ldg(c.next + m)) {
             uint4* dm = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(__ldg(&c.work[m].dst)) + c.lo + dskip);
 #pragma unroll
-            for (int u = 0; u < U; ++u) stg_s<HINT>(dm + base + u * NT + tid, v[u]);
+            for (int u = 0; u < U; ++u) stg_stream(dm + base + u * NT + tid, v[u]);
         }
     }
     for (uint32_t i = base + tid; i < nvec; i += NT) {
-        const uint4 v = ldg_s<HINT>(sv + i);
-        stg_s<HINT>(reinterpret_cast<uint4*>(c.d0 + dskip) + i, v);
+        const uint4 v = ldg_stream(sv + i);
+        stg_stream(reinterpret_cast<uint4*>(c.d0 + dskip) + i, v);
         for (uint32_t m = c.head; m != 0xFFFFFFFFu; m = __ldg(c.next + m))
-            stg_s<HINT>(reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(__ldg(&c.work[m].dst)) + c.lo + dskip) + i, v);
+            stg_stream(reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(__ldg(&c.work[m].dst)) + c.lo + dskip) + i, v);
     }
 }
 
-template <int NT, int U, int HINT>
+template <int NT, int U>
 __device__ __forceinline__ void copy_tile(const uint8_t* __restrict__ s, const DstChain& c, uint32_t n) {
     const uint32_t tid = threadIdx.x;
     // head: bring the destination to a 16 B boundary (only the first tile of a slice can need it;
@@ -700,15 +691,15 @@ __device__ __forceinline__ void copy_tile(const uint8_t* __restrict__ s, const D
     s += head;
     const unsigned mis = (unsigned)((uintptr_t)s & 15u);
     if (mis == 0) {
-        copy_vectors_aligned<NT, U, HINT>(reinterpret_cast<const uint4*>(s), c, head, nvec);
+        copy_vectors_aligned<NT, U>(reinterpret_cast<const uint4*>(s), c, head, nvec);
     } else {
         const uint4* sa = reinterpret_cast<const uint4*>(s - mis);
         const unsigned bs = (mis & 3u) * 8u;
         switch (mis >> 2) {
-        case 0: copy_vectors_shifted<0, NT, U, HINT>(sa, c, head, nvec, bs); break;
-        case 1: copy_vectors_shifted<1, NT, U, HINT>(sa, c, head, nvec, bs); break;
-        case 2: copy_vectors_shifted<2, NT, U, HINT>(sa, c, head, nvec, bs); break;
-        default: copy_vectors_shifted<3, NT, U, HINT>(sa, c, head, nvec, bs); break;
+        case 0: copy_vectors_shifted<0, NT, U>(sa, c, head, nvec, bs); break;
+        case 1: copy_vectors_shifted<1, NT, U>(sa, c, head, nvec, bs); break;
+        case 2: copy_vectors_shifted<2, NT, U>(sa, c, head, nvec, bs); break;
+        default: copy_vectors_shifted<3, NT, U>(sa, c, head, nvec, bs); break;
         }
     }
 }
@@ -731,7 +722,7 @@ __device__ void plan_fused_copy(const NzPlanArgs& a) {
             if (hi > (int64_t)w.len) hi = (int64_t)w.len;
             dc.d0 = reinterpret_cast<uint8_t*>(w.dst) + lo;
             dc.lo = lo;
-            copy_tile<1024, 2, 0>(reinterpret_cast<const uint8_t*>(w.src) + lo, dc, (uint32_t)(hi - lo));
+            copy_tile<1024, 2>(reinterpret_cast<const uint8_t*>(w.src) + lo, dc, (uint32_t)(hi - lo));
         }
     }
 }
@@ -763,17 +754,40 @@ struct TileCursor {
     }
 };
 
-template <int NT, int U, int MINB, int HINT>
+// Tile order.  Normally CTA b takes tiles b, b + grid, ...: the whole grid works on one neighbourhood of the wave,
+// which keeps DRAM pages of the destinations open.  A wave with striped sources (K5) instead walks the tile list as a
+// `spread` x C matrix column by column: the CTAs running at any moment sit at `spread` evenly spaced positions of the
+// wave, i.e. in stripes of different peer GPUs, so the NVLink pulls of one GPU are spread over all its peers instead
+// of hammering one peer's egress at a time.
+struct TileOrder {
+    uint64_t total, cols;
+    uint32_t spread;
+    __device__ __forceinline__ TileOrder(uint64_t total_, uint32_t spread_) : total(total_), cols(0), spread(spread_) {
+        if (spread > 1 && total > 4ull * spread) cols = (total + spread - 1) / spread; else spread = 0;
+    }
+    __device__ __forceinline__ uint64_t steps() const { return spread ? cols * spread : total; }
+    // tile of step i, or ~0 when the step falls off the ragged last column
+    __device__ __forceinline__ uint64_t tile(uint64_t i) const {
+        if (!spread) return i;
+        const uint64_t t = (i % spread) * cols + i / spread;
+        return t < total ? t : ~0ull;
+    }
+};
+
+// Register path on its own (NZ_GATHER_VARIANT=0): the fallback and the A/B partner of the bulk-copy kernel.
+template <int NT, int U, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 k_gather(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_begin, const uint32_t* __restrict__ chain_head,
-         const uint32_t* __restrict__ chain_next, uint32_t nseg, uint32_t tile_bytes) {
-    const uint64_t total = tile_begin[nseg];
+         const uint32_t* __restrict__ chain_next, uint32_t nseg, uint32_t tile_bytes, uint32_t spread) {
+    const TileOrder ord(tile_begin[nseg], spread);
     TileCursor c;
     DstChain dc;
     dc.work = work;
     dc.next = chain_next;
     dc.head = 0xFFFFFFFFu;
-    for (uint64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    for (uint64_t i = blockIdx.x; i < ord.steps(); i += gridDim.x) {
+        const uint64_t tile = ord.tile(i);
+        if (tile == ~0ull) continue;
         const uint32_t before = c.seg;
         const bool fresh = !(tile >= c.lo_t && tile < c.hi_t);
         c.seek(tile, work, tile_begin, nseg);
@@ -782,7 +796,7 @@ k_gather(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_b
         c.span(tile, tile_bytes, lo, hi);
         dc.d0 = reinterpret_cast<uint8_t*>(c.dst) + lo;
         dc.lo = lo;
-        copy_tile<NT, U, HINT>(reinterpret_cast<const uint8_t*>(c.src) + lo, dc, (uint32_t)(hi - lo));
+        copy_tile<NT, U>(reinterpret_cast<const uint8_t*>(c.src) + lo, dc, (uint32_t)(hi - lo));
     }
 }
 
@@ -928,13 +942,13 @@ cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s, const NzSmallWav
     return e;
 }
 // ---------------------------------------------------------------------------
-// K2 with TMA staging (variant 14).  A tile whose source, destinations and length are all
+// K2 with TMA staging (the default kernel).  A tile whose source, destinations and length are all
 // 16 B aligned is moved by the bulk-copy engine instead of through registers:
 //   cp.async.bulk  global -> shared   (one 32 KiB tile, completion on an mbarrier)
 //   cp.async.bulk  shared -> global   once per destination of the coalesced group
 // so a tile read once from HBM is written to every member with large contiguous bulk
-// stores and almost no instructions.  Two shared buffers per CTA alternate: the load of
-// tile i+1 is in flight while the stores of tile i drain.  Tiles that do not qualify (byte
+// stores and almost no instructions.  STAGES shared buffers per CTA alternate: the load of
+// tile i+1 is issued while the stores of tile i drain.  Tiles that do not qualify (byte
 // ranges, tails) take the register path of copy_tile.  One elected thread drives the engine.
 // ---------------------------------------------------------------------------
 constexpr int NZ_TMA_THREADS = 128;
@@ -944,8 +958,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
 
-// STAGES shared buffers of tile_bytes each.  The load of tile i is issued before the stores of
-// tile i-1, so a tile's HBM read overlaps the previous tile's writes inside one CTA.
 // Fused verify (VERIFY = true): the CRC-32C of every tile piece is taken from the copy that sits in
 // shared memory (or, for the few short tiles of such a slice, from the source lines just read) and
 // XOR-accumulated per 64 KiB chunk in the wave's verify entries; k_verify compares afterwards.
@@ -1005,12 +1017,47 @@ __device__ __forceinline__ void tile_verify(const VerifyCtx& vc, const uint8_t* 
     }
 }
 
-template <int STAGES, bool AHEAD, bool VERIFY>
+// L2 policy of the engine's stores (NZ_TMA_L2HINT): 0 = none, 1 = evict_first (the response bytes are not read again
+// by this GPU: let them leave L2 ahead of everything else), 2 = evict_first stores + evict_last loads.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t smem, uint32_t bytes, uint64_t pol) {
+    if (pol)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" :: "l"(dst), "r"(smem), "r"(bytes), "l"(pol) : "memory");
+    else
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t smem, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+    if (pol)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                     :: "r"(smem), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+    else
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+
+// l2h: 0 no hints, 1 evict_first stores, 2 evict_first stores + evict_last loads (a createpolicy result is never 0)
+template <int STAGES, bool VERIFY>
 __global__ void __launch_bounds__(VERIFY ? NZ_TMA_VTHREADS : NZ_TMA_THREADS)
 k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_begin, const uint32_t* __restrict__ chain_head,
              const uint32_t* __restrict__ chain_next, uint32_t nseg, uint32_t tile_bytes, const uint32_t* __restrict__ seg_ver,
-             NzVerWork* ver, const uint32_t* __restrict__ crc_tables, uint32_t pace_ns) {
-    static_assert(!(AHEAD && VERIFY), "fused verify uses the simple pipeline");
+             NzVerWork* ver, const uint32_t* __restrict__ crc_tables, uint32_t pace_ns, uint32_t spread, uint32_t l2h) {
     extern __shared__ __align__(128) uint8_t s_buf[];          // STAGES x tile_bytes [ | 32 KiB stride table when VERIFY ]
     __shared__ __align__(8) uint64_t s_bar[STAGES];
     __shared__ uint32_t s_red[16];
@@ -1030,7 +1077,8 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     __syncthreads();
-    const uint64_t total = tile_begin[nseg];
+    const uint64_t pol_st = l2h >= 1 ? l2_policy_evict_first() : 0, pol_ld = l2h >= 2 ? l2_policy_evict_last() : 0;
+    const TileOrder ord(tile_begin[nseg], spread);
     TileCursor c;
     DstChain dc;
     dc.work = work;
@@ -1044,29 +1092,9 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
     uint64_t pre_tile = 0;
     uint64_t pace_next = 0;
     if (pace_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pace_next));
-    // the engine tile whose load is in flight and whose stores are still to be issued (thread 0 only)
-    bool p_valid = false;
-    uint32_t p_slot = 0, p_bulk = 0, p_head = 0xFFFFFFFFu;
-    uint8_t* p_d = nullptr;
-    int64_t p_lo = 0;
-    auto flush = [&]() {                                       // thread 0: wait for the pending tile, fan it out
-        const uint32_t buf = smem_u32(s_buf + (size_t)p_slot * tile_bytes), bar = smem_u32(&s_bar[p_slot]);
-        uint32_t done = 0;
-        while (!done) {
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                         : "=r"(done) : "r"(bar), "r"((phase_bits >> p_slot) & 1u) : "memory");
-        }
-        phase_bits ^= 1u << p_slot;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(p_d), "r"(buf), "r"(p_bulk) : "memory");
-        for (uint32_t m = p_head; m != 0xFFFFFFFFu; m = __ldg(chain_next + m)) {
-            uint8_t* dm = reinterpret_cast<uint8_t*>(__ldg(&work[m].dst)) + p_lo;
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dm), "r"(buf), "r"(p_bulk) : "memory");
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        p_valid = false;
-    };
-    for (uint64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    for (uint64_t i = blockIdx.x; i < ord.steps(); i += gridDim.x) {
+        const uint64_t tile = ord.tile(i);
+        if (tile == ~0ull) continue;
         const uint32_t before = c.seg;
         const bool fresh = !(tile >= c.lo_t && tile < c.hi_t);
         c.seek(tile, work, tile_begin, nseg);
@@ -1087,7 +1115,7 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
         if (!engine) {
             dc.d0 = d;
             dc.lo = lo;
-            copy_tile<NT, 8, 0>(s, dc, n);
+            copy_tile<NT, 8>(s, dc, n);
             if constexpr (VERIFY) {
                 if (vbase != 0xFFFFFFFFu) tile_verify(vc, s, s, n, vbase, c0ptr);   // short tile of an engine slice: lines are L2-hot
             }
@@ -1102,75 +1130,59 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
             }
             pace_next = (now - pace_next > 8ull * pace_ns ? now : pace_next) + pace_ns;     // no burst after a stall
         }
+        const uint32_t buf = smem_u32(s_buf + (size_t)slot * tile_bytes), bar = smem_u32(&s_bar[slot]);
         if constexpr (VERIFY) {
-            // simple pipeline, every thread follows the barrier phases: load -> (all wait) -> stores -> checksum from shared memory
-            const uint32_t buf = smem_u32(s_buf + (size_t)slot * tile_bytes), bar = smem_u32(&s_bar[slot]);
+            // every thread follows the barrier phases: load -> (all wait) -> stores -> checksum from shared memory
             if (tid == 0 && !(pre_valid && pre_tile == tile)) {   // not already in flight from the previous iteration's look-ahead
                 bulk_wait_read<STAGES - 1>();
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bulk) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             :: "r"(buf), "l"(s), "r"(bulk), "r"(bar) : "memory");
+                bulk_load(buf, s, bulk, bar, pol_ld);
             }
             pre_valid = false;
             const bool vt = vbase != 0xFFFFFFFFu;
-            if (vt || tid == 0) {
-                uint32_t done = 0;
-                while (!done) {
-                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                                 : "=r"(done) : "r"(bar), "r"((phase_bits >> slot) & 1u) : "memory");
-                }
-            }
+            if (vt || tid == 0) mbar_wait(bar, (phase_bits >> slot) & 1u);
             phase_bits ^= 1u << slot;
             if (tid == 0) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(d), "r"(buf), "r"(bulk) : "memory");
-                for (uint32_t m = dc.head; m != 0xFFFFFFFFu; m = __ldg(chain_next + m)) {
-                    uint8_t* dm = reinterpret_cast<uint8_t*>(__ldg(&work[m].dst)) + lo;
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dm), "r"(buf), "r"(bulk) : "memory");
-                }
+                bulk_store(d, buf, bulk, pol_st);
+                for (uint32_t m = dc.head; m != 0xFFFFFFFFu; m = __ldg(chain_next + m))
+                    bulk_store(reinterpret_cast<uint8_t*>(__ldg(&work[m].dst)) + lo, buf, bulk, pol_st);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
             // look-ahead: the checksum below takes longer than a tile's load, so the next tile of this CTA is requested
             // first (into the other stage; its previous stores are done once at most this tile's group is pending)
-            if (vt && tile + gridDim.x < total) {
+            const uint64_t tile2 = i + gridDim.x < ord.steps() ? ord.tile(i + gridDim.x) : ~0ull;
+            if (vt && tile2 != ~0ull) {
                 TileCursor c2 = c;
-                c2.seek(tile + gridDim.x, work, tile_begin, nseg);
+                c2.seek(tile2, work, tile_begin, nseg);
                 int64_t lo2, hi2;
-                c2.span(tile + gridDim.x, tile_bytes, lo2, hi2);
+                c2.span(tile2, tile_bytes, lo2, hi2);
                 const uint8_t* s2 = reinterpret_cast<const uint8_t*>(c2.src) + lo2;
                 const uint8_t* d2 = reinterpret_cast<const uint8_t*>(c2.dst) + lo2;
                 const uint32_t bulk2 = (uint32_t)(hi2 - lo2) & ~15u;
                 if (bulk2 >= 2048 && ((((uintptr_t)s2) | ((uintptr_t)d2)) & 15u) == 0) {
                     const uint32_t slot2 = slot + 1 == STAGES ? 0 : slot + 1;
                     if (tid == 0) {
-                        const uint32_t buf2 = smem_u32(s_buf + (size_t)slot2 * tile_bytes), bar2 = smem_u32(&s_bar[slot2]);
                         bulk_wait_read<STAGES - 1>();
-                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar2), "r"(bulk2) : "memory");
-                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                     :: "r"(buf2), "l"(s2), "r"(bulk2), "r"(bar2) : "memory");
+                        bulk_load(smem_u32(s_buf + (size_t)slot2 * tile_bytes), s2, bulk2, smem_u32(&s_bar[slot2]), pol_ld);
                     }
                     pre_valid = true;
-                    pre_tile = tile + gridDim.x;
+                    pre_tile = tile2;
                 }
             }
             if (vt) tile_verify(vc, s_buf + (size_t)slot * tile_bytes, s, n, vbase, c0ptr);
-        } else
-        if (tid == 0) {
-            const uint32_t buf = smem_u32(s_buf + (size_t)slot * tile_bytes), bar = smem_u32(&s_bar[slot]);
-            // stage `slot` was last read by the stores of the engine tile STAGES back; the store groups still
-            // allowed in flight are those of the tiles between (the immediately previous tile is not committed yet)
-            if constexpr (AHEAD) bulk_wait_read<(STAGES >= 2 ? STAGES - 2 : 0)>();
-            else bulk_wait_read<STAGES - 1>();                 // every earlier tile's stores are committed here
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bulk) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"(buf), "l"(s), "r"(bulk), "r"(bar) : "memory");
-            if constexpr (AHEAD) {
-                if (p_valid) flush();                          // previous tile: its load had a whole tile of time to land
-                p_valid = true; p_slot = slot; p_bulk = bulk; p_head = dc.head; p_d = d; p_lo = lo;
-            } else {                                           // other CTAs on the SM cover this tile's load latency
-                p_slot = slot; p_bulk = bulk; p_head = dc.head; p_d = d; p_lo = lo;
-                flush();
-            }
+        } else if (tid == 0) {
+            // one elected thread drives the engine.  Stage `slot` was last read by the stores of the engine tile STAGES
+            // back: at most STAGES-1 younger store groups may still be reading shared memory.  The other CTAs resident
+            // on the SM cover this tile's load latency (a look-ahead inside the CTA was measured slower: it costs a stage).
+            bulk_wait_read<STAGES - 1>();
+            bulk_load(buf, s, bulk, bar, pol_ld);
+            mbar_wait(bar, (phase_bits >> slot) & 1u);
+            phase_bits ^= 1u << slot;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bulk_store(d, buf, bulk, pol_st);
+            for (uint32_t m = dc.head; m != 0xFFFFFFFFu; m = __ldg(chain_next + m))
+                bulk_store(reinterpret_cast<uint8_t*>(__ldg(&work[m].dst)) + lo, buf, bulk, pol_st);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         slot = slot + 1 == STAGES ? 0 : slot + 1;
         // tail bytes of a slice's last tile (every member)
@@ -1182,19 +1194,16 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
                 (reinterpret_cast<uint8_t*>(__ldg(&work[m].dst)) + lo)[bulk + tid] = b8;
         }
     }
-    if (tid == 0) {
-        if (p_valid) flush();
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-struct TmaCfg { int stages; uint32_t tile; bool ahead; };
+struct TmaCfg { int stages; uint32_t tile; int l2hint; };
 static TmaCfg tma_cfg() {
     static TmaCfg c = [] {
-        TmaCfg t{2, 32768, false};
-        if (const char* e = getenv("NZ_TMA_AHEAD")) t.ahead = atoi(e) != 0;
+        TmaCfg t{2, 32768, 0};
         if (const char* e = getenv("NZ_TMA_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 4) t.stages = v; }
         if (const char* e = getenv("NZ_TMA_TILE_KB")) { const int v = atoi(e); if (v == 16 || v == 32 || v == 64) t.tile = (uint32_t)v << 10; }
+        if (const char* e = getenv("NZ_TMA_L2HINT")) { const int v = atoi(e); if (v >= 0 && v <= 2) t.l2hint = v; }
         while ((size_t)t.stages * t.tile > (200u << 10)) --t.stages;     // stay inside one SM's shared memory
         return t;
     }();
@@ -1204,9 +1213,9 @@ struct TmaArgs {
     const NzSegWork* work; const uint64_t* tile_begin; const uint32_t* chain_head; const uint32_t* chain_next;
     uint32_t nseg; int grid; cudaStream_t s; int* occ;
     const uint32_t* seg_ver; NzVerWork* ver; const uint32_t* crc_tables;
-    uint32_t pace_ns;
+    uint32_t pace_ns, spread;
 };
-template <int STAGES, bool AHEAD, bool VERIFY>
+template <int STAGES, bool VERIFY>
 static cudaError_t launch_tma(const TmaArgs& a) {
     const TmaCfg t = tma_cfg();
     const size_t smem = (size_t)STAGES * t.tile + (VERIFY ? 32768 : 0);
@@ -1216,124 +1225,63 @@ static cudaError_t launch_tma(const TmaArgs& a) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        cudaFuncSetAttribute(k_gather_tma<STAGES, AHEAD, VERIFY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_gather_tma<STAGES, VERIFY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (dev >= 0 && dev < 64) {
             attr_set[dev] = true;
             int nb = 0, sms = 0;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather_tma<STAGES, AHEAD, VERIFY>, NTH, smem) != cudaSuccess || nb < 1) nb = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather_tma<STAGES, VERIFY>, NTH, smem) != cudaSuccess || nb < 1) nb = 1;
             max_grid[dev] = nb * (sms > 0 ? sms : 1);
         }
     }
     if (a.occ) {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather_tma<STAGES, AHEAD, VERIFY>, NTH, smem) != cudaSuccess || nb < 1) nb = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather_tma<STAGES, VERIFY>, NTH, smem) != cudaSuccess || nb < 1) nb = 1;
         *a.occ = nb;
         return cudaSuccess;
     }
     int grid = a.grid;
     if (VERIFY && dev >= 0 && dev < 64 && max_grid[dev] > 0 && grid > max_grid[dev]) grid = max_grid[dev];
-    k_gather_tma<STAGES, AHEAD, VERIFY><<<grid, NTH, smem, a.s>>>(a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, t.tile,
-                                                                              a.seg_ver, a.ver, a.crc_tables, a.pace_ns);
+    k_gather_tma<STAGES, VERIFY><<<grid, NTH, smem, a.s>>>(a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, t.tile,
+                                                                            a.seg_ver, a.ver, a.crc_tables, a.pace_ns, a.spread, (uint32_t)t.l2hint);
     return cudaGetLastError();
 }
 static cudaError_t dispatch_tma(const TmaArgs& a) {
     const TmaCfg t = tma_cfg();
-    if (a.seg_ver) {                          // fused verify: simple pipeline only
+    if (a.seg_ver) {                          // fused verify
         switch (t.stages) {
-        case 3: return launch_tma<3, false, true>(a);
-        case 4: return launch_tma<4, false, true>(a);
-        default: return launch_tma<2, false, true>(a);
-        }
-    }
-    if (t.ahead) {
-        switch (t.stages) {
-        case 2: return launch_tma<2, true, false>(a);
-        case 4: return launch_tma<4, true, false>(a);
-        default: return launch_tma<3, true, false>(a);
+        case 3: return launch_tma<3, true>(a);
+        case 4: return launch_tma<4, true>(a);
+        default: return launch_tma<2, true>(a);
         }
     }
     switch (t.stages) {
-    case 3: return launch_tma<3, false, false>(a);
-    case 4: return launch_tma<4, false, false>(a);
-    default: return launch_tma<2, false, false>(a);
+    case 3: return launch_tma<3, false>(a);
+    case 4: return launch_tma<4, false>(a);
+    default: return launch_tma<2, false>(a);
     }
 }
 
-// gather variants: {threads, vectors in flight per thread, CTAs per SM, cache hints}; tile = threads * U * 16 B
-struct GatherVariant { int nt, u, minb, hint; };
-static const GatherVariant kGatherVariants[] = {
-    {256, 8, 2, 0},   // 0: r01 baseline, 32 KiB tiles
-    {256, 4, 4, 0},   // 1
-    {512, 4, 2, 0},   // 2
-    {512, 8, 1, 0},   // 3
-    {1024, 4, 1, 0},  // 4
-    {128, 8, 4, 0},   // 5
-    {256, 8, 2, 1},   // 6: + L2::256B prefetch hint on loads
-    {256, 8, 2, 2},   // 7: + st.global.cs
-    {512, 4, 2, 1},   // 8
-    {256, 16, 1, 0},  // 9: 64 KiB tiles, deep unroll
-    {256, 8, 2, 3},   // 10: plain st.global
-    {256, 8, 2, 4},   // 11: st.global.cg
-    {256, 4, 6, 3},   // 12: plain stores, 6 CTAs/SM
-    {512, 8, 1, 3},   // 13: plain stores, 64 KiB tiles
-    {128, 16, 3, 0},  // 14: TMA bulk-copy staging (k_gather_tma); nt*u*16 = 32 KiB tile
-    {256, 8, 2, 5},   // 15: st.global.wt (write-through) - for waves whose destinations are all pinned host memory
-};
-constexpr int kNumGatherVariants = (int)(sizeof(kGatherVariants) / sizeof(kGatherVariants[0]));
-
-int nz_gather_num_variants() { return kNumGatherVariants; }
-uint32_t nz_gather_tile_bytes(int v) {
-    if (v == 14) return tma_cfg().tile;
-    if (v < 0 || v >= kNumGatherVariants) v = 0;
-    return (uint32_t)(kGatherVariants[v].nt * kGatherVariants[v].u * 16);
-}
-
-template <int NT, int U, int MINB, int HINT>
-static cudaError_t launch_gather_t(const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head,
-                                   const uint32_t* chain_next, uint32_t nseg, int grid, cudaStream_t s) {
-    k_gather<NT, U, MINB, HINT><<<grid, NT, 0, s>>>(work, tile_begin, chain_head, chain_next, nseg, (uint32_t)(NT * U * 16));
-    return cudaGetLastError();
-}
-template <int NT, int U, int MINB, int HINT>
-static int occ_gather_t() {
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather<NT, U, MINB, HINT>, NT, 0) != cudaSuccess || nb < 1) nb = MINB;
-    return nb;
-}
-#define NZ_GV_SWITCH(v, F, ...)                                   \
-    switch (v) {                                                  \
-    case 1: return F<256, 4, 4, 0>(__VA_ARGS__);                  \
-    case 2: return F<512, 4, 2, 0>(__VA_ARGS__);                  \
-    case 3: return F<512, 8, 1, 0>(__VA_ARGS__);                  \
-    case 4: return F<1024, 4, 1, 0>(__VA_ARGS__);                 \
-    case 5: return F<128, 8, 4, 0>(__VA_ARGS__);                  \
-    case 6: return F<256, 8, 2, 1>(__VA_ARGS__);                  \
-    case 7: return F<256, 8, 2, 2>(__VA_ARGS__);                  \
-    case 8: return F<512, 4, 2, 1>(__VA_ARGS__);                  \
-    case 9: return F<256, 16, 1, 0>(__VA_ARGS__);                 \
-    case 10: return F<256, 8, 2, 3>(__VA_ARGS__);                 \
-    case 11: return F<256, 8, 2, 4>(__VA_ARGS__);                 \
-    case 12: return F<256, 4, 6, 3>(__VA_ARGS__);                 \
-    case 13: return F<512, 8, 1, 3>(__VA_ARGS__);                 \
-    case 15: return F<256, 8, 2, 5>(__VA_ARGS__);                 \
-    default: return F<256, 8, 2, 0>(__VA_ARGS__);                 \
-    }
-
-bool nz_gather_fuses_verify(int variant) { return variant == 14; }
+// Two gather kernels ship: NZ_GATHER_TMA (default; bulk-copy engine staging, register path for byte-phase tiles) and
+// NZ_GATHER_REG (register path only: 256 threads x 8 vectors in flight, 2 CTAs/SM, 32 KiB tiles) as fallback and A/B partner.
+uint32_t nz_gather_tile_bytes(int v) { return v == NZ_GATHER_TMA ? tma_cfg().tile : 256u * 8u * 16u; }
+bool nz_gather_fuses_verify(int variant) { return variant == NZ_GATHER_TMA; }
 cudaError_t nz_launch_gather(int variant, const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head,
                              const uint32_t* chain_next, uint32_t nseg, int grid, cudaStream_t s,
-                             const uint32_t* seg_ver, NzVerWork* ver, const uint32_t* crc_tables, uint32_t pace_ns) {
-    if (variant == 14) return dispatch_tma(TmaArgs{work, tile_begin, chain_head, chain_next, nseg, grid, s, nullptr, seg_ver, ver, crc_tables, pace_ns});
-    NZ_GV_SWITCH(variant, launch_gather_t, work, tile_begin, chain_head, chain_next, nseg, grid, s)
+                             const uint32_t* seg_ver, NzVerWork* ver, const uint32_t* crc_tables, uint32_t pace_ns, uint32_t spread) {
+    if (variant == NZ_GATHER_TMA)
+        return dispatch_tma(TmaArgs{work, tile_begin, chain_head, chain_next, nseg, grid, s, nullptr, seg_ver, ver, crc_tables, pace_ns, spread});
+    k_gather<256, 8, 2><<<grid, 256, 0, s>>>(work, tile_begin, chain_head, chain_next, nseg, 256u * 8u * 16u, spread);
+    return cudaGetLastError();
 }
 int nz_gather_blocks_per_sm(int variant) {
-    if (variant == 14) {
-        int nb = 1;
-        dispatch_tma(TmaArgs{nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, &nb, nullptr, nullptr, nullptr, 0});
+    int nb = 1;
+    if (variant == NZ_GATHER_TMA) {
+        dispatch_tma(TmaArgs{nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, &nb, nullptr, nullptr, nullptr, 0, 0});
         return nb;
     }
-    NZ_GV_SWITCH(variant, occ_gather_t)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather<256, 8, 2>, 256, 0) != cudaSuccess || nb < 1) nb = 2;
+    return nb;
 }
 cudaError_t nz_launch_verify(const NzPlanArgs& a, const uint32_t* crc_tables, int grid, cudaStream_t s) {
     k_verify<<<grid, 256, 0, s>>>(a, crc_tables);

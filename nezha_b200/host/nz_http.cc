@@ -98,23 +98,29 @@ bool iprefix(std::string_view s, std::string_view pre) {
     return true;
 }
 
-// $host: lower-case, no port, no trailing dot (K2)
+// $host (K2): the name ends at the first ':' outside an IPv6 literal, or right after the literal's ']'; upper case
+// is folded; one trailing dot goes; a NUL, a '/' or ".." anywhere in the value (port part included) is a 400
 std::optional<std::string> normal_host(std::string_view h) {
-    size_t end = h.size();
-    if (!h.empty() && h.front() == '[') {
-        const size_t rb = h.find(']');
-        if (rb == std::string_view::npos) return std::nullopt;
-        end = rb + 1;
-    } else if (const size_t colon = h.find(':'); colon != std::string_view::npos) {
-        end = colon;
+    enum { Name, Literal, Rest } st = Name;
+    size_t end = h.size(), last_dot = std::string_view::npos;
+    for (size_t i = 0; i < h.size(); ++i) {
+        switch (h[i]) {
+        case '.':
+            if (last_dot != std::string_view::npos && last_dot + 1 == i) return std::nullopt;
+            last_dot = i;
+            break;
+        case ':': if (st == Name) { end = i; st = Rest; } break;
+        case '[': if (i == 0) st = Literal; break;
+        case ']': if (st == Literal) { end = i + 1; st = Rest; } break;
+        case '\0': case '/': return std::nullopt;
+        default: break;
+        }
     }
-    if (end && h[end - 1] == '.') --end;
+    if (end && last_dot != std::string_view::npos && last_dot + 1 == end) --end;
     if (end == 0 || end > 500) return std::nullopt;
     std::string out(h.substr(0, end));
-    for (char& ch : out) {
-        if (ch == '\0' || ch == '/' || ch == ' ') return std::nullopt;
-        ch = (char)std::tolower((unsigned char)ch);
-    }
+    for (char& ch : out)
+        if (ch >= 'A' && ch <= 'Z') ch = (char)(ch | 0x20);
     return out;
 }
 
@@ -181,7 +187,7 @@ std::optional<std::string> cache_key(const Config& cfg, const std::optional<std:
         host = normal_host(target.substr(hs, he - hs));
         if (!host) return std::nullopt;
         path = (he < target.size() && target[he] == '/') ? target.substr(he) : std::string_view("/");
-    } else if (host_header && !host_header->empty()) {
+    } else if (host_header) {                          // present but empty: invalid (400), not "absent"
         host = normal_host(*host_header);
         if (!host) return std::nullopt;
     }
@@ -373,7 +379,7 @@ int64_t parse_http_date(std::string_view s) {
     if (hh > 23 || mm > 59 || ss > 59) return -1;
     if (day == 29 && mon == 2) {
         if ((year & 3) || (year % 100 == 0 && year % 400 != 0)) return -1;
-    } else if (day > 30 + ((mon ^ (mon >> 3)) & 1) || (mon == 2 && day > 28) || day < 1) {
+    } else if (day > 30 + ((mon ^ (mon >> 3)) & 1) || (mon == 2 && day > 28)) {      // C7: no lower bound on the day (nginx has none)
         return -1;
     }
     return civil_to_days(year, mon, day) * 86400 + hh * 3600 + mm * 60 + ss;
@@ -526,6 +532,49 @@ Admission admission(int status, const std::vector<std::pair<std::string, std::st
     return a;
 }
 
+// G1: does the client take gzip?  The Accept-Encoding test nginx's gunzip filter relies on (ngx_http_gzip_ok):
+// the literal prefix "gzip,", else a case-insensitive "gzip" that starts the value or follows ',' / ' ' and is
+// followed by blanks then ',' / end, or by ";q=" with a value that is not zero.
+namespace {
+bool qvalue_nonzero(std::string_view v) {            // "0" | "1" [ "." up to 3 digits ], ends at ',' / ' ' / end
+    if (v.empty() || (v[0] != '0' && v[0] != '1')) return false;
+    unsigned q = (unsigned)(v[0] - '0') * 100, digits = 0;
+    if (v.size() == 1 || v[1] == ',' || v[1] == ' ') return q != 0;
+    if (v[1] != '.') return false;
+    for (size_t i = 2; i < v.size() && v[i] != ',' && v[i] != ' '; ++i) {
+        if (v[i] < '0' || v[i] > '9') return false;
+        q += (unsigned)(v[i] - '0');
+        ++digits;
+    }
+    return q != 0 && q <= 100 && digits <= 3;
+}
+bool accepts_gzip(std::string_view ae) {
+    if (ae.size() < 4) return false;
+    if (ae.substr(0, 5) == "gzip,") return true;
+    auto is_gzip_at = [&](size_t i) {
+        return i + 4 <= ae.size() && (ae[i] | 0x20) == 'g' && (ae[i + 1] | 0x20) == 'z' && (ae[i + 2] | 0x20) == 'i' && (ae[i + 3] | 0x20) == 'p';
+    };
+    size_t from = 0, at = std::string_view::npos;
+    for (size_t i = 0; i + 4 <= ae.size(); ++i) {
+        if (!is_gzip_at(i)) continue;
+        if (i == from || ae[i - 1] == ',' || ae[i - 1] == ' ') { at = i; break; }
+        from = i + 4;                                 // the search resumes right behind a rejected occurrence
+        i += 3;
+    }
+    if (at == std::string_view::npos) return false;
+    size_t i = at + 4;
+    for (; i < ae.size() && ae[i] == ' '; ++i) {}
+    if (i == ae.size() || ae[i] == ',') return true;
+    if (ae[i] != ';') return false;
+    for (++i; i < ae.size() && ae[i] == ' '; ++i) {}
+    if (i == ae.size()) return true;
+    if (ae[i] != 'q' && ae[i] != 'Q') return false;
+    ++i;
+    if (i + 2 > ae.size() || ae[i] != '=') return false;
+    return qvalue_nonzero(ae.substr(i + 1));
+}
+}  // namespace
+
 Plan plan_response(const Config& cfg, const Request& rq, const ObjectMeta& ob, uint64_t boundary) {
     if (!method_allowed(rq.method)) return stock_page(405, false);
     const bool head = rq.method == "HEAD";
@@ -535,7 +584,7 @@ Plan plan_response(const Config& cfg, const Request& rq, const ObjectMeta& ob, u
         return p;
     }
     // representation (G1/G3 vs B3)
-    const bool client_takes_gzip = rq.accept_encoding && rq.accept_encoding->find("gzip") != std::string::npos;
+    const bool client_takes_gzip = rq.accept_encoding && accepts_gzip(*rq.accept_encoding);
     const bool inflated = ob.stored_gzip && cfg.gunzip && ob.raw_length >= 0 && !client_takes_gzip;
     const int64_t L = inflated ? ob.raw_length : (int64_t)ob.stored_length;
     std::optional<std::string> etag = ob.etag;
@@ -545,7 +594,7 @@ Plan plan_response(const Config& cfg, const Request& rq, const ObjectMeta& ob, u
     // conditionals (C1-C3)
     if (rq.if_unmodified_since) {
         const int64_t t = parse_http_date(*rq.if_unmodified_since);
-        if (lm != -1 && t != -1 && t < lm) return stock_page(412, head);
+        if (lm == -1 || t < lm) return stock_page(412, head);      // C1: also when nothing is stored to compare with, or the date does not parse (-1)
     }
     if (rq.if_match && !etag_in_list(*rq.if_match, etag, false)) return stock_page(412, head);
     if (rq.if_modified_since || rq.if_none_match) {
@@ -566,7 +615,8 @@ Plan plan_response(const Config& cfg, const Request& rq, const ObjectMeta& ob, u
     // Range / If-Range (R1, R2)
     std::vector<ByteRange> rg;
     RangeVerdict verdict = RangeVerdict::Ignore;
-    if (rq.http_minor >= 0 && rq.range && rq.range->size() >= 7 && iprefix(*rq.range, "bytes=")) {
+    // R0: without an Accept-Ranges header on the stored upstream response nginx's range filter stays out of it
+    if (ob.allow_ranges && rq.http_minor >= 0 && rq.range && rq.range->size() >= 7 && iprefix(*rq.range, "bytes=")) {
         bool honour = true;
         if (rq.if_range) {
             const std::string& ir = *rq.if_range;
@@ -591,7 +641,7 @@ Plan plan_response(const Config& cfg, const Request& rq, const ObjectMeta& ob, u
         if (!ob.content_type.empty()) p.headers.emplace_back("Content-Type", ob.content_type);
         p.headers.emplace_back("Content-Length", std::to_string(L));
         validators();
-        p.headers.emplace_back("Accept-Ranges", "bytes");
+        if (ob.allow_ranges) p.headers.emplace_back("Accept-Ranges", "bytes");
         if (say_gzip) p.headers.emplace_back("Content-Encoding", "gzip");
         if (L > 0) p.body.push_back(slice(0, (uint64_t)L));
         return p;
@@ -702,6 +752,7 @@ int nzh_plan_text(const nzh_request* rq, const nzh_object* ob, uint64_t boundary
     o.etag = opt(ob->etag);
     o.last_modified = opt(ob->last_modified);
     o.stored_gzip = ob->content_encoding && strcasecmp(ob->content_encoding, "gzip") == 0;
+    o.allow_ranges = !ob->no_ranges;
     nzh::Config cfg = default_config();
     cfg.gunzip = ob->gunzip_enabled != 0;
     const std::string t = nzh::plan_response(cfg, r, o, boundary).to_text();

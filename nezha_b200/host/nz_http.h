@@ -45,6 +45,7 @@ struct ObjectMeta {
     std::string content_type;
     std::optional<std::string> etag, last_modified;
     bool stored_gzip = false;
+    bool allow_ranges = true;            // R0: the upstream response carried an Accept-Ranges header (no proxy_force_ranges in the conf)
 };
 
 struct Part {
@@ -105,6 +106,7 @@ struct nzh_object {
     int64_t stored_length, raw_length;
     const char *content_type, *etag, *last_modified, *content_encoding;
     int gunzip_enabled;
+    int no_ranges;
 };
 int nzh_plan_text(const nzh_request* rq, const nzh_object* ob, uint64_t boundary, char* out, size_t cap);
 // headers: "Name: value\n" lines in arrival order.  Returns 1 cacheable / 0 not; *valid_until = absolute seconds.

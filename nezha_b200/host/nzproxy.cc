@@ -262,7 +262,7 @@ bool write_fd_all(int fd, const void* p, size_t n) {
 }
 
 // ---- durable tier (PV): <dir>/<md5hex> extent files + <dir>/index.tsv ------------------------
-// index line: md5hex \t stored_len \t raw_len \t crc32c(hex) \t stored_at \t content-type \t etag \t gzip(0/1) \t last-modified [\t valid_until]
+// index line: md5hex \t stored_len \t raw_len \t crc32c(hex) \t stored_at \t content-type \t etag \t gzip(0/1) \t last-modified [\t valid_until [\t ranges(0/1)]]
 std::string tsv(const std::optional<std::string>& s) { return s ? *s : std::string("\x01"); }   // \x01 = absent
 
 void pv_index_append(Server& S, const Entry& e) {
@@ -272,7 +272,7 @@ void pv_index_append(Server& S, const Entry& e) {
     snprintf(num, sizeof num, "\t%llu\t%lld\t%08x\t%lld\t", (unsigned long long)e.meta.stored_length, (long long)e.meta.raw_length, e.crc32c,
              (long long)e.stored_at);
     const std::string line = std::string(hx) + num + e.meta.content_type + "\t" + tsv(e.meta.etag) + "\t" + (e.meta.stored_gzip ? "1" : "0") + "\t" +
-                             tsv(e.meta.last_modified) + "\t" + std::to_string((long long)e.valid_until) + "\n";
+                             tsv(e.meta.last_modified) + "\t" + std::to_string((long long)e.valid_until) + "\t" + (e.meta.allow_ranges ? "1" : "0") + "\n";
     std::lock_guard<std::mutex> g(S.pv_mu);
     int fd = open((S.opt.pv_dir + "/index.tsv").c_str(), O_WRONLY | O_CREAT | O_APPEND, 0644);
     if (fd >= 0) { write_fd_all(fd, line.data(), line.size()); close(fd); }
@@ -312,7 +312,7 @@ void pv_reload(Server& S) {
             if (t == std::string::npos) break;
             pos = t + 1;
         }
-        if ((col.size() != 9 && col.size() != 10) || col[0].size() != 32) continue;
+        if (col.size() < 9 || col.size() > 11 || col[0].size() != 32) continue;
         auto e = std::make_shared<Entry>();
         for (int i = 0; i < 16; ++i) e->key128[i] = (uint8_t)strtoul(col[0].substr(2 * i, 2).c_str(), nullptr, 16);
         e->meta.stored_length = strtoull(col[1].c_str(), nullptr, 10);
@@ -323,7 +323,8 @@ void pv_reload(Server& S) {
         if (col[6] != "\x01") e->meta.etag = col[6];
         e->meta.stored_gzip = col[7] == "1";
         if (col[8] != "\x01") e->meta.last_modified = col[8];
-        e->valid_until = col.size() == 10 ? atoll(col[9].c_str()) : (int64_t)e->stored_at + S.opt.valid_s;
+        e->valid_until = col.size() >= 10 ? atoll(col[9].c_str()) : (int64_t)e->stored_at + S.opt.valid_s;
+        e->meta.allow_ranges = col.size() < 11 || col[10] != "0";
         if ((int64_t)now > e->valid_until) continue;                            // expired: refetch on demand
         Key16 k;
         memcpy(k.b, e->key128, 16);
@@ -523,6 +524,7 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
     nzh::ObjectMeta meta;
     int64_t clen = -1;
     bool storable = true;                          // representable in the store (identity or gzip, known length)
+    bool saw_accept_ranges = false;
     std::vector<std::pair<std::string, std::string>> hv;    // upstream headers in arrival order (admission, relay)
     bool have_crc = false;
     uint32_t want_crc = 0;
@@ -541,6 +543,7 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
         else if (name == "content-type") meta.content_type = val;
         else if (name == "etag") meta.etag = val;
         else if (name == "last-modified") meta.last_modified = val;
+        else if (name == "accept-ranges") saw_accept_ranges = true;      // R0: nginx allows ranges on the cached copy only then
         else if (name == "content-encoding") { if (lower(val) == "gzip") meta.stored_gzip = true; else storable = false; }
         else if (name == "content-md5") { std::vector<uint8_t> m; if (b64_decode(val, m) && m.size() == 16) want_md5 = m; }
         else if (name == "x-goog-hash") {                                         // GCS: crc32c=<base64 of the big-endian u32>[, md5=<base64>]
@@ -666,6 +669,7 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
     }
     meta.stored_length = (uint64_t)clen;
     meta.raw_length = -1;
+    meta.allow_ranges = saw_accept_ranges;
     auto e = std::make_shared<Entry>();
     e->meta = meta;
     memcpy(e->key128, key128, 16);

@@ -19,7 +19,7 @@ class Request(C.Structure):
 class Object(C.Structure):
     _fields_ = [("stored_length", C.c_int64), ("raw_length", C.c_int64), ("content_type", C.c_char_p),
                 ("etag", C.c_char_p), ("last_modified", C.c_char_p), ("content_encoding", C.c_char_p),
-                ("gunzip_enabled", C.c_int)]
+                ("gunzip_enabled", C.c_int), ("no_ranges", C.c_int)]
 
 
 _lib = None
@@ -78,11 +78,11 @@ def md5(data: bytes) -> bytes:
 def plan_text(method="GET", http_minor=1, range=None, if_range=None, if_none_match=None, if_match=None,
               if_modified_since=None, if_unmodified_since=None, accept_encoding=None, *, stored_length=0, raw_length=-1,
               content_type="", etag=None, last_modified=None, content_encoding=None, gunzip_enabled=False,
-              boundary=1) -> str:
+              boundary=1, accept_ranges=True) -> str:
     r = Request(_e(method), http_minor, _e(range), _e(if_range), _e(if_none_match), _e(if_match), _e(if_modified_since),
                 _e(if_unmodified_since), _e(accept_encoding))
     o = Object(stored_length, raw_length, _e(content_type or ""), _e(etag), _e(last_modified), _e(content_encoding),
-               1 if gunzip_enabled else 0)
+               1 if gunzip_enabled else 0, 0 if accept_ranges else 1)
     out = C.create_string_buffer(1 << 16)
     n = load().nzh_plan_text(C.byref(r), C.byref(o), boundary, out, len(out))
     if n < 0:

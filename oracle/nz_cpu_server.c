@@ -19,7 +19,8 @@
  * zlib when they are loaded; requests without `Accept-Encoding: gzip` are served the inflated representation (a member
  * zlib declines stays as stored, SPEC G4).
  *
- * manifest line:  <md5hex> <stored_len> <raw_len|-1> <content-type|-> <etag|-> <encoding|-> <last-modified...|->
+ * manifest line:  <md5hex> <stored_len> <raw_len|-1> <content-type|-> <etag|-> <encoding|->[,noranges] <last-modified...|->
+ *                 (",noranges": the upstream response had no Accept-Ranges header, SPEC R0)
  */
 #define _GNU_SOURCE
 #include <arpa/inet.h>
@@ -49,8 +50,8 @@ typedef struct obj {
     uint8_t key[16];
     int fd;
     int64_t stored_len, raw_len;
-    char ctype[128], etag[128], lm[64], enc[16];
-    int has_etag, has_lm, has_enc;
+    char ctype[128], etag[128], lm[64], enc[32];
+    int has_etag, has_lm, has_enc, no_ranges;
     uint8_t* raw;                    /* --gunzip: inflated representation (NULL = none) */
 } obj;
 
@@ -92,10 +93,10 @@ static int load_manifest(const char* dir) {
     char line[1024];
     int cap = 0;
     while (fgets(line, sizeof line, f)) {
-        char hex[64], ct[128], et[128], en[16], lm[128];
+        char hex[64], ct[128], et[128], en[32], lm[128];
         long long sl, rl;
         lm[0] = 0;
-        int n = sscanf(line, "%63s %lld %lld %127s %127s %15s %127[^\n]", hex, &sl, &rl, ct, et, en, lm);
+        int n = sscanf(line, "%63s %lld %lld %127s %127s %31s %127[^\n]", hex, &sl, &rl, ct, et, en, lm);
         if (n < 6 || strlen(hex) != 32) continue;
         if (g_nobj == cap) { cap = cap ? cap * 2 : 64; g_objs = realloc(g_objs, (size_t)cap * sizeof(obj)); }
         obj* o = &g_objs[g_nobj];
@@ -104,6 +105,7 @@ static int load_manifest(const char* dir) {
         o->stored_len = sl; o->raw_len = rl;
         if (strcmp(ct, "-")) snprintf(o->ctype, sizeof o->ctype, "%s", ct);
         if (strcmp(et, "-")) { snprintf(o->etag, sizeof o->etag, "%s", et); o->has_etag = 1; }
+        { char* nr = strstr(en, ",noranges"); if (nr) { *nr = 0; o->no_ranges = 1; } }
         if (strcmp(en, "-")) { snprintf(o->enc, sizeof o->enc, "%s", en); o->has_enc = 1; }
         if (n == 7 && strcmp(lm, "-")) { snprintf(o->lm, sizeof o->lm, "%s", lm); o->has_lm = 1; }
         snprintf(path, sizeof path, "%s/%s", dir, hex);
@@ -221,7 +223,7 @@ static void build_response(conn* c, char* head) {
         memset(&ob, 0, sizeof ob);
         ob.stored_length = o->stored_len; ob.raw_length = o->raw_len; ob.content_type = o->ctype;
         ob.etag = o->has_etag ? o->etag : NULL; ob.last_modified = o->has_lm ? o->lm : NULL;
-        ob.content_encoding = o->has_enc ? o->enc : NULL; ob.gunzip_enabled = g_gunzip;
+        ob.content_encoding = o->has_enc ? o->enc : NULL; ob.gunzip_enabled = g_gunzip; ob.no_ranges = o->no_ranges;
         plan = malloc(1 << 16);
         if (nzo_plan(&rq, &ob, g_boundary++, plan, 1 << 16) < 0) { simple_page(c, 400, 0); goto done; }
         int status = 0, headonly = 0;

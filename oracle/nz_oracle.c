@@ -234,21 +234,30 @@ static int hexval(int c) {
 
 /* $host: lower-case, strip :port and a trailing dot (SPEC K2) */
 static int norm_host(const char* h, size_t n, char* out, size_t cap) {
-    size_t end = n;
-    if (n && h[0] == '[') { /* IPv6 literal */
-        const char* rb = memchr(h, ']', n);
-        if (!rb) return -400;
-        end = (size_t)(rb - h) + 1;
-    } else {
-        for (size_t i = 0; i < n; i++)
-            if (h[i] == ':') { end = i; break; }
+    /* K2: the name ends at the first ':' outside an IPv6 literal or after its ']'; a NUL, a '/' or two dots in a
+     * row anywhere in the header value (port part included) -> 400; one trailing dot is dropped */
+    size_t end = n, dot = n;
+    int st = 0; /* 0 name, 1 inside [..], 2 after the name */
+    for (size_t i = 0; i < n; i++) {
+        unsigned char c = (unsigned char)h[i];
+        if (c == '.') {
+            if (i > 0 && dot == i - 1) return -400;
+            dot = i;
+        } else if (c == ':') {
+            if (st == 0) { end = i; st = 2; }
+        } else if (c == '[') {
+            if (i == 0) st = 1;
+        } else if (c == ']') {
+            if (st == 1) { end = i + 1; st = 2; }
+        } else if (c == 0 || c == '/') {
+            return -400;
+        }
     }
-    if (end && h[end - 1] == '.') end--;
+    if (end && dot == end - 1) end--;
     if (end == 0 || end + 1 > cap) return -400;
     for (size_t i = 0; i < end; i++) {
         unsigned char c = (unsigned char)h[i];
-        if (c == 0 || c == '/' || c == ' ') return -400;
-        out[i] = (char)tolower(c);
+        out[i] = (c >= 'A' && c <= 'Z') ? (char)(c | 0x20) : (char)c;
     }
     out[end] = 0;
     return (int)end;
@@ -332,7 +341,7 @@ int nzo_cache_key(const char* host_hdr, const char* request_target, const char* 
         if (hl < 0) return -400;
         if (*e == '/') { path = e; plen = strlen(e); }
         else { path = "/"; plen = 1; }
-    } else if (host_hdr && *host_hdr) {
+    } else if (host_hdr) { /* a Host header that is present but empty is invalid (400), not absent */
         hl = norm_host(host_hdr, strlen(host_hdr), host, sizeof host);
         if (hl < 0) return -400;
     } else {
@@ -500,7 +509,7 @@ int64_t nzo_parse_http_time(const char* s, size_t n) {
     if (hh > 23 || mm > 59 || ss > 59) return -1;
     if (day == 29 && mon == 2) {
         if ((year & 3) || ((year % 100 == 0) && (year % 400) != 0)) return -1;
-    } else if (day > 30 + ((mon ^ (mon >> 3)) & 1) || (mon == 2 && day > 28) || day < 1) {
+    } else if (day > 30 + ((mon ^ (mon >> 3)) & 1) || (mon == 2 && day > 28)) { /* C7: no lower bound on the day, like ngx_parse_http_time */
         return -1;
     }
     return days_from_civil(year, (unsigned)mon, (unsigned)day) * 86400 + hh * 3600 + mm * 60 + ss;
@@ -532,8 +541,54 @@ static int etag_list_match(const char* list, const char* etag, int weak) {
     return 0;
 }
 
-static int has_gzip_token(const char* ae) { /* SPEC G1: ngx_http_gunzip "gzip" substring test */
-    return ae && strstr(ae, "gzip") != NULL;
+/* SPEC G1: the Accept-Encoding test of ngx_http_gzip_ok, which the gunzip filter consults */
+static unsigned gzip_qvalue(const char* p, const char* last) {
+    char c = *p++;
+    if (c != '0' && c != '1') return 0;
+    unsigned q = (unsigned)(c - '0') * 100, n = 0;
+    if (p == last) return q;
+    c = *p++;
+    if (c == ',' || c == ' ') return q;
+    if (c != '.') return 0;
+    while (p < last) {
+        c = *p++;
+        if (c == ',' || c == ' ') break;
+        if (c < '0' || c > '9') return 0;
+        q += (unsigned)(c - '0');
+        n++;
+    }
+    return (q > 100 || n > 3) ? 0 : q;
+}
+static int has_gzip_token(const char* ae) {
+    if (!ae) return 0;
+    size_t len = strlen(ae);
+    if (len < 4) return 0;
+    if (len >= 5 && memcmp(ae, "gzip,", 5) == 0) return 1;
+    const char *start = ae, *last = ae + len, *p;
+    for (;;) {
+        p = strcasestr(start, "gzip");
+        if (!p) return 0;
+        if (p == start || p[-1] == ',' || p[-1] == ' ') break;
+        start = p + 4;
+    }
+    p += 4;
+    int stage = 0; /* 0 after the token, 1 after ';' */
+    while (p < last) {
+        char c = *p++;
+        if (stage == 0) {
+            if (c == ',') return 1;
+            if (c == ';') { stage = 1; continue; }
+            if (c == ' ') continue;
+            return 0;
+        }
+        if (c == 'q' || c == 'Q') {
+            if (p + 2 > last || *p++ != '=') return 0;
+            return gzip_qvalue(p, last) != 0;
+        }
+        if (c == ' ') continue;
+        return 0;
+    }
+    return 1;
 }
 
 /* ======================================================================= */
@@ -617,7 +672,7 @@ int nzo_plan(const nzo_request* rq, const nzo_object* ob, uint64_t boundary, cha
     /* C1, C2 -> 412 */
     if (rq->if_unmodified_since) {
         int64_t t = nzo_parse_http_time(rq->if_unmodified_since, strlen(rq->if_unmodified_since));
-        if (lm != -1 && t != -1 && t < lm) {
+        if (lm == -1 || t < lm) { /* C1: no stored date, or an unparseable one (-1), also fails the precondition */
             error_page(&b, 412, head, NULL);
             return b.ovf ? -1 : (int)b.len;
         }
@@ -646,7 +701,9 @@ int nzo_plan(const nzo_request* rq, const nzo_object* ob, uint64_t boundary, cha
     /* R1, R2 */
     nzo_range rg[64];
     int nr = 0, rc = NZO_RANGE_DECLINED;
-    if (rq->http_minor >= 0 && rq->range && strlen(rq->range) >= 7 && strncasecmp(rq->range, "bytes=", 6) == 0) {
+    if (ob->no_ranges) { /* R0: the range filter is not in play at all - full 200 and no Accept-Ranges line */
+        rc = NZO_RANGE_DECLINED;
+    } else if (rq->http_minor >= 0 && rq->range && strlen(rq->range) >= 7 && strncasecmp(rq->range, "bytes=", 6) == 0) {
         int use = 1;
         if (rq->if_range) {
             size_t n = strlen(rq->if_range);
@@ -672,7 +729,7 @@ int nzo_plan(const nzo_request* rq, const nzo_object* ob, uint64_t boundary, cha
         sb_fmt(&b, "hdr Content-Length: %lld\n", (long long)L);
         if (etag) sb_fmt(&b, "hdr ETag: %s\n", etag);
         if (ob->last_modified) sb_fmt(&b, "hdr Last-Modified: %s\n", ob->last_modified);
-        sb_fmt(&b, "hdr Accept-Ranges: bytes\n");
+        if (!ob->no_ranges) sb_fmt(&b, "hdr Accept-Ranges: bytes\n");
         if (gz_stored && !inflated) sb_fmt(&b, "hdr Content-Encoding: gzip\n");
         if (L > 0) sb_fmt(&b, "slice 0 %lld\n", (long long)L);
         sb_put(&b, "end\n", 4);

@@ -78,6 +78,7 @@ typedef struct nzo_object {         /* what the cache entry stores */
     const char* last_modified;      /* NULL if none */
     const char* content_encoding;   /* NULL or "gzip" */
     int         gunzip_enabled;     /* operator switch for SPEC G */
+    int         no_ranges;          /* SPEC R0: the upstream response carried no Accept-Ranges header */
 } nzo_object;
 
 /* Serialises the response plan as text into out (NUL-terminated):

@@ -54,6 +54,7 @@ class _Object(C.Structure):
         ("last_modified", C.c_char_p),
         ("content_encoding", C.c_char_p),
         ("gunzip_enabled", C.c_int),
+        ("no_ranges", C.c_int),
     ]
 
 
@@ -221,6 +222,7 @@ class Obj:
     content_encoding: Optional[str] = None
     raw_length: int = -1
     gunzip_enabled: bool = False
+    accept_ranges: bool = True        # SPEC R0: did the stored upstream response carry an Accept-Ranges header?
 
 
 @dataclass
@@ -244,7 +246,7 @@ def plan(rq: Req, ob: Obj, boundary: int = 1) -> str:
     r = _Request(_e(rq.method), rq.http_minor, _e(rq.range), _e(rq.if_range), _e(rq.if_none_match), _e(rq.if_match),
                  _e(rq.if_modified_since), _e(rq.if_unmodified_since), _e(rq.accept_encoding))
     o = _Object(ob.stored_length, ob.raw_length, _e(ob.content_type or ""), _e(ob.etag), _e(ob.last_modified),
-                _e(ob.content_encoding), 1 if ob.gunzip_enabled else 0)
+                _e(ob.content_encoding), 1 if ob.gunzip_enabled else 0, 0 if ob.accept_ranges else 1)
     out = C.create_string_buffer(1 << 16)
     n = lib().nzo_plan(C.byref(r), C.byref(o), boundary, out, len(out))
     if n < 0:

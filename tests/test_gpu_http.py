@@ -56,7 +56,10 @@ OBJECTS = {
     "/bucket/big.bin": ("storage.googleapis.com", wl.synth_bytes(20 << 20, 3).tobytes(), "application/octet-stream", '"big"', None),
     "/bucket/empty": ("storage.googleapis.com", b"", "application/octet-stream", '"e"', None),
     "/zips/text.json.gz": ("images.cocodataset.org", wl.gzip_member(wl.text_like(500_000, 9)), "application/json", '"gz1"', "gzip"),
+    # an origin that does not say Accept-Ranges: nginx serves the cached copy whole, whatever Range says (SPEC R0)
+    "/bucket/noranges.bin": ("storage.googleapis.com", wl.synth_bytes(300_001, 4).tobytes(), "application/octet-stream", '"nr"', None),
 }
+NO_ACCEPT_RANGES = {"/bucket/noranges.bin"}
 
 
 class Origin(http.server.BaseHTTPRequestHandler):
@@ -79,6 +82,8 @@ class Origin(http.server.BaseHTTPRequestHandler):
         if etag:
             self.send_header("ETag", etag)
         self.send_header("Last-Modified", LM)
+        if path not in NO_ACCEPT_RANGES:
+            self.send_header("Accept-Ranges", "bytes")        # what GCS / S3 / Apache answer; nginx needs it to serve ranges from the cache
         if enc:
             self.send_header("Content-Encoding", enc)
         self.end_headers()
@@ -97,7 +102,7 @@ def servers(tmp_path_factory):
         hx = o.md5(key).hex()
         (d / hx).write_bytes(data)
         raw = len(o.gunzip(data)) if enc else -1
-        lines.append(f"{hx} {len(data)} {raw} {ctype} {etag or '-'} {enc or '-'} {LM}")
+        lines.append(f"{hx} {len(data)} {raw} {ctype} {etag or '-'} {enc or '-'}{',noranges' if path in NO_ACCEPT_RANGES else ''} {LM}")
     (d / "manifest").write_text("\n".join(lines) + "\n")
     origin_port, gpu_port, cpu_port = free_port(), free_port(), free_port()
     httpd = http.server.ThreadingHTTPServer(("127.0.0.1", origin_port), Origin)
@@ -241,6 +246,7 @@ class PolicyOrigin(http.server.BaseHTTPRequestHandler):
         self.send_header("Content-Type", "application/octet-stream")
         self.send_header("Content-Length", str(len(data)))
         self.send_header("ETag", '"%s"' % hashlib.md5(data).hexdigest())
+        self.send_header("Accept-Ranges", "bytes")
         for k, v in extra.items():
             self.send_header(k, v)
         self.end_headers()

@@ -60,60 +60,57 @@ def test_striped_object_single_gpu():
         assert z.lookup([key])[0].status == capi.NZ_ENOTFOUND
 
 
-def _free_port():
-    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
-    return p
-
-
-def _span_worker(rank, world, port, q):
-    import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    torch.cuda.set_device(rank)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    ok = False
-    try:
-        stripe = 4 << 20
-        z = nz.Zone(device=rank, arena_bytes=512 << 20, max_objects=1024, shard_index=rank, shard_count=world)
-        st = span.ShardedStore(z, dist, stripe_bytes=stripe)
-        st.attach_peers()
-        objs = []
-        for i in range(6):
-            key = wl.key128(b"span/two-gpu/%d" % i)
-            length = [3 * stripe + 777, stripe, stripe + 1, 10 * stripe, 1000, 7 * stripe + 3][i]
-            data = wl.synth_bytes(length, seed=900 + i)
-            crc = st.put(key, length, lambda off, ln, d=data: d[off:off + ln])
-            objs.append((key, length, data, crc))
-        dist.barrier()
-        for key, length, data, crc in objs:
-            if shard.shard_of(key, world) != rank:
-                assert z.lookup([key])[0].status == capi.NZ_ENOTFOUND       # GETs are routed to the owner
-                continue
-            assert crc == o.crc32c(data)
-            res, body = z.get(key, device_dst=True)
-            assert res.status == capi.NZ_OK and body == data.tobytes(), length
-            for s, l in [(0, 1), (length - 1, 1), (length // 3, length // 2), (max(0, stripe - 5), min(10, length - max(0, stripe - 5)))]:
-                if l <= 0:
-                    continue
-                res, body = z.get(key, segs=[(s, l)])
-                assert res.status == capi.NZ_OK and body == o.serve_slice_mem(data, s, l), (length, s, l)
-        dist.barrier()
-        z.close()
-        ok = True
-    finally:
-        q.put((rank, ok))
-        dist.destroy_process_group()
+def test_striped_verify_single_gpu():
+    """NZ_GET_VERIFY on a striped object checks every piece against its stripe's own chunk table (fused into the
+    gather for 16 B-aligned slices, k_verify otherwise); a flipped stored byte is NZ_ECORRUPT, never a silent NZ_OK."""
+    stripe = 192 * 1024          # 3 chunks per stripe
+    with nz.Zone(device=0, arena_bytes=256 << 20, max_objects=512) as z:
+        length = 7 * stripe + 4_321
+        d = wl.synth_bytes(length, seed=62)
+        key = wl.key128(b"span/verify")
+        stripes, whole = [], 0
+        for i, off in enumerate(range(0, length, stripe)):
+            ln = min(stripe, length - off)
+            sk = span.stripe_key(key, i)
+            z.put(sk, d[off:off + ln], enc=capi.NZ_ENC_STRIPE)
+            a_off, a_len, tab, crc = z.extent_location(sk)
+            stripes.append((0, a_off, ln, tab))
+            whole = crc if i == 0 else z.crc32c_combine(whole, crc, ln)
+        z.put_striped(key, length, stripe, stripes, whole)
+        st0 = z.stats()
+        cases = [[], [(0, stripe)], [(stripe - 16, 4 * stripe)], [(12_345, 3 * stripe + 17)], [(length - 100, 100)]]
+        for segs in cases:
+            for dev in (True, False):
+                res, body = z.get(key, segs=segs, flags=capi.NZ_GET_VERIFY, device_dst=dev)
+                want = b"".join(o.serve_slice_mem(d, s, l) for s, l in segs) if segs else d.tobytes()
+                assert res.status == capi.NZ_OK and body == want, (segs, dev, res.status)
+        st1 = z.stats()
+        assert st1.verify_chunks - st0.verify_chunks >= 2 * (length // 65536)      # the two whole-object GETs alone
+        assert st1.verify_fused_chunks > st0.verify_fused_chunks
+        # flip one stored byte of stripe 4: every verified GET that touches it fails, the others still pass
+        assert z.debug_poke(span.stripe_key(key, 4), 70_000, 0x10) == capi.NZ_OK
+        res, _ = z.get(key, flags=capi.NZ_GET_VERIFY, device_dst=True)
+        assert res.status == capi.NZ_ECORRUPT
+        res, _ = z.get(key, segs=[(4 * stripe + 65_536, 10_000)], flags=capi.NZ_GET_VERIFY)
+        assert res.status == capi.NZ_ECORRUPT
+        res, body = z.get(key, segs=[(0, 4 * stripe)], flags=capi.NZ_GET_VERIFY, device_dst=True)
+        assert res.status == capi.NZ_OK and body == d[:4 * stripe].tobytes()
+        res, _ = z.get(key, segs=[(4 * stripe, 100)])          # unverified: served as stored
+        assert res.status == capi.NZ_OK
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
 def test_span_gather_two_gpus_ipc():
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
+    """One process per GPU under torchrun (the launch path bench.py uses), NCCL for the handshakes."""
+    import subprocess
+    import sys
     port = _free_port()
-    procs = [ctx.Process(target=_span_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    for p in procs:
-        p.join(300)
-    res = dict(q.get(timeout=10) for _ in range(2))
-    assert res == {0: True, 1: True} and all(p.exitcode == 0 for p in procs)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(os.path.dirname(os.path.abspath(__file__)), "span_worker.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.count("span worker ok") == 2, (r.stdout[-2000:], r.stderr[-4000:])
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
