@@ -701,6 +701,8 @@ def http_bench(L_obj, requests, devices, seed=2, with_c1=False):
         httpd.shutdown()
         # ---- CPU servers ----
         for name, workers, repeat in (("cpu_1worker", 1, 1), ("cpu_allcores", os.cpu_count() or 1, 2)):
+            if os.environ.get("NZ_BENCH_HTTP_GPU_ONLY"):        # tools: front-end sweeps
+                break
             if ngpu > 2 and workers == 1:
                 repeat = 1
             cport = free_port()

@@ -145,6 +145,7 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
     }
 #undef CKI
     c->free_by_off[0] = c->arena_bytes;
+    c->free_by_len.emplace(c->arena_bytes, 0);
     c->free_desc.reserve(c->cfg.max_objects);
     for (uint32_t i = c->cfg.max_objects; i-- > 0;) c->free_desc.push_back(i);
     if (const char* ev = getenv("NZ_GATHER_VARIANT"))      // "0" / "reg": register path only; anything else: the default bulk-copy kernel
@@ -155,6 +156,7 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
     if (const char* ev = getenv("NZ_FUSE_VERIFY")) c->fuse_verify = atoi(ev) != 0;
     if (const char* ev = getenv("NZ_FUSE_SMALL")) c->fuse_small = atoi(ev) != 0;
     c->gather_grid = c->sm_count * nz_gather_blocks_per_sm(c->gather_variant);
+    c->gather_grid3 = c->sm_count * 2;              // three 32 KiB stages: two CTAs fit an SM
     if (const char* ev = getenv("NZ_GATHER_CTAS_PER_SM")) { const int v = atoi(ev); if (v >= 1 && v <= 16) c->gather_grid = c->sm_count * v; }
     c->inflate_grid = c->sm_count * nz_inflate_blocks_per_sm();
     c->inflate_seg_grid = c->sm_count * nz_inflate_seg_blocks_per_sm();
@@ -277,37 +279,44 @@ int32_t nz_buf_write(nz_buf* b, uint64_t off, const void* host_src, uint64_t n) 
 }
 
 // ---------------------------------------------------------------------------
-// arena (first fit, coalescing free list).  Extents are 4 KiB aligned so the
-// same offsets work for cuFile/GDS reads from the PV.
+// arena: free extents indexed twice - by offset (coalescing on free) and by (length, offset) (best fit in
+// O(log n): the smallest extent that holds the request, lowest address among equals) - so a zone with 10^6
+// objects and a churned free list allocates as fast as an empty one.  Extents are 4 KiB aligned so the same
+// offsets work for cuFile/GDS reads from the PV.
 // ---------------------------------------------------------------------------
+static void free_insert(nz_ctx* c, uint64_t off, uint64_t len) { c->free_by_off[off] = len; c->free_by_len.emplace(len, off); }
+static void free_remove(nz_ctx* c, std::map<uint64_t, uint64_t>::iterator it) {
+    c->free_by_len.erase({it->second, it->first});
+    c->free_by_off.erase(it);
+}
 static bool arena_alloc(nz_ctx* c, uint64_t len, uint64_t* off) {
     len = round_up(len ? len : 1, 4096);
-    for (auto it = c->free_by_off.begin(); it != c->free_by_off.end(); ++it) {
-        if (it->second >= len) {
-            *off = it->first;
-            uint64_t rest = it->second - len, o = it->first;
-            c->free_by_off.erase(it);
-            if (rest) c->free_by_off[o + len] = rest;
-            return true;
-        }
-    }
-    return false;
+    auto it = c->free_by_len.lower_bound({len, 0});
+    if (it == c->free_by_len.end()) return false;
+    const uint64_t have = it->first, o = it->second;
+    c->free_by_len.erase(it);
+    c->free_by_off.erase(o);
+    if (have > len) free_insert(c, o + len, have - len);
+    *off = o;
+    return true;
 }
 static void arena_free(nz_ctx* c, uint64_t off, uint64_t len) {
     len = round_up(len ? len : 1, 4096);
-    auto it = c->free_by_off.emplace(off, len).first;
-    auto nx = std::next(it);
-    if (nx != c->free_by_off.end() && it->first + it->second == nx->first) {
-        it->second += nx->second;
-        c->free_by_off.erase(nx);
+    auto nx = c->free_by_off.lower_bound(off);
+    if (nx != c->free_by_off.end() && off + len == nx->first) {          // merge with the extent behind
+        len += nx->second;
+        auto dead = nx++;
+        free_remove(c, dead);
     }
-    if (it != c->free_by_off.begin()) {
-        auto pv = std::prev(it);
-        if (pv->first + pv->second == it->first) {
-            pv->second += it->second;
-            c->free_by_off.erase(it);
+    if (nx != c->free_by_off.begin()) {                                  // ... and with the one in front
+        auto pv = std::prev(nx);
+        if (pv->first + pv->second == off) {
+            off = pv->first;
+            len += pv->second;
+            free_remove(c, pv);
         }
     }
+    free_insert(c, off, len);
 }
 
 // small pinned mailboxes for kernel -> host scalars (status words, CRCs)
@@ -1222,13 +1231,23 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     uint32_t spread = 0;
     if (c->span_spread)
         for (const auto& sp : split) if (!sp.empty()) { spread = c->span_spread; break; }
+    // does the wave name a key twice?  Then request coalescing will very likely chain slices (fan-out tiles: 2 stages);
+    // a wave of distinct keys copies every tile once (3 stages).  The grid follows the stage count's occupancy.
+    int stages_hint = 3;
+    if (c->coalesce && n > 1) {
+        std::unordered_set<uint64_t> seen;
+        seen.reserve(n * 2);
+        for (uint32_t i = 0; i < n; ++i)
+            if (!seen.insert(rd64(reqs[i].key) ^ (rd64(reqs[i].key + 8) * 0x9E3779B97F4A7C15ull)).second) { stages_hint = 2; break; }
+    }
+    if (stages_hint == 3 && !a.fuse_verify && ggrid > c->gather_grid3) ggrid = c->gather_grid3;
     if (fused_small) { /* copied by the plan kernel */ }
-    else if (a.fuse_verify) CKT(nz_launch_gather(variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s, a.seg_ver, a.ver, c->crc_tables, pace_ns, spread));
-    else CKT(nz_launch_gather(variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s, nullptr, nullptr, nullptr, pace_ns, spread));
+    else if (a.fuse_verify) CKT(nz_launch_gather(variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s, a.seg_ver, a.ver, c->crc_tables, pace_ns, spread, stages_hint));
+    else CKT(nz_launch_gather(variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s, nullptr, nullptr, nullptr, pace_ns, spread, stages_hint));
     if (t->profiled) CKT(cudaEventRecord(t->ev_g1, s));
     c->launches += fused_small ? 0 : 1;
     if (any_verify && ver_cap) {
-        int grid = (int)std::min<uint64_t>(ver_cap, (uint64_t)c->sm_count * 8);
+        int grid = (int)std::min<uint64_t>(ver_cap, (uint64_t)c->sm_count * 6);      // k_verify: 6 CTAs of 256 threads fit an SM (36 KiB of tables each)
         CKT(nz_launch_verify(a, c->crc_tables, grid, s));
         c->launches += 1;
     }

@@ -97,22 +97,44 @@ __device__ uint32_t block_crc_chunk(const uint8_t* __restrict__ p, uint32_t m, c
 // merged with the ordinary slice tables (Z_4), the thread's value is moved to the chunk end with one
 // GF(2) multiply by x^(8*(4096-16t-12)) and the CTA XOR-reduces.  The stride table is replicated
 // 8x in shared memory ([entry][copy], copy = lane & 7) so that random indices spread over the banks.
-//   fast tables in global memory (per polynomial): ZS[4*256] | K[256]
+//   fast tables in global memory (per polynomial): ZS[4*256] | K[256] | L[5][4*256] (warp-tree levels)
 // ---------------------------------------------------------------------------
-constexpr int NZ_CRC_FAST_WORDS = 4 * 256 + 256;
+constexpr int NZ_CRC_LVL_OFF = 4 * 256 + 256;            // warp-tree level tables start here (5 x 4 x 256 words)
+constexpr int NZ_CRC_FAST_WORDS = NZ_CRC_LVL_OFF + 5 * 4 * 256;
+static_assert(NZ_CRC_FAST_WORDS == NZ_CRC_FAST_WORDS_DECL, "table block layout (nz_internal.h)");
 
 // Stride table in shared memory, 8 copies, laid out [byte value][byte position k][copy]: word b*32 + k*8 + cp.
 // A lane uses copy cp = lane & 7 and takes the four byte positions of a word in the rotated order k = (j + g) & 3,
 // g = (lane >> 3) & 3 (XOR does not care about the order), so in every one of the four lookups the 32 lanes of a
 // warp hit 32 different banks (bank = k*8 + cp) whatever the data: no bank conflicts.  (The first layout,
 // [k*256 + b][copy], measured 2.3 wavefronts per lookup in the fused-verify gather: ncu, round 1.)
+// One lookup = rotate the byte into bits 7..14 (SHF.R.W), mask and OR in the lane's constant part of the byte offset
+// (LOP3), load (LDS [R + UR]): 3 instructions.  (The first form - shift, x32, mask, + lane offset, x4 + base - was 6
+// and made the kernel issue bound at 3.4 TB/s: ncu, profiles/r02_k_crc_chunks_before.txt.)
 #define NZ_ZS_SETUP(tid)                                                                                   \
     const uint32_t zs_cp = (tid) & 7u, zs_g = ((tid) >> 3) & 3u;                                           \
     const uint32_t zs_k0 = zs_g, zs_k1 = (zs_g + 1u) & 3u, zs_k2 = (zs_g + 2u) & 3u, zs_k3 = (zs_g + 3u) & 3u; \
-    const uint32_t zs_o0 = zs_k0 * 8u + zs_cp, zs_o1 = zs_k1 * 8u + zs_cp, zs_o2 = zs_k2 * 8u + zs_cp, zs_o3 = zs_k3 * 8u + zs_cp; \
-    const uint32_t zs_s0 = zs_k0 * 8u, zs_s1 = zs_k1 * 8u, zs_s2 = zs_k2 * 8u, zs_s3 = zs_k3 * 8u;
-#define NZ_ZS(a) (sZS8[((((a) >> zs_s0) & 0xffu) << 5) + zs_o0] ^ sZS8[((((a) >> zs_s1) & 0xffu) << 5) + zs_o1] ^ \
-                  sZS8[((((a) >> zs_s2) & 0xffu) << 5) + zs_o2] ^ sZS8[((((a) >> zs_s3) & 0xffu) << 5) + zs_o3])
+    const uint32_t zs_r0 = (8u * zs_k0 + 25u) & 31u, zs_r1 = (8u * zs_k1 + 25u) & 31u, zs_r2 = (8u * zs_k2 + 25u) & 31u, zs_r3 = (8u * zs_k3 + 25u) & 31u; \
+    const uint32_t zs_l0 = zs_k0 * 32u + zs_cp * 4u, zs_l1 = zs_k1 * 32u + zs_cp * 4u, zs_l2 = zs_k2 * 32u + zs_cp * 4u, zs_l3 = zs_k3 * 32u + zs_cp * 4u; \
+    const char* const zs_b = reinterpret_cast<const char*>(sZS8);
+#define NZ_ZS1(a, r, l) (*reinterpret_cast<const uint32_t*>(zs_b + ((__funnelshift_r((a), (a), (r)) & 0x7f80u) | (l))))
+#define NZ_ZS(a) (NZ_ZS1(a, zs_r0, zs_l0) ^ NZ_ZS1(a, zs_r1, zs_l1) ^ NZ_ZS1(a, zs_r2, zs_l2) ^ NZ_ZS1(a, zs_r3, zs_l3))
+
+// Sum over the lanes of a warp of v_l * x^(8*16*(31-l)), returned in lane 0: five shuffle levels, each "append
+// 16 * 2^s zero bytes" on the left operand = 4 lookups in that level's table (global memory, L1 resident: 20 loads
+// per thread and chunk against 256 in the row loop).  Replaces one 32-step GF(2) multiply PER THREAD (~160
+// instructions, 0.6 per byte checksummed) by one per WARP.  gL: 5 x [4][256] words.
+__device__ __forceinline__ uint32_t crc_warp_tree(uint32_t v, const uint32_t* __restrict__ gL) {
+    const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const uint32_t u = __shfl_down_sync(0xffffffffu, v, 1u << s);
+        const uint32_t* T = gL + s * 1024;
+        const uint32_t z = __ldg(T + (v & 0xffu)) ^ __ldg(T + 256 + ((v >> 8) & 0xffu)) ^ __ldg(T + 512 + ((v >> 16) & 0xffu)) ^ __ldg(T + 768 + (v >> 24));
+        if ((lane & ((2u << s) - 1u)) == 0) v = z ^ u;
+    }
+    return v;
+}
 
 template <int POLY>
 __device__ uint32_t block_crc_chunk64k(const uint8_t* __restrict__ p, const uint32_t* sZS8, const uint32_t* sT,
@@ -135,11 +157,10 @@ __device__ uint32_t block_crc_chunk64k(const uint8_t* __restrict__ p, const uint
     vv = NZ_Z4(vv) ^ a2;
     vv = NZ_Z4(vv) ^ a3;
 #undef NZ_Z4
-    uint32_t contrib = gf_mul<POLY>(__ldg(gK + tid), vv);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) contrib ^= __shfl_xor_sync(0xffffffffu, contrib, o);
+    // lanes of a warp first (tree), then ONE multiply per warp moves its 512 B to the chunk end: K[t + 31] is lane 31's factor
+    const uint32_t w = crc_warp_tree(vv, gK + (NZ_CRC_LVL_OFF - 1024));
     __syncthreads();
-    if ((tid & 31u) == 0) sred[tid >> 5] = contrib;
+    if ((tid & 31u) == 0) sred[tid >> 5] = gf_mul<POLY>(__ldg(gK + tid + 31), w);
     __syncthreads();
     uint32_t r = 0;
 #pragma unroll
@@ -170,6 +191,11 @@ static inline void nz_crc_fill_fast_tables(uint32_t* out) {
         for (int k = 0; k < 4; ++k)
             for (uint32_t b = 0; b < 256; ++b) T[k * 256 + b] = mul(xs, b << (8 * k));
         for (uint32_t t = 0; t < 256; ++t) T[1024 + t] = xpow8(4096 - 16 * t - 12);
+        for (int lv = 0; lv < 5; ++lv) {                       // warp-tree levels: append 16 << lv zero bytes
+            const uint32_t xl = xpow8(16u << lv);
+            for (int k = 0; k < 4; ++k)
+                for (uint32_t b = 0; b < 256; ++b) T[NZ_CRC_LVL_OFF + lv * 1024 + k * 256 + b] = mul(xl, b << (8 * k));
+        }
     }
 }
 
@@ -199,7 +225,7 @@ __device__ __forceinline__ uint32_t crc_xpow8_small(uint32_t n, const uint32_t* 
 }
 template <int NT>
 __device__ __forceinline__ void crc_piece_partial(const uint8_t* p, uint32_t P, bool ones, const uint32_t* sZS8, const uint32_t* __restrict__ gT,
-                                                  const uint32_t* __restrict__ gF, uint32_t& main, uint32_t& part) {
+                                                  const uint32_t* __restrict__ gF, const uint32_t* __restrict__ gL, uint32_t& main, uint32_t& part) {
     static_assert(NT == 256, "stride table is Z_4096");
     const uint32_t tid = threadIdx.x;
     const uint32_t nvec = P >> 4, R = nvec / NT, rem = nvec % NT;
@@ -221,7 +247,8 @@ __device__ __forceinline__ void crc_piece_partial(const uint8_t* p, uint32_t P, 
         vv = crc_z4g(vv, gT) ^ a2;
         vv = crc_z4g(vv, gT) ^ a3;
         vv = crc_z4g(vv, gT);
-        main = gf_mul<0>(__ldg(gF + (NT - 1 - tid)), vv);      // to the end of the full-row region
+        const uint32_t w = crc_warp_tree(vv, gL);              // R is uniform over the CTA: every lane is here
+        if ((tid & 31u) == 0) main = gf_mul<0>(__ldg(gF + (NT - 32 - tid)), w);      // lane 31's factor: to the end of the full-row region
     }
     part = 0;
     if (tid < rem) {

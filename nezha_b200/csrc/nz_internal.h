@@ -9,7 +9,9 @@
 #include <condition_variable>
 #include <map>
 #include <mutex>
+#include <set>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/nezha_gpu.h"
@@ -165,8 +167,9 @@ static_assert(sizeof(NzDevRes) == sizeof(nz_get_res), "res layout");
 // memory and XORs the piece's contribution (shifted to the chunk end) into `acc`, counting bytes
 // in `got`; k_verify then only compares.  Separate: k_verify reads the chunk itself (chunks a
 // slice covers only partly, slices the bulk-copy engine cannot take).
-// device CRC table block (c->crc_tables): slice tables 16 x 256 | fast-path tables 2 x 1280 | fused-verify powers 288
-constexpr int NZ_CRC_FUSE_OFF = 16 * 256 + 2 * 1280;
+// device CRC table block (c->crc_tables): slice tables 16 x 256 | fast-path tables 2 x 6400 | fused-verify powers 288
+constexpr int NZ_CRC_FAST_WORDS_DECL = 4 * 256 + 256 + 5 * 4 * 256;   // per polynomial: stride table | row factors | warp-tree levels (nz_crc.cuh)
+constexpr int NZ_CRC_FUSE_OFF = 16 * 256 + 2 * NZ_CRC_FAST_WORDS_DECL;
 constexpr int NZ_CRC_FUSE_WORDS = 256 + 32;
 constexpr int NZ_CRC_TABLE_WORDS = NZ_CRC_FUSE_OFF + NZ_CRC_FUSE_WORDS;
 constexpr uint32_t NZ_VER_FUSED = 0x80000000u;   // in seg
@@ -254,6 +257,7 @@ struct nz_ctx {
     int device;
     int sm_count;
     int gather_grid;       // persistent grid size for k_gather
+    int gather_grid3 = 0;  // ... when the bulk-copy kernel runs with three stages (waves without repeated keys)
     bool profile = false;   // record per-kernel CUDA events in every wave (nz_set_profiling / env NZ_PROFILE=1)
     bool fuse_small = true;  // env NZ_FUSE_SMALL=0: small waves launch plan and gather separately
     bool fuse_verify = true; // env NZ_FUSE_VERIFY=0: NZ_GET_VERIFY re-reads every chunk in k_verify (A/B measurements)
@@ -269,7 +273,8 @@ struct nz_ctx {
     NzDesc* descs = nullptr;
     uint32_t* crc_tables = nullptr; // device: 8 x 256 u32 slice tables (Castagnoli), then 8 x 256 (IEEE)
     std::mutex mu;                  // arena + shadow + desc free list
-    std::map<uint64_t, uint64_t> free_by_off;   // arena free list: off -> len
+    std::map<uint64_t, uint64_t> free_by_off;   // arena free list: off -> len (coalescing)
+    std::set<std::pair<uint64_t, uint64_t>> free_by_len;   // the same extents as (len, off): best fit in O(log n)
     std::vector<uint32_t> free_desc;
     std::unordered_map<std::pair<uint64_t, uint64_t>, NzHostObj, KeyHash> shadow;
     uint64_t gen = 1;
@@ -356,7 +361,7 @@ cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s, const NzSmallWav
 cudaError_t nz_launch_gather(int variant, const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head,
                              const uint32_t* chain_next, uint32_t nseg, int grid, cudaStream_t s,
                              const uint32_t* seg_ver = nullptr, NzVerWork* ver = nullptr, const uint32_t* crc_tables = nullptr,
-                             uint32_t pace_ns = 0, uint32_t spread = 0);
+                             uint32_t pace_ns = 0, uint32_t spread = 0, int stages_hint = 0);
 bool nz_gather_fuses_verify(int variant);
 uint32_t nz_gather_tile_bytes(int variant);
 cudaError_t nz_launch_verify(const NzPlanArgs& a, const uint32_t* crc_tables, int grid, cudaStream_t s);

@@ -396,6 +396,10 @@ k_plan(NzPlanArgs a, uint64_t* rq_src, uint64_t* rq_len, uint64_t* rq_tab, uint6
                 a.ver_stat[3] = carry;                 // statistics: index segments / members without an index in this wave
                 a.ver_stat[4] = a.counters[5];
             }
+        } else if (a.infl_seg_begin && tid == 0) {
+            // a wave that carries NZ_GET_INFLATE but names no gzip object: the segment kernel still runs and reads its
+            // total from seg_begin[0] - in a recycled ticket that word is whatever the previous wave left there
+            a.infl_seg_begin[0] = 0;
         }
     }
 
@@ -967,6 +971,7 @@ struct VerifyCtx {
     NzVerWork* ver;
     const uint32_t* gT;      // Castagnoli slice tables
     const uint32_t* gF;      // fused-verify powers (P16 | P2K)
+    const uint32_t* gL;      // warp-tree level tables (Castagnoli)
     const uint32_t* sZS8;    // Z_4096 stride table, 8 copies, shared memory
     uint32_t* sred;          // 16 words
 };
@@ -990,7 +995,7 @@ __device__ __forceinline__ void tile_verify(const VerifyCtx& vc, const uint8_t* 
         const uint32_t P = plen & ~15u, tail = plen & 15u;
         const bool ones = pb == cb;
         uint32_t m, pt;
-        crc_piece_partial<NZ_TMA_VTHREADS>(data + off, P, ones, vc.sZS8, vc.gT, vc.gF, m, pt);
+        crc_piece_partial<NZ_TMA_VTHREADS>(data + off, P, ones, vc.sZS8, vc.gT, vc.gF, vc.gL, m, pt);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             m ^= __shfl_xor_sync(0xffffffffu, m, o);
@@ -1069,7 +1074,7 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
     if constexpr (VERIFY) {
         uint32_t* sz = reinterpret_cast<uint32_t*>(s_buf + (size_t)STAGES * tile_bytes);
         crc_load_fast_tables(sz, crc_tables + 16 * 256);       // Castagnoli Z_4096
-        vc.seg_ver = seg_ver; vc.ver = ver; vc.gT = crc_tables; vc.gF = crc_tables + NZ_CRC_FUSE_OFF; vc.sZS8 = sz; vc.sred = s_red;
+        vc.seg_ver = seg_ver; vc.ver = ver; vc.gT = crc_tables; vc.gF = crc_tables + NZ_CRC_FUSE_OFF; vc.gL = crc_tables + 16 * 256 + NZ_CRC_LVL_OFF; vc.sZS8 = sz; vc.sred = s_red;
     }
     if (tid == 0) {
 #pragma unroll
@@ -1197,11 +1202,11 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-struct TmaCfg { int stages; uint32_t tile; int l2hint; };
+struct TmaCfg { int stages; uint32_t tile; int l2hint; bool stages_forced; };
 static TmaCfg tma_cfg() {
     static TmaCfg c = [] {
-        TmaCfg t{2, 32768, 0};
-        if (const char* e = getenv("NZ_TMA_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 4) t.stages = v; }
+        TmaCfg t{2, 32768, 2, false};      // L2 policy: evict_first stores + evict_last loads (+0.4 % coalesced, +1.3 % uncoalesced: profiles/r02_sweep_tma_l2hint.txt)
+        if (const char* e = getenv("NZ_TMA_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= 4) { t.stages = v; t.stages_forced = true; } }
         if (const char* e = getenv("NZ_TMA_TILE_KB")) { const int v = atoi(e); if (v == 16 || v == 32 || v == 64) t.tile = (uint32_t)v << 10; }
         if (const char* e = getenv("NZ_TMA_L2HINT")) { const int v = atoi(e); if (v >= 0 && v <= 2) t.l2hint = v; }
         while ((size_t)t.stages * t.tile > (200u << 10)) --t.stages;     // stay inside one SM's shared memory
@@ -1214,6 +1219,7 @@ struct TmaArgs {
     uint32_t nseg; int grid; cudaStream_t s; int* occ;
     const uint32_t* seg_ver; NzVerWork* ver; const uint32_t* crc_tables;
     uint32_t pace_ns, spread;
+    int stages_hint;         // 2 or 3 (0 = no opinion): see nz_launch_gather
 };
 template <int STAGES, bool VERIFY>
 static cudaError_t launch_tma(const TmaArgs& a) {
@@ -1247,7 +1253,11 @@ static cudaError_t launch_tma(const TmaArgs& a) {
     return cudaGetLastError();
 }
 static cudaError_t dispatch_tma(const TmaArgs& a) {
-    const TmaCfg t = tma_cfg();
+    TmaCfg t = tma_cfg();
+    // three stages win when every tile is read once and written once (0.98 -> 1.00 of the copy peak), two when tiles fan
+    // out to coalesced followers (a third buffer costs a resident CTA): the host says which kind of wave this is
+    // (the fused-verify instantiation keeps two: its 32 KiB stride table already costs it a resident CTA)
+    if (!t.stages_forced && !a.seg_ver && a.stages_hint >= 2 && a.stages_hint <= 3 && (size_t)a.stages_hint * t.tile <= (200u << 10)) t.stages = a.stages_hint;
     if (a.seg_ver) {                          // fused verify
         switch (t.stages) {
         case 3: return launch_tma<3, true>(a);
@@ -1268,16 +1278,17 @@ uint32_t nz_gather_tile_bytes(int v) { return v == NZ_GATHER_TMA ? tma_cfg().til
 bool nz_gather_fuses_verify(int variant) { return variant == NZ_GATHER_TMA; }
 cudaError_t nz_launch_gather(int variant, const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head,
                              const uint32_t* chain_next, uint32_t nseg, int grid, cudaStream_t s,
-                             const uint32_t* seg_ver, NzVerWork* ver, const uint32_t* crc_tables, uint32_t pace_ns, uint32_t spread) {
+                             const uint32_t* seg_ver, NzVerWork* ver, const uint32_t* crc_tables, uint32_t pace_ns, uint32_t spread,
+                             int stages_hint) {
     if (variant == NZ_GATHER_TMA)
-        return dispatch_tma(TmaArgs{work, tile_begin, chain_head, chain_next, nseg, grid, s, nullptr, seg_ver, ver, crc_tables, pace_ns, spread});
+        return dispatch_tma(TmaArgs{work, tile_begin, chain_head, chain_next, nseg, grid, s, nullptr, seg_ver, ver, crc_tables, pace_ns, spread, stages_hint});
     k_gather<256, 8, 2><<<grid, 256, 0, s>>>(work, tile_begin, chain_head, chain_next, nseg, 256u * 8u * 16u, spread);
     return cudaGetLastError();
 }
 int nz_gather_blocks_per_sm(int variant) {
     int nb = 1;
     if (variant == NZ_GATHER_TMA) {
-        dispatch_tma(TmaArgs{nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, &nb, nullptr, nullptr, nullptr, 0, 0});
+        dispatch_tma(TmaArgs{nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, &nb, nullptr, nullptr, nullptr, 0, 0, 0});
         return nb;
     }
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather<256, 8, 2>, 256, 0) != cudaSuccess || nb < 1) nb = 2;
@@ -1292,7 +1303,11 @@ cudaError_t nz_launch_crc_chunks(const uint8_t* p, uint64_t n, uint32_t* chunk_o
     const uint64_t nchunks = (n + NZ_CRC_CHUNK - 1) / NZ_CRC_CHUNK;
     if (nchunks) {
         uint64_t grid = nchunks;
-        const uint64_t cap = (uint64_t)sm_count * 8;
+        // one full wave of resident CTAs, each striding over its share of the chunks: a grid of 8 per SM with 6 resident
+        // (shared memory) ran a second, one-third-occupied wave that cost about a third of the kernel's time
+        static int per_sm = 0;
+        if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_crc_chunks, 256, 0) != cudaSuccess || per_sm < 1)) per_sm = 4;
+        const uint64_t cap = (uint64_t)sm_count * per_sm;
         if (grid > cap) grid = cap;
         k_crc_chunks<<<(unsigned)grid, 256, 0, s>>>(p, n, chunk_out, crc_tables);
         cudaError_t e = cudaGetLastError();

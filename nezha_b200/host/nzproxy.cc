@@ -10,19 +10,25 @@
 // three proxy_set_header lines of nginx.conf:52-54), admitted only on status 200
 // (proxy_cache_valid 200 1d, nginx.conf:57), then served like a hit.
 //
-// Threading: one thread per connection (cap --max-conns), blocking sockets; the GPU library is
-// thread safe.  TLS upstream for the GCS vhost (nginx.conf:113) with nginx's defaults (no verify, no SNI).  --access-log writes nginx's `main` format (nginx.conf:16-19).
+// Threading: one blocking thread per connection (cap --max-conns) whose windows go through per-GPU combining lanes, or
+// - with --io-threads N - N event-loop workers (epoll), each owning its connections and submitting / polling / sending
+// their windows itself, a miss being lent to a helper thread with blocking sockets.  The GPU library is thread safe.  TLS upstream for the GCS vhost (nginx.conf:113) with nginx's defaults (no verify, no SNI).  --access-log writes nginx's `main` format (nginx.conf:16-19).
 #include <arpa/inet.h>
 #include <errno.h>
 #include <fcntl.h>
 #include <netdb.h>
 #include <netinet/in.h>
 #include <netinet/tcp.h>
+#include <sched.h>
 #include <signal.h>
 #include <openssl/evp.h>
+#include <openssl/hmac.h>
 #include <openssl/ssl.h>
+#include <sys/epoll.h>
+#include <sys/eventfd.h>
 #include <sys/prctl.h>
 #include <sys/socket.h>
+#include <sys/syscall.h>
 #include <sys/time.h>
 #include <unistd.h>
 
@@ -64,8 +70,12 @@ struct Options {
     int host_ctas = 2;                      // CTAs per wave of windows: two saturate the link already
     uint64_t first_window = 16ull << 10;    // small first window keeps time-to-first-byte low (then x8 per window)
     int max_conns = 512;
+    int io_threads = 0;                     // > 0: that many event-loop workers (epoll) own the connections; 0 (default): one blocking thread per
+                                            // connection, which measured better wherever it was tried (profiles/r02_sweep_http_front_end.txt)
     bool gunzip = false;
     bool verify = false;
+    // the conf's private-S3 server block (nginx.conf:138-166, commented out there): bucket, access key, secret
+    std::string s3_bucket, s3_access, s3_secret;
     std::map<std::string, std::string> upstream;   // proxy_host -> ip:port override (tests; nginx resolves via DNS)
     std::string pv_dir;                            // durable tier: write-through on fill, bulk reload at start (README.md:123)
     int inactive_s = 3600;                         // proxy_cache_path ... inactive=60m (nginx.conf:38)
@@ -504,8 +514,28 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
         const size_t s = uri.find('/', uri.find("://") + 3);
         uri = s == std::string::npos ? "/" : uri.substr(s);
     }
-    std::string req = "GET " + uri + " HTTP/1.0\r\nX-Real-IP: " + client_ip + "\r\nHost: " + host + "\r\nX-Forwarded-For: " + client_ip +
-                      "\r\nConnection: close\r\n\r\n";
+    std::string req;
+    if (vh.server_name == "s3.amazonaws.com" && !S.opt.s3_bucket.empty()) {
+        // private S3 (nginx.conf:138-166): AWS signature version 2.  The conf signs
+        //   "$request_method\n\n\n\nx-amz-date:${now}\n/$bucket/$url_full"
+        // with HMAC-SHA1 under the secret key, base64, and sends `Authorization: AWS access:signature`, `x-amz-date`
+        // and `Host: $bucket.s3.amazonaws.com` over HTTP/1.1.  Its $url_full is "$1" of a regex that the block never
+        // has (so the conf as written signs "/bucket/" for every object); here it is the object's path without the
+        // leading slash, which is what S3 verifies.
+        const std::string now = http_date(time(nullptr));
+        const std::string path = uri.substr(0, uri.find('?'));
+        const std::string to_sign = "GET\n\n\n\nx-amz-date:" + now + "\n/" + S.opt.s3_bucket + path;
+        unsigned char mac[EVP_MAX_MD_SIZE];
+        unsigned int mac_len = 0;
+        HMAC(EVP_sha1(), S.opt.s3_secret.data(), (int)S.opt.s3_secret.size(), (const unsigned char*)to_sign.data(), to_sign.size(), mac, &mac_len);
+        char b64[64];
+        EVP_EncodeBlock((unsigned char*)b64, mac, (int)mac_len);
+        req = "GET " + uri + " HTTP/1.1\r\nHost: " + S.opt.s3_bucket + ".s3.amazonaws.com\r\nx-amz-date: " + now + "\r\nAuthorization: AWS " + S.opt.s3_access + ":" +
+              b64 + "\r\nConnection: close\r\n\r\n";
+    } else {
+        req = "GET " + uri + " HTTP/1.0\r\nX-Real-IP: " + client_ip + "\r\nHost: " + host + "\r\nX-Forwarded-For: " + client_ip +
+              "\r\nConnection: close\r\n\r\n";
+    }
     if (!up.write_all_(req.data(), req.size())) { up.close_(); return 502; }
     std::string head;
     std::vector<char> buf(1 << 16);
@@ -716,6 +746,9 @@ struct LaneTrace {
 static LaneTrace g_tr[2];                  // 0 = urgent, 1 = bulk
 static std::atomic<uint64_t> g_first_ns{0}, g_first_n{0};   // request parsed -> first body window written to the socket
 
+static std::atomic<int> g_spinners{0};
+static int g_spin_cap = 4;                   // set in main from the CPUs this process may actually use
+
 struct Combiner {
     nz_ctx* ctx = nullptr;                         // shard 0 (also owns the pinned windows)
     std::vector<nz_ctx*> ctxs;                      // one per GPU; shard = u64le(key128[0:8]) mod nGPU
@@ -736,12 +769,16 @@ struct Combiner {
         cv.notify_one();
     }
     static void wait(WaveItem* it) {
-        // a window is ready in tens of microseconds: poll briefly before paying a futex sleep + wake-up
-        const auto t0 = std::chrono::steady_clock::now();
-        while (!it->done.load(std::memory_order_acquire)) {
-            __builtin_ia32_pause();
-            if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(150)) break;
+        // a window is ready in tens of microseconds: poll briefly before paying a futex sleep + wake-up - but only as many
+        // threads at a time as the box can spare (g_spin_cap: an eighth of the CPUs the cgroup grants); the rest block
+        if (g_spinners.fetch_add(1, std::memory_order_relaxed) < g_spin_cap) {
+            const auto t0 = std::chrono::steady_clock::now();
+            while (!it->done.load(std::memory_order_acquire)) {
+                __builtin_ia32_pause();
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(150)) break;
+            }
         }
+        g_spinners.fetch_sub(1, std::memory_order_relaxed);
         while (!it->done.load(std::memory_order_acquire)) it->done.wait(0, std::memory_order_acquire);
     }
     void run() {
@@ -908,27 +945,130 @@ void access_log_line(Server& S, const std::string& client_ip, const Parsed& pr, 
     write_fd_all(S.log_fd, line.data(), line.size());
 }
 
-void serve_connection(Server* Sp, int fd, std::string client_ip) {
-    Server& S = *Sp;
+// One request whose head is already in hand, served with blocking sockets: the miss path (origin fetch, uncached
+// relay) and the legacy thread-per-connection mode (--io-threads 0).  Returns whether the connection stays open.
+bool serve_one(Server& S, int fd, const std::string& client_ip, const std::string& head, nz_buf* win[2]) {
+    const int64_t t_req = g_trace ? now_ns() : 0;
+    Parsed pr = parse_head(head);
+    nzh::Plan plan;
+    std::shared_ptr<Entry> ent;
+    bool keep = pr.keep_alive;
+    auto stock = [&](int code) { plan = nzh::error_page(code, pr.ok && pr.rq.method == "HEAD"); };
+    if (!pr.ok) {
+        stock(400);
+        keep = false;
+    } else if (!nzh::method_allowed(pr.rq.method) || (pr.rq.method != "GET" && pr.rq.method != "HEAD")) {
+        stock(405);
+    } else {
+        int vhost = 0;
+        auto key = nzh::cache_key(S.cfg, pr.rq.host, pr.rq.target, &vhost);
+        if (!key) {
+            stock(400);
+            keep = false;
+        } else {
+            Key16 k;
+            nzh::md5(key->data(), key->size(), k.b);
+            // lookup and reference in one critical section: the cache manager only drops entries it sees unreferenced
+            // under the same lock, so a response never streams an object that is being evicted (or its successor)
+            auto lookup_ref = [&]() {
+                std::lock_guard<std::mutex> g(S.mu);
+                auto it = S.index.find(k);
+                if (it == S.index.end()) return;
+                if ((int64_t)time(nullptr) > it->second->valid_until) return;      // SPEC H2: expired -> MISS (refetched below)
+                ent = it->second;
+                ent->inflight++;
+            };
+            lookup_ref();
+            int st = 200;
+            if (!ent) {
+                S.misses++;
+                {   // one fill per key: later misses of the same key wait for the first and then find the entry
+                    std::unique_lock<std::mutex> g(S.fill_mu);
+                    S.fill_cv.wait(g, [&] { return S.filling.count(k) == 0; });
+                    S.filling[k] = 1;
+                }
+                lookup_ref();                                                       // filled by a concurrent request while we waited
+                if (!ent) {
+                    {   // an expired (or otherwise stale) entry of this key goes first; if a response still streams it, serve as uncached miss
+                        std::shared_ptr<Entry> old;
+                        { std::lock_guard<std::mutex> g(S.mu); auto it = S.index.find(k); if (it != S.index.end()) old = it->second; }
+                        if (old && !drop_entry(S, old)) st = 504;
+                    }
+                    if (st == 200) {
+                        // $host for the upstream Host header = request host (proxy_set_header Host $host)
+                        std::string host = key->substr(0, key->find('/'));
+                        std::shared_ptr<Entry> fresh;
+                        st = fill_from_origin(S, vhost, host, pr.rq.target, client_ip, k.b, fresh, fd, pr.rq.method == "HEAD");
+                        if (st == 200) lookup_ref();
+                    }
+                }
+                {
+                    std::lock_guard<std::mutex> g(S.fill_mu);
+                    S.filling.erase(k);
+                }
+                S.fill_cv.notify_all();
+            } else {
+                S.hits++;
+            }
+            if (st == -1) {                       // relayed uncached: the response is on the wire already
+                access_log_line(S, client_ip, pr, 200, 0);
+                return false;
+            }
+            if (!ent) {
+                stock(st == 200 ? 502 : st);
+            } else {
+                ent->last_access = now_ms();
+                nzh::Config cfg = S.cfg;
+                cfg.gunzip = S.opt.gunzip;
+                plan = nzh::plan_response(cfg, pr.rq, ent->meta, S.boundary.fetch_add(1));
+            }
+        }
+    }
+    // a request that carries a body is answered and the connection closed: the body is never read (nginx would
+    // discard it; parsing it as the next request must not happen)
+    if (pr.ok && pr.has_body) keep = false;
+    if (pr.ok && pr.rq.http_minor < 1) keep = false;
+    const bool sent = send_plan(S, fd, plan, ent.get(), keep, win, t_req);
+    access_log_line(S, client_ip, pr, plan.status, plan.head ? 0 : plan.body_length());
+    if (ent) ent->inflight--;
+    return sent && keep;
+}
+
+void tune_socket(int fd) {
     int one = 1;
     setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
     int sndbuf = 4 << 20;
     setsockopt(fd, SOL_SOCKET, SO_SNDBUF, &sndbuf, sizeof sndbuf);
-    {   // nginx defaults: client_header_timeout 60s / keepalive_timeout 65s (one receive timeout covers both here), send_timeout 60s
-        struct timeval rtv = {65, 0}, stv = {60, 0};
-        setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &rtv, sizeof rtv);
-        setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &stv, sizeof stv);
-    }
-    nz_buf* win[2] = {nullptr, nullptr};
+    // nginx defaults: client_header_timeout 60s / keepalive_timeout 65s (one receive timeout covers both here), send_timeout 60s
+    struct timeval rtv = {65, 0}, stv = {60, 0};
+    setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &rtv, sizeof rtv);
+    setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &stv, sizeof stv);
+}
+
+bool take_windows(Server& S, nz_buf* win[2]) {
+    win[0] = win[1] = nullptr;
     {
         std::lock_guard<std::mutex> g(S.win_mu);
         for (int i = 0; i < 2 && !S.free_windows.empty(); ++i) { win[i] = S.free_windows.back(); S.free_windows.pop_back(); }
     }
     for (int i = 0; i < 2; ++i)
         if (!win[i] && nz_buf_alloc(S.ctx, S.opt.window_bytes, NZ_BUF_PINNED_HOST, &win[i]) != NZ_OK) win[i] = nullptr;
+    return win[0] && win[1];
+}
+void give_windows(Server& S, nz_buf* win[2]) {
+    std::lock_guard<std::mutex> g(S.win_mu);
+    for (int i = 0; i < 2; ++i) if (win[i]) S.free_windows.push_back(win[i]);
+    win[0] = win[1] = nullptr;
+}
+
+// legacy mode (--io-threads 0): one thread per connection, blocking sockets
+void serve_connection(Server* Sp, int fd, std::string client_ip) {
+    Server& S = *Sp;
+    tune_socket(fd);
+    nz_buf* win[2];
+    bool alive = take_windows(S, win);
     std::string inbuf;
     std::vector<char> tmp(16384);
-    bool alive = win[0] && win[1];
     while (alive) {
         size_t end;
         while ((end = inbuf.find("\r\n\r\n")) == std::string::npos) {
@@ -940,105 +1080,466 @@ void serve_connection(Server* Sp, int fd, std::string client_ip) {
         if (!alive) break;
         const std::string head = inbuf.substr(0, end + 2);
         inbuf.erase(0, end + 4);
-        const int64_t t_req = g_trace ? now_ns() : 0;
-        Parsed pr = parse_head(head);
-        nzh::Plan plan;
-        std::shared_ptr<Entry> ent;
-        bool keep = pr.keep_alive;
-        auto stock = [&](int code) { plan = nzh::error_page(code, pr.ok && pr.rq.method == "HEAD"); };
-        if (!pr.ok) {
-            stock(400);
-            keep = false;
-        } else if (!nzh::method_allowed(pr.rq.method) || (pr.rq.method != "GET" && pr.rq.method != "HEAD")) {
-            stock(405);
-        } else {
-            int vhost = 0;
-            auto key = nzh::cache_key(S.cfg, pr.rq.host, pr.rq.target, &vhost);
-            if (!key) {
-                stock(400);
-                keep = false;
-            } else {
-                Key16 k;
-                nzh::md5(key->data(), key->size(), k.b);
-                // lookup and reference in one critical section: the cache manager only drops entries it sees unreferenced
-                // under the same lock, so a response never streams an object that is being evicted (or its successor)
-                auto lookup_ref = [&]() {
-                    std::lock_guard<std::mutex> g(S.mu);
-                    auto it = S.index.find(k);
-                    if (it == S.index.end()) return;
-                    if ((int64_t)time(nullptr) > it->second->valid_until) return;      // SPEC H2: expired -> MISS (refetched below)
-                    ent = it->second;
-                    ent->inflight++;
-                };
-                lookup_ref();
-                int st = 200;
-                if (!ent) {
-                    S.misses++;
-                    {   // one fill per key: later misses of the same key wait for the first and then find the entry
-                        std::unique_lock<std::mutex> g(S.fill_mu);
-                        S.fill_cv.wait(g, [&] { return S.filling.count(k) == 0; });
-                        S.filling[k] = 1;
-                    }
-                    lookup_ref();                                                       // filled by a concurrent request while we waited
-                    if (!ent) {
-                        {   // an expired (or otherwise stale) entry of this key goes first; if a response still streams it, serve as uncached miss
-                            std::shared_ptr<Entry> old;
-                            { std::lock_guard<std::mutex> g(S.mu); auto it = S.index.find(k); if (it != S.index.end()) old = it->second; }
-                            if (old && !drop_entry(S, old)) st = 504;
-                        }
-                        if (st == 200) {
-                            // $host for the upstream Host header = request host (proxy_set_header Host $host)
-                            std::string host = key->substr(0, key->find('/'));
-                            std::shared_ptr<Entry> fresh;
-                            st = fill_from_origin(S, vhost, host, pr.rq.target, client_ip, k.b, fresh, fd, pr.rq.method == "HEAD");
-                            if (st == 200) lookup_ref();
-                        }
-                    }
-                    {
-                        std::lock_guard<std::mutex> g(S.fill_mu);
-                        S.filling.erase(k);
-                    }
-                    S.fill_cv.notify_all();
-                } else {
-                    S.hits++;
-                }
-                if (st == -1) {                       // relayed uncached: the response is on the wire already
-                    access_log_line(S, client_ip, pr, 200, 0);
-                    break;
-                }
-                if (!ent) {
-                    stock(st == 200 ? 502 : st);
-                } else {
-                    ent->last_access = now_ms();
-                    nzh::Config cfg = S.cfg;
-                    cfg.gunzip = S.opt.gunzip;
-                    plan = nzh::plan_response(cfg, pr.rq, ent->meta, S.boundary.fetch_add(1));
-                }
-            }
-        }
-        // a request that carries a body is answered and the connection closed: the body is never read (nginx would
-        // discard it; parsing it as the next request must not happen)
-        if (pr.ok && pr.has_body) keep = false;
-        if (pr.ok && pr.rq.http_minor < 1) keep = false;
-        const bool sent = send_plan(S, fd, plan, ent.get(), keep, win, t_req);
-        access_log_line(S, client_ip, pr, plan.status, plan.head ? 0 : plan.body_length());
-        if (ent) ent->inflight--;
-        if (!sent) break;
-        if (!keep) break;
+        if (!serve_one(S, fd, client_ip, head, win)) break;
     }
-    {
-        std::lock_guard<std::mutex> g(S.win_mu);
-        for (int i = 0; i < 2; ++i) if (win[i]) S.free_windows.push_back(win[i]);
-    }
+    give_windows(S, win);
     shutdown(fd, SHUT_RDWR);
     close(fd);
     S.conns--;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Event-driven front end (--io-threads N): N workers, each an epoll loop that OWNS its connections.
+// Replaces thread-per-connection + dispatcher lanes on the hit path (nginx's own model is an event loop per worker,
+// nginx.conf:2,8-10).  The thread that parsed a request is the thread that submits its windows to the GPU (one
+// wave per loop turn and shard: every window its connections asked for in that turn = the combining submitter), polls
+// their completion and writes them to the socket: no queue hop and no wake-up between "window ready" and send().
+// While windows are in flight the loop polls (epoll_wait timeout 0); idle it blocks.  A MISS is the rare, slow case:
+// the connection is lent to a helper thread that serves that one request with blocking sockets (serve_one), then
+// comes back.  MSG_ZEROCOPY is not used: on loopback the kernel copies at delivery anyway, and the windows are
+// reused as soon as send() returns, which zerocopy's completion notifications would only delay.
+// ---------------------------------------------------------------------------------------------------------
+struct Worker;
+struct EvConn {
+    int fd = -1;
+    Worker* w = nullptr;
+    std::string ip, in;
+    nz_buf* win[2] = {nullptr, nullptr};
+    enum WinState { FREE, INFLIGHT, READY, FAILED };
+    struct Win { WinState st = FREE; uint64_t len = 0, sent = 0; bool urgent = false; } ws[2];
+    // the response being sent
+    bool busy = false, keep = true, dead = false, want_out = false, lent = false, queued_more = false;
+    Parsed pr;
+    nzh::Plan plan;
+    std::shared_ptr<Entry> ent;
+    size_t part = 0;                      // next plan.body part to schedule
+    uint64_t part_off = 0;                // bytes of that slice already scheduled
+    uint64_t ramp = 0;
+    bool first = true;
+    uint32_t flags = 0;
+    struct Item { bool window; int slot; std::string bytes; size_t off; };
+    std::deque<Item> q;                   // what goes to the socket, in order
+    int inflight = 0;                     // windows the GPU may still be writing
+    int64_t t_req = 0, last_active = 0;
+    uint64_t body_sent = 0;
+};
+
+struct WinReq { EvConn* c; int slot; nz_get_req rq; nz_seg sg; };
+struct OutTicket { nz_ticket* t; std::vector<std::pair<EvConn*, int>> items; bool urgent; int64_t t_sub; };
+
+struct Worker {
+    Server* S = nullptr;
+    int ep = -1, evfd = -1;
+    std::mutex mu;
+    std::vector<EvConn*> inbox;                     // new connections and connections coming back from a miss helper
+    std::vector<std::vector<WinReq>> pend_urgent, pend_bulk;     // per shard, this loop turn
+    std::vector<OutTicket> out;
+    std::vector<EvConn*> conns;
+    std::deque<EvConn*> more;                       // connections that stopped sending only to let others have a turn
+    std::vector<EvConn*> dying;                     // killed this turn or earlier; deleted at the end of a turn once the GPU is done with their windows
+    std::vector<nz_get_req> reqs_scratch;
+    std::vector<nz_get_res> res_scratch;
+    void post(EvConn* c) {
+        { std::lock_guard<std::mutex> g(mu); inbox.push_back(c); }
+        uint64_t one = 1;
+        if (write(evfd, &one, 8) < 0) {}
+    }
+    void run();
+    void on_readable(EvConn* c);
+    void try_start(EvConn* c);
+    void start_response(EvConn* c);
+    void schedule(EvConn* c);
+    void pump(EvConn* c);
+    void finish(EvConn* c);
+    void kill(EvConn* c);
+    void reap(EvConn* c);
+    void submit_pending();
+    void poll_tickets();
+    void lend_to_helper(EvConn* c, const std::string& head);
+    void arm(EvConn* c, bool out);
+};
+
+void Worker::arm(EvConn* c, bool out) {
+    if (c->want_out == out) return;
+    c->want_out = out;
+    struct epoll_event ev;
+    memset(&ev, 0, sizeof ev);
+    ev.events = EPOLLIN | EPOLLRDHUP;
+    if (out) ev.events |= EPOLLOUT;
+    ev.data.ptr = c;
+    epoll_ctl(ep, EPOLL_CTL_MOD, c->fd, &ev);
+}
+
+void Worker::kill(EvConn* c) {            // stop serving; the object itself goes away at the end of a loop turn (never under a caller's feet),
+    if (c->dead) return;                  // and only once the GPU is done with its windows
+    c->dead = true;
+    epoll_ctl(ep, EPOLL_CTL_DEL, c->fd, nullptr);
+    shutdown(c->fd, SHUT_RDWR);
+    dying.push_back(c);
+}
+void Worker::reap(EvConn* c) {
+    Server& Sv = *S;
+    if (c->ent) { c->ent->inflight--; c->ent.reset(); }
+    give_windows(Sv, c->win);
+    close(c->fd);
+    Sv.conns--;
+    conns.erase(std::remove(conns.begin(), conns.end(), c), conns.end());
+    delete c;
+}
+
+void Worker::lend_to_helper(EvConn* c, const std::string& head) {
+    // miss path: blocking sockets in a helper thread for this one request (origin fetch, fill, uncached relay), then back
+    epoll_ctl(ep, EPOLL_CTL_DEL, c->fd, nullptr);
+    c->lent = true;
+    conns.erase(std::remove(conns.begin(), conns.end(), c), conns.end());
+    Server* Sp = S;
+    Worker* self = this;
+    std::thread([Sp, self, c, head] {
+        const int fl = fcntl(c->fd, F_GETFL, 0);
+        fcntl(c->fd, F_SETFL, fl & ~O_NONBLOCK);
+        const bool open_ = serve_one(*Sp, c->fd, c->ip, head, c->win);
+        if (!open_) {
+            give_windows(*Sp, c->win);
+            shutdown(c->fd, SHUT_RDWR);
+            close(c->fd);
+            Sp->conns--;
+            delete c;
+            return;
+        }
+        fcntl(c->fd, F_SETFL, fl | O_NONBLOCK);
+        c->lent = false;
+        self->post(c);
+    }).detach();
+}
+
+void Worker::try_start(EvConn* c) {
+    Server& Sv = *S;
+    while (!c->busy && !c->dead) {
+        const size_t end = c->in.find("\r\n\r\n");
+        if (end == std::string::npos) {
+            if (c->in.size() > 32768) kill(c);
+            return;
+        }
+        const std::string head = c->in.substr(0, end + 2);
+        c->in.erase(0, end + 4);
+        c->t_req = g_trace ? now_ns() : 0;
+        c->pr = parse_head(head);
+        Parsed& pr = c->pr;
+        c->keep = pr.keep_alive;
+        c->ent.reset();
+        auto stock = [&](int code) { c->plan = nzh::error_page(code, pr.ok && pr.rq.method == "HEAD"); };
+        if (!pr.ok) {
+            stock(400);
+            c->keep = false;
+        } else if (!nzh::method_allowed(pr.rq.method) || (pr.rq.method != "GET" && pr.rq.method != "HEAD")) {
+            stock(405);
+        } else {
+            int vhost = 0;
+            auto key = nzh::cache_key(Sv.cfg, pr.rq.host, pr.rq.target, &vhost);
+            if (!key) {
+                stock(400);
+                c->keep = false;
+            } else {
+                Key16 k;
+                nzh::md5(key->data(), key->size(), k.b);
+                {
+                    std::lock_guard<std::mutex> g(Sv.mu);
+                    auto it = Sv.index.find(k);
+                    if (it != Sv.index.end() && (int64_t)time(nullptr) <= it->second->valid_until) {
+                        c->ent = it->second;
+                        c->ent->inflight++;
+                    }
+                }
+                if (!c->ent) {                    // MISS (or expired): the blocking path owns this request
+                    lend_to_helper(c, head);
+                    return;
+                }
+                Sv.hits++;
+                c->ent->last_access = now_ms();
+                nzh::Config cfg = Sv.cfg;
+                cfg.gunzip = Sv.opt.gunzip;
+                c->plan = nzh::plan_response(cfg, pr.rq, c->ent->meta, Sv.boundary.fetch_add(1));
+            }
+        }
+        if (pr.ok && pr.has_body) c->keep = false;
+        if (pr.ok && pr.rq.http_minor < 1) c->keep = false;
+        start_response(c);
+    }
+}
+
+void Worker::start_response(EvConn* c) {
+    Server& Sv = *S;
+    const nzh::Plan& plan = c->plan;
+    std::string h = std::string("HTTP/1.1 ") + std::to_string(plan.status) + " " + status_text(plan.status) + "\r\nServer: nginx\r\nDate: " +
+                    http_date(time(nullptr)) + "\r\n";
+    for (const auto& kv : plan.headers) h += kv.first + ": " + kv.second + "\r\n";
+    h += c->keep ? "Connection: keep-alive\r\n" : "Connection: close\r\n";
+    h += "\r\n";
+    c->busy = true;
+    c->part = 0; c->part_off = 0; c->ramp = Sv.opt.first_window; c->first = true; c->body_sent = 0;
+    c->flags = (plan.inflated ? NZ_GET_INFLATE : 0) | (Sv.opt.verify ? NZ_GET_VERIFY : 0);
+    c->q.clear();
+    c->q.push_back(EvConn::Item{false, 0, std::move(h), 0});
+    if (plan.head) c->part = plan.body.size();          // HEAD: headers only
+    schedule(c);
+    pump(c);
+}
+
+// walk the plan: literals join the send queue as they come, slices are cut into windows while a window is free
+void Worker::schedule(EvConn* c) {
+    Server& Sv = *S;
+    const nzh::Plan& plan = c->plan;
+    while (c->part < plan.body.size()) {
+        const nzh::Part& p = plan.body[c->part];
+        if (p.literal) {
+            if (!c->q.empty() && !c->q.back().window) c->q.back().bytes += p.bytes;
+            else c->q.push_back(EvConn::Item{false, 0, p.bytes, 0});
+            c->part++;
+            continue;
+        }
+        if (c->part_off >= p.len) { c->part++; c->part_off = 0; continue; }
+        int slot = -1;
+        for (int i = 0; i < 2; ++i) if (c->ws[i].st == EvConn::FREE) { slot = i; break; }
+        if (slot < 0) return;
+        const uint64_t left = p.len - c->part_off;
+        const uint64_t n = std::min<uint64_t>(left, std::min<uint64_t>(c->ramp, Sv.opt.window_bytes));
+        c->ramp = std::min<uint64_t>(c->ramp * 8, Sv.opt.window_bytes);
+        WinReq r;
+        r.c = c; r.slot = slot;
+        memset(&r.rq, 0, sizeof r.rq);
+        memcpy(r.rq.key, c->ent->key128, 16);
+        r.rq.flags = c->flags | (c->first ? NZ_GET_URGENT : 0u);
+        r.sg = nz_seg{p.off + c->part_off, n, 0};
+        r.rq.nseg = 1; r.rq.dst = c->win[slot];
+        const uint32_t sh = nz_shard_of(c->ent->key128, (uint32_t)Sv.ctxs.size());
+        (c->first ? pend_urgent : pend_bulk)[sh].push_back(r);
+        c->ws[slot].st = EvConn::INFLIGHT; c->ws[slot].len = n; c->ws[slot].sent = 0; c->ws[slot].urgent = c->first;
+        c->inflight++;
+        c->q.push_back(EvConn::Item{true, slot, std::string(), 0});
+        c->first = false;
+        c->part_off += n;
+    }
+}
+
+void Worker::pump(EvConn* c) {
+    Server& Sv = *S;
+    size_t budget = 512u << 10;                                         // bytes this call may hand to the socket
+    while (!c->dead && !c->q.empty()) {
+        EvConn::Item& it = c->q.front();
+        const char* p;
+        size_t n;
+        if (!it.window) {
+            // the status line and headers leave at once (like a proxy forwarding upstream headers as they arrive) unless
+            // --early-header 0 asked for them to share a segment with the first body bytes
+            if (!Sv.opt.early_header && c->q.size() > 1 && c->q[1].window && c->ws[c->q[1].slot].st == EvConn::INFLIGHT && it.off == 0) return;
+            p = it.bytes.data() + it.off; n = it.bytes.size() - it.off;
+        } else {
+            EvConn::Win& w = c->ws[it.slot];
+            if (w.st == EvConn::INFLIGHT) return;                       // the GPU is still filling it
+            if (w.st == EvConn::FAILED) { kill(c); return; }             // mid-body failure: drop the connection
+            p = (const char*)nz_buf_ptr(c->win[it.slot]) + w.sent; n = (size_t)(w.len - w.sent);
+        }
+        if (budget == 0) {                                              // fairness: a 4 MiB window is ~1 ms of copying; others wait their turn no longer than a slice
+            if (!c->queued_more) { c->queued_more = true; more.push_back(c); }
+            return;
+        }
+        if (n > budget) n = budget;
+        budget -= n;
+        while (n) {
+            const ssize_t k = ::send(c->fd, p, n, MSG_NOSIGNAL | MSG_DONTWAIT);
+            if (k < 0) {
+                if (errno == EINTR) continue;
+                if (errno == EAGAIN || errno == EWOULDBLOCK) { arm(c, true); return; }
+                kill(c);
+                return;
+            }
+            p += k; n -= (size_t)k;
+            if (it.window) { c->ws[it.slot].sent += (uint64_t)k; c->body_sent += (uint64_t)k; Sv.bytes_out += (uint64_t)k; }
+            else it.off += (size_t)k;
+        }
+        if (it.window) {
+            EvConn::Win& w = c->ws[it.slot];
+            if (w.sent < w.len) continue;                               // slice budget: the rest of this window next iteration of the loop
+            if (g_trace && c->t_req && w.urgent) { g_first_ns += (uint64_t)(now_ns() - c->t_req); g_first_n++; }
+            w.st = EvConn::FREE;
+            c->q.pop_front();
+            schedule(c);                                                // the freed window goes straight back to work
+        } else {
+            if (it.off < it.bytes.size()) continue;
+            c->q.pop_front();
+        }
+    }
+    if (c->dead) return;
+    arm(c, false);
+    if (c->q.empty() && c->part >= c->plan.body.size()) finish(c);
+}
+
+void Worker::finish(EvConn* c) {
+    Server& Sv = *S;
+    access_log_line(Sv, c->ip, c->pr, c->plan.status, c->plan.head ? 0 : c->plan.body_length());
+    if (c->ent) { c->ent->inflight--; c->ent.reset(); }
+    c->busy = false;
+    c->last_active = now_ms();
+    if (!c->keep) { kill(c); return; }
+    // a pipelined request may already be waiting: try_start's loop (our caller, or the next readable event) picks it up
+}
+
+void Worker::on_readable(EvConn* c) {
+    char tmp[16384];
+    for (int turns = 0; turns < 4; ++turns) {
+        const ssize_t r = recv(c->fd, tmp, sizeof tmp, MSG_DONTWAIT);
+        if (r > 0) { c->in.append(tmp, (size_t)r); c->last_active = now_ms(); if ((size_t)r < sizeof tmp) break; continue; }
+        if (r == 0) { kill(c); return; }
+        if (errno == EINTR) continue;
+        if (errno == EAGAIN || errno == EWOULDBLOCK) break;
+        kill(c);
+        return;
+    }
+    if (!c->busy) try_start(c);
+}
+
+void Worker::submit_pending() {
+    Server& Sv = *S;
+    for (int urgent = 1; urgent >= 0; --urgent) {
+        auto& lanes = urgent ? pend_urgent : pend_bulk;
+        for (size_t sh = 0; sh < lanes.size(); ++sh) {
+            std::vector<WinReq>& v = lanes[sh];
+            if (v.empty()) continue;
+            reqs_scratch.resize(v.size());
+            for (size_t i = 0; i < v.size(); ++i) { reqs_scratch[i] = v[i].rq; reqs_scratch[i].segs = &v[i].sg; }
+            OutTicket ot;
+            ot.t = nullptr; ot.urgent = urgent != 0; ot.t_sub = now_ns();
+            const int32_t rc = nz_get_submit(Sv.ctxs[sh], reqs_scratch.data(), (uint32_t)v.size(), nullptr, &ot.t);
+            for (const WinReq& r : v) ot.items.emplace_back(r.c, r.slot);
+            if (rc != NZ_OK) {
+                fprintf(stderr, "nzproxy: nz_get_submit failed: %s [%s]\n", nz_strerror(rc), nz_last_error());
+                for (auto& it : ot.items) { it.first->ws[it.second].st = EvConn::FAILED; it.first->inflight--; }
+                for (auto& it : ot.items) if (!it.first->dead) pump(it.first);
+            } else {
+                if (g_trace) { g_tr[urgent ? 0 : 1].waves++; g_tr[urgent ? 0 : 1].items += v.size(); }
+                out.push_back(std::move(ot));
+            }
+            v.clear();
+        }
+    }
+}
+
+void Worker::poll_tickets() {
+    for (size_t i = 0; i < out.size();) {
+        OutTicket& ot = out[i];
+        const int32_t pr = nz_get_poll(ot.t);
+        if (pr == NZ_ETIMEOUT) { ++i; continue; }
+        res_scratch.resize(ot.items.size());
+        int32_t rc = pr;
+        if (rc == NZ_OK) rc = nz_get_wait(ot.t, 0, res_scratch.data());
+        nz_ticket_free(ot.t);
+        if (g_trace) g_tr[ot.urgent ? 0 : 1].device_ns += (uint64_t)(now_ns() - ot.t_sub) * ot.items.size();
+        std::vector<std::pair<EvConn*, int>> items = std::move(ot.items);
+        std::vector<nz_get_res> res = res_scratch;
+        out.erase(out.begin() + (long)i);
+        for (size_t k = 0; k < items.size(); ++k) {
+            EvConn* c = items[k].first;
+            const bool ok = rc == NZ_OK && res[k].status == NZ_OK;
+            if (!ok) fprintf(stderr, "nzproxy: window failed: rc=%d (%s) status=%d [%s]\n", rc, nz_strerror(rc), rc == NZ_OK ? res[k].status : 0, nz_last_error());
+            c->ws[items[k].second].st = ok ? EvConn::READY : EvConn::FAILED;
+            c->inflight--;
+        }
+        for (size_t k = 0; k < items.size(); ++k) {
+            EvConn* c = items[k].first;
+            bool seen = false;
+            for (size_t j = 0; j < k; ++j) seen |= items[j].first == c;
+            if (seen) continue;
+            if (c->dead) continue;
+            pump(c);
+            if (!c->dead && !c->busy) try_start(c);                      // (c may be lent to a miss helper after this: not touched again)
+        }
+    }
+}
+
+void Worker::run() {
+    Server& Sv = *S;
+    pend_urgent.resize(Sv.ctxs.size());
+    pend_bulk.resize(Sv.ctxs.size());
+    struct epoll_event evs[128];
+    int64_t last_sweep = now_ms();
+    for (;;) {
+        // How to wait.  Something to send right now: do not wait.  A first window (urgent) in flight: poll, its completion is
+        // tens of microseconds away and is the latency a client sees.  Only bulk windows in flight: sleep in short slices
+        // (a spinning worker per loop starves the very sockets it feeds on a box with fewer cores than threads).
+        // Nothing in flight: block.
+        const int64_t tnow = out.empty() ? 0 : now_ns();
+        bool urgent_out = false;
+        for (const OutTicket& ot : out) urgent_out |= ot.urgent && tnow - ot.t_sub < 300000;
+        int n;
+        if (!more.empty() || urgent_out) n = epoll_wait(ep, evs, 128, 0);
+        else if (!out.empty()) {
+            struct timespec ts = {0, 30000};
+            n = (int)syscall(SYS_epoll_pwait2, ep, evs, 128, &ts, nullptr, 0);
+            if (n < 0 && errno == ENOSYS) n = epoll_wait(ep, evs, 128, 0);
+        } else n = epoll_wait(ep, evs, 128, 1000);
+        const bool hot = urgent_out;
+        for (int i = 0; i < n; ++i) {
+            if (evs[i].data.ptr == nullptr) {                            // the eventfd: connections to adopt
+                uint64_t cnt;
+                if (read(evfd, &cnt, 8) < 0) {}
+                std::vector<EvConn*> take;
+                { std::lock_guard<std::mutex> g(mu); take.swap(inbox); }
+                for (EvConn* c : take) {
+                    c->w = this;
+                    c->want_out = false;
+                    c->last_active = now_ms();
+                    struct epoll_event ev;
+                    memset(&ev, 0, sizeof ev);
+                    ev.events = EPOLLIN | EPOLLRDHUP;
+                    ev.data.ptr = c;
+                    conns.push_back(c);
+                    if (epoll_ctl(ep, EPOLL_CTL_ADD, c->fd, &ev) != 0) { c->dead = true; shutdown(c->fd, SHUT_RDWR); dying.push_back(c); continue; }
+                    if (!c->in.empty()) try_start(c);                    // back from a miss helper with a pipelined request
+                }
+                continue;
+            }
+            EvConn* c = static_cast<EvConn*>(evs[i].data.ptr);
+            if (std::find(conns.begin(), conns.end(), c) == conns.end() || c->dead) continue;     // lent to a miss helper earlier in this batch / killed
+            if (evs[i].events & (EPOLLERR | EPOLLHUP)) { kill(c); continue; }
+            if (evs[i].events & EPOLLOUT) {
+                pump(c);
+                if (!c->dead && !c->busy) try_start(c);
+                continue;                                                // (input, if any, is reported again: level triggered)
+            }
+            if (evs[i].events & (EPOLLIN | EPOLLRDHUP)) on_readable(c);
+        }
+        submit_pending();
+        poll_tickets();
+        for (size_t k = more.size(); k > 0 && !more.empty(); --k) {     // one more slice for everyone who was cut short
+            EvConn* c = more.front();
+            more.pop_front();
+            c->queued_more = false;
+            if (c->dead) continue;
+            pump(c);
+            if (!c->dead && !c->busy) try_start(c);
+        }
+        submit_pending();                                                // windows freed by this turn's sends
+        if (hot && n == 0) __builtin_ia32_pause();
+        const int64_t now = now_ms();
+        if (now - last_sweep > 1000) {                                   // client_header_timeout 60 s / keepalive_timeout 65 s (nginx defaults)
+            last_sweep = now;
+            std::vector<EvConn*> idle;
+            for (EvConn* c : conns)
+                if (!c->dead && !c->busy && now - c->last_active > (c->in.empty() ? 65000 : 60000)) idle.push_back(c);
+            for (EvConn* c : idle) kill(c);
+        }
+        for (size_t i = 0; i < dying.size();) {
+            if (dying[i]->inflight == 0 && !dying[i]->queued_more) { reap(dying[i]); dying.erase(dying.begin() + (long)i); }
+            else ++i;
+        }
+    }
+}
+
 void usage() {
     fprintf(stderr,
             "nzproxy [--listen ip:port] [--device N | --devices 0,1,..] [--arena-gib G] [--max-objects N] [--window-mib M] [--first-window-kib K] [--host-rate-gbs R] [--host-ctas N]\n"
-            "        [--max-conns N] [--gunzip] [--verify] [--upstream proxy_host=[https://]ip:port]... [--proxy-ssl-server-name] [--access-log PATH] [--pv DIR] [--inactive-s S] [--valid-s S]\n");
+            "        [--max-conns N] [--io-threads N] [--gunzip] [--s3-private bucket:access:secret] [--verify] [--upstream proxy_host=[https://]ip:port]... [--proxy-ssl-server-name] [--access-log PATH] [--pv DIR] [--inactive-s S] [--valid-s S]\n");
 }
 
 }  // namespace
@@ -1088,7 +1589,15 @@ int main(int argc, char** argv) {
         else if (a == "--proxy-ssl-server-name") S.opt.proxy_ssl_server_name = true;
         else if (a == "--access-log") S.opt.access_log = next();
         else if (a == "--max-conns") S.opt.max_conns = atoi(next());
+        else if (a == "--io-threads") S.opt.io_threads = atoi(next());
         else if (a == "--gunzip") S.opt.gunzip = true;
+        else if (a == "--s3-private") {                // bucket:access:secret
+            const std::string v = next();
+            const size_t c1 = v.find(':'), c2 = v.find(':', c1 == std::string::npos ? 0 : c1 + 1);
+            if (c1 == std::string::npos || c2 == std::string::npos) { usage(); return 2; }
+            S.opt.s3_bucket = v.substr(0, c1); S.opt.s3_access = v.substr(c1 + 1, c2 - c1 - 1); S.opt.s3_secret = v.substr(c2 + 1);
+            S.cfg.vhosts.push_back(nzh::VHost{"s3.amazonaws.com", "s3.amazonaws.com", false});      // nginx.conf:141,164
+        }
         else if (a == "--pv") S.opt.pv_dir = next();
         else if (a == "--inactive-s") S.opt.inactive_s = atoi(next());
         else if (a == "--valid-s") S.opt.valid_s = atoi(next());
@@ -1128,9 +1637,24 @@ int main(int argc, char** argv) {
     }
     if (!S.opt.pv_dir.empty()) pv_reload(S);
     std::thread([&S] { for (;;) { std::this_thread::sleep_for(std::chrono::seconds(S.opt.inactive_s < 120 ? 1 : 60)); cache_manager_pass(S); } }).detach();
+    {   // CPUs this process may really use: affinity mask and the cgroup's CPU quota (a container that shows 128 CPUs may own 16)
+        cpu_set_t set;
+        int cpus = (int)std::thread::hardware_concurrency();
+        if (sched_getaffinity(0, sizeof set, &set) == 0) cpus = std::min(cpus, CPU_COUNT(&set));
+        if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+            long long quota = 0, period = 0;
+            char q[32];
+            if (fscanf(f, "%31s %lld", q, &period) == 2 && strcmp(q, "max") != 0 && (quota = atoll(q)) > 0 && period > 0)
+                cpus = std::min<int>(cpus, (int)std::max<long long>(1, quota / period));
+            fclose(f);
+        }
+        g_spin_cap = std::max(1, cpus / 8);
+        if (const char* e = getenv("NZ_PROXY_SPIN_CAP")) g_spin_cap = atoi(e);
+        fprintf(stderr, "nzproxy: %d usable CPUs, at most %d threads poll for a window at a time\n", cpus, g_spin_cap);
+    }
     for (nz_ctx* cx : S.ctxs) {
         auto u = std::make_unique<Combiner>();
-        u->ctx = cx; u->cap_bytes = 16ull << 20; u->linger_us = 0; u->spin_us = 2000; u->lane = 0;
+        u->ctx = cx; u->cap_bytes = 16ull << 20; u->linger_us = 0; u->spin_us = g_spin_cap >= 4 ? 2000 : 100; u->lane = 0;
         auto k = std::make_unique<Combiner>();
         k->ctx = cx; k->cap_bytes = 16ull << 20; k->linger_us = 20;
         if (const char* e = getenv("NZ_PROXY_BULK_CAP_MIB")) k->cap_bytes = (uint64_t)std::max(1, atoi(e)) << 20;
@@ -1173,6 +1697,27 @@ int main(int argc, char** argv) {
                         (unsigned long long)g_direct_n.load(), g_direct_ns / (double)std::max<uint64_t>(1, g_direct_n.load()) / 1e3);
             }
         }).detach();
+    std::vector<std::unique_ptr<Worker>> workers;
+    size_t rr = 0;
+    {
+        int nio = S.opt.io_threads;
+        if (const char* e = getenv("NZ_PROXY_IO_THREADS")) nio = atoi(e);
+        if (nio < 0) nio = 0;
+        for (int i = 0; i < nio; ++i) {
+            auto w = std::make_unique<Worker>();
+            w->S = &S;
+            w->ep = epoll_create1(EPOLL_CLOEXEC);
+            w->evfd = eventfd(0, EFD_NONBLOCK | EFD_CLOEXEC);
+            struct epoll_event ev;
+            memset(&ev, 0, sizeof ev);
+            ev.events = EPOLLIN;
+            ev.data.ptr = nullptr;
+            if (w->ep < 0 || w->evfd < 0 || epoll_ctl(w->ep, EPOLL_CTL_ADD, w->evfd, &ev) != 0) { perror("nzproxy: epoll"); return 1; }
+            Worker* wp = w.get();
+            std::thread([wp] { wp->run(); }).detach();
+            workers.push_back(std::move(w));
+        }
+    }
     int ls = socket(AF_INET, SOCK_STREAM, 0);
     int one = 1;
     setsockopt(ls, SOL_SOCKET, SO_REUSEADDR, &one, sizeof one);
@@ -1185,8 +1730,9 @@ int main(int argc, char** argv) {
         perror("nzproxy: bind/listen");
         return 1;
     }
-    fprintf(stderr, "nzproxy: listening on %s:%d, %zu GPU shard(s), arena %.1f GiB each, %zu pinned windows of %.1f MiB\n", S.opt.listen_ip.c_str(),
-            S.opt.port, S.ctxs.size(), S.opt.arena_bytes / 1073741824.0, S.free_windows.size(), S.opt.window_bytes / 1048576.0);
+    fprintf(stderr, "nzproxy: listening on %s:%d, %zu GPU shard(s), arena %.1f GiB each, %zu pinned windows of %.1f MiB, %zu event-loop worker(s)%s\n", S.opt.listen_ip.c_str(),
+            S.opt.port, S.ctxs.size(), S.opt.arena_bytes / 1073741824.0, S.free_windows.size(), S.opt.window_bytes / 1048576.0, workers.size(),
+            workers.empty() ? " (thread per connection)" : "");
     fflush(stderr);
     for (;;) {
         struct sockaddr_in ca;
@@ -1200,7 +1746,14 @@ int main(int argc, char** argv) {
         S.conns++;
         char ip[64];
         inet_ntop(AF_INET, &ca.sin_addr, ip, sizeof ip);
-        std::thread(serve_connection, &S, fd, std::string(ip)).detach();
+        if (workers.empty()) { std::thread(serve_connection, &S, fd, std::string(ip)).detach(); continue; }
+        EvConn* c = new EvConn();
+        c->fd = fd;
+        c->ip = ip;
+        tune_socket(fd);
+        if (!take_windows(S, c->win)) { give_windows(S, c->win); close(fd); S.conns--; delete c; continue; }
+        fcntl(fd, F_SETFL, fcntl(fd, F_GETFL, 0) | O_NONBLOCK);
+        workers[rr++ % workers.size()]->post(c);
     }
     for (nz_ctx* cx : S.ctxs) nz_shutdown(cx);
     return 0;

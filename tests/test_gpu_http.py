@@ -532,3 +532,54 @@ def test_gunzip_switch_differential(policy_origin, tmp_path):
             os.killpg(cpu.pid, signal.SIGTERM)
         except ProcessLookupError:
             pass
+
+
+def test_private_s3_vhost_signs_fills_with_sigv2():
+    """The conf's private-S3 server block (nginx.conf:138-166, commented out in the reference): a fill goes upstream over
+    HTTP/1.1 as `Host: <bucket>.s3.amazonaws.com` with `x-amz-date` and `Authorization: AWS <access>:<base64 HMAC-SHA1>`
+    over "GET\\n\\n\\n\\nx-amz-date:<date>\\n/<bucket><path>".  The fake S3 below checks the signature the way S3 does."""
+    import base64
+    import hmac
+
+    bucket, access, secret = "my-datasets", "AKIDEXAMPLE", "wJalrXUtnFEMI/K7MDENG+bPxRfiCYEXAMPLEKEY"
+    data = wl.synth_bytes(777_777, 91).tobytes()
+    seen = []
+
+    class S3(http.server.BaseHTTPRequestHandler):
+        protocol_version = "HTTP/1.1"
+
+        def do_GET(self):
+            date, auth, host = self.headers.get("x-amz-date", ""), self.headers.get("Authorization", ""), self.headers.get("Host", "")
+            want = base64.b64encode(hmac.new(secret.encode(), f"GET\n\n\n\nx-amz-date:{date}\n/{bucket}{self.path}".encode(), "sha1").digest()).decode()
+            ok = auth == f"AWS {access}:{want}" and host == f"{bucket}.s3.amazonaws.com" and self.path == "/train/shard-0001.tar"
+            seen.append((ok, self.request_version, host))
+            body = data if ok else b"<Error><Code>SignatureDoesNotMatch</Code></Error>"
+            self.send_response(200 if ok else 403)
+            self.send_header("Content-Length", str(len(body)))
+            self.send_header("Content-Type", "application/x-tar")
+            self.send_header("ETag", '"%s"' % hashlib.md5(data).hexdigest())
+            self.send_header("Accept-Ranges", "bytes")
+            self.send_header("Connection", "close")
+            self.end_headers()
+            self.wfile.write(body)
+
+        def log_message(self, *a):
+            pass
+
+    oport, port = free_port(), free_port()
+    httpd = http.server.ThreadingHTTPServer(("127.0.0.1", oport), S3)
+    threading.Thread(target=httpd.serve_forever, daemon=True).start()
+    p = subprocess.Popen([os.path.join(ROOT, "nezha_b200", "_build", "nzproxy"), "--listen", f"127.0.0.1:{port}", "--arena-gib", "0.5", "--max-conns", "8",
+                          "--window-mib", "1", "--s3-private", f"{bucket}:{access}:{secret}", "--upstream", f"s3.amazonaws.com=127.0.0.1:{oport}"],
+                         start_new_session=True)
+    try:
+        wait_port(port, 120)
+        for _ in range(2):
+            s, hd, b = fetch(port, "GET", "s3.amazonaws.com", "/train/shard-0001.tar", {})
+            assert s == 200 and b == data and hd.get("content-type") == "application/x-tar"
+        s, _, b = fetch(port, "GET", "s3.amazonaws.com", "/train/shard-0001.tar", {"Range": "bytes=700000-700099"})
+        assert s == 206 and b == data[700000:700100]
+        assert seen == [(True, "HTTP/1.1", f"{bucket}.s3.amazonaws.com")]            # one signed fill, then hits
+    finally:
+        _stop(p)
+        httpd.shutdown()

@@ -355,3 +355,26 @@ def test_stored_byte_corrupted_after_commit(zone, corpus):
     res, _ = zone.get(key, flags=capi.NZ_GET_INFLATE, device_dst=True)
     assert res.status in (capi.NZ_OK, capi.NZ_ECORRUPT)
     zone.evict(key)
+
+
+def test_inflate_flag_without_a_gzip_object_in_a_recycled_ticket(zone, corpus):
+    """A wave that carries NZ_GET_INFLATE but names only identity objects launches the segment decoder with nothing to do.
+    Its work total must not be whatever an earlier inflate wave left in the (recycled) ticket: found by the property
+    test as cudaErrorMisalignedAddress, round 2."""
+    raw = np.frombuffer(corpus["text_odd"], dtype=np.uint8)
+    kz = wl.key128(b"gz/recycle/z")
+    ki = wl.key128(b"gz/recycle/i")
+    zone.put(kz, np.frombuffer(wl.gzip_member(raw), dtype=np.uint8), enc=capi.NZ_ENC_GZIP, raw_len=len(raw))
+    zone.put(ki, raw[:70_001])
+    for _ in range(3):
+        # same shape (6 requests) so the second wave takes the first one's ticket back from the pool
+        bufs = [zone.alloc_device(len(raw) + 64) for _ in range(6)]
+        t = zone.submit([nz.Get(kz, b, [], capi.NZ_GET_INFLATE, 0) for b in bufs])
+        res = t.wait(); t.free()
+        assert all(r.status == capi.NZ_OK for r in res) and bufs[0].bytes(0, len(raw)) == raw.tobytes()
+        t = zone.submit([nz.Get(ki, b, [], capi.NZ_GET_INFLATE | (capi.NZ_GET_VERIFY if j & 1 else 0), j) for j, b in enumerate(bufs)])
+        res = t.wait(); t.free()
+        assert all(r.status == capi.NZ_OK for r in res)
+        assert bufs[3].bytes(3, 70_001) == raw[:70_001].tobytes()
+        for b in bufs:
+            b.free()
