@@ -151,6 +151,7 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
     if (const char* ev = getenv("NZ_GATHER_VARIANT"))      // "0" / "reg": register path only; anything else: the default bulk-copy kernel
         c->gather_variant = (!strcmp(ev, "0") || !strcmp(ev, "reg")) ? NZ_GATHER_REG : NZ_GATHER_TMA;
     if (const char* ev = getenv("NZ_COALESCE")) c->coalesce = atoi(ev) != 0;
+    if (const char* ev = getenv("NZ_SPAN_DYN")) c->span_dynamic = atoi(ev) != 0;
     if (const char* ev = getenv("NZ_SPAN_SPREAD")) { const int v = atoi(ev); if (v >= 0 && v <= 4096) c->span_spread = (uint32_t)v; }
     if (const char* ev = getenv("NZ_PROFILE")) c->profile = atoi(ev) != 0;
     if (const char* ev = getenv("NZ_FUSE_VERIFY")) c->fuse_verify = atoi(ev) != 0;
@@ -1228,9 +1229,9 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
     }
     // K5: a wave with striped sources walks its tiles spread over the whole wave, so the CTAs running at any moment
     // pull from stripes on different peers (see TileOrder in nz_kernels.cu)
-    uint32_t spread = 0;
-    if (c->span_spread)
-        for (const auto& sp : split) if (!sp.empty()) { spread = c->span_spread; break; }
+    bool striped_wave = false;
+    for (const auto& sp : split) if (!sp.empty()) { striped_wave = true; break; }
+    const uint32_t spread = striped_wave ? c->span_spread : 0;
     // does the wave name a key twice?  Then request coalescing will very likely chain slices (fan-out tiles: 2 stages);
     // a wave of distinct keys copies every tile once (3 stages).  The grid follows the stage count's occupancy.
     int stages_hint = 3;
@@ -1241,9 +1242,10 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
             if (!seen.insert(rd64(reqs[i].key) ^ (rd64(reqs[i].key + 8) * 0x9E3779B97F4A7C15ull)).second) { stages_hint = 2; break; }
     }
     if (stages_hint == 3 && !a.fuse_verify && ggrid > c->gather_grid3) ggrid = c->gather_grid3;
+    uint32_t* dyn = (striped_wave && c->span_dynamic) ? a.counters + 6 : nullptr;      // zeroed by k_plan
     if (fused_small) { /* copied by the plan kernel */ }
-    else if (a.fuse_verify) CKT(nz_launch_gather(variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s, a.seg_ver, a.ver, c->crc_tables, pace_ns, spread, stages_hint));
-    else CKT(nz_launch_gather(variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s, nullptr, nullptr, nullptr, pace_ns, spread, stages_hint));
+    else if (a.fuse_verify) CKT(nz_launch_gather(variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s, a.seg_ver, a.ver, c->crc_tables, pace_ns, spread, stages_hint, dyn));
+    else CKT(nz_launch_gather(variant, a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, ggrid, s, nullptr, nullptr, nullptr, pace_ns, spread, stages_hint, dyn));
     if (t->profiled) CKT(cudaEventRecord(t->ev_g1, s));
     c->launches += fused_small ? 0 : 1;
     if (any_verify && ver_cap) {

@@ -46,6 +46,12 @@ __device__ __forceinline__ uint4 crc_ldg16(const void* p) {
     return r;
 }
 
+__device__ __forceinline__ uint4 crc_ldg16_stream(const void* p) {   // read-once input: keep it out of L1, where the lookup tables live
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
 // CRC of one chunk (<= 64 KiB) by a 256-thread CTA: thread t owns bytes
 // [256 t, 256 t + 256), slice-by-4 from shared tables (sT: 4 x 256 u32 of the
 // chosen polynomial), then the per-thread CRCs are shifted to the chunk end
@@ -129,43 +135,78 @@ __device__ __forceinline__ uint32_t crc_warp_tree(uint32_t v, const uint32_t* __
 #pragma unroll
     for (int s = 0; s < 5; ++s) {
         const uint32_t u = __shfl_down_sync(0xffffffffu, v, 1u << s);
-        const uint32_t* T = gL + s * 1024;
-        const uint32_t z = __ldg(T + (v & 0xffu)) ^ __ldg(T + 256 + ((v >> 8) & 0xffu)) ^ __ldg(T + 512 + ((v >> 16) & 0xffu)) ^ __ldg(T + 768 + (v >> 24));
-        if ((lane & ((2u << s) - 1u)) == 0) v = z ^ u;
+        // only the lanes that carry a partial sum at this level look anything up: 16 + 8 + 4 + 2 + 1 lanes x 4 scattered
+        // loads per warp, not 5 x 32 x 4 (each scattered load is a wavefront of its own in the L1 data stage - with every
+        // lane loading, the tree cost more L1 bandwidth than the whole row loop: profiles/r02_k_crc_chunks_v2.txt)
+        if ((lane & ((2u << s) - 1u)) == 0) {
+            const uint32_t* T = gL + s * 1024;
+            v = __ldg(T + (v & 0xffu)) ^ __ldg(T + 256 + ((v >> 8) & 0xffu)) ^ __ldg(T + 512 + ((v >> 16) & 0xffu)) ^ __ldg(T + 768 + (v >> 24)) ^ u;
+        }
     }
     return v;
 }
 
-template <int POLY>
+template <int POLY, bool TREE = true>
 __device__ uint32_t block_crc_chunk64k(const uint8_t* __restrict__ p, const uint32_t* sZS8, const uint32_t* sT,
                                        const uint32_t* __restrict__ gK, uint32_t* sred) {
     const uint32_t tid = threadIdx.x;
     uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     const uint4* v = reinterpret_cast<const uint4*>(p) + tid;
     NZ_ZS_SETUP(tid)
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-        uint4 w = crc_ldg16(v + i * 256);
-        if (i == 0 && tid == 0) w.x ^= 0xFFFFFFFFu;        // the CRC's initial value, folded into the first word
-        a0 = NZ_ZS(a0) ^ w.x;
-        a1 = NZ_ZS(a1) ^ w.y;
-        a2 = NZ_ZS(a2) ^ w.z;
-        a3 = NZ_ZS(a3) ^ w.w;
+    // rows in groups of four, the next group's loads issued before the current group is folded: eight 16 B loads per
+    // thread in flight (the compiler kept two when left to itself and the kernel sat on long-scoreboard stalls)
+    uint4 w[2][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[0][j] = crc_ldg16_stream(v + j * 256);
+    if (tid == 0) w[0][0].x ^= 0xFFFFFFFFu;                // the CRC's initial value, folded into the first word
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        if (g < 3) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[(g + 1) & 1][j] = crc_ldg16_stream(v + ((g + 1) * 4 + j) * 256);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 x = w[g & 1][j];
+            a0 = NZ_ZS(a0) ^ x.x;
+            a1 = NZ_ZS(a1) ^ x.y;
+            a2 = NZ_ZS(a2) ^ x.z;
+            a3 = NZ_ZS(a3) ^ x.w;
+        }
     }
 #define NZ_Z4(a) (sT[3 * 256 + ((a) & 0xffu)] ^ sT[2 * 256 + (((a) >> 8) & 0xffu)] ^ sT[256 + (((a) >> 16) & 0xffu)] ^ sT[(a) >> 24])
     uint32_t vv = NZ_Z4(a0) ^ a1;
     vv = NZ_Z4(vv) ^ a2;
     vv = NZ_Z4(vv) ^ a3;
 #undef NZ_Z4
-    // lanes of a warp first (tree), then ONE multiply per warp moves its 512 B to the chunk end: K[t + 31] is lane 31's factor
-    const uint32_t w = crc_warp_tree(vv, gK + (NZ_CRC_LVL_OFF - 1024));
-    __syncthreads();
-    if ((tid & 31u) == 0) sred[tid >> 5] = gf_mul<POLY>(__ldg(gK + tid + 31), w);
-    __syncthreads();
-    uint32_t r = 0;
+    if constexpr (!TREE) {
+        // A/B partner: every thread multiplies (32 steps of shift-and-add, no memory traffic), then XOR-reduce
+        uint32_t contrib = gf_mul<POLY>(__ldg(gK + tid), vv);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) r ^= sred[i];
-    return ~r;
+        for (int o = 16; o > 0; o >>= 1) contrib ^= __shfl_xor_sync(0xffffffffu, contrib, o);
+        __syncthreads();
+        if ((tid & 31u) == 0) sred[tid >> 5] = contrib;
+        __syncthreads();
+        uint32_t r = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r ^= sred[i];
+        return ~r;
+    }
+    // lanes of a warp first (tree), then ONE multiply per warp moves its 512 B to the chunk end: K[t + 31] is lane 31's factor
+    const uint32_t wsum = crc_warp_tree(vv, gK + (NZ_CRC_LVL_OFF - 1024));
+    __syncthreads();                                       // sred is free again
+    if ((tid & 31u) == 0) sred[tid >> 5] = wsum;
+    __syncthreads();
+    // the eight warp sums meet in warp 0: ONE warp runs the 32-step multiply (a predicated-off lane costs the same issue
+    // slots as an active one, so "lane 0 of every warp" would still be eight multiplies' worth of instructions)
+    uint32_t r = 0;
+    if (tid < 32u) {
+        if (tid < 8u) r = gf_mul<POLY>(__ldg(gK + 32u * tid + 31u), sred[tid]);
+        r ^= __shfl_xor_sync(0xffffffffu, r, 4);
+        r ^= __shfl_xor_sync(0xffffffffu, r, 2);
+        r ^= __shfl_xor_sync(0xffffffffu, r, 1);
+    }
+    return ~r;                                             // valid in thread 0 (the only reader)
 }
 
 // loads the replicated stride table of one polynomial into shared memory (256 threads)
@@ -247,8 +288,9 @@ __device__ __forceinline__ void crc_piece_partial(const uint8_t* p, uint32_t P, 
         vv = crc_z4g(vv, gT) ^ a2;
         vv = crc_z4g(vv, gT) ^ a3;
         vv = crc_z4g(vv, gT);
-        const uint32_t w = crc_warp_tree(vv, gL);              // R is uniform over the CTA: every lane is here
-        if ((tid & 31u) == 0) main = gf_mul<0>(__ldg(gF + (NT - 32 - tid)), w);      // lane 31's factor: to the end of the full-row region
+        main = crc_warp_tree(vv, gL);                          // R is uniform over the CTA: every lane is here.  Lane 0: the warp's 512 B,
+                                                               // still to be moved to the end of the full-row region (factor gF[NT - 32 - tid])
+        if ((tid & 31u) != 0) main = 0;
     }
     part = 0;
     if (tid < rem) {

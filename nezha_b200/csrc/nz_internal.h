@@ -262,6 +262,7 @@ struct nz_ctx {
     bool fuse_small = true;  // env NZ_FUSE_SMALL=0: small waves launch plan and gather separately
     bool fuse_verify = true; // env NZ_FUSE_VERIFY=0: NZ_GET_VERIFY re-reads every chunk in k_verify (A/B measurements)
     bool coalesce = true;   // env NZ_COALESCE=0 turns request coalescing off (A/B measurements)
+    bool span_dynamic = true;  // K5: such waves hand out tiles dynamically (env NZ_SPAN_DYN=0: static split)
     uint32_t span_spread = 64; // K5: rows of the spread tile order of waves with striped sources (env NZ_SPAN_SPREAD, 0 = plain order)
     int gather_variant = NZ_GATHER_TMA; // K2 kernel: bulk-copy engine staging (default) or the register path (env NZ_GATHER_VARIANT=0|reg)
     int inflate_grid;
@@ -336,7 +337,7 @@ struct NzPlanArgs {
     NzVerWork* ver;             // capacity ver_cap
     uint32_t ver_cap;
     NzInflWork* infl;           // capacity n
-    uint32_t* counters;         // [0]=n_ver [1]=n_infl [2]=inflate work-steal cursor
+    uint32_t* counters;         // [0]=n_ver [1]=n_infl [2]=inflate work-steal cursor ... [6]=gather step counter (dynamic tile scheduling)
     uint64_t* infl_meta;        // n: (produced length << 32) | trailer CRC-32, written by k_inflate
     uint32_t tile_bytes;        // gather tile size of the selected k_gather variant
     uint32_t coalesce;          // 1 = chain identical slices behind one leader (read once, write many)
@@ -361,7 +362,7 @@ cudaError_t nz_launch_plan(const NzPlanArgs& a, cudaStream_t s, const NzSmallWav
 cudaError_t nz_launch_gather(int variant, const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head,
                              const uint32_t* chain_next, uint32_t nseg, int grid, cudaStream_t s,
                              const uint32_t* seg_ver = nullptr, NzVerWork* ver = nullptr, const uint32_t* crc_tables = nullptr,
-                             uint32_t pace_ns = 0, uint32_t spread = 0, int stages_hint = 0);
+                             uint32_t pace_ns = 0, uint32_t spread = 0, int stages_hint = 0, uint32_t* dyn = nullptr);
 bool nz_gather_fuses_verify(int variant);
 uint32_t nz_gather_tile_bytes(int variant);
 cudaError_t nz_launch_verify(const NzPlanArgs& a, const uint32_t* crc_tables, int grid, cudaStream_t s);

@@ -778,19 +778,48 @@ struct TileOrder {
     }
 };
 
+// Which step a CTA takes next.  Static: b, b + grid, ... (HBM-bound waves: every tile costs about the same).  Dynamic
+// (`dyn` = a zeroed counter): the next free step, drawn one iteration ahead so the atomic's latency hides behind the
+// current tile.  Waves with striped sources use it: a tile pulled over NVLink takes several times as long as a local
+// one, and with a static split the CTAs that happened to get more remote tiles finish last while NVLink idles.
+struct StepIter {
+    uint64_t i;
+    uint32_t* dyn;
+    uint64_t* slot;          // shared memory, one word
+    uint32_t ahead;          // thread 0: the step after this one (dynamic only)
+    __device__ __forceinline__ void begin(uint32_t* dyn_, uint64_t* slot_) {
+        dyn = dyn_; slot = slot_; ahead = 0;
+        if (!dyn) { i = blockIdx.x; return; }
+        if (threadIdx.x == 0) { *slot = atomicAdd(dyn, 1u); ahead = atomicAdd(dyn, 1u); }
+        __syncthreads();
+        i = *slot;
+    }
+    __device__ __forceinline__ void next() {
+        if (!dyn) { i += gridDim.x; return; }
+        __syncthreads();                                   // everyone has read the current step
+        if (threadIdx.x == 0) { *slot = ahead; ahead = atomicAdd(dyn, 1u); }
+        __syncthreads();
+        i = *slot;
+    }
+    // thread 0 only: the step this CTA takes after the current one (the fused-verify kernel loads it ahead)
+    __device__ __forceinline__ uint64_t peek() const { return dyn ? (uint64_t)ahead : i + gridDim.x; }
+};
+
 // Register path on its own (NZ_GATHER_VARIANT=0): the fallback and the A/B partner of the bulk-copy kernel.
 template <int NT, int U, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 k_gather(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_begin, const uint32_t* __restrict__ chain_head,
-         const uint32_t* __restrict__ chain_next, uint32_t nseg, uint32_t tile_bytes, uint32_t spread) {
+         const uint32_t* __restrict__ chain_next, uint32_t nseg, uint32_t tile_bytes, uint32_t spread, uint32_t* dyn) {
+    __shared__ uint64_t s_step;
     const TileOrder ord(tile_begin[nseg], spread);
     TileCursor c;
     DstChain dc;
     dc.work = work;
     dc.next = chain_next;
     dc.head = 0xFFFFFFFFu;
-    for (uint64_t i = blockIdx.x; i < ord.steps(); i += gridDim.x) {
-        const uint64_t tile = ord.tile(i);
+    StepIter it;
+    for (it.begin(dyn, &s_step); it.i < ord.steps(); it.next()) {
+        const uint64_t tile = ord.tile(it.i);
         if (tile == ~0ull) continue;
         const uint32_t before = c.seg;
         const bool fresh = !(tile >= c.lo_t && tile < c.hi_t);
@@ -807,7 +836,8 @@ k_gather(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_b
 // ---------------------------------------------------------------------------
 // K3: CRC-32C chunk table + whole-object fold (device code in nz_crc.cuh)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+template <bool TREE>
+__global__ void __launch_bounds__(256, 4)
 k_crc_chunks(const uint8_t* __restrict__ p, uint64_t n, uint32_t* __restrict__ chunk_out, const uint32_t* __restrict__ tables) {
     __shared__ uint32_t sT[4 * 256];
     __shared__ uint32_t sZS8[1024 * 8];
@@ -821,7 +851,7 @@ k_crc_chunks(const uint8_t* __restrict__ p, uint64_t n, uint32_t* __restrict__ c
     for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
         const uint64_t off = c * NZ_CRC_CHUNK;
         const uint32_t m = (uint32_t)min((uint64_t)NZ_CRC_CHUNK, n - off);
-        const uint32_t crc = (aligned && m == NZ_CRC_CHUNK) ? block_crc_chunk64k<0>(p + off, sZS8, sT, fast + 1024, sred)
+        const uint32_t crc = (aligned && m == NZ_CRC_CHUNK) ? block_crc_chunk64k<0, TREE>(p + off, sZS8, sT, fast + 1024, sred)
                                                             : block_crc_chunk<0>(p + off, m, sT, sred);
         if (threadIdx.x == 0) chunk_out[c] = crc;
     }
@@ -1004,10 +1034,19 @@ __device__ __forceinline__ void tile_verify(const VerifyCtx& vc, const uint8_t* 
         __syncthreads();                                       // sred reuse
         if ((tid & 31u) == 0) { vc.sred[tid >> 5] = m; vc.sred[8 + (tid >> 5)] = pt; }
         __syncthreads();                                       // also: every thread is done reading the tile
-        if (tid == 32) {
-            uint32_t M = 0, st = 0;
+        if (tid >= 32 && tid < 64) {                           // warp 1 finishes the piece
+            // every warp left the sum of its 512 B column block (warp tree); lane l moves warp l's to the end of the
+            // full-row region with that warp's factor - one 32-step multiply for the whole CTA instead of one per thread
+            const uint32_t l = tid - 32;
+            uint32_t M = 0;
+            if (l < NZ_TMA_VTHREADS / 32) M = gf_mul<0>(__ldg(vc.gF + (NZ_TMA_VTHREADS - 32 - 32 * l)), vc.sred[l]);
+            M ^= __shfl_xor_sync(0xffffffffu, M, 4);
+            M ^= __shfl_xor_sync(0xffffffffu, M, 2);
+            M ^= __shfl_xor_sync(0xffffffffu, M, 1);
+        if (l == 0) {
+            uint32_t st = 0;
 #pragma unroll
-            for (int i = 0; i < NZ_TMA_VTHREADS / 32; ++i) { M ^= vc.sred[i]; st ^= vc.sred[8 + i]; }
+            for (int i = 0; i < NZ_TMA_VTHREADS / 32; ++i) st ^= vc.sred[8 + i];
             if (M) st ^= gf_mul<0>(__ldg(vc.gF + ((P >> 4) % NZ_TMA_VTHREADS)), M);   // full rows -> end of the piece
             if (tail) {
                 if (ones && P == 0) st = 0xFFFFFFFFu;
@@ -1018,6 +1057,7 @@ __device__ __forceinline__ void tile_verify(const VerifyCtx& vc, const uint8_t* 
             if (after) st = gf_mul<0>(crc_xpow8_small(after, vc.gF), st);
             atomicXor(&e->acc, st);
             atomicAdd(&e->got, plen);
+        }
         }
     }
 }
@@ -1062,9 +1102,10 @@ template <int STAGES, bool VERIFY>
 __global__ void __launch_bounds__(VERIFY ? NZ_TMA_VTHREADS : NZ_TMA_THREADS)
 k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ tile_begin, const uint32_t* __restrict__ chain_head,
              const uint32_t* __restrict__ chain_next, uint32_t nseg, uint32_t tile_bytes, const uint32_t* __restrict__ seg_ver,
-             NzVerWork* ver, const uint32_t* __restrict__ crc_tables, uint32_t pace_ns, uint32_t spread, uint32_t l2h) {
+             NzVerWork* ver, const uint32_t* __restrict__ crc_tables, uint32_t pace_ns, uint32_t spread, uint32_t l2h, uint32_t* dyn) {
     extern __shared__ __align__(128) uint8_t s_buf[];          // STAGES x tile_bytes [ | 32 KiB stride table when VERIFY ]
     __shared__ __align__(8) uint64_t s_bar[STAGES];
+    __shared__ uint64_t s_step;
     __shared__ uint32_t s_red[16];
     constexpr int NT = VERIFY ? NZ_TMA_VTHREADS : NZ_TMA_THREADS;
     const uint32_t tid = threadIdx.x;
@@ -1097,8 +1138,9 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
     uint64_t pre_tile = 0;
     uint64_t pace_next = 0;
     if (pace_ns && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(pace_next));
-    for (uint64_t i = blockIdx.x; i < ord.steps(); i += gridDim.x) {
-        const uint64_t tile = ord.tile(i);
+    StepIter it;
+    for (it.begin(dyn, &s_step); it.i < ord.steps(); it.next()) {
+        const uint64_t tile = ord.tile(it.i);
         if (tile == ~0ull) continue;
         const uint32_t before = c.seg;
         const bool fresh = !(tile >= c.lo_t && tile < c.hi_t);
@@ -1155,7 +1197,9 @@ k_gather_tma(const NzSegWork* __restrict__ work, const uint64_t* __restrict__ ti
             }
             // look-ahead: the checksum below takes longer than a tile's load, so the next tile of this CTA is requested
             // first (into the other stage; its previous stores are done once at most this tile's group is pending)
-            const uint64_t tile2 = i + gridDim.x < ord.steps() ? ord.tile(i + gridDim.x) : ~0ull;
+            // (with dynamic steps only thread 0 knows the next one - and only thread 0 acts on it)
+            const uint64_t step2 = it.peek();
+            const uint64_t tile2 = (tid == 0 || !dyn) && step2 < ord.steps() ? ord.tile(step2) : ~0ull;
             if (vt && tile2 != ~0ull) {
                 TileCursor c2 = c;
                 c2.seek(tile2, work, tile_begin, nseg);
@@ -1220,6 +1264,7 @@ struct TmaArgs {
     const uint32_t* seg_ver; NzVerWork* ver; const uint32_t* crc_tables;
     uint32_t pace_ns, spread;
     int stages_hint;         // 2 or 3 (0 = no opinion): see nz_launch_gather
+    uint32_t* dyn;           // zeroed step counter for dynamic tile scheduling, or nullptr
 };
 template <int STAGES, bool VERIFY>
 static cudaError_t launch_tma(const TmaArgs& a) {
@@ -1249,7 +1294,7 @@ static cudaError_t launch_tma(const TmaArgs& a) {
     int grid = a.grid;
     if (VERIFY && dev >= 0 && dev < 64 && max_grid[dev] > 0 && grid > max_grid[dev]) grid = max_grid[dev];
     k_gather_tma<STAGES, VERIFY><<<grid, NTH, smem, a.s>>>(a.work, a.tile_begin, a.chain_head, a.chain_next, a.nseg, t.tile,
-                                                                            a.seg_ver, a.ver, a.crc_tables, a.pace_ns, a.spread, (uint32_t)t.l2hint);
+                                                                            a.seg_ver, a.ver, a.crc_tables, a.pace_ns, a.spread, (uint32_t)t.l2hint, a.dyn);
     return cudaGetLastError();
 }
 static cudaError_t dispatch_tma(const TmaArgs& a) {
@@ -1279,16 +1324,16 @@ bool nz_gather_fuses_verify(int variant) { return variant == NZ_GATHER_TMA; }
 cudaError_t nz_launch_gather(int variant, const NzSegWork* work, const uint64_t* tile_begin, const uint32_t* chain_head,
                              const uint32_t* chain_next, uint32_t nseg, int grid, cudaStream_t s,
                              const uint32_t* seg_ver, NzVerWork* ver, const uint32_t* crc_tables, uint32_t pace_ns, uint32_t spread,
-                             int stages_hint) {
+                             int stages_hint, uint32_t* dyn) {
     if (variant == NZ_GATHER_TMA)
-        return dispatch_tma(TmaArgs{work, tile_begin, chain_head, chain_next, nseg, grid, s, nullptr, seg_ver, ver, crc_tables, pace_ns, spread, stages_hint});
-    k_gather<256, 8, 2><<<grid, 256, 0, s>>>(work, tile_begin, chain_head, chain_next, nseg, 256u * 8u * 16u, spread);
+        return dispatch_tma(TmaArgs{work, tile_begin, chain_head, chain_next, nseg, grid, s, nullptr, seg_ver, ver, crc_tables, pace_ns, spread, stages_hint, dyn});
+    k_gather<256, 8, 2><<<grid, 256, 0, s>>>(work, tile_begin, chain_head, chain_next, nseg, 256u * 8u * 16u, spread, dyn);
     return cudaGetLastError();
 }
 int nz_gather_blocks_per_sm(int variant) {
     int nb = 1;
     if (variant == NZ_GATHER_TMA) {
-        dispatch_tma(TmaArgs{nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, &nb, nullptr, nullptr, nullptr, 0, 0, 0});
+        dispatch_tma(TmaArgs{nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, &nb, nullptr, nullptr, nullptr, 0, 0, 0, nullptr});
         return nb;
     }
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gather<256, 8, 2>, 256, 0) != cudaSuccess || nb < 1) nb = 2;
@@ -1306,10 +1351,12 @@ cudaError_t nz_launch_crc_chunks(const uint8_t* p, uint64_t n, uint32_t* chunk_o
         // one full wave of resident CTAs, each striding over its share of the chunks: a grid of 8 per SM with 6 resident
         // (shared memory) ran a second, one-third-occupied wave that cost about a third of the kernel's time
         static int per_sm = 0;
-        if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_crc_chunks, 256, 0) != cudaSuccess || per_sm < 1)) per_sm = 4;
+        static const bool tree = [] { const char* e = getenv("NZ_CRC_TREE"); return !e || atoi(e) != 0; }();
+        if (!per_sm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_crc_chunks<true>, 256, 0) != cudaSuccess || per_sm < 1)) per_sm = 4;
         const uint64_t cap = (uint64_t)sm_count * per_sm;
         if (grid > cap) grid = cap;
-        k_crc_chunks<<<(unsigned)grid, 256, 0, s>>>(p, n, chunk_out, crc_tables);
+        if (tree) k_crc_chunks<true><<<(unsigned)grid, 256, 0, s>>>(p, n, chunk_out, crc_tables);
+        else k_crc_chunks<false><<<(unsigned)grid, 256, 0, s>>>(p, n, chunk_out, crc_tables);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

@@ -52,3 +52,27 @@ def test_reference_arm_prints_the_same_shape_on_cpu():
     assert r.returncode == 0, r.stderr[-800:]
     d = json.loads(r.stdout.strip().splitlines()[-1])
     check_line(d, reference=True)
+    # one config builder for both arms (the driver compares the two dicts), and the reference's own configuration -
+    # ONE worker (nginx.conf:2) - is what `value` reports; the all-core rate sits beside it
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.c2_config(64 << 20, 64, 1)
+    assert d["cpu_baseline"]["cores"] == 1 and d["all_cores"]["cores"] >= 1 and d["all_cores"]["value"] > 0
+
+
+def test_round2_default_line_carries_every_config():
+    """The committed round-2 default line (one B200): C2 headline + C1 / C3 / C5 / HTTP sections; the N=2 line adds the span
+    section (C4) at the named 125 GiB per GPU and HTTP through `nzproxy --devices`."""
+    d = json.loads(open(os.path.join(ROOT, "profiles", "r02_bench_default_a.json")).read().strip().splitlines()[-1])
+    check_line(d)
+    assert d["config"]["request_seed"] == 22 and d["cpu_baseline"]["cores"] == 1
+    assert d["c1"]["object_bytes"] == 169_001_437 and d["c1"]["reference_published_mbs"] == 323 and d["c1"]["c_abi_host_mbs"] > 323
+    assert d["http"]["c1"]["gpu"]["status_2xx"] > 0 and d["http"]["gpu"]["errors"] == 0
+    assert "C3" in d["c3"]["config"]["workload"] and d["c3"]["value"] > 150 and d["c3"]["c3"]["single_stream_ms"] < 3
+    assert "C5" in d["c5"]["config"]["workload"] and len(d["c5"]["sweep"]) == 6
+    d2 = json.loads(open(os.path.join(ROOT, "profiles", "r02_bench_default_n2.json")).read().strip().splitlines()[-1])
+    check_line(d2)
+    sp = d2["span"]
+    assert d2["n_gpus"] == 2 and sp["config"]["arena_gib_per_gpu"] == 125.0 and 0.5 < sp["ingress_frac_of_peak"] < 1.05
+    assert len(sp["per_rank"]) == 2 and sp["nccl_allgather"]["ms"] > 0
+    assert d2["http"]["gpu"]["devices"] == 2 and d2["http"]["gpu"]["errors"] == 0
