@@ -263,7 +263,7 @@ struct nz_ctx {
     bool fuse_verify = true; // env NZ_FUSE_VERIFY=0: NZ_GET_VERIFY re-reads every chunk in k_verify (A/B measurements)
     bool coalesce = true;   // env NZ_COALESCE=0 turns request coalescing off (A/B measurements)
     bool span_dynamic = true;  // K5: such waves hand out tiles dynamically (env NZ_SPAN_DYN=0: static split)
-    uint32_t span_spread = 64; // K5: rows of the spread tile order of waves with striped sources (env NZ_SPAN_SPREAD, 0 = plain order)
+    uint32_t span_spread = 256; // K5: rows of the spread tile order of waves with striped sources (env NZ_SPAN_SPREAD, 0 = plain order)
     int gather_variant = NZ_GATHER_TMA; // K2 kernel: bulk-copy engine staging (default) or the register path (env NZ_GATHER_VARIANT=0|reg)
     int inflate_grid;
     int inflate_seg_grid;

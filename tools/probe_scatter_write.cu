@@ -43,7 +43,9 @@ __global__ void __launch_bounds__(128) k_bulk(uint8_t* const* dst, int M, uint64
 }
 
 // read one tile (bulk load, 2 alternating stages), write it to M buffers: the coalesced gather in miniature
-__global__ void __launch_bounds__(128) k_copy(const uint8_t* src, uint8_t* const* dst, int M, uint64_t tiles) {
+// mode 0: source tile t from DRAM; 1: source always in L2 (the same 2 MiB over and over: is it the DRAM READS that cost?);
+// 2: DRAM source, but pulled into L2 in 2 MiB bulk prefetches 32 MiB ahead of use (long read bursts instead of one tile at a time)
+__global__ void __launch_bounds__(128) k_copy(const uint8_t* src, uint8_t* const* dst, int M, uint64_t tiles, int mode) {
     extern __shared__ __align__(128) uint8_t sb[];
     __shared__ __align__(8) uint64_t bar[2];
     if (threadIdx.x == 0) {
@@ -53,8 +55,15 @@ __global__ void __launch_bounds__(128) k_copy(const uint8_t* src, uint8_t* const
         for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
             const uint32_t buf = (uint32_t)__cvta_generic_to_shared(sb + slot * TILE), b = (uint32_t)__cvta_generic_to_shared(&bar[slot]);
             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            const uint8_t* sp = src + (mode == 1 ? (t & 63) : t) * TILE;
+            if (mode == 2 && (t & 63) == 0) {                      // this CTA drew the first tile of a 2 MiB chunk: prefetch the chunk 16 chunks ahead
+                const uint64_t pt = t + 16 * 64;
+                if (pt < tiles)
+                    for (int k = 0; k < 64; ++k)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src + (pt + k) * TILE), "r"(TILE) : "memory");
+            }
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(TILE) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(buf), "l"(src + t * TILE), "r"(TILE), "r"(b) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(buf), "l"(sp), "r"(TILE), "r"(b) : "memory");
             uint32_t done = 0;
             while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(b), "r"((phase >> slot) & 1u) : "memory");
             phase ^= 1u << slot;
@@ -81,29 +90,31 @@ int main(int argc, char** argv) {
     cudaMemset(srcbuf, 0x5a, 1ull << 30);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const bool only32 = argc > 2;
     for (int M : {1, 8, 32, 64}) {
+        if (only32 && M != 32) continue;
         const uint64_t per = total / M > (1ull << 30) ? (1ull << 30) : total / M, tiles = per / TILE;
         std::vector<uint8_t*> h(M);
         for (int m = 0; m < M; ++m) h[m] = pool + (uint64_t)m * per;
         uint8_t** d = nullptr;
         cudaMalloc(&d, M * sizeof(uint8_t*));
         cudaMemcpy(d, h.data(), M * sizeof(uint8_t*), cudaMemcpyHostToDevice);
-        for (int kind = 0; kind < 3; ++kind) {
+        for (int kind = 0; kind < 5; ++kind) {
             for (int cps : {2, 3}) {
                 float best = 1e30f;
                 for (int rep = 0; rep < 4; ++rep) {
                     cudaEventRecord(e0);
                     if (kind == 0) k_st<<<sms * cps, 256>>>(d, M, tiles);
                     else if (kind == 1) k_bulk<<<sms * cps, 128, TILE>>>(d, M, tiles);
-                    else k_copy<<<sms * cps, 128, 2 * TILE>>>(srcbuf, d, M, tiles);
+                    else k_copy<<<sms * cps, 128, 2 * TILE>>>(srcbuf, d, M, tiles, kind - 2);
                     cudaEventRecord(e1);
                     cudaEventSynchronize(e1);
                     float ms = 0;
                     cudaEventElapsedTime(&ms, e0, e1);
                     if (rep && ms < best) best = ms;
                 }
-                printf("M=%2d %-5s %d CTAs/SM: %7.3f ms  %7.1f GB/s written%s\n", M, kind == 0 ? "st.v4" : kind == 1 ? "bulk" : "copy", cps, best,
-                       (double)tiles * TILE * M / (best * 1e-3) / 1e9, kind == 2 ? " (+ 1 tile read per M written)" : "");
+                printf("M=%2d %-5s %d CTAs/SM: %7.3f ms  %7.1f GB/s written%s\n", M, kind == 0 ? "st.v4" : kind == 1 ? "bulk" : kind == 2 ? "copy" : kind == 3 ? "copyL2" : "copyPF", cps, best,
+                       (double)tiles * TILE * M / (best * 1e-3) / 1e9, kind >= 2 ? " (+ 1 tile read per M written)" : "");
             }
         }
         cudaFree(d);
