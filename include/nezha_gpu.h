@@ -179,6 +179,13 @@ int32_t nz_put_commit(nz_put* p, uint32_t expected_crc32c, int32_t has_expected,
  * NULL.  Every handle is consumed.  Returns NZ_OK when the call ran; per-object outcomes are in out_status. */
 int32_t nz_put_commit_many(nz_put** puts, uint32_t n, const uint32_t* expected_crc32c, const int32_t* has_expected,
                            uint32_t* out_crc32c, int32_t* out_status);
+/* Bulk fill of n identity objects that lie in ONE pinned window (nz_buf_alloc ... NZ_BUF_PINNED_HOST) at window+src_off[i],
+ * len[i] bytes each: a single host->device copy of the span they cover, one scatter launch into their extents, batched
+ * CRC-32C, one publish launch.  For cold starts with very many small objects (10^6 per GPU): nz_put_begin + nz_put_write per
+ * object cost a cudaMemcpyAsync each.  user_meta, out_crc32c, out_status (n entries each) may be NULL.  All or nothing on
+ * argument / allocation errors (NZ_EEXIST, NZ_ENOMEM ...: nothing is stored); per-object outcomes otherwise in out_status. */
+int32_t nz_put_packed(nz_ctx* ctx, uint32_t n, const uint8_t (*keys)[16], const uint64_t* src_off, const uint64_t* len,
+                      nz_buf* window, const uint64_t* user_meta, uint32_t* out_crc32c, int32_t* out_status);
 int32_t nz_put_abort(nz_put* p);
 int32_t nz_evict(nz_ctx* ctx, const uint8_t key[16]);
 

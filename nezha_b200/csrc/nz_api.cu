@@ -549,11 +549,12 @@ struct CommitBlock { void* host = nullptr; void* dev = nullptr; size_t cap = 0; 
 struct CommitBlockPool {
     std::mutex mu;
     std::vector<CommitBlock> free_;
+    int large_ = 0;
     bool get(size_t need, CommitBlock* out) {
         {
             std::lock_guard<std::mutex> g(mu);
             for (size_t i = 0; i < free_.size(); ++i)
-                if (free_[i].cap >= need) { *out = free_[i]; free_.erase(free_.begin() + i); return true; }
+                if (free_[i].cap >= need) { *out = free_[i]; if (free_[i].cap > 8192) --large_; free_.erase(free_.begin() + i); return true; }
         }
         CommitBlock b;
         b.cap = std::max<size_t>(round_up(need, 4096), 4096);
@@ -563,7 +564,8 @@ struct CommitBlockPool {
         return true;
     }
     void put(CommitBlock b) {
-        if (b.cap <= 8192) { std::lock_guard<std::mutex> g(mu); if (free_.size() < 64) { free_.push_back(b); return; } }
+        // small blocks (single commits) are kept in numbers, large ones (bulk commits) a few: pinning memory costs milliseconds
+        { std::lock_guard<std::mutex> g(mu); if (b.cap <= 8192 ? free_.size() < 64 : (b.cap <= (64u << 20) && large_++ < 4)) { free_.push_back(b); return; } }
         cudaFreeHost(b.host);
     }
 };
@@ -596,7 +598,13 @@ int32_t nz_put_commit_many(nz_put** puts, uint32_t n, const uint32_t* expected, 
     const size_t o_crc = o_ires + (size_t)n * sizeof(NzDevRes);
     const size_t o_status = o_crc + round_up((size_t)n * 4, 16);
     const size_t o_trailer = o_status + round_up((size_t)n * 4, 16);
-    const size_t need = o_trailer + (size_t)n * 8;
+    // batched CRC of the small objects of the batch (<= 64 chunks each): chunk jobs + one fold job per object
+    size_t n_cjobs = 0, n_fjobs = 0;
+    if (n > 1)
+        for (uint32_t i = 0; i < n; ++i) if (puts[i]->n_chunks <= 64) { n_cjobs += puts[i]->n_chunks; ++n_fjobs; }
+    const size_t o_cjobs = round_up(o_trailer + (size_t)n * 8, 16);
+    const size_t o_fjobs = o_cjobs + n_cjobs * sizeof(NzCrcJob);
+    const size_t need = o_fjobs + n_fjobs * sizeof(NzFoldJob);
     NzPubItem* items = nullptr; NzIdxJob* jobs = nullptr; NzIdxResult* results = nullptr; NzDevRes* ires = nullptr;
     uint32_t* crcs = nullptr; int32_t* pst = nullptr; uint32_t* trailers = nullptr;
     auto dev_of = [&](const void* hostp) { return (void*)((char*)blk.dev + ((const char*)hostp - (const char*)blk.host)); };
@@ -607,13 +615,42 @@ int32_t nz_put_commit_many(nz_put** puts, uint32_t n, const uint32_t* expected, 
     crcs = (uint32_t*)((char*)blk.host + o_crc); pst = (int32_t*)((char*)blk.host + o_status);
     trailers = (uint32_t*)((char*)blk.host + o_trailer);
     // ---- 1. chunk table + whole-object CRC-32C of every object, each on the stream that carries its fill copies ----
-    for (uint32_t i = 0; i < n; ++i) {
-        nz_put* p = puts[i];
-        crcs[i] = 0;
-        uint32_t* tab = reinterpret_cast<uint32_t*>(c->arena + p->crc_tab_off);
-        e = nz_launch_crc_chunks(c->arena + p->arena_off, p->stored_len, tab, (uint32_t*)dev_of(&crcs[i]), c->crc_tables, c->sm_count, p->stream);
-        c->launches += 2;
-        if (e != cudaSuccess) { rc = cuda_fail(e, "crc kernels"); goto done; }
+    {
+        NzCrcJob* cj = (NzCrcJob*)((char*)blk.host + o_cjobs);
+        NzFoldJob* fj = (NzFoldJob*)((char*)blk.host + o_fjobs);
+        size_t nc = 0, nf = 0;
+        // small objects (<= 64 chunks): two launches per fill STREAM of the batch instead of two per object (the checksum must
+        // run behind that object's own copies; nz_put_begin spreads puts over the stream pool)
+        std::vector<cudaStream_t> streams;
+        if (n_fjobs)
+            for (uint32_t i = 0; i < n; ++i)
+                if (puts[i]->n_chunks <= 64 && std::find(streams.begin(), streams.end(), puts[i]->stream) == streams.end()) streams.push_back(puts[i]->stream);
+        for (cudaStream_t sx : streams) {
+            const size_t c0 = nc, f0 = nf;
+            for (uint32_t i = 0; i < n; ++i) {
+                nz_put* p = puts[i];
+                if (p->n_chunks > 64 || p->stream != sx) continue;
+                uint32_t* tab = reinterpret_cast<uint32_t*>(c->arena + p->crc_tab_off);
+                for (uint32_t k = 0; k < p->n_chunks; ++k) {
+                    const uint64_t off = (uint64_t)k * NZ_CRC_CHUNK;
+                    cj[nc++] = NzCrcJob{(uint64_t)(c->arena + p->arena_off + off), (uint32_t)std::min<uint64_t>(NZ_CRC_CHUNK, p->stored_len - off), 0, (uint64_t)(tab + k)};
+                }
+                crcs[i] = 0;
+                fj[nf++] = NzFoldJob{(uint64_t)tab, p->stored_len, (uint64_t)dev_of(&crcs[i])};
+            }
+            e = nz_launch_crc_jobs((const NzCrcJob*)dev_of(cj + c0), (uint32_t)(nc - c0), (const NzFoldJob*)dev_of(fj + f0), (uint32_t)(nf - f0), c->crc_tables, c->sm_count, sx);
+            c->launches += 2;
+            if (e != cudaSuccess) { rc = cuda_fail(e, "batched crc kernels"); goto done; }
+        }
+        for (uint32_t i = 0; i < n; ++i) {
+            nz_put* p = puts[i];
+            if (n_fjobs && p->n_chunks <= 64) continue;
+            crcs[i] = 0;
+            uint32_t* tab = reinterpret_cast<uint32_t*>(c->arena + p->crc_tab_off);
+            e = nz_launch_crc_chunks(c->arena + p->arena_off, p->stored_len, tab, (uint32_t*)dev_of(&crcs[i]), c->crc_tables, c->sm_count, p->stream);
+            c->launches += 2;
+            if (e != cudaSuccess) { rc = cuda_fail(e, "crc kernels"); goto done; }
+        }
     }
     {
         std::vector<cudaStream_t> seen;
@@ -776,6 +813,86 @@ done:
         if (out_status) out_status[i] = st[i];
         put_release(puts[i], st[i] != NZ_OK);
     }
+    if (blk.host) g_commit_blocks.put(blk);
+    return rc;
+}
+
+// Bulk fill of many (small) identity objects that sit in ONE pinned window: one host->device copy of the span they
+// cover, one scatter launch (the K2 gather kernel, staging -> extents), then nz_put_commit_many (batched CRC-32C, one
+// publish launch).  The per-object cudaMemcpyAsync of nz_put_write (~2-3 us each) is what bounded 10^6-object loads.
+int32_t nz_put_packed(nz_ctx* c, uint32_t n, const uint8_t (*keys)[16], const uint64_t* src_off, const uint64_t* len, nz_buf* window,
+                      const uint64_t* user_meta, uint32_t* out_crc, int32_t* out_status) {
+    if (!c || !n || !keys || !src_off || !len || !window || !window->host) return NZ_EINVAL;
+    CK(cudaSetDevice(c->device));
+    uint64_t lo = ~0ull, hi = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (src_off[i] > window->size || len[i] > window->size - src_off[i]) return NZ_EINVAL;
+        if (!len[i]) continue;
+        lo = std::min(lo, src_off[i]);
+        hi = std::max(hi, src_off[i] + len[i]);
+    }
+    if (lo == ~0ull) { lo = 0; hi = 0; }
+    lo &= ~255ull;                                    // keep the 16 B phase of every object: staging offset == window offset - lo
+    std::vector<nz_put*> puts(n, nullptr);
+    std::vector<int32_t> st(n, NZ_OK);
+    uint32_t made = 0;
+    int32_t rc = NZ_OK;
+    for (; made < n; ++made) {
+        rc = nz_put_begin(c, keys[made], len[made], len[made], NZ_ENC_IDENTITY, user_meta ? user_meta[made] : 0, &puts[made]);
+        if (rc != NZ_OK) break;
+    }
+    if (rc != NZ_OK) {
+        for (uint32_t i = 0; i < made; ++i) nz_put_abort(puts[i]);
+        return rc;
+    }
+    cudaStream_t sx = puts[0]->stream;
+    for (uint32_t i = 0; i < n; ++i) puts[i]->stream = sx;           // one stream carries the copy, the scatter and the checksums
+    char* stage = nullptr;
+    CommitBlock blk;
+    const size_t o_work = 0, o_tiles = round_up((size_t)n * sizeof(NzSegWork), 256), o_head = o_tiles + round_up((size_t)(n + 1) * 8, 256);
+    const size_t need = o_head + round_up((size_t)n * 8, 256);
+    cudaError_t e = cudaSuccess;
+    const uint32_t tb = nz_gather_tile_bytes(c->gather_variant);
+    if (hi > lo) {
+        if (!g_commit_blocks.get(need, &blk)) rc = NZ_ENOMEM;
+        const size_t span = round_up((size_t)(hi - lo), 256);
+        if (rc == NZ_OK && (e = cudaMallocAsync((void**)&stage, span + need, sx)) != cudaSuccess) { cudaGetLastError(); rc = NZ_ENOMEM; }
+        if (rc == NZ_OK) {
+            NzSegWork* w = (NzSegWork*)((char*)blk.host + o_work);
+            uint64_t* tbeg = (uint64_t*)((char*)blk.host + o_tiles);
+            uint32_t* head = (uint32_t*)((char*)blk.host + o_head);
+            uint64_t tiles = 0;
+            for (uint32_t i = 0; i < n; ++i) {
+                w[i].src = (uint64_t)(stage + (src_off[i] - lo));
+                w[i].dst = (uint64_t)(c->arena + puts[i]->arena_off);      // 4 KiB aligned: vstart 0
+                w[i].len = len[i];
+                w[i].vstart = 0;
+                tbeg[i] = tiles;
+                tiles += (len[i] + tb - 1) / tb;
+                head[i] = 0xFFFFFFFFu;
+                head[n + i] = 0xFFFFFFFFu;
+            }
+            tbeg[n] = tiles;
+            char* lists = stage + span;                               // the work lists travel with the data: the gather binary-searches them per tile
+            e = cudaMemcpyAsync(stage, (const char*)window->host + lo, hi - lo, cudaMemcpyHostToDevice, sx);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(lists, blk.host, need, cudaMemcpyHostToDevice, sx);
+            if (e == cudaSuccess && tiles) {
+                const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)c->gather_grid);
+                e = nz_launch_gather(c->gather_variant, (const NzSegWork*)(lists + o_work), (const uint64_t*)(lists + o_tiles), (const uint32_t*)(lists + o_head),
+                                     (const uint32_t*)(lists + o_head) + n, n, grid, sx);
+                c->launches += 1;
+            }
+            if (e == cudaSuccess) e = cudaFreeAsync(stage, sx);
+            if (e != cudaSuccess) rc = cuda_fail(e, "nz_put_packed");
+        }
+    }
+    if (rc != NZ_OK) {
+        cudaStreamSynchronize(sx);
+        for (uint32_t i = 0; i < n; ++i) nz_put_abort(puts[i]);
+        if (blk.host) g_commit_blocks.put(blk);
+        return rc;
+    }
+    rc = nz_put_commit_many(puts.data(), n, nullptr, nullptr, out_crc, out_status);      // syncs the stream: the work list may go after it
     if (blk.host) g_commit_blocks.put(blk);
     return rc;
 }

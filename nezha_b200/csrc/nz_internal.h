@@ -174,6 +174,9 @@ constexpr int NZ_CRC_FUSE_WORDS = 256 + 32;
 constexpr int NZ_CRC_TABLE_WORDS = NZ_CRC_FUSE_OFF + NZ_CRC_FUSE_WORDS;
 constexpr uint32_t NZ_VER_FUSED = 0x80000000u;   // in seg
 constexpr uint32_t NZ_VER_NOSEG = 0x7FFFFFFFu;   // seg & ~FUSED: no copy slice behind this entry (inflate input)
+// batched commit of small objects: one chunk to checksum / one object to fold
+struct NzCrcJob { uint64_t ptr; uint32_t len; uint32_t pad; uint64_t out; };     // out: device address of the chunk-table entry
+struct NzFoldJob { uint64_t tab; uint64_t len; uint64_t whole_out; };              // tab: the object's chunk table; whole_out: device address of a u32
 struct __align__(16) NzVerWork {
     uint64_t ptr;
     uint32_t len;
@@ -366,6 +369,8 @@ cudaError_t nz_launch_gather(int variant, const NzSegWork* work, const uint64_t*
 bool nz_gather_fuses_verify(int variant);
 uint32_t nz_gather_tile_bytes(int variant);
 cudaError_t nz_launch_verify(const NzPlanArgs& a, const uint32_t* crc_tables, int grid, cudaStream_t s);
+cudaError_t nz_launch_crc_jobs(const NzCrcJob* jobs, uint32_t n_chunks, const NzFoldJob* folds, uint32_t n_objects, const uint32_t* crc_tables,
+                               int sm_count, cudaStream_t s);
 cudaError_t nz_launch_crc_chunks(const uint8_t* p, uint64_t n, uint32_t* chunk_out, uint32_t* whole_out,
                                  const uint32_t* crc_tables, int sm_count, cudaStream_t s);
 cudaError_t nz_launch_inflate(const NzInflWork* infl, uint64_t* meta, uint32_t* counters, NzDevRes* res,

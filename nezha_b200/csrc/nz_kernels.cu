@@ -12,6 +12,7 @@
 // (/root/reference/examples/demo/nginx.conf:38) and its cache-file read loop +
 // range filter.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <stdint.h>
 #include <stdlib.h>
 
@@ -857,6 +858,42 @@ k_crc_chunks(const uint8_t* __restrict__ p, uint64_t n, uint32_t* __restrict__ c
     }
 }
 
+// Batched form for bulk loads of small objects (nz_put_commit_many): one launch checksums every chunk of every object of
+// the batch (a flat job list), one more folds each object's chunks (one thread per object).  Per-object launches cost
+// ~2 us each on the host: at 10^6 objects they were half of the fill time.
+__global__ void __launch_bounds__(256, 4)
+k_crc_jobs(const NzCrcJob* __restrict__ jobs, uint32_t n, const uint32_t* __restrict__ tables) {
+    __shared__ uint32_t sT[4 * 256];
+    __shared__ uint32_t sZS8[1024 * 8];
+    __shared__ uint32_t sred[8];
+    const uint32_t* fast = tables + 16 * 256;
+    for (uint32_t i = threadIdx.x; i < 1024; i += 256) sT[i] = tables[i];
+    crc_load_fast_tables(sZS8, fast);
+    __syncthreads();
+    for (uint32_t j = blockIdx.x; j < n; j += gridDim.x) {
+        const NzCrcJob jb = jobs[j];
+        const uint8_t* p = reinterpret_cast<const uint8_t*>(jb.ptr);
+        const uint32_t crc = (jb.len == NZ_CRC_CHUNK && (jb.ptr & 15u) == 0) ? block_crc_chunk64k<0>(p, sZS8, sT, fast + 1024, sred)
+                                                                              : block_crc_chunk<0>(p, jb.len, sT, sred);
+        if (threadIdx.x == 0) *reinterpret_cast<uint32_t*>(jb.out) = crc;
+    }
+}
+__global__ void __launch_bounds__(128)
+k_crc_fold_jobs(const NzFoldJob* __restrict__ jobs, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const NzFoldJob jb = jobs[i];
+    const uint32_t* tab = reinterpret_cast<const uint32_t*>(jb.tab);
+    const uint64_t nch = (jb.len + NZ_CRC_CHUNK - 1) / NZ_CRC_CHUNK;
+    uint32_t acc = 0;                                              // CRC-32C of the empty string
+    const uint32_t x64k = c_x8pow[0][16];
+    for (uint64_t c = 0; c < nch; ++c) {
+        const uint64_t cl = min((uint64_t)NZ_CRC_CHUNK, jb.len - c * NZ_CRC_CHUNK);
+        acc = c == 0 ? tab[0] : (gf_mul<0>(cl == NZ_CRC_CHUNK ? x64k : gf_xpow8<0>(cl), acc) ^ tab[c]);
+    }
+    *reinterpret_cast<uint32_t*>(jb.whole_out) = acc;
+}
+
 // whole-object CRC = sum_i chunk_i * x^(8 * bytes_after_i): each thread folds a
 // contiguous run of chunks Horner-style, then one shift to the object end.
 __global__ void __launch_bounds__(1024)
@@ -1361,6 +1398,17 @@ cudaError_t nz_launch_crc_chunks(const uint8_t* p, uint64_t n, uint32_t* chunk_o
         if (e != cudaSuccess) return e;
     }
     k_crc_fold<<<1, 1024, 0, s>>>(chunk_out, n, whole_out);
+    return cudaGetLastError();
+}
+
+cudaError_t nz_launch_crc_jobs(const NzCrcJob* jobs, uint32_t n_chunks, const NzFoldJob* folds, uint32_t n_objects, const uint32_t* crc_tables,
+                               int sm_count, cudaStream_t s) {
+    if (n_chunks) {
+        k_crc_jobs<<<(unsigned)std::min<uint64_t>(n_chunks, (uint64_t)sm_count * 4), 256, 0, s>>>(jobs, n_chunks, crc_tables);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    if (n_objects) k_crc_fold_jobs<<<(n_objects + 127) / 128, 128, 0, s>>>(folds, n_objects);
     return cudaGetLastError();
 }
 

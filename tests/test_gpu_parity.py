@@ -542,3 +542,28 @@ def test_concurrent_put_file_shares_bounce_lanes(tmp_path):
     st = z.stats()
     assert st.file_cufile_bytes + st.file_bounce_bytes == sum(sizes)
     z.close()
+
+
+def test_put_packed_bulk_fill_of_small_objects():
+    """nz_put_packed: hundreds of objects of every small size and byte phase through one pinned window - one copy, one scatter
+    launch, batched CRC-32C.  Every object is then found, checksummed like the oracle does, and served bit-exact."""
+    rng = np.random.default_rng(77)
+    sizes = [0, 1, 15, 16, 17, 4095, 4096, 4097, 65_535, 65_536, 65_537, 200_003, 300_000] + [int(x) for x in rng.integers(1, 150_000, 300)]
+    objs = []
+    for i, n in enumerate(sizes):
+        objs.append((wl.key128(b"packed/%d" % i), wl.synth_bytes(n, seed=8_000 + i).tobytes()))
+    with nz.Zone(device=0, arena_bytes=256 << 20, max_objects=2048) as z:
+        crcs = z.put_packed(objs)
+        assert crcs == [o.crc32c(d) for _, d in objs]
+        ext = z.lookup([k for k, _ in objs])
+        assert all(e.status == capi.NZ_OK and e.stored_length == len(d) and e.crc32c == c for e, (_, d), c in zip(ext, objs, crcs))
+        for j in (0, 1, 3, 7, 9, 10, 11, 12, 50, 311):
+            res, body = z.get(objs[j][0], flags=capi.NZ_GET_VERIFY)
+            assert res.status == capi.NZ_OK and body == objs[j][1], j
+        res, body = z.get(objs[12][0], segs=[(123_457, 100_001)])
+        assert res.status == capi.NZ_OK and body == o.serve_slice_mem(objs[12][1], 123_457, 100_001)
+        # the second load of the same keys is refused as a whole (nothing half-stored), the zone still serves
+        with pytest.raises(nz.NezhaError):
+            z.put_packed(objs[:3])
+        res, body = z.get(objs[2][0])
+        assert res.status == capi.NZ_OK and body == objs[2][1]

@@ -77,6 +77,44 @@ __global__ void __launch_bounds__(128) k_copy(const uint8_t* src, uint8_t* const
     }
 }
 
+// three stages of TB bytes, the NEXT tile's load issued before the current tile's stores: in the SM's TMA queue the load sits
+// ahead of 32 stores instead of behind them, so it has landed by the time the stores have been issued
+template <uint32_t TB>
+__global__ void __launch_bounds__(128) k_copy_ahead(const uint8_t* src, uint8_t* const* dst, int M, uint64_t tiles, int l2src) {
+    extern __shared__ __align__(128) uint8_t sb[];
+    __shared__ __align__(8) uint64_t bar[3];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 3; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((uint32_t)__cvta_generic_to_shared(&bar[i])));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+        uint32_t phase = 0, slot = 0;
+        auto issue = [&](uint64_t t, uint32_t sl) {
+            const uint32_t buf = (uint32_t)__cvta_generic_to_shared(sb + sl * TB), b = (uint32_t)__cvta_generic_to_shared(&bar[sl]);
+            const uint8_t* sp = src + (l2src ? (t & 63) : t) * (uint64_t)TB;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(TB) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(buf), "l"(sp), "r"(TB), "r"(b) : "memory");
+        };
+        uint64_t t = blockIdx.x;
+        if (t < tiles) issue(t, 0);
+        for (; t < tiles; t += gridDim.x) {
+            const uint32_t nslot = slot == 2 ? 0 : slot + 1;
+            if (t + gridDim.x < tiles) {                       // stage nslot was read by the stores two tiles back
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                issue(t + gridDim.x, nslot);
+            }
+            const uint32_t buf = (uint32_t)__cvta_generic_to_shared(sb + slot * TB), b = (uint32_t)__cvta_generic_to_shared(&bar[slot]);
+            uint32_t done = 0;
+            while (!done) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(b), "r"((phase >> slot) & 1u) : "memory");
+            phase ^= 1u << slot;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            for (int m = 0; m < M; ++m)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst[m] + t * (uint64_t)TB), "r"(buf), "r"(TB) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            slot = nslot;
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
 int main(int argc, char** argv) {
     const uint64_t total = (argc > 1 ? strtoull(argv[1], nullptr, 10) : 32ull) << 30;
     int sms = 0;
@@ -116,6 +154,29 @@ int main(int argc, char** argv) {
                 printf("M=%2d %-5s %d CTAs/SM: %7.3f ms  %7.1f GB/s written%s\n", M, kind == 0 ? "st.v4" : kind == 1 ? "bulk" : kind == 2 ? "copy" : kind == 3 ? "copyL2" : "copyPF", cps, best,
                        (double)tiles * TILE * M / (best * 1e-3) / 1e9, kind >= 2 ? " (+ 1 tile read per M written)" : "");
             }
+        }
+        if (M == 32) {
+            auto run_ahead = [&](auto kern, uint32_t tb, const char* name, int l2src) {
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * tb));
+                const uint64_t tl = per / tb;
+                for (int cps : {2, 3}) {
+                    float best = 1e30f;
+                    for (int rep = 0; rep < 4; ++rep) {
+                        cudaEventRecord(e0);
+                        kern<<<sms * cps, 128, 3 * tb>>>(srcbuf, d, M, tl, l2src);
+                        cudaEventRecord(e1);
+                        cudaEventSynchronize(e1);
+                        float ms = 0;
+                        cudaEventElapsedTime(&ms, e0, e1);
+                        if (rep && ms < best) best = ms;
+                    }
+                    printf("M=%2d %-12s %d CTAs/SM: %7.3f ms  %7.1f GB/s written (+ 1 tile read per M written)\n", M, name, cps, best, (double)tl * tb * M / (best * 1e-3) / 1e9);
+                }
+            };
+            run_ahead(k_copy_ahead<24576>, 24576, "ahead3x24K", 0);
+            run_ahead(k_copy_ahead<32768>, 32768, "ahead3x32K", 0);
+            run_ahead(k_copy_ahead<16384>, 16384, "ahead3x16K", 0);
+            run_ahead(k_copy_ahead<24576>, 24576, "ahead3x24K-L2", 1);
         }
         cudaFree(d);
     }
