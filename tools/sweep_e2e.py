@@ -18,7 +18,7 @@ print("cudaMemcpyAsync D2H (copy engine): %.1f GB/s" % (5 * (1 << 30) / (e0.elap
 del x, h
 for g in (4, 8, 16, 32, 64, 128, 296):
     env = dict(os.environ, NZ_HOST_GRID=str(g))
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--no-cpu", "--no-http"], env=env, capture_output=True, text=True)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--no-cpu", "--no-http", "--no-sections"], env=env, capture_output=True, text=True)
     line = [l for l in r.stdout.splitlines() if l.startswith("{")]
     if not line:
         print(g, "FAILED", r.stderr[-200:]); continue
