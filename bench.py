@@ -30,7 +30,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WINDOW = 8 << 20          # e2e: per-connection pinned window (double buffered)
+WINDOW = int(os.environ.get("NZ_BENCH_WINDOW_KIB", "8192")) << 10          # e2e: per-connection pinned window (double buffered)
 FALLBACK_HBM_GBS = 6650.0
 
 
@@ -423,7 +423,7 @@ def run_ours(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
         e2e = {"value": payload_all * e_steps / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "steps": e_steps, "window_bytes": WINDOW, "note": "two waves in flight (double-buffered 8 MiB windows per connection, reused only after their wave completed); each wave "
+               "steps": e_steps, "window_bytes": WINDOW, "note": "two waves in flight (double-buffered windows per connection, reused only after their wave completed); each wave "
                "is gathered into an HBM staging slot and moved to the pinned windows by the copy engine (PCIe D2H in the timed region; "
                "NZ_HOST_DMA=0: the gather kernel stores across PCIe itself); request descriptors are read by the plan kernel from pinned host memory"}
         # ---- TTFB: first 256 KiB of each GET, unloaded, host clock around submit+wait ---
