@@ -20,7 +20,7 @@
 // Members are indexed once at nz_put_commit (k_inflate_index, nz_internal.h "Checkpoint index");
 // a GET then runs k_inflate_seg:
 //   * one warp per SEGMENT (~128 KiB of output), segments of one member decode concurrently;
-//   * inside a segment the warp walks GROUPS of <= 32 sub-segments of <= 64 tokens each:
+//   * inside a segment the warp walks GROUPS of <= 32 sub-segments of <= 32 tokens each:
 //     phase 1, every LANE Huffman-decodes its own sub-segment from its recorded bit offset (tables
 //     shared by the warp), stores its literals straight to their final place and queues its matches
 //     in shared memory; phase 2, the warp resolves the queued LZ77 copies in stream order, eight

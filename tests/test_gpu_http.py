@@ -173,6 +173,12 @@ LOG += [
     ("POST", "www.cs.toronto.edu", "/~kriz/cifar-100-python.tar.gz", {}),
     ("GET", "www.cs.toronto.edu", "/../etc/passwd", {}),
     ("GET", "images.cocodataset.org", "/zips/text.json.gz", {"Accept-Encoding": "gzip"}),
+    # SPEC section Z (what the second restatement changed), over the wire against both servers
+    ("GET", "www.cs.toronto.edu", "/~kriz/cifar-100-python.tar.gz", {"If-Unmodified-Since": "not a date", "Range": "bytes=0-9"}),      # Z1: 412
+    ("GET", "www.cs.toronto.edu", "/~kriz/cifar-100-python.tar.gz", {"If-Unmodified-Since": LM, "Range": "bytes=0-9"}),                # 206
+    ("GET", "www.cs.toronto.edu", "/~kriz/cifar-100-python.tar.gz", {"If-Unmodified-Since": "Wed, 00 Nov 2018 15:20:01 GMT"}),         # Z4: day 00 parses, earlier than LM: 412
+    ("GET", "storage.googleapis.com:80/x", "/bucket/big.bin", {}),                                                                    # Z3: '/' after the port: 400
+    ("GET", "storage.googleapis.com", "/bucket/noranges.bin", {"Range": "bytes=5-9", "If-Range": '"nr"'}),                             # Z5: still the whole object
 ]
 
 
