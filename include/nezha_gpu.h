@@ -138,7 +138,11 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out);
 int32_t nz_shutdown(nz_ctx* ctx);
 
 /* ---- C-owned I/O memory -------------------------------------------------- */
+/* NZ_BUF_PINNED_HOST pages are placed on the host memory node next to ctx's GPU whatever thread calls (on a
+ * two-socket node a window on the far socket moves at about a third of the near one); NZ_NUMA=0 turns that off. */
 int32_t  nz_buf_alloc(nz_ctx* ctx, uint64_t bytes, int32_t kind, nz_buf** out);
+/* host memory node next to ctx's GPU (-1: unknown): callers that pool windows keep one pool per node */
+int32_t  nz_numa_node(nz_ctx* ctx);
 /* wrap device memory owned by the caller (e.g. a framework tensor); not freed */
 int32_t  nz_buf_wrap_device(nz_ctx* ctx, void* devptr, uint64_t bytes, nz_buf** out);
 void*    nz_buf_ptr(nz_buf* b);       /* host address (NULL for device buffers)   */

@@ -24,7 +24,7 @@ NZ_CRC_CHUNK = 65536
 SYMBOLS = [
     "nz_abi_version", "nz_strerror", "nz_last_error", "nz_init", "nz_shutdown",
     "nz_buf_alloc", "nz_buf_wrap_device", "nz_buf_ptr", "nz_buf_devptr", "nz_buf_size", "nz_buf_free", "nz_buf_read", "nz_buf_write",
-    "nz_put_begin", "nz_put_write", "nz_put_sync", "nz_put_write_device", "nz_put_file", "nz_cufile_status", "nz_put_commit", "nz_put_commit_many", "nz_put_packed", "nz_put_abort",
+    "nz_put_begin", "nz_put_write", "nz_put_sync", "nz_put_write_device", "nz_put_file", "nz_cufile_status", "nz_numa_node", "nz_put_commit", "nz_put_commit_many", "nz_put_packed", "nz_put_abort",
     "nz_evict", "nz_lookup", "nz_get_submit", "nz_get_wait", "nz_get_poll", "nz_ticket_elapsed_ms",
     "nz_ticket_gather_ms", "nz_ticket_inflate_ms", "nz_ticket_free", "nz_get_stats", "nz_set_profiling", "nz_set_host_rate", "nz_crc32c_device", "nz_debug_poke", "nz_shard_of",
     "nz_arena_ipc_export", "nz_peer_attach", "nz_extent_location", "nz_put_striped", "nz_crc32c_combine",
@@ -100,6 +100,8 @@ def load() -> C.CDLL:
     L.nz_strerror.argtypes = [C.c_int32]
     L.nz_strerror.restype = C.c_char_p
     L.nz_last_error.restype = C.c_char_p
+    L.nz_numa_node.restype = C.c_int32
+    L.nz_numa_node.argtypes = [C.c_void_p]
     L.nz_cufile_status.restype = C.c_char_p
     L.nz_cufile_status.argtypes = []
     L.nz_init.argtypes = [C.POINTER(Config), C.POINTER(vp)]

@@ -6,10 +6,12 @@
 // entry point fails with NZ_ECUDA.
 #include <cuda_runtime.h>
 #include <errno.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <sys/syscall.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -74,6 +76,82 @@ uint32_t nz_shard_of(const uint8_t key[16], uint32_t shard_count) {
     return (uint32_t)(rd64(key) % shard_count);
 }
 
+
+// ---------------------------------------------------------------------------
+// host memory placement
+// ---------------------------------------------------------------------------
+// A pinned window is written by the GPU's copy engine through the PCIe root of ONE socket.  Pages on the other
+// socket cost a trip over the inter-socket link for every byte (measured on the 2-socket B200 node: a window
+// placed on the far node moves at ~0.37x the near one, profiles/r02_d2h_probe_n8.txt).  Callers of the C ABI are
+// goroutines / connection threads that run anywhere, so the library places the pages itself: while it allocates
+// and pins, the calling thread prefers the GPU's node (set_mempolicy; where a container's seccomp profile refuses
+// that, the thread is moved onto that node's CPUs for the duration, so first touch lands there).
+static int read_int_file(const char* path, int dflt) {
+    FILE* f = fopen(path, "r");
+    if (!f) return dflt;
+    int v = dflt;
+    if (fscanf(f, "%d", &v) != 1) v = dflt;
+    fclose(f);
+    return v;
+}
+static bool parse_cpulist(const char* path, cpu_set_t* out) {
+    CPU_ZERO(out);
+    FILE* f = fopen(path, "r");
+    if (!f) return false;
+    char buf[4096];
+    const bool got = fgets(buf, sizeof buf, f) != nullptr;
+    fclose(f);
+    if (!got) return false;
+    int n = 0;
+    for (char* p = buf; *p && *p != '\n';) {
+        char* e;
+        long a = strtol(p, &e, 10), b = a;
+        if (e == p) break;
+        if (*e == '-') { p = e + 1; b = strtol(p, &e, 10); }
+        for (long i = a; i <= b && i < CPU_SETSIZE; ++i) { CPU_SET((int)i, out); ++n; }
+        p = (*e == ',') ? e + 1 : e;
+    }
+    return n > 0;
+}
+static void detect_numa(nz_ctx* c) {
+    if (const char* ev = getenv("NZ_NUMA")) if (atoi(ev) == 0) return;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, c->device) != cudaSuccess) { cudaGetLastError(); return; }
+    for (char* p = bus; *p; ++p) if (*p >= 'A' && *p <= 'Z') *p = (char)(*p - 'A' + 'a');
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    const int node = read_int_file(path, -1);
+    if (node < 0 || node >= 64) return;
+    c->numa_node = node;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d", node ? 0 : 1);
+    c->numa_place = access(path, F_OK) == 0;             // a second node exists: placement matters
+}
+struct NumaScope {
+    bool policy = false, moved = false;
+    cpu_set_t saved;
+    explicit NumaScope(const nz_ctx* c) {
+        if (!c->numa_place) return;
+#ifdef SYS_set_mempolicy
+        unsigned long mask = 1ul << c->numa_node;
+        if (syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, sizeof(mask) * 8 + 1) == 0) { policy = true; return; }
+#endif
+        char path[96];
+        cpu_set_t want, both;
+        snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", c->numa_node);
+        if (!parse_cpulist(path, &want) || sched_getaffinity(0, sizeof saved, &saved) != 0) return;
+        CPU_AND(&both, &want, &saved);
+        if (CPU_COUNT(&both) == 0 || CPU_EQUAL(&both, &saved)) return;      // not allowed on that node, or already only there
+        moved = sched_setaffinity(0, sizeof both, &both) == 0;
+    }
+    ~NumaScope() {
+#ifdef SYS_set_mempolicy
+        if (policy) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+#endif
+        if (moved) sched_setaffinity(0, sizeof saved, &saved);
+    }
+};
+int32_t nz_numa_node(nz_ctx* c) { return c ? c->numa_node : -1; }
+
 // ---------------------------------------------------------------------------
 // lifecycle
 // ---------------------------------------------------------------------------
@@ -95,6 +173,7 @@ int32_t nz_init(const nz_config* cfg, nz_ctx** out) {
     c->cfg = *cfg;
     c->device = cfg->device;
     c->sm_count = prop.multiProcessorCount;
+    detect_numa(c);
     if (c->cfg.shard_count == 0) c->cfg.shard_count = 1;
     if (c->cfg.shard_index >= c->cfg.shard_count) { delete c; return NZ_EINVAL; }
     if (c->cfg.max_objects == 0) c->cfg.max_objects = 1u << 16;
@@ -222,6 +301,7 @@ int32_t nz_buf_alloc(nz_ctx* c, uint64_t bytes, int32_t kind, nz_buf** out) {
     b->ctx = c; b->size = bytes; b->kind = kind; b->owned = true; b->host = nullptr; b->dev = nullptr;
     cudaError_t e;
     if (kind == NZ_BUF_PINNED_HOST) {
+        NumaScope near(c);
         e = cudaHostAlloc(&b->host, bytes + 256, cudaHostAllocMapped | cudaHostAllocPortable);
         if (e == cudaSuccess) e = cudaHostGetDevicePointer(&b->dev, b->host, 0);
     } else if (kind == NZ_BUF_DEVICE) {
@@ -434,6 +514,7 @@ static int32_t bounce_copy(nz_put* p, uint64_t dst_off, uint64_t len, const std:
         std::unique_lock<std::mutex> g(c->put_mu);
         if (!c->bounce[0]) {
             c->bounce_bytes = BUF * 2 * NZ_BOUNCE_LANES;
+            NumaScope near(c);
             CK(cudaHostAlloc(&c->bounce[0], c->bounce_bytes, cudaHostAllocPortable));
             c->bounce[1] = c->bounce[0];
             c->lane_busy.assign(NZ_BOUNCE_LANES, 0);

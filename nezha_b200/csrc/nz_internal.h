@@ -259,6 +259,8 @@ struct nz_ctx {
     nz_config cfg;
     int device;
     int sm_count;
+    int numa_node = -1;                 // host memory node next to this GPU (sysfs), -1 unknown / single node
+    bool numa_place = false;            // pinned buffers of this context are placed on numa_node (NZ_NUMA=0 turns it off)
     int gather_grid;       // persistent grid size for k_gather
     int gather_grid3 = 0;  // ... when the bulk-copy kernel runs with three stages (waves without repeated keys)
     bool profile = false;   // record per-kernel CUDA events in every wave (nz_set_profiling / env NZ_PROFILE=1)

@@ -100,6 +100,7 @@ struct Key16Hash {
     size_t operator()(const Key16& k) const { size_t v; memcpy(&v, k.b + 8, sizeof v); return v; }
 };
 
+constexpr int NZ_MAX_POOLS = 4;
 struct Server {
     Options opt;
     nzh::Config cfg = nzh::Config::reference_default();
@@ -115,7 +116,12 @@ struct Server {
     std::unordered_map<Key16, int, Key16Hash> filling;
     std::mutex win_mu;
     std::mutex pv_mu;
-    std::vector<nz_buf*> free_windows;
+    // pinned windows, pooled per HOST MEMORY NODE: a window is written by one GPU's copy engine, and pages on the far
+    // socket move at about a third of the near one's rate.  pool_of_shard maps a GPU to its node's pool.
+    std::vector<nz_buf*> free_windows[NZ_MAX_POOLS];
+    nz_ctx* pool_ctx[NZ_MAX_POOLS] = {};
+    int n_pools = 1;
+    std::vector<int> pool_of_shard;
     std::atomic<uint64_t> boundary{1};
     std::atomic<int> conns{0};
     std::atomic<uint64_t> hits{0}, misses{0}, bytes_out{0};
@@ -644,11 +650,12 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
         return 502;
     }
     nz_buf* win = nullptr;
+    const int pool = S.pool_of_shard[shard];
     {
         std::lock_guard<std::mutex> g(S.win_mu);
-        if (!S.free_windows.empty()) { win = S.free_windows.back(); S.free_windows.pop_back(); }
+        if (!S.free_windows[pool].empty()) { win = S.free_windows[pool].back(); S.free_windows[pool].pop_back(); }
     }
-    if (!win && nz_buf_alloc(S.ctx, S.opt.window_bytes, NZ_BUF_PINNED_HOST, &win) != NZ_OK) { nz_put_abort(put); up.close_(); return 502; }
+    if (!win && nz_buf_alloc(S.pool_ctx[pool], S.opt.window_bytes, NZ_BUF_PINNED_HOST, &win) != NZ_OK) { nz_put_abort(put); up.close_(); return 502; }
     char* wp = static_cast<char*>(nz_buf_ptr(win));
     uint64_t off = 0;
     bool ok = true;
@@ -682,7 +689,7 @@ int fill_from_origin(Server& S, int vhost, const std::string& host, const std::s
     up.close_();
     {
         std::lock_guard<std::mutex> g(S.win_mu);
-        S.free_windows.push_back(win);
+        S.free_windows[pool].push_back(win);
     }
     if (md) {                                                   // the origin's MD5 of the body must match what arrived
         uint8_t dg[EVP_MAX_MD_SIZE];
@@ -845,7 +852,12 @@ static int g_direct_max = 4;                  // env NZ_PROXY_DIRECT (0 = always
 static std::atomic<uint64_t> g_direct_ns{0}, g_direct_n{0};
 
 // ---- serving -------------------------------------------------------------------
-bool send_plan(Server& S, int fd, const nzh::Plan& plan, const Entry* ent, bool keep_alive, nz_buf* win[2], int64_t t_req = 0) {
+// a connection's pinned windows: one pair per host memory node it has been served from (taken on first use)
+struct ConnWin { nz_buf* w[NZ_MAX_POOLS][2] = {}; };
+nz_buf** conn_windows(Server& S, ConnWin& cw, uint32_t shard);
+void give_windows(Server& S, ConnWin& cw);
+
+bool send_plan(Server& S, int fd, const nzh::Plan& plan, const Entry* ent, bool keep_alive, ConnWin& cw, int64_t t_req = 0) {
     std::string h = std::string("HTTP/1.1 ") + std::to_string(plan.status) + " " + status_text(plan.status) + "\r\nServer: nginx\r\nDate: " +
                     http_date(time(nullptr)) + "\r\n";
     for (const auto& kv : plan.headers) h += kv.first + ": " + kv.second + "\r\n";
@@ -856,6 +868,8 @@ bool send_plan(Server& S, int fd, const nzh::Plan& plan, const Entry* ent, bool 
     // the first bytes of the body.
     std::string pending = h;
     const uint32_t flags = (plan.inflated ? NZ_GET_INFLATE : 0) | (S.opt.verify ? NZ_GET_VERIFY : 0);
+    nz_buf** win = conn_windows(S, cw, nz_shard_of(ent->key128, (uint32_t)S.ctxs.size()));   // windows next to the GPU that holds the object
+    if (!win) return false;
     bool first = true;                                   // first window of the RESPONSE: small and urgent
     for (const nzh::Part& part : plan.body) {
         if (part.literal) { pending += part.bytes; continue; }
@@ -947,7 +961,7 @@ void access_log_line(Server& S, const std::string& client_ip, const Parsed& pr, 
 
 // One request whose head is already in hand, served with blocking sockets: the miss path (origin fetch, uncached
 // relay) and the legacy thread-per-connection mode (--io-threads 0).  Returns whether the connection stays open.
-bool serve_one(Server& S, int fd, const std::string& client_ip, const std::string& head, nz_buf* win[2]) {
+bool serve_one(Server& S, int fd, const std::string& client_ip, const std::string& head, ConnWin& cw) {
     const int64_t t_req = g_trace ? now_ns() : 0;
     Parsed pr = parse_head(head);
     nzh::Plan plan;
@@ -1028,7 +1042,7 @@ bool serve_one(Server& S, int fd, const std::string& client_ip, const std::strin
     // discard it; parsing it as the next request must not happen)
     if (pr.ok && pr.has_body) keep = false;
     if (pr.ok && pr.rq.http_minor < 1) keep = false;
-    const bool sent = send_plan(S, fd, plan, ent.get(), keep, win, t_req);
+    const bool sent = send_plan(S, fd, plan, ent.get(), keep, cw, t_req);
     access_log_line(S, client_ip, pr, plan.status, plan.head ? 0 : plan.body_length());
     if (ent) ent->inflight--;
     return sent && keep;
@@ -1045,28 +1059,31 @@ void tune_socket(int fd) {
     setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &stv, sizeof stv);
 }
 
-bool take_windows(Server& S, nz_buf* win[2]) {
-    win[0] = win[1] = nullptr;
+nz_buf** conn_windows(Server& S, ConnWin& cw, uint32_t shard) {
+    const int pool = S.pool_of_shard[shard];
+    nz_buf** win = cw.w[pool];
+    if (win[0] && win[1]) return win;
     {
         std::lock_guard<std::mutex> g(S.win_mu);
-        for (int i = 0; i < 2 && !S.free_windows.empty(); ++i) { win[i] = S.free_windows.back(); S.free_windows.pop_back(); }
+        std::vector<nz_buf*>& fr = S.free_windows[pool];
+        for (int i = 0; i < 2 && !fr.empty(); ++i) if (!win[i]) { win[i] = fr.back(); fr.pop_back(); }
     }
     for (int i = 0; i < 2; ++i)
-        if (!win[i] && nz_buf_alloc(S.ctx, S.opt.window_bytes, NZ_BUF_PINNED_HOST, &win[i]) != NZ_OK) win[i] = nullptr;
-    return win[0] && win[1];
+        if (!win[i] && nz_buf_alloc(S.pool_ctx[pool], S.opt.window_bytes, NZ_BUF_PINNED_HOST, &win[i]) != NZ_OK) win[i] = nullptr;
+    return win[0] && win[1] ? win : nullptr;
 }
-void give_windows(Server& S, nz_buf* win[2]) {
+void give_windows(Server& S, ConnWin& cw) {
     std::lock_guard<std::mutex> g(S.win_mu);
-    for (int i = 0; i < 2; ++i) if (win[i]) S.free_windows.push_back(win[i]);
-    win[0] = win[1] = nullptr;
+    for (int p = 0; p < NZ_MAX_POOLS; ++p)
+        for (int i = 0; i < 2; ++i) if (cw.w[p][i]) { S.free_windows[p].push_back(cw.w[p][i]); cw.w[p][i] = nullptr; }
 }
 
 // legacy mode (--io-threads 0): one thread per connection, blocking sockets
 void serve_connection(Server* Sp, int fd, std::string client_ip) {
     Server& S = *Sp;
     tune_socket(fd);
-    nz_buf* win[2];
-    bool alive = take_windows(S, win);
+    ConnWin cw;
+    bool alive = true;
     std::string inbuf;
     std::vector<char> tmp(16384);
     while (alive) {
@@ -1080,9 +1097,9 @@ void serve_connection(Server* Sp, int fd, std::string client_ip) {
         if (!alive) break;
         const std::string head = inbuf.substr(0, end + 2);
         inbuf.erase(0, end + 4);
-        if (!serve_one(S, fd, client_ip, head, win)) break;
+        if (!serve_one(S, fd, client_ip, head, cw)) break;
     }
-    give_windows(S, win);
+    give_windows(S, cw);
     shutdown(fd, SHUT_RDWR);
     close(fd);
     S.conns--;
@@ -1105,7 +1122,8 @@ struct EvConn {
     int fd = -1;
     Worker* w = nullptr;
     std::string ip, in;
-    nz_buf* win[2] = {nullptr, nullptr};
+    ConnWin cw;
+    nz_buf** win = nullptr;               // the pair the current response streams through (next to its GPU)
     enum WinState { FREE, INFLIGHT, READY, FAILED };
     struct Win { WinState st = FREE; uint64_t len = 0, sent = 0; bool urgent = false; } ws[2];
     // the response being sent
@@ -1181,7 +1199,7 @@ void Worker::kill(EvConn* c) {            // stop serving; the object itself goe
 void Worker::reap(EvConn* c) {
     Server& Sv = *S;
     if (c->ent) { c->ent->inflight--; c->ent.reset(); }
-    give_windows(Sv, c->win);
+    give_windows(Sv, c->cw);
     close(c->fd);
     Sv.conns--;
     conns.erase(std::remove(conns.begin(), conns.end(), c), conns.end());
@@ -1198,9 +1216,9 @@ void Worker::lend_to_helper(EvConn* c, const std::string& head) {
     std::thread([Sp, self, c, head] {
         const int fl = fcntl(c->fd, F_GETFL, 0);
         fcntl(c->fd, F_SETFL, fl & ~O_NONBLOCK);
-        const bool open_ = serve_one(*Sp, c->fd, c->ip, head, c->win);
+        const bool open_ = serve_one(*Sp, c->fd, c->ip, head, c->cw);
         if (!open_) {
-            give_windows(*Sp, c->win);
+            give_windows(*Sp, c->cw);
             shutdown(c->fd, SHUT_RDWR);
             close(c->fd);
             Sp->conns--;
@@ -1270,6 +1288,15 @@ void Worker::try_start(EvConn* c) {
 
 void Worker::start_response(EvConn* c) {
     Server& Sv = *S;
+    c->win = nullptr;
+    if (c->ent && !c->plan.head) {
+        bool slices = false;
+        for (const nzh::Part& p : c->plan.body) slices |= !p.literal;
+        if (slices) {                                       // windows next to the GPU that holds the object
+            c->win = conn_windows(Sv, c->cw, nz_shard_of(c->ent->key128, (uint32_t)Sv.ctxs.size()));
+            if (!c->win) { c->plan = nzh::error_page(500, false); c->keep = false; }
+        }
+    }
     const nzh::Plan& plan = c->plan;
     std::string h = std::string("HTTP/1.1 ") + std::to_string(plan.status) + " " + status_text(plan.status) + "\r\nServer: nginx\r\nDate: " +
                     http_date(time(nullptr)) + "\r\n";
@@ -1630,10 +1657,23 @@ int main(int argc, char** argv) {
         S.ctxs.push_back(cx);
     }
     S.ctx = S.ctxs[0];
-    for (int i = 0; i < std::min(S.opt.max_conns, 160) * 2; ++i) {   // pinned windows up front: cudaHostAlloc is slow
-        nz_buf* b = nullptr;
-        if (nz_buf_alloc(S.ctx, S.opt.window_bytes, NZ_BUF_PINNED_HOST, &b) != NZ_OK) break;
-        S.free_windows.push_back(b);
+    {   // one window pool per host memory node that has a GPU of ours
+        int node_of_pool[NZ_MAX_POOLS];
+        S.n_pools = 0;
+        for (nz_ctx* cx : S.ctxs) {
+            const int node = nz_numa_node(cx);
+            int pool = -1;
+            for (int k = 0; k < S.n_pools; ++k) if (node_of_pool[k] == node) pool = k;
+            if (pool < 0 && S.n_pools < NZ_MAX_POOLS) { pool = S.n_pools++; node_of_pool[pool] = node; S.pool_ctx[pool] = cx; }
+            S.pool_of_shard.push_back(pool < 0 ? 0 : pool);
+        }
+        const int per_pool = std::min(S.opt.max_conns, 160) * 2 / S.n_pools;
+        for (int k = 0; k < S.n_pools; ++k)
+            for (int i = 0; i < per_pool; ++i) {                     // pinned windows up front: cudaHostAlloc is slow
+                nz_buf* b = nullptr;
+                if (nz_buf_alloc(S.pool_ctx[k], S.opt.window_bytes, NZ_BUF_PINNED_HOST, &b) != NZ_OK) break;
+                S.free_windows[k].push_back(b);
+            }
     }
     if (!S.opt.pv_dir.empty()) pv_reload(S);
     std::thread([&S] { for (;;) { std::this_thread::sleep_for(std::chrono::seconds(S.opt.inactive_s < 120 ? 1 : 60)); cache_manager_pass(S); } }).detach();
@@ -1730,8 +1770,8 @@ int main(int argc, char** argv) {
         perror("nzproxy: bind/listen");
         return 1;
     }
-    fprintf(stderr, "nzproxy: listening on %s:%d, %zu GPU shard(s), arena %.1f GiB each, %zu pinned windows of %.1f MiB, %zu event-loop worker(s)%s\n", S.opt.listen_ip.c_str(),
-            S.opt.port, S.ctxs.size(), S.opt.arena_bytes / 1073741824.0, S.free_windows.size(), S.opt.window_bytes / 1048576.0, workers.size(),
+    fprintf(stderr, "nzproxy: listening on %s:%d, %zu GPU shard(s), arena %.1f GiB each, %zu pinned windows of %.1f MiB in %d node pool(s), %zu event-loop worker(s)%s\n", S.opt.listen_ip.c_str(),
+            S.opt.port, S.ctxs.size(), S.opt.arena_bytes / 1073741824.0, [&] { size_t n = 0; for (int k = 0; k < S.n_pools; ++k) n += S.free_windows[k].size(); return n; }(), S.opt.window_bytes / 1048576.0, S.n_pools, workers.size(),
             workers.empty() ? " (thread per connection)" : "");
     fflush(stderr);
     for (;;) {
@@ -1751,7 +1791,6 @@ int main(int argc, char** argv) {
         c->fd = fd;
         c->ip = ip;
         tune_socket(fd);
-        if (!take_windows(S, c->win)) { give_windows(S, c->win); close(fd); S.conns--; delete c; continue; }
         fcntl(fd, F_SETFL, fcntl(fd, F_GETFL, 0) | O_NONBLOCK);
         workers[rr++ % workers.size()]->post(c);
     }

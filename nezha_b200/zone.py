@@ -157,6 +157,10 @@ class Zone:
         self.close()
 
     # -- memory ------------------------------------------------------------
+    def numa_node(self) -> int:
+        """host memory node next to this zone's GPU (-1 unknown); pinned buffers are placed there"""
+        return int(self.L.nz_numa_node(self.ctx))
+
     def alloc_host(self, nbytes: int) -> Buf:
         return Buf(self, nbytes, capi.NZ_BUF_PINNED_HOST)
 
