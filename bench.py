@@ -351,7 +351,7 @@ def run_ours(args):
     algo = read_bytes + payload
     achieved = algo / (g_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                "traffic": None, "peak_source": which, "kernel": "k_gather",
+                "traffic": None, "peak_source": which, "kernel": "k_gather_tma",
                 "algorithmic_bytes_per_launch": algo, "kernel_ms": g_ms,
                 "accounting": ("source read once per distinct slice (request coalescing) + every payload byte written" if coalesce
                                else "2 x payload (read + write per request)"),
