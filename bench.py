@@ -726,7 +726,7 @@ def http_bench(L_obj, requests, devices, seed=2, with_c1=False):
             out["c1"]["reference_published_mbs"] = 323
             out["c1"]["note"] = ("ONE connection, full GET of the 169 001 437 B object (README.md:116 publishes 323 MB/s for this through the one-worker "
                                  "nginx proxy cache over a pod network); here loopback TCP, same box, same run: gbs x 1000 = MB/s")
-        out["note"] = ("loopback TCP, nzload with %d keep-alive connections replaying the C2 log against %d object(s), one per GPU; TTFB = request sent -> first response byte (ttfbody: first BODY byte; nzproxy sends the header before asking the GPU for the first window); "
+        out["note"] = ("loopback TCP, nzload with %d keep-alive connections (256 KiB receive buffer each) replaying the C2 log against %d object(s), one per GPU; TTFB = request sent -> first response byte (ttfbody: first BODY byte; nzproxy sends the header before asking the GPU for the first window); "
                        "cpu_* is the nginx-restated server (oracle/nz_cpu_server.c), not nginx" % (nconn, ngpu))
     except Exception as e:      # the HTTP section must never take the kernel-level numbers down with it
         out["error"] = repr(e)

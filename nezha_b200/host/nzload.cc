@@ -37,6 +37,11 @@ static std::atomic<uint64_t> g_bytes{0}, g_reqs{0}, g_errors{0}, g_s2xx{0}, g_so
 static std::mutex g_mu;
 static std::vector<double> g_ttfb_us, g_ttfbody_us;
 
+static bool g_discard = false;
+static size_t g_buf_bytes = 256u << 10;    // --buf-kib: receive buffer per connection.  64 connections x 4 MiB (round 1) did not stay in any cache and the
+                                           // CLIENT's copies cost the shared box 20 % of the figure (profiles/r02_sweep_load_client.txt); 256 KiB is what
+                                           // curl/wget-sized clients use
+
 static int dial(const std::string& ip, int port) {
     int fd = socket(AF_INET, SOCK_STREAM, 0);
     if (fd < 0) return -1;
@@ -87,7 +92,10 @@ static int64_t one_get(int fd, const Req& r, std::vector<char>& buf, double* ttf
     *ttfbody_us = -1.0;
     if (got > 0 || clen == 0) *ttfbody_us = std::chrono::duration<double, std::micro>(Clock::now() - t0).count();
     while (got < clen) {
-        ssize_t n = recv(fd, buf.data(), (size_t)std::min<int64_t>((int64_t)buf.size(), clen - got), 0);
+        // --discard: the body is dropped inside the kernel (MSG_TRUNC on TCP: no copy to user space) - a sink that does not
+        // spend the box's cores on a second copy of every byte; the head is always read for real
+        ssize_t n = g_discard ? recv(fd, nullptr, (size_t)std::min<int64_t>((int64_t)1 << 30, clen - got), MSG_TRUNC)
+                              : recv(fd, buf.data(), (size_t)std::min<int64_t>((int64_t)buf.size(), clen - got), 0);
         if (n <= 0) return -1;
         if (*ttfbody_us < 0) *ttfbody_us = std::chrono::duration<double, std::micro>(Clock::now() - t0).count();
         got += n;
@@ -96,7 +104,7 @@ static int64_t one_get(int fd, const Req& r, std::vector<char>& buf, double* ttf
 }
 
 static void client(std::string ip, int port, std::vector<Req> mine, int repeat, int warmup) {
-    std::vector<char> buf(4 << 20);
+    std::vector<char> buf(g_buf_bytes);
     int fd = dial(ip, port);
     std::vector<double> ttfb, ttfbody;
     uint64_t bytes = 0, reqs = 0, errs = 0, ok2 = 0, oth = 0;
@@ -137,8 +145,12 @@ int main(int argc, char** argv) {
         else if (a == "--log") logf = next();
         else if (a == "--repeat") repeat = atoi(next());
         else if (a == "--warmup") warmup = atoi(next());
-        else { fprintf(stderr, "nzload --target ip:port --conns N --log FILE [--repeat R] [--warmup W]\n"); return 2; }
+        else if (a == "--buf-kib") g_buf_bytes = (size_t)std::max(4, atoi(next())) << 10;
+        else if (a == "--discard") g_discard = true;
+        else { fprintf(stderr, "nzload --target ip:port --conns N --log FILE [--repeat R] [--warmup W] [--buf-kib K] [--discard]\n"); return 2; }
     }
+    if (const char* e = getenv("NZ_LOAD_BUF_KIB")) g_buf_bytes = (size_t)std::max(4, atoi(e)) << 10;
+    if (const char* e = getenv("NZ_LOAD_DISCARD")) g_discard = atoi(e) != 0;
     const size_t c = target.rfind(':');
     const std::string ip = target.substr(0, c);
     const int port = atoi(target.c_str() + c + 1);
