@@ -125,6 +125,7 @@ static void detect_numa(nz_ctx* c) {
     c->numa_node = node;
     snprintf(path, sizeof path, "/sys/devices/system/node/node%d", node ? 0 : 1);
     c->numa_place = access(path, F_OK) == 0;             // a second node exists: placement matters
+    if (const char* ev = getenv("NZ_NUMA")) if (atoi(ev) == 2) c->numa_place = false;   // node reported, placement left to the caller
 }
 struct NumaScope {
     bool policy = false, moved = false;
@@ -1260,13 +1261,20 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
         if (need > t->scratch_cap) {
             if (t->scratch) cudaFree(t->scratch);
             t->scratch = nullptr; t->scratch_cap = 0;
-            if (cudaMalloc(&t->scratch, need) != cudaSuccess) {
+            // with headroom: the next wave's distinct members differ a little, and growing again means cudaFree (which waits
+            // for every wave in flight) + cudaMalloc on the submit path
+            size_t cap = round_up(need + need / 8, 64ull << 20);
+            if (cudaMalloc(&t->scratch, cap) != cudaSuccess) {
                 cudaGetLastError();
-                nz_ticket_free(t);
-                snprintf(tl_err, sizeof tl_err, "inflate scratch allocation of %zu bytes failed", need);
-                return NZ_ENOMEM;
+                cap = need;
+                if (cudaMalloc(&t->scratch, cap) != cudaSuccess) {
+                    cudaGetLastError();
+                    nz_ticket_free(t);
+                    snprintf(tl_err, sizeof tl_err, "inflate scratch allocation of %zu bytes failed", need);
+                    return NZ_ENOMEM;
+                }
             }
-            t->scratch_cap = need;
+            t->scratch_cap = cap;
         }
     }
     size_t scratch_off = 0;
