@@ -1263,7 +1263,7 @@ int32_t nz_get_submit(nz_ctx* c, const nz_get_req* reqs, uint32_t n, void* cuda_
             t->scratch = nullptr; t->scratch_cap = 0;
             // with headroom: the next wave's distinct members differ a little, and growing again means cudaFree (which waits
             // for every wave in flight) + cudaMalloc on the submit path
-            size_t cap = round_up(need + need / 8, 64ull << 20);
+            size_t cap = round_up(need + need / 8, 1ull << 20);     // an eighth more, MiB granular (a one-member wave keeps a small scratch)
             if (cudaMalloc(&t->scratch, cap) != cudaSuccess) {
                 cudaGetLastError();
                 cap = need;
