@@ -224,6 +224,28 @@ def test_crc32c_device_kernel_K3(zone):
             assert crc2 == o.crc32c(h[1:])
 
 
+def test_K3_and_commit_crc_against_the_cpu_crc32_instruction(zone):
+    """X1 with a witness nobody here wrote: the x86 `crc32` instruction (tests/hwcrc.py), at sizes the oracle's own loop
+    would take long on - whole CRC, the 64 KiB chunk table, an odd base address, and the CRC a put commits."""
+    import torch
+
+    import hwcrc
+    if hwcrc.lib() is None:
+        pytest.skip("no SSE4.2 crc32 instruction / gcc here")
+    torch.manual_seed(7)
+    for n in (1, 65536, 65537, 5 * 65536 + 7, (64 << 20) + 13, 256 << 20):
+        t = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda")
+        host = t.cpu().numpy()
+        crc, chunks = zone.crc32c_device(t.data_ptr(), n, want_chunks=True)
+        assert crc == hwcrc.crc32c(host), n
+        for c in {0, len(chunks) // 2, len(chunks) - 1}:
+            assert int(chunks[c]) == hwcrc.crc32c(host[c * 65536:(c + 1) * 65536]), (n, c)
+        if n > 1:
+            assert zone.crc32c_device(t.data_ptr() + 1, n - 1) == hwcrc.crc32c(host[1:]), n
+    d = wl.synth_bytes(3_000_017, seed=77)
+    assert zone.put(K(9001), d) == hwcrc.crc32c(d)
+
+
 def test_table_churn_insert_evict(zone):
     """Tombstones + re-insert keep every live key reachable (K1/K6)."""
     live = {}
