@@ -1,0 +1,117 @@
+"""-m "not gpu": the nginx-restated CPU server (oracle/nz_cpu_server.c - the wire-level oracle nzproxy is replayed
+against in tests/test_gpu_http.py, and bench.py's HTTP reference arm) asked over real sockets beside aiohttp's file
+server: the same requests as tests/test_third_party_witness.py, now through request parsing, header framing,
+keep-alive and the send loop.  Also what only shows on the wire: pipelined keep-alive requests, HEAD framing, the
+`Server: nginx` / `Accept-Ranges` headers (nginx.conf:20), 405 for other methods (nginx.conf:47-49)."""
+import asyncio
+import http.client
+import os
+import signal
+import socket
+import subprocess
+import time
+
+import pytest
+
+from oracle import oracle as o
+
+from test_third_party_witness import AGREED, AGREED_AIO, DATA, L, LM, MTIME, Aiohttp, same_answer, with_etag
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST, PATH = "www.cs.toronto.edu", "/~kriz/cifar-100-python.tar.gz"
+
+
+def free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+@pytest.fixture(scope="module")
+def wire(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cpuwire")
+    f = d / "obj.bin"
+    f.write_bytes(DATA)
+    os.utime(f, (MTIME, MTIME))
+    aio = Aiohttp(str(d))
+    hx = o.md5(o.cache_key(HOST, PATH)).hex()
+    (d / hx).write_bytes(DATA)
+    (d / "manifest").write_text(f"{hx} {L} -1 application/octet-stream {aio.etag} - {LM}\n")
+    port = free_port()
+    p = subprocess.Popen([os.path.join(ROOT, "oracle", "_build", "nz_cpu_server"), "--root", str(d), "--listen", f"127.0.0.1:{port}"], start_new_session=True)
+    t0 = time.time()
+    while time.time() - t0 < 20:
+        try:
+            socket.create_connection(("127.0.0.1", port), 0.2).close(); break
+        except OSError:
+            time.sleep(0.05)
+    try:
+        yield port, aio
+    finally:
+        try:
+            os.killpg(p.pid, signal.SIGTERM)
+        except ProcessLookupError:
+            pass
+
+
+def ask_cpu(port, method, hd, path=PATH):
+    c = http.client.HTTPConnection("127.0.0.1", port, timeout=20)
+    c.putrequest(method, path, skip_host=True, skip_accept_encoding=True)
+    c.putheader("Host", HOST)
+    for k, v in hd.items():
+        c.putheader(k, v)
+    c.endheaders()
+    r = c.getresponse()
+    body = r.read()
+    out = (r.status, r.getheader("Content-Range"), r.getheader("Content-Length"), r.getheader("Content-Type", ""), body, dict((k.lower(), v) for k, v in r.getheaders()))
+    c.close()
+    return out
+
+
+@pytest.mark.parametrize("method,hd", AGREED + AGREED_AIO, ids=lambda v: str(v))
+def test_cpu_server_answers_like_aiohttp_on_the_wire(wire, method, hd):
+    port, aio = wire
+    hd = with_etag(hd, aio.etag)
+    mine = ask_cpu(port, method, hd)
+    theirs = aio.ask(method, hd)
+    if mine[0] == 416:                                   # nginx sends its stock 416 page (SPEC E1); the comparison is about status + Content-Range
+        assert theirs[0] == 416 and (mine[1] or "").endswith(f"*/{L}") and (theirs[1] or "").endswith(f"*/{L}")
+        return
+    same_answer(mine[:5], theirs, "aiohttp", (method, hd))
+    if mine[0] in (200, 206):
+        assert mine[5].get("server") == "nginx"
+        # nginx's range filter adds Accept-Ranges only where it did NOT serve a range (its `next_filter:` label): 200 yes, 206 no
+        assert mine[5].get("accept-ranges") == ("bytes" if mine[0] == 200 else None)
+        assert mine[5].get("etag") == aio.etag and mine[5].get("last-modified") == LM
+
+
+def test_head_has_the_length_and_no_body(wire):
+    port, _ = wire
+    st, _cr, cl, _ct, body, _h = ask_cpu(port, "HEAD", {})
+    assert (st, cl, body) == (200, str(L), b"")
+
+
+def test_other_methods_are_405_with_the_stock_page(wire):
+    port, _ = wire
+    st, _cr, _cl, ct, body, hdrs = ask_cpu(port, "POST", {"Content-Length": "0"})
+    assert st == 405 and hdrs.get("server") == "nginx" and ct == "text/html" and b"405 Not Allowed" in body
+
+
+def test_pipelined_keep_alive_requests_come_back_in_order(wire):
+    port, _ = wire
+    s = socket.create_connection(("127.0.0.1", port), 5)
+    reqs = [("bytes=0-9", DATA[0:10]), ("bytes=100-199", DATA[100:200]), ("bytes=-5", DATA[-5:])]
+    s.sendall(b"".join(f"GET {PATH} HTTP/1.1\r\nHost: {HOST}\r\nRange: {r}\r\n\r\n".encode() for r, _ in reqs))
+    buf = b""
+    s.settimeout(5)
+    got = []
+    while len(got) < len(reqs):
+        while b"\r\n\r\n" not in buf:
+            buf += s.recv(65536)
+        head, _, rest = buf.partition(b"\r\n\r\n")
+        assert head.startswith(b"HTTP/1.1 206")
+        n = int([l.split(b":")[1] for l in head.split(b"\r\n") if l.lower().startswith(b"content-length:")][0])
+        while len(rest) < n:
+            rest += s.recv(65536)
+        got.append(rest[:n])
+        buf = rest[n:]
+    s.close()
+    assert got == [b for _, b in reqs]
