@@ -589,3 +589,30 @@ def test_private_s3_vhost_signs_fills_with_sigv2():
     finally:
         _stop(p)
         httpd.shutdown()
+
+
+def test_nzproxy_answers_like_aiohttp_on_the_wire(servers, tmp_path):
+    """The GPU front end beside a third-party RFC 7232/7233 implementation (aiohttp's file server), same requests as
+    tests/test_third_party_witness.py: first a miss filled from the origin, then hits from HBM."""
+    from test_third_party_witness import AGREED, AGREED_AIO, DATA as WDATA, L as WL, MTIME, Aiohttp, same_answer, with_etag
+
+    f = tmp_path / "obj.bin"
+    f.write_bytes(WDATA)
+    os.utime(f, (MTIME, MTIME))
+    aio = Aiohttp(str(tmp_path))
+    host, path = "storage.googleapis.com", "/witness/obj.bin"
+    OBJECTS[path] = (host, WDATA, "application/octet-stream", aio.etag, None)
+    gpu_port, _ = servers
+    try:
+        for method, hd in AGREED + AGREED_AIO:
+            hd = with_etag(hd, aio.etag)
+            st, hdrs, body = fetch(gpu_port, method, host, path, hd)
+            theirs = aio.ask(method, hd)
+            if st == 416:
+                assert theirs[0] == 416 and hdrs.get("content-range", "").endswith(f"*/{WL}"), (method, hd, theirs[:3])
+                continue
+            same_answer((st, hdrs.get("content-range"), hdrs.get("content-length"), hdrs.get("content-type", ""), body), theirs, "aiohttp", (method, hd))
+            if st in (200, 206):
+                assert hdrs.get("etag") == aio.etag and hdrs.get("last-modified") == LM and hdrs.get("server") == "nginx"
+    finally:
+        del OBJECTS[path]
