@@ -419,6 +419,7 @@ const char* reason_phrase(int code) {
     case 416: return "Requested Range Not Satisfiable";
     case 502: return "Bad Gateway";
     case 504: return "Gateway Time-out";
+    case 505: return "HTTP Version Not Supported";
     default: return "";
     }
 }
@@ -456,14 +457,154 @@ Part literal(std::string b) {
 
 Plan error_page(int code, bool head) { return stock_page(code, head); }
 
-// ---- admission / validity (SPEC H2) -------------------------------------------------------------
+// ---- request head (SPEC P) ----------------------------------------------------------------------
 namespace {
 bool ieq(std::string_view a, std::string_view b) {
     if (a.size() != b.size()) return false;
     for (size_t i = 0; i < a.size(); ++i)
-        if (tolower((unsigned char)a[i]) != tolower((unsigned char)b[i])) return false;
+        if (std::tolower((unsigned char)a[i]) != std::tolower((unsigned char)b[i])) return false;
     return true;
 }
+bool has_ci(std::string_view hay, std::string_view needle) {
+    if (needle.size() > hay.size()) return false;
+    for (size_t i = 0; i + needle.size() <= hay.size(); ++i)
+        if (ieq(hay.substr(i, needle.size()), needle)) return true;
+    return false;
+}
+std::string_view trim_spaces(std::string_view v) {       // P5: spaces only
+    while (!v.empty() && v.front() == ' ') v.remove_prefix(1);
+    while (!v.empty() && v.back() == ' ') v.remove_suffix(1);
+    return v;
+}
+}  // namespace
+
+Head parse_head(std::string_view raw) {
+    Head bad;
+    bad.error = 400;
+    bad.keep_alive = false;
+    while (!raw.empty() && (raw.front() == '\r' || raw.front() == '\n')) raw.remove_prefix(1);
+    while (raw.size() >= 2 && raw.substr(raw.size() - 2) == "\r\n") raw.remove_suffix(2);
+    for (size_t i = 0; i < raw.size(); ++i) {                                  // P2: NUL, bare CR, bare LF
+        const char c = raw[i];
+        if (c == '\0') return bad;
+        if (c == '\r' && (i + 1 >= raw.size() || raw[i + 1] != '\n')) return bad;
+        if (c == '\n' && (i == 0 || raw[i - 1] != '\r')) return bad;
+    }
+    std::vector<std::string_view> lines;
+    for (size_t pos = 0;;) {
+        const size_t e = raw.find("\r\n", pos);
+        lines.push_back(raw.substr(pos, e == std::string_view::npos ? std::string_view::npos : e - pos));
+        if (e == std::string_view::npos) break;
+        pos = e + 2;
+    }
+    Head h;
+    const std::string_view rl = lines[0];
+    h.request_line = std::string(rl);
+    size_t j = 0;
+    while (j < rl.size() && ((rl[j] >= 'A' && rl[j] <= 'Z') || rl[j] == '_')) ++j;
+    if (j == 0 || j >= rl.size() || rl[j] != ' ') return bad;                  // P1
+    h.rq.method = std::string(rl.substr(0, j));
+    while (j < rl.size() && rl[j] == ' ') ++j;
+    size_t k = rl.find(' ', j);
+    if (k == std::string_view::npos) k = rl.size();
+    const std::string_view target = rl.substr(j, k - j);
+    if (target.empty()) return bad;
+    if (target[0] != '/') {                                                    // P2: absolute-form
+        size_t m = 0;
+        while (m < target.size() && (unsigned char)target[m] < 128 && std::isalpha((unsigned char)target[m])) ++m;
+        if (m == 0 || target.substr(m, 3) != "://") return bad;
+    }
+    h.rq.target = std::string(target);
+    const std::string_view ver = trim_spaces(rl.substr(k));
+    if (ver.empty()) {                                                         // P3
+        if (h.rq.method != "GET") return bad;
+        h.rq.http_minor = -1;
+        h.keep_alive = false;
+    } else {                                                                   // P4
+        if (ver.substr(0, 5) != "HTTP/") return bad;
+        const std::string_view num = ver.substr(5);
+        const size_t dot = num.find('.');
+        if (dot == std::string_view::npos) return bad;
+        const std::string_view mj = num.substr(0, dot), mn = num.substr(dot + 1);
+        auto digits = [](std::string_view d) {
+            if (d.empty() || d.size() > 2) return false;
+            for (char c : d) if (c < '0' || c > '9') return false;
+            return true;
+        };
+        if (!digits(mj) || !digits(mn) || mj[0] == '0') return bad;
+        if (std::stoi(std::string(mj)) > 1) { Head v; v.error = 505; v.keep_alive = false; return v; }
+        h.rq.http_minor = std::stoi(std::string(mn)) == 0 ? 0 : 1;
+        h.keep_alive = h.rq.http_minor == 1;
+    }
+    static const char* const unique[] = {"if-modified-since", "if-unmodified-since", "if-match", "if-none-match", "if-range", "content-length",
+                                         "content-range", "expect", "authorization"};
+    bool seen[sizeof unique / sizeof unique[0]] = {};
+    int hosts = 0;
+    for (size_t li = 1; li < lines.size(); ++li) {
+        const std::string_view ln = lines[li];
+        if (ln.empty()) break;
+        const size_t c = ln.find(':');
+        const std::string_view name = ln.substr(0, c);                         // no colon: the whole line is a name (P5)
+        const std::string_view val = c == std::string_view::npos ? std::string_view() : trim_spaces(ln.substr(c + 1));
+        bool valid = !name.empty();
+        for (char ch : name)
+            if (!((unsigned char)ch < 128 && (std::isalnum((unsigned char)ch) || ch == '-'))) { valid = false; break; }
+        if (!valid) continue;                                                  // ignore_invalid_headers on
+        if (ieq(name, "host")) {                                               // P8
+            if (!normal_host(val)) return bad;
+            if (++hosts == 1) h.rq.host = std::string(val);
+            continue;
+        }
+        if (ieq(name, "range")) { if (!h.rq.range) h.rq.range = std::string(val); continue; }                          // P6
+        if (ieq(name, "accept-encoding")) { if (!h.rq.accept_encoding) h.rq.accept_encoding = std::string(val); continue; }
+        if (ieq(name, "referer")) { if (h.referer.empty()) h.referer = std::string(val); continue; }
+        if (ieq(name, "user-agent")) { if (h.user_agent.empty()) h.user_agent = std::string(val); continue; }
+        if (ieq(name, "x-forwarded-for")) { h.x_forwarded_for += (h.x_forwarded_for.empty() ? "" : ", ") + std::string(val); continue; }
+        int u = -1;
+        for (size_t i = 0; i < sizeof unique / sizeof unique[0]; ++i) if (ieq(name, unique[i])) u = (int)i;
+        if (u >= 0) {                                                          // P7
+            if (seen[u]) return bad;
+            seen[u] = true;
+            switch (u) {
+            case 0: h.rq.if_modified_since = std::string(val); break;
+            case 1: h.rq.if_unmodified_since = std::string(val); break;
+            case 2: h.rq.if_match = std::string(val); break;
+            case 3: h.rq.if_none_match = std::string(val); break;
+            case 4: h.rq.if_range = std::string(val); break;
+            case 5: {                                                          // P10
+                if (val.empty()) return bad;
+                bool nonzero = false;
+                for (char ch : val) { if (ch < '0' || ch > '9') return bad; if (ch != '0') nonzero = true; }
+                if (nonzero) h.has_body = true;
+                break;
+            }
+            default: break;
+            }
+            continue;
+        }
+        if (ieq(name, "transfer-encoding")) { h.has_body = true; continue; }
+        if (ieq(name, "connection")) {                                         // P9
+            if (has_ci(val, "close")) h.keep_alive = false;
+            else if (has_ci(val, "keep-alive")) h.keep_alive = true;
+        }
+    }
+    if (h.rq.http_minor == 1 && hosts == 0) return bad;                        // P8
+    return h;
+}
+
+std::string Head::to_text() const {
+    std::string t = "error " + std::to_string(error) + "\n";
+    if (error) return t;
+    t += "method " + rq.method + "\ntarget " + rq.target + "\nminor " + std::to_string(rq.http_minor) + "\nkeep " + (keep_alive ? "1" : "0") +
+         "\nbody " + (has_body ? "1" : "0") + "\n";
+    auto f = [&](const char* n, const std::optional<std::string>& v) { if (v) t += std::string("f ") + n + ": " + *v + "\n"; };
+    f("accept-encoding", rq.accept_encoding); f("host", rq.host); f("if-match", rq.if_match); f("if-modified-since", rq.if_modified_since);
+    f("if-none-match", rq.if_none_match); f("if-range", rq.if_range); f("if-unmodified-since", rq.if_unmodified_since); f("range", rq.range);
+    return t;
+}
+
+// ---- admission / validity (SPEC H2) -------------------------------------------------------------
+namespace {
 size_t ifind(std::string_view hay, std::string_view needle) {      // case-insensitive substring (ngx_strlcasestrn)
     if (needle.empty() || hay.size() < needle.size()) return std::string_view::npos;
     for (size_t i = 0; i + needle.size() <= hay.size(); ++i)
@@ -756,6 +897,12 @@ int nzh_plan_text(const nzh_request* rq, const nzh_object* ob, uint64_t boundary
     nzh::Config cfg = default_config();
     cfg.gunzip = ob->gunzip_enabled != 0;
     const std::string t = nzh::plan_response(cfg, r, o, boundary).to_text();
+    if (t.size() + 1 > cap) return -1;
+    std::memcpy(out, t.c_str(), t.size() + 1);
+    return (int)t.size();
+}
+int nzh_parse_head_text(const char* raw, size_t n, char* out, size_t cap) {
+    const std::string t = nzh::parse_head(std::string_view(raw, n)).to_text();
     if (t.size() + 1 > cap) return -1;
     std::memcpy(out, t.c_str(), t.size() + 1);
     return (int)t.size();

@@ -86,6 +86,18 @@ struct Admission { bool cacheable = false; int64_t valid_until = 0; };
 Admission admission(int status, const std::vector<std::pair<std::string, std::string>>& headers, int64_t now,
                     int64_t default_valid_s = 86400);
 
+// The request head (SPEC P: nginx's request-line and header-line parsers and the ngx_http_headers_in handlers): what reaches
+// the vhost / key / planner above.  error != 0 (400, 505) is answered with the stock page before anything else runs.
+struct Head {
+    int error = 0;
+    Request rq;
+    bool keep_alive = true;
+    bool has_body = false;               // Content-Length > 0 or a Transfer-Encoding line: answered, then the connection closes
+    std::string request_line, referer, user_agent, x_forwarded_for;   // access log only (nginx.conf:16-18)
+    std::string to_text() const;         // canonical text form used by the parity tests
+};
+Head parse_head(std::string_view raw);   // raw = the bytes before the blank line
+
 Plan plan_response(const Config& cfg, const Request& rq, const ObjectMeta& ob, uint64_t boundary);
 Plan error_page(int code, bool head);           // stock nginx page (server_tokens off, nginx.conf:20)
 
@@ -111,4 +123,5 @@ struct nzh_object {
 int nzh_plan_text(const nzh_request* rq, const nzh_object* ob, uint64_t boundary, char* out, size_t cap);
 // headers: "Name: value\n" lines in arrival order.  Returns 1 cacheable / 0 not; *valid_until = absolute seconds.
 int nzh_admission(int status, const char* headers, int64_t now, int64_t default_valid_s, int64_t* valid_until);
+int nzh_parse_head_text(const char* raw, size_t n, char* out, size_t cap);   // Head::to_text(); length or -1
 }

@@ -163,18 +163,16 @@ const char* status_text(int code) {
     case 416: return "Requested Range Not Satisfiable";
     case 502: return "Bad Gateway";
     case 504: return "Gateway Time-out";
+    case 505: return "HTTP Version Not Supported";
     default: return "Error";
     }
 }
 
 // ---- request parsing --------------------------------------------------------
-struct Parsed {
-    nzh::Request rq;
-    bool keep_alive = true;
-    bool ok = false;
-    bool has_body = false;               // Content-Length > 0 or Transfer-Encoding present
-    std::string request_line, referer, user_agent, x_forwarded_for;   // access log only (nginx.conf:16-18)
-};
+// the request head is parsed by the host layer (nzh::parse_head, SPEC P): request-line and header-line rules of nginx,
+// first-wins / unique / ignored header lines, 400 and 505 before anything else runs
+using Parsed = nzh::Head;
+static Parsed parse_head(const std::string& head) { return nzh::parse_head(head); }
 
 std::string lower(std::string s) {
     for (char& c : s) c = (char)tolower((unsigned char)c);
@@ -185,60 +183,6 @@ std::string trim(const std::string& s) {
     while (a < b && (s[a] == ' ' || s[a] == '\t')) ++a;
     while (b > a && (s[b - 1] == ' ' || s[b - 1] == '\t' || s[b - 1] == '\r')) --b;
     return s.substr(a, b - a);
-}
-
-Parsed parse_head(const std::string& head) {
-    Parsed p;
-    size_t eol = head.find("\r\n");
-    if (eol == std::string::npos) return p;
-    const std::string line = head.substr(0, eol);
-    p.request_line = line;
-    const size_t s1 = line.find(' ');
-    if (s1 == std::string::npos) return p;
-    const size_t s2 = line.find(' ', s1 + 1);
-    p.rq.method = line.substr(0, s1);
-    if (s2 == std::string::npos) {           // HTTP/0.9
-        p.rq.target = line.substr(s1 + 1);
-        p.rq.http_minor = -1;
-        p.keep_alive = false;
-    } else {
-        p.rq.target = line.substr(s1 + 1, s2 - s1 - 1);
-        const std::string ver = line.substr(s2 + 1);
-        if (ver == "HTTP/1.1") p.rq.http_minor = 1;
-        else if (ver == "HTTP/1.0") { p.rq.http_minor = 0; p.keep_alive = false; }
-        else return p;
-    }
-    size_t pos = eol + 2;
-    while (pos < head.size()) {
-        const size_t e = head.find("\r\n", pos);
-        if (e == std::string::npos || e == pos) break;
-        const std::string h = head.substr(pos, e - pos);
-        pos = e + 2;
-        const size_t c = h.find(':');
-        if (c == std::string::npos) continue;
-        const std::string name = lower(h.substr(0, c));
-        const std::string val = trim(h.substr(c + 1));
-        if (name == "host") p.rq.host = val;
-        else if (name == "range") p.rq.range = val;
-        else if (name == "if-range") p.rq.if_range = val;
-        else if (name == "if-none-match") p.rq.if_none_match = val;
-        else if (name == "if-match") p.rq.if_match = val;
-        else if (name == "if-modified-since") p.rq.if_modified_since = val;
-        else if (name == "if-unmodified-since") p.rq.if_unmodified_since = val;
-        else if (name == "accept-encoding") p.rq.accept_encoding = val;
-        else if (name == "content-length") { if (atoll(val.c_str()) > 0) p.has_body = true; }
-        else if (name == "transfer-encoding") p.has_body = true;
-        else if (name == "referer") p.referer = val;
-        else if (name == "user-agent") p.user_agent = val;
-        else if (name == "x-forwarded-for") p.x_forwarded_for = val;
-        else if (name == "connection") {
-            const std::string v = lower(val);
-            if (v.find("close") != std::string::npos) p.keep_alive = false;
-            else if (v.find("keep-alive") != std::string::npos) p.keep_alive = true;
-        }
-    }
-    p.ok = true;
-    return p;
 }
 
 // ---- origin fetch (miss path) ------------------------------------------------
@@ -967,9 +911,9 @@ bool serve_one(Server& S, int fd, const std::string& client_ip, const std::strin
     nzh::Plan plan;
     std::shared_ptr<Entry> ent;
     bool keep = pr.keep_alive;
-    auto stock = [&](int code) { plan = nzh::error_page(code, pr.ok && pr.rq.method == "HEAD"); };
-    if (!pr.ok) {
-        stock(400);
+    auto stock = [&](int code) { plan = nzh::error_page(code, !pr.error && pr.rq.method == "HEAD"); };
+    if (pr.error) {
+        stock(pr.error);
         keep = false;
     } else if (!nzh::method_allowed(pr.rq.method) || (pr.rq.method != "GET" && pr.rq.method != "HEAD")) {
         stock(405);
@@ -1040,8 +984,7 @@ bool serve_one(Server& S, int fd, const std::string& client_ip, const std::strin
     }
     // a request that carries a body is answered and the connection closed: the body is never read (nginx would
     // discard it; parsing it as the next request must not happen)
-    if (pr.ok && pr.has_body) keep = false;
-    if (pr.ok && pr.rq.http_minor < 1) keep = false;
+    if (!pr.error && pr.has_body) keep = false;
     const bool sent = send_plan(S, fd, plan, ent.get(), keep, cw, t_req);
     access_log_line(S, client_ip, pr, plan.status, plan.head ? 0 : plan.body_length());
     if (ent) ent->inflight--;
@@ -1246,9 +1189,9 @@ void Worker::try_start(EvConn* c) {
         Parsed& pr = c->pr;
         c->keep = pr.keep_alive;
         c->ent.reset();
-        auto stock = [&](int code) { c->plan = nzh::error_page(code, pr.ok && pr.rq.method == "HEAD"); };
-        if (!pr.ok) {
-            stock(400);
+        auto stock = [&](int code) { c->plan = nzh::error_page(code, !pr.error && pr.rq.method == "HEAD"); };
+        if (pr.error) {
+            stock(pr.error);
             c->keep = false;
         } else if (!nzh::method_allowed(pr.rq.method) || (pr.rq.method != "GET" && pr.rq.method != "HEAD")) {
             stock(405);
@@ -1280,8 +1223,7 @@ void Worker::try_start(EvConn* c) {
                 c->plan = nzh::plan_response(cfg, pr.rq, c->ent->meta, Sv.boundary.fetch_add(1));
             }
         }
-        if (pr.ok && pr.has_body) c->keep = false;
-        if (pr.ok && pr.rq.http_minor < 1) c->keep = false;
+        if (!pr.error && pr.has_body) c->keep = false;
         start_response(c);
     }
 }

@@ -96,3 +96,12 @@ def admission(status: int, headers, now: int, default_valid_s: int = 86400):
     vu = C.c_int64()
     c = load().nzh_admission(status, blob, now, default_valid_s, C.byref(vu))
     return bool(c), vu.value
+
+
+def parse_head_text(raw: bytes) -> str:
+    """SPEC P: nzh::parse_head(raw).to_text() (raw = the bytes before the blank line)"""
+    out = C.create_string_buffer(len(raw) + 4096)
+    n = load().nzh_parse_head_text(raw, len(raw), out, len(out))
+    if n < 0:
+        raise RuntimeError("head overflow")
+    return out.raw[:n].decode("latin-1")

@@ -137,7 +137,7 @@ static const char* status_text(int c) {
     switch (c) {
     case 200: return "OK"; case 206: return "Partial Content"; case 304: return "Not Modified";
     case 400: return "Bad Request"; case 405: return "Not Allowed"; case 412: return "Precondition Failed";
-    case 416: return "Requested Range Not Satisfiable"; case 504: return "Gateway Time-out";
+    case 416: return "Requested Range Not Satisfiable"; case 504: return "Gateway Time-out"; case 505: return "HTTP Version Not Supported";
     default: return "Error";
     }
 }
@@ -146,24 +146,6 @@ static void free_resp(conn* c) {
     free(c->head); c->head = NULL;
     for (int i = 0; i < c->nseg; i++) free(c->segs[i].bytes);
     c->nseg = 0; c->cur = 0; c->seg_done = 0; c->out_len = c->out_off = 0; c->active = 0;
-}
-
-static char* hdr_val(char* head, const char* name) {   /* returns malloc'd trimmed value or NULL */
-    size_t nl = strlen(name);
-    for (char* p = strstr(head, "\r\n"); p; p = strstr(p + 2, "\r\n")) {
-        char* h = p + 2;
-        if (strncasecmp(h, name, nl) == 0 && h[nl] == ':') {
-            char* v = h + nl + 1;
-            while (*v == ' ' || *v == '\t') v++;
-            char* e = strstr(v, "\r\n");
-            size_t n = e ? (size_t)(e - v) : strlen(v);
-            while (n && (v[n - 1] == ' ' || v[n - 1] == '\t')) n--;
-            char* out = malloc(n + 1);
-            memcpy(out, v, n); out[n] = 0;
-            return out;
-        }
-    }
-    return NULL;
 }
 
 static void simple_page(conn* c, int code, int keep) {
@@ -178,24 +160,45 @@ static void simple_page(conn* c, int code, int keep) {
 
 /* build the response for one parsed request head (NUL-terminated, ends with CRLF) */
 static void build_response(conn* c, char* head) {
-    char method[32] = "", target[8192] = "", ver[16] = "";
-    int nf = sscanf(head, "%31s %8191s %15s", method, target, ver);
-    int minor = 1, keep = 1;
-    if (nf < 2) { simple_page(c, 400, 0); return; }
-    if (nf == 2) { minor = -1; keep = 0; }
-    else if (!strcmp(ver, "HTTP/1.0")) { minor = 0; keep = 0; }
-    else if (strcmp(ver, "HTTP/1.1")) { simple_page(c, 400, 0); return; }
-    char* hv_conn = hdr_val(head, "Connection");
-    if (hv_conn) { if (strcasestr(hv_conn, "close")) keep = 0; else if (strcasestr(hv_conn, "keep-alive")) keep = 1; free(hv_conn); }
-    if (minor < 1 && nf == 3 && !keep) keep = 0;
-    char* host = hdr_val(head, "Host");
+    /* SPEC P: the head goes through the oracle's own parser (nzo_parse_head); its text form is read back here */
+    static __thread char ptxt[40960];
+    char method[64] = "", target[8192] = "";
+    int minor = 1, keep = 1, body = 0, perr = 400;
+    char *host = NULL, *a = NULL, *b = NULL, *d = NULL, *e = NULL, *f = NULL, *g = NULL, *h = NULL;
+    if (nzo_parse_head(head, strlen(head), ptxt, sizeof ptxt) >= 0) {
+        char* save0 = NULL;
+        for (char* ln = strtok_r(ptxt, "\n", &save0); ln; ln = strtok_r(NULL, "\n", &save0)) {
+            if (!strncmp(ln, "error ", 6)) perr = atoi(ln + 6);
+            else if (!strncmp(ln, "method ", 7)) snprintf(method, sizeof method, "%s", ln + 7);
+            else if (!strncmp(ln, "target ", 7)) snprintf(target, sizeof target, "%s", ln + 7);
+            else if (!strncmp(ln, "minor ", 6)) minor = atoi(ln + 6);
+            else if (!strncmp(ln, "keep ", 5)) keep = atoi(ln + 5);
+            else if (!strncmp(ln, "body ", 5)) body = atoi(ln + 5);
+            else if (!strncmp(ln, "f ", 2)) {
+                char* colon = strstr(ln + 2, ": ");
+                if (!colon) continue;
+                *colon = 0;
+                char* v = strdup(colon + 2);
+                const char* n = ln + 2;
+                if (!strcmp(n, "host")) host = v;
+                else if (!strcmp(n, "range")) a = v;
+                else if (!strcmp(n, "if-range")) b = v;
+                else if (!strcmp(n, "if-none-match")) d = v;
+                else if (!strcmp(n, "if-match")) e = v;
+                else if (!strcmp(n, "if-modified-since")) f = v;
+                else if (!strcmp(n, "if-unmodified-since")) g = v;
+                else if (!strcmp(n, "accept-encoding")) h = v;
+                else free(v);
+            }
+        }
+    }
+    char* plan = NULL;
+    if (perr) { simple_page(c, perr, 0); goto done; }
+    if (body) keep = 0;                       /* P10: a body is never read: answer, then close */
     nzo_request rq;
     memset(&rq, 0, sizeof rq);
     rq.method = method; rq.http_minor = minor;
-    char *a = hdr_val(head, "Range"), *b = hdr_val(head, "If-Range"), *d = hdr_val(head, "If-None-Match"), *e = hdr_val(head, "If-Match"),
-         *f = hdr_val(head, "If-Modified-Since"), *g = hdr_val(head, "If-Unmodified-Since"), *h = hdr_val(head, "Accept-Encoding");
     rq.range = a; rq.if_range = b; rq.if_none_match = d; rq.if_match = e; rq.if_modified_since = f; rq.if_unmodified_since = g; rq.accept_encoding = h;
-    char* plan = NULL;
     const obj* o = NULL;
     if (!nzo_method_gate(method) || (strcmp(method, "GET") && strcmp(method, "HEAD"))) {
         simple_page(c, 405, keep);

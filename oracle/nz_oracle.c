@@ -263,6 +263,146 @@ static int norm_host(const char* h, size_t n, char* out, size_t cap) {
     return (int)end;
 }
 
+/* ---------------------------------------------------------------------------
+ * SPEC P: the request head.  Lines are walked in place; field values are (pointer, length) pairs into raw.
+ * ------------------------------------------------------------------------- */
+typedef struct { const char* p; size_t n; int set; } hfield;
+static int name_is(const char* a, size_t n, const char* lit) {
+    return strlen(lit) == n && strncasecmp(a, lit, n) == 0;
+}
+static int contains_ci(const char* p, size_t n, const char* needle) {
+    size_t m = strlen(needle);
+    for (size_t i = 0; i + m <= n; i++) if (strncasecmp(p + i, needle, m) == 0) return 1;
+    return 0;
+}
+int nzo_parse_head(const char* raw, size_t n, char* out, size_t cap) {
+    static const char* const kept[8] = {"accept-encoding", "host", "if-match", "if-modified-since", "if-none-match", "if-range", "if-unmodified-since", "range"};
+    static const char* const uniq[9] = {"if-modified-since", "if-unmodified-since", "if-match", "if-none-match", "if-range", "content-length", "content-range", "expect", "authorization"};
+    hfield kf[8];
+    int useen[9];
+    memset(kf, 0, sizeof kf);
+    memset(useen, 0, sizeof useen);
+    int error = 0, minor = 1, keep = 1, body = 0, hosts = 0;
+    const char *method = NULL, *target = NULL;
+    size_t mlen = 0, tlen = 0;
+    while (n && (raw[0] == '\r' || raw[0] == '\n')) { raw++; n--; }          /* P: CR/LF before the request line */
+    while (n >= 2 && raw[n - 2] == '\r' && raw[n - 1] == '\n') n -= 2;
+    for (size_t i = 0; i < n; i++) {                                         /* P2: NUL, bare CR, bare LF */
+        if (raw[i] == 0) { error = 400; goto emit; }
+        if (raw[i] == '\r' && (i + 1 >= n || raw[i + 1] != '\n')) { error = 400; goto emit; }
+        if (raw[i] == '\n' && (i == 0 || raw[i - 1] != '\r')) { error = 400; goto emit; }
+    }
+    {
+        size_t le = 0;
+        while (le < n && raw[le] != '\r') le++;
+        size_t j = 0;
+        while (j < le && ((raw[j] >= 'A' && raw[j] <= 'Z') || raw[j] == '_')) j++;
+        if (j == 0 || j >= le || raw[j] != ' ') { error = 400; goto emit; }   /* P1 */
+        method = raw; mlen = j;
+        while (j < le && raw[j] == ' ') j++;
+        size_t k = j;
+        while (k < le && raw[k] != ' ') k++;
+        target = raw + j; tlen = k - j;
+        if (tlen == 0) { error = 400; goto emit; }
+        if (target[0] != '/') {                                               /* P2: absolute-form */
+            size_t m = 0;
+            while (m < tlen && isalpha((unsigned char)target[m]) && (unsigned char)target[m] < 128) m++;
+            if (m == 0 || m + 3 > tlen || memcmp(target + m, "://", 3) != 0) { error = 400; goto emit; }
+        }
+        size_t a = k, b = le;
+        while (a < b && raw[a] == ' ') a++;
+        while (b > a && raw[b - 1] == ' ') b--;
+        if (a == b) {                                                         /* P3: HTTP/0.9 */
+            if (!(mlen == 3 && memcmp(method, "GET", 3) == 0)) { error = 400; goto emit; }
+            minor = -1; keep = 0;
+        } else {                                                              /* P4 */
+            const char* v = raw + a;
+            size_t vn = b - a;
+            if (vn < 8 || memcmp(v, "HTTP/", 5) != 0) { error = 400; goto emit; }
+            size_t q = 5, d1 = 0, d2 = 0;
+            int major = 0, mn = 0;
+            while (q < vn && isdigit((unsigned char)v[q]) && d1 < 3) { major = major * 10 + (v[q] - '0'); q++; d1++; }
+            if (d1 < 1 || d1 > 2 || v[5] == '0' || q >= vn || v[q] != '.') { error = 400; goto emit; }
+            q++;
+            while (q < vn && isdigit((unsigned char)v[q]) && d2 < 3) { mn = mn * 10 + (v[q] - '0'); q++; d2++; }
+            if (d2 < 1 || d2 > 2 || q != vn) { error = 400; goto emit; }
+            if (major > 1) { error = 505; goto emit; }
+            minor = mn == 0 ? 0 : 1;
+            keep = minor == 1;
+        }
+        size_t pos = le;
+        while (pos < n) {                                                     /* P5-P10 */
+            pos += 2;                                                         /* the CRLF that ended the previous line */
+            size_t e = pos;
+            while (e < n && raw[e] != '\r') e++;
+            if (e == pos) break;
+            const char* ln = raw + pos;
+            size_t ll = e - pos, c = 0;
+            pos = e;
+            while (c < ll && ln[c] != ':') c++;
+            size_t nl = c;
+            const char* val = c < ll ? ln + c + 1 : ln + ll;
+            size_t vl = c < ll ? ll - c - 1 : 0;
+            int valid = nl > 0;
+            for (size_t i = 0; i < nl && valid; i++) {
+                unsigned char ch = (unsigned char)ln[i];
+                if (!(ch < 128 && (isalnum(ch) || ch == '-'))) valid = 0;
+            }
+            if (!valid) continue;
+            while (vl && val[0] == ' ') { val++; vl--; }
+            while (vl && val[vl - 1] == ' ') vl--;
+            if (name_is(ln, nl, "host")) {
+                char tmp[1024];
+                hosts++;
+                if (vl >= sizeof tmp || norm_host(val, vl, tmp, sizeof tmp) < 0) { error = 400; goto emit; }
+                if (hosts == 1) { kf[1].p = val; kf[1].n = vl; kf[1].set = 1; }
+                continue;
+            }
+            if (name_is(ln, nl, "range") || name_is(ln, nl, "accept-encoding")) {   /* P6 */
+                hfield* f = name_is(ln, nl, "range") ? &kf[7] : &kf[0];
+                if (!f->set) { f->p = val; f->n = vl; f->set = 1; }
+                continue;
+            }
+            int u = -1;
+            for (int i = 0; i < 9; i++) if (name_is(ln, nl, uniq[i])) u = i;
+            if (u >= 0) {                                                     /* P7 */
+                if (useen[u]) { error = 400; goto emit; }
+                useen[u] = 1;
+                for (int i = 0; i < 8; i++) if (name_is(ln, nl, kept[i])) { kf[i].p = val; kf[i].n = vl; kf[i].set = 1; }
+                if (u == 5) {                                                 /* P10 */
+                    if (vl == 0) { error = 400; goto emit; }
+                    int nz = 0;
+                    for (size_t i = 0; i < vl; i++) { if (!isdigit((unsigned char)val[i])) { error = 400; goto emit; } if (val[i] != '0') nz = 1; }
+                    if (nz) body = 1;
+                }
+                continue;
+            }
+            if (name_is(ln, nl, "transfer-encoding")) { body = 1; continue; }
+            if (name_is(ln, nl, "connection")) {                              /* P9 */
+                if (contains_ci(val, vl, "close")) keep = 0;
+                else if (contains_ci(val, vl, "keep-alive")) keep = 1;
+            }
+        }
+        if (minor == 1 && hosts == 0) error = 400;                            /* P8 */
+    }
+emit:;
+    size_t o = 0;
+    int w = snprintf(out, cap, "error %d\n", error);
+    if (w < 0 || (size_t)w >= cap) return -1;
+    o = (size_t)w;
+    if (error) return (int)o;
+    w = snprintf(out + o, cap - o, "method %.*s\ntarget %.*s\nminor %d\nkeep %d\nbody %d\n", (int)mlen, method, (int)tlen, target, minor, keep, body);
+    if (w < 0 || (size_t)w >= cap - o) return -1;
+    o += (size_t)w;
+    for (int i = 0; i < 8; i++) {
+        if (!kf[i].set) continue;
+        w = snprintf(out + o, cap - o, "f %s: %.*s\n", kept[i], (int)kf[i].n, kf[i].p);
+        if (w < 0 || (size_t)w >= cap - o) return -1;
+        o += (size_t)w;
+    }
+    return (int)o;
+}
+
 /* $uri: decode, resolve dot segments, merge slashes, cut at ? or # (SPEC K4) */
 static int norm_uri(const char* p, size_t n, char* out, size_t cap) {
     if (n == 0 || p[0] != '/') return -400;

@@ -57,6 +57,13 @@ int64_t nzo_parse_http_time(const char* s, size_t n);
 /* SPEC H2: headers = "Name: value\n" lines in arrival order; returns 1 cacheable / 0; *valid_until absolute seconds */
 int nzo_admission(int status, const char* headers, int64_t now, int64_t default_valid_s, int64_t* valid_until);
 
+/* ---- request head (SPEC P) --------------------------------------------- */
+/* raw: the bytes before the blank line.  Writes a text form: "error N" (0/400/505), and for error 0 "method M",
+ * "target T", "minor N" (-1/0/1), "keep 0|1", "body 0|1" and one "f name: value" line per field K/C/R/G read
+ * (host, range, if-range, if-none-match, if-match, if-modified-since, if-unmodified-since, accept-encoding), sorted by
+ * name.  Returns the length written or -1 (cap too small). */
+int nzo_parse_head(const char* raw, size_t n, char* out, size_t cap);
+
 /* ---- whole request plan (SPEC V,C,R,G,E) ------------------------------- */
 typedef struct nzo_request {
     const char* method;             /* "GET" */

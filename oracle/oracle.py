@@ -334,3 +334,12 @@ def admission(status: int, headers, now: int, default_valid_s: int = 86400):
     vu = C.c_int64()
     c = lib().nzo_admission(status, blob, now, default_valid_s, C.byref(vu))
     return bool(c), vu.value
+
+
+def parse_head_text(raw: bytes) -> str:
+    """SPEC P: nzo_parse_head's text form (raw = the bytes before the blank line)"""
+    out = C.create_string_buffer(len(raw) + 4096)
+    n = lib().nzo_parse_head(raw, len(raw), out, len(out))
+    if n < 0:
+        raise RuntimeError("head overflow")
+    return out.raw[:n].decode("latin-1")

@@ -847,3 +847,113 @@ def plan(rq: Request, ob: Stored, boundary: int = 1) -> Response:
     r.headers += common + enc
     r.body = pieces
     return r
+
+
+# ----------------------------------------------------------------------------------------------------------
+# P: the request head (ngx_http_parse_request_line, ngx_http_parse_header_line, the ngx_http_headers_in handlers)
+# ----------------------------------------------------------------------------------------------------------
+@dataclass
+class Head:
+    error: int = 0                      # 0, 400 or 505: answered before any vhost / cache logic runs
+    method: str = ""
+    target: str = ""
+    minor: int = 1                      # -1 = HTTP/0.9, 0 = HTTP/1.0, 1 = HTTP/1.1 or later
+    keep_alive: bool = True
+    has_body: bool = False
+    fields: dict = field(default_factory=dict)   # lower-case name -> value, only the names K/C/R/G read
+
+
+_FIRST_WINS = ("range", "accept-encoding")
+_UNIQUE = ("if-modified-since", "if-unmodified-since", "if-match", "if-none-match", "if-range", "content-length", "content-range", "expect", "authorization")
+
+
+def parse_head(raw: bytes) -> Head:
+    """SPEC P.  `raw` = everything before the blank line (with or without the final CRLF), as bytes."""
+    text = raw.decode("latin-1")
+    i = 0
+    while i < len(text) and text[i] in "\r\n":            # sw_start skips CR and LF before the request line
+        i += 1
+    text = text[i:]
+    while text.endswith("\r\n"):
+        text = text[:-2]
+    lines = text.split("\r\n")
+    bad = Head(error=400, keep_alive=False)
+    if "\0" in text or any("\r" in ln or "\n" in ln for ln in lines):
+        return bad
+    # ---- request line (P1-P4)
+    rl = lines[0]
+    j = 0
+    while j < len(rl) and ("A" <= rl[j] <= "Z" or rl[j] == "_"):
+        j += 1
+    if j == 0 or j >= len(rl) or rl[j] != " ":
+        return bad
+    h = Head(method=rl[:j])
+    while j < len(rl) and rl[j] == " ":
+        j += 1
+    k = rl.find(" ", j)
+    h.target = rl[j:] if k < 0 else rl[j:k]
+    if not h.target:
+        return bad
+    if not h.target.startswith("/"):
+        m = 0
+        while m < len(h.target) and h.target[m].isascii() and h.target[m].isalpha():
+            m += 1
+        if m == 0 or not h.target.startswith("://", m):
+            return bad
+    rest = "" if k < 0 else rl[k:].strip(" ")
+    if rest == "":
+        if h.method != "GET":
+            return bad
+        h.minor, h.keep_alive = -1, False
+    else:
+        if not rest.startswith("HTTP/"):
+            return bad
+        major, dot, minor = rest[5:].partition(".")
+        ok = (dot == "." and 1 <= len(major) <= 2 and 1 <= len(minor) <= 2 and major.isascii() and minor.isascii() and major.isdigit() and minor.isdigit()
+              and major[0] != "0")
+        if not ok:
+            return bad
+        if int(major) > 1:
+            return Head(error=505, keep_alive=False)
+        h.minor = 0 if int(minor) == 0 else 1
+        h.keep_alive = h.minor == 1
+    # ---- header lines (P5-P10)
+    hosts = 0
+    for ln in lines[1:]:
+        if ln == "":
+            break
+        name, colon, value = ln.partition(":")
+        if not colon:
+            name, value = ln, ""
+        if name == "" or any(not (c.isascii() and (c.isalnum() or c == "-")) for c in name):
+            continue                                          # ignore_invalid_headers on
+        name = name.lower()
+        value = value.strip(" ")
+        if name == "host":
+            hosts += 1
+            if normalize_host(value) is None:
+                return bad
+            if hosts == 1:
+                h.fields["host"] = value
+        elif name in _FIRST_WINS:
+            h.fields.setdefault(name, value)
+        elif name in _UNIQUE:
+            if name in h.fields:
+                return bad
+            h.fields[name] = value
+            if name == "content-length":
+                if value == "" or not (value.isascii() and value.isdigit()):
+                    return bad
+                if int(value) > 0:
+                    h.has_body = True
+        elif name == "transfer-encoding":
+            h.has_body = True
+        elif name == "connection":
+            low = value.lower()
+            if "close" in low:
+                h.keep_alive = False
+            elif "keep-alive" in low:
+                h.keep_alive = True
+    if h.minor == 1 and hosts == 0:
+        return bad
+    return h

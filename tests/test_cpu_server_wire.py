@@ -115,3 +115,74 @@ def test_pipelined_keep_alive_requests_come_back_in_order(wire):
         buf = rest[n:]
     s.close()
     assert got == [b for _, b in reqs]
+
+
+# ---- SPEC P on the wire: raw request heads, answered by status (and the first body bytes) ---------------------------
+def raw_exchange(port, head: bytes, timeout=5.0):
+    """send one raw head, read one response; returns (status, headers dict, body)"""
+    s = socket.create_connection(("127.0.0.1", port), timeout)
+    s.settimeout(timeout)
+    s.sendall(head)
+    buf = b""
+    while b"\r\n\r\n" not in buf:
+        chunk = s.recv(65536)
+        if not chunk:
+            break
+        buf += chunk
+    hd, _, rest = buf.partition(b"\r\n\r\n")
+    lines = hd.split(b"\r\n")
+    status = int(lines[0].split()[1])
+    hdrs = {}
+    for ln in lines[1:]:
+        k, _, v = ln.partition(b":")
+        hdrs[k.decode().lower()] = v.strip().decode("latin-1")
+    n = int(hdrs.get("content-length", "0"))
+    is_head = head.lstrip(b"\r\n").startswith(b"HEAD ")
+    while not is_head and status not in (304,) and len(rest) < n:
+        chunk = s.recv(65536)
+        if not chunk:
+            break
+        rest += chunk
+    s.close()
+    return status, hdrs, rest
+
+
+def P_CASES(host: str, path: str, etag: str):
+    """(raw head, expected status, expected Content-Range or None, expected Connection) - SPEC P rule in the comment"""
+    H = f"Host: {host}\r\n".encode()
+    G = f"GET {path} HTTP/1.1\r\n".encode()
+    E = etag.encode()
+    return [
+        (G + H + b"\r\n", 200, None, "keep-alive"),
+        (f"get {path} HTTP/1.1\r\n".encode() + H + b"\r\n", 400, None, "close"),                               # P1: not a 405
+        (f"POST {path} HTTP/1.1\r\n".encode() + H + b"Content-Length: 0\r\n\r\n", 405, None, "keep-alive"),    # V2 sees well-formed methods only
+        (f"GET {path} HTTP/2.0\r\n".encode() + H + b"\r\n", 505, None, "close"),                               # P4
+        (f"GET {path} HTTP/1.7\r\n".encode() + H + b"\r\n", 200, None, "keep-alive"),                          # P4: behaves as 1.1
+        (G + b"\r\n", 400, None, "close"),                                                                     # P8: 1.1 needs Host
+        (f"GET {path} HTTP/1.0\r\n".encode() + H + b"Connection: Keep-Alive\r\n\r\n", 200, None, "keep-alive"),   # P9
+        (f"GET {path} HTTP/1.0\r\n".encode() + H + b"\r\n", 200, None, "close"),
+        (G + H + b"Range: bytes=0-9\r\nRange: bytes=100-199\r\n\r\n", 206, "bytes 0-9/", "keep-alive"),        # P6: first Range line
+        (G + H + b"Host: other.example\r\n\r\n", 200, None, "keep-alive"),                                     # P8: first Host line
+        (G + H + b"Host: a..b\r\n\r\n", 400, None, "close"),                                                   # P8: every Host line validated
+        (G + H + b"If-None-Match: " + E + b"\r\nIf-None-Match: " + E + b"\r\n\r\n", 400, None, "close"),     # P7
+        (G + H + b"If-Match: " + E + b"\r\nif-match: \"x\"\r\n\r\n", 400, None, "close"),
+        (G + H + b"If-Range: " + E + b"\r\nIf-Range: " + E + b"\r\nRange: bytes=0-0\r\n\r\n", 400, None, "close"),
+        (G + H + b"Range : bytes=0-9\r\nX_Y: 1\r\n: v\r\n\r\n", 200, None, "keep-alive"),                      # P5: ignored lines
+        (G + H + b"Connection: close\r\nConnection: keep-alive\r\n\r\n", 200, None, "keep-alive"),             # P9: in order
+        (G + H + b"Content-Length: 1x\r\n\r\n", 400, None, "close"),                                           # P10
+        (b"\r\n" + G + H + b"Range:   bytes=5-6  \r\n\r\n", 206, "bytes 5-6/", "keep-alive"),                  # leading CRLF; spaces trimmed
+    ]
+
+
+def test_request_head_rules_on_the_wire(wire):
+    port, aio = wire
+    for head, status, crange, conn in P_CASES(HOST, PATH, aio.etag):
+        st, hdrs, body = raw_exchange(port, head)
+        assert st == status, (head, st, status)
+        assert hdrs.get("connection") == conn, (head, hdrs.get("connection"), conn)
+        if crange:
+            assert hdrs.get("content-range", "").startswith(crange), (head, hdrs.get("content-range"))
+        if st == 200 and not head.lstrip(b"\r\n").startswith(b"HEAD"):
+            assert body == DATA, head
+        if st in (400, 405, 505):
+            assert hdrs.get("content-type") == "text/html" and f"<title>{st} ".encode() in body, (head, body[:80])

@@ -616,3 +616,21 @@ def test_nzproxy_answers_like_aiohttp_on_the_wire(servers, tmp_path):
                 assert hdrs.get("etag") == aio.etag and hdrs.get("last-modified") == LM and hdrs.get("server") == "nginx"
     finally:
         del OBJECTS[path]
+
+
+def test_request_head_rules_gpu_front_end_vs_cpu_server(servers):
+    """SPEC P on the wire, raw heads: duplicate / ignored / invalid header lines, lower-case methods, HTTP/2.0, HTTP/1.1
+    without Host, keep-alive on 1.0 - nzproxy and the nginx-restated CPU server must give the same status, Connection,
+    Content-Range and body (the CPU server alone is pinned to the expected values in tests/test_cpu_server_wire.py)."""
+    from test_cpu_server_wire import P_CASES, raw_exchange
+
+    gpu_port, cpu_port = servers
+    host, path = "www.cs.toronto.edu", "/~kriz/cifar-100-python.tar.gz"
+    fetch(gpu_port, "GET", host, path, {"Range": "bytes=0-0"})                  # make it a hit
+    for head, status, _crange, conn in P_CASES(host, path, OBJECTS[path][3]):
+        g = raw_exchange(gpu_port, head, 20)
+        c = raw_exchange(cpu_port, head, 20)
+        assert g[0] == c[0] == status, (head, g[0], c[0], status)
+        assert g[1].get("connection") == c[1].get("connection") == conn, (head, g[1].get("connection"), c[1].get("connection"))
+        assert g[1].get("content-range") == c[1].get("content-range"), head
+        assert g[2] == c[2], (head, len(g[2]), len(c[2]))

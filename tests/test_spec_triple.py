@@ -185,3 +185,81 @@ def test_Z5_no_ranges_unless_the_upstream_response_said_accept_ranges():
 def test_Z4_day_zero_parses_like_nginx():
     for fn in (sp.parse_http_time, o.parse_http_time, h.parse_http_date):
         assert fn("Wed, 00 Nov 2018 15:20:01 GMT") == fn("Wed, 31 Oct 2018 15:20:01 GMT") != -1
+
+
+# ---- P: the request head -------------------------------------------------------------------------------------------
+KEPT = ("accept-encoding", "host", "if-match", "if-modified-since", "if-none-match", "if-range", "if-unmodified-since", "range")
+
+
+def _head_py(raw: bytes):
+    r = sp.parse_head(raw)
+    if r.error:
+        return (r.error,)
+    return (0, r.method, r.target, r.minor, r.keep_alive, r.has_body, tuple((k, r.fields[k]) for k in KEPT if k in r.fields))
+
+
+def _head_text(t: str):
+    lines = t.split("\n")
+    err = int(lines[0].split(" ", 1)[1])
+    if err:
+        return (err,)
+    d = {}
+    fields = []
+    for ln in lines[1:]:
+        if not ln:
+            continue
+        k, _, v = ln.partition(" ")
+        if k == "f":
+            n, _, val = v.partition(": ")
+            fields.append((n, val))
+        else:
+            d[k] = v
+    return (0, d["method"], d["target"], int(d["minor"]), d["keep"] == "1", d["body"] == "1", tuple(fields))
+
+
+REQ_LINES = ["GET / HTTP/1.1", "GET /a/b?x=1 HTTP/1.0", "HEAD /x HTTP/1.1", "GET /", "POST /", "get / HTTP/1.1", "GET  /two-spaces   HTTP/1.1  ", "GET / HTTP/1.2", "GET / HTTP/2.0",
+             "GET / HTTP/1.10", "GET / HTTP/01.1", "GET / HTTP/1.", "GET / HTTP/1.100", "GET / http/1.1", "GET / HTTP/1.1 x", "GET http://yann.lecun.com/p HTTP/1.1",
+             "GET yann.lecun.com/p HTTP/1.1", "GET ://x HTTP/1.1", "G_T / HTTP/1.1", "G-T / HTTP/1.1", "GET", "GET ", " GET / HTTP/1.1", "GET /a b HTTP/1.1", "PURGE / HTTP/1.1",
+             "GET / HTTP/9.9", "GET / HTTP/10.0", "GET / HTTP/0.9", "GET /\t HTTP/1.1", "GET * HTTP/1.1"]
+HDR_NAMES = ["Host", "host", "HOST", "Range", "range", "If-Range", "If-Match", "if-match", "If-None-Match", "If-Modified-Since", "If-Unmodified-Since", "Accept-Encoding",
+             "Connection", "Content-Length", "Transfer-Encoding", "Expect", "Authorization", "X-Real-IP", "X_Underscore", "Host ", " Host", "", "Ra nge", "Räng", "User-Agent",
+             "Content-Range", "Referer"]
+HDR_VALUES = ["a", "A.B.", "www.cs.toronto.edu", "a..b", "", " ", "  bytes=0-1  ", "bytes=5-", "\tx", "x\t", "close", "Keep-Alive", "keep-alive, close", "Upgrade", "0", "00", "10", "1x", "-1",
+              '"etag"', "Wed, 07 Nov 2018 15:20:01 GMT", "gzip", "chunked", "a/b", "a:80", "[::1]:8"]
+
+
+@SET
+@given(st.sampled_from(REQ_LINES), st.lists(st.tuples(st.sampled_from(HDR_NAMES), st.sampled_from([":", ": ", ":  ", " : ", ""]), st.sampled_from(HDR_VALUES)), max_size=7),
+       st.sampled_from(["", "\r\n", "\r\n\r\n", "\n"]), st.sampled_from(["\r\n", "\r\n", "\r\n", "\n", "\r", "\r\n\0"]))
+def test_request_head_three_way(rl, hdrs, lead, eol):
+    raw = (lead + rl + eol + "".join(n + sep + v + "\r\n" for n, sep, v in hdrs)).encode("latin-1")
+    a, b, c = _head_py(raw), _head_text(o.parse_head_text(raw)), _head_text(h.parse_head_text(raw))
+    assert a == b == c, (raw, a, b, c)
+
+
+def test_P_rules_by_name():
+    def every(raw):
+        a, b, c = _head_py(raw), _head_text(o.parse_head_text(raw)), _head_text(h.parse_head_text(raw))
+        assert a == b == c, (raw, a, b, c)
+        return a
+
+    ok = every(b"GET /x HTTP/1.1\r\nHost: A\r\n")
+    assert ok[:6] == (0, "GET", "/x", 1, True, False)
+    assert every(b"get /x HTTP/1.1\r\nHost: a\r\n") == (400,)                                  # P1: lower-case method never reaches the 405 gate
+    assert every(b"POST /x\r\n") == (400,) and every(b"GET /x\r\n")[3] == -1                     # P3
+    assert every(b"GET / HTTP/2.0\r\nHost: a\r\n") == (505,)                                     # P4
+    assert every(b"GET / HTTP/1.7\r\nHost: a\r\n")[3] == 1                                       # P4: any minor but 0 behaves as 1.1
+    assert every(b"GET / HTTP/1.1\r\n") == (400,) and every(b"GET / HTTP/1.0\r\n")[0] == 0       # P8: Host required from 1.1 on
+    r = every(b"GET / HTTP/1.1\r\nHost: first\r\nHost: second\r\nRange: bytes=0-0\r\nRange: bytes=5-5\r\n")
+    assert dict(r[6]) == {"host": "first", "range": "bytes=0-0"}                                 # P6/P8: first line counts
+    assert every(b"GET / HTTP/1.1\r\nHost: ok\r\nHost: a..b\r\n") == (400,)                       # P8: every Host line is validated
+    for name in (b"If-Match", b"If-None-Match", b"If-Range", b"If-Modified-Since", b"If-Unmodified-Since", b"Content-Length"):
+        assert every(b"GET / HTTP/1.1\r\nHost: a\r\n" + name + b": 1\r\n" + name.lower() + b": 1\r\n") == (400,)     # P7
+    r = every(b"GET / HTTP/1.1\r\nHost: a\r\nX_Y: 1\r\nRange : bytes=0-0\r\n: v\r\n")
+    assert dict(r[6]) == {"host": "a"}                                                            # P5: invalid names are ignored
+    assert every(b"GET / HTTP/1.1\r\nHost: a\r\nConnection: close\r\nConnection: keep-alive\r\n")[4] is True          # P9: in order
+    assert every(b"GET / HTTP/1.0\r\nConnection: Keep-Alive\r\n")[4] is True
+    assert every(b"GET / HTTP/1.1\r\nHost: a\r\nContent-Length: 1x\r\n") == (400,)                # P10
+    assert every(b"GET / HTTP/1.1\r\nHost: a\r\nContent-Length: 5\r\n")[5] is True
+    assert every(b"\r\n\r\nGET / HTTP/1.1\r\nHost: a\r\n")[0] == 0                                # CR/LF before the request line
+    assert every(b"GET / HTTP/1.1\r\nHost: a\0b\r\n") == (400,)
