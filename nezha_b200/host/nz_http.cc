@@ -631,7 +631,7 @@ Admission admission(int status, const std::vector<std::pair<std::string, std::st
     for (const auto& h : headers) {
         const std::string_view name = h.first, val = h.second;
         if (ieq(name, "set-cookie")) cacheable = false;            // H2b
-        else if (ieq(name, "vary")) { if (val == "*") cacheable = false; }
+        else if (ieq(name, "vary")) { if (val == "*" || val.size() > 128) cacheable = false; }   // "*" or longer than NGX_HTTP_CACHE_VARY_LEN
         else if (ieq(name, "x-accel-expires")) {                   // H2c
             xae_seen = true;
             if (!val.empty() && val[0] == '@') {

@@ -1090,7 +1090,7 @@ int nzo_admission(int status, const char* headers, int64_t now, int64_t default_
             if (h2_name_is(p, nlen, "Set-Cookie")) {                        /* H2b */
                 cacheable = 0;
             } else if (h2_name_is(p, nlen, "Vary")) {
-                if (vl == 1 && v[0] == '*') cacheable = 0;
+                if ((vl == 1 && v[0] == '*') || vl > 128) cacheable = 0;   /* NGX_HTTP_CACHE_VARY_LEN (128 since 1.11.10) */
             } else if (h2_name_is(p, nlen, "X-Accel-Expires")) {            /* H2c */
                 seen_xae = 1;
                 if (vl && v[0] == '@') {

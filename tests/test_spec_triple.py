@@ -116,7 +116,8 @@ def test_plan_three_way(method, minor, rng, if_range, inm, im, ims, ius, ae, sle
 
 HN = ["Cache-Control", "X-Accel-Expires", "Expires", "Set-Cookie", "Vary", "ETag", "cache-control", "EXPIRES"]
 HV = ["max-age=60", "s-maxage=5, max-age=9", "no-cache", "private, max-age=5", "max-age=0", "max-age=x", "0", "30", "@1700000000", "@", "abc",
-      "Wed, 07 Nov 2018 15:20:01 GMT", "Wed, 07 Nov 2040 15:20:01 GMT", "junk", "*", "Accept-Encoding", "a=b", "MAX-AGE=7", "public,max-age=10;x", "", "@12x", "007"]
+      "Wed, 07 Nov 2018 15:20:01 GMT", "Wed, 07 Nov 2040 15:20:01 GMT", "junk", "*", "Accept-Encoding", "a=b", "MAX-AGE=7", "public,max-age=10;x", "", "@12x", "007",
+      "Origin, " * 16, "x" * 128, "x" * 129]
 
 
 @SET
