@@ -186,3 +186,43 @@ def test_request_head_rules_on_the_wire(wire):
             assert body == DATA, head
         if st in (400, 405, 505):
             assert hdrs.get("content-type") == "text/html" and f"<title>{st} ".encode() in body, (head, body[:80])
+
+
+def test_body_loop_on_an_object_larger_than_the_output_buffers(tmp_path):
+    """the pread-32-KiB + send loop (SPEC B1) on 1 MiB + 17 bytes: random single ranges and a three-part request, bodies
+    compared with slices of the source (no planner in between)"""
+    import random
+
+    from test_third_party_witness import parts_of
+
+    big = bytes(random.Random(5).getrandbits(8) for _ in range((1 << 20) + 17))
+    hx = o.md5(o.cache_key(HOST, "/big.bin")).hex()
+    (tmp_path / hx).write_bytes(big)
+    (tmp_path / "manifest").write_text(f'{hx} {len(big)} -1 application/octet-stream "big" - {LM}\n')
+    port = free_port()
+    p = subprocess.Popen([os.path.join(ROOT, "oracle", "_build", "nz_cpu_server"), "--root", str(tmp_path), "--listen", f"127.0.0.1:{port}"], start_new_session=True)
+    try:
+        t0 = time.time()
+        while time.time() - t0 < 20:
+            try:
+                socket.create_connection(("127.0.0.1", port), 0.2).close(); break
+            except OSError:
+                time.sleep(0.05)
+        rnd = random.Random(6)
+        n = len(big)
+        assert ask_cpu(port, "GET", {}, "/big.bin")[4] == big
+        for _ in range(40):
+            a = rnd.randrange(n)
+            b = min(n - 1, a + rnd.choice([0, 1, 32767, 32768, 32769, 65536, 300_000, n]))
+            st, cr, cl, _ct, body, _h = ask_cpu(port, "GET", {"Range": f"bytes={a}-{b}"}, "/big.bin")
+            assert (st, cr, cl) == (206, f"bytes {a}-{b}/{n}", str(b - a + 1)) and body == big[a:b + 1], (a, b)
+        st, _cr, cl, ct, body, _h = ask_cpu(port, "GET", {"Range": "bytes=0-40000,500000-500000,-70000"}, "/big.bin")
+        assert st == 206 and int(cl) == len(body)
+        got = parts_of(ct, body)
+        assert [c for c, _ in got] == [f"bytes 0-40000/{n}", f"bytes 500000-500000/{n}", f"bytes {n - 70000}-{n - 1}/{n}"]
+        assert [b_ for _, b_ in got] == [big[0:40001], big[500000:500001], big[n - 70000:]]
+    finally:
+        try:
+            os.killpg(p.pid, signal.SIGTERM)
+        except ProcessLookupError:
+            pass
