@@ -226,3 +226,48 @@ def test_body_loop_on_an_object_larger_than_the_output_buffers(tmp_path):
             os.killpg(p.pid, signal.SIGTERM)
         except ProcessLookupError:
             pass
+
+
+# ---- the whole request path of the CPU server against the pure-Python restatement, head to status ---------------------
+def _model_status(raw_head: bytes, known_key: bytes, etag: str):
+    """what oracle/spec_py.py says the server must answer for this head: P (head) -> V2 (method) -> K (key) -> hit/miss -> C/R"""
+    from oracle import spec_py as sp
+
+    h_ = sp.parse_head(raw_head)
+    if h_.error:
+        return h_.error
+    if not sp.method_gate(h_.method) or h_.method not in ("GET", "HEAD"):
+        return 405
+    key = sp.cache_key(h_.fields.get("host"), h_.target)
+    if key is None:
+        return 400
+    if key != known_key:
+        return 504                                           # the oracle server has no origin: a miss is a gateway time-out
+    f = h_.fields
+    r = sp.plan(sp.Request(h_.method, h_.minor, f.get("range"), f.get("if-range"), f.get("if-none-match"), f.get("if-match"), f.get("if-modified-since"),
+                           f.get("if-unmodified-since"), f.get("accept-encoding")), sp.Stored(L, "application/octet-stream", etag, LM, None, -1, False, True), 7)
+    return r.status
+
+
+def test_whole_request_path_against_the_python_model(wire):
+    import random
+
+    from oracle import spec_py as sp
+
+    port, aio = wire
+    known = sp.cache_key(HOST, PATH)
+    rnd = random.Random(11)
+    lines = [f"GET {PATH} HTTP/1.1", f"HEAD {PATH} HTTP/1.1", f"GET {PATH} HTTP/1.0", f"GET {PATH}", f"get {PATH} HTTP/1.1", f"POST {PATH} HTTP/1.1", f"XGETX {PATH} HTTP/1.1",
+             f"GET {PATH} HTTP/2.0", f"GET {PATH} HTTP/1.9", f"GET /other HTTP/1.1", f"GET /a/../..{PATH} HTTP/1.1", f"GET //~kriz/./cifar-100-python.tar.gz?x=1 HTTP/1.1",
+             f"GET http://{HOST}{PATH} HTTP/1.1", f"GET {PATH} HTTP/1.1 x", f"GET  {PATH}   HTTP/1.1"]
+    names = ["Host", "host", "Range", "If-Range", "If-Match", "If-None-Match", "If-Modified-Since", "If-Unmodified-Since", "Connection", "Content-Length", "X_Bad", "Accept-Encoding"]
+    values = [HOST, HOST.upper() + ":80", "other.example", "a..b", "bytes=0-9", "bytes=5-", "bytes=-0", "bytes=20000-", "bytes=0-1,5-6", aio.etag, '"x"', "*", LM, "junk", "close", "0", "7", "1x", "gzip"]
+    for _ in range(400):
+        rl = rnd.choice(lines)
+        hdrs = [(rnd.choice(names), rnd.choice(values)) for _ in range(rnd.randrange(0, 5))]
+        if rnd.random() < 0.8:
+            hdrs.insert(0, ("Host", HOST))
+        raw = (rl + "\r\n" + "".join(f"{n}: {v}\r\n" for n, v in hdrs)).encode()
+        want = _model_status(raw, known, aio.etag)
+        got = raw_exchange(port, raw + b"\r\n")[0]
+        assert got == want, (raw, got, want)
